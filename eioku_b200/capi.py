@@ -1,0 +1,334 @@
+"""ctypes binding of libesd.so (include/esd.h).  Fails loudly when the CUDA library is
+missing or no GPU is present -- there is no CPU fallback in this package."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libesd.so")
+
+ESD_DET_CONTENT, ESD_DET_ADAPTIVE, ESD_DET_HIST = 1, 2, 4
+ESD_FILTER_MERGE, ESD_FILTER_SUPPRESS = 0, 1
+ESD_DOWNSCALE_FLOAT, ESD_DOWNSCALE_INT = 0, 1
+ESD_SPLIT_AUTO, ESD_SPLIT_STRIPS, ESD_SPLIT_CHUNKS = 0, 1, 2
+
+# every symbol include/esd.h declares (tests check that the library exports all of them)
+EXPORTED_SYMBOLS = (
+    "esd_abi_version", "esd_strerror", "esd_last_error", "esd_device_count", "esd_config_default",
+    "esd_create", "esd_destroy", "esd_reset", "esd_get_geometry", "esd_get_touched_rows",
+    "esd_push_frames", "esd_push_rows", "esd_ingest_open", "esd_ingest_push_host", "esd_ingest_close",
+    "esd_ingest_stats", "esd_synchronize", "esd_frames_pushed", "esd_read_scores", "esd_get_cuts",
+    "esd_decide_arrays", "esd_debug_read_prev", "esd_set_timing", "esd_kernel_time", "esd_kernel_launches", "esd_synth_fill",
+)
+
+
+class EsdConfig(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("detectors", C.c_int32),
+        ("src_width", C.c_int32), ("src_height", C.c_int32),
+        ("dst_width", C.c_int32), ("dst_height", C.c_int32),
+        ("downscale_mode", C.c_int32), ("reserved0", C.c_int32),
+        ("content_threshold", C.c_double), ("content_weights", C.c_double * 4),
+        ("content_weight_div", C.c_double),
+        ("content_min_scene_len", C.c_int32), ("content_filter_mode", C.c_int32),
+        ("adaptive_threshold", C.c_double), ("adaptive_min_content_val", C.c_double),
+        ("adaptive_weights", C.c_double * 4), ("adaptive_weight_div", C.c_double),
+        ("adaptive_window_width", C.c_int32), ("adaptive_min_scene_len", C.c_int32),
+        ("hist_threshold", C.c_double), ("hist_bins", C.c_int32), ("hist_min_scene_len", C.c_int32),
+        ("rows_per_group", C.c_int32), ("pipeline_stages", C.c_int32),
+        ("split_mode", C.c_int32), ("ctas_per_sm", C.c_int32),
+        ("max_cuts", C.c_int64), ("initial_capacity", C.c_int64),
+    ]
+
+
+class EsdGeometry(C.Structure):
+    _fields_ = [
+        ("dst_width", C.c_int32), ("dst_height", C.c_int32),
+        ("n_touched_rows", C.c_int32), ("row_bytes", C.c_int32),
+        ("alg_bytes_per_frame", C.c_int64), ("compact_frame_bytes", C.c_int64),
+    ]
+
+
+class EsdError(RuntimeError):
+    def __init__(self, status: int, what: str, detail: str = ""):
+        self.status = status
+        super().__init__(f"libesd: {what} (status {status}){': ' + detail if detail else ''}")
+
+
+_lib = None
+
+
+def load_library(path: Optional[str] = None):
+    """dlopen libesd.so and declare prototypes.  Raises if the library was not built."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise ImportError(
+            f"{path} not found: build it with `python -m eioku_b200.build` (nvcc, sm_100a). "
+            "eioku_b200 has no CPU fallback.")
+    L = C.CDLL(path)
+    vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
+    L.esd_abi_version.restype = C.c_int
+    L.esd_strerror.restype = C.c_char_p
+    L.esd_strerror.argtypes = [C.c_int]
+    L.esd_last_error.restype = C.c_char_p
+    L.esd_last_error.argtypes = [vp]
+    L.esd_device_count.restype = C.c_int
+    L.esd_config_default.restype = None
+    L.esd_config_default.argtypes = [C.POINTER(EsdConfig)]
+    L.esd_create.argtypes = [C.POINTER(vp), C.POINTER(EsdConfig), C.c_int]
+    L.esd_destroy.restype = None
+    L.esd_destroy.argtypes = [vp]
+    L.esd_reset.argtypes = [vp]
+    L.esd_get_geometry.argtypes = [vp, C.POINTER(EsdGeometry)]
+    L.esd_get_touched_rows.argtypes = [vp, vp, i32]
+    L.esd_push_frames.argtypes = [vp, vp, i64, i64, i64, i64, vp]
+    L.esd_push_rows.argtypes = [vp, vp, i64, i64, vp]
+    L.esd_ingest_open.argtypes = [vp, i32, i32]
+    L.esd_ingest_push_host.argtypes = [vp, vp, i64, i64, i64, i64]
+    L.esd_ingest_close.argtypes = [vp]
+    L.esd_ingest_stats.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
+    L.esd_synchronize.argtypes = [vp]
+    L.esd_frames_pushed.restype = i64
+    L.esd_frames_pushed.argtypes = [vp]
+    L.esd_read_scores.argtypes = [vp, i64, i64, vp, vp, vp, vp, vp, vp]
+    L.esd_get_cuts.argtypes = [vp, i32, i64, vp, i64, C.POINTER(i64), C.POINTER(i64)]
+    L.esd_decide_arrays.argtypes = [vp, i32, i64, i64, vp, vp, vp, i64, C.POINTER(i64)]
+    L.esd_debug_read_prev.argtypes = [vp, vp, i64]
+    L.esd_set_timing.argtypes = [vp, i32]
+    L.esd_kernel_time.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i64)]
+    L.esd_kernel_launches.restype = i64
+    L.esd_kernel_launches.argtypes = [vp]
+    L.esd_synth_fill.argtypes = [vp, i32, i32, i64, i64, C.c_uint32, vp, i64, C.c_int, vp]
+    if L.esd_abi_version() != 1:
+        raise ImportError("libesd.so ABI version mismatch")
+    if path == LIB_PATH:
+        _lib = L
+    return L
+
+
+def default_config() -> EsdConfig:
+    cfg = EsdConfig()
+    load_library().esd_config_default(C.byref(cfg))
+    return cfg
+
+
+def _np_ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class EsdContext:
+    """Owns one esd_ctx (one device, one video stream)."""
+
+    def __init__(self, cfg: EsdConfig, device: int = 0):
+        self._L = load_library()
+        self._h = C.c_void_p()
+        cfg.struct_size = C.sizeof(EsdConfig)
+        rc = self._L.esd_create(C.byref(self._h), C.byref(cfg), int(device))
+        if rc != 0:
+            detail = (self._L.esd_last_error(None) or b"").decode()
+            self._h = C.c_void_p()
+            if rc == -1 and "window_width" in detail:
+                raise ValueError(detail)
+            raise EsdError(rc, "esd_create", detail)
+        self.cfg = cfg
+        self.device = int(device)
+        g = EsdGeometry()
+        self._check(self._L.esd_get_geometry(self._h, C.byref(g)), "esd_get_geometry")
+        self.geometry = g
+
+    # -- plumbing
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            detail = (self._L.esd_last_error(self._h) or b"").decode()
+            raise EsdError(rc, what, detail)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._L.esd_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- geometry
+    @property
+    def dst_size(self):
+        return self.geometry.dst_width, self.geometry.dst_height
+
+    @property
+    def alg_bytes_per_frame(self) -> int:
+        return int(self.geometry.alg_bytes_per_frame)
+
+    def touched_rows(self) -> np.ndarray:
+        rows = np.empty(self.geometry.n_touched_rows, np.int32)
+        self._check(self._L.esd_get_touched_rows(self._h, _np_ptr(rows), rows.size), "esd_get_touched_rows")
+        return rows
+
+    # -- scoring
+    def reset(self):
+        self._check(self._L.esd_reset(self._h), "esd_reset")
+
+    def push_device(self, data_ptr: int, n: int, frame_stride: int, pitch: int, first_frame_num: int, stream: int = 0):
+        self._check(self._L.esd_push_frames(self._h, C.c_void_p(data_ptr), n, frame_stride, pitch, first_frame_num,
+                                            C.c_void_p(stream)), "esd_push_frames")
+
+    def push_tensor(self, frames, first_frame_num: int, stream: Optional[int] = None):
+        """frames: torch.uint8 CUDA tensor [N,H,W,3] (or [H,W,3]); rows must be dense (stride 3,1 on W,C)."""
+        import torch
+
+        if frames.dim() == 3:
+            frames = frames.unsqueeze(0)
+        if frames.dtype != torch.uint8 or not frames.is_cuda:
+            raise ValueError("push_tensor needs a CUDA uint8 tensor")
+        if frames.shape[3] != 3 or frames.stride(3) != 1 or frames.stride(2) != 3:
+            frames = frames.contiguous()
+        if frames.device.index != self.device:
+            raise ValueError(f"tensor on cuda:{frames.device.index}, context on cuda:{self.device}")
+        n, h, w, _ = frames.shape
+        if (w, h) != (self.cfg.src_width, self.cfg.src_height):
+            raise ValueError(f"frame size {w}x{h} != configured {self.cfg.src_width}x{self.cfg.src_height}")
+        if stream is None:
+            stream = torch.cuda.current_stream(frames.device).cuda_stream
+        fs = frames.stride(0) if n > 1 else frames.stride(1) * h
+        self.push_device(frames.data_ptr(), n, fs, frames.stride(1), first_frame_num, stream)
+
+    def push_rows_device(self, data_ptr: int, n: int, first_frame_num: int, stream: int = 0):
+        self._check(self._L.esd_push_rows(self._h, C.c_void_p(data_ptr), n, first_frame_num, C.c_void_p(stream)),
+                    "esd_push_rows")
+
+    # -- ingest ring (host frames)
+    def ingest_open(self, n_slots: int = 3, frames_per_slot: int = 64):
+        self._check(self._L.esd_ingest_open(self._h, n_slots, frames_per_slot), "esd_ingest_open")
+
+    def ingest_push_host(self, data_ptr: int, n: int, frame_stride: int, pitch: int, first_frame_num: int):
+        self._check(self._L.esd_ingest_push_host(self._h, C.c_void_p(data_ptr), n, frame_stride, pitch,
+                                                 first_frame_num), "esd_ingest_push_host")
+
+    def ingest_push_numpy(self, frames: np.ndarray, first_frame_num: int):
+        if frames.ndim == 3:
+            frames = frames[None]
+        if frames.dtype != np.uint8 or frames.shape[3] != 3 or frames.strides[3] != 1 or frames.strides[2] != 3:
+            frames = np.ascontiguousarray(frames, np.uint8)
+        n, h, w, _ = frames.shape
+        if (w, h) != (self.cfg.src_width, self.cfg.src_height):
+            raise ValueError(f"frame size {w}x{h} != configured {self.cfg.src_width}x{self.cfg.src_height}")
+        fs = frames.strides[0] if n > 1 else frames.strides[1] * h
+        self.ingest_push_host(frames.ctypes.data, n, fs, frames.strides[1], first_frame_num)
+
+    def ingest_close(self):
+        self._check(self._L.esd_ingest_close(self._h), "esd_ingest_close")
+
+    def ingest_stats(self):
+        b, c = C.c_int64(), C.c_int64()
+        self._check(self._L.esd_ingest_stats(self._h, C.byref(b), C.byref(c)), "esd_ingest_stats")
+        return int(b.value), int(c.value)
+
+    # -- results
+    def synchronize(self):
+        self._check(self._L.esd_synchronize(self._h), "esd_synchronize")
+
+    @property
+    def frames_pushed(self) -> int:
+        return int(self._L.esd_frames_pushed(self._h))
+
+    def read_scores(self, from_frame: int, n: int, want: Sequence[str] = ()):
+        """-> dict with any of sums3, content_val, adaptive_val, adaptive_ratio, hist, hist_diff."""
+        has_content = bool(self.cfg.detectors & (ESD_DET_CONTENT | ESD_DET_ADAPTIVE))
+        has_hist = bool(self.cfg.detectors & ESD_DET_HIST)
+        if not want:
+            want = (["sums3", "content_val", "adaptive_val", "adaptive_ratio"] if has_content else []) + \
+                   (["hist", "hist_diff"] if has_hist else [])
+        out = {}
+        if "sums3" in want: out["sums3"] = np.empty((n, 3), np.uint64)
+        if "content_val" in want: out["content_val"] = np.empty(n, np.float64)
+        if "adaptive_val" in want: out["adaptive_val"] = np.empty(n, np.float64)
+        if "adaptive_ratio" in want: out["adaptive_ratio"] = np.empty(n, np.float64)
+        if "hist" in want: out["hist"] = np.empty((n, self.cfg.hist_bins), np.uint32)
+        if "hist_diff" in want: out["hist_diff"] = np.empty(n, np.float64)
+        self._check(self._L.esd_read_scores(
+            self._h, from_frame, n, _np_ptr(out.get("sums3")), _np_ptr(out.get("content_val")),
+            _np_ptr(out.get("adaptive_val")), _np_ptr(out.get("adaptive_ratio")), _np_ptr(out.get("hist")),
+            _np_ptr(out.get("hist_diff"))), "esd_read_scores")
+        return out
+
+    def get_cuts(self, detector: int, from_index: int = 0):
+        """-> (list of cut frame numbers from `from_index` on, total cuts emitted)."""
+        cap = 4096
+        while True:
+            buf = np.empty(cap, np.int64)
+            nw, nt = C.c_int64(), C.c_int64()
+            rc = self._L.esd_get_cuts(self._h, detector, from_index, _np_ptr(buf), cap, C.byref(nw), C.byref(nt))
+            if rc == -6 and nt.value - from_index > cap:  # ESD_ERR_CAPACITY: retry with a larger buffer
+                cap = int(nt.value - from_index)
+                continue
+            self._check(rc, "esd_get_cuts")
+            return buf[: nw.value].tolist(), int(nt.value)
+
+    def decide_arrays(self, detector: int, first_frame_num: int, scores: np.ndarray):
+        scores = np.ascontiguousarray(scores, np.float64)
+        n = scores.size
+        ratio = np.empty(n, np.float64)
+        cap = max(16, n)
+        cuts = np.empty(cap, np.int64)
+        nc = C.c_int64()
+        self._check(self._L.esd_decide_arrays(self._h, detector, first_frame_num, n, _np_ptr(scores), _np_ptr(ratio),
+                                              _np_ptr(cuts), cap, C.byref(nc)), "esd_decide_arrays")
+        return cuts[: nc.value].tolist(), ratio
+
+    def debug_last_hsv(self) -> np.ndarray:
+        """uint8 [dst_h, dst_w, 3] HSV of the last pushed frame at detector resolution (test hook)."""
+        w, h = self.dst_size
+        buf = np.empty(w * h, np.uint32)
+        self._check(self._L.esd_debug_read_prev(self._h, _np_ptr(buf), buf.size), "esd_debug_read_prev")
+        out = np.empty((h, w, 3), np.uint8)
+        b = buf.reshape(h, w)
+        out[..., 0] = b & 255
+        out[..., 1] = (b >> 8) & 255
+        out[..., 2] = (b >> 16) & 255
+        return out
+
+    # -- instrumentation
+    def set_timing(self, enable: bool = True):
+        self._check(self._L.esd_set_timing(self._h, 1 if enable else 0), "esd_set_timing")
+
+    def kernel_time(self):
+        ms, n = C.c_double(), C.c_int64()
+        self._check(self._L.esd_kernel_time(self._h, C.byref(ms), C.byref(n)), "esd_kernel_time")
+        return float(ms.value), int(n.value)
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(self._L.esd_kernel_launches(self._h))
+
+
+def synth_fill(out_tensor, seed: int, descs: np.ndarray):
+    """Fill a CUDA uint8 tensor [N,H,W,3] with the synthetic clip frames described by `descs` (int32 [N,8])."""
+    import torch
+
+    L = load_library()
+    descs = np.ascontiguousarray(descs, np.int32)
+    n, h, w, _ = out_tensor.shape
+    assert out_tensor.is_cuda and out_tensor.dtype == torch.uint8 and out_tensor.is_contiguous()
+    assert descs.shape == (n, 8)
+    stream = torch.cuda.current_stream(out_tensor.device).cuda_stream
+    rc = L.esd_synth_fill(C.c_void_p(out_tensor.data_ptr()), w, h, out_tensor.stride(1), out_tensor.stride(0),
+                          seed & 0xFFFFFFFF, _np_ptr(descs), n, out_tensor.device.index, C.c_void_p(stream))
+    if rc != 0:
+        raise EsdError(rc, "esd_synth_fill", (L.esd_last_error(None) or b"").decode())
+    return out_tensor

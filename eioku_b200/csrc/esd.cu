@@ -1,0 +1,1021 @@
+// esd.cu -- host side of libesd.so: the C ABI declared in include/esd.h.
+//
+// Replaces the scoring loop that /root/reference's scene task is specified to run
+// (ModelManager.detect_scenes, ml-service/src/services/model_manager.py:715-835 ->
+// PySceneDetect SceneManager/ContentDetector/AdaptiveDetector/HistogramDetector).
+// No CPU fallback: every entry point needs a CUDA device.
+#include "../../include/esd.h"
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "esd_kernels.cuh"
+#include "synth_core.h"
+
+using namespace esd;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct UnitPlan {
+    Unit* d_units = nullptr;
+    int* d_begin = nullptr;
+    int grid = 0;
+    int n_units = 0;
+};
+
+struct IngestSlot {
+    uint8_t* h_pinned = nullptr;
+    uint8_t* d_rows = nullptr;
+    cudaEvent_t copied = nullptr;
+    cudaEvent_t consumed = nullptr;
+    bool in_flight = false;
+};
+
+}  // namespace
+
+struct esd_ctx {
+    esd_config cfg;
+    int device = 0;
+    int num_sms = 0;
+    std::string err;
+
+    // geometry
+    int dst_w = 0, dst_h = 0, row_bytes = 0;
+    bool resize = false;
+    int pxt = 1;
+    int rows_per_group = 0, n_groups = 0, stages = 0, rowbuf = 0, stage_bytes = 0;
+    int ctas_per_sm = 0;
+    size_t smem_bytes = 0;
+    bool need_content = false, need_hist = false;
+    std::vector<int32_t> touched;  // ascending source rows
+    ScoreWeights wc{}, wa{};
+    DecisionParams dparams{};
+
+    // device tables
+    YRow* d_yrows = nullptr;
+    uint2* d_xtab = nullptr;
+    int* d_sdiv = nullptr;
+    int* d_hdiv = nullptr;
+
+    // per-video state
+    int64_t first_frame = 0;
+    int64_t n_frames = 0;
+    bool started = false;
+    int prev_parity = 0;
+    uint32_t* d_prev[2] = {nullptr, nullptr};
+    DecisionState* d_state = nullptr;
+    long long* d_cuts = nullptr;  // [3][max_cuts]
+    int64_t max_cuts = 0;
+
+    // growable per-frame score arrays
+    int64_t cap = 0;
+    unsigned long long* d_sums3 = nullptr;
+    double* d_cv = nullptr;
+    double* d_av = nullptr;
+    double* d_ratio = nullptr;
+    double* d_hdiff = nullptr;
+    uint32_t* d_counts = nullptr;  // [cap][bins]
+
+    // per-batch scratch
+    int64_t part_cap_frames = 0;
+    uint4* d_part = nullptr;
+    uint16_t* d_hist_part = nullptr;
+    std::map<int64_t, UnitPlan> plans;
+
+    // streams / timing
+    cudaStream_t last_stream = nullptr;
+    bool have_last_stream = false;
+    cudaEvent_t order_event = nullptr;
+    bool timing = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing_events;
+    int64_t launches = 0;
+
+    // ingest
+    std::vector<IngestSlot> ring;
+    int frames_per_slot = 0;
+    int next_slot = 0;
+    cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
+    int64_t h2d_bytes = 0, h2d_copies = 0;
+};
+
+namespace {
+
+int fail(esd_ctx* c, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf;
+    else g_create_error = buf;
+    return code;
+}
+
+#define CU(c, call)                                                                                   \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess)                                                                        \
+            return fail((c), ESD_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, \
+                        __LINE__);                                                                    \
+    } while (0)
+
+// OpenCV resize.cpp INTER_LINEAR coefficient setup: float32 fraction from a double
+// scale, cvRound (half-even) to 11-bit fixed point.
+void axis_tables(int src, int dst, std::vector<int>& o0, std::vector<int>& o1, std::vector<int>& c0,
+                 std::vector<int>& c1) {
+    o0.resize(dst); o1.resize(dst); c0.resize(dst); c1.resize(dst);
+    const double inv_scale = (double)dst / (double)src;
+    const double scale = 1.0 / inv_scale;
+    for (int d = 0; d < dst; ++d) {
+        volatile double pos = (d + 0.5) * scale;  // volatile: no FMA contraction / excess precision
+        pos = pos - 0.5;
+        float f = (float)pos;
+        int s = (int)floorf(f);
+        f -= (float)s;
+        if (s < 0) { s = 0; f = 0.f; }
+        if (s >= src - 1) { s = src - 1; f = 0.f; }
+        o0[d] = s;
+        o1[d] = std::min(s + 1, src - 1);
+        volatile float w0 = (1.f - f) * 2048.f, w1 = f * 2048.f;
+        c0[d] = (int)lrintf(w0);
+        c1[d] = (int)lrintf(w1);
+    }
+}
+
+int64_t gcd64(int64_t a, int64_t b) { while (b) { int64_t t = a % b; a = b; b = t; } return a; }
+
+// Python round(): half to even on the double quotient
+long py_round(double x) { return lrint(x); }
+
+template <bool RESIZE, int PXT>
+cudaError_t launch_fused_rp(bool content, bool hist, const FusedParams& p, int grid, size_t smem, cudaStream_t st) {
+#define ESD_LAUNCH(C, H)                                                                                         \
+    do {                                                                                                         \
+        auto k = fused_score_kernel<RESIZE, PXT, C, H>;                                                          \
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
+        if (e != cudaSuccess) return e;                                                                          \
+        k<<<grid, kThreads, smem, st>>>(p);                                                                      \
+        return cudaGetLastError();                                                                               \
+    } while (0)
+    if (content && hist) ESD_LAUNCH(true, true);
+    if (content) ESD_LAUNCH(true, false);
+    ESD_LAUNCH(false, true);
+#undef ESD_LAUNCH
+    return cudaErrorUnknown;
+}
+
+template <bool RESIZE, int PXT>
+cudaError_t occupancy_rp(bool content, bool hist, size_t smem, int* out) {
+#define ESD_OCC(C, H)                                                                                            \
+    do {                                                                                                         \
+        auto k = fused_score_kernel<RESIZE, PXT, C, H>;                                                          \
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
+        if (e != cudaSuccess) return e;                                                                          \
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, k, kThreads, smem);                            \
+    } while (0)
+    if (content && hist) ESD_OCC(true, true);
+    if (content) ESD_OCC(true, false);
+    ESD_OCC(false, true);
+#undef ESD_OCC
+    return cudaErrorUnknown;
+}
+
+#define ESD_DISPATCH(FN, resize, pxt, ...)                                           \
+    ((resize) ? ((pxt) == 1 ? FN<true, 1>(__VA_ARGS__)                               \
+                 : (pxt) == 2 ? FN<true, 2>(__VA_ARGS__)                             \
+                              : FN<true, 4>(__VA_ARGS__))                            \
+              : ((pxt) == 1 ? FN<false, 1>(__VA_ARGS__)                              \
+                 : (pxt) == 2 ? FN<false, 2>(__VA_ARGS__)                            \
+                 : (pxt) == 4 ? FN<false, 4>(__VA_ARGS__)                            \
+                 : (pxt) == 8 ? FN<false, 8>(__VA_ARGS__)                            \
+                              : FN<false, 16>(__VA_ARGS__)))
+
+size_t fused_smem_bytes(const esd_ctx* c, int R, int stages) {
+    size_t off = 4416;  // barriers + meta + sdiv/hdiv + hist (see kernel carve-up)
+    if (c->need_content) off += (size_t)R * c->pxt * kConsumers * 4;
+    off = (off + 127) & ~(size_t)127;
+    return off + (size_t)stages * c->stage_bytes;
+}
+
+void free_plans(esd_ctx* c) {
+    for (auto& kv : c->plans) {
+        cudaFree(kv.second.d_units);
+        cudaFree(kv.second.d_begin);
+    }
+    c->plans.clear();
+}
+
+// Work decomposition.  A unit is (row group, frame range); units that do not start at frame 0
+// re-read one halo frame to rebuild the previous HSV, so fewer/longer units are cheaper.
+int build_plan(esd_ctx* c, int64_t n, UnitPlan* out) {
+    const int G = c->n_groups;
+    const int64_t total = (int64_t)G * n;  // (group, frame) items
+    int grid = (int)std::min<int64_t>((int64_t)c->num_sms * c->ctas_per_sm, total);
+    std::vector<Unit> units;
+    std::vector<int> begin(grid + 1, 0);
+    int mode = c->cfg.split_mode ? c->cfg.split_mode : ESD_SPLIT_STRIPS;
+    if (mode == ESD_SPLIT_STRIPS) {
+        // contiguous strips of the (group-major, frame-minor) item sequence, one per CTA
+        for (int g = 0; g < grid; ++g) {
+            int64_t lo = total * g / grid, hi = total * (g + 1) / grid;
+            begin[g] = (int)units.size();
+            while (lo < hi) {
+                const int rg = (int)(lo / n);
+                const int64_t f0 = lo % n;
+                const int64_t f1 = std::min<int64_t>(n, f0 + (hi - lo));
+                units.push_back(Unit{rg, (int)f0, (int)f1, 0});
+                lo += f1 - f0;
+            }
+        }
+        begin[grid] = (int)units.size();
+    } else {
+        // frame chunks shared by all row groups; consecutive CTAs work on the same frames
+        int64_t n_chunks = std::max<int64_t>(1, ((int64_t)grid * 4 + G - 1) / G);
+        n_chunks = std::min<int64_t>(n_chunks, std::max<int64_t>(1, n / 16));
+        // make the unit count a multiple of the grid when possible
+        const int64_t per = grid / gcd64(grid, G);
+        if (n_chunks >= per) n_chunks = n_chunks / per * per;
+        std::vector<Unit> all;
+        for (int64_t ch = 0; ch < n_chunks; ++ch)
+            for (int rg = 0; rg < G; ++rg)
+                all.push_back(Unit{rg, (int)(n * ch / n_chunks), (int)(n * (ch + 1) / n_chunks), 0});
+        grid = (int)std::min<int64_t>(grid, (int64_t)all.size());
+        begin.assign(grid + 1, 0);
+        for (int g = 0; g < grid; ++g) {
+            begin[g] = (int)units.size();
+            for (size_t u = g; u < all.size(); u += grid) units.push_back(all[u]);
+        }
+        begin[grid] = (int)units.size();
+    }
+    out->grid = grid;
+    out->n_units = (int)units.size();
+    CU(c, cudaMalloc(&out->d_units, sizeof(Unit) * std::max<size_t>(1, units.size())));
+    CU(c, cudaMalloc(&out->d_begin, sizeof(int) * begin.size()));
+    CU(c, cudaMemcpy(out->d_units, units.data(), sizeof(Unit) * units.size(), cudaMemcpyHostToDevice));
+    CU(c, cudaMemcpy(out->d_begin, begin.data(), sizeof(int) * begin.size(), cudaMemcpyHostToDevice));
+    return ESD_OK;
+}
+
+template <typename T>
+int grow_array(esd_ctx* c, T** p, int64_t old_elems, int64_t new_elems) {
+    T* q = nullptr;
+    CU(c, cudaMalloc(&q, sizeof(T) * new_elems));
+    if (*p && old_elems) CU(c, cudaMemcpy(q, *p, sizeof(T) * old_elems, cudaMemcpyDeviceToDevice));
+    cudaFree(*p);
+    *p = q;
+    return ESD_OK;
+}
+
+int ensure_capacity(esd_ctx* c, int64_t frames_needed) {
+    if (frames_needed <= c->cap) return ESD_OK;
+    int64_t ncap = std::max<int64_t>(c->cap ? c->cap * 2 : std::max<int64_t>(4096, c->cfg.initial_capacity), frames_needed);
+    if (c->have_last_stream) CU(c, cudaStreamSynchronize(c->last_stream));
+    int rc;
+    const int64_t used = c->n_frames;
+    if ((rc = grow_array(c, &c->d_sums3, used * 3, ncap * 3))) return rc;
+    if ((rc = grow_array(c, &c->d_cv, used, ncap))) return rc;
+    if ((rc = grow_array(c, &c->d_av, used, ncap))) return rc;
+    if ((rc = grow_array(c, &c->d_ratio, used, ncap))) return rc;
+    if ((rc = grow_array(c, &c->d_hdiff, used, ncap))) return rc;
+    if (c->need_hist)
+        if ((rc = grow_array(c, &c->d_counts, used * c->cfg.hist_bins, ncap * c->cfg.hist_bins))) return rc;
+    // ratios not yet computed read back as NaN
+    fill_nan_kernel<<<(unsigned)((ncap - used + 255) / 256), 256>>>(c->d_ratio + used, ncap - used);
+    CU(c, cudaGetLastError());
+    CU(c, cudaDeviceSynchronize());
+    c->cap = ncap;
+    return ESD_OK;
+}
+
+int ensure_scratch(esd_ctx* c, int64_t n) {
+    if (n <= c->part_cap_frames) return ESD_OK;
+    if (c->have_last_stream) CU(c, cudaStreamSynchronize(c->last_stream));
+    cudaFree(c->d_part);
+    cudaFree(c->d_hist_part);
+    c->d_part = nullptr;
+    c->d_hist_part = nullptr;
+    c->part_cap_frames = 0;
+    if (c->need_content) CU(c, cudaMalloc(&c->d_part, sizeof(uint4) * n * c->n_groups * kConsumerWarps));
+    if (c->need_hist) CU(c, cudaMalloc(&c->d_hist_part, sizeof(uint16_t) * n * c->n_groups * c->cfg.hist_bins));
+    c->part_cap_frames = n;
+    return ESD_OK;
+}
+
+int reset_video_state(esd_ctx* c) {
+    c->first_frame = 0;
+    c->n_frames = 0;
+    c->started = false;
+    c->prev_parity = 0;
+    c->h2d_bytes = 0;
+    c->h2d_copies = 0;
+    CU(c, cudaMemset(c->d_state, 0, sizeof(DecisionState)));
+    if (c->cap) {
+        fill_nan_kernel<<<(unsigned)((c->cap + 255) / 256), 256>>>(c->d_ratio, c->cap);
+        CU(c, cudaGetLastError());
+    }
+    CU(c, cudaDeviceSynchronize());
+    return ESD_OK;
+}
+
+// make `st` wait for everything previously enqueued for this ctx on another stream
+int order_after_last(esd_ctx* c, cudaStream_t st) {
+    if (c->have_last_stream && c->last_stream != st) {
+        CU(c, cudaEventRecord(c->order_event, c->last_stream));
+        CU(c, cudaStreamWaitEvent(st, c->order_event, 0));
+    }
+    c->last_stream = st;
+    c->have_last_stream = true;
+    return ESD_OK;
+}
+
+int push_common(esd_ctx* c, const uint8_t* d_src, int64_t n, int64_t frame_stride, int64_t row_stride, bool compact,
+                int64_t first_frame_num, cudaStream_t st) {
+    if (!d_src || n <= 0) return fail(c, ESD_ERR_INVALID, "push: null frames or n <= 0");
+    if (n > 0x7fffff00LL / std::max(1, c->n_groups)) return fail(c, ESD_ERR_INVALID, "push: batch too large (%lld frames)", (long long)n);
+    CU(c, cudaSetDevice(c->device));
+    if (!c->started) {
+        c->first_frame = first_frame_num;
+        c->started = true;
+    } else if (first_frame_num != c->first_frame + c->n_frames) {
+        return fail(c, ESD_ERR_STATE, "push: frame numbers must be sequential (expected %lld, got %lld)",
+                    (long long)(c->first_frame + c->n_frames), (long long)first_frame_num);
+    }
+    int rc;
+    if ((rc = ensure_capacity(c, c->n_frames + n))) return rc;
+    if ((rc = ensure_scratch(c, n))) return rc;
+    auto it = c->plans.find(n);
+    if (it == c->plans.end()) {
+        if (c->plans.size() > 64) free_plans(c);
+        UnitPlan pl;
+        if ((rc = build_plan(c, n, &pl))) return rc;
+        it = c->plans.emplace(n, pl).first;
+    }
+    const UnitPlan& plan = it->second;
+    if ((rc = order_after_last(c, st))) return rc;
+
+    const int64_t base = c->n_frames;  // index of the batch's first frame
+    FusedParams p{};
+    p.src = d_src;
+    p.frame_stride = frame_stride;
+    p.row_stride = row_stride;
+    p.compact = compact ? 1 : 0;
+    p.n_frames = (int)n;
+    p.dst_w = c->dst_w;
+    p.dst_h = c->dst_h;
+    p.row_bytes = c->row_bytes;
+    p.rows_per_group = c->rows_per_group;
+    p.n_groups = c->n_groups;
+    p.stages = c->stages;
+    p.rowbuf = c->rowbuf;
+    p.has_prev = base > 0 ? 1 : 0;
+    p.bins = c->cfg.hist_bins;
+    p.yrows = c->d_yrows;
+    p.xtab = c->d_xtab;
+    p.sdiv = c->d_sdiv;
+    p.hdiv = c->d_hdiv;
+    p.units = plan.d_units;
+    p.cta_unit_begin = plan.d_begin;
+    p.prev_in = c->d_prev[c->prev_parity];
+    p.prev_out = c->d_prev[c->prev_parity ^ 1];
+    p.part = c->d_part;
+    p.hist_part = c->d_hist_part;
+
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (c->timing) {
+        CU(c, cudaEventCreate(&e0));
+        CU(c, cudaEventCreate(&e1));
+        CU(c, cudaEventRecord(e0, st));
+    }
+    CU(c, ESD_DISPATCH(launch_fused_rp, c->resize, c->pxt, c->need_content, c->need_hist, p, plan.grid, c->smem_bytes, st));
+    c->launches++;
+    if (c->timing) {
+        CU(c, cudaEventRecord(e1, st));
+        c->timing_events.emplace_back(e0, e1);
+    }
+    c->prev_parity ^= 1;
+
+    const double npx = (double)c->dst_w * (double)c->dst_h;  // float(rows * cols)
+    if (c->need_content) {
+        const int warps_per_block = 8;
+        finalize_sums_kernel<<<(unsigned)((n + warps_per_block - 1) / warps_per_block), warps_per_block * 32, 0, st>>>(
+            c->d_part, (int)n, c->n_groups * kConsumerWarps, npx, c->wc, c->wa, c->d_sums3 + 3 * base, c->d_cv + base,
+            c->d_av + base);
+        CU(c, cudaGetLastError());
+        c->launches++;
+        if (c->cfg.detectors & ESD_DET_ADAPTIVE) {
+            const int w = c->cfg.adaptive_window_width;
+            const int64_t t0 = std::max<int64_t>(w, base - w), t1 = base + n - w;
+            if (t1 > t0) {
+                adaptive_ratio_kernel<<<(unsigned)((t1 - t0 + 255) / 256), 256, 0, st>>>(
+                    c->d_av, c->d_ratio, t0, t1, w, c->cfg.adaptive_min_content_val);
+                CU(c, cudaGetLastError());
+                c->launches++;
+            }
+        }
+    }
+    if (c->need_hist) {
+        const int bins = c->cfg.hist_bins;
+        finalize_hist_counts_kernel<<<(unsigned)n, 256, 0, st>>>(c->d_hist_part, c->n_groups, bins,
+                                                                 c->d_counts + base * bins);
+        CU(c, cudaGetLastError());
+        hist_diff_kernel<<<(unsigned)n, 256, 0, st>>>(c->d_counts + base * bins, bins, base > 0 ? 1 : 0,
+                                                      c->d_hdiff + base);
+        CU(c, cudaGetLastError());
+        c->launches += 2;
+    }
+    decide_kernel<<<3, 256, 0, st>>>(c->dparams, c->d_state, c->d_cuts, c->d_cv, c->d_av, c->d_ratio, c->d_hdiff,
+                                     c->first_frame, base, base + n);
+    CU(c, cudaGetLastError());
+    c->launches++;
+    c->n_frames += n;
+    return ESD_OK;
+}
+
+__global__ void synth_fill_kernel(uint8_t* out, int W, int H, long long pitch, long long frame_stride, uint32_t seed,
+                                  const syn_frame_desc* __restrict__ descs, long long n) {
+    const long long px = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long per = (long long)W * H;
+    if (px >= per * n) return;
+    const long long f = px / per;
+    const int rem = (int)(px - f * per);
+    const int y = rem / W, x = rem - y * W;
+    const syn_frame_desc d = descs[f];
+    uint8_t* o = out + f * frame_stride + (long long)y * pitch + 3LL * x;
+    o[0] = (uint8_t)syn_pixel(seed, &d, x, y, 0, W, H);
+    o[1] = (uint8_t)syn_pixel(seed, &d, x, y, 1, W, H);
+    o[2] = (uint8_t)syn_pixel(seed, &d, x, y, 2, W, H);
+}
+
+}  // namespace
+
+// ======================================================================================= C ABI
+extern "C" {
+
+int esd_abi_version(void) { return ESD_ABI_VERSION; }
+
+const char* esd_strerror(int s) {
+    switch (s) {
+        case ESD_OK: return "ok";
+        case ESD_ERR_INVALID: return "invalid argument";
+        case ESD_ERR_CUDA: return "CUDA error";
+        case ESD_ERR_NOMEM: return "out of memory";
+        case ESD_ERR_STATE: return "call out of order";
+        case ESD_ERR_UNSUPPORTED: return "unsupported configuration";
+        case ESD_ERR_CAPACITY: return "buffer too small";
+        default: return "unknown status";
+    }
+}
+
+const char* esd_last_error(const esd_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int esd_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+void esd_config_default(esd_config* cfg) {
+    memset(cfg, 0, sizeof *cfg);
+    cfg->struct_size = sizeof *cfg;
+    cfg->detectors = ESD_DET_CONTENT;
+    cfg->content_threshold = 27.0;
+    cfg->content_weights[0] = cfg->content_weights[1] = cfg->content_weights[2] = 1.0;
+    cfg->content_weight_div = 3.0;
+    cfg->content_min_scene_len = 15;
+    cfg->content_filter_mode = ESD_FILTER_MERGE;
+    cfg->adaptive_threshold = 3.0;
+    cfg->adaptive_min_content_val = 15.0;
+    cfg->adaptive_weights[0] = cfg->adaptive_weights[1] = cfg->adaptive_weights[2] = 1.0;
+    cfg->adaptive_weight_div = 3.0;
+    cfg->adaptive_window_width = 2;
+    cfg->adaptive_min_scene_len = 15;
+    cfg->hist_threshold = 0.05;
+    cfg->hist_bins = 256;
+    cfg->hist_min_scene_len = 15;
+}
+
+int esd_create(esd_ctx** out, const esd_config* cfg, int device) {
+    if (!out || !cfg) return fail(nullptr, ESD_ERR_INVALID, "esd_create: null argument");
+    *out = nullptr;
+    if (cfg->struct_size != sizeof(esd_config))
+        return fail(nullptr, ESD_ERR_INVALID, "esd_create: struct_size %u != %zu (ABI mismatch)", cfg->struct_size,
+                    sizeof(esd_config));
+    if (!(cfg->detectors & 7) || (cfg->detectors & ~7)) return fail(nullptr, ESD_ERR_INVALID, "esd_create: bad detector mask");
+    if (cfg->src_width < 1 || cfg->src_height < 1) return fail(nullptr, ESD_ERR_INVALID, "esd_create: bad frame size");
+    if (cfg->content_weights[3] != 0.0 || cfg->adaptive_weights[3] != 0.0)
+        return fail(nullptr, ESD_ERR_UNSUPPORTED, "delta_edges weight must be 0 (Canny/dilate is outside the hot path)");
+    if ((cfg->detectors & ESD_DET_HIST) && (cfg->hist_bins < 1 || cfg->hist_bins > 256))
+        return fail(nullptr, ESD_ERR_UNSUPPORTED, "hist_bins must be in 1..256");
+    if ((cfg->detectors & ESD_DET_ADAPTIVE) && cfg->adaptive_window_width < 1)
+        return fail(nullptr, ESD_ERR_INVALID, "window_width must be at least 1.");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        cudaGetLastError();
+        return fail(nullptr, ESD_ERR_CUDA, "no CUDA device available (libesd has no CPU fallback)");
+    }
+    if (device < 0 || device >= ndev) return fail(nullptr, ESD_ERR_INVALID, "esd_create: device %d out of range", device);
+
+    esd_ctx* c = new esd_ctx();
+    c->cfg = *cfg;
+    c->device = device;
+    auto bail = [&](int rc) {
+        g_create_error = c->err;
+        esd_destroy(c);
+        return rc;
+    };
+#define CUB(call)                                                                                      \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess) {                                                                       \
+            fail(c, ESD_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_));                     \
+            return bail(ESD_ERR_CUDA);                                                                 \
+        }                                                                                              \
+    } while (0)
+    CUB(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUB(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 9) {
+        fail(c, ESD_ERR_UNSUPPORTED, "device sm_%d%d lacks cp.async.bulk; libesd targets sm_100a", prop.major, prop.minor);
+        return bail(ESD_ERR_UNSUPPORTED);
+    }
+    c->num_sms = prop.multiProcessorCount;
+
+    // ---- geometry: SceneManager auto-downscale target
+    const int W = cfg->src_width, H = cfg->src_height;
+    int dw = cfg->dst_width, dh = cfg->dst_height;
+    if (dw <= 0 || dh <= 0) {
+        dw = W; dh = H;
+        if (W >= 256) {
+            if (cfg->downscale_mode == ESD_DOWNSCALE_INT) {
+                const int f = W / 256;
+                if (f > 1) { dw = (int)std::max(1L, py_round((double)W / f)); dh = (int)std::max(1L, py_round((double)H / f)); }
+            } else {
+                const double f = W / 256.0;
+                if (f > 1.0) { dw = (int)std::max(1L, py_round(W / f)); dh = (int)std::max(1L, py_round(H / f)); }
+            }
+        }
+    }
+    c->dst_w = dw; c->dst_h = dh;
+    c->resize = !(dw == W && dh == H);
+    c->row_bytes = W * 3;
+    c->need_content = (cfg->detectors & (ESD_DET_CONTENT | ESD_DET_ADAPTIVE)) != 0;
+    c->need_hist = (cfg->detectors & ESD_DET_HIST) != 0;
+    if (dw > kConsumers * (c->resize ? 4 : 16)) {
+        fail(c, ESD_ERR_UNSUPPORTED, "destination width %d too large (max %d)", dw, kConsumers * (c->resize ? 4 : 16));
+        return bail(ESD_ERR_UNSUPPORTED);
+    }
+    int pxt = (dw + kConsumers - 1) / kConsumers;
+    c->pxt = pxt <= 1 ? 1 : pxt <= 2 ? 2 : pxt <= 4 ? 4 : pxt <= 8 ? 8 : 16;
+
+    std::vector<int> xo0, xo1, xa0, xa1, yo0, yo1, yb0, yb1;
+    if (c->resize) {
+        axis_tables(W, dw, xo0, xo1, xa0, xa1);
+        axis_tables(H, dh, yo0, yo1, yb0, yb1);
+    } else {
+        yo0.resize(dh); yo1.resize(dh); yb0.assign(dh, 2048); yb1.assign(dh, 0);
+        for (int y = 0; y < dh; ++y) yo0[y] = yo1[y] = y;
+    }
+    {  // touched rows and compact indices
+        std::vector<char> used(H, 0);
+        for (int y = 0; y < dh; ++y) { used[yo0[y]] = 1; if (c->resize) used[yo1[y]] = 1; }
+        std::vector<int> cidx(H, -1);
+        for (int r = 0; r < H; ++r)
+            if (used[r]) { cidx[r] = (int)c->touched.size(); c->touched.push_back(r); }
+        std::vector<YRow> yr(dh);
+        for (int y = 0; y < dh; ++y) {
+            yr[y].row0 = yo0[y]; yr[y].row1 = yo1[y];
+            yr[y].crow0 = cidx[yo0[y]]; yr[y].crow1 = c->resize ? cidx[yo1[y]] : cidx[yo0[y]];
+            yr[y].b0s = (uint32_t)yb0[y] << 16; yr[y].b1s = (uint32_t)yb1[y] << 16;
+            yr[y].pad0 = yr[y].pad1 = 0;
+        }
+        CUB(cudaMalloc(&c->d_yrows, sizeof(YRow) * dh));
+        CUB(cudaMemcpy(c->d_yrows, yr.data(), sizeof(YRow) * dh, cudaMemcpyHostToDevice));
+    }
+    {
+        std::vector<uint2> xt(dw);
+        for (int x = 0; x < dw; ++x) {
+            if (c->resize) { xt[x].x = (uint32_t)(3 * xo0[x]); xt[x].y = (uint32_t)xa0[x] | ((uint32_t)xa1[x] << 16); }
+            else { xt[x].x = (uint32_t)(3 * x); xt[x].y = 2048u; }
+        }
+        CUB(cudaMalloc(&c->d_xtab, sizeof(uint2) * dw));
+        CUB(cudaMemcpy(c->d_xtab, xt.data(), sizeof(uint2) * dw, cudaMemcpyHostToDevice));
+    }
+    {  // OpenCV RGB2HSV_b tables (A.3)
+        int sdiv[256], hdiv[256];
+        sdiv[0] = hdiv[0] = 0;
+        for (int i = 1; i < 256; ++i) {
+            sdiv[i] = (int)lrint((255 << 12) / (1. * i));
+            hdiv[i] = (int)lrint((180 << 12) / (6. * i));
+        }
+        CUB(cudaMalloc(&c->d_sdiv, sizeof sdiv));
+        CUB(cudaMalloc(&c->d_hdiv, sizeof hdiv));
+        CUB(cudaMemcpy(c->d_sdiv, sdiv, sizeof sdiv, cudaMemcpyHostToDevice));
+        CUB(cudaMemcpy(c->d_hdiv, hdiv, sizeof hdiv, cudaMemcpyHostToDevice));
+    }
+
+    // ---- kernel shape
+    c->rowbuf = ((c->row_bytes + 15 + 15) & ~15) + 16;
+    c->stage_bytes = (c->resize ? 2 : 1) * c->rowbuf;
+    int R = cfg->rows_per_group > 0 ? cfg->rows_per_group : 4;
+    R = std::min(R, dh);
+    R = std::min(R, 255);
+    while (R > 1 && ((int64_t)R * c->pxt > 256 || (int64_t)R * dw > 65535)) --R;
+    c->rows_per_group = R;
+    c->n_groups = (dh + R - 1) / R;
+    int stages = cfg->pipeline_stages > 0 ? std::min(cfg->pipeline_stages, kMaxStages) : 4;
+    const size_t smem_limit = prop.sharedMemPerBlockOptin;
+    while (stages > 2 && fused_smem_bytes(c, R, stages) > smem_limit) --stages;
+    c->stages = stages;
+    c->smem_bytes = fused_smem_bytes(c, R, stages);
+    if (c->smem_bytes > smem_limit) {
+        fail(c, ESD_ERR_UNSUPPORTED, "frame rows too wide for shared memory staging (%zu > %zu bytes)", c->smem_bytes, smem_limit);
+        return bail(ESD_ERR_UNSUPPORTED);
+    }
+    int occ = 0;
+    CUB(ESD_DISPATCH(occupancy_rp, c->resize, c->pxt, c->need_content, c->need_hist, c->smem_bytes, &occ));
+    if (occ < 1) {
+        fail(c, ESD_ERR_UNSUPPORTED, "fused kernel does not fit on an SM (smem %zu)", c->smem_bytes);
+        return bail(ESD_ERR_UNSUPPORTED);
+    }
+    c->ctas_per_sm = cfg->ctas_per_sm > 0 ? std::min(cfg->ctas_per_sm, occ) : occ;
+
+    // ---- scoring / decision parameters
+    auto weights = [](const double* w, double div, ScoreWeights* o) {
+        for (int i = 0; i < 4; ++i) o->w[i] = w[i];
+        if (div > 0) o->div = div;
+        else o->div = ((fabs(w[0]) + fabs(w[1])) + fabs(w[2])) + fabs(w[3]);
+    };
+    weights(cfg->content_weights, cfg->content_weight_div, &c->wc);
+    weights(cfg->adaptive_weights, cfg->adaptive_weight_div, &c->wa);
+    c->max_cuts = cfg->max_cuts > 0 ? cfg->max_cuts : 65536;
+    DecisionParams& P = c->dparams;
+    P.detectors = cfg->detectors;
+    P.content_min_scene_len = cfg->content_min_scene_len;
+    P.content_filter_mode = cfg->content_filter_mode;
+    P.adaptive_w = cfg->adaptive_window_width;
+    P.adaptive_min_scene_len = cfg->adaptive_min_scene_len;
+    P.hist_min_scene_len = cfg->hist_min_scene_len;
+    P.content_threshold = cfg->content_threshold;
+    P.adaptive_threshold = cfg->adaptive_threshold;
+    P.adaptive_min_content_val = cfg->adaptive_min_content_val;
+    P.hist_threshold = std::max(0.0, std::min(1.0, 1.0 - cfg->hist_threshold));
+    P.max_cuts = c->max_cuts;
+
+    CUB(cudaMalloc(&c->d_state, sizeof(DecisionState)));
+    CUB(cudaMalloc(&c->d_cuts, sizeof(long long) * 3 * c->max_cuts));
+    if (c->need_content) {
+        CUB(cudaMalloc(&c->d_prev[0], sizeof(uint32_t) * dw * dh));
+        CUB(cudaMalloc(&c->d_prev[1], sizeof(uint32_t) * dw * dh));
+    }
+    CUB(cudaEventCreateWithFlags(&c->order_event, cudaEventDisableTiming));
+    if (reset_video_state(c) != ESD_OK) return bail(ESD_ERR_CUDA);
+#undef CUB
+    *out = c;
+    return ESD_OK;
+}
+
+void esd_destroy(esd_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    esd_ingest_close(c);
+    free_plans(c);
+    for (auto& ev : c->timing_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+    cudaFree(c->d_yrows); cudaFree(c->d_xtab); cudaFree(c->d_sdiv); cudaFree(c->d_hdiv);
+    cudaFree(c->d_prev[0]); cudaFree(c->d_prev[1]); cudaFree(c->d_state); cudaFree(c->d_cuts);
+    cudaFree(c->d_sums3); cudaFree(c->d_cv); cudaFree(c->d_av); cudaFree(c->d_ratio); cudaFree(c->d_hdiff);
+    cudaFree(c->d_counts); cudaFree(c->d_part); cudaFree(c->d_hist_part);
+    if (c->order_event) cudaEventDestroy(c->order_event);
+    cudaGetLastError();
+    delete c;
+}
+
+int esd_reset(esd_ctx* c) {
+    if (!c) return ESD_ERR_INVALID;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaDeviceSynchronize());
+    return reset_video_state(c);
+}
+
+int esd_get_geometry(const esd_ctx* c, esd_geometry* g) {
+    if (!c || !g) return ESD_ERR_INVALID;
+    g->dst_width = c->dst_w;
+    g->dst_height = c->dst_h;
+    g->n_touched_rows = (int32_t)c->touched.size();
+    g->row_bytes = c->row_bytes;
+    g->alg_bytes_per_frame = (int64_t)c->touched.size() * c->row_bytes;
+    g->compact_frame_bytes = (int64_t)c->touched.size() * c->row_bytes;
+    return ESD_OK;
+}
+
+int esd_get_touched_rows(const esd_ctx* c, int32_t* rows, int32_t cap) {
+    if (!c || !rows) return ESD_ERR_INVALID;
+    if (cap < (int32_t)c->touched.size()) return ESD_ERR_CAPACITY;
+    memcpy(rows, c->touched.data(), sizeof(int32_t) * c->touched.size());
+    return ESD_OK;
+}
+
+int esd_push_frames(esd_ctx* c, const uint8_t* d_bgr, int64_t n, int64_t frame_stride, int64_t pitch,
+                    int64_t first_frame_num, void* stream) {
+    if (!c) return ESD_ERR_INVALID;
+    if (pitch < c->row_bytes) return fail(c, ESD_ERR_INVALID, "push: pitch %lld < row bytes %d", (long long)pitch, c->row_bytes);
+    if (n > 1 && frame_stride < pitch * (int64_t)(c->cfg.src_height - 1) + c->row_bytes)
+        return fail(c, ESD_ERR_INVALID, "push: frame stride %lld smaller than a frame", (long long)frame_stride);
+    return push_common(c, d_bgr, n, frame_stride, pitch, false, first_frame_num, (cudaStream_t)stream);
+}
+
+int esd_push_rows(esd_ctx* c, const uint8_t* d_rows, int64_t n, int64_t first_frame_num, void* stream) {
+    if (!c) return ESD_ERR_INVALID;
+    return push_common(c, d_rows, n, (int64_t)c->touched.size() * c->row_bytes, c->row_bytes, true, first_frame_num,
+                       (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------- ingest ring
+int esd_ingest_open(esd_ctx* c, int32_t n_slots, int32_t frames_per_slot) {
+    if (!c) return ESD_ERR_INVALID;
+    if (!c->ring.empty()) return fail(c, ESD_ERR_STATE, "ingest ring already open");
+    if (n_slots < 2 || frames_per_slot < 1) return fail(c, ESD_ERR_INVALID, "ingest: need >= 2 slots and >= 1 frame per slot");
+    CU(c, cudaSetDevice(c->device));
+    const size_t slot_bytes = (size_t)frames_per_slot * c->touched.size() * c->row_bytes;
+    CU(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CU(c, cudaStreamCreateWithFlags(&c->compute_stream, cudaStreamNonBlocking));
+    c->ring.resize(n_slots);
+    c->frames_per_slot = frames_per_slot;
+    c->next_slot = 0;
+    for (auto& s : c->ring) {
+        CU(c, cudaHostAlloc(&s.h_pinned, slot_bytes, cudaHostAllocDefault));
+        CU(c, cudaMalloc(&s.d_rows, slot_bytes));
+        CU(c, cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
+        CU(c, cudaEventCreateWithFlags(&s.consumed, cudaEventDisableTiming));
+    }
+    return ESD_OK;
+}
+
+int esd_ingest_close(esd_ctx* c) {
+    if (!c) return ESD_ERR_INVALID;
+    if (c->ring.empty()) return ESD_OK;
+    cudaSetDevice(c->device);
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+    if (c->compute_stream) cudaStreamSynchronize(c->compute_stream);
+    for (auto& s : c->ring) {
+        cudaFreeHost(s.h_pinned);
+        cudaFree(s.d_rows);
+        if (s.copied) cudaEventDestroy(s.copied);
+        if (s.consumed) cudaEventDestroy(s.consumed);
+    }
+    c->ring.clear();
+    if (c->have_last_stream && (c->last_stream == c->compute_stream)) c->have_last_stream = false;
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->compute_stream) cudaStreamDestroy(c->compute_stream);
+    c->copy_stream = c->compute_stream = nullptr;
+    return ESD_OK;
+}
+
+int esd_ingest_push_host(esd_ctx* c, const uint8_t* h_bgr, int64_t n, int64_t frame_stride, int64_t pitch,
+                         int64_t first_frame_num) {
+    if (!c) return ESD_ERR_INVALID;
+    if (c->ring.empty()) return fail(c, ESD_ERR_STATE, "ingest ring not open");
+    if (!h_bgr || n <= 0) return fail(c, ESD_ERR_INVALID, "ingest: null frames or n <= 0");
+    if (pitch < c->row_bytes) return fail(c, ESD_ERR_INVALID, "ingest: pitch < row bytes");
+    CU(c, cudaSetDevice(c->device));
+    cudaPointerAttributes attr;
+    bool pinned = false;
+    if (cudaPointerGetAttributes(&attr, h_bgr) == cudaSuccess) pinned = (attr.type == cudaMemoryTypeHost);
+    else cudaGetLastError();
+    const int64_t nt = (int64_t)c->touched.size();
+    const int64_t cfb = nt * c->row_bytes;  // compact frame bytes
+    // runs of consecutive touched rows: (first compact index, first source row, length)
+    struct Run { int crow, row, len; };
+    std::vector<Run> runs;
+    for (int i = 0; i < (int)nt;) {
+        int j = i + 1;
+        while (j < (int)nt && c->touched[j] == c->touched[j - 1] + 1 && pitch == c->row_bytes) ++j;
+        runs.push_back(Run{i, c->touched[i], j - i});
+        i = j;
+    }
+    for (int64_t done = 0; done < n;) {
+        const int64_t m = std::min<int64_t>(c->frames_per_slot, n - done);
+        IngestSlot& s = c->ring[c->next_slot];
+        c->next_slot = (c->next_slot + 1) % (int)c->ring.size();
+        if (s.in_flight) CU(c, cudaEventSynchronize(s.consumed));  // device slot (and pinned slot) free again
+        const uint8_t* src = h_bgr + done * frame_stride;
+        if (pinned) {
+            // DMA straight from the caller's pinned frames: one strided 2-D copy per row run
+            // (rows = frames), so only touched rows cross PCIe.
+            for (const Run& r : runs) {
+                CU(c, cudaMemcpy2DAsync(s.d_rows + (int64_t)r.crow * c->row_bytes, (size_t)cfb,
+                                        src + (int64_t)r.row * pitch, (size_t)frame_stride,
+                                        (size_t)r.len * c->row_bytes, (size_t)m, cudaMemcpyHostToDevice, c->copy_stream));
+                c->h2d_copies++;
+            }
+        } else {
+            // pageable source: the CPU gathers the touched rows into the pinned slot
+            for (int64_t f = 0; f < m; ++f)
+                for (const Run& r : runs)
+                    memcpy(s.h_pinned + f * cfb + (int64_t)r.crow * c->row_bytes, src + f * frame_stride + (int64_t)r.row * pitch,
+                           (size_t)r.len * c->row_bytes);
+            CU(c, cudaMemcpyAsync(s.d_rows, s.h_pinned, (size_t)(m * cfb), cudaMemcpyHostToDevice, c->copy_stream));
+            c->h2d_copies++;
+        }
+        c->h2d_bytes += m * cfb;
+        CU(c, cudaEventRecord(s.copied, c->copy_stream));
+        CU(c, cudaStreamWaitEvent(c->compute_stream, s.copied, 0));
+        int rc = esd_push_rows(c, s.d_rows, m, first_frame_num + done, c->compute_stream);
+        if (rc) return rc;
+        CU(c, cudaEventRecord(s.consumed, c->compute_stream));
+        s.in_flight = true;
+        done += m;
+    }
+    return ESD_OK;
+}
+
+int esd_ingest_stats(const esd_ctx* c, int64_t* bytes, int64_t* copies) {
+    if (!c) return ESD_ERR_INVALID;
+    if (bytes) *bytes = c->h2d_bytes;
+    if (copies) *copies = c->h2d_copies;
+    return ESD_OK;
+}
+
+int esd_synchronize(esd_ctx* c) {
+    if (!c) return ESD_ERR_INVALID;
+    CU(c, cudaSetDevice(c->device));
+    if (c->copy_stream) CU(c, cudaStreamSynchronize(c->copy_stream));
+    if (c->have_last_stream) CU(c, cudaStreamSynchronize(c->last_stream));
+    return ESD_OK;
+}
+
+int64_t esd_frames_pushed(const esd_ctx* c) { return c ? c->n_frames : 0; }
+
+int esd_read_scores(esd_ctx* c, int64_t from_frame, int64_t n, uint64_t* sums3, double* content_val,
+                    double* adaptive_val, double* adaptive_ratio, uint32_t* hist, double* hist_diff) {
+    if (!c) return ESD_ERR_INVALID;
+    if (n == 0) return ESD_OK;
+    const int64_t i0 = from_frame - c->first_frame;
+    if (!c->started || n < 0 || i0 < 0 || i0 + n > c->n_frames)
+        return fail(c, ESD_ERR_INVALID, "read_scores: range [%lld, %lld) outside pushed frames", (long long)from_frame,
+                    (long long)(from_frame + n));
+    int rc = esd_synchronize(c);
+    if (rc) return rc;
+    if ((sums3 || content_val || adaptive_val || adaptive_ratio) && !c->need_content)
+        return fail(c, ESD_ERR_STATE, "read_scores: content scores requested but no content/adaptive detector configured");
+    if ((hist || hist_diff) && !c->need_hist)
+        return fail(c, ESD_ERR_STATE, "read_scores: histogram requested but no histogram detector configured");
+    if (sums3) CU(c, cudaMemcpy(sums3, c->d_sums3 + 3 * i0, sizeof(uint64_t) * 3 * n, cudaMemcpyDeviceToHost));
+    if (content_val) CU(c, cudaMemcpy(content_val, c->d_cv + i0, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    if (adaptive_val) CU(c, cudaMemcpy(adaptive_val, c->d_av + i0, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    if (adaptive_ratio) CU(c, cudaMemcpy(adaptive_ratio, c->d_ratio + i0, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    if (hist) CU(c, cudaMemcpy(hist, c->d_counts + i0 * c->cfg.hist_bins, sizeof(uint32_t) * n * c->cfg.hist_bins, cudaMemcpyDeviceToHost));
+    if (hist_diff) CU(c, cudaMemcpy(hist_diff, c->d_hdiff + i0, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    return ESD_OK;
+}
+
+static int det_index(int32_t detector) {
+    return detector == ESD_DET_CONTENT ? 0 : detector == ESD_DET_ADAPTIVE ? 1 : detector == ESD_DET_HIST ? 2 : -1;
+}
+
+int esd_get_cuts(esd_ctx* c, int32_t detector, int64_t from_index, int64_t* cuts, int64_t cap, int64_t* n_written,
+                 int64_t* n_total) {
+    if (!c) return ESD_ERR_INVALID;
+    const int di = det_index(detector);
+    if (di < 0 || !(c->cfg.detectors & detector)) return fail(c, ESD_ERR_INVALID, "get_cuts: detector %d not configured", detector);
+    int rc = esd_synchronize(c);
+    if (rc) return rc;
+    DecisionState st;
+    CU(c, cudaMemcpy(&st, c->d_state, sizeof st, cudaMemcpyDeviceToHost));
+    if (st.overflow) return fail(c, ESD_ERR_CAPACITY, "cut list overflow (max_cuts = %lld)", (long long)c->max_cuts);
+    const int64_t total = st.n_cuts[di];
+    if (n_total) *n_total = total;
+    if (from_index < 0) from_index = 0;
+    const int64_t avail = std::max<int64_t>(0, total - from_index);
+    const int64_t m = std::min(avail, cap);
+    if (n_written) *n_written = m;
+    if (m > 0 && cuts)
+        CU(c, cudaMemcpy(cuts, c->d_cuts + (int64_t)di * c->max_cuts + from_index, sizeof(int64_t) * m, cudaMemcpyDeviceToHost));
+    if (avail > cap) return fail(c, ESD_ERR_CAPACITY, "get_cuts: %lld cuts pending, buffer holds %lld", (long long)avail, (long long)cap);
+    return ESD_OK;
+}
+
+int esd_decide_arrays(esd_ctx* c, int32_t detector, int64_t first_frame_num, int64_t n, const double* scores,
+                      double* adaptive_ratio_out, int64_t* cuts, int64_t cap, int64_t* n_cuts) {
+    if (!c || !scores || n < 0) return ESD_ERR_INVALID;
+    const int di = det_index(detector);
+    if (di < 0 || !(c->cfg.detectors & detector)) return fail(c, ESD_ERR_INVALID, "decide_arrays: detector %d not configured", detector);
+    CU(c, cudaSetDevice(c->device));
+    if (n_cuts) *n_cuts = 0;
+    if (n == 0) return ESD_OK;
+    double *d_scores = nullptr, *d_ratio = nullptr;
+    DecisionState* d_st = nullptr;
+    long long* d_cuts = nullptr;
+    int rc = ESD_OK;
+    auto cleanup = [&]() { cudaFree(d_scores); cudaFree(d_ratio); cudaFree(d_st); cudaFree(d_cuts); };
+#define CUD(call)                                                                                  \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            cleanup();                                                                             \
+            return fail(c, ESD_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_));          \
+        }                                                                                          \
+    } while (0)
+    CUD(cudaMalloc(&d_scores, sizeof(double) * n));
+    CUD(cudaMalloc(&d_ratio, sizeof(double) * n));
+    CUD(cudaMalloc(&d_st, sizeof(DecisionState)));
+    CUD(cudaMalloc(&d_cuts, sizeof(long long) * 3 * c->max_cuts));
+    CUD(cudaMemcpy(d_scores, scores, sizeof(double) * n, cudaMemcpyHostToDevice));
+    CUD(cudaMemset(d_st, 0, sizeof(DecisionState)));
+    fill_nan_kernel<<<(unsigned)((n + 255) / 256), 256>>>(d_ratio, n);
+    DecisionParams P = c->dparams;
+    P.detectors = detector;
+    if (detector == ESD_DET_ADAPTIVE) {
+        const int w = P.adaptive_w;
+        if (n - w > w)
+            adaptive_ratio_kernel<<<(unsigned)((n - 2 * w + 255) / 256), 256>>>(d_scores, d_ratio, w, n - w, w,
+                                                                               P.adaptive_min_content_val);
+    }
+    decide_kernel<<<3, 256>>>(P, d_st, d_cuts, d_scores, d_scores, d_ratio, d_scores, first_frame_num, 0, n);
+    c->launches += 3;
+    CUD(cudaGetLastError());
+    CUD(cudaDeviceSynchronize());
+    DecisionState st;
+    CUD(cudaMemcpy(&st, d_st, sizeof st, cudaMemcpyDeviceToHost));
+    const int64_t total = st.n_cuts[di];
+    if (n_cuts) *n_cuts = total;
+    if (st.overflow || total > cap) rc = fail(c, ESD_ERR_CAPACITY, "decide_arrays: %lld cuts, buffer holds %lld", (long long)total, (long long)cap);
+    else if (total > 0 && cuts) CUD(cudaMemcpy(cuts, d_cuts + (int64_t)di * c->max_cuts, sizeof(int64_t) * total, cudaMemcpyDeviceToHost));
+    if (adaptive_ratio_out) CUD(cudaMemcpy(adaptive_ratio_out, d_ratio, sizeof(double) * n, cudaMemcpyDeviceToHost));
+#undef CUD
+    cleanup();
+    return rc;
+}
+
+int esd_debug_read_prev(esd_ctx* c, uint32_t* out, int64_t cap) {
+    if (!c || !out) return ESD_ERR_INVALID;
+    if (!c->need_content || c->n_frames == 0) return fail(c, ESD_ERR_STATE, "debug_read_prev: no content frame pushed yet");
+    const int64_t n = (int64_t)c->dst_w * c->dst_h;
+    if (cap < n) return ESD_ERR_CAPACITY;
+    int rc = esd_synchronize(c);
+    if (rc) return rc;
+    CU(c, cudaMemcpy(out, c->d_prev[c->prev_parity], sizeof(uint32_t) * n, cudaMemcpyDeviceToHost));
+    return ESD_OK;
+}
+
+int esd_set_timing(esd_ctx* c, int32_t enable) {
+    if (!c) return ESD_ERR_INVALID;
+    c->timing = enable != 0;
+    return ESD_OK;
+}
+
+int esd_kernel_time(esd_ctx* c, double* fused_ms, int64_t* fused_launches) {
+    if (!c) return ESD_ERR_INVALID;
+    int rc = esd_synchronize(c);
+    if (rc) return rc;
+    double total = 0.0;
+    for (auto& ev : c->timing_events) {
+        float ms = 0.f;
+        CU(c, cudaEventElapsedTime(&ms, ev.first, ev.second));
+        total += ms;
+        cudaEventDestroy(ev.first);
+        cudaEventDestroy(ev.second);
+    }
+    if (fused_ms) *fused_ms = total;
+    if (fused_launches) *fused_launches = (int64_t)c->timing_events.size();
+    c->timing_events.clear();
+    return ESD_OK;
+}
+
+int64_t esd_kernel_launches(const esd_ctx* c) { return c ? c->launches : 0; }
+
+int esd_synth_fill(uint8_t* d_out, int32_t width, int32_t height, int64_t pitch, int64_t frame_stride, uint32_t seed,
+                   const int32_t* descs, int64_t n, int device, void* stream) {
+    if (!d_out || !descs || n <= 0 || width < 1 || height < 1) return ESD_ERR_INVALID;
+    if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, ESD_ERR_CUDA, "synth_fill: cudaSetDevice(%d) failed", device);
+    syn_frame_desc* d_desc = nullptr;
+    cudaError_t e = cudaMalloc(&d_desc, sizeof(syn_frame_desc) * n);
+    if (e != cudaSuccess) return fail(nullptr, ESD_ERR_CUDA, "synth_fill: %s", cudaGetErrorString(e));
+    cudaStream_t st = (cudaStream_t)stream;
+    e = cudaMemcpyAsync(d_desc, descs, sizeof(syn_frame_desc) * n, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        const long long total = (long long)width * height * n;
+        synth_fill_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_out, width, height, pitch, frame_stride, seed,
+                                                                           d_desc, n);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_desc);
+    if (e != cudaSuccess) return fail(nullptr, ESD_ERR_CUDA, "synth_fill: %s", cudaGetErrorString(e));
+    return ESD_OK;
+}
+
+}  // extern "C"

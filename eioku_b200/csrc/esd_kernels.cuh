@@ -1,0 +1,616 @@
+// esd_kernels.cuh -- device code of libesd.so (sm_100a).
+//
+// Fused scoring kernel (one launch per pushed batch):
+//   HBM --cp.async.bulk (TMA 1-D, mbarrier complete_tx)--> smem ring of source-row pairs
+//   -> INTER_LINEAR 11-bit fixed-point 2x2 taps (OpenCV resize.cpp arithmetic)
+//   -> BGR->HSV uint8 (OpenCV RGB2HSV_b tables, A.3)  [+ BGR->Y and smem-atomic histogram, A.7]
+//   -> |cur - prev| against the previous frame's HSV kept in shared memory (A.4)
+//   -> warp REDUX -> per-(frame,rowgroup,warp) partial sums.
+// A CTA owns a group of destination rows and walks consecutive frames, so the previous
+// frame's HSV never leaves the SM; only the touched source rows are ever read from HBM.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace esd {
+
+constexpr int kConsumerWarps = 8;
+constexpr int kConsumers = kConsumerWarps * 32;  // 256 pixel threads
+constexpr int kThreads = kConsumers + 32;        // + 1 producer warp
+constexpr int kMaxStages = 8;
+
+enum : int { F_HALO = 1, F_NOPREV = 2, F_CTXPREV = 4, F_SAVE = 8, F_FRAME_END = 16, F_END = 32 };
+
+struct Unit {  // frames [f0, f1) (batch-relative) of destination-row group rg
+    int rg, f0, f1, pad;
+};
+
+struct YRow {  // per destination row
+    int row0, row1;    // source rows (full layout)
+    int crow0, crow1;  // indices into the compact (touched rows only) layout
+    uint32_t b0s, b1s; // vertical coefficients, pre-shifted << 16 for mul.hi
+    int pad0, pad1;
+};
+
+struct FusedParams {
+    const uint8_t* src;
+    long long frame_stride;  // bytes between frames
+    long long row_stride;    // bytes between rows (pitch, or row_bytes in the compact layout)
+    int compact;
+    int n_frames;
+    int dst_w, dst_h;
+    int row_bytes;  // src_w * 3
+    int rows_per_group, n_groups;
+    int stages;
+    int rowbuf;  // bytes reserved per staged source row (multiple of 16)
+    int has_prev;
+    int bins;
+    const YRow* yrows;
+    const uint2* xtab;  // per destination column: {byte offset of tap 0, a0 | a1 << 16}
+    const int* sdiv;
+    const int* hdiv;
+    const Unit* units;
+    const int* cta_unit_begin;  // [grid + 1]
+    const uint32_t* prev_in;    // packed H|S<<8|V<<16 of the frame before this batch [dst_h][dst_w]
+    uint32_t* prev_out;         // same, written from the last frame of this batch
+    uint4* part;                // [n_frames][n_groups][kConsumerWarps] {sumH, sumS, sumV, 0}
+    uint16_t* hist_part;        // [n_frames][n_groups][bins]
+};
+
+// ----------------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("{ .reg .b64 st; mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1; }" ::"r"(bar), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return done != 0;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// Bounded wait: a pipeline bug must trap (reported as a CUDA error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    unsigned long long t0 = globaltimer_ns();
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++spins & 0x3ff) == 0 && globaltimer_ns() - t0 > 4000000000ULL) __trap();
+    }
+}
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+// 1-D bulk tensor-memory-accelerator copy global -> shared, completion counted on an mbarrier.
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t pol) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+        ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(pol)
+        : "memory");
+}
+__device__ __forceinline__ void consumer_bar_sync() {
+    asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory");
+}
+
+// ----------------------------------------------------------------------------------- pixel math
+// unaligned little-endian 32-bit read at shared byte address `a` (reads a & ~3 and the next word)
+__device__ __forceinline__ uint32_t lds_u32_unaligned(const uint8_t* base, uint32_t a, uint32_t& next_word) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(base + (a & ~3u));
+    uint32_t w0 = w[0], w1 = w[1];
+    next_word = w1;
+    return __funnelshift_r(w0, w1, (a & 3u) * 8u);
+}
+
+// OpenCV RGB2HSV_b (uint8, hrange 180), packed H | S << 8 | V << 16
+__device__ __forceinline__ uint32_t bgr_to_hsv_packed(int b, int g, int r, const int* __restrict__ sdiv,
+                                                      const int* __restrict__ hdiv) {
+    int v = max(max(b, g), r);
+    int m = min(min(b, g), r);
+    int diff = v - m;
+    int s = (diff * sdiv[v] + (1 << 11)) >> 12;
+    int h = (v == r) ? (g - b) : ((v == g) ? (b - r + 2 * diff) : (r - g + 4 * diff));
+    h = (h * hdiv[diff] + (1 << 11)) >> 12;
+    h += (h < 0) ? 180 : 0;
+    return (uint32_t)h | ((uint32_t)s << 8) | ((uint32_t)v << 16);
+}
+
+// OpenCV VResizeLinear<uchar,int,short,FixedPtCast<int,uchar,22>>: b0s/b1s are the coefficients << 16
+__device__ __forceinline__ int vresize(uint32_t h0, uint32_t h1, uint32_t b0s, uint32_t b1s) {
+    int v = (int)((__umulhi(b0s, h0 >> 4) + __umulhi(b1s, h1 >> 4) + 2u) >> 2);
+    return min(v, 255);
+}
+
+template <bool RESIZE, int PXT, bool CONTENT, bool HIST>
+__global__ void __launch_bounds__(kThreads) fused_score_kernel(const FusedParams p) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    // ---- carve shared memory
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw);              // [kMaxStages]
+    uint64_t* empty_bar = full_bar + kMaxStages;                               // [kMaxStages]
+    int4* meta = reinterpret_cast<int4*>(empty_bar + kMaxStages);              // [kMaxStages] {f, rloc|row<<8, flags, mis}
+    uint2* meta_b = reinterpret_cast<uint2*>(meta + kMaxStages);               // [kMaxStages] {b0s, b1s}
+    int* s_sdiv = reinterpret_cast<int*>(meta_b + kMaxStages);                 // [256]
+    int* s_hdiv = s_sdiv + 256;                                                // [256]
+    uint32_t* s_hist = reinterpret_cast<uint32_t*>(s_hdiv + 256);              // [2][256]
+    uint32_t* s_prev = s_hist + 512;                                           // [rows_per_group][PXT*kConsumers]
+    size_t off = (size_t)(reinterpret_cast<uint8_t*>(s_prev + (CONTENT ? p.rows_per_group * PXT * kConsumers : 0)) - smem_raw);
+    off = (off + 127) & ~(size_t)127;
+    uint8_t* s_stage = smem_raw + off;                                         // [stages][2][rowbuf]
+
+    const int tid = threadIdx.x;
+    const int S = p.stages;
+    for (int i = tid; i < 256; i += kThreads) {
+        s_sdiv[i] = p.sdiv[i];
+        s_hdiv[i] = p.hdiv[i];
+        s_hist[i] = 0;
+        s_hist[256 + i] = 0;
+    }
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(smem_u32(&full_bar[s]), 1);
+            mbar_init(smem_u32(&empty_bar[s]), kConsumerWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int u_begin = p.cta_unit_begin[blockIdx.x];
+    const int u_end = p.cta_unit_begin[blockIdx.x + 1];
+    const int R = p.rows_per_group;
+    const int stage_bytes = (RESIZE ? 2 : 1) * p.rowbuf;
+
+    if (tid >= kConsumers) {
+        // ================================================================ producer warp (one lane)
+        if (tid != kConsumers) return;
+        const uint64_t pol = l2_evict_first_policy();
+        int s = 0;
+        uint32_t par = 1u;  // empty barriers start "free"
+        for (int u = u_begin; u < u_end; ++u) {
+            const Unit un = p.units[u];
+            const int r_begin = un.rg * R;
+            const int r_end = min(r_begin + R, p.dst_h);
+            const int f_start = (CONTENT && un.f0 > 0) ? un.f0 - 1 : un.f0;
+            for (int f = f_start; f < un.f1; ++f) {
+                const uint8_t* frame = p.src + (long long)f * p.frame_stride;
+                int fflags = 0;
+                if (CONTENT) {
+                    if (f < un.f0) fflags |= F_HALO;
+                    else if (f == 0) fflags |= p.has_prev ? F_CTXPREV : F_NOPREV;
+                    if (f == p.n_frames - 1) fflags |= F_SAVE;
+                }
+                for (int r = r_begin; r < r_end; ++r) {
+                    mbar_wait(smem_u32(&empty_bar[s]), par);
+                    const YRow yr = p.yrows[r];
+                    const uint8_t* a0 = frame + (long long)(p.compact ? yr.crow0 : yr.row0) * p.row_stride;
+                    const uint32_t mis0 = (uint32_t)(reinterpret_cast<uintptr_t>(a0) & 15u);
+                    const uint32_t bytes0 = (mis0 + (uint32_t)p.row_bytes + 15u) & ~15u;
+                    uint32_t mis1 = 0, bytes1 = 0;
+                    const uint8_t* a1 = a0;
+                    if (RESIZE) {
+                        a1 = frame + (long long)(p.compact ? yr.crow1 : yr.row1) * p.row_stride;
+                        mis1 = (uint32_t)(reinterpret_cast<uintptr_t>(a1) & 15u);
+                        bytes1 = (mis1 + (uint32_t)p.row_bytes + 15u) & ~15u;
+                    }
+                    const int flags = fflags | ((r == r_end - 1) ? F_FRAME_END : 0);
+                    meta[s] = make_int4(f, (r - r_begin) | (r << 8), flags, (int)(mis0 | (mis1 << 8)));
+                    meta_b[s] = make_uint2(yr.b0s, yr.b1s);
+                    const uint32_t bar = smem_u32(&full_bar[s]);
+                    const uint32_t dst = smem_u32(s_stage + (size_t)s * stage_bytes);
+                    mbar_arrive_expect_tx(bar, bytes0 + bytes1);
+                    bulk_g2s(dst, a0 - mis0, bytes0, bar, pol);
+                    if (RESIZE) bulk_g2s(dst + p.rowbuf, a1 - mis1, bytes1, bar, pol);
+                    if (++s == S) { s = 0; par ^= 1u; }
+                }
+            }
+        }
+        // sentinel: tells the consumers to stop
+        mbar_wait(smem_u32(&empty_bar[s]), par);
+        meta[s] = make_int4(0, 0, F_END, 0);
+        mbar_arrive(smem_u32(&full_bar[s]));
+        return;
+    }
+
+    // ==================================================================== consumer warps
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    uint32_t xoff[PXT], xa01[PXT];
+#pragma unroll
+    for (int k = 0; k < PXT; ++k) {
+        const int d = k * kConsumers + tid;
+        if (RESIZE) {
+            const uint2 xe = (d < p.dst_w) ? p.xtab[d] : make_uint2(0u, 0u);
+            xoff[k] = xe.x;
+            xa01[k] = xe.y;
+        } else {
+            xoff[k] = (uint32_t)(3 * d);
+            xa01[k] = 0;
+        }
+    }
+    uint32_t acc_hv = 0, acc_s = 0;  // per-frame, per-thread: H | V << 16 and S
+    int hist_buf = 0;
+    int s = 0;
+    uint32_t par = 0u;
+    for (;; ) {
+        mbar_wait(smem_u32(&full_bar[s]), par);
+        const int4 m = meta[s];
+        const int flags = m.z;
+        if (flags & F_END) break;
+        const uint2 bb = meta_b[s];
+        const int rloc = m.y & 0xff;
+        const int row = m.y >> 8;
+        const uint8_t* row0 = s_stage + (size_t)s * stage_bytes;
+        const uint8_t* row1 = row0 + p.rowbuf;
+        const uint32_t mis0 = (uint32_t)m.w & 0xffu, mis1 = ((uint32_t)m.w >> 8) & 0xffu;
+#pragma unroll
+        for (int k = 0; k < PXT; ++k) {
+            const int d = k * kConsumers + tid;
+            if (d < p.dst_w) {
+                int b, g, r;
+                if (RESIZE) {
+                    uint32_t n0, n1;
+                    const uint32_t o0 = xoff[k] + mis0, o1 = xoff[k] + mis1;
+                    const uint32_t lo0 = lds_u32_unaligned(row0, o0, n0);
+                    const uint32_t w02 = *reinterpret_cast<const uint32_t*>(row0 + (o0 & ~3u) + 8);
+                    const uint32_t hi0 = __funnelshift_r(n0, w02, (o0 & 3u) * 8u);
+                    const uint32_t lo1 = lds_u32_unaligned(row1, o1, n1);
+                    const uint32_t w12 = *reinterpret_cast<const uint32_t*>(row1 + (o1 & ~3u) + 8);
+                    const uint32_t hi1 = __funnelshift_r(n1, w12, (o1 & 3u) * 8u);
+                    // lo = [Ab Ag Ar Bb], hi = [Bg Br . .]  ->  [Ab Bb Ag Bg] and [Ar Br . .]
+                    const uint32_t bg0 = __byte_perm(lo0, hi0, 0x4130), rr0 = __byte_perm(lo0, hi0, 0x0052);
+                    const uint32_t bg1 = __byte_perm(lo1, hi1, 0x4130), rr1 = __byte_perm(lo1, hi1, 0x0052);
+                    const uint32_t a = xa01[k];
+                    // HResizeLinear: tap0 * a0 + tap1 * a1 (scale 2^11)
+                    const uint32_t hb0 = __dp2a_lo(a, bg0, 0u), hg0 = __dp2a_hi(a, bg0, 0u), hr0 = __dp2a_lo(a, rr0, 0u);
+                    const uint32_t hb1 = __dp2a_lo(a, bg1, 0u), hg1 = __dp2a_hi(a, bg1, 0u), hr1 = __dp2a_lo(a, rr1, 0u);
+                    b = vresize(hb0, hb1, bb.x, bb.y);
+                    g = vresize(hg0, hg1, bb.x, bb.y);
+                    r = vresize(hr0, hr1, bb.x, bb.y);
+                } else {
+                    uint32_t nx;
+                    const uint32_t px = lds_u32_unaligned(row0, xoff[k] + mis0, nx);
+                    b = px & 255u;
+                    g = (px >> 8) & 255u;
+                    r = (px >> 16) & 255u;
+                }
+                if (CONTENT) {
+                    const uint32_t cur = bgr_to_hsv_packed(b, g, r, s_sdiv, s_hdiv);
+                    uint32_t* slot = s_prev + (rloc * PXT + k) * kConsumers + tid;
+                    uint32_t pv = cur;
+                    if (!(flags & (F_HALO | F_NOPREV)))
+                        pv = (flags & F_CTXPREV) ? __ldg(p.prev_in + (size_t)row * p.dst_w + d) : *slot;
+                    const uint32_t diff = __vabsdiffu4(cur, pv);
+                    acc_hv += diff & 0x00ff00ffu;
+                    acc_s += (diff >> 8) & 0xffu;
+                    *slot = cur;
+                    if (flags & F_SAVE) p.prev_out[(size_t)row * p.dst_w + d] = cur;
+                }
+                if (HIST && !(flags & F_HALO)) {
+                    const int y = (4899 * r + 9617 * g + 1868 * b + 8192) >> 14;
+                    atomicAdd(&s_hist[hist_buf * 256 + ((y * p.bins) >> 8)], 1u);
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&empty_bar[s]));  // stage may be refilled
+        if (++s == S) { s = 0; par ^= 1u; }
+
+        if (flags & F_FRAME_END) {
+            const bool scored = !(flags & F_HALO);
+            if (CONTENT) {
+                if (scored) {
+                    const uint32_t sh = __reduce_add_sync(0xffffffffu, acc_hv & 0xffffu);
+                    const uint32_t sv = __reduce_add_sync(0xffffffffu, acc_hv >> 16);
+                    const uint32_t ss = __reduce_add_sync(0xffffffffu, acc_s);
+                    if (lane == 0)
+                        p.part[((size_t)m.x * p.n_groups + (row / p.rows_per_group)) * kConsumerWarps + warp] =
+                            make_uint4(sh, ss, sv, 0u);
+                }
+                acc_hv = 0;
+                acc_s = 0;
+            }
+            if (HIST && scored) {
+                consumer_bar_sync();  // all smem atomics of this frame have landed
+                if (tid < p.bins) {
+                    uint32_t* hslot = &s_hist[hist_buf * 256 + tid];
+                    p.hist_part[((size_t)m.x * p.n_groups + (row / p.rows_per_group)) * p.bins + tid] = (uint16_t)*hslot;
+                    *hslot = 0;
+                }
+                hist_buf ^= 1;  // the other buffer was zeroed one frame ago (before the barrier above)
+            }
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------- finalize
+struct ScoreWeights {
+    double w[4];
+    double div;
+};
+
+// IEEE double, left to right, no FMA: PySceneDetect ContentDetector._calculate_frame_score (A.4)
+__device__ __forceinline__ double content_val_of(const unsigned long long s[3], double npx, const ScoreWeights& W) {
+    const double dh = __ddiv_rn((double)s[0], npx);
+    const double ds = __ddiv_rn((double)s[1], npx);
+    const double dv = __ddiv_rn((double)s[2], npx);
+    double acc = 0.0;
+    acc = __dadd_rn(acc, __dmul_rn(dh, W.w[0]));
+    acc = __dadd_rn(acc, __dmul_rn(ds, W.w[1]));
+    acc = __dadd_rn(acc, __dmul_rn(dv, W.w[2]));
+    acc = __dadd_rn(acc, __dmul_rn(0.0, W.w[3]));
+    return __ddiv_rn(acc, W.div);
+}
+
+// one warp per frame: reduce the per-(group,warp) partials, emit sums and both content_val flavours
+__global__ void finalize_sums_kernel(const uint4* __restrict__ part, int n_frames, int parts_per_frame, double npx,
+                                     ScoreWeights wc, ScoreWeights wa, unsigned long long* __restrict__ sums3,
+                                     double* __restrict__ content_val, double* __restrict__ adaptive_val) {
+    const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (f >= n_frames) return;
+    unsigned long long s[3] = {0, 0, 0};
+    const uint4* pf = part + (size_t)f * parts_per_frame;
+    for (int i = lane; i < parts_per_frame; i += 32) {
+        const uint4 v = pf[i];
+        s[0] += v.x; s[1] += v.y; s[2] += v.z;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s[0] += __shfl_xor_sync(0xffffffffu, s[0], o);
+        s[1] += __shfl_xor_sync(0xffffffffu, s[1], o);
+        s[2] += __shfl_xor_sync(0xffffffffu, s[2], o);
+    }
+    if (lane == 0) {
+        sums3[3 * (size_t)f] = s[0];
+        sums3[3 * (size_t)f + 1] = s[1];
+        sums3[3 * (size_t)f + 2] = s[2];
+        content_val[f] = content_val_of(s, npx, wc);
+        adaptive_val[f] = content_val_of(s, npx, wa);
+    }
+}
+
+// one block per frame: sum the per-group partial histograms into uint32 counts
+__global__ void finalize_hist_counts_kernel(const uint16_t* __restrict__ hist_part, int n_groups, int bins,
+                                            uint32_t* __restrict__ counts) {
+    const int f = blockIdx.x;
+    for (int b = threadIdx.x; b < bins; b += blockDim.x) {
+        uint32_t c = 0;
+        const uint16_t* hp = hist_part + (size_t)f * n_groups * bins + b;
+        for (int g = 0; g < n_groups; ++g) c += hp[(size_t)g * bins];
+        counts[(size_t)f * bins + b] = c;
+    }
+}
+
+// cv2.normalize(hist, hist) (L2) then cv2.compareHist(prev, cur, CORREL) with OpenCV's summation order
+// (two interleaved double lanes over blocks of 4, scalar tail), SURVEY.md A.7.  One block per frame.
+// counts points at the batch's first frame inside the ctx-wide array; counts[-bins..-1] is the frame before.
+__global__ void hist_diff_kernel(const uint32_t* __restrict__ counts, int bins, int first_has_prev,
+                                 double* __restrict__ hist_diff) {
+    __shared__ float hn[2][256];
+    __shared__ double red[2][32];
+    __shared__ double lanes_out[10];
+    const int f = blockIdx.x;
+    const int tid = threadIdx.x;
+    if (f == 0 && !first_has_prev) {
+        if (tid == 0) hist_diff[0] = __longlong_as_double(0x7ff8000000000000LL);
+        return;
+    }
+    // L2 norms (exact integer arithmetic in double) of frame f-1 and f
+    for (int which = 0; which < 2; ++which) {
+        const uint32_t* c = counts + ((long long)f - 1 + which) * bins;
+        double ss = 0.0;
+        for (int b = tid; b < bins; b += blockDim.x) {
+            const double v = (double)c[b];
+            ss += v * v;  // exact: integers below 2^53
+        }
+        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        if ((tid & 31) == 0) red[which][tid >> 5] = ss;
+    }
+    __syncthreads();
+    for (int which = 0; which < 2; ++which) {
+        double ss = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) ss += red[which][w];
+        const double nrm = __dsqrt_rn(ss);
+        const double scale = nrm > 2.220446049250313e-16 ? __ddiv_rn(1.0, nrm) : 0.0;
+        const float fs = __double2float_rn(scale);
+        const uint32_t* c = counts + ((long long)f - 1 + which) * bins;
+        for (int b = tid; b < bins; b += blockDim.x) hn[which][b] = __fmul_rn((float)c[b], fs);
+    }
+    __syncthreads();
+    // 5 quantities x 2 lanes: strictly sequential double chains in OpenCV's order
+    if (tid < 10) {
+        const int q = tid >> 1, ln = tid & 1;
+        const int nv = (bins / 4) * 4;
+        double acc = 0.0;
+        for (int j = ln; j < nv; j += 2) {
+            const double a = (double)hn[0][j], b = (double)hn[1][j];
+            double t;
+            switch (q) {
+                case 0: t = __dmul_rn(a, b); break;  // s12
+                case 1: t = a; break;                // s1
+                case 2: t = __dmul_rn(a, a); break;  // s11
+                case 3: t = b; break;                // s2
+                default: t = __dmul_rn(b, b); break; // s22
+            }
+            acc = __dadd_rn(acc, t);
+        }
+        lanes_out[tid] = acc;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double q[5];
+        const int nv = (bins / 4) * 4;
+        for (int k = 0; k < 5; ++k) q[k] = __dadd_rn(0.0, __dadd_rn(lanes_out[2 * k], lanes_out[2 * k + 1]));
+        for (int j = nv; j < bins; ++j) {
+            const double a = (double)hn[0][j], b = (double)hn[1][j];
+            q[0] = __dadd_rn(q[0], __dmul_rn(a, b));
+            q[1] = __dadd_rn(q[1], a);
+            q[2] = __dadd_rn(q[2], __dmul_rn(a, a));
+            q[3] = __dadd_rn(q[3], b);
+            q[4] = __dadd_rn(q[4], __dmul_rn(b, b));
+        }
+        const double s12 = q[0], s1 = q[1], s11 = q[2], s2 = q[3], s22 = q[4];
+        const double scale = __ddiv_rn(1.0, (double)bins);
+        const double num = __dadd_rn(s12, -__dmul_rn(__dmul_rn(s1, s2), scale));
+        const double d1 = __dadd_rn(s11, -__dmul_rn(__dmul_rn(s1, s1), scale));
+        const double d2 = __dadd_rn(s22, -__dmul_rn(__dmul_rn(s2, s2), scale));
+        const double den2 = __dmul_rn(d1, d2);
+        hist_diff[f] = fabs(den2) > 2.220446049250313e-16 ? __ddiv_rn(num, __dsqrt_rn(den2)) : 1.0;
+    }
+}
+
+// AdaptiveDetector rolling-window ratio (A.6): one thread per target frame index t in [t_begin, t_end);
+// val/ratio are indexed from the first frame of the video (or of the array).
+__global__ void adaptive_ratio_kernel(const double* __restrict__ val, double* __restrict__ ratio, long long t_begin,
+                                      long long t_end, int w, double min_content_val) {
+    const long long t = t_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= t_end) return;
+    double sum = 0.0;
+    bool first = true;
+    for (int k = -w; k <= w; ++k) {
+        if (k == 0) continue;
+        const double s = val[t + k];
+        sum = first ? s : __dadd_rn(sum, s);  // int 0 + s == s
+        first = false;
+    }
+    const double avg = __ddiv_rn(sum, __dmul_rn(2.0, (double)w));
+    const double target = val[t];
+    double r = 0.0;
+    if (!(fabs(avg) < 0.00001)) {
+        const double q = __ddiv_rn(target, avg);
+        r = (255.0 < q) ? 255.0 : q;  // Python min(q, 255.0)
+    } else if (target >= min_content_val) {
+        r = 255.0;
+    }
+    ratio[t] = r;
+}
+
+// ----------------------------------------------------------------------------------- decision passes
+struct DecisionState {
+    long long c_last_above, c_merge_start;
+    int c_init, c_merge_enabled, c_merge_triggered, pad0;
+    long long a_last_cut;
+    int a_init, pad1;
+    long long h_last_cut;  // 0 == "not set" (Python falsiness of `if not self._last_scene_cut`)
+    long long n_cuts[3];
+    int overflow, pad2;
+};
+
+struct DecisionParams {
+    int detectors;
+    int content_min_scene_len, content_filter_mode;
+    int adaptive_w, adaptive_min_scene_len;
+    int hist_min_scene_len;
+    double content_threshold;
+    double adaptive_threshold, adaptive_min_content_val;
+    double hist_threshold;  // already clamp(1 - t, 0, 1)
+    long long max_cuts;
+};
+
+__device__ __forceinline__ void emit_cut(DecisionState* st, long long* cuts, int det, long long max_cuts, long long v) {
+    const long long n = st->n_cuts[det];
+    if (n < max_cuts) cuts[(size_t)det * max_cuts + n] = v;
+    else st->overflow = 1;
+    st->n_cuts[det] = n + 1;
+}
+
+// grid = 3 blocks (content, adaptive, hist); frames [i_begin, i_end) are indices from first_frame_num.
+// The threshold tests run in parallel into a shared bitmask; one thread then walks the sequential
+// FlashFilter / min_scene_len state machine (A.5-A.7).
+__global__ void decide_kernel(DecisionParams P, DecisionState* __restrict__ st, long long* __restrict__ cuts,
+                              const double* __restrict__ content_val, const double* __restrict__ adaptive_val,
+                              const double* __restrict__ adaptive_ratio, const double* __restrict__ hist_diff,
+                              long long first_frame_num, long long i_begin, long long i_end) {
+    constexpr int CH = 4096;
+    __shared__ uint32_t bits[CH / 32];
+    const int det = blockIdx.x;
+    if (!(P.detectors & (1 << det))) return;
+    const int tid = threadIdx.x;
+    for (long long c0 = i_begin; c0 < i_end; c0 += CH) {
+        const long long c1 = (c0 + CH < i_end) ? c0 + CH : i_end;
+        for (int j = tid; j < CH; j += blockDim.x) {
+            const long long i = c0 + j;
+            bool bit = false;
+            if (i < c1) {
+                if (det == 0) bit = content_val[i] >= P.content_threshold;
+                else if (det == 1) {
+                    const long long t = i - P.adaptive_w;
+                    if (i >= 2LL * P.adaptive_w)
+                        bit = adaptive_ratio[t] >= P.adaptive_threshold && adaptive_val[t] >= P.adaptive_min_content_val;
+                } else bit = hist_diff[i] <= P.hist_threshold;  // NaN (no previous frame) compares false
+            }
+            const uint32_t word = __ballot_sync(0xffffffffu, bit);
+            if ((tid & 31) == 0) bits[j >> 5] = word;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            for (long long i = c0; i < c1; ++i) {
+                const int j = (int)(i - c0);
+                const bool above = (bits[j >> 5] >> (j & 31)) & 1u;
+                const long long fn = first_frame_num + i;
+                if (det == 0) {
+                    const int L = P.content_min_scene_len;
+                    if (!(L > 0)) {
+                        if (above) emit_cut(st, cuts, 0, P.max_cuts, fn);
+                        continue;
+                    }
+                    if (!st->c_init) { st->c_init = 1; st->c_last_above = fn; }
+                    const bool met = (fn - st->c_last_above) >= L;
+                    if (P.content_filter_mode == 1) {  // SUPPRESS
+                        if (above && met) { st->c_last_above = fn; emit_cut(st, cuts, 0, P.max_cuts, fn); }
+                        continue;
+                    }
+                    if (above) st->c_last_above = fn;
+                    if (st->c_merge_triggered) {
+                        const long long merged = st->c_last_above - st->c_merge_start;
+                        if (met && !above && merged >= L) {
+                            st->c_merge_triggered = 0;
+                            emit_cut(st, cuts, 0, P.max_cuts, st->c_last_above);
+                        }
+                        continue;
+                    }
+                    if (!above) continue;
+                    if (met) { st->c_merge_enabled = 1; emit_cut(st, cuts, 0, P.max_cuts, fn); continue; }
+                    if (st->c_merge_enabled) { st->c_merge_triggered = 1; st->c_merge_start = fn; }
+                } else if (det == 1) {
+                    if (!st->a_init) { st->a_init = 1; st->a_last_cut = fn; }
+                    if (above && (fn - st->a_last_cut) >= P.adaptive_min_scene_len) {
+                        st->a_last_cut = fn - P.adaptive_w;
+                        emit_cut(st, cuts, 1, P.max_cuts, fn - P.adaptive_w);
+                    }
+                } else {
+                    if (st->h_last_cut == 0) st->h_last_cut = fn;
+                    if (above && (fn - st->h_last_cut) >= P.hist_min_scene_len) {
+                        emit_cut(st, cuts, 2, P.max_cuts, fn);
+                        st->h_last_cut = fn;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void fill_nan_kernel(double* p, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = __longlong_as_double(0x7ff8000000000000LL);
+}
+
+}  // namespace esd

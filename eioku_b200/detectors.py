@@ -1,0 +1,326 @@
+"""SceneDetector plugin surface (PySceneDetect's ContentDetector / AdaptiveDetector /
+HistogramDetector: same constructor keywords, ``process_frame`` / ``post_process`` /
+``get_metrics`` / ``event_buffer_length``), executed by libesd.so on a B200.
+
+The reference names this surface in /root/reference/README.md:56 and
+.kiro/specs/semantic-video-search/design.md:994-1007 and its ml-service would call it from
+``ModelManager.detect_scenes`` (ml-service/src/services/model_manager.py:715-835).
+
+Two ways to run a detector:
+  * stand-alone, frame by frame: ``det.process_frame(frame_num, frame_img)`` exactly like
+    PySceneDetect (frames arrive already downscaled; numpy or CUDA torch uint8 BGR);
+  * batched through :class:`eioku_b200.scene_manager.SceneManager`, which fuses the
+    SceneManager downscale into the scoring kernel and feeds all detectors from one pass.
+There is no CPU path: without libesd.so and a GPU these classes raise.
+"""
+from __future__ import annotations
+
+from enum import Enum
+from typing import Dict, List, NamedTuple, Optional
+
+import numpy as np
+
+from . import capi
+
+
+class FlashFilter:
+    """Namespace mirror of scenedetect.scene_detector.FlashFilter (only ``Mode`` is host-side;
+    the state machine itself runs on the device, csrc/esd_kernels.cuh:decide_kernel)."""
+
+    class Mode(Enum):
+        MERGE = 0
+        SUPPRESS = 1
+
+
+class StatsManager:
+    """Minimal stand-in for scenedetect.stats_manager.StatsManager: per-frame metric store."""
+
+    def __init__(self):
+        self._frame_metrics: Dict[int, Dict[str, float]] = {}
+        self._metric_keys: List[str] = []
+
+    def register_metrics(self, keys):
+        for k in keys:
+            if k not in self._metric_keys:
+                self._metric_keys.append(k)
+
+    def set_metrics(self, frame_number: int, metric_kv_dict: Dict[str, float]):
+        self._frame_metrics.setdefault(frame_number, {}).update(metric_kv_dict)
+        self.register_metrics(metric_kv_dict.keys())
+
+    def get_metrics(self, frame_number: int, metric_keys):
+        return [self._frame_metrics.get(frame_number, {}).get(k) for k in metric_keys]
+
+    def metrics_exist(self, frame_number: int, metric_keys) -> bool:
+        d = self._frame_metrics.get(frame_number, {})
+        return all(k in d for k in metric_keys)
+
+    @property
+    def metric_keys(self):
+        return list(self._metric_keys)
+
+    def save_to_csv(self, csv_file):
+        import csv
+
+        own = isinstance(csv_file, (str, bytes))
+        f = open(csv_file, "w", newline="") if own else csv_file
+        try:
+            wr = csv.writer(f, lineterminator="\n")
+            wr.writerow(["Frame Number"] + self._metric_keys)
+            for fn in sorted(self._frame_metrics):
+                row = self._frame_metrics[fn]
+                wr.writerow([fn + 1] + [("" if row.get(k) is None else repr(float(row[k]))) for k in self._metric_keys])
+        finally:
+            if own:
+                f.close()
+
+
+class SceneDetector:
+    """Base of the plugin surface (scenedetect.scene_detector.SceneDetector)."""
+
+    stats_manager: Optional[StatsManager] = None
+    _DET_FLAG = 0
+
+    def __init__(self):
+        self.stats_manager = None
+        self._ctx: Optional[capi.EsdContext] = None
+        self._cuts_seen = 0
+        self._device = 0
+
+    # ---- PySceneDetect API
+    def is_processing_required(self, frame_num: int) -> bool:
+        return True
+
+    def stats_manager_required(self) -> bool:
+        return False
+
+    def get_metrics(self) -> List[str]:
+        return []
+
+    def post_process(self, frame_num: int) -> List[int]:
+        return []
+
+    @property
+    def event_buffer_length(self) -> int:
+        return 0
+
+    # ---- config plumbing shared with SceneManager
+    def _fill_config(self, cfg: capi.EsdConfig) -> None:
+        raise NotImplementedError
+
+    def _metrics_for(self, scores: dict, k: int) -> Dict[str, float]:
+        return {}
+
+    def _make_ctx(self, width: int, height: int, device: int) -> capi.EsdContext:
+        cfg = capi.default_config()
+        cfg.detectors = 0
+        self._fill_config(cfg)
+        cfg.src_width, cfg.src_height = width, height
+        cfg.dst_width, cfg.dst_height = width, height  # stand-alone detectors never resize (SceneManager does)
+        return capi.EsdContext(cfg, device)
+
+    def _validate_frame(self, frame_img):
+        pass
+
+    def _to_device(self, frame_img):
+        import torch
+
+        if isinstance(frame_img, np.ndarray):
+            self._validate_frame(frame_img)
+            return torch.from_numpy(np.ascontiguousarray(frame_img)).to(f"cuda:{self._device}", non_blocking=False)
+        if not frame_img.is_cuda:
+            frame_img = frame_img.to(f"cuda:{self._device}")
+        self._validate_frame(frame_img)
+        return frame_img
+
+    def process_frames(self, first_frame_num: int, frames) -> List[int]:
+        """Batched process_frame: frames [N,H,W,3] uint8 BGR (numpy or CUDA tensor), already at detector
+        resolution.  Returns every cut the N frames produced, in emission order."""
+        t = self._to_device(frames)
+        if t.dim() == 3:
+            t = t.unsqueeze(0)
+        if self._ctx is None:
+            self._device = t.device.index
+            self._ctx = self._make_ctx(t.shape[2], t.shape[1], self._device)
+        self._ctx.push_tensor(t, first_frame_num)
+        cuts, total = self._ctx.get_cuts(self._DET_FLAG, self._cuts_seen)
+        self._cuts_seen = total
+        if self.stats_manager is not None:
+            n = t.shape[0]
+            sc = self._ctx.read_scores(first_frame_num, n)
+            for k in range(n):
+                m = self._metrics_for(sc, k)
+                if m:
+                    self.stats_manager.set_metrics(first_frame_num + k, m)
+            self._publish_late_metrics(first_frame_num, n)
+        return cuts
+
+    def _publish_late_metrics(self, first_frame_num: int, n: int):
+        pass
+
+    def process_frame(self, frame_num: int, frame_img) -> List[int]:
+        return self.process_frames(frame_num, frame_img)
+
+    def close(self):
+        if self._ctx is not None:
+            self._ctx.close()
+            self._ctx = None
+
+
+class ContentDetector(SceneDetector):
+    """scenedetect.detectors.ContentDetector: weighted mean |delta| of the H, S, V planes between
+    consecutive frames, cut when ``content_val >= threshold`` subject to the flash filter."""
+
+    class Components(NamedTuple):
+        delta_hue: float = 1.0
+        delta_sat: float = 1.0
+        delta_lum: float = 1.0
+        delta_edges: float = 0.0
+
+    DEFAULT_COMPONENT_WEIGHTS = Components()
+    LUMA_ONLY_WEIGHTS = Components(delta_hue=0.0, delta_sat=0.0, delta_lum=1.0, delta_edges=0.0)
+    FRAME_SCORE_KEY = "content_val"
+    METRIC_KEYS = [FRAME_SCORE_KEY, *Components._fields]
+    _DET_FLAG = capi.ESD_DET_CONTENT
+
+    def __init__(self, threshold: float = 27.0, min_scene_len: int = 15,
+                 weights: "ContentDetector.Components" = DEFAULT_COMPONENT_WEIGHTS, luma_only: bool = False,
+                 kernel_size: Optional[int] = None, filter_mode: FlashFilter.Mode = FlashFilter.Mode.MERGE):
+        super().__init__()
+        self._threshold = threshold
+        self._min_scene_len = min_scene_len
+        self._weights = ContentDetector.Components(*weights)
+        if luma_only:
+            self._weights = ContentDetector.LUMA_ONLY_WEIGHTS
+        if self._weights.delta_edges != 0.0:
+            raise NotImplementedError(
+                "delta_edges != 0 needs Canny+dilate, which is outside the B200 hot path (SURVEY.md section 8 a14)")
+        if kernel_size is not None and (kernel_size < 3 or kernel_size % 2 == 0):
+            raise ValueError("kernel_size must be odd integer >= 3")
+        self._kernel_size = kernel_size
+        self._filter_mode = FlashFilter.Mode(filter_mode) if not isinstance(filter_mode, FlashFilter.Mode) else filter_mode
+
+    def get_metrics(self):
+        return ContentDetector.METRIC_KEYS
+
+    def _weight_div(self) -> float:
+        # exactly PySceneDetect's divisor expression, evaluated by the host interpreter
+        return float(sum(abs(w) for w in self._weights))
+
+    def _fill_config(self, cfg):
+        cfg.detectors |= capi.ESD_DET_CONTENT
+        cfg.content_threshold = float(self._threshold)
+        for i, w in enumerate(self._weights):
+            cfg.content_weights[i] = float(w)
+        cfg.content_weight_div = self._weight_div()
+        cfg.content_min_scene_len = int(self._min_scene_len)
+        cfg.content_filter_mode = int(self._filter_mode.value)
+
+    def _metrics_for(self, scores, k):
+        npx = float(self._ctx.geometry.dst_width * self._ctx.geometry.dst_height) if self._ctx else 1.0
+        return _content_metrics(scores, k, "content_val", npx)
+
+
+def _content_metrics(scores, k, val_key, npx):
+    s = scores["sums3"][k]
+    return {
+        ContentDetector.FRAME_SCORE_KEY: float(scores[val_key][k]),
+        "delta_hue": float(np.int64(s[0]) / npx),
+        "delta_sat": float(np.int64(s[1]) / npx),
+        "delta_lum": float(np.int64(s[2]) / npx),
+    }
+
+
+class AdaptiveDetector(ContentDetector):
+    """scenedetect.detectors.AdaptiveDetector: rolling-window ratio of content_val."""
+
+    ADAPTIVE_RATIO_KEY_TEMPLATE = "adaptive_ratio{luma_only} (w={window_width})"
+    _DET_FLAG = capi.ESD_DET_ADAPTIVE
+
+    def __init__(self, adaptive_threshold: float = 3.0, min_scene_len: int = 15, window_width: int = 2,
+                 min_content_val: float = 15.0, weights: ContentDetector.Components = ContentDetector.DEFAULT_COMPONENT_WEIGHTS,
+                 luma_only: bool = False, kernel_size: Optional[int] = None, video_manager=None,
+                 min_delta_hsv: Optional[float] = None):
+        if min_delta_hsv is not None:
+            min_content_val = min_delta_hsv
+        if window_width < 1:
+            raise ValueError("window_width must be at least 1.")
+        super().__init__(threshold=255.0, min_scene_len=0, weights=weights, luma_only=luma_only, kernel_size=kernel_size)
+        self.min_scene_len = min_scene_len
+        self.adaptive_threshold = adaptive_threshold
+        self.min_content_val = min_content_val
+        self.window_width = window_width
+        self._adaptive_ratio_key = AdaptiveDetector.ADAPTIVE_RATIO_KEY_TEMPLATE.format(
+            window_width=window_width, luma_only="" if not luma_only else "_lum")
+
+    @property
+    def event_buffer_length(self) -> int:
+        return self.window_width
+
+    def get_metrics(self):
+        return super().get_metrics() + [self._adaptive_ratio_key]
+
+    def _fill_config(self, cfg):
+        cfg.detectors |= capi.ESD_DET_ADAPTIVE
+        cfg.adaptive_threshold = float(self.adaptive_threshold)
+        cfg.adaptive_min_content_val = float(self.min_content_val)
+        for i, w in enumerate(self._weights):
+            cfg.adaptive_weights[i] = float(w)
+        cfg.adaptive_weight_div = self._weight_div()
+        cfg.adaptive_window_width = int(self.window_width)
+        cfg.adaptive_min_scene_len = int(self.min_scene_len)
+
+    def _metrics_for(self, scores, k):
+        npx = float(self._ctx.geometry.dst_width * self._ctx.geometry.dst_height) if self._ctx else 1.0
+        return _content_metrics(scores, k, "adaptive_val", npx)
+
+    def _publish_late_metrics(self, first_frame_num, n):
+        # the ratio of frame t becomes known once frame t + window_width has been processed
+        w = self.window_width
+        first_video_frame = first_frame_num + n - self._ctx.frames_pushed
+        lo = max(first_frame_num - w, first_video_frame)
+        cnt = first_frame_num + n - lo
+        sc = self._ctx.read_scores(lo, cnt, ["adaptive_ratio"])
+        for k in range(cnt):
+            r = sc["adaptive_ratio"][k]
+            if r == r:
+                self.stats_manager.set_metrics(lo + k, {self._adaptive_ratio_key: float(r)})
+
+
+class HistogramDetector(SceneDetector):
+    """scenedetect.detectors.HistogramDetector: correlation of consecutive normalised Y histograms."""
+
+    METRIC_KEYS = ["hist_diff"]
+    _DET_FLAG = capi.ESD_DET_HIST
+
+    def __init__(self, threshold: float = 0.05, bins: int = 256, min_scene_len: int = 15):
+        super().__init__()
+        self._user_threshold = threshold
+        # PySceneDetect keeps the correlation-space threshold; the library applies the same clamp
+        self._threshold = max(0.0, min(1.0, 1.0 - threshold))
+        self._bins = bins
+        self._min_scene_len = min_scene_len
+        self._metric_keys = [f"hist_diff [bins={self._bins}]"]
+
+    def get_metrics(self):
+        return self._metric_keys
+
+    def is_processing_required(self, frame_num: int) -> bool:
+        return True
+
+    def _validate_frame(self, frame_img):
+        dt = str(frame_img.dtype)
+        if not dt.endswith("uint8"):
+            raise ValueError("Image must be 8-bit rgb for HistogramDetector")
+        if frame_img.shape[-1] != 3:
+            raise ValueError("Image must have three color channels for HistogramDetector")
+
+    def _fill_config(self, cfg):
+        cfg.detectors |= capi.ESD_DET_HIST
+        cfg.hist_threshold = float(self._user_threshold)
+        cfg.hist_bins = int(self._bins)
+        cfg.hist_min_scene_len = int(self._min_scene_len)
+
+    def _metrics_for(self, scores, k):
+        d = scores["hist_diff"][k]
+        return {self._metric_keys[0]: float(d)} if d == d else {}

@@ -1,0 +1,189 @@
+/* esd.h -- C ABI of libesd.so: B200-native scene-detection scoring.
+ *
+ * The reference (codihuston/eioku) is pure Python and has NO FFI for this path; its
+ * scene task is `ModelManager.detect_scenes(video_path, config)`
+ * (/root/reference/ml-service/src/services/model_manager.py:715-835), specified to run
+ * PySceneDetect's ContentDetector / AdaptiveDetector / HistogramDetector
+ * (/root/reference/README.md:56, .kiro/specs/semantic-video-search/design.md:994-1007;
+ * producer "scenedetect", ml-service/src/models/responses.py:141-142).  This ABI is
+ * therefore defined by what a Python `ctypes` binding needs to implement the
+ * SceneDetector plugin surface (process_frame / post_process) and the scene-task
+ * schema on top of device-resident uint8 BGR frames.
+ *
+ * Conventions
+ *  - plain C, POD only; every function returns ESD_OK (0) or a negative esd_status,
+ *    never throws/aborts; esd_last_error() gives the detail string of the last failure.
+ *  - the caller owns frame memory and every output buffer; the library owns scratch,
+ *    tables, score arrays, cut lists and the pinned ingest ring.
+ *  - one ctx per (device, video stream); not thread-safe; no global state.
+ *  - work is enqueued on the caller's CUDA stream (`void* stream` = cudaStream_t);
+ *    only esd_read_scores / esd_get_cuts / esd_synchronize / esd_kernel_time wait.
+ *  - there is NO CPU fallback: without a CUDA device every entry point fails.
+ */
+#ifndef ESD_H
+#define ESD_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ESD_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define ESD_API __attribute__((visibility("default")))
+#else
+#define ESD_API
+#endif
+
+typedef struct esd_ctx esd_ctx;
+
+typedef enum esd_status {
+    ESD_OK = 0,
+    ESD_ERR_INVALID = -1,     /* bad argument / config */
+    ESD_ERR_CUDA = -2,        /* a CUDA runtime call failed (see esd_last_error) */
+    ESD_ERR_NOMEM = -3,
+    ESD_ERR_STATE = -4,       /* call out of order (e.g. non-sequential frame numbers) */
+    ESD_ERR_UNSUPPORTED = -5, /* e.g. delta_edges weight != 0, dst width > 4096 */
+    ESD_ERR_CAPACITY = -6     /* caller buffer or cut list too small */
+} esd_status;
+
+/* detector bitmask: which decision passes (and therefore which per-frame features) run */
+enum { ESD_DET_CONTENT = 1, ESD_DET_ADAPTIVE = 2, ESD_DET_HIST = 4 };
+/* FlashFilter.Mode of PySceneDetect >= 0.6.4; SUPPRESS == the legacy (<= 0.6.3) min_scene_len rule */
+enum { ESD_FILTER_MERGE = 0, ESD_FILTER_SUPPRESS = 1 };
+/* compute_downscale_factor: W/256.0 (>= 0.6.2) or W//256 (<= 0.6.1) */
+enum { ESD_DOWNSCALE_FLOAT = 0, ESD_DOWNSCALE_INT = 1 };
+/* work decomposition of the fused kernel (tuning; results are identical) */
+enum { ESD_SPLIT_AUTO = 0, ESD_SPLIT_STRIPS = 1, ESD_SPLIT_CHUNKS = 2 };
+
+typedef struct esd_config {
+    uint32_t struct_size;      /* = sizeof(esd_config) */
+    int32_t detectors;         /* ESD_DET_* bitmask, != 0 */
+    int32_t src_width;         /* frame geometry handed to esd_push_frames */
+    int32_t src_height;
+    int32_t dst_width;         /* SceneManager resize target; 0,0 = auto (downscale_mode); == src = no resize */
+    int32_t dst_height;
+    int32_t downscale_mode;    /* ESD_DOWNSCALE_*; used when dst_* == 0 */
+    int32_t reserved0;
+
+    /* ContentDetector(threshold, min_scene_len, weights, filter_mode); luma_only = weights {0,0,1,0} */
+    double content_threshold;
+    double content_weights[4]; /* delta_hue, delta_sat, delta_lum, delta_edges (must be 0) */
+    double content_weight_div; /* sum(abs(w)) as the host language computes it; <= 0 -> naive left-to-right */
+    int32_t content_min_scene_len;
+    int32_t content_filter_mode;
+
+    /* AdaptiveDetector(adaptive_threshold, min_scene_len, window_width, min_content_val, weights) */
+    double adaptive_threshold;
+    double adaptive_min_content_val;
+    double adaptive_weights[4];
+    double adaptive_weight_div;
+    int32_t adaptive_window_width;
+    int32_t adaptive_min_scene_len;
+
+    /* HistogramDetector(threshold, bins, min_scene_len) */
+    double hist_threshold;     /* user threshold; the library applies clamp(1 - t, 0, 1) */
+    int32_t hist_bins;         /* 1..256 */
+    int32_t hist_min_scene_len;
+
+    /* tuning knobs, 0 = auto */
+    int32_t rows_per_group;    /* destination rows one CTA keeps on-chip per frame */
+    int32_t pipeline_stages;   /* TMA ring depth per CTA */
+    int32_t split_mode;        /* ESD_SPLIT_* */
+    int32_t ctas_per_sm;
+    int64_t max_cuts;          /* per-detector cut capacity (default 65536) */
+    int64_t initial_capacity;  /* frames of per-frame score storage to pre-allocate (grows by doubling) */
+} esd_config;
+
+/* derived geometry, for the caller's roofline accounting and ingest sizing */
+typedef struct esd_geometry {
+    int32_t dst_width, dst_height;
+    int32_t n_touched_rows;      /* distinct source rows the vertical taps read */
+    int32_t row_bytes;           /* src_width * 3 */
+    int64_t alg_bytes_per_frame; /* n_touched_rows * row_bytes: algorithmic HBM bytes per frame */
+    int64_t compact_frame_bytes; /* size of one frame in the compact (touched rows only) layout */
+} esd_geometry;
+
+ESD_API int esd_abi_version(void);
+ESD_API const char* esd_strerror(int status);
+/* detail of the last failure on this ctx (or of the last esd_create failure when ctx == NULL) */
+ESD_API const char* esd_last_error(const esd_ctx* ctx);
+ESD_API int esd_device_count(void);
+
+ESD_API void esd_config_default(esd_config* cfg); /* PySceneDetect defaults; detectors = CONTENT */
+ESD_API int esd_create(esd_ctx** out, const esd_config* cfg, int device);
+ESD_API void esd_destroy(esd_ctx* ctx);
+/* forget all frames, scores, cuts and filter state (start of a new video) */
+ESD_API int esd_reset(esd_ctx* ctx);
+ESD_API int esd_get_geometry(const esd_ctx* ctx, esd_geometry* out);
+/* touched source rows in ascending order (n_touched_rows entries) */
+ESD_API int esd_get_touched_rows(const esd_ctx* ctx, int32_t* rows, int32_t cap);
+
+/* Score n device-resident frames (uint8 BGR, row pitch `pitch_bytes`, frame stride
+ * `frame_stride_bytes`) and run the decision passes.  Frame numbers must be sequential
+ * across calls: first_frame_num == (first frame of the first push) + frames pushed so far.
+ * Asynchronous on `stream`. */
+ESD_API int esd_push_frames(esd_ctx* ctx, const uint8_t* d_bgr, int64_t n, int64_t frame_stride_bytes,
+                    int64_t pitch_bytes, int64_t first_frame_num, void* stream);
+/* Same, for frames stored in the compact layout [n][n_touched_rows][row_bytes] (touched rows only,
+ * ascending source-row order) that the ingest ring produces. */
+ESD_API int esd_push_rows(esd_ctx* ctx, const uint8_t* d_rows, int64_t n, int64_t first_frame_num, void* stream);
+
+/* Host frames -> pinned ring -> cudaMemcpyAsync on a copy stream -> scoring on the ctx's own
+ * compute stream.  Only the touched source rows cross PCIe.  h_bgr may be pageable (staged through
+ * the ring by the CPU) or pinned (DMA'd directly). */
+ESD_API int esd_ingest_open(esd_ctx* ctx, int32_t n_slots, int32_t frames_per_slot);
+ESD_API int esd_ingest_push_host(esd_ctx* ctx, const uint8_t* h_bgr, int64_t n, int64_t frame_stride_bytes,
+                         int64_t pitch_bytes, int64_t first_frame_num);
+ESD_API int esd_ingest_close(esd_ctx* ctx);
+/* bytes moved host->device by the ingest path since esd_reset */
+ESD_API int esd_ingest_stats(const esd_ctx* ctx, int64_t* h2d_bytes, int64_t* h2d_copies);
+
+/* Wait for all enqueued work of this ctx. */
+ESD_API int esd_synchronize(esd_ctx* ctx);
+ESD_API int64_t esd_frames_pushed(const esd_ctx* ctx);
+
+/* Per-frame results for frames [from_frame, from_frame + n) (absolute frame numbers).  Any output
+ * pointer may be NULL.  sums3: [n][3] sum|dH|,sum|dS|,sum|dV| (0 for the first frame of the video);
+ * content_val / adaptive_val: float64 score with the content / adaptive weights; adaptive_ratio: NaN
+ * where the window is incomplete; hist: [n][bins] Y-histogram counts; hist_diff: NaN for the first frame.
+ * Synchronises. */
+ESD_API int esd_read_scores(esd_ctx* ctx, int64_t from_frame, int64_t n, uint64_t* sums3, double* content_val,
+                    double* adaptive_val, double* adaptive_ratio, uint32_t* hist, double* hist_diff);
+
+/* Cuts emitted so far by one detector (ESD_DET_*), starting at index `from_index` of its cut list.
+ * *n_total receives the total number of cuts the detector has emitted.  Synchronises. */
+ESD_API int esd_get_cuts(esd_ctx* ctx, int32_t detector, int64_t from_index, int64_t* cuts, int64_t cap,
+                 int64_t* n_written, int64_t* n_total);
+
+/* Stand-alone decision pass over score arrays already on the host (merge step of frame-range
+ * sharding: shards return scores, one global pass decides).  Uses the ctx's detector parameters but
+ * none of its frame state.  For ESD_DET_ADAPTIVE `scores` = adaptive_val (ratios are recomputed);
+ * ESD_DET_CONTENT: content_val; ESD_DET_HIST: hist_diff (NaN = no previous frame). */
+ESD_API int esd_decide_arrays(esd_ctx* ctx, int32_t detector, int64_t first_frame_num, int64_t n,
+                      const double* scores, double* adaptive_ratio_out, int64_t* cuts, int64_t cap,
+                      int64_t* n_cuts);
+
+/* Instrumentation: CUDA-event timing of the fused scoring kernel on the launching stream. */
+ESD_API int esd_set_timing(esd_ctx* ctx, int32_t enable);
+/* total fused-kernel milliseconds and launch count since the last call (synchronises) */
+ESD_API int esd_kernel_time(esd_ctx* ctx, double* fused_ms, int64_t* fused_launches);
+/* every kernel the library launched on this ctx since esd_create */
+ESD_API int64_t esd_kernel_launches(const esd_ctx* ctx);
+
+/* Test hook: packed H | S<<8 | V<<16 of the last pushed frame at detector resolution
+ * ([dst_height][dst_width] uint32), i.e. the on-device twin of cvtColor(resize(frame)).  Synchronises. */
+ESD_API int esd_debug_read_prev(esd_ctx* ctx, uint32_t* out, int64_t cap_elems);
+
+/* Synthetic clip filler (benchmark/test input, csrc/synth_core.h): writes n frames of WxHx3 BGR
+ * described by host descriptors `descs` (int32[n][8]) into device memory. */
+ESD_API int esd_synth_fill(uint8_t* d_out, int32_t width, int32_t height, int64_t pitch_bytes,
+                   int64_t frame_stride_bytes, uint32_t seed, const int32_t* descs, int64_t n,
+                   int device, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ESD_H */
