@@ -218,6 +218,7 @@ def bench_ours(args):
     for _ in range(args.steps):
         ctx.push_tensor(clip, pos, stream)
         pos += NB
+    ctx.join(stream)  # the last batch's finalize/decision tail is part of the step
     e1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None

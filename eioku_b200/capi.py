@@ -21,7 +21,7 @@ EXPORTED_SYMBOLS = (
     "esd_abi_version", "esd_strerror", "esd_last_error", "esd_device_count", "esd_config_default",
     "esd_create", "esd_destroy", "esd_reset", "esd_get_geometry", "esd_get_touched_rows",
     "esd_push_frames", "esd_push_rows", "esd_ingest_open", "esd_ingest_push_host", "esd_ingest_close",
-    "esd_ingest_stats", "esd_synchronize", "esd_frames_pushed", "esd_read_scores", "esd_get_cuts",
+    "esd_ingest_stats", "esd_synchronize", "esd_join", "esd_frames_pushed", "esd_read_scores", "esd_get_cuts",
     "esd_decide_arrays", "esd_debug_read_prev", "esd_set_timing", "esd_kernel_time", "esd_kernel_launches", "esd_synth_fill",
 )
 
@@ -95,6 +95,7 @@ def load_library(path: Optional[str] = None):
     L.esd_ingest_close.argtypes = [vp]
     L.esd_ingest_stats.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
     L.esd_synchronize.argtypes = [vp]
+    L.esd_join.argtypes = [vp, vp]
     L.esd_frames_pushed.restype = i64
     L.esd_frames_pushed.argtypes = [vp]
     L.esd_read_scores.argtypes = [vp, i64, i64, vp, vp, vp, vp, vp, vp]
@@ -242,6 +243,10 @@ class EsdContext:
     # -- results
     def synchronize(self):
         self._check(self._L.esd_synchronize(self._h), "esd_synchronize")
+
+    def join(self, stream: int = 0):
+        """Make `stream` wait for the finalize/decision tails enqueued so far (device-side)."""
+        self._check(self._L.esd_join(self._h, C.c_void_p(stream)), "esd_join")
 
     @property
     def frames_pushed(self) -> int:

@@ -88,14 +88,20 @@ struct esd_ctx {
 
     // per-batch scratch
     int64_t part_cap_frames = 0;
-    uint4* d_part = nullptr;
-    uint16_t* d_hist_part = nullptr;
+    uint4* d_part[2] = {nullptr, nullptr};          // double-buffered: the tail of push k overlaps push k+1
+    uint16_t* d_hist_part[2] = {nullptr, nullptr};
+    int part_buf = 0;
     std::map<int64_t, UnitPlan> plans;
 
     // streams / timing
     cudaStream_t last_stream = nullptr;
     bool have_last_stream = false;
     cudaEvent_t order_event = nullptr;
+    // finalize + decision kernels run on a library-owned stream so they overlap the next batch's fused kernel
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t ev_fused = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_fin[2] = {nullptr, nullptr};
+    bool fin_recorded[2] = {false, false};
     bool timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing_events;
     int64_t launches = 0;
@@ -128,6 +134,13 @@ int fail(esd_ctx* c, int code, const char* fmt, ...) {
             return fail((c), ESD_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, \
                         __LINE__);                                                                    \
     } while (0)
+
+int sync_all(esd_ctx* c) {
+    if (c->copy_stream) CU(c, cudaStreamSynchronize(c->copy_stream));
+    if (c->have_last_stream) CU(c, cudaStreamSynchronize(c->last_stream));
+    if (c->aux_stream) CU(c, cudaStreamSynchronize(c->aux_stream));
+    return ESD_OK;
+}
 
 // OpenCV resize.cpp INTER_LINEAR coefficient setup: float32 fraction from a double
 // scale, cvRound (half-even) to 11-bit fixed point.
@@ -279,7 +292,7 @@ int grow_array(esd_ctx* c, T** p, int64_t old_elems, int64_t new_elems) {
 int ensure_capacity(esd_ctx* c, int64_t frames_needed) {
     if (frames_needed <= c->cap) return ESD_OK;
     int64_t ncap = std::max<int64_t>(c->cap ? c->cap * 2 : std::max<int64_t>(4096, c->cfg.initial_capacity), frames_needed);
-    if (c->have_last_stream) CU(c, cudaStreamSynchronize(c->last_stream));
+    { int rc0 = sync_all(c); if (rc0) return rc0; }
     int rc;
     const int64_t used = c->n_frames;
     if ((rc = grow_array(c, &c->d_sums3, used * 3, ncap * 3))) return rc;
@@ -299,14 +312,17 @@ int ensure_capacity(esd_ctx* c, int64_t frames_needed) {
 
 int ensure_scratch(esd_ctx* c, int64_t n) {
     if (n <= c->part_cap_frames) return ESD_OK;
-    if (c->have_last_stream) CU(c, cudaStreamSynchronize(c->last_stream));
-    cudaFree(c->d_part);
-    cudaFree(c->d_hist_part);
-    c->d_part = nullptr;
-    c->d_hist_part = nullptr;
+    { int rc0 = sync_all(c); if (rc0) return rc0; }
     c->part_cap_frames = 0;
-    if (c->need_content) CU(c, cudaMalloc(&c->d_part, sizeof(uint4) * n * c->n_groups * kConsumerWarps));
-    if (c->need_hist) CU(c, cudaMalloc(&c->d_hist_part, sizeof(uint16_t) * n * c->n_groups * c->cfg.hist_bins));
+    for (int b = 0; b < 2; ++b) {
+        cudaFree(c->d_part[b]);
+        cudaFree(c->d_hist_part[b]);
+        c->d_part[b] = nullptr;
+        c->d_hist_part[b] = nullptr;
+        c->fin_recorded[b] = false;
+        if (c->need_content) CU(c, cudaMalloc(&c->d_part[b], sizeof(uint4) * n * c->n_groups * kConsumerWarps));
+        if (c->need_hist) CU(c, cudaMalloc(&c->d_hist_part[b], sizeof(uint16_t) * n * c->n_groups * c->cfg.hist_bins));
+    }
     c->part_cap_frames = n;
     return ESD_OK;
 }
@@ -387,8 +403,12 @@ int push_common(esd_ctx* c, const uint8_t* d_src, int64_t n, int64_t frame_strid
     p.cta_unit_begin = plan.d_begin;
     p.prev_in = c->d_prev[c->prev_parity];
     p.prev_out = c->d_prev[c->prev_parity ^ 1];
-    p.part = c->d_part;
-    p.hist_part = c->d_hist_part;
+    const int buf = c->part_buf;
+    c->part_buf ^= 1;
+    p.part = c->d_part[buf];
+    p.hist_part = c->d_hist_part[buf];
+    // the fused kernel overwrites part[buf]: wait until the tail of the push that last used it is done
+    if (c->fin_recorded[buf]) CU(c, cudaStreamWaitEvent(st, c->ev_fin[buf], 0));
 
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (c->timing) {
@@ -403,12 +423,16 @@ int push_common(esd_ctx* c, const uint8_t* d_src, int64_t n, int64_t frame_strid
         c->timing_events.emplace_back(e0, e1);
     }
     c->prev_parity ^= 1;
+    // tail (finalize + decision) on the library's own stream, ordered after this fused kernel
+    cudaStream_t ts = c->aux_stream;
+    CU(c, cudaEventRecord(c->ev_fused, st));
+    CU(c, cudaStreamWaitEvent(ts, c->ev_fused, 0));
 
     const double npx = (double)c->dst_w * (double)c->dst_h;  // float(rows * cols)
     if (c->need_content) {
         const int warps_per_block = 8;
-        finalize_sums_kernel<<<(unsigned)((n + warps_per_block - 1) / warps_per_block), warps_per_block * 32, 0, st>>>(
-            c->d_part, (int)n, c->n_groups * kConsumerWarps, npx, c->wc, c->wa, c->d_sums3 + 3 * base, c->d_cv + base,
+        finalize_sums_kernel<<<(unsigned)((n + warps_per_block - 1) / warps_per_block), warps_per_block * 32, 0, ts>>>(
+            c->d_part[buf], (int)n, c->n_groups * kConsumerWarps, npx, c->wc, c->wa, c->d_sums3 + 3 * base, c->d_cv + base,
             c->d_av + base);
         CU(c, cudaGetLastError());
         c->launches++;
@@ -416,7 +440,7 @@ int push_common(esd_ctx* c, const uint8_t* d_src, int64_t n, int64_t frame_strid
             const int w = c->cfg.adaptive_window_width;
             const int64_t t0 = std::max<int64_t>(w, base - w), t1 = base + n - w;
             if (t1 > t0) {
-                adaptive_ratio_kernel<<<(unsigned)((t1 - t0 + 255) / 256), 256, 0, st>>>(
+                adaptive_ratio_kernel<<<(unsigned)((t1 - t0 + 255) / 256), 256, 0, ts>>>(
                     c->d_av, c->d_ratio, t0, t1, w, c->cfg.adaptive_min_content_val);
                 CU(c, cudaGetLastError());
                 c->launches++;
@@ -425,17 +449,19 @@ int push_common(esd_ctx* c, const uint8_t* d_src, int64_t n, int64_t frame_strid
     }
     if (c->need_hist) {
         const int bins = c->cfg.hist_bins;
-        finalize_hist_counts_kernel<<<(unsigned)n, 256, 0, st>>>(c->d_hist_part, c->n_groups, bins,
+        finalize_hist_counts_kernel<<<(unsigned)n, 256, 0, ts>>>(c->d_hist_part[buf], c->n_groups, bins,
                                                                  c->d_counts + base * bins);
         CU(c, cudaGetLastError());
-        hist_diff_kernel<<<(unsigned)n, 256, 0, st>>>(c->d_counts + base * bins, bins, base > 0 ? 1 : 0,
+        hist_diff_kernel<<<(unsigned)n, 256, 0, ts>>>(c->d_counts + base * bins, bins, base > 0 ? 1 : 0,
                                                       c->d_hdiff + base);
         CU(c, cudaGetLastError());
         c->launches += 2;
     }
-    decide_kernel<<<3, 256, 0, st>>>(c->dparams, c->d_state, c->d_cuts, c->d_cv, c->d_av, c->d_ratio, c->d_hdiff,
+    decide_kernel<<<3, 256, 0, ts>>>(c->dparams, c->d_state, c->d_cuts, c->d_cv, c->d_av, c->d_ratio, c->d_hdiff,
                                      c->first_frame, base, base + n);
     CU(c, cudaGetLastError());
+    CU(c, cudaEventRecord(c->ev_fin[buf], ts));
+    c->fin_recorded[buf] = true;
     c->launches++;
     c->n_frames += n;
     return ESD_OK;
@@ -629,7 +655,9 @@ int esd_create(esd_ctx** out, const esd_config* cfg, int device) {
     // ---- kernel shape
     c->rowbuf = ((c->row_bytes + 15 + 15) & ~15) + 16;
     c->stage_bytes = (c->resize ? 2 : 1) * c->rowbuf;
-    int R = cfg->rows_per_group > 0 ? cfg->rows_per_group : 4;
+    // rows per group: 16 measured best at 1080p->256x144 (profiles/r01_sweep.md); the previous-frame HSV of
+    // a group lives in shared memory (R * pxt KB), keep it <= 32 KB unless the caller insists
+    int R = cfg->rows_per_group > 0 ? cfg->rows_per_group : std::max(1, std::min(16, 32 / c->pxt));
     R = std::min(R, dh);
     R = std::min(R, 255);
     while (R > 1 && ((int64_t)R * c->pxt > 256 || (int64_t)R * dw > 65535)) --R;
@@ -681,6 +709,11 @@ int esd_create(esd_ctx** out, const esd_config* cfg, int device) {
         CUB(cudaMalloc(&c->d_prev[1], sizeof(uint32_t) * dw * dh));
     }
     CUB(cudaEventCreateWithFlags(&c->order_event, cudaEventDisableTiming));
+    CUB(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+    CUB(cudaEventCreateWithFlags(&c->ev_fused, cudaEventDisableTiming));
+    CUB(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    CUB(cudaEventCreateWithFlags(&c->ev_fin[0], cudaEventDisableTiming));
+    CUB(cudaEventCreateWithFlags(&c->ev_fin[1], cudaEventDisableTiming));
     if (reset_video_state(c) != ESD_OK) return bail(ESD_ERR_CUDA);
 #undef CUB
     *out = c;
@@ -697,8 +730,12 @@ void esd_destroy(esd_ctx* c) {
     cudaFree(c->d_yrows); cudaFree(c->d_xtab); cudaFree(c->d_sdiv); cudaFree(c->d_hdiv);
     cudaFree(c->d_prev[0]); cudaFree(c->d_prev[1]); cudaFree(c->d_state); cudaFree(c->d_cuts);
     cudaFree(c->d_sums3); cudaFree(c->d_cv); cudaFree(c->d_av); cudaFree(c->d_ratio); cudaFree(c->d_hdiff);
-    cudaFree(c->d_counts); cudaFree(c->d_part); cudaFree(c->d_hist_part);
+    cudaFree(c->d_counts);
+    for (int b = 0; b < 2; ++b) { cudaFree(c->d_part[b]); cudaFree(c->d_hist_part[b]); if (c->ev_fin[b]) cudaEventDestroy(c->ev_fin[b]); }
     if (c->order_event) cudaEventDestroy(c->order_event);
+    if (c->ev_fused) cudaEventDestroy(c->ev_fused);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
     cudaGetLastError();
     delete c;
 }
@@ -852,8 +889,14 @@ int esd_ingest_stats(const esd_ctx* c, int64_t* bytes, int64_t* copies) {
 int esd_synchronize(esd_ctx* c) {
     if (!c) return ESD_ERR_INVALID;
     CU(c, cudaSetDevice(c->device));
-    if (c->copy_stream) CU(c, cudaStreamSynchronize(c->copy_stream));
-    if (c->have_last_stream) CU(c, cudaStreamSynchronize(c->last_stream));
+    return sync_all(c);
+}
+
+int esd_join(esd_ctx* c, void* stream) {
+    if (!c) return ESD_ERR_INVALID;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaEventRecord(c->ev_join, c->aux_stream));
+    CU(c, cudaStreamWaitEvent((cudaStream_t)stream, c->ev_join, 0));
     return ESD_OK;
 }
 

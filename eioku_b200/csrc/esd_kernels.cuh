@@ -524,25 +524,50 @@ struct DecisionParams {
     long long max_cuts;
 };
 
-__device__ __forceinline__ void emit_cut(DecisionState* st, long long* cuts, int det, long long max_cuts, long long v) {
-    const long long n = st->n_cuts[det];
-    if (n < max_cuts) cuts[(size_t)det * max_cuts + n] = v;
-    else st->overflow = 1;
-    st->n_cuts[det] = n + 1;
-}
+struct CutSink {
+    long long* cuts;
+    long long n, max_cuts;
+    int overflow;
+    __device__ __forceinline__ void emit(long long v) {
+        if (n < max_cuts) cuts[n] = v;
+        else overflow = 1;
+        ++n;
+    }
+};
 
 // grid = 3 blocks (content, adaptive, hist); frames [i_begin, i_end) are indices from first_frame_num.
 // The threshold tests run in parallel into a shared bitmask; one thread then walks the sequential
-// FlashFilter / min_scene_len state machine (A.5-A.7).
+// FlashFilter / min_scene_len state machine (A.5-A.7) with its state in registers, visiting only
+// frames that can change it (set bits, or every frame while a MERGE burst is open).
 __global__ void decide_kernel(DecisionParams P, DecisionState* __restrict__ st, long long* __restrict__ cuts,
                               const double* __restrict__ content_val, const double* __restrict__ adaptive_val,
                               const double* __restrict__ adaptive_ratio, const double* __restrict__ hist_diff,
                               long long first_frame_num, long long i_begin, long long i_end) {
-    constexpr int CH = 4096;
+    constexpr int CH = 8192;
     __shared__ uint32_t bits[CH / 32];
     const int det = blockIdx.x;
-    if (!(P.detectors & (1 << det))) return;
+    if (!(P.detectors & (1 << det)) || i_end <= i_begin) return;
     const int tid = threadIdx.x;
+
+    // thread 0's register copy of this detector's state
+    CutSink sink{cuts + (size_t)det * P.max_cuts, 0, P.max_cuts, 0};
+    long long last = 0, merge_start = 0;
+    int init = 0, merge_enabled = 0, merge_triggered = 0;
+    if (tid == 0) {
+        sink.n = st->n_cuts[det];
+        if (det == 0) {
+            last = st->c_last_above; merge_start = st->c_merge_start; init = st->c_init;
+            merge_enabled = st->c_merge_enabled; merge_triggered = st->c_merge_triggered;
+            if (!init && P.content_min_scene_len > 0) { init = 1; last = first_frame_num + i_begin; }
+        } else if (det == 1) {
+            last = st->a_last_cut; init = st->a_init;
+            if (!init) { init = 1; last = first_frame_num + i_begin; }
+        } else {
+            last = st->h_last_cut;
+        }
+    }
+    const int L = det == 0 ? P.content_min_scene_len : det == 1 ? P.adaptive_min_scene_len : P.hist_min_scene_len;
+
     for (long long c0 = i_begin; c0 < i_end; c0 += CH) {
         const long long c1 = (c0 + CH < i_end) ? c0 + CH : i_end;
         for (int j = tid; j < CH; j += blockDim.x) {
@@ -561,50 +586,81 @@ __global__ void decide_kernel(DecisionParams P, DecisionState* __restrict__ st, 
         }
         __syncthreads();
         if (tid == 0) {
-            for (long long i = c0; i < c1; ++i) {
-                const int j = (int)(i - c0);
-                const bool above = (bits[j >> 5] >> (j & 31)) & 1u;
-                const long long fn = first_frame_num + i;
-                if (det == 0) {
-                    const int L = P.content_min_scene_len;
-                    if (!(L > 0)) {
-                        if (above) emit_cut(st, cuts, 0, P.max_cuts, fn);
-                        continue;
+            const int nj = (int)(c1 - c0);
+            int j = 0;
+            while (j < nj) {
+                if (det == 0 && merge_triggered) {
+                    // Open MERGE burst: nothing changes between above-threshold frames, and the burst closes at
+                    // the first below-threshold frame fstar = last + L once (last - merge_start) >= L.
+                    int ja = j;
+                    while (ja < nj) {
+                        const uint32_t word = bits[ja >> 5] >> (ja & 31);
+                        if (word) { ja += __ffs(word) - 1; break; }
+                        ja = (ja | 31) + 1;
                     }
-                    if (!st->c_init) { st->c_init = 1; st->c_last_above = fn; }
-                    const bool met = (fn - st->c_last_above) >= L;
-                    if (P.content_filter_mode == 1) {  // SUPPRESS
-                        if (above && met) { st->c_last_above = fn; emit_cut(st, cuts, 0, P.max_cuts, fn); }
-                        continue;
-                    }
-                    if (above) st->c_last_above = fn;
-                    if (st->c_merge_triggered) {
-                        const long long merged = st->c_last_above - st->c_merge_start;
-                        if (met && !above && merged >= L) {
-                            st->c_merge_triggered = 0;
-                            emit_cut(st, cuts, 0, P.max_cuts, st->c_last_above);
+                    if (ja > nj) ja = nj;
+                    const long long fn_a = first_frame_num + c0 + ja;  // next above frame (or end of chunk)
+                    if ((last - merge_start) >= L) {
+                        const long long fn_j = first_frame_num + c0 + j;
+                        const long long fstar = (last + L > fn_j) ? last + L : fn_j;
+                        if (fstar < fn_a) {
+                            merge_triggered = 0;
+                            sink.emit(last);
+                            j = (int)(fstar - first_frame_num - c0) + 1;
+                            continue;
                         }
+                    }
+                    if (ja >= nj) break;
+                    last = fn_a;  // above frame inside the burst only advances last_above
+                    j = ja + 1;
+                    continue;
+                }
+                const bool every_frame = (det == 2 && last == 0);
+                if (!every_frame) {  // jump to the next frame whose test is true
+                    uint32_t word = bits[j >> 5] >> (j & 31);
+                    if (word == 0) { j = (j | 31) + 1; continue; }
+                    j += __ffs(word) - 1;
+                    if (j >= nj) break;
+                }
+                const bool above = (bits[j >> 5] >> (j & 31)) & 1u;
+                const long long fn = first_frame_num + c0 + j;
+                ++j;
+                if (det == 0) {
+                    if (!(L > 0)) { if (above) sink.emit(fn); continue; }
+                    const bool met = (fn - last) >= L;
+                    if (P.content_filter_mode == 1) {  // SUPPRESS (legacy min_scene_len)
+                        if (above && met) { last = fn; sink.emit(fn); }
+                        continue;
+                    }
+                    if (above) last = fn;
+                    if (merge_triggered) {
+                        if (met && !above && (last - merge_start) >= L) { merge_triggered = 0; sink.emit(last); }
                         continue;
                     }
                     if (!above) continue;
-                    if (met) { st->c_merge_enabled = 1; emit_cut(st, cuts, 0, P.max_cuts, fn); continue; }
-                    if (st->c_merge_enabled) { st->c_merge_triggered = 1; st->c_merge_start = fn; }
+                    if (met) { merge_enabled = 1; sink.emit(fn); continue; }
+                    if (merge_enabled) { merge_triggered = 1; merge_start = fn; }
                 } else if (det == 1) {
-                    if (!st->a_init) { st->a_init = 1; st->a_last_cut = fn; }
-                    if (above && (fn - st->a_last_cut) >= P.adaptive_min_scene_len) {
-                        st->a_last_cut = fn - P.adaptive_w;
-                        emit_cut(st, cuts, 1, P.max_cuts, fn - P.adaptive_w);
-                    }
+                    if (above && (fn - last) >= L) { last = fn - P.adaptive_w; sink.emit(last); }
                 } else {
-                    if (st->h_last_cut == 0) st->h_last_cut = fn;
-                    if (above && (fn - st->h_last_cut) >= P.hist_min_scene_len) {
-                        emit_cut(st, cuts, 2, P.max_cuts, fn);
-                        st->h_last_cut = fn;
-                    }
+                    if (last == 0) last = fn;  // `if not self._last_scene_cut` (0 is falsy)
+                    if (above && (fn - last) >= L) { sink.emit(fn); last = fn; }
                 }
             }
         }
         __syncthreads();
+    }
+    if (tid == 0) {
+        st->n_cuts[det] = sink.n;
+        if (sink.overflow) st->overflow = 1;
+        if (det == 0) {
+            st->c_last_above = last; st->c_merge_start = merge_start; st->c_init = init;
+            st->c_merge_enabled = merge_enabled; st->c_merge_triggered = merge_triggered;
+        } else if (det == 1) {
+            st->a_last_cut = last; st->a_init = init;
+        } else {
+            st->h_last_cut = last;
+        }
     }
 }
 

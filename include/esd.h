@@ -143,6 +143,9 @@ ESD_API int esd_ingest_stats(const esd_ctx* ctx, int64_t* h2d_bytes, int64_t* h2
 
 /* Wait for all enqueued work of this ctx. */
 ESD_API int esd_synchronize(esd_ctx* ctx);
+/* The finalize/decision tail of a push runs on a library-owned stream so that it overlaps the next
+ * batch's fused kernel.  esd_join makes `stream` wait (on the device) for every tail enqueued so far. */
+ESD_API int esd_join(esd_ctx* ctx, void* stream);
 ESD_API int64_t esd_frames_pushed(const esd_ctx* ctx);
 
 /* Per-frame results for frames [from_frame, from_frame + n) (absolute frame numbers).  Any output

@@ -213,7 +213,7 @@ def test_batching_and_tuning_invariance():
     variants = [dict(), dict(split_mode=capi.ESD_SPLIT_CHUNKS), dict(rows_per_group=1), dict(rows_per_group=7, pipeline_stages=2),
                 dict(rows_per_group=16, pipeline_stages=8, ctas_per_sm=1), dict(split_mode=capi.ESD_SPLIT_CHUNKS, rows_per_group=3)]
     for vi, kw in enumerate(variants):
-        for sizes in ([n], [1] * 5 + [2, 3, 50, 1, 88], [37] * 4 + [2]):
+        for sizes in ([n], [1] * 5 + [2, 3, 50, 1, 89], [37] * 4 + [2]):
             if vi > 0 and sizes != [n] and vi != 3:
                 continue
             with make_ctx(w, h, None, **kw) as ctx:
