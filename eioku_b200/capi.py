@@ -9,7 +9,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libesd.so")
+LIB_PATH = os.environ.get("ESD_LIB") or os.path.join(_HERE, "libesd.so")  # ESD_LIB: tuning experiments only
 
 ESD_DET_CONTENT, ESD_DET_ADAPTIVE, ESD_DET_HIST = 1, 2, 4
 ESD_FILTER_MERGE, ESD_FILTER_SUPPRESS = 0, 1

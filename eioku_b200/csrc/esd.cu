@@ -11,8 +11,11 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
+#include <time.h>
 
 #include <algorithm>
+#include <type_traits>
 #include <map>
 #include <string>
 #include <vector>
@@ -85,6 +88,7 @@ struct esd_ctx {
     double* d_ratio = nullptr;
     double* d_hdiff = nullptr;
     uint32_t* d_counts = nullptr;  // [cap][bins]
+    uint8_t* d_slab = nullptr;     // backing allocation of the six arrays above
 
     // per-batch scratch
     int64_t part_cap_frames = 0;
@@ -171,12 +175,11 @@ int64_t gcd64(int64_t a, int64_t b) { while (b) { int64_t t = a % b; a = b; b = 
 long py_round(double x) { return lrint(x); }
 
 template <bool RESIZE, int PXT>
-cudaError_t launch_fused_rp(bool content, bool hist, const FusedParams& p, int grid, size_t smem, cudaStream_t st) {
+cudaError_t launch_fused_rp(bool content, bool hist, bool aligned, const FusedParams& p, int grid, size_t smem,
+                            cudaStream_t st) {
 #define ESD_LAUNCH(C, H)                                                                                         \
     do {                                                                                                         \
-        auto k = fused_score_kernel<RESIZE, PXT, C, H>;                                                          \
-        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
-        if (e != cudaSuccess) return e;                                                                          \
+        auto k = aligned ? fused_score_kernel<RESIZE, PXT, C, H, true> : fused_score_kernel<RESIZE, PXT, C, H, false>; \
         k<<<grid, kThreads, smem, st>>>(p);                                                                      \
         return cudaGetLastError();                                                                               \
     } while (0)
@@ -191,8 +194,11 @@ template <bool RESIZE, int PXT>
 cudaError_t occupancy_rp(bool content, bool hist, size_t smem, int* out) {
 #define ESD_OCC(C, H)                                                                                            \
     do {                                                                                                         \
-        auto k = fused_score_kernel<RESIZE, PXT, C, H>;                                                          \
+        auto k = fused_score_kernel<RESIZE, PXT, C, H, true>;                                                    \
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
+        if (e != cudaSuccess) return e;                                                                          \
+        e = cudaFuncSetAttribute(fused_score_kernel<RESIZE, PXT, C, H, false>,                                   \
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                        \
         if (e != cudaSuccess) return e;                                                                          \
         return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, k, kThreads, smem);                            \
     } while (0)
@@ -279,29 +285,42 @@ int build_plan(esd_ctx* c, int64_t n, UnitPlan* out) {
     return ESD_OK;
 }
 
-template <typename T>
-int grow_array(esd_ctx* c, T** p, int64_t old_elems, int64_t new_elems) {
-    T* q = nullptr;
-    CU(c, cudaMalloc(&q, sizeof(T) * new_elems));
-    if (*p && old_elems) CU(c, cudaMemcpy(q, *p, sizeof(T) * old_elems, cudaMemcpyDeviceToDevice));
-    cudaFree(*p);
-    *p = q;
-    return ESD_OK;
-}
-
+// Per-frame score arrays live in ONE device slab (a single cudaMalloc per growth: cudaMalloc/cudaFree cost
+// milliseconds each on a busy device and sit on the first push's latency).
 int ensure_capacity(esd_ctx* c, int64_t frames_needed) {
     if (frames_needed <= c->cap) return ESD_OK;
-    int64_t ncap = std::max<int64_t>(c->cap ? c->cap * 2 : std::max<int64_t>(4096, c->cfg.initial_capacity), frames_needed);
+    const int64_t ncap = std::max<int64_t>(c->cap ? c->cap * 2 : std::max<int64_t>(4096, c->cfg.initial_capacity), frames_needed);
     { int rc0 = sync_all(c); if (rc0) return rc0; }
-    int rc;
+    const int64_t bins = c->need_hist ? c->cfg.hist_bins : 0;
+    const size_t bytes = (size_t)ncap * (3 * sizeof(unsigned long long) + 4 * sizeof(double) + bins * sizeof(uint32_t));
+    uint8_t* slab = nullptr;
+    CU(c, cudaMalloc(&slab, bytes));
+    uint8_t* q = slab;
+    auto carve = [&](auto** dst, int64_t per_frame) {
+        using T = typename std::remove_pointer<typename std::remove_pointer<decltype(dst)>::type>::type;
+        T* np = reinterpret_cast<T*>(q);
+        q += sizeof(T) * per_frame * ncap;
+        return np;
+    };
     const int64_t used = c->n_frames;
-    if ((rc = grow_array(c, &c->d_sums3, used * 3, ncap * 3))) return rc;
-    if ((rc = grow_array(c, &c->d_cv, used, ncap))) return rc;
-    if ((rc = grow_array(c, &c->d_av, used, ncap))) return rc;
-    if ((rc = grow_array(c, &c->d_ratio, used, ncap))) return rc;
-    if ((rc = grow_array(c, &c->d_hdiff, used, ncap))) return rc;
-    if (c->need_hist)
-        if ((rc = grow_array(c, &c->d_counts, used * c->cfg.hist_bins, ncap * c->cfg.hist_bins))) return rc;
+    auto* n_sums = carve(&c->d_sums3, 3);
+    auto* n_cv = carve(&c->d_cv, 1);
+    auto* n_av = carve(&c->d_av, 1);
+    auto* n_ratio = carve(&c->d_ratio, 1);
+    auto* n_hdiff = carve(&c->d_hdiff, 1);
+    auto* n_counts = carve(&c->d_counts, bins);
+    if (used > 0) {
+        CU(c, cudaMemcpy(n_sums, c->d_sums3, sizeof(unsigned long long) * 3 * used, cudaMemcpyDeviceToDevice));
+        CU(c, cudaMemcpy(n_cv, c->d_cv, sizeof(double) * used, cudaMemcpyDeviceToDevice));
+        CU(c, cudaMemcpy(n_av, c->d_av, sizeof(double) * used, cudaMemcpyDeviceToDevice));
+        CU(c, cudaMemcpy(n_ratio, c->d_ratio, sizeof(double) * used, cudaMemcpyDeviceToDevice));
+        CU(c, cudaMemcpy(n_hdiff, c->d_hdiff, sizeof(double) * used, cudaMemcpyDeviceToDevice));
+        if (bins) CU(c, cudaMemcpy(n_counts, c->d_counts, sizeof(uint32_t) * bins * used, cudaMemcpyDeviceToDevice));
+    }
+    cudaFree(c->d_slab);
+    c->d_slab = slab;
+    c->d_sums3 = n_sums; c->d_cv = n_cv; c->d_av = n_av; c->d_ratio = n_ratio; c->d_hdiff = n_hdiff;
+    c->d_counts = bins ? n_counts : nullptr;
     // ratios not yet computed read back as NaN
     fill_nan_kernel<<<(unsigned)((ncap - used + 255) / 256), 256>>>(c->d_ratio + used, ncap - used);
     CU(c, cudaGetLastError());
@@ -354,8 +373,21 @@ int order_after_last(esd_ctx* c, cudaStream_t st) {
     return ESD_OK;
 }
 
+struct TraceTimer {
+    bool on = getenv("ESD_TRACE") != nullptr;
+    double t0 = now();
+    static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+    void lap(const char* what) {
+        if (!on) return;
+        const double t = now();
+        fprintf(stderr, "[esd trace] %-18s %.3f ms\n", what, t - t0);
+        t0 = t;
+    }
+};
+
 int push_common(esd_ctx* c, const uint8_t* d_src, int64_t n, int64_t frame_stride, int64_t row_stride, bool compact,
                 int64_t first_frame_num, cudaStream_t st) {
+    TraceTimer tr;
     if (!d_src || n <= 0) return fail(c, ESD_ERR_INVALID, "push: null frames or n <= 0");
     if (n > 0x7fffff00LL / std::max(1, c->n_groups)) return fail(c, ESD_ERR_INVALID, "push: batch too large (%lld frames)", (long long)n);
     CU(c, cudaSetDevice(c->device));
@@ -368,7 +400,9 @@ int push_common(esd_ctx* c, const uint8_t* d_src, int64_t n, int64_t frame_strid
     }
     int rc;
     if ((rc = ensure_capacity(c, c->n_frames + n))) return rc;
+    tr.lap("ensure_capacity");
     if ((rc = ensure_scratch(c, n))) return rc;
+    tr.lap("ensure_scratch");
     auto it = c->plans.find(n);
     if (it == c->plans.end()) {
         if (c->plans.size() > 64) free_plans(c);
@@ -377,6 +411,7 @@ int push_common(esd_ctx* c, const uint8_t* d_src, int64_t n, int64_t frame_strid
         it = c->plans.emplace(n, pl).first;
     }
     const UnitPlan& plan = it->second;
+    tr.lap("plan");
     if ((rc = order_after_last(c, st))) return rc;
 
     const int64_t base = c->n_frames;  // index of the batch's first frame
@@ -416,8 +451,10 @@ int push_common(esd_ctx* c, const uint8_t* d_src, int64_t n, int64_t frame_strid
         CU(c, cudaEventCreate(&e1));
         CU(c, cudaEventRecord(e0, st));
     }
-    CU(c, ESD_DISPATCH(launch_fused_rp, c->resize, c->pxt, c->need_content, c->need_hist, p, plan.grid, c->smem_bytes, st));
+    const bool aligned = ((reinterpret_cast<uintptr_t>(d_src) | (uintptr_t)frame_stride | (uintptr_t)row_stride) & 15u) == 0;
+    CU(c, ESD_DISPATCH(launch_fused_rp, c->resize, c->pxt, c->need_content, c->need_hist, aligned, p, plan.grid, c->smem_bytes, st));
     c->launches++;
+    tr.lap("launch fused");
     if (c->timing) {
         CU(c, cudaEventRecord(e1, st));
         c->timing_events.emplace_back(e0, e1);
@@ -464,6 +501,7 @@ int push_common(esd_ctx* c, const uint8_t* d_src, int64_t n, int64_t frame_strid
     c->fin_recorded[buf] = true;
     c->launches++;
     c->n_frames += n;
+    tr.lap("launch tail");
     return ESD_OK;
 }
 
@@ -714,6 +752,7 @@ int esd_create(esd_ctx** out, const esd_config* cfg, int device) {
     CUB(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     CUB(cudaEventCreateWithFlags(&c->ev_fin[0], cudaEventDisableTiming));
     CUB(cudaEventCreateWithFlags(&c->ev_fin[1], cudaEventDisableTiming));
+    if (ensure_capacity(c, std::max<int64_t>(4096, cfg->initial_capacity)) != ESD_OK) return bail(ESD_ERR_CUDA);
     if (reset_video_state(c) != ESD_OK) return bail(ESD_ERR_CUDA);
 #undef CUB
     *out = c;
@@ -729,8 +768,7 @@ void esd_destroy(esd_ctx* c) {
     for (auto& ev : c->timing_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     cudaFree(c->d_yrows); cudaFree(c->d_xtab); cudaFree(c->d_sdiv); cudaFree(c->d_hdiv);
     cudaFree(c->d_prev[0]); cudaFree(c->d_prev[1]); cudaFree(c->d_state); cudaFree(c->d_cuts);
-    cudaFree(c->d_sums3); cudaFree(c->d_cv); cudaFree(c->d_av); cudaFree(c->d_ratio); cudaFree(c->d_hdiff);
-    cudaFree(c->d_counts);
+    cudaFree(c->d_slab);
     for (int b = 0; b < 2; ++b) { cudaFree(c->d_part[b]); cudaFree(c->d_hist_part[b]); if (c->ev_fin[b]) cudaEventDestroy(c->ev_fin[b]); }
     if (c->order_event) cudaEventDestroy(c->order_event);
     if (c->ev_fused) cudaEventDestroy(c->ev_fused);

@@ -14,7 +14,10 @@
 
 namespace esd {
 
-constexpr int kConsumerWarps = 8;
+#ifndef ESD_CONSUMER_WARPS
+#define ESD_CONSUMER_WARPS 8
+#endif
+constexpr int kConsumerWarps = ESD_CONSUMER_WARPS;
 constexpr int kConsumers = kConsumerWarps * 32;  // 256 pixel threads
 constexpr int kThreads = kConsumers + 32;        // + 1 producer warp
 constexpr int kMaxStages = 8;
@@ -138,7 +141,9 @@ __device__ __forceinline__ int vresize(uint32_t h0, uint32_t h1, uint32_t b0s, u
     return min(v, 255);
 }
 
-template <bool RESIZE, int PXT, bool CONTENT, bool HIST>
+// ALIGNED: every source row starts on a 16-byte boundary (base, pitch and frame stride multiples of 16), so the
+// per-row misalignment is zero and each thread's smem word offset / funnel shift are loop invariants.
+template <bool RESIZE, int PXT, bool CONTENT, bool HIST, bool ALIGNED>
 __global__ void __launch_bounds__(kThreads) fused_score_kernel(const FusedParams p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     // ---- carve shared memory
@@ -181,6 +186,7 @@ __global__ void __launch_bounds__(kThreads) fused_score_kernel(const FusedParams
         // ================================================================ producer warp (one lane)
         if (tid != kConsumers) return;
         const uint64_t pol = l2_evict_first_policy();
+        const uint32_t full_base = smem_u32(full_bar), empty_base = smem_u32(empty_bar), stage_base = smem_u32(s_stage);
         int s = 0;
         uint32_t par = 1u;  // empty barriers start "free"
         for (int u = u_begin; u < u_end; ++u) {
@@ -197,7 +203,7 @@ __global__ void __launch_bounds__(kThreads) fused_score_kernel(const FusedParams
                     if (f == p.n_frames - 1) fflags |= F_SAVE;
                 }
                 for (int r = r_begin; r < r_end; ++r) {
-                    mbar_wait(smem_u32(&empty_bar[s]), par);
+                    mbar_wait(empty_base + 8u * s, par);
                     const YRow yr = p.yrows[r];
                     const uint8_t* a0 = frame + (long long)(p.compact ? yr.crow0 : yr.row0) * p.row_stride;
                     const uint32_t mis0 = (uint32_t)(reinterpret_cast<uintptr_t>(a0) & 15u);
@@ -212,8 +218,8 @@ __global__ void __launch_bounds__(kThreads) fused_score_kernel(const FusedParams
                     const int flags = fflags | ((r == r_end - 1) ? F_FRAME_END : 0);
                     meta[s] = make_int4(f, (r - r_begin) | (r << 8), flags, (int)(mis0 | (mis1 << 8)));
                     meta_b[s] = make_uint2(yr.b0s, yr.b1s);
-                    const uint32_t bar = smem_u32(&full_bar[s]);
-                    const uint32_t dst = smem_u32(s_stage + (size_t)s * stage_bytes);
+                    const uint32_t bar = full_base + 8u * s;
+                    const uint32_t dst = stage_base + (uint32_t)s * stage_bytes;
                     mbar_arrive_expect_tx(bar, bytes0 + bytes1);
                     bulk_g2s(dst, a0 - mis0, bytes0, bar, pol);
                     if (RESIZE) bulk_g2s(dst + p.rowbuf, a1 - mis1, bytes1, bar, pol);
@@ -222,9 +228,9 @@ __global__ void __launch_bounds__(kThreads) fused_score_kernel(const FusedParams
             }
         }
         // sentinel: tells the consumers to stop
-        mbar_wait(smem_u32(&empty_bar[s]), par);
+        mbar_wait(empty_base + 8u * s, par);
         meta[s] = make_int4(0, 0, F_END, 0);
-        mbar_arrive(smem_u32(&full_bar[s]));
+        mbar_arrive(full_base + 8u * s);
         return;
     }
 
@@ -244,12 +250,13 @@ __global__ void __launch_bounds__(kThreads) fused_score_kernel(const FusedParams
             xa01[k] = 0;
         }
     }
+    const uint32_t full_base = smem_u32(full_bar), empty_base = smem_u32(empty_bar);
     uint32_t acc_hv = 0, acc_s = 0;  // per-frame, per-thread: H | V << 16 and S
     int hist_buf = 0;
     int s = 0;
     uint32_t par = 0u;
     for (;; ) {
-        mbar_wait(smem_u32(&full_bar[s]), par);
+        mbar_wait(full_base + 8u * s, par);
         const int4 m = meta[s];
         const int flags = m.z;
         if (flags & F_END) break;
@@ -258,7 +265,7 @@ __global__ void __launch_bounds__(kThreads) fused_score_kernel(const FusedParams
         const int row = m.y >> 8;
         const uint8_t* row0 = s_stage + (size_t)s * stage_bytes;
         const uint8_t* row1 = row0 + p.rowbuf;
-        const uint32_t mis0 = (uint32_t)m.w & 0xffu, mis1 = ((uint32_t)m.w >> 8) & 0xffu;
+        const uint32_t mis0 = ALIGNED ? 0u : ((uint32_t)m.w & 0xffu), mis1 = ALIGNED ? 0u : (((uint32_t)m.w >> 8) & 0xffu);
 #pragma unroll
         for (int k = 0; k < PXT; ++k) {
             const int d = k * kConsumers + tid;
@@ -309,7 +316,7 @@ __global__ void __launch_bounds__(kThreads) fused_score_kernel(const FusedParams
             }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&empty_bar[s]));  // stage may be refilled
+        if (lane == 0) mbar_arrive(empty_base + 8u * s);  // stage may be refilled
         if (++s == S) { s = 0; par ^= 1u; }
 
         if (flags & F_FRAME_END) {

@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""Measures the other BASELINE.json configs (3: adaptive + frame-range sharding with halo, 4: 4K histogram +
+luma_only from one pass, 5: library batch partitioned by whole videos) and two PCIe probes.  One JSON line
+per config on rank 0.  Launch with python (1 GPU) or torchrun (N GPUs):
+
+    python scripts/bench_configs.py [--configs 3,4,5,pcie] [--videos-per-gpu 8]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from eioku_b200 import capi, sharding, synth  # noqa: E402
+from eioku_b200.detectors import AdaptiveDetector, ContentDetector, HistogramDetector  # noqa: E402
+from eioku_b200.scene_manager import SceneManager  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        return 6650.0
+
+
+def dist_env():
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return world, rank, local
+
+
+def fill(seed, w, h, descs, dev, chunk=256):
+    out = torch.empty((len(descs), h, w, 3), dtype=torch.uint8, device=dev)
+    for a in range(0, len(descs), chunk):
+        capi.synth_fill(out[a:a + chunk], seed, descs[a:a + chunk])
+    return out
+
+
+def max_over_ranks(x, dev, dist):
+    t = torch.tensor([x], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t[0])
+
+
+def config3(dev, local, world, rank, dist, n_total=18000):
+    """AdaptiveDetector(3.0, w=2) on the config-2 clip, frame ranges + halo, one global decision pass."""
+    W, H, seed, ww = 1920, 1080, 1002, 2
+    sch = synth.build_schedule(seed, n_total)
+    sh = sharding.frame_range_shards(n_total, world, ww)[rank]
+    n_load = sh.load_end - sh.load_start
+    sm = SceneManager(device=local)
+    det = AdaptiveDetector(adaptive_threshold=3.0, window_width=ww)
+    sm.add_detector(det)
+    ctx = sm.make_context(W, H)
+    batch = 1024
+    ms_total = 0.0
+    pos = sh.load_start
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stream = torch.cuda.current_stream().cuda_stream
+    while pos < sh.load_end:
+        m = min(batch, sh.load_end - pos)
+        clip = fill(seed, W, H, sch.descs[pos:pos + m], dev)
+        torch.cuda.synchronize()
+        e0.record()
+        ctx.push_tensor(clip, pos, stream)
+        ctx.join(stream)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_total += e0.elapsed_time(e1)
+        pos += m
+        del clip
+    scores = sharding.owned_slice(ctx.read_scores(sh.load_start, n_load, ["adaptive_val", "adaptive_ratio"]), sh)
+    ms = max_over_ranks(ms_total, dev, dist)
+    gathered = [None] * world
+    if dist is not None:
+        dist.all_gather_object(gathered, scores)
+    else:
+        gathered = [scores]
+    out = None
+    if rank == 0:
+        shards = sharding.frame_range_shards(n_total, world, ww)
+        merged = sharding.fix_video_start(sharding.merge_owned(gathered, shards))
+        t0 = time.perf_counter()
+        cuts, ratio = ctx.decide_arrays(capi.ESD_DET_ADAPTIVE, 0, merged["adaptive_val"])
+        t_decide = time.perf_counter() - t0
+        parity = None
+        gp = os.path.join(GOLD, "clip_c2_1080p_full.npz")
+        if os.path.exists(gp) and n_total == 18000:
+            g = np.load(gp)
+            parity = bool(cuts == g["cuts_adaptive"].tolist() and
+                          np.array_equal(np.nan_to_num(ratio, nan=-1).view(np.uint64), np.nan_to_num(g["adaptive_ratio"], nan=-1).view(np.uint64)) and
+                          np.array_equal(merged["adaptive_val"].view(np.uint64), g["content_val"].view(np.uint64)))
+        out = {"config": 3, "what": "AdaptiveDetector(3.0,w=2) 1080p, frame-range shards + (w+1)/w halo, global decision pass",
+               "n_gpus": world, "frames": n_total, "frames_scored_incl_halo": n_load * world if world > 1 else n_load,
+               "value": n_total / (ms / 1000.0), "unit": "frames/s", "ms_scoring_max_rank": ms, "ms_global_decision": 1000 * t_decide,
+               "cuts": len(cuts), "bit_exact_vs_cv2_golden": parity}
+    ctx.close()
+    return out
+
+
+def config4(dev, local, world, rank, dist, n=512, steps=10):
+    """4K: HistogramDetector(0.05, 256 bins) + ContentDetector(luma_only) fed from one pass."""
+    W, H, seed = 3840, 2160, 1004
+    first = rank * n
+    sch = synth.build_schedule(seed, first + n)
+    clip = fill(seed, W, H, sch.descs[first:first + n], dev, chunk=64)
+    sm = SceneManager(device=local, tuning={"initial_capacity": (steps + 4) * n})
+    sm.add_detector(HistogramDetector(threshold=0.05, bins=256, min_scene_len=15))
+    sm.add_detector(ContentDetector(luma_only=True))
+    ctx = sm.make_context(W, H)
+    stream = torch.cuda.current_stream().cuda_stream
+    pos = 0
+    for _ in range(3):
+        ctx.push_tensor(clip, pos, stream); pos += n
+    ctx.synchronize()
+    ctx.set_timing(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    e0.record()
+    for _ in range(steps):
+        ctx.push_tensor(clip, pos, stream); pos += n
+    ctx.join(stream)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = max_over_ranks(e0.elapsed_time(e1), dev, dist)
+    kms, kn = ctx.kernel_time()
+    parity = None
+    gp = os.path.join(GOLD, "clip_c4_4k_head.npz")
+    if rank == 0 and os.path.exists(gp):
+        g = np.load(gp)
+        m = int(g["n_frames"])
+        ctx.reset()
+        ctx.push_tensor(clip[:m], 0, stream)
+        sc = ctx.read_scores(0, m)
+        parity = bool(np.array_equal(sc["hist_diff"][1:].view(np.uint64), g["hist_diff"][1:].view(np.uint64)) and
+                      np.array_equal(sc["content_val"].view(np.uint64), g["luma_val"].view(np.uint64)) and
+                      ctx.get_cuts(capi.ESD_DET_HIST)[0] == g["cuts_hist"].tolist() and
+                      ctx.get_cuts(capi.ESD_DET_CONTENT)[0] == g["cuts_content_luma"].tolist())
+    alg = ctx.alg_bytes_per_frame
+    out = None
+    if rank == 0:
+        ach = n * alg / (kms / kn / 1000.0) / 1e9
+        out = {"config": 4, "what": "4K: HistogramDetector(256 bins) + ContentDetector(luma_only), one pass", "n_gpus": world,
+               "value": steps * n * world / (ms / 1000.0), "unit": "frames/s", "frames_per_step": n, "alg_bytes_per_frame": alg,
+               "roofline": {"achieved": ach, "peak": peak(), "frac": ach / peak(), "unit": "GB/s", "avg_kernel_ms": kms / kn},
+               "bit_exact_vs_cv2_golden_first_240": parity}
+    ctx.close()
+    return out
+
+
+def config5(dev, local, world, rank, dist, videos_per_gpu=8, n_videos=512, frames_per_video=9000):
+    """Library batch: whole videos per GPU (LPT), generation excluded from the timed region."""
+    W, H = 1920, 1080
+    mine = sharding.partition_videos([frames_per_video] * n_videos, world)[rank][:videos_per_gpu]
+    sm = SceneManager(device=local, tuning={"initial_capacity": frames_per_video + 16})
+    sm.add_detector(ContentDetector())
+    ctx = sm.make_context(W, H)
+    stream = torch.cuda.current_stream().cuda_stream
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ms_total, frames, cuts_total = 0.0, 0, 0
+    batch = 2048
+    for j in mine:
+        seed = 5000 + j
+        sch = synth.build_schedule(seed, frames_per_video)
+        ctx.reset()
+        pos = 0
+        while pos < frames_per_video:
+            m = min(batch, frames_per_video - pos)
+            clip = fill(seed, W, H, sch.descs[pos:pos + m], dev)
+            torch.cuda.synchronize()
+            e0.record()
+            ctx.push_tensor(clip, pos, stream)
+            ctx.join(stream)
+            e1.record()
+            torch.cuda.synchronize()
+            ms_total += e0.elapsed_time(e1)
+            if os.environ.get("ESD_DEBUG"):
+                print("c5 push", j, pos, m, round(e0.elapsed_time(e1), 3), flush=True)
+            pos += m
+            del clip
+        cuts, _ = ctx.get_cuts(capi.ESD_DET_CONTENT)
+        cuts_total += len(cuts)
+        frames += frames_per_video
+    ms = max_over_ranks(ms_total, dev, dist)
+    tot = torch.tensor([frames, cuts_total], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(tot)
+    ctx.close()
+    if rank != 0:
+        return None
+    return {"config": 5, "what": "library batch: whole 9000-frame 1080p videos per GPU, ContentDetector, generation excluded",
+            "n_gpus": world, "videos_scored": int(tot[0]) // frames_per_video, "of_videos": n_videos,
+            "value": float(tot[0]) / (ms / 1000.0), "unit": "frames/s", "cuts": int(tot[1]),
+            "note": "bounded subset of the 512-video library; per-video throughput is independent of library size"}
+
+
+def pcie_probe(dev, local):
+    """H2D ceilings on this box: plain pinned memcpy, the touched-rows ring, and zero-copy TMA reads of pinned frames."""
+    W, H, n = 1920, 1080, 256
+    sch = synth.build_schedule(1002, n)
+    clip = fill(1002, W, H, sch.descs, dev)
+    host = clip.cpu().pin_memory()
+    out = {"config": "pcie"}
+    dst = torch.empty_like(clip)
+    for _ in range(2):
+        dst.copy_(host, non_blocking=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        dst.copy_(host, non_blocking=True)
+    torch.cuda.synchronize()
+    out["pinned_memcpy_GBps"] = 3 * host.numel() / (time.perf_counter() - t0) / 1e9
+    cfg = capi.default_config()
+    cfg.src_width, cfg.src_height = W, H
+    # ring
+    for fps_slot in (64, 128, 256):
+        ctx = capi.EsdContext(cfg, local)
+        ctx.ingest_open(3, fps_slot)
+        hn = host.numpy()
+        ctx.ingest_push_numpy(hn, 0); ctx.synchronize()
+        t0 = time.perf_counter()
+        for i in range(1, 5):
+            ctx.ingest_push_numpy(hn, i * n)
+        ctx.synchronize()
+        dt = time.perf_counter() - t0
+        out[f"ring_slot{fps_slot}_frames_per_s"] = 4 * n / dt
+        out[f"ring_slot{fps_slot}_GBps"] = 4 * n * ctx.alg_bytes_per_frame / dt / 1e9
+        want = ctx.read_scores(0, n, ["sums3"])["sums3"]
+        ctx.close()
+    # zero copy: the fused kernel's TMA loads read the pinned host frames directly over PCIe
+    ctx = capi.EsdContext(cfg, local)
+    stream = torch.cuda.current_stream().cuda_stream
+    ctx.push_device(host.data_ptr(), n, host.stride(0), host.stride(1), 0, stream); ctx.synchronize()
+    t0 = time.perf_counter()
+    for i in range(1, 5):
+        ctx.push_device(host.data_ptr(), n, host.stride(0), host.stride(1), i * n, stream)
+    ctx.synchronize()
+    dt = time.perf_counter() - t0
+    out["zero_copy_frames_per_s"] = 4 * n / dt
+    out["zero_copy_GBps"] = 4 * n * ctx.alg_bytes_per_frame / dt / 1e9
+    got = ctx.read_scores(0, n, ["sums3"])["sums3"]
+    out["zero_copy_bit_exact"] = bool(np.array_equal(got, want))
+    ctx.close()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--configs", default="3,4,5,pcie")
+    ap.add_argument("--videos-per-gpu", type=int, default=4)
+    ap.add_argument("--c3-frames", type=int, default=18000)
+    args = ap.parse_args()
+    world, rank, local = dist_env()
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    for c in args.configs.split(","):
+        if c == "3":
+            r = config3(dev, local, world, rank, dist, args.c3_frames)
+        elif c == "4":
+            r = config4(dev, local, world, rank, dist)
+        elif c == "5":
+            r = config5(dev, local, world, rank, dist, args.videos_per_gpu)
+        elif c == "pcie":
+            r = pcie_probe(dev, local) if rank == 0 else None
+        else:
+            continue
+        if rank == 0 and r is not None:
+            print(json.dumps(r), flush=True)
+        if dist is not None:
+            dist.barrier()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -383,6 +383,41 @@ def test_errors_are_loud():
 
 
 @pytest.mark.slow
+@pytest.mark.parametrize("name,batch", [("c2_1080p_full", 1024), ("c4_4k_full", 256)])
+def test_full_length_baseline_configs_vs_cv2_golden(name, batch):
+    """BASELINE config 2 (18 000 x 1080p, 10 min) and config 4 (3 600 x 4K60) at FULL length: per-frame integer
+    sums, float64 content_val / adaptive_ratio / hist_diff and all cut lists equal the cv2 run frozen in
+    tests/golden (generated by tests/golden/make_golden.py --full)."""
+    g = load_golden(f"clip_{name}.npz")
+    w, h, n, seed = int(g["width"]), int(g["height"]), int(g["n_frames"]), int(g["seed"])
+    sch = synth.build_schedule(seed, n)
+    dets = [ContentDetector(threshold=27.0, min_scene_len=15), AdaptiveDetector(adaptive_threshold=3.0, window_width=2),
+            HistogramDetector(threshold=0.05, bins=256, min_scene_len=15)]
+    sm = SceneManager(batch_frames=batch)
+    for d in dets:
+        sm.add_detector(d)
+
+    def batches():
+        for a in range(0, n, batch):
+            yield gpu_clip(seed, w, h, sch.descs[a:a + batch])
+
+    from eioku_b200.scene_manager import BatchVideo
+    assert sm.detect_scenes(BatchVideo(batches(), (w, h), 30.0), collect_scores=True) == n
+    sc = sm.scores
+    assert np.array_equal(sc["sums3"], g["sums3"])
+    assert same_f64(sc["content_val"], g["content_val"])
+    assert same_f64(sc["adaptive_ratio"], g["adaptive_ratio"])
+    assert same_f64(sc["hist_diff"], g["hist_diff"])
+    assert hashlib.sha256(np.ascontiguousarray(sc["hist"]).tobytes()).digest() == bytes(g["hist_sha256"])
+    assert sm.cuts_of(dets[0]) == g["cuts_content"].tolist() and len(g["cuts_content"]) > 20
+    assert sm.cuts_of(dets[1]) == g["cuts_adaptive"].tolist()
+    assert sm.cuts_of(dets[2]) == g["cuts_hist"].tolist()
+    scenes = sm.get_scene_list(start_in_scene=True)
+    assert scenes[0][0] == 0 and scenes[-1][1] == n and len(scenes) == len(sm.get_cut_list()) + 1
+    sm.close()
+
+
+@pytest.mark.slow
 def test_full_size_1080p_properties():
     """BASELINE config-2 size (1080p, 2048-frame batches): size-independent properties of the full-size path:
     idempotence, |a-b| == |b-a| under frame reversal, zero deltas for duplicated frames, histogram mass."""
