@@ -54,6 +54,7 @@ struct esd_ctx {
 
     // geometry
     int dst_w = 0, dst_h = 0, row_bytes = 0;
+    int alg_row_bytes = 0;  // 32-byte sectors of a row that contain a horizontal tap, in bytes
     bool resize = false;
     int pxt = 1;
     int rows_per_group = 0, n_groups = 0, stages = 0, rowbuf = 0, stage_bytes = 0;
@@ -674,6 +675,16 @@ int esd_create(esd_ctx** out, const esd_config* cfg, int device) {
             if (c->resize) { xt[x].x = (uint32_t)(3 * xo0[x]); xt[x].y = (uint32_t)xa0[x] | ((uint32_t)xa1[x] << 16); }
             else { xt[x].x = (uint32_t)(3 * x); xt[x].y = 2048u; }
         }
+        {  // sector-granular touched bytes per row (SURVEY.md section 8d accounting)
+            std::vector<char> sec((c->row_bytes + 31) / 32, 0);
+            for (int x = 0; x < dw; ++x) {
+                const int b0 = (int)xt[x].x, b1 = std::min(c->row_bytes, b0 + (c->resize ? 6 : 3)) - 1;
+                for (int q = b0 / 32; q <= b1 / 32; ++q) sec[q] = 1;
+            }
+            int nsec = 0;
+            for (char v : sec) nsec += v;
+            c->alg_row_bytes = std::min(c->row_bytes, nsec * 32);
+        }
         CUB(cudaMalloc(&c->d_xtab, sizeof(uint2) * dw));
         CUB(cudaMemcpy(c->d_xtab, xt.data(), sizeof(uint2) * dw, cudaMemcpyHostToDevice));
     }
@@ -791,7 +802,7 @@ int esd_get_geometry(const esd_ctx* c, esd_geometry* g) {
     g->dst_height = c->dst_h;
     g->n_touched_rows = (int32_t)c->touched.size();
     g->row_bytes = c->row_bytes;
-    g->alg_bytes_per_frame = (int64_t)c->touched.size() * c->row_bytes;
+    g->alg_bytes_per_frame = (int64_t)c->touched.size() * c->alg_row_bytes;
     g->compact_frame_bytes = (int64_t)c->touched.size() * c->row_bytes;
     return ESD_OK;
 }
@@ -831,7 +842,7 @@ int esd_ingest_open(esd_ctx* c, int32_t n_slots, int32_t frames_per_slot) {
     c->frames_per_slot = frames_per_slot;
     c->next_slot = 0;
     for (auto& s : c->ring) {
-        CU(c, cudaHostAlloc(&s.h_pinned, slot_bytes, cudaHostAllocDefault));
+        // the pinned staging buffer is only needed for pageable sources: allocated on first use
         CU(c, cudaMalloc(&s.d_rows, slot_bytes));
         CU(c, cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
         CU(c, cudaEventCreateWithFlags(&s.consumed, cudaEventDisableTiming));
@@ -846,7 +857,7 @@ int esd_ingest_close(esd_ctx* c) {
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     if (c->compute_stream) cudaStreamSynchronize(c->compute_stream);
     for (auto& s : c->ring) {
-        cudaFreeHost(s.h_pinned);
+        if (s.h_pinned) cudaFreeHost(s.h_pinned);
         cudaFree(s.d_rows);
         if (s.copied) cudaEventDestroy(s.copied);
         if (s.consumed) cudaEventDestroy(s.consumed);
@@ -898,6 +909,8 @@ int esd_ingest_push_host(esd_ctx* c, const uint8_t* h_bgr, int64_t n, int64_t fr
             }
         } else {
             // pageable source: the CPU gathers the touched rows into the pinned slot
+            if (!s.h_pinned)
+                CU(c, cudaHostAlloc(&s.h_pinned, (size_t)c->frames_per_slot * cfb, cudaHostAllocDefault));
             for (int64_t f = 0; f < m; ++f)
                 for (const Run& r : runs)
                     memcpy(s.h_pinned + f * cfb + (int64_t)r.crow * c->row_bytes, src + f * frame_stride + (int64_t)r.row * pitch,

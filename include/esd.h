@@ -102,8 +102,8 @@ typedef struct esd_geometry {
     int32_t dst_width, dst_height;
     int32_t n_touched_rows;      /* distinct source rows the vertical taps read */
     int32_t row_bytes;           /* src_width * 3 */
-    int64_t alg_bytes_per_frame; /* n_touched_rows * row_bytes: algorithmic HBM bytes per frame */
-    int64_t compact_frame_bytes; /* size of one frame in the compact (touched rows only) layout */
+    int64_t alg_bytes_per_frame; /* algorithmic HBM bytes per frame: 32-byte sectors of the touched rows that hold a tap */
+    int64_t compact_frame_bytes; /* n_touched_rows * row_bytes: one frame in the compact layout = bytes the kernel fetches */
 } esd_geometry;
 
 ESD_API int esd_abi_version(void);
