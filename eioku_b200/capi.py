@@ -41,6 +41,7 @@ class EsdConfig(C.Structure):
         ("hist_threshold", C.c_double), ("hist_bins", C.c_int32), ("hist_min_scene_len", C.c_int32),
         ("rows_per_group", C.c_int32), ("pipeline_stages", C.c_int32),
         ("split_mode", C.c_int32), ("ctas_per_sm", C.c_int32),
+        ("rows_per_stage", C.c_int32), ("reserved1", C.c_int32),
         ("max_cuts", C.c_int64), ("initial_capacity", C.c_int64),
     ]
 

@@ -57,7 +57,7 @@ struct esd_ctx {
     int alg_row_bytes = 0;  // 32-byte sectors of a row that contain a horizontal tap, in bytes
     bool resize = false;
     int pxt = 1;
-    int rows_per_group = 0, n_groups = 0, stages = 0, rowbuf = 0, stage_bytes = 0;
+    int rows_per_group = 0, n_groups = 0, stages = 0, rowbuf = 0, stage_bytes = 0, rows_per_stage = 1;
     int ctas_per_sm = 0;
     size_t smem_bytes = 0;
     bool need_content = false, need_hist = false;
@@ -221,7 +221,7 @@ cudaError_t occupancy_rp(bool content, bool hist, size_t smem, int* out) {
                               : FN<false, 16>(__VA_ARGS__)))
 
 size_t fused_smem_bytes(const esd_ctx* c, int R, int stages) {
-    size_t off = 4416;  // barriers + meta + sdiv/hdiv + hist (see kernel carve-up)
+    size_t off = 4864;  // barriers + meta + per-row meta + sdiv/hdiv + hist (see kernel carve-up)
     if (c->need_content) off += (size_t)R * c->pxt * kConsumers * 4;
     off = (off + 127) & ~(size_t)127;
     return off + (size_t)stages * c->stage_bytes;
@@ -428,6 +428,7 @@ int push_common(esd_ctx* c, const uint8_t* d_src, int64_t n, int64_t frame_strid
     p.rows_per_group = c->rows_per_group;
     p.n_groups = c->n_groups;
     p.stages = c->stages;
+    p.rows_per_stage = c->rows_per_stage;
     p.rowbuf = c->rowbuf;
     p.has_prev = base > 0 ? 1 : 0;
     p.bins = c->cfg.hist_bins;
@@ -703,7 +704,12 @@ int esd_create(esd_ctx** out, const esd_config* cfg, int device) {
 
     // ---- kernel shape
     c->rowbuf = ((c->row_bytes + 15 + 15) & ~15) + 16;
-    c->stage_bytes = (c->resize ? 2 : 1) * c->rowbuf;
+    // destination rows per pipeline stage: 2 amortises the per-stage barrier/metadata work over two pixels per thread
+    int RS = cfg->rows_per_stage > 0 ? cfg->rows_per_stage : 4;
+    RS = std::max(1, std::min(RS, kMaxRowsPerStage));
+    while (RS > 1 && (size_t)RS * (c->resize ? 2 : 1) * c->rowbuf > 48 * 1024) --RS;
+    c->rows_per_stage = RS;
+    c->stage_bytes = RS * (c->resize ? 2 : 1) * c->rowbuf;
     // rows per group: 16 measured best at 1080p->256x144 (profiles/r01_sweep.md); the previous-frame HSV of
     // a group lives in shared memory (R * pxt KB), keep it <= 32 KB unless the caller insists
     int R = cfg->rows_per_group > 0 ? cfg->rows_per_group : std::max(1, std::min(16, 32 / c->pxt));
@@ -712,7 +718,7 @@ int esd_create(esd_ctx** out, const esd_config* cfg, int device) {
     while (R > 1 && ((int64_t)R * c->pxt > 256 || (int64_t)R * dw > 65535)) --R;
     c->rows_per_group = R;
     c->n_groups = (dh + R - 1) / R;
-    int stages = cfg->pipeline_stages > 0 ? std::min(cfg->pipeline_stages, kMaxStages) : 4;
+    int stages = cfg->pipeline_stages > 0 ? std::min(cfg->pipeline_stages, kMaxStages) : (c->rows_per_stage >= 4 ? 2 : c->rows_per_stage > 1 ? 3 : 4);
     const size_t smem_limit = prop.sharedMemPerBlockOptin;
     while (stages > 2 && fused_smem_bytes(c, R, stages) > smem_limit) --stages;
     c->stages = stages;

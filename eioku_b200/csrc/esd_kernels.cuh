@@ -21,6 +21,7 @@ constexpr int kConsumerWarps = ESD_CONSUMER_WARPS;
 constexpr int kConsumers = kConsumerWarps * 32;  // 256 pixel threads
 constexpr int kThreads = kConsumers + 32;        // + 1 producer warp
 constexpr int kMaxStages = 8;
+constexpr int kMaxRowsPerStage = 4;  // destination rows staged per pipeline slot
 
 enum : int { F_HALO = 1, F_NOPREV = 2, F_CTXPREV = 4, F_SAVE = 8, F_FRAME_END = 16, F_END = 32 };
 
@@ -45,6 +46,7 @@ struct FusedParams {
     int row_bytes;  // src_w * 3
     int rows_per_group, n_groups;
     int stages;
+    int rows_per_stage;  // destination rows per pipeline stage (1..kMaxRowsPerStage)
     int rowbuf;  // bytes reserved per staged source row (multiple of 16)
     int has_prev;
     int bins;
@@ -137,8 +139,74 @@ __device__ __forceinline__ uint32_t bgr_to_hsv_packed(int b, int g, int r, const
 
 // OpenCV VResizeLinear<uchar,int,short,FixedPtCast<int,uchar,22>>: b0s/b1s are the coefficients << 16
 __device__ __forceinline__ int vresize(uint32_t h0, uint32_t h1, uint32_t b0s, uint32_t b1s) {
-    int v = (int)((__umulhi(b0s, h0 >> 4) + __umulhi(b1s, h1 >> 4) + 2u) >> 2);
-    return min(v, 255);
+    // no saturation needed: a0+a1 and b0+b1 are 2048 (+-1), so the sum of the two terms is <= 1021 and
+    // (1021 + 2) >> 2 == 255
+    return (int)((__umulhi(b0s, h0 >> 4) + __umulhi(b1s, h1 >> 4) + 2u) >> 2);
+}
+
+// One destination row of one frame for one consumer thread (PXT columns).  SPECIAL = the stage carries a rare flag
+// (halo frame, first frame of the video / of the batch, last frame of the batch); the common path has none.
+template <bool RESIZE, int PXT, bool CONTENT, bool HIST, bool SPECIAL>
+__device__ __forceinline__ void score_row(const FusedParams& p, const uint8_t* __restrict__ row0, const uint8_t* __restrict__ row1,
+                                          uint32_t mis0, uint32_t mis1, uint32_t b0s, uint32_t b1s, int flags, int rloc,
+                                          int row, int tid, const uint32_t (&xoff)[PXT], const uint32_t (&xa01)[PXT],
+                                          const int* __restrict__ s_sdiv, const int* __restrict__ s_hdiv,
+                                          uint32_t* __restrict__ s_prev, uint32_t* __restrict__ s_hist_cur,
+                                          uint32_t& acc_hv, uint32_t& acc_s) {
+#pragma unroll
+    for (int k = 0; k < PXT; ++k) {
+        const int d = k * kConsumers + tid;
+        if (d < p.dst_w) {
+            int b, g, r;
+            if (RESIZE) {
+                uint32_t n0, n1;
+                const uint32_t o0 = xoff[k] + mis0, o1 = xoff[k] + mis1;
+                const uint32_t lo0 = lds_u32_unaligned(row0, o0, n0);
+                const uint32_t w02 = *reinterpret_cast<const uint32_t*>(row0 + (o0 & ~3u) + 8);
+                const uint32_t hi0 = __funnelshift_r(n0, w02, (o0 & 3u) * 8u);
+                const uint32_t lo1 = lds_u32_unaligned(row1, o1, n1);
+                const uint32_t w12 = *reinterpret_cast<const uint32_t*>(row1 + (o1 & ~3u) + 8);
+                const uint32_t hi1 = __funnelshift_r(n1, w12, (o1 & 3u) * 8u);
+                // lo = [Ab Ag Ar Bb], hi = [Bg Br . .]  ->  [Ab Bb Ag Bg] and [Ar Br . .]
+                const uint32_t bg0 = __byte_perm(lo0, hi0, 0x4130), rr0 = __byte_perm(lo0, hi0, 0x0052);
+                const uint32_t bg1 = __byte_perm(lo1, hi1, 0x4130), rr1 = __byte_perm(lo1, hi1, 0x0052);
+                const uint32_t a = xa01[k];
+                // HResizeLinear: tap0 * a0 + tap1 * a1 (scale 2^11)
+                const uint32_t hb0 = __dp2a_lo(a, bg0, 0u), hg0 = __dp2a_hi(a, bg0, 0u), hr0 = __dp2a_lo(a, rr0, 0u);
+                const uint32_t hb1 = __dp2a_lo(a, bg1, 0u), hg1 = __dp2a_hi(a, bg1, 0u), hr1 = __dp2a_lo(a, rr1, 0u);
+                b = vresize(hb0, hb1, b0s, b1s);
+                g = vresize(hg0, hg1, b0s, b1s);
+                r = vresize(hr0, hr1, b0s, b1s);
+            } else {
+                uint32_t nx;
+                const uint32_t px = lds_u32_unaligned(row0, xoff[k] + mis0, nx);
+                b = px & 255u;
+                g = (px >> 8) & 255u;
+                r = (px >> 16) & 255u;
+            }
+            if (CONTENT) {
+                const uint32_t cur = bgr_to_hsv_packed(b, g, r, s_sdiv, s_hdiv);
+                uint32_t* slot = s_prev + (rloc * PXT + k) * kConsumers + tid;
+                uint32_t pv;
+                if (SPECIAL) {
+                    pv = cur;
+                    if (!(flags & (F_HALO | F_NOPREV)))
+                        pv = (flags & F_CTXPREV) ? __ldg(p.prev_in + (size_t)row * p.dst_w + d) : *slot;
+                    if (flags & F_SAVE) p.prev_out[(size_t)row * p.dst_w + d] = cur;
+                } else {
+                    pv = *slot;
+                }
+                const uint32_t diff = __vabsdiffu4(cur, pv);
+                acc_hv += diff & 0x00ff00ffu;
+                acc_s += (diff >> 8) & 0xffu;
+                *slot = cur;
+            }
+            if (HIST && !(SPECIAL && (flags & F_HALO))) {
+                const int y = (4899 * r + 9617 * g + 1868 * b + 8192) >> 14;
+                atomicAdd(&s_hist_cur[(y * p.bins) >> 8], 1u);
+            }
+        }
+    }
 }
 
 // ALIGNED: every source row starts on a 16-byte boundary (base, pitch and frame stride multiples of 16), so the
@@ -146,18 +214,18 @@ __device__ __forceinline__ int vresize(uint32_t h0, uint32_t h1, uint32_t b0s, u
 template <bool RESIZE, int PXT, bool CONTENT, bool HIST, bool ALIGNED>
 __global__ void __launch_bounds__(kThreads) fused_score_kernel(const FusedParams p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    // ---- carve shared memory
+    // ---- carve shared memory (host twin: fused_smem_bytes in esd.cu)
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw);              // [kMaxStages]
     uint64_t* empty_bar = full_bar + kMaxStages;                               // [kMaxStages]
-    int4* meta = reinterpret_cast<int4*>(empty_bar + kMaxStages);              // [kMaxStages] {f, rloc|row<<8, flags, mis}
-    uint2* meta_b = reinterpret_cast<uint2*>(meta + kMaxStages);               // [kMaxStages] {b0s, b1s}
-    int* s_sdiv = reinterpret_cast<int*>(meta_b + kMaxStages);                 // [256]
+    int4* meta = reinterpret_cast<int4*>(empty_bar + kMaxStages);              // [kMaxStages] {f, rloc|row<<8, flags, nrows}
+    uint4* meta_r = reinterpret_cast<uint4*>(meta + kMaxStages);               // [kMaxStages][kMaxRowsPerStage] {b0s,b1s,mis,0}
+    int* s_sdiv = reinterpret_cast<int*>(meta_r + kMaxStages * kMaxRowsPerStage);  // [256]
     int* s_hdiv = s_sdiv + 256;                                                // [256]
     uint32_t* s_hist = reinterpret_cast<uint32_t*>(s_hdiv + 256);              // [2][256]
     uint32_t* s_prev = s_hist + 512;                                           // [rows_per_group][PXT*kConsumers]
     size_t off = (size_t)(reinterpret_cast<uint8_t*>(s_prev + (CONTENT ? p.rows_per_group * PXT * kConsumers : 0)) - smem_raw);
     off = (off + 127) & ~(size_t)127;
-    uint8_t* s_stage = smem_raw + off;                                         // [stages][2][rowbuf]
+    uint8_t* s_stage = smem_raw + off;                                         // [stages][rows_per_stage][1|2][rowbuf]
 
     const int tid = threadIdx.x;
     const int S = p.stages;
@@ -180,7 +248,9 @@ __global__ void __launch_bounds__(kThreads) fused_score_kernel(const FusedParams
     const int u_begin = p.cta_unit_begin[blockIdx.x];
     const int u_end = p.cta_unit_begin[blockIdx.x + 1];
     const int R = p.rows_per_group;
-    const int stage_bytes = (RESIZE ? 2 : 1) * p.rowbuf;
+    const int RS = p.rows_per_stage;
+    const int row_slot = (RESIZE ? 2 : 1) * p.rowbuf;  // smem bytes of one destination row's source rows
+    const int stage_bytes = RS * row_slot;
 
     if (tid >= kConsumers) {
         // ================================================================ producer warp (one lane)
@@ -202,27 +272,46 @@ __global__ void __launch_bounds__(kThreads) fused_score_kernel(const FusedParams
                     else if (f == 0) fflags |= p.has_prev ? F_CTXPREV : F_NOPREV;
                     if (f == p.n_frames - 1) fflags |= F_SAVE;
                 }
-                for (int r = r_begin; r < r_end; ++r) {
+                for (int r = r_begin; r < r_end; r += RS) {
+                    const int nr = min(RS, r_end - r);
                     mbar_wait(empty_base + 8u * s, par);
-                    const YRow yr = p.yrows[r];
-                    const uint8_t* a0 = frame + (long long)(p.compact ? yr.crow0 : yr.row0) * p.row_stride;
-                    const uint32_t mis0 = (uint32_t)(reinterpret_cast<uintptr_t>(a0) & 15u);
-                    const uint32_t bytes0 = (mis0 + (uint32_t)p.row_bytes + 15u) & ~15u;
-                    uint32_t mis1 = 0, bytes1 = 0;
-                    const uint8_t* a1 = a0;
-                    if (RESIZE) {
-                        a1 = frame + (long long)(p.compact ? yr.crow1 : yr.row1) * p.row_stride;
-                        mis1 = (uint32_t)(reinterpret_cast<uintptr_t>(a1) & 15u);
-                        bytes1 = (mis1 + (uint32_t)p.row_bytes + 15u) & ~15u;
+                    const uint8_t* src0[kMaxRowsPerStage];
+                    const uint8_t* src1[kMaxRowsPerStage];
+                    uint32_t nb0[kMaxRowsPerStage], nb1[kMaxRowsPerStage];
+                    uint32_t tx = 0;
+#pragma unroll
+                    for (int q = 0; q < kMaxRowsPerStage; ++q) {
+                        if (q < nr) {
+                            const YRow yr = p.yrows[r + q];
+                            const uint8_t* a0 = frame + (long long)(p.compact ? yr.crow0 : yr.row0) * p.row_stride;
+                            const uint32_t mis0 = ALIGNED ? 0u : (uint32_t)(reinterpret_cast<uintptr_t>(a0) & 15u);
+                            nb0[q] = (mis0 + (uint32_t)p.row_bytes + 15u) & ~15u;
+                            src0[q] = a0 - mis0;
+                            uint32_t mis1 = 0;
+                            nb1[q] = 0;
+                            src1[q] = a0;
+                            if (RESIZE) {
+                                const uint8_t* a1 = frame + (long long)(p.compact ? yr.crow1 : yr.row1) * p.row_stride;
+                                mis1 = ALIGNED ? 0u : (uint32_t)(reinterpret_cast<uintptr_t>(a1) & 15u);
+                                nb1[q] = (mis1 + (uint32_t)p.row_bytes + 15u) & ~15u;
+                                src1[q] = a1 - mis1;
+                            }
+                            tx += nb0[q] + nb1[q];
+                            meta_r[s * kMaxRowsPerStage + q] = make_uint4(yr.b0s, yr.b1s, mis0 | (mis1 << 8), 0u);
+                        }
                     }
-                    const int flags = fflags | ((r == r_end - 1) ? F_FRAME_END : 0);
-                    meta[s] = make_int4(f, (r - r_begin) | (r << 8), flags, (int)(mis0 | (mis1 << 8)));
-                    meta_b[s] = make_uint2(yr.b0s, yr.b1s);
+                    const int flags = fflags | ((r + nr >= r_end) ? F_FRAME_END : 0);
+                    meta[s] = make_int4(f, (r - r_begin) | (r << 8), flags, nr);
                     const uint32_t bar = full_base + 8u * s;
                     const uint32_t dst = stage_base + (uint32_t)s * stage_bytes;
-                    mbar_arrive_expect_tx(bar, bytes0 + bytes1);
-                    bulk_g2s(dst, a0 - mis0, bytes0, bar, pol);
-                    if (RESIZE) bulk_g2s(dst + p.rowbuf, a1 - mis1, bytes1, bar, pol);
+                    mbar_arrive_expect_tx(bar, tx);
+#pragma unroll
+                    for (int q = 0; q < kMaxRowsPerStage; ++q) {
+                        if (q < nr) {
+                            bulk_g2s(dst + q * row_slot, src0[q], nb0[q], bar, pol);
+                            if (RESIZE) bulk_g2s(dst + q * row_slot + p.rowbuf, src1[q], nb1[q], bar, pol);
+                        }
+                    }
                     if (++s == S) { s = 0; par ^= 1u; }
                 }
             }
@@ -255,64 +344,31 @@ __global__ void __launch_bounds__(kThreads) fused_score_kernel(const FusedParams
     int hist_buf = 0;
     int s = 0;
     uint32_t par = 0u;
-    for (;; ) {
+    for (;;) {
         mbar_wait(full_base + 8u * s, par);
         const int4 m = meta[s];
         const int flags = m.z;
         if (flags & F_END) break;
-        const uint2 bb = meta_b[s];
-        const int rloc = m.y & 0xff;
-        const int row = m.y >> 8;
-        const uint8_t* row0 = s_stage + (size_t)s * stage_bytes;
-        const uint8_t* row1 = row0 + p.rowbuf;
-        const uint32_t mis0 = ALIGNED ? 0u : ((uint32_t)m.w & 0xffu), mis1 = ALIGNED ? 0u : (((uint32_t)m.w >> 8) & 0xffu);
-#pragma unroll
-        for (int k = 0; k < PXT; ++k) {
-            const int d = k * kConsumers + tid;
-            if (d < p.dst_w) {
-                int b, g, r;
-                if (RESIZE) {
-                    uint32_t n0, n1;
-                    const uint32_t o0 = xoff[k] + mis0, o1 = xoff[k] + mis1;
-                    const uint32_t lo0 = lds_u32_unaligned(row0, o0, n0);
-                    const uint32_t w02 = *reinterpret_cast<const uint32_t*>(row0 + (o0 & ~3u) + 8);
-                    const uint32_t hi0 = __funnelshift_r(n0, w02, (o0 & 3u) * 8u);
-                    const uint32_t lo1 = lds_u32_unaligned(row1, o1, n1);
-                    const uint32_t w12 = *reinterpret_cast<const uint32_t*>(row1 + (o1 & ~3u) + 8);
-                    const uint32_t hi1 = __funnelshift_r(n1, w12, (o1 & 3u) * 8u);
-                    // lo = [Ab Ag Ar Bb], hi = [Bg Br . .]  ->  [Ab Bb Ag Bg] and [Ar Br . .]
-                    const uint32_t bg0 = __byte_perm(lo0, hi0, 0x4130), rr0 = __byte_perm(lo0, hi0, 0x0052);
-                    const uint32_t bg1 = __byte_perm(lo1, hi1, 0x4130), rr1 = __byte_perm(lo1, hi1, 0x0052);
-                    const uint32_t a = xa01[k];
-                    // HResizeLinear: tap0 * a0 + tap1 * a1 (scale 2^11)
-                    const uint32_t hb0 = __dp2a_lo(a, bg0, 0u), hg0 = __dp2a_hi(a, bg0, 0u), hr0 = __dp2a_lo(a, rr0, 0u);
-                    const uint32_t hb1 = __dp2a_lo(a, bg1, 0u), hg1 = __dp2a_hi(a, bg1, 0u), hr1 = __dp2a_lo(a, rr1, 0u);
-                    b = vresize(hb0, hb1, bb.x, bb.y);
-                    g = vresize(hg0, hg1, bb.x, bb.y);
-                    r = vresize(hr0, hr1, bb.x, bb.y);
-                } else {
-                    uint32_t nx;
-                    const uint32_t px = lds_u32_unaligned(row0, xoff[k] + mis0, nx);
-                    b = px & 255u;
-                    g = (px >> 8) & 255u;
-                    r = (px >> 16) & 255u;
-                }
-                if (CONTENT) {
-                    const uint32_t cur = bgr_to_hsv_packed(b, g, r, s_sdiv, s_hdiv);
-                    uint32_t* slot = s_prev + (rloc * PXT + k) * kConsumers + tid;
-                    uint32_t pv = cur;
-                    if (!(flags & (F_HALO | F_NOPREV)))
-                        pv = (flags & F_CTXPREV) ? __ldg(p.prev_in + (size_t)row * p.dst_w + d) : *slot;
-                    const uint32_t diff = __vabsdiffu4(cur, pv);
-                    acc_hv += diff & 0x00ff00ffu;
-                    acc_s += (diff >> 8) & 0xffu;
-                    *slot = cur;
-                    if (flags & F_SAVE) p.prev_out[(size_t)row * p.dst_w + d] = cur;
-                }
-                if (HIST && !(flags & F_HALO)) {
-                    const int y = (4899 * r + 9617 * g + 1868 * b + 8192) >> 14;
-                    atomicAdd(&s_hist[hist_buf * 256 + ((y * p.bins) >> 8)], 1u);
-                }
+        const int nrows = m.w;
+        const int rloc0 = m.y & 0xff;
+        const int row_first = m.y >> 8;
+        const uint8_t* stage = s_stage + (size_t)s * stage_bytes;
+        uint32_t* hist_cur = s_hist + hist_buf * 256;
+        if (flags & (F_HALO | F_NOPREV | F_CTXPREV | F_SAVE)) {
+            for (int q = 0; q < nrows; ++q) {
+                const uint4 mr = meta_r[s * kMaxRowsPerStage + q];
+                const uint32_t mis0 = ALIGNED ? 0u : (mr.z & 0xffu), mis1 = ALIGNED ? 0u : ((mr.z >> 8) & 0xffu);
+                score_row<RESIZE, PXT, CONTENT, HIST, true>(p, stage + q * row_slot, stage + q * row_slot + p.rowbuf, mis0, mis1, mr.x,
+                                                            mr.y, flags, rloc0 + q, row_first + q, tid, xoff, xa01, s_sdiv, s_hdiv,
+                                                            s_prev, hist_cur, acc_hv, acc_s);
+            }
+        } else {
+            for (int q = 0; q < nrows; ++q) {
+                const uint4 mr = meta_r[s * kMaxRowsPerStage + q];
+                const uint32_t mis0 = ALIGNED ? 0u : (mr.z & 0xffu), mis1 = ALIGNED ? 0u : ((mr.z >> 8) & 0xffu);
+                score_row<RESIZE, PXT, CONTENT, HIST, false>(p, stage + q * row_slot, stage + q * row_slot + p.rowbuf, mis0, mis1, mr.x,
+                                                             mr.y, flags, rloc0 + q, row_first + q, tid, xoff, xa01, s_sdiv, s_hdiv,
+                                                             s_prev, hist_cur, acc_hv, acc_s);
             }
         }
         __syncwarp();
@@ -321,14 +377,14 @@ __global__ void __launch_bounds__(kThreads) fused_score_kernel(const FusedParams
 
         if (flags & F_FRAME_END) {
             const bool scored = !(flags & F_HALO);
+            const int group = row_first / p.rows_per_group;
             if (CONTENT) {
                 if (scored) {
                     const uint32_t sh = __reduce_add_sync(0xffffffffu, acc_hv & 0xffffu);
                     const uint32_t sv = __reduce_add_sync(0xffffffffu, acc_hv >> 16);
                     const uint32_t ss = __reduce_add_sync(0xffffffffu, acc_s);
                     if (lane == 0)
-                        p.part[((size_t)m.x * p.n_groups + (row / p.rows_per_group)) * kConsumerWarps + warp] =
-                            make_uint4(sh, ss, sv, 0u);
+                        p.part[((size_t)m.x * p.n_groups + group) * kConsumerWarps + warp] = make_uint4(sh, ss, sv, 0u);
                 }
                 acc_hv = 0;
                 acc_s = 0;
@@ -337,7 +393,7 @@ __global__ void __launch_bounds__(kThreads) fused_score_kernel(const FusedParams
                 consumer_bar_sync();  // all smem atomics of this frame have landed
                 if (tid < p.bins) {
                     uint32_t* hslot = &s_hist[hist_buf * 256 + tid];
-                    p.hist_part[((size_t)m.x * p.n_groups + (row / p.rows_per_group)) * p.bins + tid] = (uint16_t)*hslot;
+                    p.hist_part[((size_t)m.x * p.n_groups + group) * p.bins + tid] = (uint16_t)*hslot;
                     *hslot = 0;
                 }
                 hist_buf ^= 1;  // the other buffer was zeroed one frame ago (before the barrier above)

@@ -93,6 +93,8 @@ typedef struct esd_config {
     int32_t pipeline_stages;   /* TMA ring depth per CTA */
     int32_t split_mode;        /* ESD_SPLIT_* */
     int32_t ctas_per_sm;
+    int32_t rows_per_stage;    /* destination rows staged per pipeline slot (1..4) */
+    int32_t reserved1;
     int64_t max_cuts;          /* per-detector cut capacity (default 65536) */
     int64_t initial_capacity;  /* frames of per-frame score storage to pre-allocate (grows by doubling) */
 } esd_config;
