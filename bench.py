@@ -94,6 +94,25 @@ class ClockSampler:
                 "samples": len(sm), "power_w_max": max(power)}
 
 
+def bind_to_gpu_numa_node(gpu_index: int):
+    """Pin this rank to the CPUs NVML reports as local to its GPU, so the pinned host frames of the e2e leg are
+    first-touched on the NUMA node that owns the GPU's PCIe root (matters when 8 ranks pull 50 GB/s each)."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
+
+
 def host_sample_frames(n: int, start: int = 0) -> np.ndarray:
     """n frames of the config-2 clip on the host (GPU generator if there is one, else the CPU twin)."""
     from eioku_b200 import synth
@@ -132,7 +151,7 @@ def bench_reference(args):
     from oracle import cpu_baseline
 
     cores = cpu_baseline.available_cores()
-    sample, reps = 192, 8
+    sample, reps = args.ref_sample, args.ref_reps
     frames = host_sample_frames(sample)
     times = []
     total = 0
@@ -174,6 +193,8 @@ def bench_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = f"cuda:{local}"
+    if world > 1:
+        bind_to_gpu_numa_node(local)
     dist = None
     if world > 1:
         import torch.distributed as dist  # plumbing only: barrier + max-reduce of the timing
@@ -343,6 +364,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=192)
     ap.add_argument("--cpu-reps", type=int, default=40)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--ref-sample", type=int, default=192, help="--impl reference: frames per process per pass")
+    ap.add_argument("--ref-reps", type=int, default=8, help="--impl reference: passes per process per step")
     ap.add_argument("--tune", action="append", default=[], help="esd_config field=value (e.g. rows_per_group=2)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)  # timing rule: at least 3 warm-up steps

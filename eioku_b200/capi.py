@@ -11,7 +11,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("ESD_LIB") or os.path.join(_HERE, "libesd.so")  # ESD_LIB: tuning experiments only
 
-ESD_DET_CONTENT, ESD_DET_ADAPTIVE, ESD_DET_HIST = 1, 2, 4
+ESD_DET_CONTENT, ESD_DET_ADAPTIVE, ESD_DET_HIST, ESD_DET_THRESHOLD = 1, 2, 4, 8
+ESD_THRESH_FLOOR, ESD_THRESH_CEILING = 0, 1
 ESD_FILTER_MERGE, ESD_FILTER_SUPPRESS = 0, 1
 ESD_DOWNSCALE_FLOAT, ESD_DOWNSCALE_INT = 0, 1
 ESD_SPLIT_AUTO, ESD_SPLIT_STRIPS, ESD_SPLIT_CHUNKS = 0, 1, 2
@@ -21,7 +22,8 @@ EXPORTED_SYMBOLS = (
     "esd_abi_version", "esd_strerror", "esd_last_error", "esd_device_count", "esd_config_default",
     "esd_create", "esd_destroy", "esd_reset", "esd_get_geometry", "esd_get_touched_rows",
     "esd_push_frames", "esd_push_rows", "esd_ingest_open", "esd_ingest_push_host", "esd_ingest_close",
-    "esd_ingest_stats", "esd_synchronize", "esd_join", "esd_frames_pushed", "esd_read_scores", "esd_get_cuts",
+    "esd_ingest_stats", "esd_synchronize", "esd_join", "esd_frames_pushed", "esd_read_scores", "esd_read_average_rgb",
+    "esd_post_process", "esd_get_cuts",
     "esd_decide_arrays", "esd_debug_read_prev", "esd_set_timing", "esd_kernel_time", "esd_kernel_launches", "esd_synth_fill",
 )
 
@@ -39,6 +41,9 @@ class EsdConfig(C.Structure):
         ("adaptive_weights", C.c_double * 4), ("adaptive_weight_div", C.c_double),
         ("adaptive_window_width", C.c_int32), ("adaptive_min_scene_len", C.c_int32),
         ("hist_threshold", C.c_double), ("hist_bins", C.c_int32), ("hist_min_scene_len", C.c_int32),
+        ("thresh_threshold", C.c_double), ("thresh_fade_bias", C.c_double),
+        ("thresh_min_scene_len", C.c_int32), ("thresh_add_final_scene", C.c_int32),
+        ("thresh_method", C.c_int32), ("reserved2", C.c_int32),
         ("rows_per_group", C.c_int32), ("pipeline_stages", C.c_int32),
         ("split_mode", C.c_int32), ("ctas_per_sm", C.c_int32),
         ("rows_per_stage", C.c_int32), ("reserved1", C.c_int32),
@@ -101,6 +106,8 @@ def load_library(path: Optional[str] = None):
     L.esd_frames_pushed.argtypes = [vp]
     L.esd_read_scores.argtypes = [vp, i64, i64, vp, vp, vp, vp, vp, vp]
     L.esd_get_cuts.argtypes = [vp, i32, i64, vp, i64, C.POINTER(i64), C.POINTER(i64)]
+    L.esd_read_average_rgb.argtypes = [vp, i64, i64, vp]
+    L.esd_post_process.argtypes = [vp, i32, i64, vp, i64, C.POINTER(i64)]
     L.esd_decide_arrays.argtypes = [vp, i32, i64, i64, vp, vp, vp, i64, C.POINTER(i64)]
     L.esd_debug_read_prev.argtypes = [vp, vp, i64]
     L.esd_set_timing.argtypes = [vp, i32]
@@ -255,7 +262,7 @@ class EsdContext:
 
     def read_scores(self, from_frame: int, n: int, want: Sequence[str] = ()):
         """-> dict with any of sums3, content_val, adaptive_val, adaptive_ratio, hist, hist_diff."""
-        has_content = bool(self.cfg.detectors & (ESD_DET_CONTENT | ESD_DET_ADAPTIVE))
+        has_content = bool(self.cfg.detectors & (ESD_DET_CONTENT | ESD_DET_ADAPTIVE | ESD_DET_THRESHOLD))
         has_hist = bool(self.cfg.detectors & ESD_DET_HIST)
         if not want:
             want = (["sums3", "content_val", "adaptive_val", "adaptive_ratio"] if has_content else []) + \
@@ -272,6 +279,18 @@ class EsdContext:
             _np_ptr(out.get("adaptive_val")), _np_ptr(out.get("adaptive_ratio")), _np_ptr(out.get("hist")),
             _np_ptr(out.get("hist_diff"))), "esd_read_scores")
         return out
+
+    def read_average_rgb(self, from_frame: int, n: int) -> np.ndarray:
+        out = np.empty(n, np.float64)
+        self._check(self._L.esd_read_average_rgb(self._h, from_frame, n, _np_ptr(out)), "esd_read_average_rgb")
+        return out
+
+    def post_process(self, detector: int, last_frame_num: int):
+        buf = np.empty(4, np.int64)
+        nc = C.c_int64()
+        self._check(self._L.esd_post_process(self._h, detector, last_frame_num, _np_ptr(buf), buf.size, C.byref(nc)),
+                    "esd_post_process")
+        return buf[: nc.value].tolist()
 
     def get_cuts(self, detector: int, from_index: int = 0):
         """-> (list of cut frame numbers from `from_index` on, total cuts emitted)."""

@@ -88,6 +88,7 @@ struct esd_ctx {
     double* d_av = nullptr;
     double* d_ratio = nullptr;
     double* d_hdiff = nullptr;
+    double* d_avg = nullptr;       // ThresholdDetector average_rgb
     uint32_t* d_counts = nullptr;  // [cap][bins]
     uint8_t* d_slab = nullptr;     // backing allocation of the six arrays above
 
@@ -293,7 +294,7 @@ int ensure_capacity(esd_ctx* c, int64_t frames_needed) {
     const int64_t ncap = std::max<int64_t>(c->cap ? c->cap * 2 : std::max<int64_t>(4096, c->cfg.initial_capacity), frames_needed);
     { int rc0 = sync_all(c); if (rc0) return rc0; }
     const int64_t bins = c->need_hist ? c->cfg.hist_bins : 0;
-    const size_t bytes = (size_t)ncap * (3 * sizeof(unsigned long long) + 4 * sizeof(double) + bins * sizeof(uint32_t));
+    const size_t bytes = (size_t)ncap * (3 * sizeof(unsigned long long) + 5 * sizeof(double) + bins * sizeof(uint32_t));
     uint8_t* slab = nullptr;
     CU(c, cudaMalloc(&slab, bytes));
     uint8_t* q = slab;
@@ -309,6 +310,7 @@ int ensure_capacity(esd_ctx* c, int64_t frames_needed) {
     auto* n_av = carve(&c->d_av, 1);
     auto* n_ratio = carve(&c->d_ratio, 1);
     auto* n_hdiff = carve(&c->d_hdiff, 1);
+    auto* n_avg = carve(&c->d_avg, 1);
     auto* n_counts = carve(&c->d_counts, bins);
     if (used > 0) {
         CU(c, cudaMemcpy(n_sums, c->d_sums3, sizeof(unsigned long long) * 3 * used, cudaMemcpyDeviceToDevice));
@@ -316,11 +318,12 @@ int ensure_capacity(esd_ctx* c, int64_t frames_needed) {
         CU(c, cudaMemcpy(n_av, c->d_av, sizeof(double) * used, cudaMemcpyDeviceToDevice));
         CU(c, cudaMemcpy(n_ratio, c->d_ratio, sizeof(double) * used, cudaMemcpyDeviceToDevice));
         CU(c, cudaMemcpy(n_hdiff, c->d_hdiff, sizeof(double) * used, cudaMemcpyDeviceToDevice));
+        CU(c, cudaMemcpy(n_avg, c->d_avg, sizeof(double) * used, cudaMemcpyDeviceToDevice));
         if (bins) CU(c, cudaMemcpy(n_counts, c->d_counts, sizeof(uint32_t) * bins * used, cudaMemcpyDeviceToDevice));
     }
     cudaFree(c->d_slab);
     c->d_slab = slab;
-    c->d_sums3 = n_sums; c->d_cv = n_cv; c->d_av = n_av; c->d_ratio = n_ratio; c->d_hdiff = n_hdiff;
+    c->d_sums3 = n_sums; c->d_cv = n_cv; c->d_av = n_av; c->d_ratio = n_ratio; c->d_hdiff = n_hdiff; c->d_avg = n_avg;
     c->d_counts = bins ? n_counts : nullptr;
     // ratios not yet computed read back as NaN
     fill_nan_kernel<<<(unsigned)((ncap - used + 255) / 256), 256>>>(c->d_ratio + used, ncap - used);
@@ -432,6 +435,7 @@ int push_common(esd_ctx* c, const uint8_t* d_src, int64_t n, int64_t frame_strid
     p.rowbuf = c->rowbuf;
     p.has_prev = base > 0 ? 1 : 0;
     p.bins = c->cfg.hist_bins;
+    p.want_bgr = (c->cfg.detectors & ESD_DET_THRESHOLD) ? 1 : 0;
     p.yrows = c->d_yrows;
     p.xtab = c->d_xtab;
     p.sdiv = c->d_sdiv;
@@ -472,7 +476,7 @@ int push_common(esd_ctx* c, const uint8_t* d_src, int64_t n, int64_t frame_strid
         const int warps_per_block = 8;
         finalize_sums_kernel<<<(unsigned)((n + warps_per_block - 1) / warps_per_block), warps_per_block * 32, 0, ts>>>(
             c->d_part[buf], (int)n, c->n_groups * kConsumerWarps, npx, c->wc, c->wa, c->d_sums3 + 3 * base, c->d_cv + base,
-            c->d_av + base);
+            c->d_av + base, c->d_avg + base);
         CU(c, cudaGetLastError());
         c->launches++;
         if (c->cfg.detectors & ESD_DET_ADAPTIVE) {
@@ -496,7 +500,7 @@ int push_common(esd_ctx* c, const uint8_t* d_src, int64_t n, int64_t frame_strid
         CU(c, cudaGetLastError());
         c->launches += 2;
     }
-    decide_kernel<<<3, 256, 0, ts>>>(c->dparams, c->d_state, c->d_cuts, c->d_cv, c->d_av, c->d_ratio, c->d_hdiff,
+    decide_kernel<<<4, 256, 0, ts>>>(c->dparams, c->d_state, c->d_cuts, c->d_cv, c->d_av, c->d_ratio, c->d_hdiff, c->d_avg,
                                      c->first_frame, base, base + n);
     CU(c, cudaGetLastError());
     CU(c, cudaEventRecord(c->ev_fin[buf], ts));
@@ -571,6 +575,9 @@ void esd_config_default(esd_config* cfg) {
     cfg->hist_threshold = 0.05;
     cfg->hist_bins = 256;
     cfg->hist_min_scene_len = 15;
+    cfg->thresh_threshold = 12.0;
+    cfg->thresh_min_scene_len = 15;
+    cfg->thresh_method = ESD_THRESH_FLOOR;
 }
 
 int esd_create(esd_ctx** out, const esd_config* cfg, int device) {
@@ -579,7 +586,7 @@ int esd_create(esd_ctx** out, const esd_config* cfg, int device) {
     if (cfg->struct_size != sizeof(esd_config))
         return fail(nullptr, ESD_ERR_INVALID, "esd_create: struct_size %u != %zu (ABI mismatch)", cfg->struct_size,
                     sizeof(esd_config));
-    if (!(cfg->detectors & 7) || (cfg->detectors & ~7)) return fail(nullptr, ESD_ERR_INVALID, "esd_create: bad detector mask");
+    if (!(cfg->detectors & 15) || (cfg->detectors & ~15)) return fail(nullptr, ESD_ERR_INVALID, "esd_create: bad detector mask");
     if (cfg->src_width < 1 || cfg->src_height < 1) return fail(nullptr, ESD_ERR_INVALID, "esd_create: bad frame size");
     if (cfg->content_weights[3] != 0.0 || cfg->adaptive_weights[3] != 0.0)
         return fail(nullptr, ESD_ERR_UNSUPPORTED, "delta_edges weight must be 0 (Canny/dilate is outside the hot path)");
@@ -637,7 +644,7 @@ int esd_create(esd_ctx** out, const esd_config* cfg, int device) {
     c->dst_w = dw; c->dst_h = dh;
     c->resize = !(dw == W && dh == H);
     c->row_bytes = W * 3;
-    c->need_content = (cfg->detectors & (ESD_DET_CONTENT | ESD_DET_ADAPTIVE)) != 0;
+    c->need_content = (cfg->detectors & (ESD_DET_CONTENT | ESD_DET_ADAPTIVE | ESD_DET_THRESHOLD)) != 0;
     c->need_hist = (cfg->detectors & ESD_DET_HIST) != 0;
     if (dw > kConsumers * (c->resize ? 4 : 16)) {
         fail(c, ESD_ERR_UNSUPPORTED, "destination width %d too large (max %d)", dw, kConsumers * (c->resize ? 4 : 16));
@@ -756,9 +763,13 @@ int esd_create(esd_ctx** out, const esd_config* cfg, int device) {
     P.adaptive_min_content_val = cfg->adaptive_min_content_val;
     P.hist_threshold = std::max(0.0, std::min(1.0, 1.0 - cfg->hist_threshold));
     P.max_cuts = c->max_cuts;
+    P.thresh_threshold = (double)(long long)cfg->thresh_threshold;  // self.threshold = int(threshold)
+    P.thresh_fade_bias = cfg->thresh_fade_bias;
+    P.thresh_min_scene_len = cfg->thresh_min_scene_len;
+    P.thresh_method = cfg->thresh_method;
 
     CUB(cudaMalloc(&c->d_state, sizeof(DecisionState)));
-    CUB(cudaMalloc(&c->d_cuts, sizeof(long long) * 3 * c->max_cuts));
+    CUB(cudaMalloc(&c->d_cuts, sizeof(long long) * 4 * c->max_cuts));
     if (c->need_content) {
         CUB(cudaMalloc(&c->d_prev[0], sizeof(uint32_t) * dw * dh));
         CUB(cudaMalloc(&c->d_prev[1], sizeof(uint32_t) * dw * dh));
@@ -983,7 +994,41 @@ int esd_read_scores(esd_ctx* c, int64_t from_frame, int64_t n, uint64_t* sums3, 
 }
 
 static int det_index(int32_t detector) {
-    return detector == ESD_DET_CONTENT ? 0 : detector == ESD_DET_ADAPTIVE ? 1 : detector == ESD_DET_HIST ? 2 : -1;
+    return detector == ESD_DET_CONTENT ? 0 : detector == ESD_DET_ADAPTIVE ? 1 : detector == ESD_DET_HIST ? 2
+         : detector == ESD_DET_THRESHOLD ? 3 : -1;
+}
+
+int esd_read_average_rgb(esd_ctx* c, int64_t from_frame, int64_t n, double* average_rgb) {
+    if (!c || !average_rgb) return ESD_ERR_INVALID;
+    if (n == 0) return ESD_OK;
+    const int64_t i0 = from_frame - c->first_frame;
+    if (!c->started || n < 0 || i0 < 0 || i0 + n > c->n_frames)
+        return fail(c, ESD_ERR_INVALID, "read_average_rgb: range outside pushed frames");
+    if (!(c->cfg.detectors & ESD_DET_THRESHOLD)) return fail(c, ESD_ERR_STATE, "read_average_rgb: no threshold detector configured");
+    int rc = esd_synchronize(c);
+    if (rc) return rc;
+    CU(c, cudaMemcpy(average_rgb, c->d_avg + i0, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    return ESD_OK;
+}
+
+int esd_post_process(esd_ctx* c, int32_t detector, int64_t last_frame_num, int64_t* cuts, int64_t cap, int64_t* n_cuts) {
+    if (!c) return ESD_ERR_INVALID;
+    if (det_index(detector) < 0 || !(c->cfg.detectors & detector)) return fail(c, ESD_ERR_INVALID, "post_process: detector %d not configured", detector);
+    if (n_cuts) *n_cuts = 0;
+    if (detector != ESD_DET_THRESHOLD) return ESD_OK;  // the other detectors' post_process returns []
+    int rc = esd_synchronize(c);
+    if (rc) return rc;
+    DecisionState st;
+    CU(c, cudaMemcpy(&st, c->d_state, sizeof st, cudaMemcpyDeviceToHost));
+    // ThresholdDetector.post_process: close the scene at the last fade-out when asked to
+    const int L = c->cfg.thresh_min_scene_len;
+    const bool len_ok = st.t_init ? (last_frame_num - st.t_last_scene_cut) >= L : last_frame_num >= L;
+    if (st.t_processed && st.t_fade_out && c->cfg.thresh_add_final_scene && len_ok) {
+        if (cap < 1 || !cuts) return fail(c, ESD_ERR_CAPACITY, "post_process: buffer too small");
+        cuts[0] = st.t_fade_frame;
+        if (n_cuts) *n_cuts = 1;
+    }
+    return ESD_OK;
 }
 
 int esd_get_cuts(esd_ctx* c, int32_t detector, int64_t from_index, int64_t* cuts, int64_t cap, int64_t* n_written,
@@ -1032,7 +1077,7 @@ int esd_decide_arrays(esd_ctx* c, int32_t detector, int64_t first_frame_num, int
     CUD(cudaMalloc(&d_scores, sizeof(double) * n));
     CUD(cudaMalloc(&d_ratio, sizeof(double) * n));
     CUD(cudaMalloc(&d_st, sizeof(DecisionState)));
-    CUD(cudaMalloc(&d_cuts, sizeof(long long) * 3 * c->max_cuts));
+    CUD(cudaMalloc(&d_cuts, sizeof(long long) * 4 * c->max_cuts));
     CUD(cudaMemcpy(d_scores, scores, sizeof(double) * n, cudaMemcpyHostToDevice));
     CUD(cudaMemset(d_st, 0, sizeof(DecisionState)));
     fill_nan_kernel<<<(unsigned)((n + 255) / 256), 256>>>(d_ratio, n);
@@ -1044,7 +1089,7 @@ int esd_decide_arrays(esd_ctx* c, int32_t detector, int64_t first_frame_num, int
             adaptive_ratio_kernel<<<(unsigned)((n - 2 * w + 255) / 256), 256>>>(d_scores, d_ratio, w, n - w, w,
                                                                                P.adaptive_min_content_val);
     }
-    decide_kernel<<<3, 256>>>(P, d_st, d_cuts, d_scores, d_scores, d_ratio, d_scores, first_frame_num, 0, n);
+    decide_kernel<<<4, 256>>>(P, d_st, d_cuts, d_scores, d_scores, d_ratio, d_scores, d_scores, first_frame_num, 0, n);
     c->launches += 3;
     CUD(cudaGetLastError());
     CUD(cudaDeviceSynchronize());

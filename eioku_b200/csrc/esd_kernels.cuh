@@ -50,6 +50,7 @@ struct FusedParams {
     int rowbuf;  // bytes reserved per staged source row (multiple of 16)
     int has_prev;
     int bins;
+    int want_bgr;  // also accumulate sum(B+G+R) per frame (ThresholdDetector's average_rgb)
     const YRow* yrows;
     const uint2* xtab;  // per destination column: {byte offset of tap 0, a0 | a1 << 16}
     const int* sdiv;
@@ -152,7 +153,7 @@ __device__ __forceinline__ void score_row(const FusedParams& p, const uint8_t* _
                                           int row, int tid, const uint32_t (&xoff)[PXT], const uint32_t (&xa01)[PXT],
                                           const int* __restrict__ s_sdiv, const int* __restrict__ s_hdiv,
                                           uint32_t* __restrict__ s_prev, uint32_t* __restrict__ s_hist_cur,
-                                          uint32_t& acc_hv, uint32_t& acc_s) {
+                                          uint32_t& acc_hv, uint32_t& acc_s, uint32_t& acc_bgr) {
 #pragma unroll
     for (int k = 0; k < PXT; ++k) {
         const int d = k * kConsumers + tid;
@@ -185,6 +186,7 @@ __device__ __forceinline__ void score_row(const FusedParams& p, const uint8_t* _
                 r = (px >> 16) & 255u;
             }
             if (CONTENT) {
+                if (p.want_bgr && !(SPECIAL && (flags & F_HALO))) acc_bgr += (uint32_t)(b + g + r);
                 const uint32_t cur = bgr_to_hsv_packed(b, g, r, s_sdiv, s_hdiv);
                 uint32_t* slot = s_prev + (rloc * PXT + k) * kConsumers + tid;
                 uint32_t pv;
@@ -341,6 +343,7 @@ __global__ void __launch_bounds__(kThreads) fused_score_kernel(const FusedParams
     }
     const uint32_t full_base = smem_u32(full_bar), empty_base = smem_u32(empty_bar);
     uint32_t acc_hv = 0, acc_s = 0;  // per-frame, per-thread: H | V << 16 and S
+    uint32_t acc_bgr = 0;            // per-frame, per-thread: sum of B+G+R (only when p.want_bgr)
     int hist_buf = 0;
     int s = 0;
     uint32_t par = 0u;
@@ -360,7 +363,7 @@ __global__ void __launch_bounds__(kThreads) fused_score_kernel(const FusedParams
                 const uint32_t mis0 = ALIGNED ? 0u : (mr.z & 0xffu), mis1 = ALIGNED ? 0u : ((mr.z >> 8) & 0xffu);
                 score_row<RESIZE, PXT, CONTENT, HIST, true>(p, stage + q * row_slot, stage + q * row_slot + p.rowbuf, mis0, mis1, mr.x,
                                                             mr.y, flags, rloc0 + q, row_first + q, tid, xoff, xa01, s_sdiv, s_hdiv,
-                                                            s_prev, hist_cur, acc_hv, acc_s);
+                                                            s_prev, hist_cur, acc_hv, acc_s, acc_bgr);
             }
         } else {
             for (int q = 0; q < nrows; ++q) {
@@ -368,7 +371,7 @@ __global__ void __launch_bounds__(kThreads) fused_score_kernel(const FusedParams
                 const uint32_t mis0 = ALIGNED ? 0u : (mr.z & 0xffu), mis1 = ALIGNED ? 0u : ((mr.z >> 8) & 0xffu);
                 score_row<RESIZE, PXT, CONTENT, HIST, false>(p, stage + q * row_slot, stage + q * row_slot + p.rowbuf, mis0, mis1, mr.x,
                                                              mr.y, flags, rloc0 + q, row_first + q, tid, xoff, xa01, s_sdiv, s_hdiv,
-                                                             s_prev, hist_cur, acc_hv, acc_s);
+                                                             s_prev, hist_cur, acc_hv, acc_s, acc_bgr);
             }
         }
         __syncwarp();
@@ -383,11 +386,13 @@ __global__ void __launch_bounds__(kThreads) fused_score_kernel(const FusedParams
                     const uint32_t sh = __reduce_add_sync(0xffffffffu, acc_hv & 0xffffu);
                     const uint32_t sv = __reduce_add_sync(0xffffffffu, acc_hv >> 16);
                     const uint32_t ss = __reduce_add_sync(0xffffffffu, acc_s);
+                    const uint32_t sb = p.want_bgr ? __reduce_add_sync(0xffffffffu, acc_bgr) : 0u;
                     if (lane == 0)
-                        p.part[((size_t)m.x * p.n_groups + group) * kConsumerWarps + warp] = make_uint4(sh, ss, sv, 0u);
+                        p.part[((size_t)m.x * p.n_groups + group) * kConsumerWarps + warp] = make_uint4(sh, ss, sv, sb);
                 }
                 acc_hv = 0;
                 acc_s = 0;
+                acc_bgr = 0;
             }
             if (HIST && scored) {
                 consumer_bar_sync();  // all smem atomics of this frame have landed
@@ -424,21 +429,24 @@ __device__ __forceinline__ double content_val_of(const unsigned long long s[3], 
 // one warp per frame: reduce the per-(group,warp) partials, emit sums and both content_val flavours
 __global__ void finalize_sums_kernel(const uint4* __restrict__ part, int n_frames, int parts_per_frame, double npx,
                                      ScoreWeights wc, ScoreWeights wa, unsigned long long* __restrict__ sums3,
-                                     double* __restrict__ content_val, double* __restrict__ adaptive_val) {
+                                     double* __restrict__ content_val, double* __restrict__ adaptive_val,
+                                     double* __restrict__ average_rgb) {
     const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (f >= n_frames) return;
     unsigned long long s[3] = {0, 0, 0};
+    unsigned long long sb = 0;
     const uint4* pf = part + (size_t)f * parts_per_frame;
     for (int i = lane; i < parts_per_frame; i += 32) {
         const uint4 v = pf[i];
-        s[0] += v.x; s[1] += v.y; s[2] += v.z;
+        s[0] += v.x; s[1] += v.y; s[2] += v.z; sb += v.w;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         s[0] += __shfl_xor_sync(0xffffffffu, s[0], o);
         s[1] += __shfl_xor_sync(0xffffffffu, s[1], o);
         s[2] += __shfl_xor_sync(0xffffffffu, s[2], o);
+        sb += __shfl_xor_sync(0xffffffffu, sb, o);
     }
     if (lane == 0) {
         sums3[3 * (size_t)f] = s[0];
@@ -446,6 +454,8 @@ __global__ void finalize_sums_kernel(const uint4* __restrict__ part, int n_frame
         sums3[3 * (size_t)f + 2] = s[2];
         content_val[f] = content_val_of(s, npx, wc);
         adaptive_val[f] = content_val_of(s, npx, wa);
+        // ThresholdDetector._compute_frame_average: numpy.sum(frame) / float(rows * cols * channels)
+        average_rgb[f] = __ddiv_rn((double)sb, __dmul_rn(npx, 3.0));
     }
 }
 
@@ -572,8 +582,11 @@ struct DecisionState {
     long long a_last_cut;
     int a_init, pad1;
     long long h_last_cut;  // 0 == "not set" (Python falsiness of `if not self._last_scene_cut`)
-    long long n_cuts[3];
+    long long n_cuts[4];
     int overflow, pad2;
+    // ThresholdDetector: last_scene_cut, last_fade {frame, type}, processed_frame
+    long long t_last_scene_cut, t_fade_frame;
+    int t_init, t_processed, t_fade_out, pad3;
 };
 
 struct DecisionParams {
@@ -585,6 +598,9 @@ struct DecisionParams {
     double adaptive_threshold, adaptive_min_content_val;
     double hist_threshold;  // already clamp(1 - t, 0, 1)
     long long max_cuts;
+    double thresh_threshold;  // int(threshold) as double
+    double thresh_fade_bias;
+    int thresh_min_scene_len, thresh_method;  // method 0 FLOOR, 1 CEILING
 };
 
 struct CutSink {
@@ -598,14 +614,15 @@ struct CutSink {
     }
 };
 
-// grid = 3 blocks (content, adaptive, hist); frames [i_begin, i_end) are indices from first_frame_num.
+// grid = 4 blocks (content, adaptive, hist, threshold); frames [i_begin, i_end) are indices from first_frame_num.
 // The threshold tests run in parallel into a shared bitmask; one thread then walks the sequential
 // FlashFilter / min_scene_len state machine (A.5-A.7) with its state in registers, visiting only
 // frames that can change it (set bits, or every frame while a MERGE burst is open).
 __global__ void decide_kernel(DecisionParams P, DecisionState* __restrict__ st, long long* __restrict__ cuts,
                               const double* __restrict__ content_val, const double* __restrict__ adaptive_val,
                               const double* __restrict__ adaptive_ratio, const double* __restrict__ hist_diff,
-                              long long first_frame_num, long long i_begin, long long i_end) {
+                              const double* __restrict__ average_rgb, long long first_frame_num, long long i_begin,
+                              long long i_end) {
     constexpr int CH = 8192;
     __shared__ uint32_t bits[CH / 32];
     const int det = blockIdx.x;
@@ -625,11 +642,18 @@ __global__ void decide_kernel(DecisionParams P, DecisionState* __restrict__ st, 
         } else if (det == 1) {
             last = st->a_last_cut; init = st->a_init;
             if (!init) { init = 1; last = first_frame_num + i_begin; }
-        } else {
+        } else if (det == 2) {
             last = st->h_last_cut;
+        } else {
+            last = st->t_last_scene_cut; init = st->t_init;
+            if (!init) { init = 1; last = first_frame_num + i_begin; }
         }
     }
-    const int L = det == 0 ? P.content_min_scene_len : det == 1 ? P.adaptive_min_scene_len : P.hist_min_scene_len;
+    const int L = det == 0 ? P.content_min_scene_len : det == 1 ? P.adaptive_min_scene_len
+                : det == 2 ? P.hist_min_scene_len : P.thresh_min_scene_len;
+    // ThresholdDetector state (thread 0): merge_start doubles as last_fade.frame
+    int t_processed = 0, t_fade_out = 0;
+    if (tid == 0 && det == 3) { t_processed = st->t_processed; t_fade_out = st->t_fade_out; merge_start = st->t_fade_frame; }
 
     for (long long c0 = i_begin; c0 < i_end; c0 += CH) {
         const long long c1 = (c0 + CH < i_end) ? c0 + CH : i_end;
@@ -642,7 +666,8 @@ __global__ void decide_kernel(DecisionParams P, DecisionState* __restrict__ st, 
                     const long long t = i - P.adaptive_w;
                     if (i >= 2LL * P.adaptive_w)
                         bit = adaptive_ratio[t] >= P.adaptive_threshold && adaptive_val[t] >= P.adaptive_min_content_val;
-                } else bit = hist_diff[i] <= P.hist_threshold;  // NaN (no previous frame) compares false
+                } else if (det == 2) bit = hist_diff[i] <= P.hist_threshold;  // NaN (no previous frame) compares false
+                else bit = average_rgb[i] < P.thresh_threshold;                // "below the fade threshold"
             }
             const uint32_t word = __ballot_sync(0xffffffffu, bit);
             if ((tid & 31) == 0) bits[j >> 5] = word;
@@ -651,6 +676,47 @@ __global__ void decide_kernel(DecisionParams P, DecisionState* __restrict__ st, 
         if (tid == 0) {
             const int nj = (int)(c1 - c0);
             int j = 0;
+            if (det == 3) {
+                // ThresholdDetector.process_frame: fades are crossings of the threshold; FLOOR fades out below it,
+                // CEILING fades out at/above it.  Only frames where the "faded out" predicate flips matter.
+                while (j < nj) {
+                    const bool below = (bits[j >> 5] >> (j & 31)) & 1u;
+                    const long long fn = first_frame_num + c0 + j;
+                    if (!t_processed) {
+                        merge_start = 0;        // last_fade.frame
+                        t_fade_out = below;     // first frame: type is 'out' iff frame_avg < threshold (both methods)
+                        t_processed = 1;
+                        ++j;
+                        continue;
+                    }
+                    const bool out_now = (P.thresh_method == 0) ? below : !below;
+                    if (out_now == (bool)t_fade_out) {  // no transition: skip ahead to the next flip of `below`
+                        uint32_t word = bits[j >> 5] >> (j & 31);
+                        if (!below) { if (word == 0) { j = (j | 31) + 1; continue; } j += __ffs(word) - 1; }
+                        else {
+                            word = ~word & (0xffffffffu >> (j & 31));
+                            if (word == 0) { j = (j | 31) + 1; continue; }
+                            j += __ffs(word) - 1;
+                        }
+                        continue;
+                    }
+                    if (!t_fade_out) {  // was 'in', now faded out: remember where
+                        t_fade_out = 1;
+                        merge_start = fn;
+                    } else {            // was 'out', now faded in: emit the split point if the scene is long enough
+                        if ((fn - last) >= L) {
+                            const long long f_out = merge_start;
+                            const long long bias = (long long)(P.thresh_fade_bias * (double)(fn - f_out));
+                            sink.emit((long long)((double)(fn + f_out + bias) / 2.0));
+                            last = fn;
+                        }
+                        t_fade_out = 0;
+                        merge_start = fn;
+                    }
+                    ++j;
+                }
+                j = nj;
+            }
             while (j < nj) {
                 if (det == 0 && merge_triggered) {
                     // Open MERGE burst: nothing changes between above-threshold frames, and the burst closes at
@@ -721,8 +787,11 @@ __global__ void decide_kernel(DecisionParams P, DecisionState* __restrict__ st, 
             st->c_merge_enabled = merge_enabled; st->c_merge_triggered = merge_triggered;
         } else if (det == 1) {
             st->a_last_cut = last; st->a_init = init;
-        } else {
+        } else if (det == 2) {
             st->h_last_cut = last;
+        } else {
+            st->t_last_scene_cut = last; st->t_init = init; st->t_processed = t_processed;
+            st->t_fade_out = t_fade_out; st->t_fade_frame = merge_start;
         }
     }
 }

@@ -84,6 +84,7 @@ class SceneDetector:
     def __init__(self):
         self.stats_manager = None
         self._ctx: Optional[capi.EsdContext] = None
+        self._manager_ctx: Optional[capi.EsdContext] = None  # set by SceneManager while it drives this detector
         self._cuts_seen = 0
         self._device = 0
 
@@ -324,3 +325,47 @@ class HistogramDetector(SceneDetector):
     def _metrics_for(self, scores, k):
         d = scores["hist_diff"][k]
         return {self._metric_keys[0]: float(d)} if d == d else {}
+
+
+class ThresholdDetector(SceneDetector):
+    """scenedetect.detectors.ThresholdDetector: fade out / fade in detection on the average B,G,R value of the
+    frame.  Cuts are placed between a fade-out and the next fade-in."""
+
+    class Method(Enum):
+        FLOOR = 0    # fade out when the frame average falls below the threshold
+        CEILING = 1  # fade out when it rises to / above the threshold
+
+    THRESHOLD_VALUE_KEY = "average_rgb"
+    _DET_FLAG = capi.ESD_DET_THRESHOLD
+
+    def __init__(self, threshold: float = 12, min_scene_len: int = 15, fade_bias: float = 0.0,
+                 add_final_scene: bool = False, method: "ThresholdDetector.Method" = Method.FLOOR, block_size=None):
+        super().__init__()
+        self.threshold = int(threshold)
+        self.method = ThresholdDetector.Method(method)
+        self.fade_bias = fade_bias
+        self.min_scene_len = min_scene_len
+        self.add_final_scene = add_final_scene
+        self._metric_keys = [ThresholdDetector.THRESHOLD_VALUE_KEY]
+
+    def get_metrics(self) -> List[str]:
+        return self._metric_keys
+
+    def _fill_config(self, cfg):
+        cfg.detectors |= capi.ESD_DET_THRESHOLD
+        cfg.thresh_threshold = float(self.threshold)
+        cfg.thresh_fade_bias = float(self.fade_bias)
+        cfg.thresh_min_scene_len = int(self.min_scene_len)
+        cfg.thresh_add_final_scene = 1 if self.add_final_scene else 0
+        cfg.thresh_method = int(self.method.value)
+
+    def post_process(self, frame_num: int) -> List[int]:
+        ctx = self._ctx or self._manager_ctx
+        if ctx is None:
+            return []
+        return ctx.post_process(capi.ESD_DET_THRESHOLD, frame_num)
+
+    def _publish_late_metrics(self, first_frame_num: int, n: int):
+        avg = self._ctx.read_average_rgb(first_frame_num, n)
+        for k in range(n):
+            self.stats_manager.set_metrics(first_frame_num + k, {self._metric_keys[0]: float(avg[k])})

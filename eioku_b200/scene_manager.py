@@ -12,7 +12,8 @@ from typing import Iterable, List, Optional, Sequence, Tuple
 import numpy as np
 
 from . import capi
-from .detectors import AdaptiveDetector, ContentDetector, HistogramDetector, SceneDetector, StatsManager
+from .detectors import (AdaptiveDetector, ContentDetector, HistogramDetector, SceneDetector, StatsManager,
+                        ThresholdDetector)
 
 DEFAULT_MIN_WIDTH: int = 256
 
@@ -126,7 +127,7 @@ class SceneManager:
     def add_detector(self, detector: SceneDetector) -> None:
         kinds = [type(d)._DET_FLAG for d in self._detector_list]
         if type(detector)._DET_FLAG in kinds:
-            raise ValueError("one detector of each kind (content / adaptive / histogram) per SceneManager")
+            raise ValueError("one detector of each kind (content / adaptive / histogram / threshold) per SceneManager")
         if self.stats_manager is not None:
             detector.stats_manager = self.stats_manager
             self.stats_manager.register_metrics(detector.get_metrics())
@@ -212,11 +213,15 @@ class SceneManager:
         self._cutting_list = []
         for det in self._detector_list:
             cuts, _ = ctx.get_cuts(type(det)._DET_FLAG, 0)
+            det._manager_ctx = ctx
+            cuts = cuts + det.post_process(pos - 1)
+            det._manager_ctx = None
             self._cuts_by_detector[type(det).__name__] = cuts
             self._cutting_list += cuts
-            self._cutting_list += det.post_process(pos - 1)
         if collect_scores or self.stats_manager is not None:
             self.scores = ctx.read_scores(start, total)
+            if any(isinstance(d, ThresholdDetector) for d in self._detector_list):
+                self.scores["average_rgb"] = ctx.read_average_rgb(start, total)
             if self.stats_manager is not None:
                 self._publish_stats(start, total)
         if host_ring_open:
@@ -246,6 +251,10 @@ class SceneManager:
                     d = sc["hist_diff"][k]
                     if d == d:
                         self.stats_manager.set_metrics(fn, {det.get_metrics()[0]: float(d)})
+            if isinstance(det, ThresholdDetector):
+                avg = self._ctx.read_average_rgb(start, total)
+                for k in range(total):
+                    self.stats_manager.set_metrics(start + k, {det.get_metrics()[0]: float(avg[k])})
 
     def get_cut_list(self) -> List[int]:
         return sorted(set(self._cutting_list))

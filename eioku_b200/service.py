@@ -20,7 +20,7 @@ from typing import Callable, List, Optional, Sequence, Tuple
 
 import numpy as np
 
-from .detectors import AdaptiveDetector, ContentDetector, FlashFilter, HistogramDetector
+from .detectors import AdaptiveDetector, ContentDetector, FlashFilter, HistogramDetector, ThresholdDetector
 from .scene_manager import BatchVideo, SceneManager, TensorVideo
 
 logger = logging.getLogger(__name__)
@@ -93,8 +93,20 @@ def build_detectors(config: dict) -> list:
             if "bins" in cfg:
                 kw["bins"] = int(cfg["bins"])
             dets.append(HistogramDetector(**kw))
+        elif name in ("threshold", "detect-threshold"):
+            kw = dict(common)
+            if "fade_threshold" in cfg:
+                kw["threshold"] = float(cfg["fade_threshold"])
+            elif "threshold" in cfg and len(names) == 1:
+                kw["threshold"] = float(cfg["threshold"])
+            for k in ("fade_bias",):
+                if k in cfg:
+                    kw[k] = float(cfg[k])
+            if "add_final_scene" in cfg:
+                kw["add_final_scene"] = bool(cfg["add_final_scene"])
+            dets.append(ThresholdDetector(**kw))
         else:
-            raise ValueError(f"unknown scene detector {name!r} (content | adaptive | hist)")
+            raise ValueError(f"unknown scene detector {name!r} (content | adaptive | hist | threshold)")
     return dets
 
 

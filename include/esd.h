@@ -50,7 +50,9 @@ typedef enum esd_status {
 } esd_status;
 
 /* detector bitmask: which decision passes (and therefore which per-frame features) run */
-enum { ESD_DET_CONTENT = 1, ESD_DET_ADAPTIVE = 2, ESD_DET_HIST = 4 };
+enum { ESD_DET_CONTENT = 1, ESD_DET_ADAPTIVE = 2, ESD_DET_HIST = 4, ESD_DET_THRESHOLD = 8 };
+/* ThresholdDetector.Method */
+enum { ESD_THRESH_FLOOR = 0, ESD_THRESH_CEILING = 1 };
 /* FlashFilter.Mode of PySceneDetect >= 0.6.4; SUPPRESS == the legacy (<= 0.6.3) min_scene_len rule */
 enum { ESD_FILTER_MERGE = 0, ESD_FILTER_SUPPRESS = 1 };
 /* compute_downscale_factor: W/256.0 (>= 0.6.2) or W//256 (<= 0.6.1) */
@@ -87,6 +89,14 @@ typedef struct esd_config {
     double hist_threshold;     /* user threshold; the library applies clamp(1 - t, 0, 1) */
     int32_t hist_bins;         /* 1..256 */
     int32_t hist_min_scene_len;
+
+    /* ThresholdDetector(threshold, min_scene_len, fade_bias, add_final_scene, method) -- fades through black */
+    double thresh_threshold;   /* compared as int(threshold), like PySceneDetect */
+    double thresh_fade_bias;   /* -1..1 */
+    int32_t thresh_min_scene_len;
+    int32_t thresh_add_final_scene;
+    int32_t thresh_method;     /* ESD_THRESH_* */
+    int32_t reserved2;
 
     /* tuning knobs, 0 = auto */
     int32_t rows_per_group;    /* destination rows one CTA keeps on-chip per frame */
@@ -158,6 +168,14 @@ ESD_API int64_t esd_frames_pushed(const esd_ctx* ctx);
 ESD_API int esd_read_scores(esd_ctx* ctx, int64_t from_frame, int64_t n, uint64_t* sums3, double* content_val,
                     double* adaptive_val, double* adaptive_ratio, uint32_t* hist, double* hist_diff);
 
+/* ThresholdDetector's per-frame metric: average of all B,G,R values of the (downscaled) frame.  Synchronises. */
+ESD_API int esd_read_average_rgb(esd_ctx* ctx, int64_t from_frame, int64_t n, double* average_rgb);
+
+/* SceneDetector.post_process(last_frame_num): cuts a detector adds after the last frame (only the
+ * ThresholdDetector can: the final fade-out when add_final_scene is set).  Synchronises. */
+ESD_API int esd_post_process(esd_ctx* ctx, int32_t detector, int64_t last_frame_num, int64_t* cuts, int64_t cap,
+                             int64_t* n_cuts);
+
 /* Cuts emitted so far by one detector (ESD_DET_*), starting at index `from_index` of its cut list.
  * *n_total receives the total number of cuts the detector has emitted.  Synchronises. */
 ESD_API int esd_get_cuts(esd_ctx* ctx, int32_t detector, int64_t from_index, int64_t* cuts, int64_t cap,
@@ -166,7 +184,7 @@ ESD_API int esd_get_cuts(esd_ctx* ctx, int32_t detector, int64_t from_index, int
 /* Stand-alone decision pass over score arrays already on the host (merge step of frame-range
  * sharding: shards return scores, one global pass decides).  Uses the ctx's detector parameters but
  * none of its frame state.  For ESD_DET_ADAPTIVE `scores` = adaptive_val (ratios are recomputed);
- * ESD_DET_CONTENT: content_val; ESD_DET_HIST: hist_diff (NaN = no previous frame). */
+ * ESD_DET_CONTENT: content_val; ESD_DET_HIST: hist_diff (NaN = no previous frame); ESD_DET_THRESHOLD: average_rgb. */
 ESD_API int esd_decide_arrays(esd_ctx* ctx, int32_t detector, int64_t first_frame_num, int64_t n,
                       const double* scores, double* adaptive_ratio_out, int64_t* cuts, int64_t cap,
                       int64_t* n_cuts);

@@ -336,6 +336,68 @@ class HistogramDetector:
         return 0
 
 
+class ThresholdDetector:
+    """scenedetect.detectors.ThresholdDetector.process_frame / post_process (0.6.4)
+    [upstream-recall: restated from knowledge of the package, parity unpinned]."""
+
+    FLOOR, CEILING = 0, 1
+
+    def __init__(self, threshold=12, min_scene_len=15, fade_bias=0.0, add_final_scene=False, method=0, backend="cv2"):
+        self.threshold = int(threshold)
+        self.method = method
+        self.fade_bias = fade_bias
+        self.min_scene_len = min_scene_len
+        self.processed_frame = False
+        self.last_scene_cut = None
+        self.add_final_scene = add_final_scene
+        self.last_fade = {"frame": 0, "type": None}
+        self.averages: list = []
+
+    def process_frame(self, frame_num, frame_img) -> List[int]:
+        if self.last_scene_cut is None:
+            self.last_scene_cut = frame_num
+        cut_list = []
+        num_pixel_values = float(frame_img.shape[0] * frame_img.shape[1] * frame_img.shape[2])
+        frame_avg = np.sum(frame_img[:, :, :]) / num_pixel_values
+        self.averages.append(float(frame_avg))
+        if self.processed_frame:
+            if self.last_fade["type"] == "in" and (
+                    (self.method == self.FLOOR and frame_avg < self.threshold)
+                    or (self.method == self.CEILING and frame_avg >= self.threshold)):
+                self.last_fade["type"] = "out"
+                self.last_fade["frame"] = frame_num
+            elif self.last_fade["type"] == "out" and (
+                    (self.method == self.FLOOR and frame_avg >= self.threshold)
+                    or (self.method == self.CEILING and frame_avg < self.threshold)):
+                if (frame_num - self.last_scene_cut) >= self.min_scene_len:
+                    f_out = self.last_fade["frame"]
+                    f_split = int((frame_num + f_out + int(self.fade_bias * (frame_num - f_out))) / 2)
+                    cut_list.append(f_split)
+                    self.last_scene_cut = frame_num
+                self.last_fade["type"] = "in"
+                self.last_fade["frame"] = frame_num
+        else:
+            self.last_fade["frame"] = 0
+            if frame_avg < self.threshold:
+                self.last_fade["type"] = "out"
+            else:
+                self.last_fade["type"] = "in"
+        self.processed_frame = True
+        return cut_list
+
+    def post_process(self, frame_num) -> List[int]:
+        cut_times = []
+        if (self.last_fade["type"] == "out" and self.add_final_scene and (
+                (self.last_scene_cut is None and frame_num >= self.min_scene_len)
+                or (frame_num - self.last_scene_cut) >= self.min_scene_len)):
+            cut_times.append(self.last_fade["frame"])
+        return cut_times
+
+    @property
+    def event_buffer_length(self):
+        return 0
+
+
 # ----------------------------------------------------------------------------- SceneManager (A.1, A.8)
 def get_scenes_from_cuts(cut_list: Sequence[int], start_pos: int, end_pos: int):
     """scenedetect.scene_manager.get_scenes_from_cuts on frame numbers."""

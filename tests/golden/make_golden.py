@@ -69,6 +69,7 @@ def clip(name, seed, w, h, n, chunk=64, downscale_mode="float"):
         "content_luma": P.ContentDetector(threshold=27.0, min_scene_len=15, luma_only=True),
         "adaptive": P.AdaptiveDetector(adaptive_threshold=3.0, window_width=2),
         "hist": P.HistogramDetector(threshold=0.05, bins=256, min_scene_len=15),
+        "threshold": P.ThresholdDetector(threshold=12, min_scene_len=15, fade_bias=0.0, add_final_scene=True),
     }
     cuts = {k: [] for k in dets}
 
@@ -85,6 +86,7 @@ def clip(name, seed, w, h, n, chunk=64, downscale_mode="float"):
         small = cv2.resize(frame, (dw, dh), interpolation=cv2.INTER_LINEAR) if factor > 1 else frame
         for name_d, det in dets.items():
             cuts[name_d] += det.process_frame(k, small)
+    cuts["threshold"] += dets["threshold"].post_process(n - 1)
     ad = dets["adaptive"]
     ratio = np.full(n, np.nan)
     for t, r in ad.ratios.items():
@@ -100,10 +102,11 @@ def clip(name, seed, w, h, n, chunk=64, downscale_mode="float"):
         hist_sha256=np.frombuffer(hashlib.sha256(counts.astype(np.uint32).tobytes()).digest(), np.uint8),
         cuts_content=np.array(cuts["content"], np.int64), cuts_content_suppress=np.array(cuts["content_suppress"], np.int64),
         cuts_content_luma=np.array(cuts["content_luma"], np.int64), cuts_adaptive=np.array(cuts["adaptive"], np.int64),
-        cuts_hist=np.array(cuts["hist"], np.int64),
+        cuts_hist=np.array(cuts["hist"], np.int64), cuts_threshold=np.array(cuts["threshold"], np.int64),
+        average_rgb=np.array(dets["threshold"].averages),
         hard_cuts=np.array(sch.hard_cuts, np.int64), versions=json.dumps(VERSIONS))
     print(f"clip_{name}: {n} frames {w}x{h} -> {dw}x{dh} in {time.time() - t0:.1f}s; cuts content={len(cuts['content'])} "
-          f"adaptive={len(cuts['adaptive'])} hist={len(cuts['hist'])}", flush=True)
+          f"adaptive={len(cuts['adaptive'])} hist={len(cuts['hist'])} threshold={len(cuts['threshold'])}", flush=True)
 
 
 def filter_vectors():

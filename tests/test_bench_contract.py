@@ -1,0 +1,48 @@
+"""CPU suite: the JSON line bench.py prints keeps the driver's contract (checked on the reference arm, which
+needs no GPU; the GPU arm's line is checked by tests/test_gpu_bench.py on the box)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+             "vs_baseline", "dtype", "data", "config", "e2e", "cpu_baseline", "gpu_launches"}
+
+
+def _run(args, env=None):
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py")] + args, capture_output=True, text=True,
+                         timeout=600, env={**os.environ, **(env or {})})
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, out.stdout
+    return json.loads(lines[0])
+
+
+def test_reference_arm_line():
+    d = _run(["--impl", "reference", "--steps", "1", "--warmup", "1", "--ref-sample", "6", "--ref-reps", "1"])
+    assert BASE_KEYS <= set(d) and d["impl"] == "reference"
+    assert d["metric"] == "frames/sec (1080p ContentDetector)" and d["unit"] == "frames/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["dtype"] == "u8" and d["data"] == "synthetic" and d["vs_baseline"] is None
+    assert "workload" in d["config"] and "model" not in d["config"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_reference_arm_other_ranks_exit_quietly():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
+                         capture_output=True, text=True, timeout=120, env={**os.environ, "RANK": "1", "WORLD_SIZE": "2"})
+    assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_gpu_arm_refuses_to_run_on_cpu():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True, timeout=300)
+    assert out.returncode != 0 and "no CPU fallback" in (out.stderr + out.stdout)

@@ -1,0 +1,30 @@
+"""GPU: bench.py's own line keeps the contract (short run)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def test_bench_line_contract():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "5", "--warmup", "3", "--no-cpu",
+                          "--frames-per-step", "512", "--e2e-frames", "128"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    d = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert k in d, k
+    assert d["steps"] == 5 and d["n_gpus"] == 1 and d["scaling"] == "weak" and d["dtype"] == "u8"
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert 0.2 < r["frac"] < 1.3
+    assert d["gpu_launches"] >= 5 * 3
+    e = d["e2e"]
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] == 128 * 1658880 and e["d2h_bytes_per_step"] > 0
+    assert e["value"] < d["value"]
+    assert d["value"] > 5e5

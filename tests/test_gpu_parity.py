@@ -14,7 +14,8 @@ pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
 
 from eioku_b200 import capi, synth  # noqa: E402
-from eioku_b200.detectors import AdaptiveDetector, ContentDetector, FlashFilter, HistogramDetector  # noqa: E402
+from eioku_b200.detectors import (AdaptiveDetector, ContentDetector, FlashFilter, HistogramDetector,  # noqa: E402
+                                  ThresholdDetector)
 from eioku_b200.scene_manager import SceneManager, TensorVideo  # noqa: E402
 from eioku_b200.service import detect_scenes_frames  # noqa: E402
 from oracle import c_oracle as co  # noqa: E402
@@ -105,7 +106,8 @@ def test_clip_golden_scores_and_cuts(name):
     sch = synth.build_schedule(seed, n)
     batch = {1280: 257, 1920: 128, 3840: 48}[w]
     dets = [ContentDetector(threshold=27.0, min_scene_len=15), AdaptiveDetector(adaptive_threshold=3.0, window_width=2),
-            HistogramDetector(threshold=0.05, bins=256, min_scene_len=15)]
+            HistogramDetector(threshold=0.05, bins=256, min_scene_len=15),
+            ThresholdDetector(threshold=12, min_scene_len=15, add_final_scene=True)]
     sm = SceneManager(batch_frames=batch)
     for d in dets:
         sm.add_detector(d)
@@ -118,6 +120,8 @@ def test_clip_golden_scores_and_cuts(name):
     got_n = sm.detect_scenes(BatchVideo(batches(), (w, h), 30.0), collect_scores=True)
     assert got_n == n
     sc = sm.scores
+    assert same_f64(sc["average_rgb"], g["average_rgb"])
+    assert sm.cuts_of(dets[3]) == g["cuts_threshold"].tolist()
     assert np.array_equal(sc["sums3"], g["sums3"])
     assert same_f64(sc["content_val"], g["content_val"])
     assert same_f64(sc["adaptive_val"], g["content_val"])
@@ -249,7 +253,9 @@ def test_plugin_surface_frame_by_frame_vs_oracle():
               P.ContentDetector(weights=P.Components(0.3, 0.7, 1.9, 0.0), min_scene_len=0, backend="closed_form")),
              (AdaptiveDetector(adaptive_threshold=2.0, window_width=3, min_content_val=8.0, min_scene_len=5),
               P.AdaptiveDetector(adaptive_threshold=2.0, window_width=3, min_content_val=8.0, min_scene_len=5, backend="closed_form")),
-             (HistogramDetector(threshold=0.01, bins=100, min_scene_len=4), P.HistogramDetector(threshold=0.01, bins=100, min_scene_len=4, backend="closed_form"))]
+             (HistogramDetector(threshold=0.01, bins=100, min_scene_len=4), P.HistogramDetector(threshold=0.01, bins=100, min_scene_len=4, backend="closed_form")),
+             (ThresholdDetector(threshold=130, min_scene_len=3, fade_bias=0.4, method=ThresholdDetector.Method.CEILING),
+              P.ThresholdDetector(threshold=130, min_scene_len=3, fade_bias=0.4, method=P.ThresholdDetector.CEILING))]
     for mine, theirs in pairs:
         got, want = [], []
         for k in range(n):
@@ -392,7 +398,8 @@ def test_full_length_baseline_configs_vs_cv2_golden(name, batch):
     w, h, n, seed = int(g["width"]), int(g["height"]), int(g["n_frames"]), int(g["seed"])
     sch = synth.build_schedule(seed, n)
     dets = [ContentDetector(threshold=27.0, min_scene_len=15), AdaptiveDetector(adaptive_threshold=3.0, window_width=2),
-            HistogramDetector(threshold=0.05, bins=256, min_scene_len=15)]
+            HistogramDetector(threshold=0.05, bins=256, min_scene_len=15),
+            ThresholdDetector(threshold=12, min_scene_len=15, add_final_scene=True)]
     sm = SceneManager(batch_frames=batch)
     for d in dets:
         sm.add_detector(d)
@@ -404,6 +411,8 @@ def test_full_length_baseline_configs_vs_cv2_golden(name, batch):
     from eioku_b200.scene_manager import BatchVideo
     assert sm.detect_scenes(BatchVideo(batches(), (w, h), 30.0), collect_scores=True) == n
     sc = sm.scores
+    assert same_f64(sc["average_rgb"], g["average_rgb"])
+    assert sm.cuts_of(dets[3]) == g["cuts_threshold"].tolist() and len(g["cuts_threshold"]) >= 1
     assert np.array_equal(sc["sums3"], g["sums3"])
     assert same_f64(sc["content_val"], g["content_val"])
     assert same_f64(sc["adaptive_ratio"], g["adaptive_ratio"])
@@ -449,3 +458,55 @@ def test_full_size_1080p_properties():
     assert np.array_equal(a["sums3"][:m], g["sums3"]) and same_f64(a["content_val"][:m], g["content_val"])
     hard = [c for c in sch.hard_cuts if c >= 15]
     assert set(hard) <= set(cuts_a)
+
+
+def test_threshold_detector_state_machine_vectors():
+    """ThresholdDetector fade state machine (FLOOR / CEILING, fade_bias, min_scene_len, add_final_scene) on random
+    brightness traces: device decision pass vs the oracle class fed 1x1 frames of the same averages."""
+    rng = np.random.default_rng(12)
+    for trial in range(24):
+        n = int(rng.integers(5, 400))
+        method = trial % 2
+        thr = int(rng.integers(5, 60))
+        L = int(rng.choice([0, 1, 7, 15]))
+        bias = float(rng.choice([0.0, -1.0, 1.0, 0.35, -0.6]))
+        level = rng.integers(0, 2, n)  # slow random telegraph + noise around the threshold
+        for i in range(1, n):
+            if rng.random() > 0.08:
+                level[i] = level[i - 1]
+        avg = np.where(level > 0, thr + rng.integers(0, 40, n), thr - rng.integers(1, 5, n)).clip(0, 255).astype(np.float64)
+        start = int(rng.choice([0, 1, 500]))
+        o = P.ThresholdDetector(threshold=thr, min_scene_len=L, fade_bias=bias, add_final_scene=True, method=method)
+        want = []
+        for i in range(n):
+            want += o.process_frame(start + i, np.full((1, 1, 3), avg[i], np.uint8))
+        with make_ctx(64, 48, None, detectors=capi.ESD_DET_THRESHOLD, thresh_threshold=float(thr), thresh_min_scene_len=L,
+                      thresh_fade_bias=bias, thresh_method=method, thresh_add_final_scene=1) as ctx:
+            cuts, _ = ctx.decide_arrays(capi.ESD_DET_THRESHOLD, start, avg)
+        assert cuts == want, (trial, method, thr, L, bias)
+
+
+def test_threshold_detector_frames_and_post_process():
+    """Fade to black at the end of a clip: the final scene is closed by post_process when add_final_scene is set."""
+    w, h, n = 320, 180, 90
+    fr = np.full((n, h, w, 3), 120, np.uint8)
+    fr[30:40] = 3          # fade out / in inside the clip
+    fr[70:] = 1            # ends faded out
+    fr[:, ::7, ::5, 1] += 9
+    for kw in (dict(add_final_scene=True), dict(add_final_scene=False), dict(add_final_scene=True, min_scene_len=60, fade_bias=1.0)):
+        mine = ThresholdDetector(**kw)
+        theirs = P.ThresholdDetector(**kw)
+        got, want = [], []
+        for k in range(n):
+            got += mine.process_frame(k, fr[k])
+            want += theirs.process_frame(k, fr[k])
+        assert got == want
+        assert mine.post_process(n - 1) == theirs.post_process(n - 1)
+        sm = SceneManager()
+        det = ThresholdDetector(**kw)
+        sm.add_detector(det)
+        sm.auto_downscale = False
+        sm.detect_scenes(TensorVideo(torch.from_numpy(fr).to(DEV), 30.0), collect_scores=True)
+        assert sm.cuts_of(det) == want + theirs.post_process(n - 1)
+        assert same_f64(sm.scores["average_rgb"], np.array(theirs.averages))
+        sm.close(); mine.close()

@@ -13,7 +13,8 @@ import pytest
 
 from conftest import ROOT
 from eioku_b200 import capi, sharding
-from eioku_b200.detectors import AdaptiveDetector, ContentDetector, FlashFilter, HistogramDetector, StatsManager
+from eioku_b200.detectors import (AdaptiveDetector, ContentDetector, FlashFilter, HistogramDetector, StatsManager,
+                                  ThresholdDetector)
 from eioku_b200.scene_manager import SceneManager, compute_downscale_factor, get_scenes_from_cuts
 from eioku_b200.service import ModelManager, build_detectors, scenes_to_dicts
 from oracle import psd_cv2 as P
@@ -115,7 +116,11 @@ def test_detector_constructors_and_metrics():
                     filter_mode=FlashFilter.Mode.SUPPRESS)._fill_config(cfg)
     AdaptiveDetector(adaptive_threshold=2.5, window_width=4, luma_only=True)._fill_config(cfg)
     HistogramDetector(threshold=0.1, bins=32, min_scene_len=3)._fill_config(cfg)
-    assert cfg.detectors == 7 and cfg.content_threshold == 31.5 and cfg.content_filter_mode == 1
+    t = ThresholdDetector(threshold=12.9, fade_bias=-0.5, add_final_scene=True, method=ThresholdDetector.Method.CEILING)
+    assert t.threshold == 12 and t.get_metrics() == ["average_rgb"] and t.post_process(5) == []
+    t._fill_config(cfg)
+    assert (cfg.thresh_threshold, cfg.thresh_fade_bias, cfg.thresh_add_final_scene, cfg.thresh_method) == (12.0, -0.5, 1, 1)
+    assert cfg.detectors == 15 and cfg.content_threshold == 31.5 and cfg.content_filter_mode == 1
     # the divisor is the host interpreter's sum(abs(w)) -- same expression as PySceneDetect
     assert cfg.content_weight_div == sum(abs(w) for w in (0.1, 0.2, 0.3, 0.0))
     assert list(cfg.adaptive_weights) == [0.0, 0.0, 1.0, 0.0] and cfg.adaptive_window_width == 4
@@ -164,8 +169,10 @@ def test_build_detectors_from_task_config():
     assert isinstance(a, AdaptiveDetector) and (a.adaptive_threshold, a.window_width, a.min_content_val) == (2.0, 3, 10.0)
     both = build_detectors({"detector": "hist+content", "bins": 128, "hist_threshold": 0.1})
     assert isinstance(both[0], HistogramDetector) and both[0]._bins == 128 and isinstance(both[1], ContentDetector)
+    th = build_detectors({"detector": "threshold", "threshold": 20, "fade_bias": 0.5, "add_final_scene": True})[0]
+    assert isinstance(th, ThresholdDetector) and (th.threshold, th.fade_bias, th.add_final_scene) == (20, 0.5, True)
     with pytest.raises(ValueError):
-        build_detectors({"detector": "threshold"})
+        build_detectors({"detector": "hash"})
 
 
 def test_model_manager_raises_like_the_reference():

@@ -160,3 +160,22 @@ def test_schedule_is_deterministic():
     assert hashlib.sha256(a.descs.tobytes()).hexdigest()[:16] == "84395418ff2fce5f"  # frozen: goldens depend on it
     assert a.descs.shape == (5000, 8) and (a.descs[:, 3] >= 1).all()
     assert a.fades and a.dissolves and a.flashes
+
+
+def test_threshold_detector_oracle_hand_cases():
+    """ThresholdDetector restatement on hand-checked traces (fade out at 10, back in at 20 -> cut at 15)."""
+    def run(avgs, **kw):
+        d = P.ThresholdDetector(**kw)
+        cuts = []
+        for i, a in enumerate(avgs):
+            cuts += d.process_frame(i, np.full((2, 2, 3), a, np.uint8))
+        return cuts, d.post_process(len(avgs) - 1)
+    trace = [100] * 10 + [2] * 10 + [100] * 30
+    assert run(trace, min_scene_len=15) == ([15], [])
+    assert run(trace, min_scene_len=15, fade_bias=1.0) == ([20], [])
+    assert run(trace, min_scene_len=15, fade_bias=-1.0) == ([10], [])
+    assert run(trace, min_scene_len=25) == ([], [])                       # fade-in too close to the start
+    assert run(trace + [1] * 5, min_scene_len=15, add_final_scene=True) == ([15], [50])
+    assert run(trace + [1] * 5, min_scene_len=15) == ([15], [])
+    assert run([1] * 5 + [90] * 40, min_scene_len=3) == ([2], [])          # starts faded out: cut at (5 + 0) / 2
+    assert run([10, 30, 10, 30, 10, 30], threshold=20, min_scene_len=0, method=P.ThresholdDetector.CEILING)[0] == [1, 3]
