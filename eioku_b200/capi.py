@@ -22,7 +22,7 @@ EXPORTED_SYMBOLS = (
     "esd_abi_version", "esd_strerror", "esd_last_error", "esd_device_count", "esd_config_default",
     "esd_create", "esd_destroy", "esd_reset", "esd_get_geometry", "esd_get_touched_rows",
     "esd_push_frames", "esd_push_rows", "esd_ingest_open", "esd_ingest_push_host", "esd_ingest_close",
-    "esd_ingest_stats", "esd_synchronize", "esd_join", "esd_frames_pushed", "esd_read_scores", "esd_read_average_rgb",
+    "esd_ingest_stats", "esd_synchronize", "esd_join", "esd_frames_pushed", "esd_read_scores", "esd_read_edge_counts", "esd_read_average_rgb",
     "esd_post_process", "esd_get_cuts",
     "esd_decide_arrays", "esd_debug_read_prev", "esd_set_timing", "esd_kernel_time", "esd_kernel_launches", "esd_synth_fill",
 )
@@ -43,7 +43,7 @@ class EsdConfig(C.Structure):
         ("hist_threshold", C.c_double), ("hist_bins", C.c_int32), ("hist_min_scene_len", C.c_int32),
         ("thresh_threshold", C.c_double), ("thresh_fade_bias", C.c_double),
         ("thresh_min_scene_len", C.c_int32), ("thresh_add_final_scene", C.c_int32),
-        ("thresh_method", C.c_int32), ("reserved2", C.c_int32),
+        ("thresh_method", C.c_int32), ("edge_kernel_size", C.c_int32),
         ("rows_per_group", C.c_int32), ("pipeline_stages", C.c_int32),
         ("split_mode", C.c_int32), ("ctas_per_sm", C.c_int32),
         ("rows_per_stage", C.c_int32), ("reserved1", C.c_int32),
@@ -107,6 +107,7 @@ def load_library(path: Optional[str] = None):
     L.esd_read_scores.argtypes = [vp, i64, i64, vp, vp, vp, vp, vp, vp]
     L.esd_get_cuts.argtypes = [vp, i32, i64, vp, i64, C.POINTER(i64), C.POINTER(i64)]
     L.esd_read_average_rgb.argtypes = [vp, i64, i64, vp]
+    L.esd_read_edge_counts.argtypes = [vp, i64, i64, vp]
     L.esd_post_process.argtypes = [vp, i32, i64, vp, i64, C.POINTER(i64)]
     L.esd_decide_arrays.argtypes = [vp, i32, i64, i64, vp, vp, vp, i64, C.POINTER(i64)]
     L.esd_debug_read_prev.argtypes = [vp, vp, i64]
@@ -278,6 +279,11 @@ class EsdContext:
             self._h, from_frame, n, _np_ptr(out.get("sums3")), _np_ptr(out.get("content_val")),
             _np_ptr(out.get("adaptive_val")), _np_ptr(out.get("adaptive_ratio")), _np_ptr(out.get("hist")),
             _np_ptr(out.get("hist_diff"))), "esd_read_scores")
+        return out
+
+    def read_edge_counts(self, from_frame: int, n: int) -> np.ndarray:
+        out = np.empty(n, np.uint32)
+        self._check(self._L.esd_read_edge_counts(self._h, from_frame, n, _np_ptr(out)), "esd_read_edge_counts")
         return out
 
     def read_average_rgb(self, from_frame: int, n: int) -> np.ndarray:

@@ -60,7 +60,8 @@ struct esd_ctx {
     int rows_per_group = 0, n_groups = 0, stages = 0, rowbuf = 0, stage_bytes = 0, rows_per_stage = 1;
     int ctas_per_sm = 0;
     size_t smem_bytes = 0;
-    bool need_content = false, need_hist = false;
+    bool need_content = false, need_hist = false, need_edges = false;
+    int edge_ksize = 0, edge_words = 0;
     std::vector<int32_t> touched;  // ascending source rows
     ScoreWeights wc{}, wa{};
     DecisionParams dparams{};
@@ -89,6 +90,7 @@ struct esd_ctx {
     double* d_ratio = nullptr;
     double* d_hdiff = nullptr;
     double* d_avg = nullptr;       // ThresholdDetector average_rgb
+    uint32_t* d_edge_counts = nullptr;  // differing edge pixels vs the previous frame
     uint32_t* d_counts = nullptr;  // [cap][bins]
     uint8_t* d_slab = nullptr;     // backing allocation of the six arrays above
 
@@ -96,6 +98,9 @@ struct esd_ctx {
     int64_t part_cap_frames = 0;
     uint4* d_part[2] = {nullptr, nullptr};          // double-buffered: the tail of push k overlaps push k+1
     uint16_t* d_hist_part[2] = {nullptr, nullptr};
+    uint8_t* d_vplane[2] = {nullptr, nullptr};      // V planes of the batch (edge detector input)
+    uint32_t* d_edge_bits = nullptr;                // [n][edge_words] dilated edge bitmaps of the batch
+    uint32_t* d_edge_prev = nullptr;                // [edge_words] bitmap of the last frame of the previous batch
     int part_buf = 0;
     std::map<int64_t, UnitPlan> plans;
 
@@ -294,7 +299,7 @@ int ensure_capacity(esd_ctx* c, int64_t frames_needed) {
     const int64_t ncap = std::max<int64_t>(c->cap ? c->cap * 2 : std::max<int64_t>(4096, c->cfg.initial_capacity), frames_needed);
     { int rc0 = sync_all(c); if (rc0) return rc0; }
     const int64_t bins = c->need_hist ? c->cfg.hist_bins : 0;
-    const size_t bytes = (size_t)ncap * (3 * sizeof(unsigned long long) + 5 * sizeof(double) + bins * sizeof(uint32_t));
+    const size_t bytes = (size_t)ncap * (3 * sizeof(unsigned long long) + 5 * sizeof(double) + (bins + 1) * sizeof(uint32_t));
     uint8_t* slab = nullptr;
     CU(c, cudaMalloc(&slab, bytes));
     uint8_t* q = slab;
@@ -311,6 +316,7 @@ int ensure_capacity(esd_ctx* c, int64_t frames_needed) {
     auto* n_ratio = carve(&c->d_ratio, 1);
     auto* n_hdiff = carve(&c->d_hdiff, 1);
     auto* n_avg = carve(&c->d_avg, 1);
+    auto* n_edge = carve(&c->d_edge_counts, 1);
     auto* n_counts = carve(&c->d_counts, bins);
     if (used > 0) {
         CU(c, cudaMemcpy(n_sums, c->d_sums3, sizeof(unsigned long long) * 3 * used, cudaMemcpyDeviceToDevice));
@@ -319,11 +325,12 @@ int ensure_capacity(esd_ctx* c, int64_t frames_needed) {
         CU(c, cudaMemcpy(n_ratio, c->d_ratio, sizeof(double) * used, cudaMemcpyDeviceToDevice));
         CU(c, cudaMemcpy(n_hdiff, c->d_hdiff, sizeof(double) * used, cudaMemcpyDeviceToDevice));
         CU(c, cudaMemcpy(n_avg, c->d_avg, sizeof(double) * used, cudaMemcpyDeviceToDevice));
+        CU(c, cudaMemcpy(n_edge, c->d_edge_counts, sizeof(uint32_t) * used, cudaMemcpyDeviceToDevice));
         if (bins) CU(c, cudaMemcpy(n_counts, c->d_counts, sizeof(uint32_t) * bins * used, cudaMemcpyDeviceToDevice));
     }
     cudaFree(c->d_slab);
     c->d_slab = slab;
-    c->d_sums3 = n_sums; c->d_cv = n_cv; c->d_av = n_av; c->d_ratio = n_ratio; c->d_hdiff = n_hdiff; c->d_avg = n_avg;
+    c->d_sums3 = n_sums; c->d_cv = n_cv; c->d_av = n_av; c->d_ratio = n_ratio; c->d_hdiff = n_hdiff; c->d_avg = n_avg; c->d_edge_counts = n_edge;
     c->d_counts = bins ? n_counts : nullptr;
     // ratios not yet computed read back as NaN
     fill_nan_kernel<<<(unsigned)((ncap - used + 255) / 256), 256>>>(c->d_ratio + used, ncap - used);
@@ -340,11 +347,19 @@ int ensure_scratch(esd_ctx* c, int64_t n) {
     for (int b = 0; b < 2; ++b) {
         cudaFree(c->d_part[b]);
         cudaFree(c->d_hist_part[b]);
+        cudaFree(c->d_vplane[b]);
         c->d_part[b] = nullptr;
         c->d_hist_part[b] = nullptr;
+        c->d_vplane[b] = nullptr;
         c->fin_recorded[b] = false;
+        if (c->need_edges) CU(c, cudaMalloc(&c->d_vplane[b], (size_t)n * c->dst_w * c->dst_h));
         if (c->need_content) CU(c, cudaMalloc(&c->d_part[b], sizeof(uint4) * n * c->n_groups * kConsumerWarps));
         if (c->need_hist) CU(c, cudaMalloc(&c->d_hist_part[b], sizeof(uint16_t) * n * c->n_groups * c->cfg.hist_bins));
+    }
+    if (c->need_edges) {
+        cudaFree(c->d_edge_bits);
+        c->d_edge_bits = nullptr;
+        CU(c, cudaMalloc(&c->d_edge_bits, sizeof(uint32_t) * n * c->edge_words));
     }
     c->part_cap_frames = n;
     return ESD_OK;
@@ -448,6 +463,7 @@ int push_common(esd_ctx* c, const uint8_t* d_src, int64_t n, int64_t frame_strid
     c->part_buf ^= 1;
     p.part = c->d_part[buf];
     p.hist_part = c->d_hist_part[buf];
+    p.vplane = c->need_edges ? c->d_vplane[buf] : nullptr;
     // the fused kernel overwrites part[buf]: wait until the tail of the push that last used it is done
     if (c->fin_recorded[buf]) CU(c, cudaStreamWaitEvent(st, c->ev_fin[buf], 0));
 
@@ -472,11 +488,23 @@ int push_common(esd_ctx* c, const uint8_t* d_src, int64_t n, int64_t frame_strid
     CU(c, cudaStreamWaitEvent(ts, c->ev_fused, 0));
 
     const double npx = (double)c->dst_w * (double)c->dst_h;  // float(rows * cols)
+    if (c->need_edges) {
+        const size_t esmem = 2 * (size_t)(((c->dst_w * c->dst_h) + 31) & ~31);
+        edges_kernel<<<(unsigned)n, kEdgeThreads, esmem, ts>>>(c->d_vplane[buf], c->dst_w, c->dst_h, c->edge_ksize, c->d_edge_bits,
+                                                             c->edge_words);
+        CU(c, cudaGetLastError());
+        edge_delta_kernel<<<(unsigned)n, 256, 0, ts>>>(c->d_edge_bits, c->d_edge_prev, c->edge_words, base > 0 ? 1 : 0,
+                                                      c->d_edge_counts + base);
+        CU(c, cudaGetLastError());
+        CU(c, cudaMemcpyAsync(c->d_edge_prev, c->d_edge_bits + (size_t)(n - 1) * c->edge_words, sizeof(uint32_t) * c->edge_words,
+                              cudaMemcpyDeviceToDevice, ts));
+        c->launches += 2;
+    }
     if (c->need_content) {
         const int warps_per_block = 8;
         finalize_sums_kernel<<<(unsigned)((n + warps_per_block - 1) / warps_per_block), warps_per_block * 32, 0, ts>>>(
             c->d_part[buf], (int)n, c->n_groups * kConsumerWarps, npx, c->wc, c->wa, c->d_sums3 + 3 * base, c->d_cv + base,
-            c->d_av + base, c->d_avg + base);
+            c->d_av + base, c->d_avg + base, c->need_edges ? c->d_edge_counts + base : nullptr);
         CU(c, cudaGetLastError());
         c->launches++;
         if (c->cfg.detectors & ESD_DET_ADAPTIVE) {
@@ -588,8 +616,6 @@ int esd_create(esd_ctx** out, const esd_config* cfg, int device) {
                     sizeof(esd_config));
     if (!(cfg->detectors & 15) || (cfg->detectors & ~15)) return fail(nullptr, ESD_ERR_INVALID, "esd_create: bad detector mask");
     if (cfg->src_width < 1 || cfg->src_height < 1) return fail(nullptr, ESD_ERR_INVALID, "esd_create: bad frame size");
-    if (cfg->content_weights[3] != 0.0 || cfg->adaptive_weights[3] != 0.0)
-        return fail(nullptr, ESD_ERR_UNSUPPORTED, "delta_edges weight must be 0 (Canny/dilate is outside the hot path)");
     if ((cfg->detectors & ESD_DET_HIST) && (cfg->hist_bins < 1 || cfg->hist_bins > 256))
         return fail(nullptr, ESD_ERR_UNSUPPORTED, "hist_bins must be in 1..256");
     if ((cfg->detectors & ESD_DET_ADAPTIVE) && cfg->adaptive_window_width < 1)
@@ -646,6 +672,30 @@ int esd_create(esd_ctx** out, const esd_config* cfg, int device) {
     c->row_bytes = W * 3;
     c->need_content = (cfg->detectors & (ESD_DET_CONTENT | ESD_DET_ADAPTIVE | ESD_DET_THRESHOLD)) != 0;
     c->need_hist = (cfg->detectors & ESD_DET_HIST) != 0;
+    c->need_edges = ((cfg->detectors & ESD_DET_CONTENT) && cfg->content_weights[3] > 0.0) ||
+                    ((cfg->detectors & ESD_DET_ADAPTIVE) && cfg->adaptive_weights[3] > 0.0);
+    if (c->need_edges) {
+        // _estimated_kernel_size: 4 + round(sqrt(w * h) / 192), made odd
+        int ks = cfg->edge_kernel_size;
+        if (ks <= 0) {
+            ks = 4 + (int)py_round(sqrt((double)dw * (double)dh) / 192.0);
+            if (ks % 2 == 0) ks += 1;
+        }
+        if (ks < 3 || ks % 2 == 0) {
+            fail(c, ESD_ERR_INVALID, "kernel_size must be odd integer >= 3");
+            return bail(ESD_ERR_INVALID);
+        }
+        c->edge_ksize = ks;
+        c->edge_words = (dw * dh + 31) / 32;
+        const size_t esmem = 2 * (size_t)((dw * dh + 31) & ~31);
+        if (esmem + 2048 > prop.sharedMemPerBlockOptin) {
+            fail(c, ESD_ERR_UNSUPPORTED, "delta_edges needs the detector-resolution frame (%dx%d) in shared memory; at most ~%zu pixels",
+                 dw, dh, (size_t)(prop.sharedMemPerBlockOptin - 2048) / 2);
+            return bail(ESD_ERR_UNSUPPORTED);
+        }
+        CUB(cudaFuncSetAttribute(edges_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esmem));
+        CUB(cudaMalloc(&c->d_edge_prev, sizeof(uint32_t) * c->edge_words));
+    }
     if (dw > kConsumers * (c->resize ? 4 : 16)) {
         fail(c, ESD_ERR_UNSUPPORTED, "destination width %d too large (max %d)", dw, kConsumers * (c->resize ? 4 : 16));
         return bail(ESD_ERR_UNSUPPORTED);
@@ -797,7 +847,8 @@ void esd_destroy(esd_ctx* c) {
     cudaFree(c->d_yrows); cudaFree(c->d_xtab); cudaFree(c->d_sdiv); cudaFree(c->d_hdiv);
     cudaFree(c->d_prev[0]); cudaFree(c->d_prev[1]); cudaFree(c->d_state); cudaFree(c->d_cuts);
     cudaFree(c->d_slab);
-    for (int b = 0; b < 2; ++b) { cudaFree(c->d_part[b]); cudaFree(c->d_hist_part[b]); if (c->ev_fin[b]) cudaEventDestroy(c->ev_fin[b]); }
+    for (int b = 0; b < 2; ++b) { cudaFree(c->d_part[b]); cudaFree(c->d_hist_part[b]); cudaFree(c->d_vplane[b]); if (c->ev_fin[b]) cudaEventDestroy(c->ev_fin[b]); }
+    cudaFree(c->d_edge_bits); cudaFree(c->d_edge_prev);
     if (c->order_event) cudaEventDestroy(c->order_event);
     if (c->ev_fused) cudaEventDestroy(c->ev_fused);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
@@ -996,6 +1047,19 @@ int esd_read_scores(esd_ctx* c, int64_t from_frame, int64_t n, uint64_t* sums3, 
 static int det_index(int32_t detector) {
     return detector == ESD_DET_CONTENT ? 0 : detector == ESD_DET_ADAPTIVE ? 1 : detector == ESD_DET_HIST ? 2
          : detector == ESD_DET_THRESHOLD ? 3 : -1;
+}
+
+int esd_read_edge_counts(esd_ctx* c, int64_t from_frame, int64_t n, uint32_t* counts) {
+    if (!c || !counts) return ESD_ERR_INVALID;
+    if (n == 0) return ESD_OK;
+    const int64_t i0 = from_frame - c->first_frame;
+    if (!c->started || n < 0 || i0 < 0 || i0 + n > c->n_frames)
+        return fail(c, ESD_ERR_INVALID, "read_edge_counts: range outside pushed frames");
+    if (!c->need_edges) return fail(c, ESD_ERR_STATE, "read_edge_counts: no delta_edges weight configured");
+    int rc = esd_synchronize(c);
+    if (rc) return rc;
+    CU(c, cudaMemcpy(counts, c->d_edge_counts + i0, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost));
+    return ESD_OK;
 }
 
 int esd_read_average_rgb(esd_ctx* c, int64_t from_frame, int64_t n, double* average_rgb) {

@@ -61,6 +61,7 @@ struct FusedParams {
     uint32_t* prev_out;         // same, written from the last frame of this batch
     uint4* part;                // [n_frames][n_groups][kConsumerWarps] {sumH, sumS, sumV, 0}
     uint16_t* hist_part;        // [n_frames][n_groups][bins]
+    uint8_t* vplane;            // [n_frames][dst_h][dst_w] V plane for the edge detector, or nullptr
 };
 
 // ----------------------------------------------------------------------------------- PTX helpers
@@ -150,7 +151,7 @@ __device__ __forceinline__ int vresize(uint32_t h0, uint32_t h1, uint32_t b0s, u
 template <bool RESIZE, int PXT, bool CONTENT, bool HIST, bool SPECIAL>
 __device__ __forceinline__ void score_row(const FusedParams& p, const uint8_t* __restrict__ row0, const uint8_t* __restrict__ row1,
                                           uint32_t mis0, uint32_t mis1, uint32_t b0s, uint32_t b1s, int flags, int rloc,
-                                          int row, int tid, const uint32_t (&xoff)[PXT], const uint32_t (&xa01)[PXT],
+                                          int row, int frame, int tid, const uint32_t (&xoff)[PXT], const uint32_t (&xa01)[PXT],
                                           const int* __restrict__ s_sdiv, const int* __restrict__ s_hdiv,
                                           uint32_t* __restrict__ s_prev, uint32_t* __restrict__ s_hist_cur,
                                           uint32_t& acc_hv, uint32_t& acc_s, uint32_t& acc_bgr) {
@@ -198,6 +199,8 @@ __device__ __forceinline__ void score_row(const FusedParams& p, const uint8_t* _
                 } else {
                     pv = *slot;
                 }
+                if (p.vplane && !(SPECIAL && (flags & F_HALO)))
+                    p.vplane[((size_t)frame * p.dst_h + row) * p.dst_w + d] = (uint8_t)(cur >> 16);
                 const uint32_t diff = __vabsdiffu4(cur, pv);
                 acc_hv += diff & 0x00ff00ffu;
                 acc_s += (diff >> 8) & 0xffu;
@@ -362,7 +365,7 @@ __global__ void __launch_bounds__(kThreads) fused_score_kernel(const FusedParams
                 const uint4 mr = meta_r[s * kMaxRowsPerStage + q];
                 const uint32_t mis0 = ALIGNED ? 0u : (mr.z & 0xffu), mis1 = ALIGNED ? 0u : ((mr.z >> 8) & 0xffu);
                 score_row<RESIZE, PXT, CONTENT, HIST, true>(p, stage + q * row_slot, stage + q * row_slot + p.rowbuf, mis0, mis1, mr.x,
-                                                            mr.y, flags, rloc0 + q, row_first + q, tid, xoff, xa01, s_sdiv, s_hdiv,
+                                                            mr.y, flags, rloc0 + q, row_first + q, m.x, tid, xoff, xa01, s_sdiv, s_hdiv,
                                                             s_prev, hist_cur, acc_hv, acc_s, acc_bgr);
             }
         } else {
@@ -370,7 +373,7 @@ __global__ void __launch_bounds__(kThreads) fused_score_kernel(const FusedParams
                 const uint4 mr = meta_r[s * kMaxRowsPerStage + q];
                 const uint32_t mis0 = ALIGNED ? 0u : (mr.z & 0xffu), mis1 = ALIGNED ? 0u : ((mr.z >> 8) & 0xffu);
                 score_row<RESIZE, PXT, CONTENT, HIST, false>(p, stage + q * row_slot, stage + q * row_slot + p.rowbuf, mis0, mis1, mr.x,
-                                                             mr.y, flags, rloc0 + q, row_first + q, tid, xoff, xa01, s_sdiv, s_hdiv,
+                                                             mr.y, flags, rloc0 + q, row_first + q, m.x, tid, xoff, xa01, s_sdiv, s_hdiv,
                                                              s_prev, hist_cur, acc_hv, acc_s, acc_bgr);
             }
         }
@@ -414,15 +417,18 @@ struct ScoreWeights {
 };
 
 // IEEE double, left to right, no FMA: PySceneDetect ContentDetector._calculate_frame_score (A.4)
-__device__ __forceinline__ double content_val_of(const unsigned long long s[3], double npx, const ScoreWeights& W) {
+__device__ __forceinline__ double content_val_of(const unsigned long long s[3], unsigned long long edge_sum, double npx,
+                                                 const ScoreWeights& W) {
     const double dh = __ddiv_rn((double)s[0], npx);
     const double ds = __ddiv_rn((double)s[1], npx);
     const double dv = __ddiv_rn((double)s[2], npx);
+    // delta_edges is 0.0 unless the weight is > 0 (PySceneDetect only computes edges then)
+    const double de = W.w[3] > 0.0 ? __ddiv_rn((double)edge_sum, npx) : 0.0;
     double acc = 0.0;
     acc = __dadd_rn(acc, __dmul_rn(dh, W.w[0]));
     acc = __dadd_rn(acc, __dmul_rn(ds, W.w[1]));
     acc = __dadd_rn(acc, __dmul_rn(dv, W.w[2]));
-    acc = __dadd_rn(acc, __dmul_rn(0.0, W.w[3]));
+    acc = __dadd_rn(acc, __dmul_rn(de, W.w[3]));
     return __ddiv_rn(acc, W.div);
 }
 
@@ -430,7 +436,7 @@ __device__ __forceinline__ double content_val_of(const unsigned long long s[3], 
 __global__ void finalize_sums_kernel(const uint4* __restrict__ part, int n_frames, int parts_per_frame, double npx,
                                      ScoreWeights wc, ScoreWeights wa, unsigned long long* __restrict__ sums3,
                                      double* __restrict__ content_val, double* __restrict__ adaptive_val,
-                                     double* __restrict__ average_rgb) {
+                                     double* __restrict__ average_rgb, const uint32_t* __restrict__ edge_counts) {
     const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (f >= n_frames) return;
@@ -452,8 +458,10 @@ __global__ void finalize_sums_kernel(const uint4* __restrict__ part, int n_frame
         sums3[3 * (size_t)f] = s[0];
         sums3[3 * (size_t)f + 1] = s[1];
         sums3[3 * (size_t)f + 2] = s[2];
-        content_val[f] = content_val_of(s, npx, wc);
-        adaptive_val[f] = content_val_of(s, npx, wa);
+        // sum |edges - last_edges| over 0/255 maps = 255 x (number of differing pixels)
+        const unsigned long long es = edge_counts ? 255ull * edge_counts[f] : 0ull;
+        content_val[f] = content_val_of(s, es, npx, wc);
+        adaptive_val[f] = content_val_of(s, es, npx, wa);
         // ThresholdDetector._compute_frame_average: numpy.sum(frame) / float(rows * cols * channels)
         average_rgb[f] = __ddiv_rn((double)sb, __dmul_rn(npx, 3.0));
     }
@@ -573,6 +581,167 @@ __global__ void adaptive_ratio_kernel(const double* __restrict__ val, double* __
         r = 255.0;
     }
     ratio[t] = r;
+}
+
+
+// ----------------------------------------------------------------------------------- edges
+// ContentDetector._detect_edges on the device: numpy.median(lum) -> Canny(low, high) -> dilate(k x k ones).
+// One CTA per frame at detector resolution; the whole V plane and the edge map live in shared memory.
+// cv2.Canny (aperture 3, L1 gradient) restated from OpenCV canny.cpp: Sobel with replicated borders, |dx|+|dy|,
+// non-maximum suppression with the TG22 fixed-point sector test against a zero-bordered magnitude map, hysteresis =
+// weak pixels 8-connected to a strong one.  Output: one bit per pixel, [n][words_per_frame].
+constexpr int kEdgeThreads = 1024;
+
+__device__ __forceinline__ int sobel_mag(const uint8_t* __restrict__ V, int w, int h, int x, int y, int& dx, int& dy) {
+    const int xm = max(x - 1, 0), xp = min(x + 1, w - 1);
+    const uint8_t* r0 = V + max(y - 1, 0) * w;
+    const uint8_t* r1 = V + y * w;
+    const uint8_t* r2 = V + min(y + 1, h - 1) * w;
+    const int a = r0[xm], b = r0[x], c = r0[xp], d = r1[xm], e = r1[xp], f = r2[xm], g = r2[x], i = r2[xp];
+    dx = (c + 2 * e + i) - (a + 2 * d + f);
+    dy = (f + 2 * g + i) - (a + 2 * b + c);
+    return abs(dx) + abs(dy);
+}
+__device__ __forceinline__ int mag_at(const uint8_t* __restrict__ V, int w, int h, int x, int y) {
+    if (x < 0 || y < 0 || x >= w || y >= h) return 0;  // the magnitude map has a zero border
+    int dx, dy;
+    return sobel_mag(V, w, h, x, y, dx, dy);
+}
+
+__global__ void __launch_bounds__(kEdgeThreads) edges_kernel(const uint8_t* __restrict__ vplane, int w, int h, int ksize,
+                                                             uint32_t* __restrict__ bitmaps, int words_per_frame) {
+    extern __shared__ __align__(16) uint8_t esm[];
+    const int npx = w * h;
+    const int npx_pad = (npx + 31) & ~31;
+    uint8_t* V = esm;                  // [npx_pad]   (reused as the horizontal-dilate buffer)
+    uint8_t* map = esm + npx_pad;      // [npx_pad]   0 none, 1 weak, 2/4 frontier, 3 edge
+    __shared__ uint32_t hist[256];
+    __shared__ int s_low, s_high;
+    __shared__ int changed[3];
+    const int tid = threadIdx.x;
+    const uint8_t* src = vplane + (size_t)blockIdx.x * npx;
+
+    for (int i = tid; i < 256; i += kEdgeThreads) hist[i] = 0;
+    if (tid < 3) changed[tid] = 0;
+    __syncthreads();
+    for (int i = tid; i < npx_pad; i += kEdgeThreads) {
+        const uint8_t v = i < npx ? src[i] : 0;
+        V[i] = v;
+        if (i < npx) atomicAdd(&hist[v], 1u);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        // numpy.median: middle element, or the mean of the two middle elements for an even count
+        const int k_lo = (npx - 1) / 2, k_hi = npx / 2;
+        int acc = 0, v_lo = -1, v_hi = -1;
+        for (int b = 0; b < 256 && v_hi < 0; ++b) {
+            acc += (int)hist[b];
+            if (v_lo < 0 && acc > k_lo) v_lo = b;
+            if (acc > k_hi) v_hi = b;
+        }
+        const double median = __ddiv_rn((double)(v_lo + v_hi), 2.0);
+        const double sigma = 1.0 / 3.0;
+        const double lo = __dmul_rn(1.0 - sigma, median), hi = __dmul_rn(1.0 + sigma, median);
+        int low = (int)(lo > 0.0 ? lo : 0.0);
+        int high = (int)(hi < 255.0 ? hi : 255.0);
+        if (low > high) { const int t = low; low = high; high = t; }
+        s_low = low;
+        s_high = high;
+    }
+    __syncthreads();
+    const int low = s_low, high = s_high;
+    constexpr int TG22 = 13573;  // (int)(0.4142135623730950488016887242097 * (1 << 15) + 0.5)
+    for (int i = tid; i < npx_pad; i += kEdgeThreads) {
+        uint8_t out = 0;
+        if (i < npx) {
+            const int y = i / w, x = i - y * w;
+            int dx, dy;
+            const int m = sobel_mag(V, w, h, x, y, dx, dy);
+            if (m > low) {
+                const int xa = abs(dx), ya = abs(dy) << 15;
+                const int tg22x = xa * TG22;
+                bool ok;
+                if (ya < tg22x) ok = m > mag_at(V, w, h, x - 1, y) && m >= mag_at(V, w, h, x + 1, y);
+                else {
+                    const int tg67x = tg22x + (xa << 16);
+                    if (ya > tg67x) ok = m > mag_at(V, w, h, x, y - 1) && m >= mag_at(V, w, h, x, y + 1);
+                    else {
+                        const int sgn = ((dx ^ dy) < 0) ? -1 : 1;
+                        ok = m > mag_at(V, w, h, x - sgn, y - 1) && m > mag_at(V, w, h, x + sgn, y + 1);
+                    }
+                }
+                if (ok) out = (m > high) ? 2 : 1;
+            }
+        }
+        map[i] = out;
+    }
+    __syncthreads();
+    // hysteresis: breadth-first growth of the strong set through weak pixels; frontier label alternates 2 <-> 4
+    const uint32_t* map32 = reinterpret_cast<const uint32_t*>(map);
+    for (int r = 0;; ++r) {
+        const uint32_t cur = (r & 1) ? 4u : 2u, nxt = (r & 1) ? 2u : 4u;
+        if (tid == 0) changed[(r + 1) % 3] = 0;
+        bool any = false;
+        for (int wi = tid; wi < npx_pad / 4; wi += kEdgeThreads) {
+            const uint32_t word = map32[wi];
+            const uint32_t t = word ^ (cur * 0x01010101u);
+            if (!((t - 0x01010101u) & ~t & 0x80808080u)) continue;  // no byte equals `cur`
+            for (int b = 0; b < 4; ++b) {
+                if (((word >> (8 * b)) & 0xffu) != cur) continue;
+                const int i = wi * 4 + b;
+                const int y = i / w, x = i - y * w;
+                for (int yy = max(y - 1, 0); yy <= min(y + 1, h - 1); ++yy)
+                    for (int xx = max(x - 1, 0); xx <= min(x + 1, w - 1); ++xx)
+                        if (map[yy * w + xx] == 1) { map[yy * w + xx] = (uint8_t)nxt; any = true; }
+                map[i] = 3;
+            }
+        }
+        if (any) changed[r % 3] = 1;
+        __syncthreads();
+        if (!changed[r % 3]) break;
+    }
+    // pixels marked in the last round carry the frontier label; together with 3 they are the edges.
+    // dilate with a k x k block of ones (anchor at the centre, outside ignored): separable max
+    const int rad = ksize / 2, rad1 = ksize - 1 - rad;  // window [p - rad, p + rad1] (anchor = k / 2)
+    for (int i = tid; i < npx_pad; i += kEdgeThreads) {
+        uint8_t o = 0;
+        if (i < npx) {
+            const int y = i / w, x = i - y * w;
+            for (int xx = max(x - rad, 0); xx <= min(x + rad1, w - 1); ++xx) o |= (map[y * w + xx] >= 2);
+        }
+        V[i] = o;
+    }
+    __syncthreads();
+    for (int i = tid; i < npx_pad; i += kEdgeThreads) {
+        bool o = false;
+        if (i < npx) {
+            const int y = i / w, x = i - y * w;
+            for (int yy = max(y - rad, 0); yy <= min(y + rad1, h - 1); ++yy) o |= (V[yy * w + x] != 0);
+        }
+        const uint32_t bits = __ballot_sync(0xffffffffu, o);
+        if ((tid & 31) == 0) bitmaps[(size_t)blockIdx.x * words_per_frame + (i >> 5)] = bits;
+    }
+}
+
+// number of pixels whose dilated edge bit differs from the previous frame's (block per frame);
+// bitmaps points at the batch's first frame, prev_last at the last frame of the previous batch (or nullptr)
+__global__ void edge_delta_kernel(const uint32_t* __restrict__ bitmaps, const uint32_t* __restrict__ prev_last,
+                                  int words_per_frame, int first_has_prev, uint32_t* __restrict__ counts) {
+    __shared__ uint32_t red[32];
+    const int f = blockIdx.x;
+    const uint32_t* cur = bitmaps + (size_t)f * words_per_frame;
+    const uint32_t* prv = f > 0 ? cur - words_per_frame : (first_has_prev ? prev_last : nullptr);
+    uint32_t c = 0;
+    if (prv)
+        for (int i = threadIdx.x; i < words_per_frame; i += blockDim.x) c += __popc(cur[i] ^ prv[i]);
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+        counts[f] = t;
+    }
 }
 
 // ----------------------------------------------------------------------------------- decision passes

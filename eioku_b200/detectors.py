@@ -193,9 +193,6 @@ class ContentDetector(SceneDetector):
         self._weights = ContentDetector.Components(*weights)
         if luma_only:
             self._weights = ContentDetector.LUMA_ONLY_WEIGHTS
-        if self._weights.delta_edges != 0.0:
-            raise NotImplementedError(
-                "delta_edges != 0 needs Canny+dilate, which is outside the B200 hot path (SURVEY.md section 8 a14)")
         if kernel_size is not None and (kernel_size < 3 or kernel_size % 2 == 0):
             raise ValueError("kernel_size must be odd integer >= 3")
         self._kernel_size = kernel_size
@@ -208,7 +205,15 @@ class ContentDetector(SceneDetector):
         # exactly PySceneDetect's divisor expression, evaluated by the host interpreter
         return float(sum(abs(w) for w in self._weights))
 
+    def _fill_edge_config(self, cfg):
+        # delta_edges > 0 switches the Canny + dilate edge map on (ContentDetector._detect_edges); one kernel size per pass
+        if self._weights.delta_edges > 0.0 and self._kernel_size is not None:
+            if cfg.edge_kernel_size not in (0, self._kernel_size):
+                raise ValueError("detectors fed from one pass must share kernel_size")
+            cfg.edge_kernel_size = int(self._kernel_size)
+
     def _fill_config(self, cfg):
+        self._fill_edge_config(cfg)
         cfg.detectors |= capi.ESD_DET_CONTENT
         cfg.content_threshold = float(self._threshold)
         for i, w in enumerate(self._weights):
@@ -220,6 +225,13 @@ class ContentDetector(SceneDetector):
     def _metrics_for(self, scores, k):
         npx = float(self._ctx.geometry.dst_width * self._ctx.geometry.dst_height) if self._ctx else 1.0
         return _content_metrics(scores, k, "content_val", npx)
+
+    def _publish_late_metrics(self, first_frame_num, n):
+        if self._weights.delta_edges > 0.0:
+            npx = float(self._ctx.geometry.dst_width * self._ctx.geometry.dst_height)
+            cnt = self._ctx.read_edge_counts(first_frame_num, n)
+            for k in range(n):
+                self.stats_manager.set_metrics(first_frame_num + k, {"delta_edges": float(np.int64(255 * int(cnt[k])) / npx)})
 
 
 def _content_metrics(scores, k, val_key, npx):
@@ -262,6 +274,7 @@ class AdaptiveDetector(ContentDetector):
         return super().get_metrics() + [self._adaptive_ratio_key]
 
     def _fill_config(self, cfg):
+        self._fill_edge_config(cfg)
         cfg.detectors |= capi.ESD_DET_ADAPTIVE
         cfg.adaptive_threshold = float(self.adaptive_threshold)
         cfg.adaptive_min_content_val = float(self.min_content_val)
@@ -276,6 +289,7 @@ class AdaptiveDetector(ContentDetector):
         return _content_metrics(scores, k, "adaptive_val", npx)
 
     def _publish_late_metrics(self, first_frame_num, n):
+        ContentDetector._publish_late_metrics(self, first_frame_num, n)
         # the ratio of frame t becomes known once frame t + window_width has been processed
         w = self.window_width
         first_video_frame = first_frame_num + n - self._ctx.frames_pushed

@@ -222,6 +222,8 @@ class SceneManager:
             self.scores = ctx.read_scores(start, total)
             if any(isinstance(d, ThresholdDetector) for d in self._detector_list):
                 self.scores["average_rgb"] = ctx.read_average_rgb(start, total)
+            if any(isinstance(d, ContentDetector) and d._weights.delta_edges > 0.0 for d in self._detector_list):
+                self.scores["edge_counts"] = ctx.read_edge_counts(start, total)
             if self.stats_manager is not None:
                 self._publish_stats(start, total)
         if host_ring_open:
@@ -278,5 +280,8 @@ class SceneManager:
 
 def _deltas(sc, k, npx):
     s = sc["sums3"][k]
-    return {"delta_hue": float(np.int64(s[0]) / npx), "delta_sat": float(np.int64(s[1]) / npx),
-            "delta_lum": float(np.int64(s[2]) / npx)}
+    out = {"delta_hue": float(np.int64(s[0]) / npx), "delta_sat": float(np.int64(s[1]) / npx),
+           "delta_lum": float(np.int64(s[2]) / npx)}
+    if "edge_counts" in sc:
+        out["delta_edges"] = float(np.int64(255 * int(sc["edge_counts"][k])) / npx)
+    return out

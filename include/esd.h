@@ -72,7 +72,7 @@ typedef struct esd_config {
 
     /* ContentDetector(threshold, min_scene_len, weights, filter_mode); luma_only = weights {0,0,1,0} */
     double content_threshold;
-    double content_weights[4]; /* delta_hue, delta_sat, delta_lum, delta_edges (must be 0) */
+    double content_weights[4]; /* delta_hue, delta_sat, delta_lum, delta_edges (> 0 enables the Canny/dilate edge map) */
     double content_weight_div; /* sum(abs(w)) as the host language computes it; <= 0 -> naive left-to-right */
     int32_t content_min_scene_len;
     int32_t content_filter_mode;
@@ -96,7 +96,7 @@ typedef struct esd_config {
     int32_t thresh_min_scene_len;
     int32_t thresh_add_final_scene;
     int32_t thresh_method;     /* ESD_THRESH_* */
-    int32_t reserved2;
+    int32_t edge_kernel_size;  /* ContentDetector kernel_size for the edge dilation; 0 = PySceneDetect's estimate */
 
     /* tuning knobs, 0 = auto */
     int32_t rows_per_group;    /* destination rows one CTA keeps on-chip per frame */
@@ -167,6 +167,10 @@ ESD_API int64_t esd_frames_pushed(const esd_ctx* ctx);
  * Synchronises. */
 ESD_API int esd_read_scores(esd_ctx* ctx, int64_t from_frame, int64_t n, uint64_t* sums3, double* content_val,
                     double* adaptive_val, double* adaptive_ratio, uint32_t* hist, double* hist_diff);
+
+/* Number of pixels whose dilated edge bit differs from the previous frame (delta_edges = 255 * count / pixels);
+ * only when a delta_edges weight is > 0.  Synchronises. */
+ESD_API int esd_read_edge_counts(esd_ctx* ctx, int64_t from_frame, int64_t n, uint32_t* counts);
 
 /* ThresholdDetector's per-frame metric: average of all B,G,R values of the (downscaled) frame.  Synchronises. */
 ESD_API int esd_read_average_rgb(esd_ctx* ctx, int64_t from_frame, int64_t n, double* average_rgb);

@@ -151,3 +151,82 @@ def plane_abs_sums(cur_hsv: np.ndarray, prev_hsv: np.ndarray) -> np.ndarray:
     """(sum|dH|, sum|dS|, sum|dV|) as int64 -- numerator of _mean_pixel_distance."""
     d = np.abs(cur_hsv.astype(np.int32) - prev_hsv.astype(np.int32))
     return d.reshape(-1, 3).sum(axis=0, dtype=np.int64)
+
+
+# --------------------------------------------------------------------------- a14: ContentDetector._detect_edges
+CANNY_SHIFT = 15
+TG22 = int(0.4142135623730950488016887242097 * (1 << CANNY_SHIFT) + 0.5)
+
+
+def estimated_kernel_size(frame_width: int, frame_height: int) -> int:
+    """scenedetect.detectors.content_detector._estimated_kernel_size."""
+    import math
+
+    size = 4 + round(math.sqrt(frame_width * frame_height) / 192)
+    if size % 2 == 0:
+        size += 1
+    return size
+
+
+def canny_thresholds(lum: np.ndarray):
+    """low/high of ContentDetector._detect_edges: sigma = 1/3 around numpy.median(lum), truncated to int."""
+    sigma = 1.0 / 3.0
+    median = np.median(lum)
+    low = int(max(0, (1.0 - sigma) * median))
+    high = int(min(255, (1.0 + sigma) * median))
+    return low, high
+
+
+def canny_u8(img: np.ndarray, low: int, high: int) -> np.ndarray:
+    """cv2.Canny(img, low, high) (aperture 3, L1 gradient) restated from OpenCV canny.cpp:
+    Sobel with BORDER_REPLICATE, |dx|+|dy|, non-maximum suppression with the TG22 fixed-point sector test
+    against a zero-padded magnitude map, hysteresis = weak pixels 8-connected to a strong one."""
+    if low > high:
+        low, high = high, low
+    img = img.astype(np.int32)
+    p = np.pad(img, 1, mode="edge")
+    dx = (p[:-2, 2:] + 2 * p[1:-1, 2:] + p[2:, 2:]) - (p[:-2, :-2] + 2 * p[1:-1, :-2] + p[2:, :-2])
+    dy = (p[2:, :-2] + 2 * p[2:, 1:-1] + p[2:, 2:]) - (p[:-2, :-2] + 2 * p[:-2, 1:-1] + p[:-2, 2:])
+    mag = np.abs(dx) + np.abs(dy)
+    mp = np.pad(mag, 1, mode="constant")
+    m = mp[1:-1, 1:-1]
+    x = np.abs(dx)
+    y = np.abs(dy) << CANNY_SHIFT
+    tg22x = x * TG22
+    tg67x = tg22x + (x << (CANNY_SHIFT + 1))
+    left, right, up, down = mp[1:-1, :-2], mp[1:-1, 2:], mp[:-2, 1:-1], mp[2:, 1:-1]
+    s_pos = (dx ^ dy) >= 0
+    prev_d = np.where(s_pos, mp[:-2, :-2], mp[:-2, 2:])
+    next_d = np.where(s_pos, mp[2:, 2:], mp[2:, :-2])
+    horiz = (y < tg22x) & (m > left) & (m >= right)
+    vert = (y > tg67x) & (m > up) & (m >= down)
+    diag = ~(y < tg22x) & ~(y > tg67x) & (m > prev_d) & (m > next_d)
+    nms = (m > low) & (horiz | vert | diag)
+    out = nms & (m > high)
+    while True:
+        q = np.pad(out, 1)
+        nb = (q[:-2, :-2] | q[:-2, 1:-1] | q[:-2, 2:] | q[1:-1, :-2] | q[1:-1, 2:] | q[2:, :-2] | q[2:, 1:-1] | q[2:, 2:])
+        new = out | (nms & nb)
+        if (new == out).all():
+            break
+        out = new
+    return (out * 255).astype(np.uint8)
+
+
+def dilate_ones_u8(img: np.ndarray, k: int) -> np.ndarray:
+    """cv2.dilate(img, numpy.ones((k, k), uint8)): max over the k x k window centred on the pixel (anchor k//2),
+    pixels outside the image ignored."""
+    r0 = k // 2
+    r1 = k - 1 - r0
+    h, w = img.shape
+    p = np.pad(img, ((r0, r1), (r0, r1)), mode="constant")
+    out = np.zeros_like(img)
+    for dy in range(k):
+        for dx in range(k):
+            out = np.maximum(out, p[dy:dy + h, dx:dx + w])
+    return out
+
+
+def detect_edges(lum: np.ndarray, kernel_size: int) -> np.ndarray:
+    low, high = canny_thresholds(lum)
+    return dilate_ones_u8(canny_u8(lum, low, high), kernel_size)

@@ -205,9 +205,11 @@ class ContentDetector:
         self._weights = Components(*weights)
         if luma_only:
             self._weights = LUMA_ONLY_WEIGHTS
-        if self._weights.delta_edges != 0.0:
-            raise NotImplementedError("delta_edges is outside the hot path (SURVEY.md a14)")
+        if kernel_size is not None and (kernel_size < 3 or kernel_size % 2 == 0):
+            raise ValueError("kernel_size must be odd integer >= 3")
+        self._kernel_size = kernel_size
         self._last = None
+        self.edge_sums: list = []  # number of differing edge pixels x 255 (0 for the first frame / when unused)
         self._frame_score = None
         self._flash_filter = FlashFilter(filter_mode, min_scene_len)
         self._backend = backend
@@ -215,22 +217,36 @@ class ContentDetector:
         self.sums: list = []  # int64[3] (0 for the first frame)
         self.scores: list = []  # content_val (float64)
 
+    def _detect_edges(self, lum):
+        """ContentDetector._detect_edges: Canny around the median + dilate."""
+        if self._kernel_size is None:
+            self._kernel_size = cf.estimated_kernel_size(lum.shape[1], lum.shape[0])
+        if self._backend == "cv2":
+            low, high = cf.canny_thresholds(lum)
+            edges = cv2.Canny(lum, low, high)
+            return cv2.dilate(edges, np.ones((self._kernel_size, self._kernel_size), np.uint8))
+        return cf.detect_edges(np.ascontiguousarray(lum), self._kernel_size)
+
     def _calculate_frame_score(self, frame_num, frame_img):
         hue, sat, lum = _hsv_planes(frame_img, self._backend)
+        calculate_edges = self._weights.delta_edges > 0.0
+        edges = self._detect_edges(lum) if calculate_edges else None
         if self._last is None:
-            self._last = (hue, sat, lum)
+            self._last = (hue, sat, lum, edges)
             self.sums.append(np.zeros(3, np.int64))
+            self.edge_sums.append(0)
             return 0.0
         comps = Components(
             delta_hue=_mean_pixel_distance(hue, self._last[0]),
             delta_sat=_mean_pixel_distance(sat, self._last[1]),
             delta_lum=_mean_pixel_distance(lum, self._last[2]),
-            delta_edges=0.0,
+            delta_edges=(0.0 if edges is None else _mean_pixel_distance(edges, self._last[3])),
         )
+        self.edge_sums.append(0 if edges is None else int(np.sum(np.abs(edges.astype(np.int32) - self._last[3].astype(np.int32)))))
         n = hue.shape[0] * hue.shape[1]
         self.sums.append(np.array([int(round(float(c) * n)) for c in comps[:3]], np.int64))
         score = sum(c * w for (c, w) in zip(comps, self._weights)) / sum(abs(w) for w in self._weights)
-        self._last = (hue, sat, lum)
+        self._last = (hue, sat, lum, edges)
         return score
 
     def process_frame(self, frame_num, frame_img) -> List[int]:

@@ -364,8 +364,8 @@ def test_filter_vectors_on_device():
 
 
 def test_errors_are_loud():
-    with pytest.raises(NotImplementedError):
-        ContentDetector(weights=ContentDetector.Components(1, 1, 1, 1))
+    with pytest.raises(ValueError):
+        ContentDetector(kernel_size=4)
     with pytest.raises(ValueError):
         AdaptiveDetector(window_width=0)
     with pytest.raises(ValueError):
@@ -382,10 +382,11 @@ def test_errors_are_loud():
         with pytest.raises(ValueError):
             ctx.push_tensor(torch.zeros((1, 50, 64, 3), dtype=torch.uint8, device=DEV), 12)
     cfg = capi.default_config()
-    cfg.src_width, cfg.src_height = 64, 48
-    cfg.content_weights[3] = 1.0
-    with pytest.raises(capi.EsdError):
+    cfg.src_width, cfg.src_height, cfg.dst_width, cfg.dst_height = 1920, 1080, 1920, 1080
+    cfg.content_weights[3] = 1.0  # delta_edges at full 1080p detector resolution does not fit on an SM
+    with pytest.raises(capi.EsdError) as e:
         capi.EsdContext(cfg, 0)
+    assert "delta_edges" in str(e.value)
 
 
 @pytest.mark.slow
@@ -510,3 +511,35 @@ def test_threshold_detector_frames_and_post_process():
         assert sm.cuts_of(det) == want + theirs.post_process(n - 1)
         assert same_f64(sm.scores["average_rgb"], np.array(theirs.averages))
         sm.close(); mine.close()
+
+
+def test_delta_edges_canny_dilate_vs_oracle():
+    """ContentDetector with a delta_edges weight -- numpy.median thresholds, cv2.Canny
+    and cv2.dilate restated on the device; edge-change counts, float64 content_val and cuts equal the oracle
+    (whose Canny/dilate restatement is itself pinned to cv2 in tests/test_oracle.py)."""
+    w, h, n, seed = 1280, 720, 140, 1001
+    sch = synth.build_schedule(seed, n, min_len=15, max_len=50)
+    clip = gpu_clip(seed, w, h, sch.descs)
+    frames = clip.cpu().numpy()
+    W = (1.0, 0.5, 1.0, 0.8)
+    for ks in (None, 3, 7):
+        o = P.ContentDetector(threshold=20.0, min_scene_len=10, weights=P.Components(*W), kernel_size=ks, backend="closed_form")
+        want, _ = P.detect(frames, [o], backend="closed_form")
+        sm = SceneManager(batch_frames=37)
+        det = ContentDetector(threshold=20.0, min_scene_len=10, weights=ContentDetector.Components(*W), kernel_size=ks)
+        sm.add_detector(det)
+        sm.detect_scenes(TensorVideo(clip, 30.0), collect_scores=True)
+        assert (sm.scores["edge_counts"].astype(np.int64) * 255).tolist() == o.edge_sums, ks
+        assert same_f64(sm.scores["content_val"], np.array(o.scores)), ks
+        assert sm.cuts_of(det) == want and len(want) >= 2
+        assert max(o.edge_sums) > 0
+        sm.close()
+    # frame by frame, stand-alone, on small odd-sized frames (dilation window clipped at the borders)
+    rng = np.random.default_rng(8)
+    import cv2 as _cv2  # only to blur the random test frames
+    small = np.stack([_cv2.GaussianBlur(rng.integers(0, 256, (37, 53, 3), dtype=np.uint8), (0, 0), 1.2 + 0.2 * (k % 4)) for k in range(12)])
+    mine = ContentDetector(weights=ContentDetector.Components(0.0, 0.0, 0.0, 1.0), threshold=5.0, min_scene_len=0)
+    theirs = P.ContentDetector(weights=P.Components(0.0, 0.0, 0.0, 1.0), threshold=5.0, min_scene_len=0, backend="closed_form")
+    for k in range(12):
+        assert mine.process_frame(k, small[k]) == theirs.process_frame(k, small[k]), k
+    mine.close()

@@ -106,8 +106,12 @@ def test_detector_constructors_and_metrics():
     assert HistogramDetector(threshold=2.0)._threshold == 0.0
     with pytest.raises(ValueError):
         AdaptiveDetector(window_width=0)
-    with pytest.raises(NotImplementedError):
-        ContentDetector(weights=ContentDetector.Components(1.0, 1.0, 1.0, 0.5))
+    e = ContentDetector(weights=ContentDetector.Components(1.0, 1.0, 1.0, 0.5), kernel_size=7)
+    ecfg = capi.default_config()
+    e._fill_config(ecfg)
+    assert ecfg.edge_kernel_size == 7 and ecfg.content_weights[3] == 0.5
+    with pytest.raises(ValueError):
+        AdaptiveDetector(weights=ContentDetector.Components(1.0, 1.0, 1.0, 0.5), kernel_size=5)._fill_config(ecfg)
     with pytest.raises(ValueError):
         ContentDetector(kernel_size=4)
     cfg = capi.default_config()

@@ -179,3 +179,24 @@ def test_threshold_detector_oracle_hand_cases():
     assert run(trace + [1] * 5, min_scene_len=15) == ([15], [])
     assert run([1] * 5 + [90] * 40, min_scene_len=3) == ([2], [])          # starts faded out: cut at (5 + 0) / 2
     assert run([10, 30, 10, 30, 10, 30], threshold=20, min_scene_len=0, method=P.ThresholdDetector.CEILING)[0] == [1, 3]
+
+
+def test_canny_dilate_restatement_vs_cv2():
+    """ContentDetector._detect_edges (median thresholds, cv2.Canny, cv2.dilate) restated in numpy == real cv2."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(3)
+    assert cf.estimated_kernel_size(256, 144) == 5 and cf.estimated_kernel_size(1920, 1080) == 13
+    for t in range(24):
+        h, w, k = int(rng.integers(6, 160)), int(rng.integers(6, 280)), int(rng.choice([3, 5, 7, 9]))
+        lum = cv2.GaussianBlur(rng.integers(0, 256, (h, w), dtype=np.uint8), (0, 0), 0.8 + 0.3 * (t % 6))
+        low, high = cf.canny_thresholds(lum)
+        assert np.array_equal(cf.canny_u8(lum, low, high), cv2.Canny(lum, low, high))
+        assert np.array_equal(cf.detect_edges(lum, k), cv2.dilate(cv2.Canny(lum, low, high), np.ones((k, k), np.uint8)))
+    sch = synth.build_schedule(1001, 60, min_len=15, max_len=40)
+    frames = co.synth_frames(1001, 640, 360, sch.descs)
+    W = P.Components(1.0, 1.0, 1.0, 1.0)
+    a, b = P.ContentDetector(weights=W, backend="cv2"), P.ContentDetector(weights=W, backend="closed_form")
+    ca, _ = P.detect(frames, [a], backend="cv2")
+    cb, _ = P.detect(frames, [b], backend="closed_form")
+    assert ca == cb and a.edge_sums == b.edge_sums and max(a.edge_sums) > 0
+    assert np.array_equal(np.array(a.scores).view(np.uint64), np.array(b.scores).view(np.uint64))
