@@ -208,6 +208,51 @@ def config5(dev, local, world, rank, dist, videos_per_gpu=8, n_videos=512, frame
             "note": "bounded subset of the 512-video library; per-video throughput is independent of library size"}
 
 
+def config_edges(dev, local, n=1024, steps=10):
+    """ContentDetector with a delta_edges weight (Canny + dilate per frame) and stand-alone no-resize scoring."""
+    W, H, seed = 1920, 1080, 1002
+    sch = synth.build_schedule(seed, n)
+    clip = fill(seed, W, H, sch.descs, dev)
+    out = {"config": "extras"}
+    stream = torch.cuda.current_stream().cuda_stream
+    for name, dets, auto in (("content", [ContentDetector()], True),
+                             ("content+edges", [ContentDetector(weights=ContentDetector.Components(1.0, 1.0, 1.0, 1.0))], True),
+                             ("all4", None, True), ("content_noresize_1080p", [ContentDetector()], False)):
+        sm = SceneManager(device=local, tuning={"initial_capacity": (steps + 4) * n})
+        if dets is None:
+            from eioku_b200.detectors import ThresholdDetector
+            dets = [ContentDetector(), AdaptiveDetector(), HistogramDetector(), ThresholdDetector()]
+        for d in dets:
+            sm.add_detector(d)
+        sm.auto_downscale = auto
+        ctx = sm.make_context(W, H)
+        m = n if auto else 128
+        pos = 0
+        for _ in range(2):
+            ctx.push_tensor(clip[:m], pos, stream); pos += m
+        ctx.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            ctx.push_tensor(clip[:m], pos, stream); pos += m
+        ctx.join(stream)
+        e1.record()
+        torch.cuda.synchronize()
+        out[name + "_frames_per_s"] = steps * m / (e0.elapsed_time(e1) / 1000.0)
+        ctx.close()
+    # per-frame latency of the plugin surface (process_frame with a sync per frame)
+    det = ContentDetector()
+    small = torch.empty((300, 144, 256, 3), dtype=torch.uint8, device=dev).random_(0, 256)
+    for k in range(20):
+        det.process_frame(k, small[k])
+    t0 = time.perf_counter()
+    for k in range(20, 300):
+        det.process_frame(k, small[k])
+    out["process_frame_latency_us"] = (time.perf_counter() - t0) / 280 * 1e6
+    det.close()
+    return out
+
+
 def pcie_probe(dev, local):
     """H2D ceilings on this box: plain pinned memcpy, the touched-rows ring, and zero-copy TMA reads of pinned frames."""
     W, H, n = 1920, 1080, 256
@@ -281,6 +326,8 @@ def main():
             r = config5(dev, local, world, rank, dist, args.videos_per_gpu)
         elif c == "pcie":
             r = pcie_probe(dev, local) if rank == 0 else None
+        elif c == "extras":
+            r = config_edges(dev, local) if rank == 0 else None
         else:
             continue
         if rank == 0 and r is not None:
