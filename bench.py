@@ -271,7 +271,18 @@ def bench_ours(args):
     host = clip[:NE].cpu().pin_memory()
     host_np = host.numpy()
     ectx = capi.EsdContext(cfg, local)
-    ectx.ingest_open(3, 256)
+    # e2e ingest mode: host threads gather the tap bytes of the touched rows (442 KB/frame over PCIe instead of
+    # 1.66 MB); 0 = plain DMA of the touched rows.  Default: this rank's share of the host cores.
+    gthreads = args.e2e_gather_threads
+    if gthreads < 0:
+        try:
+            share = len(os.sched_getaffinity(0)) if world == 1 else (os.cpu_count() or 1) // world
+        except Exception:
+            share = (os.cpu_count() or 1) // world
+        # measured (profiles/r01_pcie.log): gather beats the 28-30 k frames/s of plain DMA from ~10 threads up
+        gthreads = share if share >= 10 else 0
+    ectx.ingest_open(4, 128) if gthreads else ectx.ingest_open(3, 256)
+    ectx.ingest_set_gather(gthreads)
     e2e_steps = max(2, min(args.steps, 6))
 
     def e2e_step(p):
@@ -295,7 +306,7 @@ def bench_ours(args):
     if dist is not None:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = e2e_steps * NE * world / float(te[0])
-    h2d_per_step = NE * int(geo.compact_frame_bytes)  # touched rows only
+    h2d_per_step = ectx.ingest_stats()[0] // (e2e_steps + 2)  # bytes that actually crossed PCIe per step
     ectx.ingest_close()
     ectx.close()
 
@@ -342,7 +353,10 @@ def bench_ours(args):
                      "equivalent_ingest_GBps_not_roofline": value / world * W * H * 3 / 1e9},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_per_step, "d2h_bytes_per_step": d2h,
-                "frames_per_step": NE, "note": "pinned host frames -> touched-rows-only H2D ring -> scoring -> cuts+scores D2H"},
+                "frames_per_step": NE, "host_gather_threads": gthreads,
+                "note": ("pinned host frames -> host threads gather the tap bytes of the touched rows -> pinned ring -> H2D -> "
+                         "scoring -> cuts+scores D2H") if gthreads else
+                        "pinned host frames -> touched-rows-only H2D ring -> scoring -> cuts+scores D2H"},
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
@@ -360,10 +374,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames-per-step", type=int, default=2048)
-    ap.add_argument("--e2e-frames", type=int, default=512)
+    ap.add_argument("--e2e-frames", type=int, default=1024)
     ap.add_argument("--cpu-sample", type=int, default=192)
     ap.add_argument("--cpu-reps", type=int, default=40)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-gather-threads", type=int, default=-1, help="host gather threads of the e2e leg (-1 = this rank's share of cores, 0 = DMA rows)")
     ap.add_argument("--ref-sample", type=int, default=192, help="--impl reference: frames per process per pass")
     ap.add_argument("--ref-reps", type=int, default=8, help="--impl reference: passes per process per step")
     ap.add_argument("--tune", action="append", default=[], help="esd_config field=value (e.g. rows_per_group=2)")

@@ -21,7 +21,7 @@ ESD_SPLIT_AUTO, ESD_SPLIT_STRIPS, ESD_SPLIT_CHUNKS = 0, 1, 2
 EXPORTED_SYMBOLS = (
     "esd_abi_version", "esd_strerror", "esd_last_error", "esd_device_count", "esd_config_default",
     "esd_create", "esd_destroy", "esd_reset", "esd_get_geometry", "esd_get_touched_rows",
-    "esd_push_frames", "esd_push_rows", "esd_ingest_open", "esd_ingest_push_host", "esd_ingest_close",
+    "esd_push_frames", "esd_push_rows", "esd_ingest_open", "esd_ingest_push_host", "esd_ingest_close", "esd_ingest_set_gather",
     "esd_ingest_stats", "esd_synchronize", "esd_join", "esd_frames_pushed", "esd_read_scores", "esd_read_edge_counts", "esd_read_average_rgb",
     "esd_post_process", "esd_get_cuts",
     "esd_decide_arrays", "esd_debug_read_prev", "esd_set_timing", "esd_kernel_time", "esd_kernel_launches", "esd_synth_fill",
@@ -99,6 +99,7 @@ def load_library(path: Optional[str] = None):
     L.esd_ingest_open.argtypes = [vp, i32, i32]
     L.esd_ingest_push_host.argtypes = [vp, vp, i64, i64, i64, i64]
     L.esd_ingest_close.argtypes = [vp]
+    L.esd_ingest_set_gather.argtypes = [vp, i32]
     L.esd_ingest_stats.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
     L.esd_synchronize.argtypes = [vp]
     L.esd_join.argtypes = [vp, vp]
@@ -240,6 +241,10 @@ class EsdContext:
             raise ValueError(f"frame size {w}x{h} != configured {self.cfg.src_width}x{self.cfg.src_height}")
         fs = frames.strides[0] if n > 1 else frames.strides[1] * h
         self.ingest_push_host(frames.ctypes.data, n, fs, frames.strides[1], first_frame_num)
+
+    def ingest_set_gather(self, n_threads: int):
+        """n_threads > 0: host threads gather only the tap bytes of touched rows before the H2D copy."""
+        self._check(self._L.esd_ingest_set_gather(self._h, int(n_threads)), "esd_ingest_set_gather")
 
     def ingest_close(self):
         self._check(self._L.esd_ingest_close(self._h), "esd_ingest_close")

@@ -15,6 +15,11 @@
 #include <time.h>
 
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
 #include <type_traits>
 #include <map>
 #include <string>
@@ -38,10 +43,77 @@ struct UnitPlan {
 
 struct IngestSlot {
     uint8_t* h_pinned = nullptr;
+    size_t h_pinned_bytes = 0;
     uint8_t* d_rows = nullptr;
     cudaEvent_t copied = nullptr;
     cudaEvent_t consumed = nullptr;
     bool in_flight = false;
+};
+
+// Minimal fork-join pool for the host-side tap gather of the ingest path.
+class GatherPool {
+   public:
+    explicit GatherPool(int n) {
+        for (int i = 0; i < n; ++i) workers_.emplace_back([this, i] { run(i); });
+    }
+    ~GatherPool() {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            stop_ = true;
+            ++gen_;
+        }
+        cv_.notify_all();
+        for (auto& t : workers_) t.join();
+    }
+    // fn(item) for item in [0, n_items), items handed out dynamically in blocks
+    void parallel_for(int64_t n_items, int64_t block, const std::function<void(int64_t, int64_t)>& fn) {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            fn_ = &fn;
+            n_items_ = n_items;
+            block_ = block;
+            next_.store(0);
+            pending_ = (int)workers_.size();
+            ++gen_;
+        }
+        cv_.notify_all();
+        std::unique_lock<std::mutex> lk(m_);
+        done_cv_.wait(lk, [this] { return pending_ == 0; });
+        fn_ = nullptr;
+    }
+
+   private:
+    void run(int) {
+        uint64_t seen = 0;
+        for (;;) {
+            const std::function<void(int64_t, int64_t)>* fn;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return gen_ != seen; });
+                seen = gen_;
+                if (stop_) return;
+                fn = fn_;
+            }
+            for (;;) {
+                const int64_t lo = next_.fetch_add(block_);
+                if (lo >= n_items_) break;
+                (*fn)(lo, std::min(n_items_, lo + block_));
+            }
+            {
+                std::lock_guard<std::mutex> lk(m_);
+                if (--pending_ == 0) done_cv_.notify_all();
+            }
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex m_;
+    std::condition_variable cv_, done_cv_;
+    const std::function<void(int64_t, int64_t)>* fn_ = nullptr;
+    std::atomic<int64_t> next_{0};
+    int64_t n_items_ = 0, block_ = 1;
+    int pending_ = 0;
+    uint64_t gen_ = 0;
+    bool stop_ = false;
 };
 
 }  // namespace
@@ -123,6 +195,11 @@ struct esd_ctx {
     int next_slot = 0;
     cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
     int64_t h2d_bytes = 0, h2d_copies = 0;
+    // tap gather: host threads copy only the 6 bytes (two BGR taps) each destination column reads from a touched row
+    GatherPool* pool = nullptr;
+    int tap_row_bytes = 0;               // 6 * dst_w rounded up to 16
+    uint2* d_xtab_taps = nullptr;        // x table for the tap-compact layout {6 d, a0 | a1 << 16}
+    std::vector<int> tap_src_off;        // byte offset of tap 0 in a source row, per destination column
 };
 
 namespace {
@@ -404,8 +481,11 @@ struct TraceTimer {
     }
 };
 
-int push_common(esd_ctx* c, const uint8_t* d_src, int64_t n, int64_t frame_stride, int64_t row_stride, bool compact,
+enum Layout { LAYOUT_FULL = 0, LAYOUT_ROWS = 1, LAYOUT_TAPS = 2 };
+
+int push_common(esd_ctx* c, const uint8_t* d_src, int64_t n, int64_t frame_stride, int64_t row_stride, int layout,
                 int64_t first_frame_num, cudaStream_t st) {
+    const bool compact = layout != LAYOUT_FULL;
     TraceTimer tr;
     if (!d_src || n <= 0) return fail(c, ESD_ERR_INVALID, "push: null frames or n <= 0");
     if (n > 0x7fffff00LL / std::max(1, c->n_groups)) return fail(c, ESD_ERR_INVALID, "push: batch too large (%lld frames)", (long long)n);
@@ -442,7 +522,7 @@ int push_common(esd_ctx* c, const uint8_t* d_src, int64_t n, int64_t frame_strid
     p.n_frames = (int)n;
     p.dst_w = c->dst_w;
     p.dst_h = c->dst_h;
-    p.row_bytes = c->row_bytes;
+    p.row_bytes = layout == LAYOUT_TAPS ? c->tap_row_bytes : c->row_bytes;
     p.rows_per_group = c->rows_per_group;
     p.n_groups = c->n_groups;
     p.stages = c->stages;
@@ -452,7 +532,7 @@ int push_common(esd_ctx* c, const uint8_t* d_src, int64_t n, int64_t frame_strid
     p.bins = c->cfg.hist_bins;
     p.want_bgr = (c->cfg.detectors & ESD_DET_THRESHOLD) ? 1 : 0;
     p.yrows = c->d_yrows;
-    p.xtab = c->d_xtab;
+    p.xtab = layout == LAYOUT_TAPS ? c->d_xtab_taps : c->d_xtab;
     p.sdiv = c->d_sdiv;
     p.hdiv = c->d_hdiv;
     p.units = plan.d_units;
@@ -745,6 +825,18 @@ int esd_create(esd_ctx** out, const esd_config* cfg, int device) {
         }
         CUB(cudaMalloc(&c->d_xtab, sizeof(uint2) * dw));
         CUB(cudaMemcpy(c->d_xtab, xt.data(), sizeof(uint2) * dw, cudaMemcpyHostToDevice));
+        if (c->resize) {  // tap-compact layout: column d of a gathered row holds [tap0 BGR, tap1 BGR] at byte 6 d
+            c->tap_row_bytes = (6 * dw + 15) & ~15;
+            c->tap_src_off.resize(dw);
+            std::vector<uint2> xt2(dw);
+            for (int x = 0; x < dw; ++x) {
+                c->tap_src_off[x] = 3 * xo0[x];
+                xt2[x].x = (uint32_t)(6 * x);
+                xt2[x].y = xt[x].y;
+            }
+            CUB(cudaMalloc(&c->d_xtab_taps, sizeof(uint2) * dw));
+            CUB(cudaMemcpy(c->d_xtab_taps, xt2.data(), sizeof(uint2) * dw, cudaMemcpyHostToDevice));
+        }
     }
     {  // OpenCV RGB2HSV_b tables (A.3)
         int sdiv[256], hdiv[256];
@@ -762,20 +854,23 @@ int esd_create(esd_ctx** out, const esd_config* cfg, int device) {
     // ---- kernel shape
     c->rowbuf = ((c->row_bytes + 15 + 15) & ~15) + 16;
     // destination rows per pipeline stage: 2 amortises the per-stage barrier/metadata work over two pixels per thread
-    int RS = cfg->rows_per_stage > 0 ? cfg->rows_per_stage : 4;
+    // full-resolution scoring (no resize, >= 4 pixels per thread per row) is compute/latency-bound: small groups,
+    // single-row stages and a deeper ring measured best there (scripts/noresize_probe.py)
+    const bool wide_noresize = !c->resize && c->pxt >= 4;
+    int RS = cfg->rows_per_stage > 0 ? cfg->rows_per_stage : (wide_noresize ? 1 : 4);
     RS = std::max(1, std::min(RS, kMaxRowsPerStage));
     while (RS > 1 && (size_t)RS * (c->resize ? 2 : 1) * c->rowbuf > 48 * 1024) --RS;
     c->rows_per_stage = RS;
     c->stage_bytes = RS * (c->resize ? 2 : 1) * c->rowbuf;
     // rows per group: 16 measured best at 1080p->256x144 (profiles/r01_sweep.md); the previous-frame HSV of
     // a group lives in shared memory (R * pxt KB), keep it <= 32 KB unless the caller insists
-    int R = cfg->rows_per_group > 0 ? cfg->rows_per_group : std::max(1, std::min(16, 32 / c->pxt));
+    int R = cfg->rows_per_group > 0 ? cfg->rows_per_group : wide_noresize ? 2 : std::max(1, std::min(16, 32 / c->pxt));
     R = std::min(R, dh);
     R = std::min(R, 255);
     while (R > 1 && ((int64_t)R * c->pxt > 256 || (int64_t)R * dw > 65535)) --R;
     c->rows_per_group = R;
     c->n_groups = (dh + R - 1) / R;
-    int stages = cfg->pipeline_stages > 0 ? std::min(cfg->pipeline_stages, kMaxStages) : (c->rows_per_stage >= 4 ? 2 : c->rows_per_stage > 1 ? 3 : 4);
+    int stages = cfg->pipeline_stages > 0 ? std::min(cfg->pipeline_stages, kMaxStages) : (wide_noresize ? 4 : c->rows_per_stage >= 4 ? 2 : c->rows_per_stage > 1 ? 3 : 4);
     const size_t smem_limit = prop.sharedMemPerBlockOptin;
     while (stages > 2 && fused_smem_bytes(c, R, stages) > smem_limit) --stages;
     c->stages = stages;
@@ -844,6 +939,9 @@ void esd_destroy(esd_ctx* c) {
     esd_ingest_close(c);
     free_plans(c);
     for (auto& ev : c->timing_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+    delete c->pool;
+    c->pool = nullptr;
+    cudaFree(c->d_xtab_taps);
     cudaFree(c->d_yrows); cudaFree(c->d_xtab); cudaFree(c->d_sdiv); cudaFree(c->d_hdiv);
     cudaFree(c->d_prev[0]); cudaFree(c->d_prev[1]); cudaFree(c->d_state); cudaFree(c->d_cuts);
     cudaFree(c->d_slab);
@@ -888,13 +986,23 @@ int esd_push_frames(esd_ctx* c, const uint8_t* d_bgr, int64_t n, int64_t frame_s
     if (pitch < c->row_bytes) return fail(c, ESD_ERR_INVALID, "push: pitch %lld < row bytes %d", (long long)pitch, c->row_bytes);
     if (n > 1 && frame_stride < pitch * (int64_t)(c->cfg.src_height - 1) + c->row_bytes)
         return fail(c, ESD_ERR_INVALID, "push: frame stride %lld smaller than a frame", (long long)frame_stride);
-    return push_common(c, d_bgr, n, frame_stride, pitch, false, first_frame_num, (cudaStream_t)stream);
+    return push_common(c, d_bgr, n, frame_stride, pitch, LAYOUT_FULL, first_frame_num, (cudaStream_t)stream);
 }
 
 int esd_push_rows(esd_ctx* c, const uint8_t* d_rows, int64_t n, int64_t first_frame_num, void* stream) {
     if (!c) return ESD_ERR_INVALID;
-    return push_common(c, d_rows, n, (int64_t)c->touched.size() * c->row_bytes, c->row_bytes, true, first_frame_num,
+    return push_common(c, d_rows, n, (int64_t)c->touched.size() * c->row_bytes, c->row_bytes, LAYOUT_ROWS, first_frame_num,
                        (cudaStream_t)stream);
+}
+
+static int ensure_pinned(esd_ctx* c, IngestSlot& s, size_t bytes) {
+    if (s.h_pinned && s.h_pinned_bytes >= bytes) return ESD_OK;
+    if (s.h_pinned) cudaFreeHost(s.h_pinned);
+    s.h_pinned = nullptr;
+    s.h_pinned_bytes = 0;
+    CU(c, cudaHostAlloc(&s.h_pinned, bytes, cudaHostAllocDefault));
+    s.h_pinned_bytes = bytes;
+    return ESD_OK;
 }
 
 // ------------------------------------------------------------------------------------- ingest ring
@@ -903,7 +1011,7 @@ int esd_ingest_open(esd_ctx* c, int32_t n_slots, int32_t frames_per_slot) {
     if (!c->ring.empty()) return fail(c, ESD_ERR_STATE, "ingest ring already open");
     if (n_slots < 2 || frames_per_slot < 1) return fail(c, ESD_ERR_INVALID, "ingest: need >= 2 slots and >= 1 frame per slot");
     CU(c, cudaSetDevice(c->device));
-    const size_t slot_bytes = (size_t)frames_per_slot * c->touched.size() * c->row_bytes;
+    const size_t slot_bytes = (size_t)frames_per_slot * c->touched.size() * std::max(c->row_bytes, c->tap_row_bytes);
     CU(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CU(c, cudaStreamCreateWithFlags(&c->compute_stream, cudaStreamNonBlocking));
     c->ring.resize(n_slots);
@@ -960,12 +1068,65 @@ int esd_ingest_push_host(esd_ctx* c, const uint8_t* h_bgr, int64_t n, int64_t fr
         runs.push_back(Run{i, c->touched[i], j - i});
         i = j;
     }
+    // the tap gather only pays when it shrinks the rows (downscale factor > 2)
+    const bool gather = c->pool != nullptr && c->resize && c->tap_row_bytes < c->row_bytes;
+    const int64_t tfb = nt * c->tap_row_bytes;  // tap-compact frame bytes
     for (int64_t done = 0; done < n;) {
         const int64_t m = std::min<int64_t>(c->frames_per_slot, n - done);
         IngestSlot& s = c->ring[c->next_slot];
         c->next_slot = (c->next_slot + 1) % (int)c->ring.size();
+        TraceTimer trw;
         if (s.in_flight) CU(c, cudaEventSynchronize(s.consumed));  // device slot (and pinned slot) free again
+        trw.lap("wait slot");
         const uint8_t* src = h_bgr + done * frame_stride;
+        const bool use_gather = gather;
+        if (use_gather) {
+            // host threads gather, per touched row, the two BGR taps of every destination column (6 of every
+            // ~3*scale bytes) into the pinned slot: 3.75x fewer PCIe bytes again at 1080p (442 KB per frame)
+            { int rcp = ensure_pinned(c, s, (size_t)c->frames_per_slot * tfb); if (rcp) return rcp; }
+            const int dw = c->dst_w, trb = c->tap_row_bytes, rb = c->row_bytes;
+            const int* off = c->tap_src_off.data();
+            const int32_t* touched = c->touched.data();
+            uint8_t* dst_base = s.h_pinned;
+            std::function<void(int64_t, int64_t)> job = [=](int64_t lo, int64_t hi) {
+                for (int64_t it = lo; it < hi; ++it) {
+                    const int64_t f = it / nt, i = it - f * nt;
+                    const uint8_t* sr = src + f * frame_stride + (int64_t)touched[i] * pitch;
+                    uint8_t* dr = dst_base + it * trb;
+                    if (it + 1 < hi) {  // touch the next row's pages early: hardware prefetchers stop at 4 KB boundaries
+                        const int64_t f1 = (it + 1) / nt, i1 = (it + 1) - f1 * nt;
+                        const uint8_t* nx = src + f1 * frame_stride + (int64_t)touched[i1] * pitch;
+                        for (int b = 0; b < rb; b += 2048) __builtin_prefetch(nx + b, 0, 1);
+                    }
+                    int d = 0;
+                    for (; d < dw - 1 && off[d] + 8 <= rb; ++d) {  // 8-byte moves; the 2 spare bytes are overwritten by d + 1
+                        uint64_t v;
+                        memcpy(&v, sr + off[d], 8);
+                        memcpy(dr + 6 * d, &v, 8);
+                    }
+                    for (; d < dw; ++d) {
+                        const int nbytes = std::min(6, rb - off[d]);  // a clamped last column only has tap 0 (tap 1 weighs 0)
+                        memcpy(dr + 6 * d, sr + off[d], (size_t)nbytes);
+                        if (nbytes < 6) memset(dr + 6 * d + nbytes, 0, (size_t)(6 - nbytes));
+                    }
+                }
+            };
+            TraceTimer tr;
+            c->pool->parallel_for(m * nt, 16, job);
+            tr.lap("host tap gather");
+            CU(c, cudaMemcpyAsync(s.d_rows, s.h_pinned, (size_t)(m * tfb), cudaMemcpyHostToDevice, c->copy_stream));
+            tr.lap("memcpyAsync call");
+            c->h2d_copies++;
+            c->h2d_bytes += m * tfb;
+            CU(c, cudaEventRecord(s.copied, c->copy_stream));
+            CU(c, cudaStreamWaitEvent(c->compute_stream, s.copied, 0));
+            int rc = push_common(c, s.d_rows, m, tfb, c->tap_row_bytes, LAYOUT_TAPS, first_frame_num + done, c->compute_stream);
+            if (rc) return rc;
+            CU(c, cudaEventRecord(s.consumed, c->compute_stream));
+            s.in_flight = true;
+            done += m;
+            continue;
+        }
         if (pinned) {
             // DMA straight from the caller's pinned frames: one strided 2-D copy per row run
             // (rows = frames), so only touched rows cross PCIe.
@@ -977,8 +1138,7 @@ int esd_ingest_push_host(esd_ctx* c, const uint8_t* h_bgr, int64_t n, int64_t fr
             }
         } else {
             // pageable source: the CPU gathers the touched rows into the pinned slot
-            if (!s.h_pinned)
-                CU(c, cudaHostAlloc(&s.h_pinned, (size_t)c->frames_per_slot * cfb, cudaHostAllocDefault));
+            { int rcp = ensure_pinned(c, s, (size_t)c->frames_per_slot * cfb); if (rcp) return rcp; }
             for (int64_t f = 0; f < m; ++f)
                 for (const Run& r : runs)
                     memcpy(s.h_pinned + f * cfb + (int64_t)r.crow * c->row_bytes, src + f * frame_stride + (int64_t)r.row * pitch,
@@ -995,6 +1155,18 @@ int esd_ingest_push_host(esd_ctx* c, const uint8_t* h_bgr, int64_t n, int64_t fr
         s.in_flight = true;
         done += m;
     }
+    return ESD_OK;
+}
+
+int esd_ingest_set_gather(esd_ctx* c, int32_t n_threads) {
+    if (!c) return ESD_ERR_INVALID;
+    if (n_threads < 0 || n_threads > 256) return fail(c, ESD_ERR_INVALID, "ingest: gather threads must be in 0..256");
+    if (n_threads > 0 && !c->resize) return fail(c, ESD_ERR_UNSUPPORTED, "ingest: tap gather needs a resizing context");
+    CU(c, cudaSetDevice(c->device));
+    int rc = sync_all(c);
+    if (rc) return rc;
+    delete c->pool;
+    c->pool = n_threads > 0 ? new GatherPool(n_threads) : nullptr;
     return ESD_OK;
 }
 

@@ -86,7 +86,7 @@ class BatchVideo:
 
 class SceneManager:
     def __init__(self, stats_manager: Optional[StatsManager] = None, device: int = 0, batch_frames: int = 512,
-                 downscale_mode: str = "float", tuning: Optional[dict] = None):
+                 downscale_mode: str = "float", tuning: Optional[dict] = None, ingest_threads: int = 0):
         self._detector_list: List[SceneDetector] = []
         self.stats_manager = stats_manager
         self._device = device
@@ -95,6 +95,8 @@ class SceneManager:
         self._downscale = 1
         self._downscale_mode = downscale_mode
         self._tuning = dict(tuning or {})
+        # host frames: > 0 lets that many host threads gather only the bytes the kernel reads before the H2D copy
+        self._ingest_threads = int(ingest_threads)
         self._cutting_list: List[int] = []
         self._cuts_by_detector: dict = {}
         self._start_pos: Optional[int] = None
@@ -200,6 +202,8 @@ class SceneManager:
             if isinstance(batch, np.ndarray):
                 if not host_ring_open:
                     ctx.ingest_open(3, min(self._batch_frames, 64))
+                    if self._ingest_threads > 0 and ctx.dst_size != (width, height):
+                        ctx.ingest_set_gather(self._ingest_threads)
                     host_ring_open = True
                 ctx.ingest_push_numpy(batch, pos)
                 ctx.synchronize()  # the caller may recycle `batch` as soon as we return to read_batch

@@ -117,7 +117,8 @@ def detect_scenes_frames(video, config: Optional[dict] = None, fps: Optional[flo
     if not hasattr(video, "read_batch"):
         video = TensorVideo(video, fps or float(config.get("fps", 30.0)))
     sm = SceneManager(device=device, batch_frames=batch_frames,
-                      downscale_mode=str(config.get("downscale_mode", "float")))
+                      downscale_mode=str(config.get("downscale_mode", "float")),
+                      ingest_threads=int(config.get("ingest_threads", 0)))
     if "downscale" in config:
         sm.downscale = int(config["downscale"])
     if config.get("auto_downscale") is False:

@@ -286,6 +286,24 @@ def pcie_probe(dev, local):
         out[f"ring_slot{fps_slot}_GBps"] = 4 * n * ctx.alg_bytes_per_frame / dt / 1e9
         want = ctx.read_scores(0, n, ["sums3"])["sums3"]
         ctx.close()
+    # host tap gather: threads copy only the 6 tap bytes per destination column of the touched rows
+    hn = host.numpy()
+    for threads in (4, 8, 16, 32):
+        if threads > (os.cpu_count() or 1):
+            continue
+        ctx = capi.EsdContext(cfg, local)
+        ctx.ingest_open(3, 128)
+        ctx.ingest_set_gather(threads)
+        ctx.ingest_push_numpy(hn, 0); ctx.synchronize()
+        t0 = time.perf_counter()
+        for i in range(1, 5):
+            ctx.ingest_push_numpy(hn, i * n)
+        ctx.synchronize()
+        dt = time.perf_counter() - t0
+        out[f"gather{threads}_frames_per_s"] = 4 * n / dt
+        got = ctx.read_scores(0, n, ["sums3"])["sums3"]
+        out[f"gather{threads}_bit_exact"] = bool(np.array_equal(got, want))
+        ctx.close()
     # zero copy: the fused kernel's TMA loads read the pinned host frames directly over PCIe
     ctx = capi.EsdContext(cfg, local)
     stream = torch.cuda.current_stream().cuda_stream

@@ -25,6 +25,6 @@ def test_bench_line_contract():
     assert 0.2 < r["frac"] < 1.3
     assert d["gpu_launches"] >= 5 * 3
     e = d["e2e"]
-    assert e["value"] > 0 and e["h2d_bytes_per_step"] == 128 * 1658880 and e["d2h_bytes_per_step"] > 0
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] in (128 * 1658880, 128 * 288 * 1536) and e["d2h_bytes_per_step"] > 0
     assert e["value"] < d["value"]
     assert d["value"] > 5e5

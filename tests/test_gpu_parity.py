@@ -284,7 +284,8 @@ def test_service_dict_vs_oracle():
         want = P.detect_scenes_dicts(list(frames_np), mk(), 30.0, backend="closed_form")
         got_dev = detect_scenes_frames(torch.from_numpy(frames_np).to(DEV), cfg, fps=30.0, batch_frames=96)
         got_host = detect_scenes_frames(frames_np, cfg, fps=30.0, batch_frames=96)  # through the pinned ingest ring
-        assert got_dev == want and got_host == want
+        got_gather = detect_scenes_frames(frames_np, dict(cfg, ingest_threads=3), fps=30.0, batch_frames=96)  # host tap gather
+        assert got_dev == want and got_host == want and got_gather == want
         assert all(s["duration_ms"] > 0 and s["end_ms"] >= s["start_ms"] >= 0 for s in got_dev["scenes"])
         assert [s["scene_index"] for s in got_dev["scenes"]] == list(range(len(got_dev["scenes"])))
 
@@ -301,16 +302,33 @@ def test_ingest_ring_touched_rows_only():
         geo = ref.geometry
     assert geo.n_touched_rows == 288 and geo.alg_bytes_per_frame == 1658880
     for src in (host.numpy(), pinned.numpy()):
-        with make_ctx(w, h, None) as ctx:
-            ctx.ingest_open(3, 16)
-            ctx.ingest_push_numpy(src[:25], 0)
-            ctx.ingest_push_numpy(src[25:], 25)
-            got = ctx.read_scores(0, n)
-            nbytes, _ = ctx.ingest_stats()
+        for threads, per_frame in ((0, 1658880), (5, 288 * 1536)):
+            with make_ctx(w, h, None) as ctx:
+                ctx.ingest_open(3, 16)
+                ctx.ingest_set_gather(threads)  # 0: DMA of touched rows; >0: host threads gather the tap bytes only
+                ctx.ingest_push_numpy(src[:25], 0)
+                ctx.ingest_push_numpy(src[25:], 25)
+                got = ctx.read_scores(0, n)
+                nbytes, _ = ctx.ingest_stats()
+                ctx.ingest_close()
+            assert nbytes == n * per_frame
+            for k in want:
+                assert np.array_equal(got[k], want[k], equal_nan=True), (k, threads)
+    # gather on ragged geometry: unaligned rows, clamped last column, odd pitch
+    rng = np.random.default_rng(77)
+    for (gw, gh, dst) in ((333, 200, (256, 154)), (257, 64, (256, 64)), (1000, 30, (500, 15)), (1001, 31, (143, 5)), (700, 33, (100, 11))):
+        fr = rng.integers(0, 256, (11, gh, gw, 3), dtype=np.uint8)
+        with make_ctx(gw, gh, dst) as ref:
+            ref.push_tensor(torch.from_numpy(fr).to(DEV), 0)
+            w2 = ref.read_scores(0, 11)
+        with make_ctx(gw, gh, dst) as ctx:
+            ctx.ingest_open(2, 4)
+            ctx.ingest_set_gather(3)
+            ctx.ingest_push_numpy(fr, 0)
+            g2 = ctx.read_scores(0, 11)
             ctx.ingest_close()
-        assert nbytes == n * 1658880
-        for k in want:
-            assert np.array_equal(got[k], want[k], equal_nan=True), k
+        for k in w2:
+            assert np.array_equal(g2[k], w2[k], equal_nan=True), (gw, k)
 
 
 def test_frame_range_shards_and_global_decision():
@@ -543,3 +561,41 @@ def test_delta_edges_canny_dilate_vs_oracle():
     for k in range(12):
         assert mine.process_frame(k, small[k]) == theirs.process_frame(k, small[k]), k
     mine.close()
+
+
+def test_model_manager_on_a_real_video_file(tmp_path):
+    """The ml-service surface end to end: `await ModelManager().detect_scenes(video_path, config)` on an .mp4 written
+    and decoded by OpenCV (decode is out of scope, so it stays on the CPU), against the oracle on the same decoded frames."""
+    import asyncio
+
+    cv2 = pytest.importorskip("cv2")
+    from eioku_b200.service import ModelManager
+
+    w, h, n, seed = 640, 360, 180, 41
+    sch = synth.build_schedule(seed, n, min_len=25, max_len=60, noise_amp=0)
+    frames = co.synth_frames(seed, w, h, sch.descs)
+    path = str(tmp_path / "clip.mp4")
+    vw = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"mp4v"), 25.0, (w, h))
+    if not vw.isOpened():
+        pytest.skip("no mp4v encoder in this OpenCV build")
+    for f in frames:
+        vw.write(f)
+    vw.release()
+    cap = cv2.VideoCapture(path)
+    decoded = []
+    while True:
+        ok, fr = cap.read()
+        if not ok:
+            break
+        decoded.append(fr)
+    cap.release()
+    assert len(decoded) == n
+    for cfg, mk in (({}, lambda: [P.ContentDetector(backend="closed_form")]),
+                    ({"detector": "adaptive+threshold", "fade_threshold": 20, "min_scene_len": 10},
+                     lambda: [P.AdaptiveDetector(min_scene_len=10, backend="closed_form"), P.ThresholdDetector(threshold=20, min_scene_len=10)])):
+        want = P.detect_scenes_dicts(decoded, mk(), 25.0, backend="closed_form")
+        got = asyncio.run(ModelManager().detect_scenes(path, cfg))
+        assert got == want and len(got["scenes"]) >= 3
+    np.save(str(tmp_path / "clip.npy"), np.stack(decoded))
+    assert asyncio.run(ModelManager().detect_scenes(str(tmp_path / "clip.npy"), {"fps": 25.0})) == \
+        P.detect_scenes_dicts(decoded, [P.ContentDetector(backend="closed_form")], 25.0, backend="closed_form")
