@@ -599,3 +599,60 @@ def test_model_manager_on_a_real_video_file(tmp_path):
     np.save(str(tmp_path / "clip.npy"), np.stack(decoded))
     assert asyncio.run(ModelManager().detect_scenes(str(tmp_path / "clip.npy"), {"fps": 25.0})) == \
         P.detect_scenes_dicts(decoded, [P.ContentDetector(backend="closed_form")], 25.0, backend="closed_form")
+
+
+def test_adaptive_and_hist_decisions_on_random_score_traces():
+    """AdaptiveDetector rolling-window ratio (incl. the zero-average branches) + min_scene_len rule and the
+    HistogramDetector rule (incl. its `if not self._last_scene_cut` quirk) on random score arrays: device decision
+    pass through esd_decide_arrays vs the oracle classes replaying the same scores."""
+    rng = np.random.default_rng(99)
+
+    class ReplayAdaptive(P.AdaptiveDetector):
+        def _calculate_frame_score(self, frame_num, frame_img):
+            return frame_img  # np.float64 score (python float 0.0 for the first frame, like PySceneDetect)
+
+    for trial in range(30):
+        n = int(rng.integers(1, 300))
+        w = int(rng.choice([1, 2, 3, 5]))
+        L = int(rng.choice([0, 1, 5, 15]))
+        thr = float(rng.choice([1.5, 3.0, 7.0]))
+        mcv = float(rng.choice([0.0, 5.0, 15.0]))
+        start = int(rng.choice([0, 7, 1000]))
+        base = rng.gamma(1.5, 2.0, n)
+        base[rng.random(n) < 0.08] *= rng.uniform(5, 30)
+        if trial % 3 == 0:
+            base[rng.random(n) < 0.5] = 0.0  # stretches of identical frames -> average_is_zero branches
+        base[0] = 0.0
+        scores = base.astype(np.float64)
+        o = ReplayAdaptive(adaptive_threshold=thr, min_scene_len=L, window_width=w, min_content_val=mcv, backend="closed_form")
+        want = []
+        for i in range(n):
+            want += o.process_frame(start + i, np.float64(scores[i]) if i else 0.0)
+        with make_ctx(64, 48, None, detectors=capi.ESD_DET_ADAPTIVE, adaptive_threshold=thr, adaptive_min_scene_len=L,
+                      adaptive_window_width=w, adaptive_min_content_val=mcv) as ctx:
+            cuts, ratio = ctx.decide_arrays(capi.ESD_DET_ADAPTIVE, start, scores)
+        assert cuts == want, (trial, w, L, thr, mcv)
+        for t, r in o.ratios.items():
+            assert np.float64(r).view(np.uint64) == ratio[t - start].view(np.uint64), (trial, t)
+        assert np.isnan(ratio[:min(w, n)]).all() and (n <= w or np.isnan(ratio[max(n - w, 0):]).all())
+
+    for trial in range(30):
+        n = int(rng.integers(1, 300))
+        L = int(rng.choice([0, 1, 5, 15]))
+        thr = float(rng.choice([0.05, 0.3, 0.9]))
+        start = int(rng.choice([0, 1, 42]))
+        diffs = np.clip(1.0 - rng.gamma(0.5, 0.1, n), -1.0, 1.0)
+        diffs[0] = np.nan
+        T = max(0.0, min(1.0, 1.0 - thr))
+        last = None
+        want = []
+        for i in range(n):  # HistogramDetector.process_frame with the histogram comparison replaced by diffs[i]
+            fn = start + i
+            if not last:
+                last = fn
+            if i > 0 and diffs[i] <= T and (fn - last) >= L:
+                want.append(fn)
+                last = fn
+        with make_ctx(64, 48, None, detectors=capi.ESD_DET_HIST, hist_threshold=thr, hist_min_scene_len=L) as ctx:
+            cuts, _ = ctx.decide_arrays(capi.ESD_DET_HIST, start, diffs)
+        assert cuts == want, (trial, L, thr, start)
