@@ -41,6 +41,34 @@ def scenes_to_dicts(scenes: Sequence[Tuple[int, int]], fps: float) -> List[dict]
     return out
 
 
+def frame_to_timecode(frame: int, fps: float, precision: int = 3) -> str:
+    """HH:MM:SS.nnn of a frame number, formatted like scenedetect.FrameTimecode.get_timecode (rounded to
+    `precision` decimals, with the 60-second carry guard) [upstream-recall]."""
+    secs = frame / fps
+    hrs = int(secs / 3600.0)
+    secs -= hrs * 3600.0
+    mins = int(secs / 60.0)
+    secs = max(0.0, secs - mins * 60.0)
+    secs = min(60.0, round(secs, precision))
+    if int(secs) == 60:
+        secs = 0.0
+        mins += 1
+        if mins >= 60:
+            mins = 0
+            hrs += 1
+    msec = format(secs, ".%df" % (precision + 1)) if precision else ""
+    msec_str = msec[-(2 + precision):-1]
+    return "%02d:%02d:%02d%s" % (hrs, mins, int(secs), msec_str)
+
+
+def scenes_to_boundaries(scenes: Sequence[Tuple[int, int]], fps: float) -> List[dict]:
+    """SceneBoundary records of the reference's design document
+    (/root/reference/.kiro/specs/semantic-video-search/design.md:994-1007): {scene, start, end} with
+    HH:MM:SS.mmm timecodes."""
+    return [{"scene": i, "start": frame_to_timecode(a, fps), "end": frame_to_timecode(b, fps)}
+            for i, (a, b) in enumerate(scenes)]
+
+
 def build_detectors(config: dict) -> list:
     """Detector objects for a scene-task config dict (surface B1)."""
     cfg = dict(config or {})

@@ -16,7 +16,7 @@ from eioku_b200 import capi, sharding
 from eioku_b200.detectors import (AdaptiveDetector, ContentDetector, FlashFilter, HistogramDetector, StatsManager,
                                   ThresholdDetector)
 from eioku_b200.scene_manager import SceneManager, compute_downscale_factor, get_scenes_from_cuts
-from eioku_b200.service import ModelManager, build_detectors, scenes_to_dicts
+from eioku_b200.service import ModelManager, build_detectors, frame_to_timecode, scenes_to_boundaries, scenes_to_dicts
 from oracle import psd_cv2 as P
 
 
@@ -162,6 +162,17 @@ def test_scene_dicts_match_reference_schema():
         assert s["duration_ms"] > 0 and s["end_ms"] >= s["start_ms"] >= 0
         assert all(isinstance(v, int) for v in s.values())
     assert scenes_to_dicts([(0, 1001)], 29.97)[0]["end_ms"] == int(1001 / 29.97 * 1000)
+
+
+def test_scene_boundaries_timecodes():
+    assert frame_to_timecode(0, 30.0) == "00:00:00.000"
+    assert frame_to_timecode(150, 30.0) == "00:00:05.000"
+    assert frame_to_timecode(1001, 29.97) == "00:00:33.400"
+    assert frame_to_timecode(30 * 3600 + 30 * 61 + 7, 30.0) == "01:01:01.233"
+    assert frame_to_timecode(1799, 30.0) == "00:00:59.967"
+    assert frame_to_timecode(215999, 60.0) == "00:59:59.983"
+    assert scenes_to_boundaries([(0, 150), (150, 375)], 30.0) == [
+        {"scene": 0, "start": "00:00:00.000", "end": "00:00:05.000"}, {"scene": 1, "start": "00:00:05.000", "end": "00:00:12.500"}]
 
 
 def test_build_detectors_from_task_config():
