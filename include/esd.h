@@ -124,6 +124,9 @@ ESD_API const char* esd_strerror(int status);
 ESD_API const char* esd_last_error(const esd_ctx* ctx);
 ESD_API int esd_device_count(void);
 
+/* Replaces: detector construction + SceneManager set-up the spec calls for (README.md:56; design.md:994-1007); in
+ * the shipped reference, the ffmpeg command line built at ml-service/src/services/model_manager.py:731-745
+ * (config.get("threshold") :732 is the only knob read there). */
 ESD_API void esd_config_default(esd_config* cfg); /* PySceneDetect defaults; detectors = CONTENT */
 ESD_API int esd_create(esd_ctx** out, const esd_config* cfg, int device);
 ESD_API void esd_destroy(esd_ctx* ctx);
@@ -133,7 +136,10 @@ ESD_API int esd_get_geometry(const esd_ctx* ctx, esd_geometry* out);
 /* touched source rows in ascending order (n_touched_rows entries) */
 ESD_API int esd_get_touched_rows(const esd_ctx* ctx, int32_t* rows, int32_t cap);
 
-/* Score n device-resident frames (uint8 BGR, row pitch `pitch_bytes`, frame stride
+/* Replaces: the per-frame scoring loop -- in the shipped reference the ffmpeg child process started by
+ * subprocess.run at model_manager.py:750-755 (`select='gt(scene,T)'` scores every decoded frame); as specified,
+ * PySceneDetect's SceneManager loop `cv2.resize -> detector.process_frame`.
+ * Score n device-resident frames (uint8 BGR, row pitch `pitch_bytes`, frame stride
  * `frame_stride_bytes`) and run the decision passes.  Frame numbers must be sequential
  * across calls: first_frame_num == (first frame of the first push) + frames pushed so far.
  * Asynchronous on `stream`. */
@@ -143,7 +149,9 @@ ESD_API int esd_push_frames(esd_ctx* ctx, const uint8_t* d_bgr, int64_t n, int64
  * ascending source-row order) that the ingest ring produces. */
 ESD_API int esd_push_rows(esd_ctx* ctx, const uint8_t* d_rows, int64_t n, int64_t first_frame_num, void* stream);
 
-/* Host frames -> pinned ring -> cudaMemcpyAsync on a copy stream -> scoring on the ctx's own
+/* Replaces: the decoded-frame hand-off (`ffmpeg -i <path>` decode feeding the select filter, model_manager.py:736-745;
+ * `cv2.VideoCapture.read()` in the other tasks, e.g. :237-263).  Decode itself stays outside.
+ * Host frames -> pinned ring -> cudaMemcpyAsync on a copy stream -> scoring on the ctx's own
  * compute stream.  Only the touched source rows cross PCIe.  h_bgr may be pageable (staged through
  * the ring by the CPU) or pinned (DMA'd directly). */
 ESD_API int esd_ingest_open(esd_ctx* ctx, int32_t n_slots, int32_t frames_per_slot);
@@ -164,7 +172,9 @@ ESD_API int esd_synchronize(esd_ctx* ctx);
 ESD_API int esd_join(esd_ctx* ctx, void* stream);
 ESD_API int64_t esd_frames_pushed(const esd_ctx* ctx);
 
-/* Per-frame results for frames [from_frame, from_frame + n) (absolute frame numbers).  Any output
+/* Replaces: nothing in the shipped reference (ffmpeg's per-frame scene score is discarded, model_manager.py:762);
+ * PySceneDetect's StatsManager metrics in the specified design.
+ * Per-frame results for frames [from_frame, from_frame + n) (absolute frame numbers).  Any output
  * pointer may be NULL.  sums3: [n][3] sum|dH|,sum|dS|,sum|dV| (0 for the first frame of the video);
  * content_val / adaptive_val: float64 score with the content / adaptive weights; adaptive_ratio: NaN
  * where the window is incomplete; hist: [n][bins] Y-histogram counts; hist_diff: NaN for the first frame.
@@ -184,7 +194,10 @@ ESD_API int esd_read_average_rgb(esd_ctx* ctx, int64_t from_frame, int64_t n, do
 ESD_API int esd_post_process(esd_ctx* ctx, int32_t detector, int64_t last_frame_num, int64_t* cuts, int64_t cap,
                              int64_t* n_cuts);
 
-/* Cuts emitted so far by one detector (ESD_DET_*), starting at index `from_index` of its cut list.
+/* Replaces: parsing the `pts_time:` lines of ffmpeg's showinfo output into cut timestamps
+ * (model_manager.py:762-786); the scene dicts of :775-781 / :809-824 are built from these cuts on the host
+ * (eioku_b200/service.py:scenes_to_dicts).
+ * Cuts emitted so far by one detector (ESD_DET_*), starting at index `from_index` of its cut list.
  * *n_total receives the total number of cuts the detector has emitted.  Synchronises. */
 ESD_API int esd_get_cuts(esd_ctx* ctx, int32_t detector, int64_t from_index, int64_t* cuts, int64_t cap,
                  int64_t* n_written, int64_t* n_total);
