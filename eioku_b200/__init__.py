@@ -8,11 +8,11 @@ from .detectors import (AdaptiveDetector, ContentDetector, FlashFilter, Histogra
                         StatsManager, ThresholdDetector)
 from .scene_manager import (BatchVideo, SceneManager, TensorVideo, compute_downscale_factor,
                             get_scenes_from_cuts)
-from .service import ModelManager, detect_scenes_frames, scenes_to_dicts
+from .service import ModelManager, detect, detect_scenes_frames, scenes_to_boundaries, scenes_to_dicts
 
 __all__ = [
     "AdaptiveDetector", "ContentDetector", "FlashFilter", "HistogramDetector", "SceneDetector", "StatsManager", "ThresholdDetector",
     "BatchVideo", "SceneManager", "TensorVideo", "compute_downscale_factor", "get_scenes_from_cuts",
-    "ModelManager", "detect_scenes_frames", "scenes_to_dicts",
+    "ModelManager", "detect", "detect_scenes_frames", "scenes_to_boundaries", "scenes_to_dicts",
 ]
 __version__ = "0.1.0"

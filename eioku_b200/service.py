@@ -165,6 +165,29 @@ def detect_scenes_frames(video, config: Optional[dict] = None, fps: Optional[flo
         sm.close()
 
 
+def detect(video, detector, stats_file_path: Optional[str] = None, start_in_scene: bool = False, fps: Optional[float] = None,
+           device: int = 0) -> List[Tuple[int, int]]:
+    """Counterpart of ``scenedetect.detect(video_path, detector, ...)``: run one detector over a video and return the
+    scene list as (start_frame, end_frame) pairs.  `video` is a path (decoded on the host, see `_default_decoder`),
+    a TensorVideo / BatchVideo, or an [N,H,W,3] uint8 array / CUDA tensor."""
+    if isinstance(video, str):
+        video = _default_decoder(video, {"fps": fps or 30.0})
+    elif not hasattr(video, "read_batch"):
+        video = TensorVideo(video, fps or 30.0)
+    from .detectors import StatsManager
+
+    stats = StatsManager() if stats_file_path else None
+    sm = SceneManager(stats_manager=stats, device=device)
+    sm.add_detector(detector)
+    try:
+        sm.detect_scenes(video)
+        if stats is not None:
+            stats.save_to_csv(stats_file_path)
+        return sm.get_scene_list(start_in_scene=start_in_scene)
+    finally:
+        sm.close()
+
+
 def _default_decoder(video_path: str, config: dict):
     """Frames for a path.  Decode is out of scope (north_star); this handles .npy frame dumps and,
     when OpenCV is importable, container files via cv2.VideoCapture in host batches."""

@@ -596,6 +596,15 @@ def test_model_manager_on_a_real_video_file(tmp_path):
         want = P.detect_scenes_dicts(decoded, mk(), 25.0, backend="closed_form")
         got = asyncio.run(ModelManager().detect_scenes(path, cfg))
         assert got == want and len(got["scenes"]) >= 3
+    import eioku_b200
+    stats_csv = str(tmp_path / "stats.csv")
+    scenes = eioku_b200.detect(path, ContentDetector(), stats_file_path=stats_csv)  # scenedetect.detect() counterpart
+    ref_det = P.ContentDetector(backend="closed_form")
+    ref_cuts, _ = P.detect(decoded, [ref_det], backend="closed_form")
+    assert scenes == P.get_scenes_from_cuts(ref_cuts, 0, n)
+    rows = open(stats_csv).read().strip().split("\n")
+    assert rows[0].startswith("Frame Number,content_val") and len(rows) == n  # header + frames 2..n (frame 1 has no score)
+    assert float(rows[1].split(",")[1]) == ref_det.scores[1]
     np.save(str(tmp_path / "clip.npy"), np.stack(decoded))
     assert asyncio.run(ModelManager().detect_scenes(str(tmp_path / "clip.npy"), {"fps": 25.0})) == \
         P.detect_scenes_dicts(decoded, [P.ContentDetector(backend="closed_form")], 25.0, backend="closed_form")
