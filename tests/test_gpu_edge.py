@@ -187,3 +187,29 @@ def test_stats_manager_metrics_equal_oracle():
     for t, r in ref.ratios.items():
         assert st2.get_metrics(t, ["adaptive_ratio (w=2)"])[0] == r
     det.close()
+
+
+def test_ingest_of_cropped_host_views():
+    """Host frames that are a crop of a wider/taller array (row pitch > row bytes, unaligned base, frame stride > frame):
+    every ingest route (CPU row staging, pinned DMA, host tap gather) must equal the device-resident result."""
+    rng = np.random.default_rng(21)
+    big = rng.integers(0, 256, (9, 130, 700, 3), dtype=np.uint8)
+    view = big[:, 5:125, 13:653]  # 640x120 crop
+    assert not view.flags["C_CONTIGUOUS"] and view.strides[2] == 3
+    dense = np.ascontiguousarray(view)
+    n, h, w, _ = dense.shape
+    with make_ctx(w, h, None) as ref:
+        ref.push_tensor(torch.from_numpy(dense).to(DEV), 0)
+        want = ref.read_scores(0, n)
+    pinned_big = torch.from_numpy(big).pin_memory().numpy()
+    for src_big in (big, pinned_big):
+        src = src_big[:, 5:125, 13:653]
+        for threads in (0, 4):
+            with make_ctx(w, h, None) as ctx:
+                ctx.ingest_open(2, 4)
+                ctx.ingest_set_gather(threads)
+                ctx.ingest_push_host(src.ctypes.data, n, src.strides[0], src.strides[1], 0)
+                got = ctx.read_scores(0, n)
+                ctx.ingest_close()
+            for k in want:
+                assert np.array_equal(got[k], want[k], equal_nan=True), (k, threads)
