@@ -864,7 +864,7 @@ int esd_create(esd_ctx** out, const esd_config* cfg, int device) {
     c->stage_bytes = RS * (c->resize ? 2 : 1) * c->rowbuf;
     // rows per group: 16 measured best at 1080p->256x144 (profiles/r01_sweep.md); the previous-frame HSV of
     // a group lives in shared memory (R * pxt KB), keep it <= 32 KB unless the caller insists
-    int R = cfg->rows_per_group > 0 ? cfg->rows_per_group : wide_noresize ? 2 : std::max(1, std::min(16, 32 / c->pxt));
+    int R = cfg->rows_per_group > 0 ? cfg->rows_per_group : wide_noresize ? std::max(1, std::min(4, 32 / c->pxt)) : std::max(1, std::min(16, 32 / c->pxt));
     R = std::min(R, dh);
     R = std::min(R, 255);
     while (R > 1 && ((int64_t)R * c->pxt > 256 || (int64_t)R * dw > 65535)) --R;

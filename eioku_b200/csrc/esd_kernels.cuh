@@ -214,6 +214,70 @@ __device__ __forceinline__ void score_row(const FusedParams& p, const uint8_t* _
     }
 }
 
+// Full-resolution rows (no resize) with 16-byte aligned rows: a thread takes four consecutive pixels = three aligned
+// words, so there are no funnel shifts, the previous HSV moves as one 16-byte vector and guards are per quad.
+template <int QPT, bool CONTENT, bool HIST, bool SPECIAL>
+__device__ __forceinline__ void score_row_quads(const FusedParams& p, const uint8_t* __restrict__ row0, int flags, int rloc,
+                                                int row, int frame, int tid, const int* __restrict__ s_sdiv,
+                                                const int* __restrict__ s_hdiv, uint32_t* __restrict__ s_prev,
+                                                uint32_t* __restrict__ s_hist_cur, uint32_t& acc_hv, uint32_t& acc_s,
+                                                uint32_t& acc_bgr) {
+    const int quads = (p.dst_w + 3) >> 2;
+#pragma unroll
+    for (int j = 0; j < QPT; ++j) {
+        const int q = j * kConsumers + tid;
+        if (q < quads) {
+            const uint32_t* w = reinterpret_cast<const uint32_t*>(row0) + 3 * q;
+            const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+            const uint32_t px[4] = {w0, __funnelshift_r(w0, w1, 24), __funnelshift_r(w1, w2, 16), w2 >> 8};
+            const int nvalid = min(4, p.dst_w - 4 * q);
+            uint32_t cur[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int b = px[e] & 255u, g = (px[e] >> 8) & 255u, r = (px[e] >> 16) & 255u;
+                cur[e] = CONTENT ? bgr_to_hsv_packed(b, g, r, s_sdiv, s_hdiv) : 0u;
+                if (CONTENT && p.want_bgr && e < nvalid && !(SPECIAL && (flags & F_HALO))) acc_bgr += (uint32_t)(b + g + r);
+                if (HIST && e < nvalid && !(SPECIAL && (flags & F_HALO))) {
+                    const int y = (4899 * r + 9617 * g + 1868 * b + 8192) >> 14;
+                    atomicAdd(&s_hist_cur[(y * p.bins) >> 8], 1u);
+                }
+            }
+            if (CONTENT) {
+                uint4* slot = reinterpret_cast<uint4*>(s_prev) + (rloc * QPT + j) * kConsumers + tid;
+                uint32_t pv[4] = {cur[0], cur[1], cur[2], cur[3]};
+                if (SPECIAL) {
+                    if (!(flags & (F_HALO | F_NOPREV))) {
+                        if (flags & F_CTXPREV) {
+                            for (int e = 0; e < nvalid; ++e) pv[e] = __ldg(p.prev_in + (size_t)row * p.dst_w + 4 * q + e);
+                        } else {
+                            const uint4 t = *slot;
+                            pv[0] = t.x; pv[1] = t.y; pv[2] = t.z; pv[3] = t.w;
+                        }
+                    }
+                    if (flags & F_SAVE)
+                        for (int e = 0; e < nvalid; ++e) p.prev_out[(size_t)row * p.dst_w + 4 * q + e] = cur[e];
+                    if (p.vplane && !(flags & F_HALO))
+                        for (int e = 0; e < nvalid; ++e)
+                            p.vplane[((size_t)frame * p.dst_h + row) * p.dst_w + 4 * q + e] = (uint8_t)(cur[e] >> 16);
+                } else {
+                    const uint4 t = *slot;
+                    pv[0] = t.x; pv[1] = t.y; pv[2] = t.z; pv[3] = t.w;
+                    if (p.vplane)
+                        for (int e = 0; e < nvalid; ++e)
+                            p.vplane[((size_t)frame * p.dst_h + row) * p.dst_w + 4 * q + e] = (uint8_t)(cur[e] >> 16);
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const uint32_t diff = (e < nvalid) ? __vabsdiffu4(cur[e], pv[e]) : 0u;
+                    acc_hv += diff & 0x00ff00ffu;
+                    acc_s += (diff >> 8) & 0xffu;
+                }
+                *slot = make_uint4(cur[0], cur[1], cur[2], cur[3]);
+            }
+        }
+    }
+}
+
 // ALIGNED: every source row starts on a 16-byte boundary (base, pitch and frame stride multiples of 16), so the
 // per-row misalignment is zero and each thread's smem word offset / funnel shift are loop invariants.
 template <bool RESIZE, int PXT, bool CONTENT, bool HIST, bool ALIGNED>
@@ -345,6 +409,7 @@ __global__ void __launch_bounds__(kThreads) fused_score_kernel(const FusedParams
         }
     }
     const uint32_t full_base = smem_u32(full_bar), empty_base = smem_u32(empty_bar);
+    constexpr bool kQuads = !RESIZE && ALIGNED && PXT >= 4;  // wide full-resolution rows: four pixels per thread step
     uint32_t acc_hv = 0, acc_s = 0;  // per-frame, per-thread: H | V << 16 and S
     uint32_t acc_bgr = 0;            // per-frame, per-thread: sum of B+G+R (only when p.want_bgr)
     int hist_buf = 0;
@@ -362,6 +427,12 @@ __global__ void __launch_bounds__(kThreads) fused_score_kernel(const FusedParams
         uint32_t* hist_cur = s_hist + hist_buf * 256;
         if (flags & (F_HALO | F_NOPREV | F_CTXPREV | F_SAVE)) {
             for (int q = 0; q < nrows; ++q) {
+                if (kQuads) {
+                    score_row_quads<(PXT >= 4 ? PXT / 4 : 1), CONTENT, HIST, true>(p, stage + q * row_slot, flags, rloc0 + q, row_first + q,
+                                                                                   m.x, tid, s_sdiv, s_hdiv, s_prev, hist_cur, acc_hv,
+                                                                                   acc_s, acc_bgr);
+                    continue;
+                }
                 const uint4 mr = meta_r[s * kMaxRowsPerStage + q];
                 const uint32_t mis0 = ALIGNED ? 0u : (mr.z & 0xffu), mis1 = ALIGNED ? 0u : ((mr.z >> 8) & 0xffu);
                 score_row<RESIZE, PXT, CONTENT, HIST, true>(p, stage + q * row_slot, stage + q * row_slot + p.rowbuf, mis0, mis1, mr.x,
@@ -370,6 +441,12 @@ __global__ void __launch_bounds__(kThreads) fused_score_kernel(const FusedParams
             }
         } else {
             for (int q = 0; q < nrows; ++q) {
+                if (kQuads) {
+                    score_row_quads<(PXT >= 4 ? PXT / 4 : 1), CONTENT, HIST, false>(p, stage + q * row_slot, flags, rloc0 + q, row_first + q,
+                                                                                    m.x, tid, s_sdiv, s_hdiv, s_prev, hist_cur, acc_hv,
+                                                                                    acc_s, acc_bgr);
+                    continue;
+                }
                 const uint4 mr = meta_r[s * kMaxRowsPerStage + q];
                 const uint32_t mis0 = ALIGNED ? 0u : (mr.z & 0xffu), mis1 = ALIGNED ? 0u : ((mr.z >> 8) & 0xffu);
                 score_row<RESIZE, PXT, CONTENT, HIST, false>(p, stage + q * row_slot, stage + q * row_slot + p.rowbuf, mis0, mis1, mr.x,

@@ -6,7 +6,7 @@ W,H,n=1920,1080,128
 sch=synth.build_schedule(1002,n)
 clip=torch.empty((n,H,W,3),dtype=torch.uint8,device="cuda:0"); capi.synth_fill(clip,1002,sch.descs)
 stream=torch.cuda.current_stream().cuda_stream
-for R,RS,S,occ in [(4,4,2,0),(2,2,3,0),(2,2,4,0),(1,1,4,0),(1,1,6,0),(2,1,4,0),(4,2,3,0),(8,4,2,0),(2,2,2,0),(1,1,8,0)]:
+for R,RS,S,occ in [(0,0,0,0),(2,1,4,0),(2,2,3,0),(4,1,4,0),(1,1,4,0),(4,2,2,0)]:
     cfg=capi.default_config(); cfg.src_width,cfg.src_height,cfg.dst_width,cfg.dst_height=W,H,W,H
     cfg.rows_per_group,cfg.rows_per_stage,cfg.pipeline_stages,cfg.ctas_per_sm=R,RS,S,occ
     cfg.initial_capacity=40*n

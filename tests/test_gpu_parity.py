@@ -161,7 +161,8 @@ def test_int_downscale_mode_golden():
 
 
 @pytest.mark.parametrize("w,h,dst", [(101, 37, None), (333, 200, (256, 154)), (640, 360, (256, 144)), (257, 64, (256, 64)),
-                                     (64, 48, (64, 48)), (1000, 30, (500, 15)), (513, 77, (171, 26)), (2000, 16, (2000, 16))])
+                                     (64, 48, (64, 48)), (1000, 30, (500, 15)), (513, 77, (171, 26)), (2000, 16, (2000, 16)),
+                                     (2001, 9, (2001, 9)), (1366, 11, (1366, 11)), (1922, 7, (1922, 7)), (1024, 5, (1024, 5))])
 def test_random_sizes_vs_oracle(w, h, dst):
     """Ragged / odd / unaligned geometries (row bytes not a multiple of 16, 2x area path, no-resize)."""
     rng = np.random.default_rng(w * 31 + h)
