@@ -213,6 +213,7 @@ def bench_ours(args):
     cfg.detectors = capi.ESD_DET_CONTENT
     cfg.src_width, cfg.src_height = W, H
     cfg.initial_capacity = (args.steps + args.warmup + 2100) * NB
+    cfg.max_cuts = max(65536, 64 * (args.steps + args.warmup + 2100))  # the repeated clip yields ~12 cuts per batch
     for kv in args.tune:
         k, v = kv.split("=")
         setattr(cfg, k, int(v))

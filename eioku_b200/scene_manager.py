@@ -53,6 +53,8 @@ class TensorVideo:
         self.frame_rate = float(fps)
         self.start_frame = int(start_frame)
         self._pos = 0
+        # batches are views of one persistent array: the ingest ring may keep reading them after read_batch returns
+        self.frames_stable = True
 
     @property
     def frame_size(self) -> Tuple[int, int]:
@@ -206,7 +208,8 @@ class SceneManager:
                         ctx.ingest_set_gather(self._ingest_threads)
                     host_ring_open = True
                 ctx.ingest_push_numpy(batch, pos)
-                ctx.synchronize()  # the caller may recycle `batch` as soon as we return to read_batch
+                if not getattr(video, "frames_stable", False):
+                    ctx.synchronize()  # the producer may recycle `batch` as soon as we return to read_batch
             else:
                 ctx.push_tensor(batch, pos)
             pos += n
