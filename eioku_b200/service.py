@@ -222,6 +222,48 @@ def _default_decoder(video_path: str, config: dict):
     return BatchVideo(batches(), (w, h), fps)
 
 
+def provenance_hashes(video_path: str, config: dict) -> Tuple[str, str]:
+    """(config_hash, input_hash) with the semantics of the reference's provenance helpers
+    (/root/reference/ml-service/src/utils/hashing.py:12-54): xxh64 of the key-sorted JSON config and xxh64 of the video
+    file's bytes (of the path string when the file does not exist), first 16 hex digits.  The task handler leaves both
+    empty today (ml-service/src/workers/task_handler.py:149-150); SURVEY.md 8f N2 asks for real ones."""
+    import json
+    import os
+
+    try:
+        import xxhash
+
+        def new():
+            return xxhash.xxh64()
+    except Exception:  # pragma: no cover - xxhash is a reference dependency; keep the task alive without it
+        import hashlib
+
+        def new():
+            return hashlib.blake2b(digest_size=8)
+    h = new()
+    h.update(json.dumps(config or {}, sort_keys=True).encode())
+    config_hash = h.hexdigest()[:16]
+    h = new()
+    if os.path.exists(video_path):
+        with open(video_path, "rb") as f:
+            for block in iter(lambda: f.read(1 << 20), b""):
+                h.update(block)
+    else:
+        h.update(video_path.encode())
+    return config_hash, h.hexdigest()[:16]
+
+
+def scene_detection_response(video_path: str, config: dict, scenes: Sequence[dict], run_id: Optional[str] = None) -> dict:
+    """Fields of the reference's SceneDetectionResponse (ml-service/src/models/responses.py:135-143) around a
+    detect_scenes result."""
+    import uuid
+
+    config_hash, input_hash = provenance_hashes(video_path, config)
+    return {"run_id": run_id or str(uuid.uuid4()), "config_hash": config_hash, "input_hash": input_hash,
+            "producer": PRODUCER, "producer_version": PRODUCER_VERSION,
+            "scenes": [{"scene_index": s["scene_index"], "start_ms": s["start_ms"], "end_ms": s["end_ms"]} for s in scenes]}
+
+
 class ModelManager:
     """The scene-detection slice of the reference's ModelManager (model_manager.py:715)."""
 

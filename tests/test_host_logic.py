@@ -175,6 +175,26 @@ def test_scene_boundaries_timecodes():
         {"scene": 0, "start": "00:00:00.000", "end": "00:00:05.000"}, {"scene": 1, "start": "00:00:05.000", "end": "00:00:12.500"}]
 
 
+def test_provenance_hashes_and_response(tmp_path):
+    xxhash = pytest.importorskip("xxhash")
+    import json
+
+    from eioku_b200.service import provenance_hashes, scene_detection_response
+
+    cfg = {"threshold": 27.0, "detector": "content", "min_scene_len": 15}
+    f = tmp_path / "v.bin"
+    f.write_bytes(bytes(range(256)) * 4099)
+    ch, ih = provenance_hashes(str(f), cfg)
+    assert ch == xxhash.xxh64(json.dumps(cfg, sort_keys=True).encode()).hexdigest()[:16]
+    assert ih == xxhash.xxh64(f.read_bytes()).hexdigest()[:16]
+    assert provenance_hashes("/no/such/file.mp4", {})[1] == xxhash.xxh64(b"/no/such/file.mp4").hexdigest()[:16]
+    scenes = scenes_to_dicts([(0, 150), (150, 375)], 30.0)
+    r = scene_detection_response(str(f), cfg, scenes, run_id="r1")
+    assert set(r) == {"run_id", "config_hash", "input_hash", "producer", "producer_version", "scenes"}  # responses.py:135-143
+    assert r["producer"] == "scenedetect" and r["run_id"] == "r1" and r["config_hash"] == ch and r["input_hash"] == ih
+    assert r["scenes"] == [{"scene_index": 0, "start_ms": 0, "end_ms": 5000}, {"scene_index": 1, "start_ms": 5000, "end_ms": 12500}]
+
+
 def test_build_detectors_from_task_config():
     legacy = build_detectors({"threshold": 0.7, "min_scene_length": 0.6})  # video_discovery_service.py:425-428
     assert len(legacy) == 1 and isinstance(legacy[0], ContentDetector) and legacy[0]._threshold == 27.0
