@@ -569,7 +569,7 @@ int push_common(esd_ctx* c, const uint8_t* d_src, int64_t n, int64_t frame_strid
 
     const double npx = (double)c->dst_w * (double)c->dst_h;  // float(rows * cols)
     if (c->need_edges) {
-        const size_t esmem = 2 * (size_t)(((c->dst_w * c->dst_h) + 31) & ~31);
+        const size_t esmem = 2 * (size_t)(((c->dst_w * c->dst_h) + 31) & ~31) + 8 * (size_t)c->edge_words;
         edges_kernel<<<(unsigned)n, kEdgeThreads, esmem, ts>>>(c->d_vplane[buf], c->dst_w, c->dst_h, c->edge_ksize, c->d_edge_bits,
                                                              c->edge_words);
         CU(c, cudaGetLastError());
@@ -765,9 +765,13 @@ int esd_create(esd_ctx** out, const esd_config* cfg, int device) {
             fail(c, ESD_ERR_INVALID, "kernel_size must be odd integer >= 3");
             return bail(ESD_ERR_INVALID);
         }
+        if (ks > 63) {
+            fail(c, ESD_ERR_UNSUPPORTED, "kernel_size %d too large for the bit-packed dilation (max 63)", ks);
+            return bail(ESD_ERR_UNSUPPORTED);
+        }
         c->edge_ksize = ks;
-        c->edge_words = (dw * dh + 31) / 32;
-        const size_t esmem = 2 * (size_t)((dw * dh + 31) & ~31);
+        c->edge_words = dh * ((dw + 31) / 32);  // row-padded bitmaps
+        const size_t esmem = 2 * (size_t)((dw * dh + 31) & ~31) + 8 * (size_t)c->edge_words;
         if (esmem + 2048 > prop.sharedMemPerBlockOptin) {
             fail(c, ESD_ERR_UNSUPPORTED, "delta_edges needs the detector-resolution frame (%dx%d) in shared memory; at most ~%zu pixels",
                  dw, dh, (size_t)(prop.sharedMemPerBlockOptin - 2048) / 2);

@@ -685,12 +685,26 @@ __device__ __forceinline__ int mag_at(const uint8_t* __restrict__ V, int w, int 
     return sobel_mag(V, w, h, x, y, dx, dy);
 }
 
+// Walks the pixels i = tid, tid + T, tid + 2T, ... of a w-wide image keeping (x, y) without a division per pixel.
+struct PixelWalk {
+    int x, y, dx, dy, w;
+    __device__ __forceinline__ PixelWalk(int first, int step, int width) : w(width) {
+        y = first / width; x = first - y * width;
+        dy = step / width; dx = step - dy * width;
+    }
+    __device__ __forceinline__ void next() {
+        x += dx; y += dy;
+        if (x >= w) { x -= w; ++y; }
+    }
+};
+
+// Output: one bit per pixel in row-padded order, [n][h][ceil(w / 32)] words (padding bits are zero).
 __global__ void __launch_bounds__(kEdgeThreads) edges_kernel(const uint8_t* __restrict__ vplane, int w, int h, int ksize,
                                                              uint32_t* __restrict__ bitmaps, int words_per_frame) {
     extern __shared__ __align__(16) uint8_t esm[];
     const int npx = w * h;
     const int npx_pad = (npx + 31) & ~31;
-    uint8_t* V = esm;                  // [npx_pad]   (reused as the horizontal-dilate buffer)
+    uint8_t* V = esm;                  // [npx_pad]
     uint8_t* map = esm + npx_pad;      // [npx_pad]   0 none, 1 weak, 2/4 frontier, 3 edge
     __shared__ uint32_t hist[256];
     __shared__ int s_low, s_high;
@@ -728,29 +742,32 @@ __global__ void __launch_bounds__(kEdgeThreads) edges_kernel(const uint8_t* __re
     __syncthreads();
     const int low = s_low, high = s_high;
     constexpr int TG22 = 13573;  // (int)(0.4142135623730950488016887242097 * (1 << 15) + 0.5)
-    for (int i = tid; i < npx_pad; i += kEdgeThreads) {
-        uint8_t out = 0;
-        if (i < npx) {
-            const int y = i / w, x = i - y * w;
-            int dx, dy;
-            const int m = sobel_mag(V, w, h, x, y, dx, dy);
-            if (m > low) {
-                const int xa = abs(dx), ya = abs(dy) << 15;
-                const int tg22x = xa * TG22;
-                bool ok;
-                if (ya < tg22x) ok = m > mag_at(V, w, h, x - 1, y) && m >= mag_at(V, w, h, x + 1, y);
-                else {
-                    const int tg67x = tg22x + (xa << 16);
-                    if (ya > tg67x) ok = m > mag_at(V, w, h, x, y - 1) && m >= mag_at(V, w, h, x, y + 1);
+    {
+        PixelWalk pw(tid, kEdgeThreads, w);
+        for (int i = tid; i < npx_pad; i += kEdgeThreads, pw.next()) {
+            uint8_t out = 0;
+            if (i < npx) {
+                const int x = pw.x, y = pw.y;
+                int dx, dy;
+                const int m = sobel_mag(V, w, h, x, y, dx, dy);
+                if (m > low) {
+                    const int xa = abs(dx), ya = abs(dy) << 15;
+                    const int tg22x = xa * TG22;
+                    bool ok;
+                    if (ya < tg22x) ok = m > mag_at(V, w, h, x - 1, y) && m >= mag_at(V, w, h, x + 1, y);
                     else {
-                        const int sgn = ((dx ^ dy) < 0) ? -1 : 1;
-                        ok = m > mag_at(V, w, h, x - sgn, y - 1) && m > mag_at(V, w, h, x + sgn, y + 1);
+                        const int tg67x = tg22x + (xa << 16);
+                        if (ya > tg67x) ok = m > mag_at(V, w, h, x, y - 1) && m >= mag_at(V, w, h, x, y + 1);
+                        else {
+                            const int sgn = ((dx ^ dy) < 0) ? -1 : 1;
+                            ok = m > mag_at(V, w, h, x - sgn, y - 1) && m > mag_at(V, w, h, x + sgn, y + 1);
+                        }
                     }
+                    if (ok) out = (m > high) ? 2 : 1;
                 }
-                if (ok) out = (m > high) ? 2 : 1;
             }
+            map[i] = out;
         }
-        map[i] = out;
     }
     __syncthreads();
     // hysteresis: breadth-first growth of the strong set through weak pixels; frontier label alternates 2 <-> 4
@@ -777,26 +794,40 @@ __global__ void __launch_bounds__(kEdgeThreads) edges_kernel(const uint8_t* __re
         __syncthreads();
         if (!changed[r % 3]) break;
     }
-    // pixels marked in the last round carry the frontier label; together with 3 they are the edges.
-    // dilate with a k x k block of ones (anchor at the centre, outside ignored): separable max
-    const int rad = ksize / 2, rad1 = ksize - 1 - rad;  // window [p - rad, p + rad1] (anchor = k / 2)
-    for (int i = tid; i < npx_pad; i += kEdgeThreads) {
-        uint8_t o = 0;
-        if (i < npx) {
-            const int y = i / w, x = i - y * w;
-            for (int xx = max(x - rad, 0); xx <= min(x + rad1, w - 1); ++xx) o |= (map[y * w + xx] >= 2);
+    // Every edge pixel now carries the label 3.  Dilate with a k x k block of ones (anchor at the centre, outside
+    // ignored) on a bit-packed copy: rows of ceil(w / 32) words, horizontal then vertical OR of shifted words.
+    const int wpr = (w + 31) >> 5;  // words per row
+    uint32_t* bits0 = reinterpret_cast<uint32_t*>(esm + 2 * (size_t)npx_pad);  // [h][wpr] packed edge map
+    uint32_t* bits1 = bits0 + h * wpr;                          // [h][wpr] after the horizontal pass
+    const int rad = ksize / 2, rad1 = ksize - 1 - rad;          // window [p - rad, p + rad1] (anchor = k / 2)
+    {
+        const int lane = tid & 31, warp = tid >> 5;
+        for (int wd = warp; wd < h * wpr; wd += kEdgeThreads / 32) {
+            const int y = wd / wpr, j = wd - y * wpr;
+            const int x = 32 * j + lane;
+            const bool e = x < w && map[y * w + x] == 3;
+            const uint32_t bits = __ballot_sync(0xffffffffu, e);
+            if (lane == 0) bits0[wd] = bits;
         }
-        V[i] = o;
     }
     __syncthreads();
-    for (int i = tid; i < npx_pad; i += kEdgeThreads) {
-        bool o = false;
-        if (i < npx) {
-            const int y = i / w, x = i - y * w;
-            for (int yy = max(y - rad, 0); yy <= min(y + rad1, h - 1); ++yy) o |= (V[yy * w + x] != 0);
-        }
-        const uint32_t bits = __ballot_sync(0xffffffffu, o);
-        if ((tid & 31) == 0) bitmaps[(size_t)blockIdx.x * words_per_frame + (i >> 5)] = bits;
+    for (int wd = tid; wd < h * wpr; wd += kEdgeThreads) {
+        const int y = wd / wpr, j = wd - y * wpr;
+        const uint32_t c = bits0[wd];
+        const uint32_t l = j > 0 ? bits0[wd - 1] : 0u, r = j + 1 < wpr ? bits0[wd + 1] : 0u;
+        uint32_t o = c;
+        // output bit x is set when any input bit in [x - rad, x + rad1] is set
+        for (int d = 1; d <= rad; ++d) o |= (c << d) | (l >> (32 - d));    // input at x - d
+        for (int d = 1; d <= rad1; ++d) o |= (c >> d) | (r << (32 - d));   // input at x + d
+        if (j == wpr - 1 && (w & 31)) o &= (1u << (w & 31)) - 1u;           // keep the padding bits zero
+        bits1[wd] = o;
+    }
+    __syncthreads();
+    for (int wd = tid; wd < h * wpr; wd += kEdgeThreads) {
+        const int y = wd / wpr;
+        uint32_t o = 0;
+        for (int yy = max(y - rad, 0); yy <= min(y + rad1, h - 1); ++yy) o |= bits1[wd + (yy - y) * wpr];
+        bitmaps[(size_t)blockIdx.x * words_per_frame + wd] = o;
     }
 }
 
