@@ -18,6 +18,7 @@ NVCC_FLAGS = [
     "-fmad=false",  # float64 score math must not be contracted (SURVEY.md hard parts)
     "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=hidden",
     "-Xptxas", "-v",
+    "-ldl",
 ]
 
 

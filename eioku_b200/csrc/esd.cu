@@ -10,6 +10,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <dlfcn.h>
 #include <string.h>
 #include <stdlib.h>
 #include <time.h>
@@ -466,6 +467,35 @@ int order_after_last(esd_ctx* c, cudaStream_t st) {
     }
     c->last_stream = st;
     c->have_last_stream = true;
+    return ESD_OK;
+}
+
+
+// Caller-supplied frame pointers are validated before a kernel touches them: an out-of-bounds TMA read is a sticky
+// CUDA fault.  Pageable host memory is rejected; for device allocations the driver's cuMemGetAddressRange (resolved
+// lazily, so the library still loads on machines without a driver) bounds the [first byte, last byte] span.
+int validate_device_span(esd_ctx* c, const uint8_t* ptr, size_t span_bytes, const char* what) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, ptr) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(c, ESD_ERR_INVALID, "%s: pointer is not known to CUDA", what);
+    }
+    if (attr.type == cudaMemoryTypeUnregistered)
+        return fail(c, ESD_ERR_INVALID, "%s: pageable host memory is not device-accessible (use esd_ingest_push_host)", what);
+    if (attr.type != cudaMemoryTypeDevice) return ESD_OK;  // pinned / managed memory: reachable, extent unknown
+    typedef int (*get_range_fn)(unsigned long long*, size_t*, unsigned long long);
+    static get_range_fn get_range = [] {
+        void* h = dlopen("libcuda.so.1", RTLD_LAZY | RTLD_LOCAL);
+        return h ? (get_range_fn)dlsym(h, "cuMemGetAddressRange_v2") : (get_range_fn) nullptr;
+    }();
+    if (!get_range) return ESD_OK;
+    unsigned long long base = 0;
+    size_t size = 0;
+    if (get_range(&base, &size, (unsigned long long)(uintptr_t)ptr) != 0) return ESD_OK;
+    const unsigned long long end = (unsigned long long)(uintptr_t)ptr + span_bytes;
+    if ((unsigned long long)(uintptr_t)ptr < base || end > base + size)
+        return fail(c, ESD_ERR_INVALID, "%s: frames span %zu bytes but the allocation ends %lld bytes earlier", what, span_bytes,
+                    (long long)(end - (base + size)));
     return ESD_OK;
 }
 
@@ -990,11 +1020,20 @@ int esd_push_frames(esd_ctx* c, const uint8_t* d_bgr, int64_t n, int64_t frame_s
     if (pitch < c->row_bytes) return fail(c, ESD_ERR_INVALID, "push: pitch %lld < row bytes %d", (long long)pitch, c->row_bytes);
     if (n > 1 && frame_stride < pitch * (int64_t)(c->cfg.src_height - 1) + c->row_bytes)
         return fail(c, ESD_ERR_INVALID, "push: frame stride %lld smaller than a frame", (long long)frame_stride);
+    if (n > 0 && d_bgr) {
+        const size_t span = (size_t)(n - 1) * (size_t)frame_stride + (size_t)(c->cfg.src_height - 1) * (size_t)pitch + (size_t)c->row_bytes;
+        int rc = validate_device_span(c, d_bgr, span, "push_frames");
+        if (rc) return rc;
+    }
     return push_common(c, d_bgr, n, frame_stride, pitch, LAYOUT_FULL, first_frame_num, (cudaStream_t)stream);
 }
 
 int esd_push_rows(esd_ctx* c, const uint8_t* d_rows, int64_t n, int64_t first_frame_num, void* stream) {
     if (!c) return ESD_ERR_INVALID;
+    if (n > 0 && d_rows) {
+        int rc = validate_device_span(c, d_rows, (size_t)n * c->touched.size() * c->row_bytes, "push_rows");
+        if (rc) return rc;
+    }
     return push_common(c, d_rows, n, (int64_t)c->touched.size() * c->row_bytes, c->row_bytes, LAYOUT_ROWS, first_frame_num,
                        (cudaStream_t)stream);
 }

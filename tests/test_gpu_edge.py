@@ -213,3 +213,28 @@ def test_ingest_of_cropped_host_views():
                 ctx.ingest_close()
             for k in want:
                 assert np.array_equal(got[k], want[k], equal_nan=True), (k, threads)
+
+
+def test_bad_frame_pointers_are_rejected_before_launch():
+    """Pageable host pointers and spans that overrun the device allocation are refused with an error instead of
+    faulting inside the kernel."""
+    w, h = 320, 180
+    with make_ctx(w, h, None) as ctx:
+        host = np.zeros((2, h, w, 3), np.uint8)
+        with pytest.raises(capi.EsdError) as e:
+            ctx.push_device(host.ctypes.data, 2, host.strides[0], host.strides[1], 0)
+        assert "pageable" in str(e.value)
+        own = torch.empty(3 * h * w * 3 + (1 << 22), dtype=torch.uint8, device=DEV)  # private cudaMalloc-sized block
+        torch.cuda.synchronize()
+        big = torch.empty(1 << 28, dtype=torch.uint8, device=DEV)  # its own 256 MiB segment
+        end = big.data_ptr() + big.numel()
+        with pytest.raises(capi.EsdError) as e:
+            ctx.push_device(end - 2 * h * w * 3, 3, h * w * 3, w * 3, 0)  # third frame lies past the allocation
+        assert "allocation ends" in str(e.value)
+        assert ctx.frames_pushed == 0
+        ctx.push_device(end - 3 * h * w * 3, 3, h * w * 3, w * 3, 0)      # exactly fits: accepted
+        assert ctx.frames_pushed == 3
+        pinned = torch.zeros((2, h, w, 3), dtype=torch.uint8).pin_memory()
+        ctx.push_device(pinned.data_ptr(), 2, pinned.stride(0), pinned.stride(1), 3)  # pinned host memory is reachable (zero-copy)
+        assert ctx.read_scores(3, 2)["sums3"][1].tolist() == [0, 0, 0]
+        del own
