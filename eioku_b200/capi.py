@@ -11,7 +11,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("ESD_LIB") or os.path.join(_HERE, "libesd.so")  # ESD_LIB: tuning experiments only
 
-ESD_DET_CONTENT, ESD_DET_ADAPTIVE, ESD_DET_HIST, ESD_DET_THRESHOLD = 1, 2, 4, 8
+ESD_DET_CONTENT, ESD_DET_ADAPTIVE, ESD_DET_HIST, ESD_DET_THRESHOLD, ESD_DET_HASH = 1, 2, 4, 8, 16
+ESD_ABI_VERSION = 2
 ESD_THRESH_FLOOR, ESD_THRESH_CEILING = 0, 1
 ESD_FILTER_MERGE, ESD_FILTER_SUPPRESS = 0, 1
 ESD_DOWNSCALE_FLOAT, ESD_DOWNSCALE_INT = 0, 1
@@ -23,6 +24,7 @@ EXPORTED_SYMBOLS = (
     "esd_create", "esd_destroy", "esd_reset", "esd_get_geometry", "esd_get_touched_rows",
     "esd_push_frames", "esd_push_rows", "esd_ingest_open", "esd_ingest_push_host", "esd_ingest_close", "esd_ingest_set_gather",
     "esd_ingest_stats", "esd_synchronize", "esd_join", "esd_frames_pushed", "esd_read_scores", "esd_read_edge_counts", "esd_read_average_rgb",
+    "esd_read_hash", "esd_debug_read_hash_input",
     "esd_post_process", "esd_get_cuts",
     "esd_decide_arrays", "esd_debug_read_prev", "esd_set_timing", "esd_kernel_time", "esd_kernel_launches", "esd_synth_fill",
 )
@@ -48,6 +50,8 @@ class EsdConfig(C.Structure):
         ("split_mode", C.c_int32), ("ctas_per_sm", C.c_int32),
         ("rows_per_stage", C.c_int32), ("reserved1", C.c_int32),
         ("max_cuts", C.c_int64), ("initial_capacity", C.c_int64),
+        ("hash_threshold", C.c_double), ("hash_size", C.c_int32), ("hash_lowpass", C.c_int32),
+        ("hash_min_scene_len", C.c_int32), ("reserved2", C.c_int32),
     ]
 
 
@@ -109,6 +113,8 @@ def load_library(path: Optional[str] = None):
     L.esd_get_cuts.argtypes = [vp, i32, i64, vp, i64, C.POINTER(i64), C.POINTER(i64)]
     L.esd_read_average_rgb.argtypes = [vp, i64, i64, vp]
     L.esd_read_edge_counts.argtypes = [vp, i64, i64, vp]
+    L.esd_read_hash.argtypes = [vp, i64, i64, vp, vp]
+    L.esd_debug_read_hash_input.argtypes = [vp, i64, vp, i64]
     L.esd_post_process.argtypes = [vp, i32, i64, vp, i64, C.POINTER(i64)]
     L.esd_decide_arrays.argtypes = [vp, i32, i64, i64, vp, vp, vp, i64, C.POINTER(i64)]
     L.esd_debug_read_prev.argtypes = [vp, vp, i64]
@@ -117,7 +123,7 @@ def load_library(path: Optional[str] = None):
     L.esd_kernel_launches.restype = i64
     L.esd_kernel_launches.argtypes = [vp]
     L.esd_synth_fill.argtypes = [vp, i32, i32, i64, i64, C.c_uint32, vp, i64, C.c_int, vp]
-    if L.esd_abi_version() != 1:
+    if L.esd_abi_version() != ESD_ABI_VERSION:
         raise ImportError("libesd.so ABI version mismatch")
     if path == LIB_PATH:
         _lib = L
@@ -268,7 +274,7 @@ class EsdContext:
 
     def read_scores(self, from_frame: int, n: int, want: Sequence[str] = ()):
         """-> dict with any of sums3, content_val, adaptive_val, adaptive_ratio, hist, hist_diff."""
-        has_content = bool(self.cfg.detectors & (ESD_DET_CONTENT | ESD_DET_ADAPTIVE | ESD_DET_THRESHOLD))
+        has_content = bool(self.cfg.detectors & (ESD_DET_CONTENT | ESD_DET_ADAPTIVE | ESD_DET_THRESHOLD | ESD_DET_HASH))
         has_hist = bool(self.cfg.detectors & ESD_DET_HIST)
         if not want:
             want = (["sums3", "content_val", "adaptive_val", "adaptive_ratio"] if has_content else []) + \
@@ -294,6 +300,23 @@ class EsdContext:
     def read_average_rgb(self, from_frame: int, n: int) -> np.ndarray:
         out = np.empty(n, np.float64)
         self._check(self._L.esd_read_average_rgb(self._h, from_frame, n, _np_ptr(out)), "esd_read_average_rgb")
+        return out
+
+    def read_hash(self, from_frame: int, n: int):
+        """-> (bits bool [n, size, size], hash_dist float64 [n]; NaN for the first frame of the video)."""
+        size = int(self.cfg.hash_size)
+        words = (size * size + 31) // 32
+        raw = np.empty((n, words), np.uint32)
+        dist = np.empty(n, np.float64)
+        self._check(self._L.esd_read_hash(self._h, from_frame, n, _np_ptr(raw), _np_ptr(dist)), "esd_read_hash")
+        bits = np.unpackbits(raw.view(np.uint8).reshape(n, words * 4), axis=1, bitorder="little")[:, :size * size]
+        return bits.reshape(n, size, size).astype(bool), dist
+
+    def debug_hash_input(self, frame: int) -> np.ndarray:
+        """uint8 [S, S] INTER_AREA thumbnail the hash of `frame` was computed from (most recent push only; test hook)."""
+        s = int(self.cfg.hash_size) * int(self.cfg.hash_lowpass)
+        out = np.empty((s, s), np.uint8)
+        self._check(self._L.esd_debug_read_hash_input(self._h, frame, _np_ptr(out), out.size), "esd_debug_read_hash_input")
         return out
 
     def post_process(self, detector: int, last_frame_num: int):

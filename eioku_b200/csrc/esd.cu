@@ -133,8 +133,13 @@ struct esd_ctx {
     int rows_per_group = 0, n_groups = 0, stages = 0, rowbuf = 0, stage_bytes = 0, rows_per_stage = 1;
     int ctas_per_sm = 0;
     size_t smem_bytes = 0;
-    bool need_content = false, need_hist = false, need_edges = false;
+    bool need_content = false, need_hist = false, need_edges = false, need_hash = false;
     int edge_ksize = 0, edge_words = 0;
+    HashParams hparams{};          // perceptual hash geometry + device tables
+    int hash_words = 0;
+    int* d_hash_itab = nullptr;    // area-resize tables: x begin, y begin, x src, y src (one allocation)
+    float* d_hash_wtab = nullptr;  // x weights, y weights
+    double* d_hash_C = nullptr;    // [hash_size][S] DCT rows
     std::vector<int32_t> touched;  // ascending source rows
     ScoreWeights wc{}, wa{};
     DecisionParams dparams{};
@@ -152,7 +157,7 @@ struct esd_ctx {
     int prev_parity = 0;
     uint32_t* d_prev[2] = {nullptr, nullptr};
     DecisionState* d_state = nullptr;
-    long long* d_cuts = nullptr;  // [3][max_cuts]
+    long long* d_cuts = nullptr;  // [5][max_cuts]
     int64_t max_cuts = 0;
 
     // growable per-frame score arrays
@@ -165,6 +170,8 @@ struct esd_ctx {
     double* d_avg = nullptr;       // ThresholdDetector average_rgb
     uint32_t* d_edge_counts = nullptr;  // differing edge pixels vs the previous frame
     uint32_t* d_counts = nullptr;  // [cap][bins]
+    uint32_t* d_hash = nullptr;    // [cap][hash_words] perceptual hash bits
+    double* d_hdist = nullptr;     // HashDetector hash_dist (normalised Hamming distance to the previous frame)
     uint8_t* d_slab = nullptr;     // backing allocation of the six arrays above
 
     // per-batch scratch
@@ -172,6 +179,9 @@ struct esd_ctx {
     uint4* d_part[2] = {nullptr, nullptr};          // double-buffered: the tail of push k overlaps push k+1
     uint16_t* d_hist_part[2] = {nullptr, nullptr};
     uint8_t* d_vplane[2] = {nullptr, nullptr};      // V planes of the batch (edge detector input)
+    uint8_t* d_gplane[2] = {nullptr, nullptr};      // BGR2GRAY planes of the batch (hash detector input)
+    uint8_t* d_hash_small = nullptr;                // [n][S * S] INTER_AREA thumbnails of the batch (test hook)
+    int64_t last_batch_base = 0, last_batch_n = 0;
     uint32_t* d_edge_bits = nullptr;                // [n][edge_words] dilated edge bitmaps of the batch
     uint32_t* d_edge_prev = nullptr;                // [edge_words] bitmap of the last frame of the previous batch
     int part_buf = 0;
@@ -377,7 +387,8 @@ int ensure_capacity(esd_ctx* c, int64_t frames_needed) {
     const int64_t ncap = std::max<int64_t>(c->cap ? c->cap * 2 : std::max<int64_t>(4096, c->cfg.initial_capacity), frames_needed);
     { int rc0 = sync_all(c); if (rc0) return rc0; }
     const int64_t bins = c->need_hist ? c->cfg.hist_bins : 0;
-    const size_t bytes = (size_t)ncap * (3 * sizeof(unsigned long long) + 5 * sizeof(double) + (bins + 1) * sizeof(uint32_t));
+    const int64_t hwords = c->need_hash ? c->hash_words : 0;
+    const size_t bytes = (size_t)ncap * (3 * sizeof(unsigned long long) + 6 * sizeof(double) + (bins + 1 + hwords) * sizeof(uint32_t));
     uint8_t* slab = nullptr;
     CU(c, cudaMalloc(&slab, bytes));
     uint8_t* q = slab;
@@ -394,8 +405,10 @@ int ensure_capacity(esd_ctx* c, int64_t frames_needed) {
     auto* n_ratio = carve(&c->d_ratio, 1);
     auto* n_hdiff = carve(&c->d_hdiff, 1);
     auto* n_avg = carve(&c->d_avg, 1);
+    auto* n_hdist = carve(&c->d_hdist, 1);
     auto* n_edge = carve(&c->d_edge_counts, 1);
     auto* n_counts = carve(&c->d_counts, bins);
+    auto* n_hash = carve(&c->d_hash, hwords);
     if (used > 0) {
         CU(c, cudaMemcpy(n_sums, c->d_sums3, sizeof(unsigned long long) * 3 * used, cudaMemcpyDeviceToDevice));
         CU(c, cudaMemcpy(n_cv, c->d_cv, sizeof(double) * used, cudaMemcpyDeviceToDevice));
@@ -405,11 +418,15 @@ int ensure_capacity(esd_ctx* c, int64_t frames_needed) {
         CU(c, cudaMemcpy(n_avg, c->d_avg, sizeof(double) * used, cudaMemcpyDeviceToDevice));
         CU(c, cudaMemcpy(n_edge, c->d_edge_counts, sizeof(uint32_t) * used, cudaMemcpyDeviceToDevice));
         if (bins) CU(c, cudaMemcpy(n_counts, c->d_counts, sizeof(uint32_t) * bins * used, cudaMemcpyDeviceToDevice));
+        CU(c, cudaMemcpy(n_hdist, c->d_hdist, sizeof(double) * used, cudaMemcpyDeviceToDevice));
+        if (hwords) CU(c, cudaMemcpy(n_hash, c->d_hash, sizeof(uint32_t) * hwords * used, cudaMemcpyDeviceToDevice));
     }
     cudaFree(c->d_slab);
     c->d_slab = slab;
     c->d_sums3 = n_sums; c->d_cv = n_cv; c->d_av = n_av; c->d_ratio = n_ratio; c->d_hdiff = n_hdiff; c->d_avg = n_avg; c->d_edge_counts = n_edge;
     c->d_counts = bins ? n_counts : nullptr;
+    c->d_hdist = n_hdist;
+    c->d_hash = hwords ? n_hash : nullptr;
     // ratios not yet computed read back as NaN
     fill_nan_kernel<<<(unsigned)((ncap - used + 255) / 256), 256>>>(c->d_ratio + used, ncap - used);
     CU(c, cudaGetLastError());
@@ -426,11 +443,14 @@ int ensure_scratch(esd_ctx* c, int64_t n) {
         cudaFree(c->d_part[b]);
         cudaFree(c->d_hist_part[b]);
         cudaFree(c->d_vplane[b]);
+        cudaFree(c->d_gplane[b]);
+        c->d_gplane[b] = nullptr;
         c->d_part[b] = nullptr;
         c->d_hist_part[b] = nullptr;
         c->d_vplane[b] = nullptr;
         c->fin_recorded[b] = false;
         if (c->need_edges) CU(c, cudaMalloc(&c->d_vplane[b], (size_t)n * c->dst_w * c->dst_h));
+        if (c->need_hash) CU(c, cudaMalloc(&c->d_gplane[b], (size_t)n * c->dst_w * c->dst_h));
         if (c->need_content) CU(c, cudaMalloc(&c->d_part[b], sizeof(uint4) * n * c->n_groups * kConsumerWarps));
         if (c->need_hist) CU(c, cudaMalloc(&c->d_hist_part[b], sizeof(uint16_t) * n * c->n_groups * c->cfg.hist_bins));
     }
@@ -438,6 +458,11 @@ int ensure_scratch(esd_ctx* c, int64_t n) {
         cudaFree(c->d_edge_bits);
         c->d_edge_bits = nullptr;
         CU(c, cudaMalloc(&c->d_edge_bits, sizeof(uint32_t) * n * c->edge_words));
+    }
+    if (c->need_hash) {
+        cudaFree(c->d_hash_small);
+        c->d_hash_small = nullptr;
+        CU(c, cudaMalloc(&c->d_hash_small, (size_t)n * c->hparams.S * c->hparams.S));
     }
     c->part_cap_frames = n;
     return ESD_OK;
@@ -574,6 +599,7 @@ int push_common(esd_ctx* c, const uint8_t* d_src, int64_t n, int64_t frame_strid
     p.part = c->d_part[buf];
     p.hist_part = c->d_hist_part[buf];
     p.vplane = c->need_edges ? c->d_vplane[buf] : nullptr;
+    p.gplane = c->need_hash ? c->d_gplane[buf] : nullptr;
     // the fused kernel overwrites part[buf]: wait until the tail of the push that last used it is done
     if (c->fin_recorded[buf]) CU(c, cudaStreamWaitEvent(st, c->ev_fin[buf], 0));
 
@@ -638,8 +664,21 @@ int push_common(esd_ctx* c, const uint8_t* d_src, int64_t n, int64_t frame_strid
         CU(c, cudaGetLastError());
         c->launches += 2;
     }
-    decide_kernel<<<4, 256, 0, ts>>>(c->dparams, c->d_state, c->d_cuts, c->d_cv, c->d_av, c->d_ratio, c->d_hdiff, c->d_avg,
-                                     c->first_frame, base, base + n);
+    if (c->need_hash) {
+        const HashParams& hp = c->hparams;
+        const size_t hsmem = sizeof(float) * hp.S * hp.S + sizeof(double) * hp.hs * hp.S + sizeof(float) * hp.hs * hp.hs;
+        hash_kernel<<<(unsigned)n, kHashThreads, hsmem, ts>>>(c->d_gplane[buf], hp, c->d_hash_small,
+                                                             c->d_hash + base * c->hash_words);
+        CU(c, cudaGetLastError());
+        hash_dist_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ts>>>(c->d_hash + base * c->hash_words, c->hash_words, (int)n,
+                                                                     base > 0 ? 1 : 0, (double)(hp.hs * hp.hs), c->d_hdist + base);
+        CU(c, cudaGetLastError());
+        c->launches += 2;
+        c->last_batch_base = base;
+        c->last_batch_n = n;
+    }
+    decide_kernel<<<5, 256, 0, ts>>>(c->dparams, c->d_state, c->d_cuts, c->d_cv, c->d_av, c->d_ratio, c->d_hdiff, c->d_avg,
+                                     c->d_hdist, c->first_frame, base, base + n);
     CU(c, cudaGetLastError());
     CU(c, cudaEventRecord(c->ev_fin[buf], ts));
     c->fin_recorded[buf] = true;
@@ -716,6 +755,10 @@ void esd_config_default(esd_config* cfg) {
     cfg->thresh_threshold = 12.0;
     cfg->thresh_min_scene_len = 15;
     cfg->thresh_method = ESD_THRESH_FLOOR;
+    cfg->hash_threshold = 0.395;
+    cfg->hash_size = 16;
+    cfg->hash_lowpass = 2;
+    cfg->hash_min_scene_len = 15;
 }
 
 int esd_create(esd_ctx** out, const esd_config* cfg, int device) {
@@ -724,7 +767,14 @@ int esd_create(esd_ctx** out, const esd_config* cfg, int device) {
     if (cfg->struct_size != sizeof(esd_config))
         return fail(nullptr, ESD_ERR_INVALID, "esd_create: struct_size %u != %zu (ABI mismatch)", cfg->struct_size,
                     sizeof(esd_config));
-    if (!(cfg->detectors & 15) || (cfg->detectors & ~15)) return fail(nullptr, ESD_ERR_INVALID, "esd_create: bad detector mask");
+    if (!(cfg->detectors & 31) || (cfg->detectors & ~31)) return fail(nullptr, ESD_ERR_INVALID, "esd_create: bad detector mask");
+    if (cfg->detectors & ESD_DET_HASH) {
+        const int64_t S = (int64_t)cfg->hash_size * cfg->hash_lowpass;
+        if (cfg->hash_size < 1 || cfg->hash_lowpass < 1) return fail(nullptr, ESD_ERR_INVALID, "hash size and lowpass must be >= 1");
+        if (S % 2) return fail(nullptr, ESD_ERR_UNSUPPORTED, "Odd-size DCT's are not implemented (size * lowpass = %lld)", (long long)S);
+        if (S > 64 || cfg->hash_size * cfg->hash_size > 1024)
+            return fail(nullptr, ESD_ERR_UNSUPPORTED, "hash: size * lowpass must be <= 64 and size * size <= 1024");
+    }
     if (cfg->src_width < 1 || cfg->src_height < 1) return fail(nullptr, ESD_ERR_INVALID, "esd_create: bad frame size");
     if ((cfg->detectors & ESD_DET_HIST) && (cfg->hist_bins < 1 || cfg->hist_bins > 256))
         return fail(nullptr, ESD_ERR_UNSUPPORTED, "hist_bins must be in 1..256");
@@ -780,7 +830,9 @@ int esd_create(esd_ctx** out, const esd_config* cfg, int device) {
     c->dst_w = dw; c->dst_h = dh;
     c->resize = !(dw == W && dh == H);
     c->row_bytes = W * 3;
-    c->need_content = (cfg->detectors & (ESD_DET_CONTENT | ESD_DET_ADAPTIVE | ESD_DET_THRESHOLD)) != 0;
+    c->need_hash = (cfg->detectors & ESD_DET_HASH) != 0;
+    // the hash detector's gray plane rides on the content pass (a hash-only context also produces the HSV sums)
+    c->need_content = (cfg->detectors & (ESD_DET_CONTENT | ESD_DET_ADAPTIVE | ESD_DET_THRESHOLD | ESD_DET_HASH)) != 0;
     c->need_hist = (cfg->detectors & ESD_DET_HIST) != 0;
     c->need_edges = ((cfg->detectors & ESD_DET_CONTENT) && cfg->content_weights[3] > 0.0) ||
                     ((cfg->detectors & ESD_DET_ADAPTIVE) && cfg->adaptive_weights[3] > 0.0);
@@ -809,6 +861,69 @@ int esd_create(esd_ctx** out, const esd_config* cfg, int device) {
         }
         CUB(cudaFuncSetAttribute(edges_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esmem));
         CUB(cudaMalloc(&c->d_edge_prev, sizeof(uint32_t) * c->edge_words));
+    }
+    if (c->need_hash) {
+        HashParams& hp = c->hparams;
+        hp.w = dw; hp.h = dh;
+        hp.hs = cfg->hash_size;
+        hp.S = cfg->hash_size * cfg->hash_lowpass;
+        if (hp.S > dw || hp.S > dh) {
+            fail(c, ESD_ERR_UNSUPPORTED, "hash: the %dx%d DCT thumbnail is larger than the detector-resolution frame (%dx%d)", hp.S, hp.S, dw, dh);
+            return bail(ESD_ERR_UNSUPPORTED);
+        }
+        c->hash_words = (hp.hs * hp.hs + 31) / 32;
+        hp.words = c->hash_words;
+        const double sx = (double)dw / hp.S, sy = (double)dh / hp.S;
+        hp.isx = (int)sx; hp.isy = (int)sy;
+        hp.fast = (fabs(sx - hp.isx) < 2.220446049250313e-16 && fabs(sy - hp.isy) < 2.220446049250313e-16) ? 1 : 0;
+        hp.fast_scale = (float)(1.0 / (hp.isx * hp.isy));
+        // OpenCV resize.cpp computeResizeAreaTab, one axis (cn = 1)
+        auto area_tab = [](int ssize, int dsize, std::vector<int>& begin, std::vector<int>& src, std::vector<float>& wt) {
+            const double scale = (double)ssize / dsize;
+            begin.assign(1, 0);
+            for (int d = 0; d < dsize; ++d) {
+                volatile double fsx1 = d * scale;
+                volatile double fsx2 = fsx1 + scale;
+                const double cell = std::min(scale, ssize - fsx1);
+                int sx1 = (int)ceil(fsx1), sx2 = (int)floor(fsx2);
+                sx2 = std::min(sx2, ssize - 1);
+                sx1 = std::min(sx1, sx2);
+                if (sx1 - fsx1 > 1e-3) { src.push_back(sx1 - 1); wt.push_back((float)((sx1 - fsx1) / cell)); }
+                for (int x = sx1; x < sx2; ++x) { src.push_back(x); wt.push_back((float)(1.0 / cell)); }
+                if (fsx2 - sx2 > 1e-3) { src.push_back(sx2); wt.push_back((float)(std::min(std::min(fsx2 - sx2, 1.), cell) / cell)); }
+                begin.push_back((int)src.size());
+            }
+        };
+        std::vector<int> xb, xs, yb, ys;
+        std::vector<float> xw, yw;
+        area_tab(dw, hp.S, xb, xs, xw);
+        area_tab(dh, hp.S, yb, ys, yw);
+        std::vector<int> itab;
+        itab.insert(itab.end(), xb.begin(), xb.end());
+        itab.insert(itab.end(), yb.begin(), yb.end());
+        itab.insert(itab.end(), xs.begin(), xs.end());
+        itab.insert(itab.end(), ys.begin(), ys.end());
+        std::vector<float> wtab(xw);
+        wtab.insert(wtab.end(), yw.begin(), yw.end());
+        CUB(cudaMalloc(&c->d_hash_itab, sizeof(int) * itab.size()));
+        CUB(cudaMemcpy(c->d_hash_itab, itab.data(), sizeof(int) * itab.size(), cudaMemcpyHostToDevice));
+        CUB(cudaMalloc(&c->d_hash_wtab, sizeof(float) * wtab.size()));
+        CUB(cudaMemcpy(c->d_hash_wtab, wtab.data(), sizeof(float) * wtab.size(), cudaMemcpyHostToDevice));
+        hp.ax.begin = c->d_hash_itab;
+        hp.ay.begin = hp.ax.begin + xb.size();
+        hp.ax.src = hp.ay.begin + yb.size();
+        hp.ay.src = hp.ax.src + xs.size();
+        hp.ax.w = c->d_hash_wtab;
+        hp.ay.w = hp.ax.w + xw.size();
+        // orthonormal DCT-II rows 0..hs-1 of size S
+        std::vector<double> Cm((size_t)hp.hs * hp.S);
+        const double pi = 3.14159265358979323846;
+        for (int u = 0; u < hp.hs; ++u)
+            for (int i = 0; i < hp.S; ++i)
+                Cm[(size_t)u * hp.S + i] = u == 0 ? sqrt(1.0 / hp.S) : sqrt(2.0 / hp.S) * cos(pi * (2 * i + 1) * u / (2.0 * hp.S));
+        CUB(cudaMalloc(&c->d_hash_C, sizeof(double) * Cm.size()));
+        CUB(cudaMemcpy(c->d_hash_C, Cm.data(), sizeof(double) * Cm.size(), cudaMemcpyHostToDevice));
+        hp.C = c->d_hash_C;
     }
     if (dw > kConsumers * (c->resize ? 4 : 16)) {
         fail(c, ESD_ERR_UNSUPPORTED, "destination width %d too large (max %d)", dw, kConsumers * (c->resize ? 4 : 16));
@@ -946,9 +1061,11 @@ int esd_create(esd_ctx** out, const esd_config* cfg, int device) {
     P.thresh_fade_bias = cfg->thresh_fade_bias;
     P.thresh_min_scene_len = cfg->thresh_min_scene_len;
     P.thresh_method = cfg->thresh_method;
+    P.hash_threshold = cfg->hash_threshold;
+    P.hash_min_scene_len = cfg->hash_min_scene_len;
 
     CUB(cudaMalloc(&c->d_state, sizeof(DecisionState)));
-    CUB(cudaMalloc(&c->d_cuts, sizeof(long long) * 4 * c->max_cuts));
+    CUB(cudaMalloc(&c->d_cuts, sizeof(long long) * 5 * c->max_cuts));
     if (c->need_content) {
         CUB(cudaMalloc(&c->d_prev[0], sizeof(uint32_t) * dw * dh));
         CUB(cudaMalloc(&c->d_prev[1], sizeof(uint32_t) * dw * dh));
@@ -981,6 +1098,8 @@ void esd_destroy(esd_ctx* c) {
     cudaFree(c->d_slab);
     for (int b = 0; b < 2; ++b) { cudaFree(c->d_part[b]); cudaFree(c->d_hist_part[b]); cudaFree(c->d_vplane[b]); if (c->ev_fin[b]) cudaEventDestroy(c->ev_fin[b]); }
     cudaFree(c->d_edge_bits); cudaFree(c->d_edge_prev);
+    cudaFree(c->d_gplane[0]); cudaFree(c->d_gplane[1]); cudaFree(c->d_hash_small);
+    cudaFree(c->d_hash_itab); cudaFree(c->d_hash_wtab); cudaFree(c->d_hash_C);
     if (c->order_event) cudaEventDestroy(c->order_event);
     if (c->ev_fused) cudaEventDestroy(c->ev_fused);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
@@ -1261,7 +1380,7 @@ int esd_read_scores(esd_ctx* c, int64_t from_frame, int64_t n, uint64_t* sums3, 
 
 static int det_index(int32_t detector) {
     return detector == ESD_DET_CONTENT ? 0 : detector == ESD_DET_ADAPTIVE ? 1 : detector == ESD_DET_HIST ? 2
-         : detector == ESD_DET_THRESHOLD ? 3 : -1;
+         : detector == ESD_DET_THRESHOLD ? 3 : detector == ESD_DET_HASH ? 4 : -1;
 }
 
 int esd_read_edge_counts(esd_ctx* c, int64_t from_frame, int64_t n, uint32_t* counts) {
@@ -1274,6 +1393,34 @@ int esd_read_edge_counts(esd_ctx* c, int64_t from_frame, int64_t n, uint32_t* co
     int rc = esd_synchronize(c);
     if (rc) return rc;
     CU(c, cudaMemcpy(counts, c->d_edge_counts + i0, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost));
+    return ESD_OK;
+}
+
+int esd_read_hash(esd_ctx* c, int64_t from_frame, int64_t n, uint32_t* bits, double* hash_dist) {
+    if (!c) return ESD_ERR_INVALID;
+    if (n == 0) return ESD_OK;
+    const int64_t i0 = from_frame - c->first_frame;
+    if (!c->started || n < 0 || i0 < 0 || i0 + n > c->n_frames)
+        return fail(c, ESD_ERR_INVALID, "read_hash: range outside pushed frames");
+    if (!c->need_hash) return fail(c, ESD_ERR_STATE, "read_hash: no hash detector configured");
+    int rc = esd_synchronize(c);
+    if (rc) return rc;
+    if (bits) CU(c, cudaMemcpy(bits, c->d_hash + i0 * c->hash_words, sizeof(uint32_t) * n * c->hash_words, cudaMemcpyDeviceToHost));
+    if (hash_dist) CU(c, cudaMemcpy(hash_dist, c->d_hdist + i0, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    return ESD_OK;
+}
+
+int esd_debug_read_hash_input(esd_ctx* c, int64_t frame, uint8_t* out, int64_t cap) {
+    if (!c || !out) return ESD_ERR_INVALID;
+    if (!c->need_hash) return fail(c, ESD_ERR_STATE, "debug_read_hash_input: no hash detector configured");
+    const int64_t i = frame - c->first_frame - c->last_batch_base;
+    if (!c->started || i < 0 || i >= c->last_batch_n)
+        return fail(c, ESD_ERR_INVALID, "debug_read_hash_input: frame %lld is not part of the most recent push", (long long)frame);
+    const int64_t sz = (int64_t)c->hparams.S * c->hparams.S;
+    if (cap < sz) return ESD_ERR_CAPACITY;
+    int rc = esd_synchronize(c);
+    if (rc) return rc;
+    CU(c, cudaMemcpy(out, c->d_hash_small + i * sz, (size_t)sz, cudaMemcpyDeviceToHost));
     return ESD_OK;
 }
 
@@ -1356,7 +1503,7 @@ int esd_decide_arrays(esd_ctx* c, int32_t detector, int64_t first_frame_num, int
     CUD(cudaMalloc(&d_scores, sizeof(double) * n));
     CUD(cudaMalloc(&d_ratio, sizeof(double) * n));
     CUD(cudaMalloc(&d_st, sizeof(DecisionState)));
-    CUD(cudaMalloc(&d_cuts, sizeof(long long) * 4 * c->max_cuts));
+    CUD(cudaMalloc(&d_cuts, sizeof(long long) * 5 * c->max_cuts));
     CUD(cudaMemcpy(d_scores, scores, sizeof(double) * n, cudaMemcpyHostToDevice));
     CUD(cudaMemset(d_st, 0, sizeof(DecisionState)));
     fill_nan_kernel<<<(unsigned)((n + 255) / 256), 256>>>(d_ratio, n);
@@ -1368,7 +1515,7 @@ int esd_decide_arrays(esd_ctx* c, int32_t detector, int64_t first_frame_num, int
             adaptive_ratio_kernel<<<(unsigned)((n - 2 * w + 255) / 256), 256>>>(d_scores, d_ratio, w, n - w, w,
                                                                                P.adaptive_min_content_val);
     }
-    decide_kernel<<<4, 256>>>(P, d_st, d_cuts, d_scores, d_scores, d_ratio, d_scores, d_scores, first_frame_num, 0, n);
+    decide_kernel<<<5, 256>>>(P, d_st, d_cuts, d_scores, d_scores, d_ratio, d_scores, d_scores, d_scores, first_frame_num, 0, n);
     c->launches += 3;
     CUD(cudaGetLastError());
     CUD(cudaDeviceSynchronize());

@@ -62,6 +62,7 @@ struct FusedParams {
     uint4* part;                // [n_frames][n_groups][kConsumerWarps] {sumH, sumS, sumV, 0}
     uint16_t* hist_part;        // [n_frames][n_groups][bins]
     uint8_t* vplane;            // [n_frames][dst_h][dst_w] V plane for the edge detector, or nullptr
+    uint8_t* gplane;            // [n_frames][dst_h][dst_w] BGR2GRAY plane for the hash detector, or nullptr
 };
 
 // ----------------------------------------------------------------------------------- PTX helpers
@@ -139,6 +140,11 @@ __device__ __forceinline__ uint32_t bgr_to_hsv_packed(int b, int g, int r, const
     return (uint32_t)h | ((uint32_t)s << 8) | ((uint32_t)v << 16);
 }
 
+// cv2.cvtColor(BGR2GRAY) for uint8: 15-bit coefficients (OpenCV RGB2Gray<uchar>), not the 14-bit Y of BGR2YUV
+__device__ __forceinline__ uint8_t bgr_to_gray(int b, int g, int r) {
+    return (uint8_t)((9798 * r + 19235 * g + 3735 * b + 16384) >> 15);
+}
+
 // OpenCV VResizeLinear<uchar,int,short,FixedPtCast<int,uchar,22>>: b0s/b1s are the coefficients << 16
 __device__ __forceinline__ int vresize(uint32_t h0, uint32_t h1, uint32_t b0s, uint32_t b1s) {
     // no saturation needed: a0+a1 and b0+b1 are 2048 (+-1), so the sum of the two terms is <= 1021 and
@@ -210,6 +216,8 @@ __device__ __forceinline__ void score_row(const FusedParams& p, const uint8_t* _
                 const int y = (4899 * r + 9617 * g + 1868 * b + 8192) >> 14;
                 atomicAdd(&s_hist_cur[(y * p.bins) >> 8], 1u);
             }
+            if (p.gplane && !(SPECIAL && (flags & F_HALO)))
+                p.gplane[((size_t)frame * p.dst_h + row) * p.dst_w + d] = bgr_to_gray(b, g, r);
         }
     }
 }
@@ -241,6 +249,8 @@ __device__ __forceinline__ void score_row_quads(const FusedParams& p, const uint
                     const int y = (4899 * r + 9617 * g + 1868 * b + 8192) >> 14;
                     atomicAdd(&s_hist_cur[(y * p.bins) >> 8], 1u);
                 }
+                if (p.gplane && e < nvalid && !(SPECIAL && (flags & F_HALO)))
+                    p.gplane[((size_t)frame * p.dst_h + row) * p.dst_w + 4 * q + e] = bgr_to_gray(b, g, r);
             }
             if (CONTENT) {
                 uint4* slot = reinterpret_cast<uint4*>(s_prev) + (rloc * QPT + j) * kConsumers + tid;
@@ -852,6 +862,133 @@ __global__ void edge_delta_kernel(const uint32_t* __restrict__ bitmaps, const ui
     }
 }
 
+// ----------------------------------------------------------------------------------- perceptual hash
+// HashDetector.hash_frame on the device, one CTA per frame, reading the BGR2GRAY plane the fused kernel wrote:
+//   cv2.resize(gray, (S, S), INTER_AREA)  -- OpenCV resize.cpp restated exactly: ResizeAreaFast_ (integral scales:
+//       integer box sum, saturate_cast(sum * float(1/area)); 2x2 is (sum + 2) >> 2) or ResizeArea_ (float32 row
+//       buffer `buf += S * alpha` in table order, rows combined as `sum = beta * buf` / `sum += beta * buf`, no FMA)
+//   x = float32(v) / max(v)   (max == 0 -> 1)
+//   DCT-II of x, low-frequency hs x hs block, evaluated in float64 and narrowed to float32.  cv2.dct's own float32
+//       rounding is build-dependent (its IPP and plain paths differ by 1-2 ulp), so this stage is tolerance-parity.
+//   bits = coefficient > numpy.median(block)   (float32; even count: (a + b) / 2 in float32)
+struct AreaAxis {      // computeResizeAreaTab for one axis, grouped per destination index
+    const int* begin;  // [S + 1]
+    const int* src;    // source index per entry
+    const float* w;    // float32 weight per entry
+};
+struct HashParams {
+    int w, h;        // detector-resolution frame
+    int S, hs;       // DCT size (hash_size * lowpass) and hash size
+    int fast;        // both scales integral
+    int isx, isy;    // integral scales (fast path)
+    float fast_scale;  // float32(1 / (isx * isy))
+    AreaAxis ax, ay;
+    const double* C;   // [hs][S] orthonormal DCT-II rows
+    int words;         // ceil(hs * hs / 32)
+};
+constexpr int kHashThreads = 256;
+
+__global__ void __launch_bounds__(kHashThreads) hash_kernel(const uint8_t* __restrict__ gplane, HashParams P,
+                                                            uint8_t* __restrict__ small_out, uint32_t* __restrict__ bits_out) {
+    extern __shared__ __align__(16) uint8_t hsm[];
+    const int S = P.S, hs = P.hs, N = hs * hs;
+    float* x = reinterpret_cast<float*>(hsm);                         // [S * S]
+    double* T = reinterpret_cast<double*>(hsm + sizeof(float) * S * S);  // [hs * S]   (S * S is even -> 8-byte aligned)
+    float* coef = reinterpret_cast<float*>(T + hs * S);               // [N]
+    __shared__ int s_max;
+    __shared__ float s_lo, s_hi;
+    const int tid = threadIdx.x;
+    const uint8_t* g = gplane + (size_t)blockIdx.x * P.w * P.h;
+    if (tid == 0) s_max = 0;
+    __syncthreads();
+    int vmax = 0;
+    for (int p = tid; p < S * S; p += kHashThreads) {
+        const int dy = p / S, dx = p - dy * S;
+        int v;
+        if (P.fast) {
+            int sum = 0;
+            for (int yy = 0; yy < P.isy; ++yy) {
+                const uint8_t* row = g + (size_t)(dy * P.isy + yy) * P.w + dx * P.isx;
+                for (int xx = 0; xx < P.isx; ++xx) sum += row[xx];
+            }
+            if (P.isx == 2 && P.isy == 2) v = (sum + 2) >> 2;
+            else v = min(255, max(0, __float2int_rn(__fmul_rn((float)sum, P.fast_scale))));
+        } else {
+            float sum = 0.f;
+            const int xb = P.ax.begin[dx], xe = P.ax.begin[dx + 1];
+            for (int ky = P.ay.begin[dy]; ky < P.ay.begin[dy + 1]; ++ky) {
+                const uint8_t* row = g + (size_t)P.ay.src[ky] * P.w;
+                float buf = 0.f;
+                for (int kx = xb; kx < xe; ++kx) buf = __fadd_rn(buf, __fmul_rn((float)row[P.ax.src[kx]], P.ax.w[kx]));
+                const float t = __fmul_rn(P.ay.w[ky], buf);
+                sum = (ky == P.ay.begin[dy]) ? t : __fadd_rn(sum, t);
+            }
+            v = min(255, max(0, __float2int_rn(sum)));
+        }
+        x[p] = (float)v;
+        vmax = max(vmax, v);
+        if (small_out) small_out[(size_t)blockIdx.x * S * S + p] = (uint8_t)v;
+    }
+    vmax = __reduce_max_sync(0xffffffffu, vmax);
+    if ((tid & 31) == 0) atomicMax(&s_max, vmax);
+    __syncthreads();
+    const float fmax_v = (float)(s_max == 0 ? 1 : s_max);
+    for (int p = tid; p < S * S; p += kHashThreads) x[p] = __fdiv_rn(x[p], fmax_v);
+    __syncthreads();
+    // T = C[:hs] . x   then   D = T . C[:hs]^T
+    for (int idx = tid; idx < hs * S; idx += kHashThreads) {
+        const int u = idx / S, j = idx - u * S;
+        double acc = 0.0;
+        for (int i = 0; i < S; ++i) acc = fma(P.C[u * S + i], (double)x[i * S + j], acc);
+        T[idx] = acc;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < N; idx += kHashThreads) {
+        const int u = idx / hs, v = idx - u * hs;
+        double acc = 0.0;
+        for (int j = 0; j < S; ++j) acc = fma(T[u * S + j], P.C[v * S + j], acc);
+        coef[idx] = (float)acc;
+    }
+    __syncthreads();
+    // numpy.median: rank every coefficient (ties broken by index), pick the middle one(s)
+    const int k_lo = (N - 1) / 2, k_hi = N / 2;
+    for (int idx = tid; idx < N; idx += kHashThreads) {
+        const float c = coef[idx];
+        int rank = 0;
+        for (int k = 0; k < N; ++k) {
+            const float o = coef[k];
+            rank += (o < c || (o == c && k < idx)) ? 1 : 0;
+        }
+        if (rank == k_lo) s_lo = c;
+        if (rank == k_hi) s_hi = c;
+    }
+    __syncthreads();
+    const float med = (k_lo == k_hi) ? s_lo : __fmul_rn(__fadd_rn(s_lo, s_hi), 0.5f);
+    for (int base = 0; base < P.words * 32; base += kHashThreads) {
+        const int idx = base + tid;
+        const bool bit = idx < N && coef[idx] > med;
+        const uint32_t word = __ballot_sync(0xffffffffu, bit);
+        if ((tid & 31) == 0 && (idx >> 5) < P.words) bits_out[(size_t)blockIdx.x * P.words + (idx >> 5)] = word;
+    }
+}
+
+// hash_dist_norm = count_nonzero(cur != prev) / float(size * size); hashes points at the batch's first frame inside
+// the ctx-wide array, so hashes[-words..-1] is the last frame of the previous batch.  NaN = no previous frame.
+__global__ void hash_dist_kernel(const uint32_t* __restrict__ hashes, int words, int n, int first_has_prev, double size_sq,
+                                 double* __restrict__ hash_dist) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n) return;
+    if (f == 0 && !first_has_prev) {
+        hash_dist[0] = __longlong_as_double(0x7ff8000000000000LL);
+        return;
+    }
+    const uint32_t* cur = hashes + (long long)f * words;
+    const uint32_t* prv = cur - words;
+    int cnt = 0;
+    for (int i = 0; i < words; ++i) cnt += __popc(cur[i] ^ prv[i]);
+    hash_dist[f] = __ddiv_rn((double)cnt, size_sq);
+}
+
 // ----------------------------------------------------------------------------------- decision passes
 struct DecisionState {
     long long c_last_above, c_merge_start;
@@ -859,11 +996,14 @@ struct DecisionState {
     long long a_last_cut;
     int a_init, pad1;
     long long h_last_cut;  // 0 == "not set" (Python falsiness of `if not self._last_scene_cut`)
-    long long n_cuts[4];
+    long long n_cuts[5];
     int overflow, pad2;
     // ThresholdDetector: last_scene_cut, last_fade {frame, type}, processed_frame
     long long t_last_scene_cut, t_fade_frame;
     int t_init, t_processed, t_fade_out, pad3;
+    // HashDetector: _last_scene_cut
+    long long x_last_cut;
+    int x_init, pad4;
 };
 
 struct DecisionParams {
@@ -878,6 +1018,8 @@ struct DecisionParams {
     double thresh_threshold;  // int(threshold) as double
     double thresh_fade_bias;
     int thresh_min_scene_len, thresh_method;  // method 0 FLOOR, 1 CEILING
+    double hash_threshold;
+    int hash_min_scene_len, pad;
 };
 
 struct CutSink {
@@ -891,15 +1033,15 @@ struct CutSink {
     }
 };
 
-// grid = 4 blocks (content, adaptive, hist, threshold); frames [i_begin, i_end) are indices from first_frame_num.
+// grid = 5 blocks (content, adaptive, hist, threshold, hash); frames [i_begin, i_end) are indices from first_frame_num.
 // The threshold tests run in parallel into a shared bitmask; one thread then walks the sequential
 // FlashFilter / min_scene_len state machine (A.5-A.7) with its state in registers, visiting only
 // frames that can change it (set bits, or every frame while a MERGE burst is open).
 __global__ void decide_kernel(DecisionParams P, DecisionState* __restrict__ st, long long* __restrict__ cuts,
                               const double* __restrict__ content_val, const double* __restrict__ adaptive_val,
                               const double* __restrict__ adaptive_ratio, const double* __restrict__ hist_diff,
-                              const double* __restrict__ average_rgb, long long first_frame_num, long long i_begin,
-                              long long i_end) {
+                              const double* __restrict__ average_rgb, const double* __restrict__ hash_dist,
+                              long long first_frame_num, long long i_begin, long long i_end) {
     constexpr int CH = 8192;
     __shared__ uint32_t bits[CH / 32];
     const int det = blockIdx.x;
@@ -921,13 +1063,16 @@ __global__ void decide_kernel(DecisionParams P, DecisionState* __restrict__ st, 
             if (!init) { init = 1; last = first_frame_num + i_begin; }
         } else if (det == 2) {
             last = st->h_last_cut;
-        } else {
+        } else if (det == 3) {
             last = st->t_last_scene_cut; init = st->t_init;
+            if (!init) { init = 1; last = first_frame_num + i_begin; }
+        } else {
+            last = st->x_last_cut; init = st->x_init;
             if (!init) { init = 1; last = first_frame_num + i_begin; }
         }
     }
     const int L = det == 0 ? P.content_min_scene_len : det == 1 ? P.adaptive_min_scene_len
-                : det == 2 ? P.hist_min_scene_len : P.thresh_min_scene_len;
+                : det == 2 ? P.hist_min_scene_len : det == 3 ? P.thresh_min_scene_len : P.hash_min_scene_len;
     // ThresholdDetector state (thread 0): merge_start doubles as last_fade.frame
     int t_processed = 0, t_fade_out = 0;
     if (tid == 0 && det == 3) { t_processed = st->t_processed; t_fade_out = st->t_fade_out; merge_start = st->t_fade_frame; }
@@ -944,6 +1089,7 @@ __global__ void decide_kernel(DecisionParams P, DecisionState* __restrict__ st, 
                     if (i >= 2LL * P.adaptive_w)
                         bit = adaptive_ratio[t] >= P.adaptive_threshold && adaptive_val[t] >= P.adaptive_min_content_val;
                 } else if (det == 2) bit = hist_diff[i] <= P.hist_threshold;  // NaN (no previous frame) compares false
+                else if (det == 4) bit = hash_dist[i] >= P.hash_threshold;    // NaN (no previous frame) compares false
                 else bit = average_rgb[i] < P.thresh_threshold;                // "below the fade threshold"
             }
             const uint32_t word = __ballot_sync(0xffffffffu, bit);
@@ -1048,8 +1194,10 @@ __global__ void decide_kernel(DecisionParams P, DecisionState* __restrict__ st, 
                     if (merge_enabled) { merge_triggered = 1; merge_start = fn; }
                 } else if (det == 1) {
                     if (above && (fn - last) >= L) { last = fn - P.adaptive_w; sink.emit(last); }
-                } else {
+                } else if (det == 2) {
                     if (last == 0) last = fn;  // `if not self._last_scene_cut` (0 is falsy)
+                    if (above && (fn - last) >= L) { sink.emit(fn); last = fn; }
+                } else {  // HashDetector: `_last_scene_cut is None` -> first frame; plain min_scene_len rule
                     if (above && (fn - last) >= L) { sink.emit(fn); last = fn; }
                 }
             }
@@ -1066,9 +1214,11 @@ __global__ void decide_kernel(DecisionParams P, DecisionState* __restrict__ st, 
             st->a_last_cut = last; st->a_init = init;
         } else if (det == 2) {
             st->h_last_cut = last;
-        } else {
+        } else if (det == 3) {
             st->t_last_scene_cut = last; st->t_init = init; st->t_processed = t_processed;
             st->t_fade_out = t_fade_out; st->t_fade_frame = merge_start;
+        } else {
+            st->x_last_cut = last; st->x_init = init;
         }
     }
 }

@@ -341,6 +341,42 @@ class HistogramDetector(SceneDetector):
         return {self._metric_keys[0]: float(d)} if d == d else {}
 
 
+class HashDetector(SceneDetector):
+    """scenedetect.detectors.HashDetector: perceptual (DCT) hash of each frame; cut when the Hamming distance to the
+    previous frame's hash, divided by size^2, reaches ``threshold`` and ``min_scene_len`` frames have passed
+    (SURVEY.md section 8f, row N4).  gray -> INTER_AREA thumbnail -> DCT -> bits run on the device (hash_kernel)."""
+
+    _DET_FLAG = capi.ESD_DET_HASH
+
+    def __init__(self, threshold: float = 0.395, size: int = 16, lowpass: int = 2, min_scene_len: int = 15):
+        super().__init__()
+        self._threshold = threshold
+        self._min_scene_len = min_scene_len
+        self._size = size
+        self._size_sq = float(size * size)
+        self._factor = lowpass
+        self._metric_keys = [f"hash_dist [size={self._size} lowpass={self._factor}]"]
+
+    def get_metrics(self) -> List[str]:
+        return self._metric_keys
+
+    def is_processing_required(self, frame_num: int) -> bool:
+        return True
+
+    def _fill_config(self, cfg):
+        cfg.detectors |= capi.ESD_DET_HASH
+        cfg.hash_threshold = float(self._threshold)
+        cfg.hash_size = int(self._size)
+        cfg.hash_lowpass = int(self._factor)
+        cfg.hash_min_scene_len = int(self._min_scene_len)
+
+    def _publish_late_metrics(self, first_frame_num: int, n: int):
+        _bits, dist = self._ctx.read_hash(first_frame_num, n)
+        for k in range(n):
+            if dist[k] == dist[k]:
+                self.stats_manager.set_metrics(first_frame_num + k, {self._metric_keys[0]: float(dist[k])})
+
+
 class ThresholdDetector(SceneDetector):
     """scenedetect.detectors.ThresholdDetector: fade out / fade in detection on the average B,G,R value of the
     frame.  Cuts are placed between a fade-out and the next fade-in."""

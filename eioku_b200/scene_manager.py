@@ -12,7 +12,7 @@ from typing import Iterable, List, Optional, Sequence, Tuple
 import numpy as np
 
 from . import capi
-from .detectors import (AdaptiveDetector, ContentDetector, HistogramDetector, SceneDetector, StatsManager,
+from .detectors import (AdaptiveDetector, ContentDetector, HashDetector, HistogramDetector, SceneDetector, StatsManager,
                         ThresholdDetector)
 
 DEFAULT_MIN_WIDTH: int = 256
@@ -131,7 +131,7 @@ class SceneManager:
     def add_detector(self, detector: SceneDetector) -> None:
         kinds = [type(d)._DET_FLAG for d in self._detector_list]
         if type(detector)._DET_FLAG in kinds:
-            raise ValueError("one detector of each kind (content / adaptive / histogram / threshold) per SceneManager")
+            raise ValueError("one detector of each kind (content / adaptive / histogram / threshold / hash) per SceneManager")
         if self.stats_manager is not None:
             detector.stats_manager = self.stats_manager
             self.stats_manager.register_metrics(detector.get_metrics())
@@ -229,6 +229,8 @@ class SceneManager:
             self.scores = ctx.read_scores(start, total)
             if any(isinstance(d, ThresholdDetector) for d in self._detector_list):
                 self.scores["average_rgb"] = ctx.read_average_rgb(start, total)
+            if any(isinstance(d, HashDetector) for d in self._detector_list):
+                self.scores["hash_bits"], self.scores["hash_dist"] = ctx.read_hash(start, total)
             if any(isinstance(d, ContentDetector) and d._weights.delta_edges > 0.0 for d in self._detector_list):
                 self.scores["edge_counts"] = ctx.read_edge_counts(start, total)
             if self.stats_manager is not None:
@@ -260,6 +262,11 @@ class SceneManager:
                     d = sc["hist_diff"][k]
                     if d == d:
                         self.stats_manager.set_metrics(fn, {det.get_metrics()[0]: float(d)})
+            if isinstance(det, HashDetector):
+                for k in range(total):
+                    d = sc["hash_dist"][k]
+                    if d == d:
+                        self.stats_manager.set_metrics(start + k, {det.get_metrics()[0]: float(d)})
             if isinstance(det, ThresholdDetector):
                 avg = self._ctx.read_average_rgb(start, total)
                 for k in range(total):

@@ -20,7 +20,7 @@ from typing import Callable, List, Optional, Sequence, Tuple
 
 import numpy as np
 
-from .detectors import AdaptiveDetector, ContentDetector, FlashFilter, HistogramDetector, ThresholdDetector
+from .detectors import AdaptiveDetector, ContentDetector, FlashFilter, HashDetector, HistogramDetector, ThresholdDetector
 from .scene_manager import BatchVideo, SceneManager, TensorVideo
 
 logger = logging.getLogger(__name__)
@@ -133,8 +133,18 @@ def build_detectors(config: dict) -> list:
             if "add_final_scene" in cfg:
                 kw["add_final_scene"] = bool(cfg["add_final_scene"])
             dets.append(ThresholdDetector(**kw))
+        elif name in ("hash", "detect-hash"):
+            kw = dict(common)
+            if "hash_threshold" in cfg:
+                kw["threshold"] = float(cfg["hash_threshold"])
+            elif "threshold" in cfg and len(names) == 1:
+                kw["threshold"] = float(cfg["threshold"])
+            for k in ("size", "lowpass"):
+                if k in cfg:
+                    kw[k] = int(cfg[k])
+            dets.append(HashDetector(**kw))
         else:
-            raise ValueError(f"unknown scene detector {name!r} (content | adaptive | hist | threshold)")
+            raise ValueError(f"unknown scene detector {name!r} (content | adaptive | hist | threshold | hash)")
     return dets
 
 

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define ESD_ABI_VERSION 1
+#define ESD_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define ESD_API __attribute__((visibility("default")))
@@ -50,7 +50,7 @@ typedef enum esd_status {
 } esd_status;
 
 /* detector bitmask: which decision passes (and therefore which per-frame features) run */
-enum { ESD_DET_CONTENT = 1, ESD_DET_ADAPTIVE = 2, ESD_DET_HIST = 4, ESD_DET_THRESHOLD = 8 };
+enum { ESD_DET_CONTENT = 1, ESD_DET_ADAPTIVE = 2, ESD_DET_HIST = 4, ESD_DET_THRESHOLD = 8, ESD_DET_HASH = 16 };
 /* ThresholdDetector.Method */
 enum { ESD_THRESH_FLOOR = 0, ESD_THRESH_CEILING = 1 };
 /* FlashFilter.Mode of PySceneDetect >= 0.6.4; SUPPRESS == the legacy (<= 0.6.3) min_scene_len rule */
@@ -107,6 +107,13 @@ typedef struct esd_config {
     int32_t reserved1;
     int64_t max_cuts;          /* per-detector cut capacity (default 65536) */
     int64_t initial_capacity;  /* frames of per-frame score storage to pre-allocate (grows by doubling) */
+
+    /* HashDetector(threshold, size, lowpass, min_scene_len) -- perceptual (DCT) hash, ABI >= 2 */
+    double hash_threshold;     /* normalised Hamming distance, default 0.395 */
+    int32_t hash_size;         /* hash is size x size bits (default 16; size * size <= 1024) */
+    int32_t hash_lowpass;      /* DCT runs on a (size * lowpass)^2 INTER_AREA thumbnail (default 2; size * lowpass <= 64, even) */
+    int32_t hash_min_scene_len;
+    int32_t reserved2;
 } esd_config;
 
 /* derived geometry, for the caller's roofline accounting and ingest sizing */
@@ -186,6 +193,16 @@ ESD_API int esd_read_scores(esd_ctx* ctx, int64_t from_frame, int64_t n, uint64_
  * only when a delta_edges weight is > 0.  Synchronises. */
 ESD_API int esd_read_edge_counts(esd_ctx* ctx, int64_t from_frame, int64_t n, uint32_t* counts);
 
+/* HashDetector's per-frame results: `bits` [n][ceil(size*size/32)] (bit i of the row-major size x size hash in word
+ * i / 32, bit i % 32; padding bits zero) and `hash_dist` = Hamming distance to the previous frame / size^2 (NaN for the
+ * first frame).  Either pointer may be NULL.  The integer stages (BGR2GRAY, INTER_AREA) are bit-exact with OpenCV; the
+ * DCT is evaluated in float64, so a bit whose coefficient lies within float32 rounding noise of the median may differ
+ * from a given cv2 build (cv2.dct itself differs between its IPP and plain paths).  Synchronises. */
+ESD_API int esd_read_hash(esd_ctx* ctx, int64_t from_frame, int64_t n, uint32_t* bits, double* hash_dist);
+/* Test hook: the (size*lowpass)^2 uint8 INTER_AREA thumbnail the hash of frame `frame` was computed from; only frames of
+ * the most recent push are available.  Synchronises. */
+ESD_API int esd_debug_read_hash_input(esd_ctx* ctx, int64_t frame, uint8_t* out, int64_t cap);
+
 /* ThresholdDetector's per-frame metric: average of all B,G,R values of the (downscaled) frame.  Synchronises. */
 ESD_API int esd_read_average_rgb(esd_ctx* ctx, int64_t from_frame, int64_t n, double* average_rgb);
 
@@ -205,7 +222,8 @@ ESD_API int esd_get_cuts(esd_ctx* ctx, int32_t detector, int64_t from_index, int
 /* Stand-alone decision pass over score arrays already on the host (merge step of frame-range
  * sharding: shards return scores, one global pass decides).  Uses the ctx's detector parameters but
  * none of its frame state.  For ESD_DET_ADAPTIVE `scores` = adaptive_val (ratios are recomputed);
- * ESD_DET_CONTENT: content_val; ESD_DET_HIST: hist_diff (NaN = no previous frame); ESD_DET_THRESHOLD: average_rgb. */
+ * ESD_DET_CONTENT: content_val; ESD_DET_HIST: hist_diff (NaN = no previous frame); ESD_DET_THRESHOLD: average_rgb;
+ * ESD_DET_HASH: hash_dist (NaN = no previous frame). */
 ESD_API int esd_decide_arrays(esd_ctx* ctx, int32_t detector, int64_t first_frame_num, int64_t n,
                       const double* scores, double* adaptive_ratio_out, int64_t* cuts, int64_t cap,
                       int64_t* n_cuts);

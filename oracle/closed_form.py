@@ -230,3 +230,110 @@ def dilate_ones_u8(img: np.ndarray, k: int) -> np.ndarray:
 def detect_edges(lum: np.ndarray, kernel_size: int) -> np.ndarray:
     low, high = canny_thresholds(lum)
     return dilate_ones_u8(canny_u8(lum, low, high), kernel_size)
+
+
+# --------------------------------------------------------------------------- N4: HashDetector.hash_frame stages
+def bgr2gray_u8(img: np.ndarray) -> np.ndarray:
+    """cv2.cvtColor(img, COLOR_BGR2GRAY) for uint8: 15-bit coefficients (OpenCV 4.x color_rgb, RGB2Gray<uchar>:
+    BY15 = 3735, GY15 = 19235, RY15 = 9798), NOT the 14-bit Y of BGR2YUV.  Verified over all 2^24 BGR values
+    against cv2 4.13 (tests/test_oracle.py)."""
+    b = img[..., 0].astype(np.int32)
+    g = img[..., 1].astype(np.int32)
+    r = img[..., 2].astype(np.int32)
+    return ((9798 * r + 19235 * g + 3735 * b + 16384) >> 15).astype(np.uint8)
+
+
+def area_axis_table(ssize: int, dsize: int):
+    """OpenCV resize.cpp computeResizeAreaTab for one axis (cn = 1): list of (dst index, src index, float32 weight)
+    in the order the C++ loop visits them.  `scale` is a double; the weights are narrowed to float32."""
+    import math
+
+    scale = ssize / dsize
+    tab = []
+    for d in range(dsize):
+        fsx1 = d * scale
+        fsx2 = fsx1 + scale
+        cell = min(scale, ssize - fsx1)
+        sx1 = math.ceil(fsx1)
+        sx2 = math.floor(fsx2)
+        sx2 = min(sx2, ssize - 1)
+        sx1 = min(sx1, sx2)
+        if sx1 - fsx1 > 1e-3:
+            tab.append((d, sx1 - 1, np.float32((sx1 - fsx1) / cell)))
+        for sx in range(sx1, sx2):
+            tab.append((d, sx, np.float32(1.0 / cell)))
+        if fsx2 - sx2 > 1e-3:
+            tab.append((d, sx2, np.float32(min(min(fsx2 - sx2, 1.0), cell) / cell)))
+    return tab
+
+
+def resize_area_u8(img: np.ndarray, dst_w: int, dst_h: int) -> np.ndarray:
+    """cv2.resize(img, (dst_w, dst_h), interpolation=INTER_AREA) for one-channel uint8 when shrinking on both axes.
+
+    * both scale factors integral: ResizeAreaFast_ -- integer box sum, `saturate_cast<uchar>(sum * float32(1/area))`
+      (the 2x2 case is the SIMD special `(sum + 2) >> 2`);
+    * otherwise ResizeArea_: per source row a float32 row buffer `buf[dx] += S[sx] * alpha` in table order, rows
+      combined as `sum = beta * buf` / `sum += beta * buf`, float32 throughout, no FMA, cvRound at the end.
+    Verified bit-exact against cv2 4.13 (IPP on and off) for a range of geometries (tests/test_oracle.py)."""
+    h, w = img.shape
+    if dst_w > w or dst_h > h:
+        raise ValueError("resize_area_u8 only restates the shrinking case")
+    sx, sy = w / dst_w, h / dst_h
+    eps = np.finfo(np.float64).eps
+    if abs(sx - int(sx)) < eps and abs(sy - int(sy)) < eps:
+        isx, isy = int(sx), int(sy)
+        s = img.reshape(dst_h, isy, dst_w, isx).astype(np.int64).sum(axis=(1, 3))
+        if isx == 2 and isy == 2:
+            return ((s + 2) >> 2).astype(np.uint8)
+        v = s.astype(np.float32) * np.float32(1.0 / (isx * isy))
+        return np.clip(np.rint(v), 0, 255).astype(np.uint8)
+    xt = area_axis_table(w, dst_w)
+    yt = area_axis_table(h, dst_h)
+    f = img.astype(np.float32)
+    res = np.zeros((dst_h, dst_w), np.float32)
+    xd = np.array([t[0] for t in xt])
+    xs = np.array([t[1] for t in xt])
+    xa = np.array([t[2] for t in xt], np.float32)
+    # position of every x entry inside its destination column (0, 1, 2, ...): entries of equal rank are independent
+    rank = np.zeros(len(xt), np.int64)
+    for i in range(1, len(xt)):
+        rank[i] = rank[i - 1] + 1 if xd[i] == xd[i - 1] else 0
+    prev = -1
+    for (dy, sy_, beta) in yt:
+        buf = np.zeros(dst_w, np.float32)
+        for k in range(int(rank.max()) + 1):
+            sel = rank == k
+            buf[xd[sel]] = buf[xd[sel]] + f[sy_, xs[sel]] * xa[sel]
+        if dy != prev:
+            res[dy] = beta * buf
+            prev = dy
+        else:
+            res[dy] = res[dy] + beta * buf
+    return np.clip(np.rint(res), 0, 255).astype(np.uint8)
+
+
+def dct_matrix(n: int) -> np.ndarray:
+    """Orthonormal DCT-II basis C[u, i] (float64): cv2.dct(x) == C @ x @ C.T up to float32 rounding."""
+    i = np.arange(n)
+    c = np.sqrt(2.0 / n) * np.cos(np.pi * (2 * i[None, :] + 1) * i[:, None] / (2 * n))
+    c[0, :] = np.sqrt(1.0 / n)
+    return c
+
+
+def hash_frame(frame_bgr: np.ndarray, hash_size: int = 16, factor: int = 2):
+    """HashDetector.hash_frame with the DCT evaluated in float64 and narrowed to float32.
+
+    Returns (bits bool[hash_size, hash_size], margin float64[hash_size, hash_size] = |coef - median|).  cv2.dct's
+    float32 result depends on the OpenCV build (IPP vs. plain differ in ~70 % of the coefficients by 1-2 ulp), so
+    only bits whose margin exceeds that noise are comparable across implementations."""
+    gray = bgr2gray_u8(frame_bgr)
+    imsize = hash_size * factor
+    small = resize_area_u8(gray, imsize, imsize)
+    max_value = int(small.max())
+    if max_value == 0:
+        max_value = 1
+    x = small.astype(np.float32) / np.float32(max_value)
+    c = dct_matrix(imsize)[:hash_size]
+    low = (c @ x.astype(np.float64) @ c.T).astype(np.float32)
+    med = np.median(low)
+    return low > med, np.abs(low.astype(np.float64) - float(med))

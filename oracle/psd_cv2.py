@@ -414,6 +414,77 @@ class ThresholdDetector:
         return 0
 
 
+class HashDetector:
+    """scenedetect.detectors.HashDetector.process_frame / hash_frame (0.6.4)
+    [upstream-recall: restated from knowledge of the package, parity unpinned].
+
+    Perceptual hash: gray -> INTER_AREA resize to (size*lowpass)^2 -> / max -> cv2.dct -> low-frequency
+    size x size block -> bits = coefficient > median; the score is the Hamming distance to the previous frame's
+    hash divided by size^2.  cv2.dct's float32 output is build-dependent (IPP), so besides the bits this class
+    records each bit's margin |coef - median| for tolerance-aware comparisons."""
+
+    def __init__(self, threshold=0.395, size=16, lowpass=2, min_scene_len=15, backend="cv2"):
+        self._threshold = threshold
+        self._min_scene_len = min_scene_len
+        self._size = size
+        self._size_sq = float(size * size)
+        self._factor = lowpass
+        self._last_frame = None
+        self._last_scene_cut = None
+        self._last_hash = np.array([])
+        self._backend = backend
+        self.hashes: list = []   # bool[size, size] per frame
+        self.margins: list = []  # float64[size, size] |coef - median| per frame
+        self.dists: list = []    # hash_dist_norm per frame (nan for the first)
+
+    def get_metrics(self):
+        return [f"hash_dist [size={self._size} lowpass={self._factor}]"]
+
+    def hash_frame(self, frame_img):
+        if self._backend != "cv2":
+            return cf.hash_frame(frame_img, self._size, self._factor)
+        gray_img = cv2.cvtColor(frame_img, cv2.COLOR_BGR2GRAY)
+        imsize = self._size * self._factor
+        resized_img = cv2.resize(gray_img, (imsize, imsize), interpolation=cv2.INTER_AREA)
+        max_value = np.max(np.max(resized_img))
+        if max_value == 0:
+            max_value = 1
+        resized_img = np.float32(resized_img) / max_value
+        dct_complete = cv2.dct(resized_img)
+        dct_low_freq = dct_complete[:self._size, :self._size]
+        med = np.median(dct_low_freq)
+        return dct_low_freq > med, np.abs(dct_low_freq.astype(np.float64) - float(med))
+
+    def process_frame(self, frame_num, frame_img) -> List[int]:
+        cut_list = []
+        if self._last_scene_cut is None:
+            self._last_scene_cut = frame_num
+        # the reference hashes a frame when it is compared; hashing every frame as it arrives yields the same values
+        curr_hash, margin = self.hash_frame(frame_img)
+        self.hashes.append(curr_hash)
+        self.margins.append(margin)
+        if self._last_frame is not None:
+            last_hash = self._last_hash
+            hash_dist = np.count_nonzero(curr_hash.flatten() != last_hash.flatten())
+            hash_dist_norm = hash_dist / self._size_sq
+            self.dists.append(float(hash_dist_norm))
+            if hash_dist_norm >= self._threshold and (frame_num - self._last_scene_cut) >= self._min_scene_len:
+                cut_list.append(frame_num)
+                self._last_scene_cut = frame_num
+        else:
+            self.dists.append(float("nan"))
+        self._last_hash = curr_hash
+        self._last_frame = True
+        return cut_list
+
+    def post_process(self, frame_num) -> List[int]:
+        return []
+
+    @property
+    def event_buffer_length(self):
+        return 0
+
+
 # ----------------------------------------------------------------------------- SceneManager (A.1, A.8)
 def get_scenes_from_cuts(cut_list: Sequence[int], start_pos: int, end_pos: int):
     """scenedetect.scene_manager.get_scenes_from_cuts on frame numbers."""

@@ -11,6 +11,10 @@ What is frozen (SURVEY.md section 8c "golden vectors to create"):
                 BASELINE configs, computed by oracle/psd_cv2.py (PySceneDetect logic on real cv2)
                 on frames from the CPU twin of the clip generator.
   filter_vectors.json   FlashFilter / min_scene_len state-machine unit vectors.
+  hash_*.npz    HashDetector on the same clips, from real cv2 (cvtColor GRAY, resize INTER_AREA,
+                dct): per-frame hash bits, the bits whose DCT coefficient lies within 4e-6 of the median
+                ("unstable": cv2.dct's float32 rounding is build-dependent), hash_dist, cut list, and a sha256
+                of the INTER_AREA thumbnails (integer stage, bit-exact).
 --full also produces the full-length config-2 (18 000 x 1080p) and config-4 (3 600 x 4K) files.
 """
 from __future__ import annotations
@@ -109,6 +113,37 @@ def clip(name, seed, w, h, n, chunk=64, downscale_mode="float"):
           f"adaptive={len(cuts['adaptive'])} hist={len(cuts['hist'])} threshold={len(cuts['threshold'])}", flush=True)
 
 
+HASH_MARGIN = 4e-6  # cv2.dct IPP vs plain differ by <= ~2e-7 on [0,1] inputs; float64 DCT vs cv2 by <= ~1.5e-6
+
+
+def hash_clip(name, seed, w, h, n, chunk=64, size=16, lowpass=2):
+    t0 = time.time()
+    sch = synth.build_schedule(seed, n)
+    det = P.HashDetector(threshold=0.395, size=size, lowpass=lowpass, min_scene_len=15)
+    from oracle import closed_form as cf
+    factor = cf.compute_downscale_factor(w)
+    dw, dh = cf.downscaled_size(w, h, factor)
+    cuts = []
+    thumbs = hashlib.sha256()
+    k = 0
+    for a in range(0, n, chunk):
+        for f in co.synth_frames(seed, w, h, sch.descs[a:a + chunk]):
+            small = cv2.resize(f, (dw, dh), interpolation=cv2.INTER_LINEAR) if factor > 1 else f
+            cuts += det.process_frame(k, small)
+            g = cv2.cvtColor(small, cv2.COLOR_BGR2GRAY)
+            thumbs.update(cv2.resize(g, (size * lowpass, size * lowpass), interpolation=cv2.INTER_AREA).tobytes())
+            k += 1
+    bits = np.array(det.hashes).reshape(n, -1)
+    unstable = np.array(det.margins).reshape(n, -1) <= HASH_MARGIN
+    np.savez_compressed(os.path.join(HERE, f"hash_{name}.npz"), seed=seed, width=w, height=h, n_frames=n, dst=np.array([dw, dh]),
+                        size=size, lowpass=lowpass, bits=np.packbits(bits, axis=1, bitorder="little"),
+                        unstable=np.packbits(unstable, axis=1, bitorder="little"), hash_dist=np.array(det.dists),
+                        cuts_hash=np.array(cuts, np.int64), thumbs_sha256=np.frombuffer(thumbs.digest(), np.uint8),
+                        margin=HASH_MARGIN, versions=json.dumps(VERSIONS))
+    print(f"hash_{name}: {n} frames, {len(cuts)} cuts, {int(unstable.sum())} unstable bits of {unstable.size} "
+          f"in {time.time() - t0:.1f}s", flush=True)
+
+
 def filter_vectors():
     rng = np.random.default_rng(7)
     vecs = []
@@ -144,6 +179,10 @@ if __name__ == "__main__":
         clip("c2_1080p_head", 1002, 1920, 1080, 600)    # first 600 frames of config 2
         clip("c4_4k_head", 1004, 3840, 2160, 240)       # first 240 frames of config 4
         clip("c2_1080p_int_head", 1002, 1920, 1080, 300, downscale_mode="int")  # <= 0.6.1 downscale (274x154)
+    if not only or "hash" in only:
+        hash_clip("c1_720p", 1001, 1280, 720, 1800)
+        hash_clip("c2_1080p_head", 1002, 1920, 1080, 600)
+        hash_clip("c4_4k_head_s8l4", 1004, 3840, 2160, 120, size=8, lowpass=4)
     if full:
         clip("c2_1080p_full", 1002, 1920, 1080, 18000)
         clip("c4_4k_full", 1004, 3840, 2160, 3600)

@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol(lib_built):
     for name in declared:
         assert hasattr(L, name), name
     assert sorted(capi.EXPORTED_SYMBOLS) == declared
-    assert L.esd_abi_version() == 1
+    assert L.esd_abi_version() == capi.ESD_ABI_VERSION == int(re.search(r"#define ESD_ABI_VERSION (\d+)", hdr).group(1))
     assert L.esd_strerror(-4) == b"call out of order"
     out = subprocess.run(["nm", "-D", "--defined-only", capi.LIB_PATH], capture_output=True, text=True).stdout
     exported = set(re.findall(r" T (\w+)", out))
@@ -47,13 +47,14 @@ def test_ctypes_struct_layout_matches_header(tmp_path):
     src = tmp_path / "layout.c"
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "esd.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu\\n",'
                    "sizeof(esd_config), offsetof(esd_config, content_threshold), offsetof(esd_config, adaptive_weights),"
-                   "offsetof(esd_config, hist_bins), offsetof(esd_config, max_cuts), sizeof(esd_geometry));return 0;}\n")
+                   "offsetof(esd_config, hist_bins), offsetof(esd_config, max_cuts), sizeof(esd_geometry));"
+                   'printf("%zu %zu\\n", offsetof(esd_config, hash_threshold), offsetof(esd_config, hash_min_scene_len));return 0;}\n')
     exe = tmp_path / "layout"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     got = list(map(int, subprocess.check_output([str(exe)]).split()))
     C = capi.EsdConfig
     assert got == [ctypes.sizeof(C), C.content_threshold.offset, C.adaptive_weights.offset, C.hist_bins.offset,
-                   C.max_cuts.offset, ctypes.sizeof(capi.EsdGeometry)]
+                   C.max_cuts.offset, ctypes.sizeof(capi.EsdGeometry), C.hash_threshold.offset, C.hash_min_scene_len.offset]
 
 
 def test_defaults_are_pyscenedetect_defaults():
@@ -62,6 +63,7 @@ def test_defaults_are_pyscenedetect_defaults():
     assert list(cfg.content_weights) == [1.0, 1.0, 1.0, 0.0] and cfg.content_weight_div == 3.0
     assert (cfg.adaptive_threshold, cfg.adaptive_window_width, cfg.adaptive_min_content_val, cfg.adaptive_min_scene_len) == (3.0, 2, 15.0, 15)
     assert (cfg.hist_threshold, cfg.hist_bins, cfg.hist_min_scene_len) == (0.05, 256, 15)
+    assert (cfg.hash_threshold, cfg.hash_size, cfg.hash_lowpass, cfg.hash_min_scene_len) == (0.395, 16, 2, 15)
 
 
 @pytest.mark.skipif(_has_gpu(), reason="checks the no-GPU failure mode")
@@ -206,8 +208,11 @@ def test_build_detectors_from_task_config():
     assert isinstance(both[0], HistogramDetector) and both[0]._bins == 128 and isinstance(both[1], ContentDetector)
     th = build_detectors({"detector": "threshold", "threshold": 20, "fade_bias": 0.5, "add_final_scene": True})[0]
     assert isinstance(th, ThresholdDetector) and (th.threshold, th.fade_bias, th.add_final_scene) == (20, 0.5, True)
+    hs = build_detectors({"detector": "hash", "threshold": 0.3, "size": 8, "lowpass": 4, "min_scene_len": 10})[0]
+    assert type(hs).__name__ == "HashDetector" and (hs._threshold, hs._size, hs._factor, hs._min_scene_len) == (0.3, 8, 4, 10)
+    assert hs.get_metrics() == ["hash_dist [size=8 lowpass=4]"]
     with pytest.raises(ValueError):
-        build_detectors({"detector": "hash"})
+        build_detectors({"detector": "optical-flow"})
 
 
 def test_model_manager_raises_like_the_reference():

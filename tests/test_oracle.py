@@ -200,3 +200,47 @@ def test_canny_dilate_restatement_vs_cv2():
     cb, _ = P.detect(frames, [b], backend="closed_form")
     assert ca == cb and a.edge_sums == b.edge_sums and max(a.edge_sums) > 0
     assert np.array_equal(np.array(a.scores).view(np.uint64), np.array(b.scores).view(np.uint64))
+
+
+# ------------------------------------------------------------------------------------------------ HashDetector stages
+def test_gray_restatement_exhaustive_vs_cv2():
+    """cv2 BGR2GRAY uses the 15-bit coefficients (not the 14-bit Y of BGR2YUV): all 2^24 BGR values."""
+    cv2 = pytest.importorskip("cv2")
+    x = np.arange(1 << 24, dtype=np.uint32)
+    img = np.stack([x & 255, (x >> 8) & 255, (x >> 16) & 255], -1).astype(np.uint8).reshape(4096, 4096, 3)
+    assert np.array_equal(cv2.cvtColor(img, cv2.COLOR_BGR2GRAY), cf.bgr2gray_u8(img))
+
+
+@pytest.mark.parametrize("w,h,s", [(256, 144, 32), (274, 154, 32), (285, 160, 32), (100, 77, 32), (64, 64, 32), (128, 96, 32),
+                                   (32, 32, 32), (33, 40, 32), (300, 200, 64), (320, 180, 6), (200, 120, 20)])
+def test_inter_area_restatement_vs_cv2(w, h, s):
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(w * 7 + h)
+    for _ in range(3):
+        img = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        assert np.array_equal(cf.resize_area_u8(img, s, s), cv2.resize(img, (s, s), interpolation=cv2.INTER_AREA))
+
+
+def test_hash_closed_form_vs_cv2_golden():
+    """The float64-DCT restatement reproduces the cv2-derived golden hashes on every stable bit, and the golden's
+    thumbnails hash matches the restated integer stages."""
+    import hashlib
+
+    from eioku_b200 import synth
+    from oracle import c_oracle as co
+    g = load_golden("hash_c2_1080p_head.npz")
+    w, h, seed = int(g["width"]), int(g["height"]), int(g["seed"])
+    n = 48
+    sch = synth.build_schedule(seed, n)
+    frames = co.synth_frames(seed, w, h, sch.descs)
+    dw, dh = [int(v) for v in g["dst"]]
+    want = np.unpackbits(g["bits"], axis=1, bitorder="little")[:n].astype(bool)
+    unstable = np.unpackbits(g["unstable"], axis=1, bitorder="little")[:n].astype(bool)
+    det = P.HashDetector(backend="closed_form")
+    for k in range(n):
+        small = cf.resize_linear_u8(frames[k], dw, dh)
+        det.process_frame(k, small)
+    got = np.array(det.hashes).reshape(n, -1)
+    assert not ((got != want) & ~unstable).any()
+    if not unstable.any():
+        assert np.array_equal(np.array(det.dists)[1:], g["hash_dist"][1:n])
