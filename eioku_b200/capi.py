@@ -24,7 +24,7 @@ EXPORTED_SYMBOLS = (
     "esd_create", "esd_destroy", "esd_reset", "esd_get_geometry", "esd_get_touched_rows",
     "esd_push_frames", "esd_push_rows", "esd_ingest_open", "esd_ingest_push_host", "esd_ingest_close", "esd_ingest_set_gather",
     "esd_ingest_stats", "esd_synchronize", "esd_join", "esd_frames_pushed", "esd_read_scores", "esd_read_edge_counts", "esd_read_average_rgb",
-    "esd_read_hash", "esd_debug_read_hash_input",
+    "esd_read_hash", "esd_debug_read_hash_input", "esd_process_frame_host",
     "esd_post_process", "esd_get_cuts",
     "esd_decide_arrays", "esd_debug_read_prev", "esd_set_timing", "esd_kernel_time", "esd_kernel_launches", "esd_synth_fill",
 )
@@ -114,6 +114,7 @@ def load_library(path: Optional[str] = None):
     L.esd_read_average_rgb.argtypes = [vp, i64, i64, vp]
     L.esd_read_edge_counts.argtypes = [vp, i64, i64, vp]
     L.esd_read_hash.argtypes = [vp, i64, i64, vp, vp]
+    L.esd_process_frame_host.argtypes = [vp, vp, i64, i64, i32, i64, vp, i64, C.POINTER(i64), C.POINTER(i64)]
     L.esd_debug_read_hash_input.argtypes = [vp, i64, vp, i64]
     L.esd_post_process.argtypes = [vp, i32, i64, vp, i64, C.POINTER(i64)]
     L.esd_decide_arrays.argtypes = [vp, i32, i64, i64, vp, vp, vp, i64, C.POINTER(i64)]
@@ -159,6 +160,7 @@ class EsdContext:
         g = EsdGeometry()
         self._check(self._L.esd_get_geometry(self._h, C.byref(g)), "esd_get_geometry")
         self.geometry = g
+        self._pf_buf = np.empty(64, np.int64)
 
     # -- plumbing
     def _check(self, rc: int, what: str):
@@ -338,6 +340,23 @@ class EsdContext:
                 continue
             self._check(rc, "esd_get_cuts")
             return buf[: nw.value].tolist(), int(nt.value)
+
+    def process_frame_host(self, frame: np.ndarray, frame_num: int, detector: int, from_index: int = 0):
+        """One host frame [H,W,3] uint8 (dense pixels, any row pitch) through the per-frame fast path.
+        -> (cuts of `detector` from `from_index` on, total cuts emitted)."""
+        if frame.dtype != np.uint8 or frame.ndim != 3 or frame.shape[2] != 3 or frame.strides[2] != 1 or frame.strides[1] != 3:
+            frame = np.ascontiguousarray(frame, np.uint8)
+        h, w, _ = frame.shape
+        if (w, h) != (self.cfg.src_width, self.cfg.src_height):
+            raise ValueError(f"frame size {w}x{h} != configured {self.cfg.src_width}x{self.cfg.src_height}")
+        buf = self._pf_buf
+        nw, nt = C.c_int64(), C.c_int64()
+        rc = self._L.esd_process_frame_host(self._h, frame.ctypes.data, frame.strides[0], frame_num, detector, from_index,
+                                            buf.ctypes.data, buf.size, C.byref(nw), C.byref(nt))
+        if rc == -6 and nt.value - from_index > buf.size:  # more cuts pending than the small buffer holds
+            return self.get_cuts(detector, from_index)
+        self._check(rc, "esd_process_frame_host")
+        return buf[: nw.value].tolist(), int(nt.value)
 
     def decide_arrays(self, detector: int, first_frame_num: int, scores: np.ndarray):
         scores = np.ascontiguousarray(scores, np.float64)

@@ -117,6 +117,45 @@ class GatherPool {
     bool stop_ = false;
 };
 
+// Kernel launcher of push_common.  DIRECT launches on the stream; the per-frame plugin path (esd_process_frame_host) is
+// launch-bound (three to seven tiny kernels per call), so there the same call sequence BUILDs a CUDA graph once (one
+// kernel node per launch, chained) and afterwards only UPDATEs the nodes' parameters before a single cudaGraphLaunch.
+struct KernelGraph {
+    enum Mode { DIRECT = 0, BUILD = 1, UPDATE = 2 };
+    int mode = DIRECT;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    std::vector<cudaGraphNode_t> nodes;
+    size_t cursor = 0;
+    void destroy() {
+        if (exec) cudaGraphExecDestroy(exec);
+        if (graph) cudaGraphDestroy(graph);
+        exec = nullptr; graph = nullptr; nodes.clear(); cursor = 0; mode = DIRECT;
+    }
+};
+
+template <typename... P>
+cudaError_t klaunch(KernelGraph& g, cudaStream_t st, void (*kernel)(P...), dim3 grid, dim3 block, size_t smem,
+                    typename std::decay<P>::type... args) {
+    void* argv[] = {(void*)&args...};
+    if (g.mode == KernelGraph::DIRECT) return cudaLaunchKernel((const void*)kernel, grid, block, argv, smem, st);
+    cudaKernelNodeParams kp{};
+    kp.func = (void*)kernel;
+    kp.gridDim = grid;
+    kp.blockDim = block;
+    kp.sharedMemBytes = (unsigned)smem;
+    kp.kernelParams = argv;
+    if (g.mode == KernelGraph::BUILD) {
+        cudaGraphNode_t node;
+        const cudaGraphNode_t* dep = g.nodes.empty() ? nullptr : &g.nodes.back();
+        cudaError_t e = cudaGraphAddKernelNode(&node, g.graph, dep, g.nodes.empty() ? 0 : 1, &kp);
+        if (e == cudaSuccess) g.nodes.push_back(node);
+        return e;
+    }
+    if (g.cursor >= g.nodes.size()) return cudaErrorInvalidValue;  // topology changed: caller rebuilds
+    return cudaGraphExecKernelNodeSetParams(g.exec, g.nodes[g.cursor++], &kp);
+}
+
 }  // namespace
 
 struct esd_ctx {
@@ -200,6 +239,12 @@ struct esd_ctx {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing_events;
     int64_t launches = 0;
 
+    // per-frame plugin path (esd_process_frame_host): one pinned + one device frame, results through pinned memory
+    uint8_t* pf_h = nullptr;           // pinned frame, read by the fused kernel's TMA loads straight over PCIe
+    long long* pf_mailbox = nullptr;   // pinned, host-mapped: n_cuts[5] + overflow flag written by decide_kernel
+    cudaStream_t pf_stream = nullptr;
+    KernelGraph kg;                    // DIRECT except inside esd_process_frame_host
+
     // ingest
     std::vector<IngestSlot> ring;
     int frames_per_slot = 0;
@@ -271,12 +316,11 @@ long py_round(double x) { return lrint(x); }
 
 template <bool RESIZE, int PXT>
 cudaError_t launch_fused_rp(bool content, bool hist, bool aligned, const FusedParams& p, int grid, size_t smem,
-                            cudaStream_t st) {
+                            cudaStream_t st, KernelGraph& kg) {
 #define ESD_LAUNCH(C, H)                                                                                         \
     do {                                                                                                         \
         auto k = aligned ? fused_score_kernel<RESIZE, PXT, C, H, true> : fused_score_kernel<RESIZE, PXT, C, H, false>; \
-        k<<<grid, kThreads, smem, st>>>(p);                                                                      \
-        return cudaGetLastError();                                                                               \
+        return klaunch(kg, st, k, dim3(grid), dim3(kThreads), smem, p);                                          \
     } while (0)
     if (content && hist) ESD_LAUNCH(true, true);
     if (content) ESD_LAUNCH(true, false);
@@ -538,8 +582,10 @@ struct TraceTimer {
 
 enum Layout { LAYOUT_FULL = 0, LAYOUT_ROWS = 1, LAYOUT_TAPS = 2 };
 
+// inline_tail: run the finalize/decision tail on `st` itself (per-frame path: nothing to overlap with, and the
+// cross-stream event round trip would cost more than the tail)
 int push_common(esd_ctx* c, const uint8_t* d_src, int64_t n, int64_t frame_stride, int64_t row_stride, int layout,
-                int64_t first_frame_num, cudaStream_t st) {
+                int64_t first_frame_num, cudaStream_t st, bool inline_tail = false, long long* mailbox = nullptr) {
     const bool compact = layout != LAYOUT_FULL;
     TraceTimer tr;
     if (!d_src || n <= 0) return fail(c, ESD_ERR_INVALID, "push: null frames or n <= 0");
@@ -601,7 +647,9 @@ int push_common(esd_ctx* c, const uint8_t* d_src, int64_t n, int64_t frame_strid
     p.vplane = c->need_edges ? c->d_vplane[buf] : nullptr;
     p.gplane = c->need_hash ? c->d_gplane[buf] : nullptr;
     // the fused kernel overwrites part[buf]: wait until the tail of the push that last used it is done
-    if (c->fin_recorded[buf]) CU(c, cudaStreamWaitEvent(st, c->ev_fin[buf], 0));
+    // (the per-frame path is synchronous: nothing of it is ever in flight here)
+    if (c->fin_recorded[buf] && !inline_tail) CU(c, cudaStreamWaitEvent(st, c->ev_fin[buf], 0));
+    KernelGraph& kg = c->kg;
 
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (c->timing) {
@@ -610,7 +658,7 @@ int push_common(esd_ctx* c, const uint8_t* d_src, int64_t n, int64_t frame_strid
         CU(c, cudaEventRecord(e0, st));
     }
     const bool aligned = ((reinterpret_cast<uintptr_t>(d_src) | (uintptr_t)frame_stride | (uintptr_t)row_stride) & 15u) == 0;
-    CU(c, ESD_DISPATCH(launch_fused_rp, c->resize, c->pxt, c->need_content, c->need_hist, aligned, p, plan.grid, c->smem_bytes, st));
+    CU(c, ESD_DISPATCH(launch_fused_rp, c->resize, c->pxt, c->need_content, c->need_hist, aligned, p, plan.grid, c->smem_bytes, st, kg));
     c->launches++;
     tr.lap("launch fused");
     if (c->timing) {
@@ -619,69 +667,65 @@ int push_common(esd_ctx* c, const uint8_t* d_src, int64_t n, int64_t frame_strid
     }
     c->prev_parity ^= 1;
     // tail (finalize + decision) on the library's own stream, ordered after this fused kernel
-    cudaStream_t ts = c->aux_stream;
-    CU(c, cudaEventRecord(c->ev_fused, st));
-    CU(c, cudaStreamWaitEvent(ts, c->ev_fused, 0));
+    cudaStream_t ts = inline_tail ? st : c->aux_stream;
+    if (!inline_tail) {
+        CU(c, cudaEventRecord(c->ev_fused, st));
+        CU(c, cudaStreamWaitEvent(ts, c->ev_fused, 0));
+    }
 
     const double npx = (double)c->dst_w * (double)c->dst_h;  // float(rows * cols)
     if (c->need_edges) {
         const size_t esmem = 2 * (size_t)(((c->dst_w * c->dst_h) + 31) & ~31) + 8 * (size_t)c->edge_words;
-        edges_kernel<<<(unsigned)n, kEdgeThreads, esmem, ts>>>(c->d_vplane[buf], c->dst_w, c->dst_h, c->edge_ksize, c->d_edge_bits,
-                                                             c->edge_words);
-        CU(c, cudaGetLastError());
-        edge_delta_kernel<<<(unsigned)n, 256, 0, ts>>>(c->d_edge_bits, c->d_edge_prev, c->edge_words, base > 0 ? 1 : 0,
-                                                      c->d_edge_counts + base);
-        CU(c, cudaGetLastError());
+        CU(c, klaunch(kg, ts, edges_kernel, dim3((unsigned)n), dim3(kEdgeThreads), esmem, c->d_vplane[buf], c->dst_w, c->dst_h,
+                      c->edge_ksize, c->d_edge_bits, c->edge_words));
+        CU(c, klaunch(kg, ts, edge_delta_kernel, dim3((unsigned)n), dim3(256), 0, c->d_edge_bits, c->d_edge_prev, c->edge_words,
+                      base > 0 ? 1 : 0, c->d_edge_counts + base));
         CU(c, cudaMemcpyAsync(c->d_edge_prev, c->d_edge_bits + (size_t)(n - 1) * c->edge_words, sizeof(uint32_t) * c->edge_words,
                               cudaMemcpyDeviceToDevice, ts));
         c->launches += 2;
     }
     if (c->need_content) {
         const int warps_per_block = 8;
-        finalize_sums_kernel<<<(unsigned)((n + warps_per_block - 1) / warps_per_block), warps_per_block * 32, 0, ts>>>(
-            c->d_part[buf], (int)n, c->n_groups * kConsumerWarps, npx, c->wc, c->wa, c->d_sums3 + 3 * base, c->d_cv + base,
-            c->d_av + base, c->d_avg + base, c->need_edges ? c->d_edge_counts + base : nullptr);
-        CU(c, cudaGetLastError());
+        CU(c, klaunch(kg, ts, finalize_sums_kernel, dim3((unsigned)((n + warps_per_block - 1) / warps_per_block)),
+                      dim3(warps_per_block * 32), 0, c->d_part[buf], (int)n, c->n_groups * kConsumerWarps, npx, c->wc, c->wa,
+                      c->d_sums3 + 3 * base, c->d_cv + base, c->d_av + base, c->d_avg + base,
+                      c->need_edges ? c->d_edge_counts + base : nullptr));
         c->launches++;
         if (c->cfg.detectors & ESD_DET_ADAPTIVE) {
             const int w = c->cfg.adaptive_window_width;
             const int64_t t0 = std::max<int64_t>(w, base - w), t1 = base + n - w;
             if (t1 > t0) {
-                adaptive_ratio_kernel<<<(unsigned)((t1 - t0 + 255) / 256), 256, 0, ts>>>(
-                    c->d_av, c->d_ratio, t0, t1, w, c->cfg.adaptive_min_content_val);
-                CU(c, cudaGetLastError());
+                CU(c, klaunch(kg, ts, adaptive_ratio_kernel, dim3((unsigned)((t1 - t0 + 255) / 256)), dim3(256), 0, c->d_av,
+                              c->d_ratio, (long long)t0, (long long)t1, w, c->cfg.adaptive_min_content_val));
                 c->launches++;
             }
         }
     }
     if (c->need_hist) {
         const int bins = c->cfg.hist_bins;
-        finalize_hist_counts_kernel<<<(unsigned)n, 256, 0, ts>>>(c->d_hist_part[buf], c->n_groups, bins,
-                                                                 c->d_counts + base * bins);
-        CU(c, cudaGetLastError());
-        hist_diff_kernel<<<(unsigned)n, 256, 0, ts>>>(c->d_counts + base * bins, bins, base > 0 ? 1 : 0,
-                                                      c->d_hdiff + base);
-        CU(c, cudaGetLastError());
+        CU(c, klaunch(kg, ts, finalize_hist_counts_kernel, dim3((unsigned)n), dim3(256), 0, c->d_hist_part[buf], c->n_groups, bins,
+                      c->d_counts + base * bins));
+        CU(c, klaunch(kg, ts, hist_diff_kernel, dim3((unsigned)n), dim3(256), 0, c->d_counts + base * bins, bins, base > 0 ? 1 : 0,
+                      c->d_hdiff + base));
         c->launches += 2;
     }
     if (c->need_hash) {
         const HashParams& hp = c->hparams;
         const size_t hsmem = sizeof(float) * hp.S * hp.S + sizeof(double) * hp.hs * hp.S + sizeof(float) * hp.hs * hp.hs;
-        hash_kernel<<<(unsigned)n, kHashThreads, hsmem, ts>>>(c->d_gplane[buf], hp, c->d_hash_small,
-                                                             c->d_hash + base * c->hash_words);
-        CU(c, cudaGetLastError());
-        hash_dist_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ts>>>(c->d_hash + base * c->hash_words, c->hash_words, (int)n,
-                                                                     base > 0 ? 1 : 0, (double)(hp.hs * hp.hs), c->d_hdist + base);
-        CU(c, cudaGetLastError());
+        CU(c, klaunch(kg, ts, hash_kernel, dim3((unsigned)n), dim3(kHashThreads), hsmem, c->d_gplane[buf], hp, c->d_hash_small,
+                      c->d_hash + base * c->hash_words));
+        CU(c, klaunch(kg, ts, hash_dist_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, c->d_hash + base * c->hash_words,
+                      c->hash_words, (int)n, base > 0 ? 1 : 0, (double)(hp.hs * hp.hs), c->d_hdist + base));
         c->launches += 2;
         c->last_batch_base = base;
         c->last_batch_n = n;
     }
-    decide_kernel<<<5, 256, 0, ts>>>(c->dparams, c->d_state, c->d_cuts, c->d_cv, c->d_av, c->d_ratio, c->d_hdiff, c->d_avg,
-                                     c->d_hdist, c->first_frame, base, base + n);
-    CU(c, cudaGetLastError());
-    CU(c, cudaEventRecord(c->ev_fin[buf], ts));
-    c->fin_recorded[buf] = true;
+    CU(c, klaunch(kg, ts, decide_kernel, dim3(5), dim3(256), 0, c->dparams, c->d_state, c->d_cuts, c->d_cv, c->d_av, c->d_ratio,
+                  c->d_hdiff, c->d_avg, c->d_hdist, (long long)c->first_frame, (long long)base, (long long)(base + n), mailbox));
+    if (!inline_tail) {
+        CU(c, cudaEventRecord(c->ev_fin[buf], ts));
+        c->fin_recorded[buf] = true;
+    }
     c->launches++;
     c->n_frames += n;
     tr.lap("launch tail");
@@ -1098,6 +1142,10 @@ void esd_destroy(esd_ctx* c) {
     cudaFree(c->d_slab);
     for (int b = 0; b < 2; ++b) { cudaFree(c->d_part[b]); cudaFree(c->d_hist_part[b]); cudaFree(c->d_vplane[b]); if (c->ev_fin[b]) cudaEventDestroy(c->ev_fin[b]); }
     cudaFree(c->d_edge_bits); cudaFree(c->d_edge_prev);
+    c->kg.destroy();
+    if (c->pf_h) cudaFreeHost(c->pf_h);
+    if (c->pf_mailbox) cudaFreeHost(c->pf_mailbox);
+    if (c->pf_stream) cudaStreamDestroy(c->pf_stream);
     cudaFree(c->d_gplane[0]); cudaFree(c->d_gplane[1]); cudaFree(c->d_hash_small);
     cudaFree(c->d_hash_itab); cudaFree(c->d_hash_wtab); cudaFree(c->d_hash_C);
     if (c->order_event) cudaEventDestroy(c->order_event);
@@ -1479,6 +1527,75 @@ int esd_get_cuts(esd_ctx* c, int32_t detector, int64_t from_index, int64_t* cuts
     return ESD_OK;
 }
 
+int esd_process_frame_host(esd_ctx* c, const uint8_t* h_bgr, int64_t pitch, int64_t frame_num, int32_t detector,
+                           int64_t from_index, int64_t* cuts, int64_t cap, int64_t* n_written, int64_t* n_total) {
+    if (!c) return ESD_ERR_INVALID;
+    const int di = det_index(detector);
+    if (di < 0 || !(c->cfg.detectors & detector)) return fail(c, ESD_ERR_INVALID, "process_frame: detector %d not configured", detector);
+    if (!h_bgr) return fail(c, ESD_ERR_INVALID, "process_frame: null frame");
+    if (pitch < c->row_bytes) return fail(c, ESD_ERR_INVALID, "process_frame: pitch %lld < row bytes %d", (long long)pitch, c->row_bytes);
+    CU(c, cudaSetDevice(c->device));
+    const int H = c->cfg.src_height;
+    const size_t fb = (size_t)H * c->row_bytes;
+    if (!c->pf_stream) {
+        CU(c, cudaStreamCreateWithFlags(&c->pf_stream, cudaStreamNonBlocking));
+        CU(c, cudaHostAlloc(&c->pf_h, fb + 64, cudaHostAllocMapped));  // + slack: TMA copies are rounded up to 16 bytes
+        CU(c, cudaHostAlloc(&c->pf_mailbox, 8 * sizeof(long long), cudaHostAllocMapped));
+        memset(c->pf_mailbox, 0, 8 * sizeof(long long));
+    }
+    cudaStream_t st = c->pf_stream;
+    // work enqueued through another entry point may still be running its tail on the library stream
+    if (c->have_last_stream && c->last_stream != st) CU(c, cudaStreamSynchronize(c->aux_stream));
+    TraceTimer trp;
+    if (pitch == c->row_bytes) memcpy(c->pf_h, h_bgr, fb);
+    else for (int y = 0; y < H; ++y) memcpy(c->pf_h + (size_t)y * c->row_bytes, h_bgr + (size_t)y * pitch, (size_t)c->row_bytes);
+    // zero-copy: the fused kernel reads the pinned frame over PCIe (110 KB at detector resolution) and the decision
+    // kernel posts the cut counts into host-mapped memory, so the call is three kernel launches and one synchronise
+    trp.lap("pf stage memcpy");
+    c->h2d_bytes += (int64_t)fb;
+    c->h2d_copies++;
+    // The kernel sequence of a one-frame push is fixed once the adaptive window has filled, so it runs as a CUDA graph
+    // whose node parameters are refreshed per call (ESD_NO_GRAPH=1 keeps plain launches, for A/B timing).
+    static const bool no_graph = getenv("ESD_NO_GRAPH") != nullptr;
+    const int64_t warm = (c->cfg.detectors & ESD_DET_ADAPTIVE) ? 2LL * c->cfg.adaptive_window_width + 1 : 1;
+    const bool use_graph = !no_graph && !c->need_edges && !c->timing && c->started && c->n_frames >= warm;
+    KernelGraph& kg = c->kg;
+    int rc;
+    if (use_graph) {
+        if (!kg.exec) {
+            kg.destroy();
+            CU(c, cudaGraphCreate(&kg.graph, 0));
+            kg.mode = KernelGraph::BUILD;
+        } else {
+            kg.mode = KernelGraph::UPDATE;
+            kg.cursor = 0;
+        }
+        rc = push_common(c, c->pf_h, 1, (int64_t)fb, c->row_bytes, LAYOUT_FULL, frame_num, st, true, c->pf_mailbox);
+        const int mode = kg.mode;
+        kg.mode = KernelGraph::DIRECT;
+        if (rc) { kg.destroy(); return rc; }
+        if (mode == KernelGraph::BUILD) CU(c, cudaGraphInstantiate(&kg.exec, kg.graph, 0));
+        CU(c, cudaGraphLaunch(kg.exec, st));
+    } else {
+        rc = push_common(c, c->pf_h, 1, (int64_t)fb, c->row_bytes, LAYOUT_FULL, frame_num, st, true, c->pf_mailbox);
+        if (rc) return rc;
+    }
+    trp.lap("pf enqueue");
+    CU(c, cudaStreamSynchronize(st));
+    trp.lap("pf synchronize");
+    if (c->pf_mailbox[5]) return fail(c, ESD_ERR_CAPACITY, "cut list overflow (max_cuts = %lld)", (long long)c->max_cuts);
+    const int64_t total = c->pf_mailbox[di];
+    if (n_total) *n_total = total;
+    if (from_index < 0) from_index = 0;
+    const int64_t avail = std::max<int64_t>(0, total - from_index);
+    const int64_t m = std::min(avail, cap);
+    if (n_written) *n_written = m;
+    if (m > 0 && cuts)
+        CU(c, cudaMemcpy(cuts, c->d_cuts + (int64_t)di * c->max_cuts + from_index, sizeof(int64_t) * m, cudaMemcpyDeviceToHost));
+    if (avail > cap) return fail(c, ESD_ERR_CAPACITY, "process_frame: %lld cuts pending, buffer holds %lld", (long long)avail, (long long)cap);
+    return ESD_OK;
+}
+
 int esd_decide_arrays(esd_ctx* c, int32_t detector, int64_t first_frame_num, int64_t n, const double* scores,
                       double* adaptive_ratio_out, int64_t* cuts, int64_t cap, int64_t* n_cuts) {
     if (!c || !scores || n < 0) return ESD_ERR_INVALID;
@@ -1515,7 +1632,7 @@ int esd_decide_arrays(esd_ctx* c, int32_t detector, int64_t first_frame_num, int
             adaptive_ratio_kernel<<<(unsigned)((n - 2 * w + 255) / 256), 256>>>(d_scores, d_ratio, w, n - w, w,
                                                                                P.adaptive_min_content_val);
     }
-    decide_kernel<<<5, 256>>>(P, d_st, d_cuts, d_scores, d_scores, d_ratio, d_scores, d_scores, d_scores, first_frame_num, 0, n);
+    decide_kernel<<<5, 256>>>(P, d_st, d_cuts, d_scores, d_scores, d_ratio, d_scores, d_scores, d_scores, first_frame_num, 0, n, nullptr);
     c->launches += 3;
     CUD(cudaGetLastError());
     CUD(cudaDeviceSynchronize());

@@ -87,6 +87,21 @@ class SceneDetector:
         self._manager_ctx: Optional[capi.EsdContext] = None  # set by SceneManager while it drives this detector
         self._cuts_seen = 0
         self._device = 0
+        # deferred mode (see `defer`): frames staged on the host and scored `_defer` at a time
+        self._defer = 0
+        self._stage = None
+        self._stage_n = 0
+        self._stage_first = 0
+
+    def defer(self, frames: int) -> "SceneDetector":
+        """Opt-in deferred scoring for frame-by-frame callers: ``process_frame`` only stages the (host) frame and every
+        `frames` calls one batch is scored, so cuts are reported up to `frames` - 1 calls late (with their exact frame
+        numbers; ``event_buffer_length`` grows accordingly and ``post_process`` flushes the rest) -- the contract
+        PySceneDetect already gives detectors that look ahead, e.g. AdaptiveDetector.  0 / 1 = score every call."""
+        if self._stage_n:
+            raise RuntimeError("defer() must be called before frames are staged")
+        self._defer = max(0, int(frames))
+        return self
 
     # ---- PySceneDetect API
     def is_processing_required(self, frame_num: int) -> bool:
@@ -99,10 +114,13 @@ class SceneDetector:
         return []
 
     def post_process(self, frame_num: int) -> List[int]:
-        return []
+        return self._flush_staged()
 
     @property
     def event_buffer_length(self) -> int:
+        return self._own_buffer_length() + max(0, self._defer - 1)
+
+    def _own_buffer_length(self) -> int:
         return 0
 
     # ---- config plumbing shared with SceneManager
@@ -147,20 +165,61 @@ class SceneDetector:
         cuts, total = self._ctx.get_cuts(self._DET_FLAG, self._cuts_seen)
         self._cuts_seen = total
         if self.stats_manager is not None:
-            n = t.shape[0]
-            sc = self._ctx.read_scores(first_frame_num, n)
-            for k in range(n):
-                m = self._metrics_for(sc, k)
-                if m:
-                    self.stats_manager.set_metrics(first_frame_num + k, m)
-            self._publish_late_metrics(first_frame_num, n)
+            self._publish_metrics(first_frame_num, t.shape[0])
         return cuts
 
     def _publish_late_metrics(self, first_frame_num: int, n: int):
         pass
 
     def process_frame(self, frame_num: int, frame_img) -> List[int]:
-        return self.process_frames(frame_num, frame_img)
+        """PySceneDetect's per-frame entry point.  A numpy frame takes the library's single-call fast path
+        (esd_process_frame_host: pinned staging, one stream, one synchronisation); CUDA tensors and batches go
+        through ``process_frames``."""
+        if not isinstance(frame_img, np.ndarray) or frame_img.ndim != 3:
+            return self.process_frames(frame_num, frame_img)
+        self._validate_frame(frame_img)
+        if self._defer > 1:
+            return self._stage_frame(frame_num, frame_img)
+        if self._ctx is None:
+            self._ctx = self._make_ctx(frame_img.shape[1], frame_img.shape[0], self._device)
+        cuts, total = self._ctx.process_frame_host(frame_img, frame_num, self._DET_FLAG, self._cuts_seen)
+        self._cuts_seen = total
+        if self.stats_manager is not None:
+            self._publish_metrics(frame_num, 1)
+        return cuts
+
+    def _publish_metrics(self, first_frame_num: int, n: int):
+        sc = self._ctx.read_scores(first_frame_num, n)
+        for k in range(n):
+            m = self._metrics_for(sc, k)
+            if m:
+                self.stats_manager.set_metrics(first_frame_num + k, m)
+        self._publish_late_metrics(first_frame_num, n)
+
+    def _stage_frame(self, frame_num: int, frame_img: np.ndarray) -> List[int]:
+        import torch
+
+        if self._stage is None:
+            h, w, _ = frame_img.shape
+            self._stage = torch.empty((self._defer, h, w, 3), dtype=torch.uint8).pin_memory()
+            self._stage_np = self._stage.numpy()
+            self._stage_dev = torch.empty((self._defer, h, w, 3), dtype=torch.uint8, device=f"cuda:{self._device}")
+        if self._stage_n == 0:
+            self._stage_first = frame_num
+        elif frame_num != self._stage_first + self._stage_n:
+            raise ValueError("deferred process_frame needs sequential frame numbers")
+        np.copyto(self._stage_np[self._stage_n], frame_img)
+        self._stage_n += 1
+        return self._flush_staged() if self._stage_n == self._defer else []
+
+    def _flush_staged(self) -> List[int]:
+        n = self._stage_n
+        if n == 0:
+            return []
+        self._stage_n = 0
+        dev = self._stage_dev[:n]
+        dev.copy_(self._stage[:n], non_blocking=True)
+        return self.process_frames(self._stage_first, dev)
 
     def close(self):
         if self._ctx is not None:
@@ -266,8 +325,7 @@ class AdaptiveDetector(ContentDetector):
         self._adaptive_ratio_key = AdaptiveDetector.ADAPTIVE_RATIO_KEY_TEMPLATE.format(
             window_width=window_width, luma_only="" if not luma_only else "_lum")
 
-    @property
-    def event_buffer_length(self) -> int:
+    def _own_buffer_length(self) -> int:
         return self.window_width
 
     def get_metrics(self):
@@ -410,10 +468,11 @@ class ThresholdDetector(SceneDetector):
         cfg.thresh_method = int(self.method.value)
 
     def post_process(self, frame_num: int) -> List[int]:
+        cuts = self._flush_staged()
         ctx = self._ctx or self._manager_ctx
         if ctx is None:
-            return []
-        return ctx.post_process(capi.ESD_DET_THRESHOLD, frame_num)
+            return cuts
+        return cuts + ctx.post_process(capi.ESD_DET_THRESHOLD, frame_num)
 
     def _publish_late_metrics(self, first_frame_num: int, n: int):
         avg = self._ctx.read_average_rgb(first_frame_num, n)

@@ -156,6 +156,15 @@ ESD_API int esd_push_frames(esd_ctx* ctx, const uint8_t* d_bgr, int64_t n, int64
  * ascending source-row order) that the ingest ring produces. */
 ESD_API int esd_push_rows(esd_ctx* ctx, const uint8_t* d_rows, int64_t n, int64_t first_frame_num, void* stream);
 
+/* Replaces: one call of PySceneDetect's `SceneDetector.process_frame(frame_num, frame_img)` with a host (numpy) frame --
+ * the plugin surface the reference names (README.md:56; design.md:994-1007) as PySceneDetect's own SceneManager loop
+ * drives it, frame by frame.  The frame (src_width x src_height BGR, `pitch_bytes` per row; pageable or pinned) is
+ * staged through a library-owned pinned buffer, copied to the device, scored and decided on one library-owned stream
+ * with a single synchronisation; cuts [from_index, ...) of `detector` come back exactly like esd_get_cuts.  Frame
+ * numbers follow the same sequencing rule as esd_push_frames.  Synchronises. */
+ESD_API int esd_process_frame_host(esd_ctx* ctx, const uint8_t* h_bgr, int64_t pitch_bytes, int64_t frame_num, int32_t detector,
+                                   int64_t from_index, int64_t* cuts, int64_t cap, int64_t* n_written, int64_t* n_total);
+
 /* Replaces: the decoded-frame hand-off (`ffmpeg -i <path>` decode feeding the select filter, model_manager.py:736-745;
  * `cv2.VideoCapture.read()` in the other tasks, e.g. :237-263).  Decode itself stays outside.
  * Host frames -> pinned ring -> cudaMemcpyAsync on a copy stream -> scoring on the ctx's own

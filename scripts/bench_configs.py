@@ -257,8 +257,12 @@ def config_edges(dev, local, n=1024, steps=10):
     stream = torch.cuda.current_stream().cuda_stream
     for name, dets, auto in (("content", [ContentDetector()], True),
                              ("content+edges", [ContentDetector(weights=ContentDetector.Components(1.0, 1.0, 1.0, 1.0))], True),
+                             ("content+hash", "hash", True),
                              ("all4", None, True), ("content_noresize_1080p", [ContentDetector()], False)):
         sm = SceneManager(device=local, tuning={"initial_capacity": (steps + 4) * n})
+        if dets == "hash":
+            from eioku_b200.detectors import HashDetector
+            dets = [ContentDetector(), HashDetector()]
         if dets is None:
             from eioku_b200.detectors import ThresholdDetector
             dets = [ContentDetector(), AdaptiveDetector(), HistogramDetector(), ThresholdDetector()]
@@ -290,6 +294,19 @@ def config_edges(dev, local, n=1024, steps=10):
         det.process_frame(k, small[k])
     out["process_frame_latency_us"] = (time.perf_counter() - t0) / 280 * 1e6
     det.close()
+    # the same surface with host (numpy) frames, as PySceneDetect's SceneManager loop calls it: strict and deferred
+    small_np = small.cpu().numpy()
+    for label, mk in (("content", lambda: ContentDetector()), ("content_defer64", lambda: ContentDetector().defer(64)),
+                      ("adaptive", lambda: AdaptiveDetector()), ("hist", lambda: HistogramDetector())):
+        det = mk()
+        for k in range(64):
+            det.process_frame(k, small_np[k])
+        t0 = time.perf_counter()
+        for k in range(64, 300):
+            det.process_frame(k, small_np[k])
+        det.post_process(299)
+        out[f"process_frame_numpy_{label}_us"] = (time.perf_counter() - t0) / 236 * 1e6
+        det.close()
     return out
 
 
