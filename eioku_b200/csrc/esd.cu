@@ -176,6 +176,8 @@ struct esd_ctx {
     int edge_ksize = 0, edge_words = 0;
     HashParams hparams{};          // perceptual hash geometry + device tables
     int hash_words = 0;
+    size_t hash_smem = 0;
+    void (*hash_fn)(const uint8_t*, int, HashParams, uint8_t*, uint32_t*) = nullptr;
     int* d_hash_itab = nullptr;    // area-resize tables: x begin, y begin, x src, y src (one allocation)
     float* d_hash_wtab = nullptr;  // x weights, y weights
     double* d_hash_C = nullptr;    // [hash_size][S] DCT rows
@@ -494,7 +496,7 @@ int ensure_scratch(esd_ctx* c, int64_t n) {
         c->d_vplane[b] = nullptr;
         c->fin_recorded[b] = false;
         if (c->need_edges) CU(c, cudaMalloc(&c->d_vplane[b], (size_t)n * c->dst_w * c->dst_h));
-        if (c->need_hash) CU(c, cudaMalloc(&c->d_gplane[b], (size_t)n * c->dst_w * c->dst_h));
+        if (c->need_hash) CU(c, cudaMalloc(&c->d_gplane[b], (size_t)n * c->dst_w * c->dst_h + 16));  // + slack: word loads
         if (c->need_content) CU(c, cudaMalloc(&c->d_part[b], sizeof(uint4) * n * c->n_groups * kConsumerWarps));
         if (c->need_hist) CU(c, cudaMalloc(&c->d_hist_part[b], sizeof(uint16_t) * n * c->n_groups * c->cfg.hist_bins));
     }
@@ -711,8 +713,8 @@ int push_common(esd_ctx* c, const uint8_t* d_src, int64_t n, int64_t frame_strid
     }
     if (c->need_hash) {
         const HashParams& hp = c->hparams;
-        const size_t hsmem = sizeof(float) * hp.S * hp.S + sizeof(double) * hp.hs * hp.S + sizeof(float) * hp.hs * hp.hs;
-        CU(c, klaunch(kg, ts, hash_kernel, dim3((unsigned)n), dim3(kHashThreads), hsmem, c->d_gplane[buf], hp, c->d_hash_small,
+        const size_t hsmem = c->hash_smem;
+        CU(c, klaunch(kg, ts, c->hash_fn, dim3((unsigned)n), dim3(kHashThreads), hsmem, c->d_gplane[buf], (int)n, hp, c->d_hash_small,
                       c->d_hash + base * c->hash_words));
         CU(c, klaunch(kg, ts, hash_dist_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, c->d_hash + base * c->hash_words,
                       c->hash_words, (int)n, base > 0 ? 1 : 0, (double)(hp.hs * hp.hs), c->d_hdist + base));
@@ -942,23 +944,57 @@ int esd_create(esd_ctx** out, const esd_config* cfg, int device) {
         std::vector<float> xw, yw;
         area_tab(dw, hp.S, xb, xs, xw);
         area_tab(dh, hp.S, yb, ys, yw);
+        for (int d = 0; d < hp.S; ++d)  // hash_kernel walks the taps of a destination column as consecutive pixels
+            for (int k = xb[d] + 1; k < xb[d + 1]; ++k)
+                if (xs[k] != xs[k - 1] + 1) {
+                    fail(c, ESD_ERR_UNSUPPORTED, "hash: non-contiguous area-resize taps for %d -> %d", dw, hp.S);
+                    return bail(ESD_ERR_UNSUPPORTED);
+                }
+        // horizontal pass as an exact integer sum: the fast path, or one power-of-two weight everywhere (e.g. 256 -> 32)
+        bool uniform = true;
+        for (float v : xw) uniform = uniform && v == xw[0];
+        int expo = 0;
+        const bool pow2 = uniform && frexpf(xw[0], &expo) == 0.5f;
+        hp.xsum_int = (hp.fast || pow2) ? 1 : 0;
+        hp.xalpha = xw[0];
+        // aligned-words variant: uniform tap count, a multiple of 4 bytes, every tap run on a 4-byte boundary of the plane
+        hp.xwords = 0;
+        if (hp.xsum_int && dw % 4 == 0 && ((int64_t)dw * dh) % 4 == 0) {
+            const int cnt = xb[1] - xb[0];
+            bool ok = cnt % 4 == 0 && cnt / 4 >= 1 && cnt / 4 <= 4;
+            for (int d = 0; d < hp.S && ok; ++d) ok = (xb[d + 1] - xb[d] == cnt) && (xs[xb[d]] % 4 == 0);
+            if (ok) hp.xwords = cnt / 4;
+        }
+        hp.n_xent = (int)xs.size();
+        hp.n_yent = (int)ys.size();
+        // band buffer of the area resize: at least the source rows of one destination row
+        int need = 1;
+        for (int d = 0; d < hp.S; ++d) need = std::max(need, ys[yb[d + 1] - 1] - ys[yb[d]] + 1);
+        hp.band_rows = std::min(dh, std::max(need, (12 * 1024) / (hp.S * 4)));  // 12 KB: keeps eight CTAs per SM resident
+        std::vector<int> bands;  // {dy0, dy1, r0, nrows}
+        for (int dy0 = 0; dy0 < hp.S;) {
+            const int r0 = ys[yb[dy0]];
+            int dy1 = dy0 + 1;
+            while (dy1 < hp.S && ys[yb[dy1 + 1] - 1] - r0 + 1 <= hp.band_rows) ++dy1;
+            bands.insert(bands.end(), {dy0, dy1, r0, ys[yb[dy1] - 1] - r0 + 1});
+            dy0 = dy1;
+        }
+        hp.n_bands = (int)bands.size() / 4;
         std::vector<int> itab;
         itab.insert(itab.end(), xb.begin(), xb.end());
+        for (int d = 0; d < hp.S; ++d) itab.push_back(xs[xb[d]]);
         itab.insert(itab.end(), yb.begin(), yb.end());
-        itab.insert(itab.end(), xs.begin(), xs.end());
         itab.insert(itab.end(), ys.begin(), ys.end());
+        while (itab.size() % 4) itab.push_back(0);
+        itab.insert(itab.end(), bands.begin(), bands.end());
         std::vector<float> wtab(xw);
         wtab.insert(wtab.end(), yw.begin(), yw.end());
         CUB(cudaMalloc(&c->d_hash_itab, sizeof(int) * itab.size()));
         CUB(cudaMemcpy(c->d_hash_itab, itab.data(), sizeof(int) * itab.size(), cudaMemcpyHostToDevice));
         CUB(cudaMalloc(&c->d_hash_wtab, sizeof(float) * wtab.size()));
         CUB(cudaMemcpy(c->d_hash_wtab, wtab.data(), sizeof(float) * wtab.size(), cudaMemcpyHostToDevice));
-        hp.ax.begin = c->d_hash_itab;
-        hp.ay.begin = hp.ax.begin + xb.size();
-        hp.ax.src = hp.ay.begin + yb.size();
-        hp.ay.src = hp.ax.src + xs.size();
-        hp.ax.w = c->d_hash_wtab;
-        hp.ay.w = hp.ax.w + xw.size();
+        hp.itab = c->d_hash_itab;
+        hp.wtab = c->d_hash_wtab;
         // orthonormal DCT-II rows 0..hs-1 of size S
         std::vector<double> Cm((size_t)hp.hs * hp.S);
         const double pi = 3.14159265358979323846;
@@ -968,6 +1004,19 @@ int esd_create(esd_ctx** out, const esd_config* cfg, int device) {
         CUB(cudaMalloc(&c->d_hash_C, sizeof(double) * Cm.size()));
         CUB(cudaMemcpy(c->d_hash_C, Cm.data(), sizeof(double) * Cm.size(), cudaMemcpyHostToDevice));
         hp.C = c->d_hash_C;
+        {   // shared-memory carve-up of hash_kernel
+            const size_t region = std::max<size_t>(sizeof(float) * hp.band_rows * hp.S,
+                                                   sizeof(double) * hp.hs * hp.S + sizeof(uint32_t) * hp.hs * hp.hs);
+            c->hash_smem = sizeof(double) * hp.hs * hp.S + sizeof(float) * hp.S * hp.S + ((region + 7) & ~(size_t)7) +
+                           sizeof(float) * (hp.n_xent + hp.n_yent) + sizeof(int) * (3 * hp.S + 2 + hp.n_yent) + 16;
+        }
+        if (c->hash_smem + 2048 > prop.sharedMemPerBlockOptin) {
+            fail(c, ESD_ERR_UNSUPPORTED, "hash: frame too large for the shared-memory tables of the area resize (%zu bytes)", c->hash_smem);
+            return bail(ESD_ERR_UNSUPPORTED);
+        }
+        c->hash_fn = hp.xwords == 1 ? hash_kernel<1> : hp.xwords == 2 ? hash_kernel<2> : hp.xwords == 3 ? hash_kernel<3>
+                   : hp.xwords == 4 ? hash_kernel<4> : hash_kernel<0>;
+        CUB(cudaFuncSetAttribute(c->hash_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->hash_smem));
     }
     if (dw > kConsumers * (c->resize ? 4 : 16)) {
         fail(c, ESD_ERR_UNSUPPORTED, "destination width %d too large (max %d)", dw, kConsumers * (c->resize ? 4 : 16));

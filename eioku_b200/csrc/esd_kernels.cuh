@@ -871,104 +871,250 @@ __global__ void edge_delta_kernel(const uint32_t* __restrict__ bitmaps, const ui
 //   DCT-II of x, low-frequency hs x hs block, evaluated in float64 and narrowed to float32.  cv2.dct's own float32
 //       rounding is build-dependent (its IPP and plain paths differ by 1-2 ulp), so this stage is tolerance-parity.
 //   bits = coefficient > numpy.median(block)   (float32; even count: (a + b) / 2 in float32)
-struct AreaAxis {      // computeResizeAreaTab for one axis, grouped per destination index
-    const int* begin;  // [S + 1]
-    const int* src;    // source index per entry
-    const float* w;    // float32 weight per entry
-};
 struct HashParams {
-    int w, h;        // detector-resolution frame
-    int S, hs;       // DCT size (hash_size * lowpass) and hash size
-    int fast;        // both scales integral
-    int isx, isy;    // integral scales (fast path)
+    int w, h;          // detector-resolution frame
+    int S, hs;         // DCT size (hash_size * lowpass) and hash size
+    int fast;          // both scales integral (ResizeAreaFast_)
+    int isx, isy;      // integral scales (fast path)
     float fast_scale;  // float32(1 / (isx * isy))
-    AreaAxis ax, ay;
+    int xsum_int;      // horizontal pass as an exact integer byte sum: fast path, or every x weight is the same power of two
+    int xwords;        // > 0: every column sums 4 * xwords bytes from a 4-byte boundary (hash_kernel<WORDS>)
+    float xalpha;      // that weight
+    int n_xent, n_yent, n_bands;
+    // computeResizeAreaTab tables, grouped per destination index, in one block each (staged into shared memory):
+    const int* itab;   // xb[S + 1] | xs0[S] (first source column) | yb[S + 1] | ysrc[n_yent] | bands[n_bands] {dy0, dy1, r0, nrows}
+    const float* wtab; // xw[n_xent] | yw[n_yent]
     const double* C;   // [hs][S] orthonormal DCT-II rows
     int words;         // ceil(hs * hs / 32)
+    int band_rows;     // source rows of horizontal sums the shared-memory band buffer holds
 };
 constexpr int kHashThreads = 256;
 
-__global__ void __launch_bounds__(kHashThreads) hash_kernel(const uint8_t* __restrict__ gplane, HashParams P,
+// order-preserving float -> uint key (for the radix select of the median)
+__device__ __forceinline__ uint32_t float_key(float f) {
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_float(uint32_t k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+// k-th smallest (0-based) of keys[0..n) by 4 passes of an 8-bit radix histogram.  All threads of the CTA call it;
+// hist is 256 words of shared memory, sel two more.  Returns the key to every thread.
+__device__ uint32_t block_radix_select(const uint32_t* __restrict__ keys, int n, int k, uint32_t* hist, uint32_t* sel) {
+    const int tid = threadIdx.x;
+    uint32_t prefix = 0, mask = 0;
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        hist[tid] = 0;  // kHashThreads == 256 bins
+        __syncthreads();
+        for (int i = tid; i < n; i += kHashThreads) {
+            const uint32_t key = keys[i];
+            if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (tid < 32) {
+            uint32_t b[8], s = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { b[q] = hist[8 * tid + q]; s += b[q]; }
+            uint32_t incl = s;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (tid >= o) incl += t;
+            }
+            uint32_t cum = incl - s;
+            if ((uint32_t)k >= cum && (uint32_t)k < incl) {  // exactly one lane
+                int q = 0;
+                while (cum + b[q] <= (uint32_t)k) { cum += b[q]; ++q; }
+                sel[0] = (uint32_t)(8 * tid + q);
+                sel[1] = (uint32_t)k - cum;
+            }
+        }
+        __syncthreads();
+        prefix |= sel[0] << shift;
+        mask |= 0xffu << shift;
+        k = (int)sel[1];
+    }
+    return prefix;
+}
+
+// Persistent over frames (grid-stride), tables staged once per CTA.  Shared memory:
+//   C[hs*S] f64 | xd[S*S] f32 | union { hrow[band_rows][S] f32 (area resize) ; T[hs*S] f64 + keys[hs*hs] u32 } | wtab f32 | itab i32
+// WORDS > 0: every destination column sums exactly 4 * WORDS bytes starting on a 4-byte boundary (e.g. 256 -> 32 columns:
+// 8 bytes), so the horizontal pass is WORDS aligned word loads and DP4As; WORDS == 0 is the general code.
+template <int WORDS>
+__global__ void __launch_bounds__(kHashThreads, 8) hash_kernel(const uint8_t* __restrict__ gplane, int n_frames, HashParams P,
                                                             uint8_t* __restrict__ small_out, uint32_t* __restrict__ bits_out) {
     extern __shared__ __align__(16) uint8_t hsm[];
     const int S = P.S, hs = P.hs, N = hs * hs;
-    float* x = reinterpret_cast<float*>(hsm);                         // [S * S]
-    double* T = reinterpret_cast<double*>(hsm + sizeof(float) * S * S);  // [hs * S]   (S * S is even -> 8-byte aligned)
-    float* coef = reinterpret_cast<float*>(T + hs * S);               // [N]
+    double* Cs = reinterpret_cast<double*>(hsm);                // [hs * S]
+    float* xd = reinterpret_cast<float*>(Cs + hs * S);          // [S * S] normalised thumbnail (S * S is even)
+    uint8_t* region = reinterpret_cast<uint8_t*>(xd + S * S);
+    const size_t region_bytes = max((size_t)P.band_rows * S * sizeof(float), (size_t)hs * S * sizeof(double) + (size_t)N * sizeof(uint32_t));
+    float* hrow = reinterpret_cast<float*>(region);             // [band_rows][S] horizontal sums
+    double* T = reinterpret_cast<double*>(region);              // [hs * S]
+    uint32_t* keys = reinterpret_cast<uint32_t*>(T + hs * S);   // [N] order-preserving coefficient keys
+    float* s_xw = reinterpret_cast<float*>(region + ((region_bytes + 7) & ~(size_t)7));  // [n_xent]
+    float* s_yw = s_xw + P.n_xent;                              // [n_yent]
+    int* s_xb = reinterpret_cast<int*>(s_yw + P.n_yent);        // [S + 1]
+    int* s_xs0 = s_xb + S + 1;                                  // [S]
+    int* s_yb = s_xs0 + S;                                      // [S + 1]
+    int* s_ysrc = s_yb + S + 1;                                 // [n_yent]
+    __shared__ uint32_t s_hist[256];
+    __shared__ uint32_t s_sel[2];
     __shared__ int s_max;
-    __shared__ float s_lo, s_hi;
+    __shared__ uint32_t s_cnt, s_min;
     const int tid = threadIdx.x;
-    const uint8_t* g = gplane + (size_t)blockIdx.x * P.w * P.h;
-    if (tid == 0) s_max = 0;
-    __syncthreads();
-    int vmax = 0;
-    for (int p = tid; p < S * S; p += kHashThreads) {
-        const int dy = p / S, dx = p - dy * S;
-        int v;
-        if (P.fast) {
-            int sum = 0;
-            for (int yy = 0; yy < P.isy; ++yy) {
-                const uint8_t* row = g + (size_t)(dy * P.isy + yy) * P.w + dx * P.isx;
-                for (int xx = 0; xx < P.isx; ++xx) sum += row[xx];
+    const int n_itab = 3 * S + 2 + P.n_yent;
+    for (int i = tid; i < n_itab; i += kHashThreads) s_xb[i] = P.itab[i];
+    for (int i = tid; i < P.n_xent + P.n_yent; i += kHashThreads) s_xw[i] = P.wtab[i];
+    for (int i = tid; i < hs * S; i += kHashThreads) Cs[i] = P.C[i];
+    const int4* bands = reinterpret_cast<const int4*>(P.itab + ((n_itab + 3) & ~3));  // a few uniform loads per frame
+
+    for (int f = blockIdx.x; f < n_frames; f += gridDim.x) {
+        const uint8_t* g = gplane + (size_t)f * P.w * P.h;
+        __syncthreads();  // tables staged / previous frame done with every buffer
+        if (tid == 0) { s_max = 0; s_cnt = 0; s_min = 0xffffffffu; }
+        // ---- INTER_AREA, separable exactly like OpenCV: per source row the horizontal sums (phase 1), then the
+        //      vertical combination per destination pixel (phase 2), in bands of destination rows whose source rows fit
+        //      the shared-memory buffer.
+        int vmax = 0;
+        for (int bi = 0; bi < P.n_bands; ++bi) {
+            const int4 band = bands[bi];  // {dy0, dy1, r0, nrows}
+            const int r0 = band.z;
+            if (bi > 0) __syncthreads();  // previous band's phase 2 is done with hrow
+            {
+                PixelWalk pw(tid, kHashThreads, S);
+                for (int it = tid; it < band.w * S; it += kHashThreads, pw.next()) {
+                    const int dx = pw.x;
+                    const int xb = s_xb[dx], cnt = s_xb[dx + 1] - xb;
+                    const uint8_t* px = g + (size_t)(r0 + pw.y) * P.w + s_xs0[dx];  // the taps of a column are consecutive pixels
+                    if (WORDS > 0) {
+                        const uint32_t* wp = reinterpret_cast<const uint32_t*>(px);
+                        uint32_t sum = 0;
+#pragma unroll
+                        for (int j = 0; j < WORDS; ++j) sum = __dp4a(wp[j], 0x01010101u, sum);
+                        hrow[it] = P.fast ? __uint_as_float(sum) : __fmul_rn((float)sum, P.xalpha);
+                    } else if (P.xsum_int) {
+                        // exact integer sum of cnt bytes at any alignment: masked words through DP4A
+                        const uintptr_t a = reinterpret_cast<uintptr_t>(px);
+                        const uint32_t* wp = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+                        const int lead = (int)(a & 3), total = lead + cnt, nw = (total + 3) >> 2;
+                        uint32_t sum = 0;
+                        for (int j = 0; j < nw; ++j) {
+                            uint32_t word = wp[j];
+                            if (j == 0) word &= 0xffffffffu << (8 * lead);
+                            if (j == nw - 1 && (total & 3)) word &= 0xffffffffu >> (8 * (4 - (total & 3)));
+                            sum = __dp4a(word, 0x01010101u, sum);
+                        }
+                        // fast path keeps the integer; otherwise sum * 2^-k equals the float accumulation exactly
+                        hrow[it] = P.fast ? __uint_as_float(sum) : __fmul_rn((float)sum, P.xalpha);
+                    } else {
+                        float buf = 0.f;
+                        for (int k = 0; k < cnt; ++k) buf = __fadd_rn(buf, __fmul_rn((float)px[k], s_xw[xb + k]));
+                        hrow[it] = buf;
+                    }
+                }
             }
-            if (P.isx == 2 && P.isy == 2) v = (sum + 2) >> 2;
-            else v = min(255, max(0, __float2int_rn(__fmul_rn((float)sum, P.fast_scale))));
-        } else {
-            float sum = 0.f;
-            const int xb = P.ax.begin[dx], xe = P.ax.begin[dx + 1];
-            for (int ky = P.ay.begin[dy]; ky < P.ay.begin[dy + 1]; ++ky) {
-                const uint8_t* row = g + (size_t)P.ay.src[ky] * P.w;
-                float buf = 0.f;
-                for (int kx = xb; kx < xe; ++kx) buf = __fadd_rn(buf, __fmul_rn((float)row[P.ax.src[kx]], P.ax.w[kx]));
-                const float t = __fmul_rn(P.ay.w[ky], buf);
-                sum = (ky == P.ay.begin[dy]) ? t : __fadd_rn(sum, t);
+            __syncthreads();
+            {
+                const int first = band.x * S + tid;
+                PixelWalk pw(first, kHashThreads, S);
+                for (int p = first; p < band.y * S; p += kHashThreads, pw.next()) {
+                    const int dx = pw.x, dy = pw.y;
+                    const int yb = s_yb[dy], ye = s_yb[dy + 1];
+                    int v;
+                    if (P.fast) {
+                        int sum = 0;
+                        for (int ky = yb; ky < ye; ++ky) sum += __float_as_int(hrow[(s_ysrc[ky] - r0) * S + dx]);
+                        if (P.isx == 2 && P.isy == 2) v = (sum + 2) >> 2;
+                        else v = min(255, max(0, __float2int_rn(__fmul_rn((float)sum, P.fast_scale))));
+                    } else {
+                        float sum = 0.f;
+                        for (int ky = yb; ky < ye; ++ky) {
+                            const float t = __fmul_rn(s_yw[ky], hrow[(s_ysrc[ky] - r0) * S + dx]);
+                            sum = (ky == yb) ? t : __fadd_rn(sum, t);
+                        }
+                        v = min(255, max(0, __float2int_rn(sum)));
+                    }
+                    xd[p] = (float)v;
+                    vmax = max(vmax, v);
+                    if (small_out) small_out[(size_t)f * S * S + p] = (uint8_t)v;
+                }
             }
-            v = min(255, max(0, __float2int_rn(sum)));
         }
-        x[p] = (float)v;
-        vmax = max(vmax, v);
-        if (small_out) small_out[(size_t)blockIdx.x * S * S + p] = (uint8_t)v;
-    }
-    vmax = __reduce_max_sync(0xffffffffu, vmax);
-    if ((tid & 31) == 0) atomicMax(&s_max, vmax);
-    __syncthreads();
-    const float fmax_v = (float)(s_max == 0 ? 1 : s_max);
-    for (int p = tid; p < S * S; p += kHashThreads) x[p] = __fdiv_rn(x[p], fmax_v);
-    __syncthreads();
-    // T = C[:hs] . x   then   D = T . C[:hs]^T
-    for (int idx = tid; idx < hs * S; idx += kHashThreads) {
-        const int u = idx / S, j = idx - u * S;
-        double acc = 0.0;
-        for (int i = 0; i < S; ++i) acc = fma(P.C[u * S + i], (double)x[i * S + j], acc);
-        T[idx] = acc;
-    }
-    __syncthreads();
-    for (int idx = tid; idx < N; idx += kHashThreads) {
-        const int u = idx / hs, v = idx - u * hs;
-        double acc = 0.0;
-        for (int j = 0; j < S; ++j) acc = fma(T[u * S + j], P.C[v * S + j], acc);
-        coef[idx] = (float)acc;
-    }
-    __syncthreads();
-    // numpy.median: rank every coefficient (ties broken by index), pick the middle one(s)
-    const int k_lo = (N - 1) / 2, k_hi = N / 2;
-    for (int idx = tid; idx < N; idx += kHashThreads) {
-        const float c = coef[idx];
-        int rank = 0;
-        for (int k = 0; k < N; ++k) {
-            const float o = coef[k];
-            rank += (o < c || (o == c && k < idx)) ? 1 : 0;
+        vmax = __reduce_max_sync(0xffffffffu, vmax);
+        if ((tid & 31) == 0) atomicMax(&s_max, vmax);
+        __syncthreads();
+        const float fmax_v = (float)(s_max == 0 ? 1 : s_max);
+        for (int p = tid; p < S * S; p += kHashThreads) xd[p] = __fdiv_rn(xd[p], fmax_v);
+        __syncthreads();
+        // ---- T = C[:hs] . x   then   D = T . C[:hs]^T   (float64, narrowed to float32 at the end)
+        {
+            PixelWalk pw(tid, kHashThreads, S);
+            for (int idx = tid; idx < hs * S; idx += kHashThreads, pw.next()) {
+                const double* cu = Cs + pw.y * S;
+                const float* xj = xd + pw.x;
+                double acc = 0.0;
+#pragma unroll 8
+                for (int i = 0; i < S; ++i) acc = fma(cu[i], (double)xj[i * S], acc);
+                T[idx] = acc;
+            }
         }
-        if (rank == k_lo) s_lo = c;
-        if (rank == k_hi) s_hi = c;
-    }
-    __syncthreads();
-    const float med = (k_lo == k_hi) ? s_lo : __fmul_rn(__fadd_rn(s_lo, s_hi), 0.5f);
-    for (int base = 0; base < P.words * 32; base += kHashThreads) {
-        const int idx = base + tid;
-        const bool bit = idx < N && coef[idx] > med;
-        const uint32_t word = __ballot_sync(0xffffffffu, bit);
-        if ((tid & 31) == 0 && (idx >> 5) < P.words) bits_out[(size_t)blockIdx.x * P.words + (idx >> 5)] = word;
+        __syncthreads();
+        float mine[4];  // this thread's coefficients (N <= 1024)
+        {
+            PixelWalk pw(tid, kHashThreads, hs);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int idx = q * kHashThreads + tid;
+                mine[q] = 0.f;
+                if (idx < N) {
+                    const double* tu = T + pw.y * S;
+                    const double* cv = Cs + pw.x * S;
+                    double acc = 0.0;
+#pragma unroll 8
+                    for (int j = 0; j < S; ++j) acc = fma(tu[j], cv[j], acc);
+                    mine[q] = (float)acc;
+                }
+                pw.next();
+            }
+        }
+        __syncthreads();  // every T read is done before keys (behind T) and the next frame's hrow are written
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int idx = q * kHashThreads + tid;
+            if (idx < N) keys[idx] = float_key(mine[q]);
+        }
+        __syncthreads();
+        // ---- numpy.median: the middle element, or the float32 mean of the two middle elements
+        const int k_lo = (N - 1) / 2, k_hi = N / 2;
+        const uint32_t key_lo = block_radix_select(keys, N, k_lo, s_hist, s_sel);
+        float med = key_float(key_lo);
+        if (k_hi != k_lo) {
+            // the next order statistic: key_lo again if it occurs often enough, else the smallest key above it
+            uint32_t cnt = 0, mn = 0xffffffffu;
+            for (int i = tid; i < N; i += kHashThreads) {
+                const uint32_t key = keys[i];
+                cnt += key <= key_lo ? 1u : 0u;
+                if (key > key_lo) mn = min(mn, key);
+            }
+            cnt = __reduce_add_sync(0xffffffffu, cnt);
+            mn = __reduce_min_sync(0xffffffffu, mn);
+            if ((tid & 31) == 0) { atomicAdd(&s_cnt, cnt); atomicMin(&s_min, mn); }
+            __syncthreads();
+            const float hi = (s_cnt > (uint32_t)k_hi) ? med : key_float(s_min);
+            med = __fmul_rn(__fadd_rn(med, hi), 0.5f);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int idx = q * kHashThreads + tid;
+            if (q * kHashThreads < P.words * 32) {  // uniform per iteration: whole warps vote
+                const bool bit = idx < N && mine[q] > med;
+                const uint32_t word = __ballot_sync(0xffffffffu, bit);
+                if ((tid & 31) == 0 && (idx >> 5) < P.words) bits_out[(size_t)f * P.words + (idx >> 5)] = word;
+            }
+        }
     }
 }
 
