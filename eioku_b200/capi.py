@@ -17,12 +17,13 @@ ESD_THRESH_FLOOR, ESD_THRESH_CEILING = 0, 1
 ESD_FILTER_MERGE, ESD_FILTER_SUPPRESS = 0, 1
 ESD_DOWNSCALE_FLOAT, ESD_DOWNSCALE_INT = 0, 1
 ESD_SPLIT_AUTO, ESD_SPLIT_STRIPS, ESD_SPLIT_CHUNKS = 0, 1, 2
+ESD_FMT_BGR24, ESD_FMT_NV12 = 0, 1
 
 # every symbol include/esd.h declares (tests check that the library exports all of them)
 EXPORTED_SYMBOLS = (
     "esd_abi_version", "esd_strerror", "esd_last_error", "esd_device_count", "esd_config_default",
     "esd_create", "esd_destroy", "esd_reset", "esd_get_geometry", "esd_get_touched_rows",
-    "esd_push_frames", "esd_push_rows", "esd_ingest_open", "esd_ingest_push_host", "esd_ingest_close", "esd_ingest_set_gather",
+    "esd_push_frames", "esd_push_nv12", "esd_push_rows", "esd_ingest_open", "esd_ingest_push_host", "esd_ingest_close", "esd_ingest_set_gather",
     "esd_ingest_stats", "esd_synchronize", "esd_join", "esd_frames_pushed", "esd_read_scores", "esd_read_edge_counts", "esd_read_average_rgb",
     "esd_read_hash", "esd_debug_read_hash_input", "esd_process_frame_host",
     "esd_post_process", "esd_get_cuts",
@@ -35,7 +36,7 @@ class EsdConfig(C.Structure):
         ("struct_size", C.c_uint32), ("detectors", C.c_int32),
         ("src_width", C.c_int32), ("src_height", C.c_int32),
         ("dst_width", C.c_int32), ("dst_height", C.c_int32),
-        ("downscale_mode", C.c_int32), ("reserved0", C.c_int32),
+        ("downscale_mode", C.c_int32), ("src_format", C.c_int32),
         ("content_threshold", C.c_double), ("content_weights", C.c_double * 4),
         ("content_weight_div", C.c_double),
         ("content_min_scene_len", C.c_int32), ("content_filter_mode", C.c_int32),
@@ -100,6 +101,7 @@ def load_library(path: Optional[str] = None):
     L.esd_get_touched_rows.argtypes = [vp, vp, i32]
     L.esd_push_frames.argtypes = [vp, vp, i64, i64, i64, i64, vp]
     L.esd_push_rows.argtypes = [vp, vp, i64, i64, vp]
+    L.esd_push_nv12.argtypes = [vp, vp, vp, i64, i64, i64, i64, vp]
     L.esd_ingest_open.argtypes = [vp, i32, i32]
     L.esd_ingest_push_host.argtypes = [vp, vp, i64, i64, i64, i64]
     L.esd_ingest_close.argtypes = [vp]
@@ -226,6 +228,45 @@ class EsdContext:
             stream = torch.cuda.current_stream(frames.device).cuda_stream
         fs = frames.stride(0) if n > 1 else frames.stride(1) * h
         self.push_device(frames.data_ptr(), n, fs, frames.stride(1), first_frame_num, stream)
+
+    def push_nv12_device(self, y_ptr: int, uv_ptr: int, n: int, frame_stride: int, pitch: int, first_frame_num: int, stream: int = 0):
+        self._check(self._L.esd_push_nv12(self._h, C.c_void_p(y_ptr), C.c_void_p(uv_ptr), n, frame_stride, pitch, first_frame_num,
+                                          C.c_void_p(stream)), "esd_push_nv12")
+
+    def _check_nv12_shape(self, n_rows: int, w: int):
+        W, H = self.cfg.src_width, self.cfg.src_height
+        if self.cfg.src_format != ESD_FMT_NV12:
+            raise ValueError("context was not created with src_format = ESD_FMT_NV12")
+        if (w, n_rows) != (W, H * 3 // 2):
+            raise ValueError(f"NV12 frames must be [N, {H * 3 // 2}, {W}] (Y plane then interleaved UV), got [.., {n_rows}, {w}]")
+
+    def push_nv12_tensor(self, frames, first_frame_num: int, stream: Optional[int] = None):
+        """frames: torch.uint8 CUDA tensor [N, H*3/2, W] -- contiguous NV12 frames (rows dense, any row pitch)."""
+        import torch
+
+        if frames.dim() == 2:
+            frames = frames.unsqueeze(0)
+        if frames.dtype != torch.uint8 or not frames.is_cuda:
+            raise ValueError("push_nv12_tensor needs a CUDA uint8 tensor")
+        if frames.stride(2) != 1:
+            frames = frames.contiguous()
+        n, rows, w = frames.shape
+        self._check_nv12_shape(rows, w)
+        if stream is None:
+            stream = torch.cuda.current_stream(frames.device).cuda_stream
+        fs = frames.stride(0) if n > 1 else frames.stride(1) * rows
+        self.push_device(frames.data_ptr(), n, fs, frames.stride(1), first_frame_num, stream)
+
+    def ingest_push_nv12_numpy(self, frames: np.ndarray, first_frame_num: int):
+        """Host NV12 frames [N, H*3/2, W] through the ingest ring (touched Y and UV rows only cross PCIe)."""
+        if frames.ndim == 2:
+            frames = frames[None]
+        if frames.dtype != np.uint8 or frames.strides[2] != 1:
+            frames = np.ascontiguousarray(frames, np.uint8)
+        n, rows, w = frames.shape
+        self._check_nv12_shape(rows, w)
+        fs = frames.strides[0] if n > 1 else frames.strides[1] * rows
+        self.ingest_push_host(frames.ctypes.data, n, fs, frames.strides[1], first_frame_num)
 
     def push_rows_device(self, data_ptr: int, n: int, first_frame_num: int, stream: int = 0):
         self._check(self._L.esd_push_rows(self._h, C.c_void_p(data_ptr), n, first_frame_num, C.c_void_p(stream)),

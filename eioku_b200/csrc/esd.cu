@@ -167,6 +167,9 @@ struct esd_ctx {
     // geometry
     int dst_w = 0, dst_h = 0, row_bytes = 0;
     int alg_row_bytes = 0;  // 32-byte sectors of a row that contain a horizontal tap, in bytes
+    int64_t alg_frame_bytes = 0;  // sum over the touched rows (NV12: Y rows and UV rows have different sector sets)
+    bool nv12 = false;
+    int n_touched_y = 0;    // NV12: the first n_touched_y entries of `touched` are Y rows, the rest UV rows (as H + row)
     bool resize = false;
     int pxt = 1;
     int rows_per_group = 0, n_groups = 0, stages = 0, rowbuf = 0, stage_bytes = 0, rows_per_stage = 1;
@@ -316,38 +319,36 @@ int64_t gcd64(int64_t a, int64_t b) { while (b) { int64_t t = a % b; a = b; b = 
 // Python round(): half to even on the double quotient
 long py_round(double x) { return lrint(x); }
 
+// the kernel instance for a (content, hist, aligned, nv12) combination; NV12 exists only for resizing contexts
 template <bool RESIZE, int PXT>
-cudaError_t launch_fused_rp(bool content, bool hist, bool aligned, const FusedParams& p, int grid, size_t smem,
-                            cudaStream_t st, KernelGraph& kg) {
-#define ESD_LAUNCH(C, H)                                                                                         \
+void (*fused_fn(bool content, bool hist, bool aligned, bool nv12))(const FusedParams) {
+#define ESD_PICK(C, H)                                                                                           \
     do {                                                                                                         \
-        auto k = aligned ? fused_score_kernel<RESIZE, PXT, C, H, true> : fused_score_kernel<RESIZE, PXT, C, H, false>; \
-        return klaunch(kg, st, k, dim3(grid), dim3(kThreads), smem, p);                                          \
+        if constexpr (RESIZE && PXT <= 4) {                                                                      \
+            if (nv12) return aligned ? fused_score_kernel<RESIZE, PXT, C, H, true, true> : fused_score_kernel<RESIZE, PXT, C, H, false, true>; \
+        }                                                                                                        \
+        return aligned ? fused_score_kernel<RESIZE, PXT, C, H, true> : fused_score_kernel<RESIZE, PXT, C, H, false>; \
     } while (0)
-    if (content && hist) ESD_LAUNCH(true, true);
-    if (content) ESD_LAUNCH(true, false);
-    ESD_LAUNCH(false, true);
-#undef ESD_LAUNCH
-    return cudaErrorUnknown;
+    if (content && hist) ESD_PICK(true, true);
+    if (content) ESD_PICK(true, false);
+    ESD_PICK(false, true);
+#undef ESD_PICK
 }
 
 template <bool RESIZE, int PXT>
-cudaError_t occupancy_rp(bool content, bool hist, size_t smem, int* out) {
-#define ESD_OCC(C, H)                                                                                            \
-    do {                                                                                                         \
-        auto k = fused_score_kernel<RESIZE, PXT, C, H, true>;                                                    \
-        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
-        if (e != cudaSuccess) return e;                                                                          \
-        e = cudaFuncSetAttribute(fused_score_kernel<RESIZE, PXT, C, H, false>,                                   \
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                        \
-        if (e != cudaSuccess) return e;                                                                          \
-        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, k, kThreads, smem);                            \
-    } while (0)
-    if (content && hist) ESD_OCC(true, true);
-    if (content) ESD_OCC(true, false);
-    ESD_OCC(false, true);
-#undef ESD_OCC
-    return cudaErrorUnknown;
+cudaError_t launch_fused_rp(bool content, bool hist, bool aligned, bool nv12, const FusedParams& p, int grid, size_t smem,
+                            cudaStream_t st, KernelGraph& kg) {
+    return klaunch(kg, st, fused_fn<RESIZE, PXT>(content, hist, aligned, nv12), dim3(grid), dim3(kThreads), smem, p);
+}
+
+template <bool RESIZE, int PXT>
+cudaError_t occupancy_rp(bool content, bool hist, bool nv12, size_t smem, int* out) {
+    for (int al = 0; al < 2; ++al) {
+        cudaError_t e = cudaFuncSetAttribute(fused_fn<RESIZE, PXT>(content, hist, al != 0, nv12),
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, fused_fn<RESIZE, PXT>(content, hist, true, nv12), kThreads, smem);
 }
 
 #define ESD_DISPATCH(FN, resize, pxt, ...)                                           \
@@ -587,7 +588,8 @@ enum Layout { LAYOUT_FULL = 0, LAYOUT_ROWS = 1, LAYOUT_TAPS = 2 };
 // inline_tail: run the finalize/decision tail on `st` itself (per-frame path: nothing to overlap with, and the
 // cross-stream event round trip would cost more than the tail)
 int push_common(esd_ctx* c, const uint8_t* d_src, int64_t n, int64_t frame_stride, int64_t row_stride, int layout,
-                int64_t first_frame_num, cudaStream_t st, bool inline_tail = false, long long* mailbox = nullptr) {
+                int64_t first_frame_num, cudaStream_t st, bool inline_tail = false, long long* mailbox = nullptr,
+                const uint8_t* d_uv = nullptr) {
     const bool compact = layout != LAYOUT_FULL;
     TraceTimer tr;
     if (!d_src || n <= 0) return fail(c, ESD_ERR_INVALID, "push: null frames or n <= 0");
@@ -619,6 +621,7 @@ int push_common(esd_ctx* c, const uint8_t* d_src, int64_t n, int64_t frame_strid
     const int64_t base = c->n_frames;  // index of the batch's first frame
     FusedParams p{};
     p.src = d_src;
+    p.src_uv = d_uv ? d_uv : d_src + (int64_t)c->cfg.src_height * row_stride;  // NV12 default: UV plane right behind the Y plane
     p.frame_stride = frame_stride;
     p.row_stride = row_stride;
     p.compact = compact ? 1 : 0;
@@ -659,8 +662,9 @@ int push_common(esd_ctx* c, const uint8_t* d_src, int64_t n, int64_t frame_strid
         CU(c, cudaEventCreate(&e1));
         CU(c, cudaEventRecord(e0, st));
     }
-    const bool aligned = ((reinterpret_cast<uintptr_t>(d_src) | (uintptr_t)frame_stride | (uintptr_t)row_stride) & 15u) == 0;
-    CU(c, ESD_DISPATCH(launch_fused_rp, c->resize, c->pxt, c->need_content, c->need_hist, aligned, p, plan.grid, c->smem_bytes, st, kg));
+    const bool aligned = ((reinterpret_cast<uintptr_t>(d_src) | (c->nv12 ? reinterpret_cast<uintptr_t>(p.src_uv) : 0) |
+                           (uintptr_t)frame_stride | (uintptr_t)row_stride) & 15u) == 0;
+    CU(c, ESD_DISPATCH(launch_fused_rp, c->resize, c->pxt, c->need_content, c->need_hist, aligned, c->nv12, p, plan.grid, c->smem_bytes, st, kg));
     c->launches++;
     tr.lap("launch fused");
     if (c->timing) {
@@ -875,7 +879,16 @@ int esd_create(esd_ctx** out, const esd_config* cfg, int device) {
     }
     c->dst_w = dw; c->dst_h = dh;
     c->resize = !(dw == W && dh == H);
-    c->row_bytes = W * 3;
+    c->nv12 = cfg->src_format == ESD_FMT_NV12;
+    if (cfg->src_format != ESD_FMT_BGR24 && cfg->src_format != ESD_FMT_NV12) {
+        fail(c, ESD_ERR_INVALID, "esd_create: unknown src_format %d", cfg->src_format);
+        return bail(ESD_ERR_INVALID);
+    }
+    if (c->nv12 && (!c->resize || (W & 1) || (H & 1) || H > 32766)) {
+        fail(c, ESD_ERR_UNSUPPORTED, "NV12 input needs even dimensions and a downscaling context (frames %dx%d -> %dx%d)", W, H, dw, dh);
+        return bail(ESD_ERR_UNSUPPORTED);
+    }
+    c->row_bytes = c->nv12 ? W : W * 3;
     c->need_hash = (cfg->detectors & ESD_DET_HASH) != 0;
     // the hash detector's gray plane rides on the content pass (a hash-only context also produces the HSV sums)
     c->need_content = (cfg->detectors & (ESD_DET_CONTENT | ESD_DET_ADAPTIVE | ESD_DET_THRESHOLD | ESD_DET_HASH)) != 0;
@@ -1039,12 +1052,24 @@ int esd_create(esd_ctx** out, const esd_config* cfg, int device) {
         std::vector<int> cidx(H, -1);
         for (int r = 0; r < H; ++r)
             if (used[r]) { cidx[r] = (int)c->touched.size(); c->touched.push_back(r); }
+        c->n_touched_y = (int)c->touched.size();
+        std::vector<int> uvidx(H / 2 + 1, -1);
+        if (c->nv12) {  // UV rows behind the Y rows, as virtual rows H + r of a contiguous NV12 frame
+            std::vector<char> uused(H / 2, 0);
+            for (int y = 0; y < dh; ++y) { uused[yo0[y] >> 1] = 1; uused[yo1[y] >> 1] = 1; }
+            for (int r = 0; r < H / 2; ++r)
+                if (uused[r]) { uvidx[r] = (int)c->touched.size(); c->touched.push_back(H + r); }
+        }
         std::vector<YRow> yr(dh);
         for (int y = 0; y < dh; ++y) {
             yr[y].row0 = yo0[y]; yr[y].row1 = yo1[y];
             yr[y].crow0 = cidx[yo0[y]]; yr[y].crow1 = c->resize ? cidx[yo1[y]] : cidx[yo0[y]];
             yr[y].b0s = (uint32_t)yb0[y] << 16; yr[y].b1s = (uint32_t)yb1[y] << 16;
-            yr[y].pad0 = yr[y].pad1 = 0;
+            yr[y].uvrows = yr[y].cuvrows = 0;
+            if (c->nv12) {
+                yr[y].uvrows = (uint32_t)(yo0[y] >> 1) | ((uint32_t)(yo1[y] >> 1) << 16);
+                yr[y].cuvrows = (uint32_t)uvidx[yo0[y] >> 1] | ((uint32_t)uvidx[yo1[y] >> 1] << 16);
+            }
         }
         CUB(cudaMalloc(&c->d_yrows, sizeof(YRow) * dh));
         CUB(cudaMemcpy(c->d_yrows, yr.data(), sizeof(YRow) * dh, cudaMemcpyHostToDevice));
@@ -1052,7 +1077,7 @@ int esd_create(esd_ctx** out, const esd_config* cfg, int device) {
     {
         std::vector<uint2> xt(dw);
         for (int x = 0; x < dw; ++x) {
-            if (c->resize) { xt[x].x = (uint32_t)(3 * xo0[x]); xt[x].y = (uint32_t)xa0[x] | ((uint32_t)xa1[x] << 16); }
+            if (c->resize) { xt[x].x = (uint32_t)((c->nv12 ? 1 : 3) * xo0[x]); xt[x].y = (uint32_t)xa0[x] | ((uint32_t)xa1[x] << 16); }
             else { xt[x].x = (uint32_t)(3 * x); xt[x].y = 2048u; }
         }
         {  // sector-granular touched bytes per row (SURVEY.md section 8d accounting)
@@ -1061,13 +1086,31 @@ int esd_create(esd_ctx** out, const esd_config* cfg, int device) {
                 const int b0 = (int)xt[x].x, b1 = std::min(c->row_bytes, b0 + (c->resize ? 6 : 3)) - 1;
                 for (int q = b0 / 32; q <= b1 / 32; ++q) sec[q] = 1;
             }
-            int nsec = 0;
-            for (char v : sec) nsec += v;
-            c->alg_row_bytes = std::min(c->row_bytes, nsec * 32);
+            if (c->nv12) {  // Y rows: bytes x0, x0 + 1; UV rows: the chroma pairs of those two columns
+                std::fill(sec.begin(), sec.end(), 0);
+                std::vector<char> secuv(sec.size(), 0);
+                for (int x = 0; x < dw; ++x) {
+                    const int x0 = xo0[x], x1 = std::min(x0 + 1, W - 1);
+                    sec[x0 / 32] = sec[x1 / 32] = 1;
+                    secuv[(x0 & ~1) / 32] = secuv[((x0 & ~1) + 1) / 32] = 1;
+                    secuv[(x1 & ~1) / 32] = secuv[((x1 & ~1) + 1) / 32] = 1;
+                }
+                int ny = 0, nuv = 0;
+                for (char v : sec) ny += v;
+                for (char v : secuv) nuv += v;
+                c->alg_row_bytes = std::min(c->row_bytes, ny * 32);
+                c->alg_frame_bytes = (int64_t)c->n_touched_y * c->alg_row_bytes +
+                                     (int64_t)(c->touched.size() - c->n_touched_y) * std::min(c->row_bytes, nuv * 32);
+            } else {
+                int nsec = 0;
+                for (char v : sec) nsec += v;
+                c->alg_row_bytes = std::min(c->row_bytes, nsec * 32);
+                c->alg_frame_bytes = (int64_t)c->touched.size() * c->alg_row_bytes;
+            }
         }
         CUB(cudaMalloc(&c->d_xtab, sizeof(uint2) * dw));
         CUB(cudaMemcpy(c->d_xtab, xt.data(), sizeof(uint2) * dw, cudaMemcpyHostToDevice));
-        if (c->resize) {  // tap-compact layout: column d of a gathered row holds [tap0 BGR, tap1 BGR] at byte 6 d
+        if (c->resize && !c->nv12) {  // tap-compact layout: column d of a gathered row holds [tap0 BGR, tap1 BGR] at byte 6 d
             c->tap_row_bytes = (6 * dw + 15) & ~15;
             c->tap_src_off.resize(dw);
             std::vector<uint2> xt2(dw);
@@ -1101,9 +1144,10 @@ int esd_create(esd_ctx** out, const esd_config* cfg, int device) {
     const bool wide_noresize = !c->resize && c->pxt >= 4;
     int RS = cfg->rows_per_stage > 0 ? cfg->rows_per_stage : (wide_noresize ? 1 : 4);
     RS = std::max(1, std::min(RS, kMaxRowsPerStage));
-    while (RS > 1 && (size_t)RS * (c->resize ? 2 : 1) * c->rowbuf > 48 * 1024) --RS;
+    const int rows_per_dst = c->resize ? (c->nv12 ? 4 : 2) : 1;  // staged source rows per destination row
+    while (RS > 1 && (size_t)RS * rows_per_dst * c->rowbuf > 48 * 1024) --RS;
     c->rows_per_stage = RS;
-    c->stage_bytes = RS * (c->resize ? 2 : 1) * c->rowbuf;
+    c->stage_bytes = RS * rows_per_dst * c->rowbuf;
     // rows per group: 16 measured best at 1080p->256x144 (profiles/r01_sweep.md); the previous-frame HSV of
     // a group lives in shared memory (R * pxt KB), keep it <= 32 KB unless the caller insists
     int R = cfg->rows_per_group > 0 ? cfg->rows_per_group : wide_noresize ? std::max(1, std::min(4, 32 / c->pxt)) : std::max(1, std::min(16, 32 / c->pxt));
@@ -1122,7 +1166,7 @@ int esd_create(esd_ctx** out, const esd_config* cfg, int device) {
         return bail(ESD_ERR_UNSUPPORTED);
     }
     int occ = 0;
-    CUB(ESD_DISPATCH(occupancy_rp, c->resize, c->pxt, c->need_content, c->need_hist, c->smem_bytes, &occ));
+    CUB(ESD_DISPATCH(occupancy_rp, c->resize, c->pxt, c->need_content, c->need_hist, c->nv12, c->smem_bytes, &occ));
     if (occ < 1) {
         fail(c, ESD_ERR_UNSUPPORTED, "fused kernel does not fit on an SM (smem %zu)", c->smem_bytes);
         return bail(ESD_ERR_UNSUPPORTED);
@@ -1218,7 +1262,7 @@ int esd_get_geometry(const esd_ctx* c, esd_geometry* g) {
     g->dst_height = c->dst_h;
     g->n_touched_rows = (int32_t)c->touched.size();
     g->row_bytes = c->row_bytes;
-    g->alg_bytes_per_frame = (int64_t)c->touched.size() * c->alg_row_bytes;
+    g->alg_bytes_per_frame = c->alg_frame_bytes;
     g->compact_frame_bytes = (int64_t)c->touched.size() * c->row_bytes;
     return ESD_OK;
 }
@@ -1233,6 +1277,9 @@ int esd_get_touched_rows(const esd_ctx* c, int32_t* rows, int32_t cap) {
 int esd_push_frames(esd_ctx* c, const uint8_t* d_bgr, int64_t n, int64_t frame_stride, int64_t pitch,
                     int64_t first_frame_num, void* stream) {
     if (!c) return ESD_ERR_INVALID;
+    if (c->nv12)  // contiguous NV12 frames: the UV plane starts at row src_height of the same pitch
+        return esd_push_nv12(c, d_bgr, d_bgr ? d_bgr + (int64_t)c->cfg.src_height * pitch : nullptr, n, frame_stride, pitch,
+                             first_frame_num, stream);
     if (pitch < c->row_bytes) return fail(c, ESD_ERR_INVALID, "push: pitch %lld < row bytes %d", (long long)pitch, c->row_bytes);
     if (n > 1 && frame_stride < pitch * (int64_t)(c->cfg.src_height - 1) + c->row_bytes)
         return fail(c, ESD_ERR_INVALID, "push: frame stride %lld smaller than a frame", (long long)frame_stride);
@@ -1242,6 +1289,23 @@ int esd_push_frames(esd_ctx* c, const uint8_t* d_bgr, int64_t n, int64_t frame_s
         if (rc) return rc;
     }
     return push_common(c, d_bgr, n, frame_stride, pitch, LAYOUT_FULL, first_frame_num, (cudaStream_t)stream);
+}
+
+int esd_push_nv12(esd_ctx* c, const uint8_t* d_y, const uint8_t* d_uv, int64_t n, int64_t frame_stride, int64_t pitch,
+                  int64_t first_frame_num, void* stream) {
+    if (!c) return ESD_ERR_INVALID;
+    if (!c->nv12) return fail(c, ESD_ERR_STATE, "push_nv12: the context was created for BGR24 frames (src_format)");
+    if (!d_y || !d_uv) return fail(c, ESD_ERR_INVALID, "push_nv12: null plane");
+    if (pitch < c->row_bytes) return fail(c, ESD_ERR_INVALID, "push_nv12: pitch %lld < row bytes %d", (long long)pitch, c->row_bytes);
+    const int H = c->cfg.src_height;
+    if (n > 0) {
+        const size_t fspan = (size_t)std::max<int64_t>(0, n - 1) * (size_t)frame_stride;
+        int rc = validate_device_span(c, d_y, fspan + (size_t)(H - 1) * (size_t)pitch + (size_t)c->row_bytes, "push_nv12 (Y plane)");
+        if (rc) return rc;
+        rc = validate_device_span(c, d_uv, fspan + (size_t)(H / 2 - 1) * (size_t)pitch + (size_t)c->row_bytes, "push_nv12 (UV plane)");
+        if (rc) return rc;
+    }
+    return push_common(c, d_y, n, frame_stride, pitch, LAYOUT_FULL, first_frame_num, (cudaStream_t)stream, false, nullptr, d_uv);
 }
 
 int esd_push_rows(esd_ctx* c, const uint8_t* d_rows, int64_t n, int64_t first_frame_num, void* stream) {
@@ -1420,7 +1484,7 @@ int esd_ingest_push_host(esd_ctx* c, const uint8_t* h_bgr, int64_t n, int64_t fr
 int esd_ingest_set_gather(esd_ctx* c, int32_t n_threads) {
     if (!c) return ESD_ERR_INVALID;
     if (n_threads < 0 || n_threads > 256) return fail(c, ESD_ERR_INVALID, "ingest: gather threads must be in 0..256");
-    if (n_threads > 0 && !c->resize) return fail(c, ESD_ERR_UNSUPPORTED, "ingest: tap gather needs a resizing context");
+    if (n_threads > 0 && (!c->resize || c->nv12)) return fail(c, ESD_ERR_UNSUPPORTED, "ingest: tap gather needs a resizing BGR24 context");
     CU(c, cudaSetDevice(c->device));
     int rc = sync_all(c);
     if (rc) return rc;
@@ -1582,6 +1646,7 @@ int esd_process_frame_host(esd_ctx* c, const uint8_t* h_bgr, int64_t pitch, int6
     const int di = det_index(detector);
     if (di < 0 || !(c->cfg.detectors & detector)) return fail(c, ESD_ERR_INVALID, "process_frame: detector %d not configured", detector);
     if (!h_bgr) return fail(c, ESD_ERR_INVALID, "process_frame: null frame");
+    if (c->nv12) return fail(c, ESD_ERR_UNSUPPORTED, "process_frame: BGR24 contexts only");
     if (pitch < c->row_bytes) return fail(c, ESD_ERR_INVALID, "process_frame: pitch %lld < row bytes %d", (long long)pitch, c->row_bytes);
     CU(c, cudaSetDevice(c->device));
     const int H = c->cfg.src_height;

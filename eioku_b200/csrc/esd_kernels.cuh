@@ -30,20 +30,22 @@ struct Unit {  // frames [f0, f1) (batch-relative) of destination-row group rg
 };
 
 struct YRow {  // per destination row
-    int row0, row1;    // source rows (full layout)
+    int row0, row1;    // source rows (full layout); NV12: rows of the Y plane
     int crow0, crow1;  // indices into the compact (touched rows only) layout
     uint32_t b0s, b1s; // vertical coefficients, pre-shifted << 16 for mul.hi
-    int pad0, pad1;
+    uint32_t uvrows;   // NV12: rows of the interleaved UV plane, row0 >> 1 | (row1 >> 1) << 16
+    uint32_t cuvrows;  // NV12: their indices in the compact layout (Y rows first, then UV rows), packed the same way
 };
 
 struct FusedParams {
     const uint8_t* src;
+    const uint8_t* src_uv;   // NV12: interleaved UV plane of frame 0 (same row and frame strides as the Y plane)
     long long frame_stride;  // bytes between frames
     long long row_stride;    // bytes between rows (pitch, or row_bytes in the compact layout)
     int compact;
     int n_frames;
     int dst_w, dst_h;
-    int row_bytes;  // src_w * 3
+    int row_bytes;  // bytes of one source row: src_w * 3 (BGR24) or src_w (NV12: Y rows and UV rows alike)
     int rows_per_group, n_groups;
     int stages;
     int rows_per_stage;  // destination rows per pipeline stage (1..kMaxRowsPerStage)
@@ -152,10 +154,29 @@ __device__ __forceinline__ int vresize(uint32_t h0, uint32_t h1, uint32_t b0s, u
     return (int)((__umulhi(b0s, h0 >> 4) + __umulhi(b1s, h1 >> 4) + 2u) >> 2);
 }
 
+// cv2.cvtColor(COLOR_YUV2BGR_NV12), OpenCV color_yuv (ITU-R BT.601, 20-bit fixed point); verified over all 2^24 (Y, U, V):
+//   yy = max(0, Y - 16) * 1220542;  B = sat((yy + buv) >> 20) ...  with the chroma terms below (1 << 19 is the rounding)
+struct Chroma { int ruv, guv, buv; };
+__device__ __forceinline__ Chroma nv12_chroma(int u, int v) {
+    u -= 128; v -= 128;
+    Chroma c;
+    c.ruv = (1 << 19) + 1673527 * v;
+    c.guv = (1 << 19) - 852492 * v - 409993 * u;
+    c.buv = (1 << 19) + 2116026 * u;
+    return c;
+}
+__device__ __forceinline__ void nv12_pixel(int y, const Chroma& c, int& b, int& g, int& r) {
+    const int yy = __vimax_s32_relu(y - 16, 0) * 1220542;
+    b = __vimin_s32_relu((yy + c.buv) >> 20, 255);
+    g = __vimin_s32_relu((yy + c.guv) >> 20, 255);
+    r = __vimin_s32_relu((yy + c.ruv) >> 20, 255);
+}
+
 // One destination row of one frame for one consumer thread (PXT columns).  SPECIAL = the stage carries a rare flag
 // (halo frame, first frame of the video / of the batch, last frame of the batch); the common path has none.
-template <bool RESIZE, int PXT, bool CONTENT, bool HIST, bool SPECIAL>
+template <bool RESIZE, int PXT, bool CONTENT, bool HIST, bool SPECIAL, bool NV12>
 __device__ __forceinline__ void score_row(const FusedParams& p, const uint8_t* __restrict__ row0, const uint8_t* __restrict__ row1,
+                                          const uint8_t* __restrict__ uv0, const uint8_t* __restrict__ uv1, uint32_t misuv,
                                           uint32_t mis0, uint32_t mis1, uint32_t b0s, uint32_t b1s, int flags, int rloc,
                                           int row, int frame, int tid, const uint32_t (&xoff)[PXT], const uint32_t (&xa01)[PXT],
                                           const int* __restrict__ s_sdiv, const int* __restrict__ s_hdiv,
@@ -166,7 +187,30 @@ __device__ __forceinline__ void score_row(const FusedParams& p, const uint8_t* _
         const int d = k * kConsumers + tid;
         if (d < p.dst_w) {
             int b, g, r;
-            if (RESIZE) {
+            if (RESIZE && NV12) {
+                // xoff = source column x0 of tap 0 (tap 1 is x0 + 1); chroma pair index x >> 1
+                uint32_t nx;
+                const uint32_t x0 = xoff[k];
+                const uint32_t ya = lds_u32_unaligned(row0, x0 + mis0, nx);   // [Y(x0), Y(x0+1), ..] of source row 0
+                const uint32_t yb = lds_u32_unaligned(row1, x0 + mis1, nx);   // same for source row 1
+                const uint32_t co = (x0 & ~1u);
+                const uint32_t ca = lds_u32_unaligned(uv0, co + (misuv & 0xffu), nx);         // [U V U' V'] for row 0
+                const uint32_t cb = lds_u32_unaligned(uv1, co + ((misuv >> 8) & 0xffu), nx);  // and for row 1
+                const uint32_t sh = (x0 & 1u) * 16u;  // odd x0: tap 1 belongs to the next chroma pair
+                const Chroma c00 = nv12_chroma(ca & 255u, (ca >> 8) & 255u);
+                const Chroma c01 = nv12_chroma((ca >> sh) & 255u, (ca >> (sh + 8u)) & 255u);
+                const Chroma c10 = nv12_chroma(cb & 255u, (cb >> 8) & 255u);
+                const Chroma c11 = nv12_chroma((cb >> sh) & 255u, (cb >> (sh + 8u)) & 255u);
+                int b00, g00, r00, b01, g01, r01, b10, g10, r10, b11, g11, r11;
+                nv12_pixel(ya & 255u, c00, b00, g00, r00);
+                nv12_pixel((ya >> 8) & 255u, c01, b01, g01, r01);
+                nv12_pixel(yb & 255u, c10, b10, g10, r10);
+                nv12_pixel((yb >> 8) & 255u, c11, b11, g11, r11);
+                const uint32_t a0 = xa01[k] & 0xffffu, a1 = xa01[k] >> 16;
+                b = vresize(a0 * b00 + a1 * b01, a0 * b10 + a1 * b11, b0s, b1s);
+                g = vresize(a0 * g00 + a1 * g01, a0 * g10 + a1 * g11, b0s, b1s);
+                r = vresize(a0 * r00 + a1 * r01, a0 * r10 + a1 * r11, b0s, b1s);
+            } else if (RESIZE) {
                 uint32_t n0, n1;
                 const uint32_t o0 = xoff[k] + mis0, o1 = xoff[k] + mis1;
                 const uint32_t lo0 = lds_u32_unaligned(row0, o0, n0);
@@ -290,7 +334,7 @@ __device__ __forceinline__ void score_row_quads(const FusedParams& p, const uint
 
 // ALIGNED: every source row starts on a 16-byte boundary (base, pitch and frame stride multiples of 16), so the
 // per-row misalignment is zero and each thread's smem word offset / funnel shift are loop invariants.
-template <bool RESIZE, int PXT, bool CONTENT, bool HIST, bool ALIGNED>
+template <bool RESIZE, int PXT, bool CONTENT, bool HIST, bool ALIGNED, bool NV12 = false>
 __global__ void __launch_bounds__(kThreads) fused_score_kernel(const FusedParams p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     // ---- carve shared memory (host twin: fused_smem_bytes in esd.cu)
@@ -328,7 +372,8 @@ __global__ void __launch_bounds__(kThreads) fused_score_kernel(const FusedParams
     const int u_end = p.cta_unit_begin[blockIdx.x + 1];
     const int R = p.rows_per_group;
     const int RS = p.rows_per_stage;
-    const int row_slot = (RESIZE ? 2 : 1) * p.rowbuf;  // smem bytes of one destination row's source rows
+    // smem bytes of one destination row's source rows: [row0][row1], NV12: [Y row0][Y row1][UV row0][UV row1]
+    const int row_slot = (RESIZE ? (NV12 ? 4 : 2) : 1) * p.rowbuf;
     const int stage_bytes = RS * row_slot;
 
     if (tid >= kConsumers) {
@@ -357,6 +402,9 @@ __global__ void __launch_bounds__(kThreads) fused_score_kernel(const FusedParams
                     const uint8_t* src0[kMaxRowsPerStage];
                     const uint8_t* src1[kMaxRowsPerStage];
                     uint32_t nb0[kMaxRowsPerStage], nb1[kMaxRowsPerStage];
+                    const uint8_t* srcu0[kMaxRowsPerStage];
+                    const uint8_t* srcu1[kMaxRowsPerStage];
+                    uint32_t nbu0[kMaxRowsPerStage], nbu1[kMaxRowsPerStage];
                     uint32_t tx = 0;
 #pragma unroll
                     for (int q = 0; q < kMaxRowsPerStage; ++q) {
@@ -376,7 +424,24 @@ __global__ void __launch_bounds__(kThreads) fused_score_kernel(const FusedParams
                                 src1[q] = a1 - mis1;
                             }
                             tx += nb0[q] + nb1[q];
-                            meta_r[s * kMaxRowsPerStage + q] = make_uint4(yr.b0s, yr.b1s, mis0 | (mis1 << 8), 0u);
+                            uint32_t misuv = 0;
+                            if (NV12) {
+                                // UV rows: from the UV plane (full layout) or from the compact frame (absolute indices)
+                                const uint8_t* uvbase = p.compact ? frame : p.src_uv + (long long)f * p.frame_stride;
+                                const uint32_t rows = p.compact ? yr.cuvrows : yr.uvrows;
+                                const uint8_t* u0 = uvbase + (long long)(rows & 0xffffu) * p.row_stride;
+                                const uint8_t* u1 = uvbase + (long long)(rows >> 16) * p.row_stride;
+                                const uint32_t m0 = ALIGNED ? 0u : (uint32_t)(reinterpret_cast<uintptr_t>(u0) & 15u);
+                                const uint32_t m1 = ALIGNED ? 0u : (uint32_t)(reinterpret_cast<uintptr_t>(u1) & 15u);
+                                nbu0[q] = (m0 + (uint32_t)p.row_bytes + 15u) & ~15u;
+                                srcu0[q] = u0 - m0;
+                                const bool same = (rows & 0xffffu) == (rows >> 16);  // both source rows share one chroma row
+                                nbu1[q] = same ? 0u : ((m1 + (uint32_t)p.row_bytes + 15u) & ~15u);
+                                srcu1[q] = u1 - m1;
+                                misuv = m0 | ((same ? m0 : m1) << 8) | (same ? 0x10000u : 0u);
+                                tx += nbu0[q] + nbu1[q];
+                            }
+                            meta_r[s * kMaxRowsPerStage + q] = make_uint4(yr.b0s, yr.b1s, mis0 | (mis1 << 8), misuv);
                         }
                     }
                     const int flags = fflags | ((r + nr >= r_end) ? F_FRAME_END : 0);
@@ -389,6 +454,10 @@ __global__ void __launch_bounds__(kThreads) fused_score_kernel(const FusedParams
                         if (q < nr) {
                             bulk_g2s(dst + q * row_slot, src0[q], nb0[q], bar, pol);
                             if (RESIZE) bulk_g2s(dst + q * row_slot + p.rowbuf, src1[q], nb1[q], bar, pol);
+                            if (NV12) {
+                                bulk_g2s(dst + q * row_slot + 2 * p.rowbuf, srcu0[q], nbu0[q], bar, pol);
+                                if (nbu1[q]) bulk_g2s(dst + q * row_slot + 3 * p.rowbuf, srcu1[q], nbu1[q], bar, pol);
+                            }
                         }
                     }
                     if (++s == S) { s = 0; par ^= 1u; }
@@ -445,9 +514,12 @@ __global__ void __launch_bounds__(kThreads) fused_score_kernel(const FusedParams
                 }
                 const uint4 mr = meta_r[s * kMaxRowsPerStage + q];
                 const uint32_t mis0 = ALIGNED ? 0u : (mr.z & 0xffu), mis1 = ALIGNED ? 0u : ((mr.z >> 8) & 0xffu);
-                score_row<RESIZE, PXT, CONTENT, HIST, true>(p, stage + q * row_slot, stage + q * row_slot + p.rowbuf, mis0, mis1, mr.x,
-                                                            mr.y, flags, rloc0 + q, row_first + q, m.x, tid, xoff, xa01, s_sdiv, s_hdiv,
-                                                            s_prev, hist_cur, acc_hv, acc_s, acc_bgr);
+                const uint8_t* uvp0 = stage + q * row_slot + 2 * p.rowbuf;
+                const uint8_t* uvp1 = (mr.w & 0x10000u) ? uvp0 : uvp0 + p.rowbuf;
+                score_row<RESIZE, PXT, CONTENT, HIST, true, NV12>(p, stage + q * row_slot, stage + q * row_slot + p.rowbuf, uvp0, uvp1,
+                                                                  ALIGNED ? 0u : mr.w, mis0, mis1, mr.x, mr.y, flags, rloc0 + q,
+                                                                  row_first + q, m.x, tid, xoff, xa01, s_sdiv, s_hdiv, s_prev,
+                                                                  hist_cur, acc_hv, acc_s, acc_bgr);
             }
         } else {
             for (int q = 0; q < nrows; ++q) {
@@ -459,9 +531,12 @@ __global__ void __launch_bounds__(kThreads) fused_score_kernel(const FusedParams
                 }
                 const uint4 mr = meta_r[s * kMaxRowsPerStage + q];
                 const uint32_t mis0 = ALIGNED ? 0u : (mr.z & 0xffu), mis1 = ALIGNED ? 0u : ((mr.z >> 8) & 0xffu);
-                score_row<RESIZE, PXT, CONTENT, HIST, false>(p, stage + q * row_slot, stage + q * row_slot + p.rowbuf, mis0, mis1, mr.x,
-                                                             mr.y, flags, rloc0 + q, row_first + q, m.x, tid, xoff, xa01, s_sdiv, s_hdiv,
-                                                             s_prev, hist_cur, acc_hv, acc_s, acc_bgr);
+                const uint8_t* uvp0 = stage + q * row_slot + 2 * p.rowbuf;
+                const uint8_t* uvp1 = (mr.w & 0x10000u) ? uvp0 : uvp0 + p.rowbuf;
+                score_row<RESIZE, PXT, CONTENT, HIST, false, NV12>(p, stage + q * row_slot, stage + q * row_slot + p.rowbuf, uvp0, uvp1,
+                                                                   ALIGNED ? 0u : mr.w, mis0, mis1, mr.x, mr.y, flags, rloc0 + q,
+                                                                   row_first + q, m.x, tid, xoff, xa01, s_sdiv, s_hdiv, s_prev,
+                                                                   hist_cur, acc_hv, acc_s, acc_bgr);
             }
         }
         __syncwarp();

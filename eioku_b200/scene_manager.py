@@ -46,8 +46,14 @@ class TensorVideo:
     """A decoded clip held as one array: numpy uint8 [N,H,W,3] (host) or a CUDA torch tensor.
     Stands where PySceneDetect's VideoStream stands; decode itself is out of scope."""
 
-    def __init__(self, frames, fps: float = 30.0, start_frame: int = 0):
-        if frames.ndim != 4 or frames.shape[3] != 3:
+    def __init__(self, frames, fps: float = 30.0, start_frame: int = 0, pixel_format: str = "bgr24"):
+        self.pixel_format = pixel_format
+        if pixel_format == "nv12":
+            if frames.ndim != 3 or frames.shape[1] % 3:
+                raise ValueError("NV12 frames must be [N, H*3/2, W] uint8 (Y plane, then the interleaved UV plane)")
+        elif pixel_format != "bgr24":
+            raise ValueError("pixel_format must be 'bgr24' or 'nv12'")
+        elif frames.ndim != 4 or frames.shape[3] != 3:
             raise ValueError("frames must be [N,H,W,3] uint8 BGR")
         self.frames = frames
         self.frame_rate = float(fps)
@@ -58,6 +64,8 @@ class TensorVideo:
 
     @property
     def frame_size(self) -> Tuple[int, int]:
+        if self.pixel_format == "nv12":
+            return int(self.frames.shape[2]), int(self.frames.shape[1]) * 2 // 3
         return int(self.frames.shape[2]), int(self.frames.shape[1])
 
     @property
@@ -76,7 +84,9 @@ class BatchVideo:
     """A clip delivered as an iterable of batches ([k,H,W,3] numpy or CUDA tensors), e.g. a decoder
     or a synthetic generator that cannot hold the whole clip."""
 
-    def __init__(self, batches: Iterable, frame_size: Tuple[int, int], fps: float = 30.0, start_frame: int = 0):
+    def __init__(self, batches: Iterable, frame_size: Tuple[int, int], fps: float = 30.0, start_frame: int = 0,
+                 pixel_format: str = "bgr24"):
+        self.pixel_format = pixel_format
         self._it = iter(batches)
         self.frame_size = (int(frame_size[0]), int(frame_size[1]))
         self.frame_rate = float(fps)
@@ -163,7 +173,7 @@ class SceneManager:
             return max(1, round(width / factor)), max(1, round(height / factor))
         return width, height
 
-    def make_context(self, width: int, height: int, device: Optional[int] = None) -> capi.EsdContext:
+    def make_context(self, width: int, height: int, device: Optional[int] = None, pixel_format: str = "bgr24") -> capi.EsdContext:
         """The esd_ctx this manager's detectors need for frames of the given size."""
         if not self._detector_list:
             raise RuntimeError("No detectors registered; call add_detector() first.")
@@ -173,6 +183,7 @@ class SceneManager:
             det._fill_config(cfg)
         cfg.src_width, cfg.src_height = width, height
         cfg.dst_width, cfg.dst_height = self._target_size(width, height)
+        cfg.src_format = capi.ESD_FMT_NV12 if pixel_format == "nv12" else capi.ESD_FMT_BGR24
         for k, v in self._tuning.items():
             setattr(cfg, k, v)
         return capi.EsdContext(cfg, self._device if device is None else device)
@@ -191,7 +202,8 @@ class SceneManager:
             self._frame_rate = float(getattr(video, "frame_rate", 30.0))
         width, height = video.frame_size
         self.close()
-        self._ctx = ctx = self.make_context(width, height)
+        nv12 = getattr(video, "pixel_format", "bgr24") == "nv12"
+        self._ctx = ctx = self.make_context(width, height, pixel_format="nv12" if nv12 else "bgr24")
         start = int(getattr(video, "start_frame", 0))
         self._start_pos = start
         pos = start
@@ -204,12 +216,17 @@ class SceneManager:
             if isinstance(batch, np.ndarray):
                 if not host_ring_open:
                     ctx.ingest_open(3, min(self._batch_frames, 64))
-                    if self._ingest_threads > 0 and ctx.dst_size != (width, height):
+                    if self._ingest_threads > 0 and ctx.dst_size != (width, height) and not nv12:
                         ctx.ingest_set_gather(self._ingest_threads)
                     host_ring_open = True
-                ctx.ingest_push_numpy(batch, pos)
+                if nv12:
+                    ctx.ingest_push_nv12_numpy(batch, pos)
+                else:
+                    ctx.ingest_push_numpy(batch, pos)
                 if not getattr(video, "frames_stable", False):
                     ctx.synchronize()  # the producer may recycle `batch` as soon as we return to read_batch
+            elif nv12:
+                ctx.push_nv12_tensor(batch, pos)
             else:
                 ctx.push_tensor(batch, pos)
             pos += n

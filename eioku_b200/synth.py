@@ -103,3 +103,22 @@ def build_schedule(seed: int, n_frames: int, *, noise_amp: int = 2, pan_div: int
             t += n
         k += 1
     return ClipSchedule(seed, n_frames, descs, hard_cuts, dissolves, fades, flashes)
+
+
+def bgr_to_test_nv12(frames):
+    """Deterministic NV12 test content from BGR frames [N,H,W,3] (numpy or torch; pure indexing, so identical on both):
+    Y = the G channel, U / V = the B / R channels at the even rows and columns.  Returns [N, H * 3 // 2, W] uint8 --
+    the contiguous NV12 layout (Y plane, then the interleaved UV plane).  Not a colour-space conversion: it only makes
+    NV12 frames whose scene structure (cuts, fades, flashes) follows the synthetic clip."""
+    n, h, w, _ = frames.shape
+    assert h % 2 == 0 and w % 2 == 0
+    if isinstance(frames, np.ndarray):
+        out = np.empty((n, h * 3 // 2, w), np.uint8)
+    else:
+        import torch
+
+        out = torch.empty((n, h * 3 // 2, w), dtype=torch.uint8, device=frames.device)
+    out[:, :h, :] = frames[..., 1]
+    out[:, h:, 0::2] = frames[:, 0::2, 0::2, 0]
+    out[:, h:, 1::2] = frames[:, 0::2, 0::2, 2]
+    return out

@@ -59,6 +59,10 @@ enum { ESD_FILTER_MERGE = 0, ESD_FILTER_SUPPRESS = 1 };
 enum { ESD_DOWNSCALE_FLOAT = 0, ESD_DOWNSCALE_INT = 1 };
 /* work decomposition of the fused kernel (tuning; results are identical) */
 enum { ESD_SPLIT_AUTO = 0, ESD_SPLIT_STRIPS = 1, ESD_SPLIT_CHUNKS = 2 };
+/* pixel format of the frames handed to the library.  NV12 (what NVDEC and most hardware decoders emit: a Y plane followed
+ * by an interleaved half-resolution UV plane) is converted exactly like cv2.cvtColor(COLOR_YUV2BGR_NV12) inside the fused
+ * kernel, only for the source pixels the downscale taps read; it needs a downscaling context and even dimensions. */
+enum { ESD_FMT_BGR24 = 0, ESD_FMT_NV12 = 1 };
 
 typedef struct esd_config {
     uint32_t struct_size;      /* = sizeof(esd_config) */
@@ -68,7 +72,7 @@ typedef struct esd_config {
     int32_t dst_width;         /* SceneManager resize target; 0,0 = auto (downscale_mode); == src = no resize */
     int32_t dst_height;
     int32_t downscale_mode;    /* ESD_DOWNSCALE_*; used when dst_* == 0 */
-    int32_t reserved0;
+    int32_t src_format;        /* ESD_FMT_*; 0 = BGR24 */
 
     /* ContentDetector(threshold, min_scene_len, weights, filter_mode); luma_only = weights {0,0,1,0} */
     double content_threshold;
@@ -120,7 +124,7 @@ typedef struct esd_config {
 typedef struct esd_geometry {
     int32_t dst_width, dst_height;
     int32_t n_touched_rows;      /* distinct source rows the vertical taps read */
-    int32_t row_bytes;           /* src_width * 3 */
+    int32_t row_bytes;           /* bytes per source row: src_width * 3 (BGR24) or src_width (NV12) */
     int64_t alg_bytes_per_frame; /* algorithmic HBM bytes per frame: 32-byte sectors of the touched rows that hold a tap */
     int64_t compact_frame_bytes; /* n_touched_rows * row_bytes: one frame in the compact layout = bytes the kernel fetches */
 } esd_geometry;
@@ -140,7 +144,8 @@ ESD_API void esd_destroy(esd_ctx* ctx);
 /* forget all frames, scores, cuts and filter state (start of a new video) */
 ESD_API int esd_reset(esd_ctx* ctx);
 ESD_API int esd_get_geometry(const esd_ctx* ctx, esd_geometry* out);
-/* touched source rows in ascending order (n_touched_rows entries) */
+/* touched source rows in ascending order (n_touched_rows entries); NV12: Y rows, then UV rows numbered src_height + r,
+ * i.e. row indices into a contiguous NV12 frame */
 ESD_API int esd_get_touched_rows(const esd_ctx* ctx, int32_t* rows, int32_t cap);
 
 /* Replaces: the per-frame scoring loop -- in the shipped reference the ffmpeg child process started by
@@ -152,8 +157,14 @@ ESD_API int esd_get_touched_rows(const esd_ctx* ctx, int32_t* rows, int32_t cap)
  * Asynchronous on `stream`. */
 ESD_API int esd_push_frames(esd_ctx* ctx, const uint8_t* d_bgr, int64_t n, int64_t frame_stride_bytes,
                     int64_t pitch_bytes, int64_t first_frame_num, void* stream);
+/* NV12 contexts: Y plane and interleaved UV plane given separately (as a decoder surface has them: the UV plane usually
+ * starts at an aligned height); both use `pitch_bytes` and `frame_stride_bytes`.  esd_push_frames on an NV12 context is
+ * the contiguous case d_uv = d_y + src_height * pitch_bytes.  This is the device half of SURVEY.md 8f N1 (decode ->
+ * device): the scoring chain consumes decoder surfaces directly, 0.97 MB instead of 1.66 MB per 1080p frame. */
+ESD_API int esd_push_nv12(esd_ctx* ctx, const uint8_t* d_y, const uint8_t* d_uv, int64_t n, int64_t frame_stride_bytes,
+                          int64_t pitch_bytes, int64_t first_frame_num, void* stream);
 /* Same, for frames stored in the compact layout [n][n_touched_rows][row_bytes] (touched rows only,
- * ascending source-row order) that the ingest ring produces. */
+ * ascending source-row order; NV12: the touched Y rows, then the touched UV rows) that the ingest ring produces. */
 ESD_API int esd_push_rows(esd_ctx* ctx, const uint8_t* d_rows, int64_t n, int64_t first_frame_num, void* stream);
 
 /* Replaces: one call of PySceneDetect's `SceneDetector.process_frame(frame_num, frame_img)` with a host (numpy) frame --

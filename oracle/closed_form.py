@@ -337,3 +337,23 @@ def hash_frame(frame_bgr: np.ndarray, hash_size: int = 16, factor: int = 2):
     low = (c @ x.astype(np.float64) @ c.T).astype(np.float32)
     med = np.median(low)
     return low > med, np.abs(low.astype(np.float64) - float(med))
+
+
+# --------------------------------------------------------------------------- N1: decoder surfaces
+def nv12_to_bgr_u8(nv12: np.ndarray) -> np.ndarray:
+    """cv2.cvtColor(nv12, COLOR_YUV2BGR_NV12) for a contiguous NV12 frame [H*3/2, W] uint8 -> [H, W, 3].
+
+    OpenCV color_yuv (ITU-R BT.601, 20-bit fixed point): yy = max(0, Y-16)*1220542; R = sat((yy + 2^19 + 1673527 v) >> 20),
+    G = sat((yy + 2^19 - 852492 v - 409993 u) >> 20), B = sat((yy + 2^19 + 2116026 u) >> 20) with u = U-128, v = V-128 taken
+    from the chroma pair of the pixel's 2x2 block.  Verified over all 2^24 (Y, U, V) against cv2 4.13 (tests/test_oracle.py)."""
+    rows, w = nv12.shape
+    h = rows * 2 // 3
+    y = nv12[:h].astype(np.int64)
+    uv = nv12[h:].astype(np.int64)
+    u = np.repeat(np.repeat(uv[:, 0::2], 2, 0), 2, 1) - 128
+    v = np.repeat(np.repeat(uv[:, 1::2], 2, 0), 2, 1) - 128
+    yy = np.maximum(0, y - 16) * 1220542
+    r = np.clip((yy + (1 << 19) + 1673527 * v) >> 20, 0, 255)
+    g = np.clip((yy + (1 << 19) - 852492 * v - 409993 * u) >> 20, 0, 255)
+    b = np.clip((yy + (1 << 19) + 2116026 * u) >> 20, 0, 255)
+    return np.stack([b, g, r], -1).astype(np.uint8)

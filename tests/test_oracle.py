@@ -244,3 +244,20 @@ def test_hash_closed_form_vs_cv2_golden():
     assert not ((got != want) & ~unstable).any()
     if not unstable.any():
         assert np.array_equal(np.array(det.dists)[1:], g["hash_dist"][1:n])
+
+
+def test_nv12_to_bgr_restatement_exhaustive_vs_cv2():
+    """Every (Y, U, V) combination: the closed form of cv2.cvtColor(COLOR_YUV2BGR_NV12) the CUDA kernel restates."""
+    cv2 = pytest.importorskip("cv2")
+    W = H = 4096
+    c = np.arange(2 ** 22).reshape(H // 2, W // 2)
+    uvid, grp = c % 65536, c // 65536
+    uv = np.zeros((H // 2, W), np.uint8)
+    uv[:, 0::2] = (uvid & 255).astype(np.uint8)
+    uv[:, 1::2] = (uvid >> 8).astype(np.uint8)
+    y = np.zeros((H, W), np.uint8)
+    for dy in range(2):
+        for dx in range(2):
+            y[dy::2, dx::2] = (grp * 4 + dy * 2 + dx).astype(np.uint8)
+    nv12 = np.vstack([y, uv])
+    assert np.array_equal(cv2.cvtColor(nv12, cv2.COLOR_YUV2BGR_NV12), cf.nv12_to_bgr_u8(nv12))
