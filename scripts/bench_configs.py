@@ -310,6 +310,58 @@ def config_edges(dev, local, n=1024, steps=10):
     return out
 
 
+def config_nv12(dev, local, n=2048, steps=20):
+    """ContentDetector on NV12 decoder surfaces (1080p): device-resident batches, and host NV12 frames through the ring."""
+    W, H, seed = 1920, 1080, 1002
+    sch = synth.build_schedule(seed, n)
+    out = {"config": "nv12"}
+    nv12 = torch.empty((n, H * 3 // 2, W), dtype=torch.uint8, device=dev)
+    for a in range(0, n, 256):
+        bgr = fill(seed, W, H, sch.descs[a:a + 256], dev)
+        nv12[a:a + 256] = synth.bgr_to_test_nv12(bgr)
+        del bgr
+    cfg = capi.default_config()
+    cfg.src_width, cfg.src_height, cfg.src_format = W, H, capi.ESD_FMT_NV12
+    cfg.initial_capacity = (steps + 4) * n
+    stream = torch.cuda.current_stream().cuda_stream
+    ctx = capi.EsdContext(cfg, local)
+    pos = 0
+    for _ in range(3):
+        ctx.push_nv12_tensor(nv12, pos, stream); pos += n
+    ctx.synchronize()
+    ctx.set_timing(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        ctx.push_nv12_tensor(nv12, pos, stream); pos += n
+    ctx.join(stream)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    kms, kn = ctx.kernel_time()
+    alg = ctx.alg_bytes_per_frame
+    out.update({"frames_per_s": steps * n / (ms / 1000.0), "alg_bytes_per_frame": alg, "fetched_bytes_per_frame": int(ctx.geometry.compact_frame_bytes),
+                "fused_ms": kms / kn, "achieved_GBps": n * alg / (kms / kn / 1000.0) / 1e9,
+                "frac_of_measured_peak": n * alg / (kms / kn / 1000.0) / 1e9 / peak()})
+    ctx.close()
+    # host NV12 frames (pinned) through the touched-rows DMA ring
+    m = 512
+    host = nv12[:m].cpu().pin_memory()
+    hn = host.numpy()
+    ctx = capi.EsdContext(cfg, local)
+    ctx.ingest_open(3, 256)
+    ctx.ingest_push_nv12_numpy(hn, 0); ctx.synchronize()
+    t0 = time.perf_counter()
+    for i in range(1, 5):
+        ctx.ingest_push_nv12_numpy(hn, i * m)
+    ctx.synchronize()
+    dt = time.perf_counter() - t0
+    out["host_ring_frames_per_s"] = 4 * m / dt
+    out["host_ring_GBps"] = 4 * m * int(ctx.geometry.compact_frame_bytes) / dt / 1e9
+    ctx.close()
+    return out
+
+
 def pcie_probe(dev, local):
     """H2D ceilings on this box: plain pinned memcpy, the touched-rows ring, and zero-copy TMA reads of pinned frames."""
     W, H, n = 1920, 1080, 256
@@ -401,6 +453,8 @@ def main():
             r = config4(dev, local, world, rank, dist)
         elif c == "5":
             r = config5(dev, local, world, rank, dist, args.videos_per_gpu)
+        elif c == "nv12":
+            r = config_nv12(dev, local)
         elif c == "pcie":
             r = pcie_probe(dev, local) if rank == 0 else None
         elif c == "2full":
