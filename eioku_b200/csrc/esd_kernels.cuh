@@ -81,13 +81,26 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
     asm volatile("{ .reg .b64 st; mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1; }" ::"r"(bar), "r"(bytes)
                  : "memory");
 }
+#ifndef ESD_WAIT_HINT_NS
+#define ESD_WAIT_HINT_NS 0
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t done;
+#if ESD_WAIT_HINT_NS > 0
+    // suspend-time hint: the warp may stay suspended (not issuing) up to this long before try_wait returns false; it still
+    // wakes as soon as the phase completes, so unlike a sleep this only removes spin iterations
+    asm volatile(
+        "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; selp.u32 %0, 1, 0, p; }"
+        : "=r"(done)
+        : "r"(bar), "r"(parity), "r"((uint32_t)ESD_WAIT_HINT_NS)
+        : "memory");
+#else
     asm volatile(
         "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
         : "=r"(done)
         : "r"(bar), "r"(parity)
         : "memory");
+#endif
     return done != 0;
 }
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -98,10 +111,14 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 // Bounded wait: a pipeline bug must trap (reported as a CUDA error) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
-    unsigned long long t0 = globaltimer_ns();
+    unsigned long long t0 = 0;  // the clock is only read on the (never taken in a healthy run) long-wait path
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if ((++spins & 0x3ff) == 0 && globaltimer_ns() - t0 > 4000000000ULL) __trap();
+        if ((++spins & 0x3ff) == 0) {
+            const unsigned long long t = globaltimer_ns();
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > 4000000000ULL) __trap();
+        }
     }
 }
 __device__ __forceinline__ uint64_t l2_evict_first_policy() {

@@ -173,6 +173,11 @@ def config5(dev, local, world, rank, dist, videos_per_gpu=8, n_videos=512, frame
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ms_total, frames, cuts_total = 0.0, 0, 0
     batch = 2048
+    # one untimed push first: the first launch of a kernel pays CUDA's lazy module loading (~20 ms for this library)
+    warm = fill(5000, W, H, synth.build_schedule(5000, 64).descs, dev)
+    ctx.push_tensor(warm, 0, stream)
+    ctx.synchronize()
+    del warm
     for j in mine:
         seed = 5000 + j
         sch = synth.build_schedule(seed, frames_per_video)
