@@ -1402,6 +1402,8 @@ int esd_ingest_push_host(esd_ctx* c, const uint8_t* h_bgr, int64_t n, int64_t fr
         if (s.in_flight) CU(c, cudaEventSynchronize(s.consumed));  // device slot (and pinned slot) free again
         trw.lap("wait slot");
         const uint8_t* src = h_bgr + done * frame_stride;
+        // (A per-slot DMA + gather hybrid was measured twice and is slower: both share PCIe and the in-order pushes stall
+        // behind the 4x larger DMA slots -- 31-36 k vs 55 k frames/s, profiles/r01_gather_prefetch.log.)
         const bool use_gather = gather;
         if (use_gather) {
             // host threads gather, per touched row, the two BGR taps of every destination column (6 of every
@@ -1411,17 +1413,38 @@ int esd_ingest_push_host(esd_ctx* c, const uint8_t* h_bgr, int64_t n, int64_t fr
             const int* off = c->tap_src_off.data();
             const int32_t* touched = c->touched.data();
             uint8_t* dst_base = s.h_pinned;
+            static const int pf_env = getenv("ESD_GATHER_PF") ? atoi(getenv("ESD_GATHER_PF")) : -1;
+            // measured best of 0 / 512 ... 8192 at 1080p (profiles/r01_gather_prefetch.log); never further than one row
+            const int pf_dist = std::min(pf_env >= 0 ? pf_env : 4096, c->row_bytes);
+
             std::function<void(int64_t, int64_t)> job = [=](int64_t lo, int64_t hi) {
                 for (int64_t it = lo; it < hi; ++it) {
                     const int64_t f = it / nt, i = it - f * nt;
                     const uint8_t* sr = src + f * frame_stride + (int64_t)touched[i] * pitch;
                     uint8_t* dr = dst_base + it * trb;
-                    if (it + 1 < hi) {  // touch the next row's pages early: hardware prefetchers stop at 4 KB boundaries
+                    if (pf_dist == 0 && it + 1 < hi) {  // touch the next row's pages early: hardware prefetchers stop at 4 KB boundaries
                         const int64_t f1 = (it + 1) / nt, i1 = (it + 1) - f1 * nt;
                         const uint8_t* nx = src + f1 * frame_stride + (int64_t)touched[i1] * pitch;
                         for (int b = 0; b < rb; b += 2048) __builtin_prefetch(nx + b, 0, 1);
                     }
                     int d = 0;
+                    if (pf_dist > 0) {
+                        // rolling software prefetch `pf_dist` bytes ahead, running over into the next touched row
+                        const uint8_t* nx = sr;
+                        if (it + 1 < hi) {
+                            const int64_t f1 = (it + 1) / nt, i1 = (it + 1) - f1 * nt;
+                            nx = src + f1 * frame_stride + (int64_t)touched[i1] * pitch;
+                        }
+                        for (; d < dw - 1 && off[d] + 8 <= rb; ++d) {
+                            if ((d & 3) == 0) {
+                                const int o = off[d] + pf_dist;
+                                __builtin_prefetch(o < rb ? sr + o : nx + (o - rb), 0, 3);
+                            }
+                            uint64_t v;
+                            memcpy(&v, sr + off[d], 8);
+                            memcpy(dr + 6 * d, &v, 8);
+                        }
+                    }
                     for (; d < dw - 1 && off[d] + 8 <= rb; ++d) {  // 8-byte moves; the 2 spare bytes are overwritten by d + 1
                         uint64_t v;
                         memcpy(&v, sr + off[d], 8);
