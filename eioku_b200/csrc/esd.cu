@@ -523,6 +523,8 @@ int reset_video_state(esd_ctx* c) {
     c->prev_parity = 0;
     c->h2d_bytes = 0;
     c->h2d_copies = 0;
+    c->last_batch_base = c->last_batch_n = 0;
+    if (c->pf_mailbox) memset(c->pf_mailbox, 0, 8 * sizeof(long long));
     CU(c, cudaMemset(c->d_state, 0, sizeof(DecisionState)));
     if (c->cap) {
         fill_nan_kernel<<<(unsigned)((c->cap + 255) / 256), 256>>>(c->d_ratio, c->cap);
