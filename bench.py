@@ -113,6 +113,16 @@ def bind_to_gpu_numa_node(gpu_index: int):
         return 0
 
 
+def cpu_model() -> str:
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def host_sample_frames(n: int, start: int = 0) -> np.ndarray:
     """n frames of the config-2 clip on the host (GPU generator if there is one, else the CPU twin)."""
     from eioku_b200 import synth
@@ -171,7 +181,7 @@ def bench_reference(args):
         "warmup": args.warmup, "ms_per_step": 1000.0 * dt / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": WORKLOAD, "step": f"{cores} processes x {sample} frames x {reps} passes each (bounded sample of the clip)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "cpu_model": cpu_model(), "kind": "port",
                          "sample": f"{sample} frames x {reps} passes of the config-2 clip per process per step, PySceneDetect logic restated "
                                    f"over {res['backend']} (scenedetect itself is not installable offline), frames in RAM"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -336,7 +346,7 @@ def bench_ours(args):
         del clip
         torch.cuda.empty_cache()
         r = run_cpu_baseline(args.cpu_sample, args.cpu_reps)
-        cpu = {"value": r["frames_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+        cpu = {"value": r["frames_per_s"], "unit": UNIT, "cores": r["cores"], "cpu_model": cpu_model(), "kind": "port",
                "sample": f"{args.cpu_sample} frames of the same clip x {args.cpu_reps} passes per process, one process per core, "
                          f"PySceneDetect logic over {r['backend']} ({r['seconds']:.1f} s)",
                "per_core": r["per_core_frames_per_s"]}
