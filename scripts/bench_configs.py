@@ -173,9 +173,11 @@ def config5(dev, local, world, rank, dist, videos_per_gpu=8, n_videos=512, frame
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ms_total, frames, cuts_total = 0.0, 0, 0
     batch = 2048
-    # one untimed push first: the first launch of a kernel pays CUDA's lazy module loading (~20 ms for this library)
-    warm = fill(5000, W, H, synth.build_schedule(5000, 64).descs, dev)
+    # untimed pushes of both batch shapes first: the first launch of a kernel pays CUDA's lazy module loading (~20 ms for
+    # this library) and the first push of a batch size allocates its scratch and work plan (cudaMalloc, ~6 ms)
+    warm = fill(5000, W, H, synth.build_schedule(5000, batch).descs, dev)
     ctx.push_tensor(warm, 0, stream)
+    ctx.push_tensor(warm[:frames_per_video % batch or batch], batch, stream)
     ctx.synchronize()
     del warm
     for j in mine:
@@ -213,10 +215,9 @@ def config5(dev, local, world, rank, dist, videos_per_gpu=8, n_videos=512, frame
             "note": "bounded subset of the 512-video library; per-video throughput is independent of library size"}
 
 
-def config2_full(dev, local, n=18000):
+def config2_full(dev, local, n=18000, W=1920, H=1080, seed=1002, golden="clip_c2_1080p_full.npz", label=None):
     """BASELINE config 2 literally: the whole 10-minute 1080p clip (18 000 frames, 112 GB) resident in one B200's HBM,
-    scored by ONE esd_push_frames call; scores and cuts checked against the cv2 golden."""
-    W, H, seed = 1920, 1080, 1002
+    scored by ONE esd_push_frames call; scores and cuts checked against the cv2 golden.  (Also config 1: the 60 s 720p clip.)"""
     sch = synth.build_schedule(seed, n)
     clip = fill(seed, W, H, sch.descs, dev, chunk=512)
     torch.cuda.synchronize()
@@ -239,7 +240,7 @@ def config2_full(dev, local, n=18000):
     sc = ctx.read_scores(0, n, ["sums3", "content_val"])
     cuts, _ = ctx.get_cuts(capi.ESD_DET_CONTENT)
     parity = None
-    gp = os.path.join(GOLD, "clip_c2_1080p_full.npz")
+    gp = os.path.join(GOLD, golden)
     if os.path.exists(gp):
         g = np.load(gp)
         parity = bool(np.array_equal(sc["sums3"], g["sums3"]) and np.array_equal(sc["content_val"].view(np.uint64), g["content_val"].view(np.uint64))
@@ -247,7 +248,8 @@ def config2_full(dev, local, n=18000):
     ms = min(times)
     alg = ctx.alg_bytes_per_frame
     ctx.close()
-    return {"config": 2, "what": "whole 10-min 1080p clip (18 000 frames, 112 GB) resident, one push, ContentDetector(27,15)",
+    return {"config": 2 if label is None else 1,
+            "what": label or "whole 10-min 1080p clip (18 000 frames, 112 GB) resident, one push, ContentDetector(27,15)",
             "n_gpus": 1, "frames": n, "ms": ms, "ms_all": times, "value": n / (ms / 1000.0), "unit": "frames/s",
             "achieved_GBps": n * alg / (ms / 1000.0) / 1e9, "frac_of_measured_peak": n * alg / (ms / 1000.0) / 1e9 / peak(),
             "cuts": len(cuts), "bit_exact_vs_cv2_golden": parity}
@@ -464,6 +466,9 @@ def main():
             r = pcie_probe(dev, local) if rank == 0 else None
         elif c == "2full":
             r = config2_full(dev, local) if rank == 0 else None
+        elif c == "1":
+            r = config2_full(dev, local, n=1800, W=1280, H=720, seed=1001, golden="clip_c1_720p.npz",
+                             label="whole 60 s 720p clip (1 800 frames, 5 GB) resident, one push, ContentDetector(27,15)") if rank == 0 else None
         elif c == "extras":
             r = config_edges(dev, local) if rank == 0 else None
         else:
