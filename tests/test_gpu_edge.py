@@ -226,6 +226,9 @@ def test_bad_frame_pointers_are_rejected_before_launch():
         assert "pageable" in str(e.value)
         own = torch.empty(3 * h * w * 3 + (1 << 22), dtype=torch.uint8, device=DEV)  # private cudaMalloc-sized block
         torch.cuda.synchronize()
+        # the caching allocator must not carve `big` out of a larger block an earlier test left cached: its end has to be
+        # the end of a real cudaMalloc allocation
+        torch.cuda.empty_cache()
         big = torch.empty(1 << 28, dtype=torch.uint8, device=DEV)  # its own 256 MiB segment
         end = big.data_ptr() + big.numel()
         with pytest.raises(capi.EsdError) as e:
