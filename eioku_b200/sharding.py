@@ -79,8 +79,9 @@ def fix_video_start(merged: Dict[str, np.ndarray]) -> Dict[str, np.ndarray]:
             merged[k][0] = 0.0
     if "sums3" in merged and merged["sums3"].size:
         merged["sums3"][0] = 0
-    if "hist_diff" in merged and merged["hist_diff"].size:
-        merged["hist_diff"][0] = np.nan
+    for k in ("hist_diff", "hash_dist"):
+        if k in merged and merged[k].size:
+            merged[k][0] = np.nan
     return merged
 
 
