@@ -250,6 +250,7 @@ struct esd_ctx {
     long long* pf_mailbox = nullptr;   // pinned, host-mapped: n_cuts[5] + overflow flag written by decide_kernel
     cudaStream_t pf_stream = nullptr;
     KernelGraph kg;                    // DIRECT except inside esd_process_frame_host
+    int64_t pf_ticket = 0;             // sequence number decide_kernel posts into the mailbox when a detector's pass is done
 
     // ingest
     std::vector<IngestSlot> ring;
@@ -524,7 +525,7 @@ int reset_video_state(esd_ctx* c) {
     c->h2d_bytes = 0;
     c->h2d_copies = 0;
     c->last_batch_base = c->last_batch_n = 0;
-    if (c->pf_mailbox) memset(c->pf_mailbox, 0, 8 * sizeof(long long));
+    if (c->pf_mailbox) memset(c->pf_mailbox, 0, 8 * sizeof(long long));  // counts and overflow; the tickets keep increasing
     CU(c, cudaMemset(c->d_state, 0, sizeof(DecisionState)));
     if (c->cap) {
         fill_nan_kernel<<<(unsigned)((c->cap + 255) / 256), 256>>>(c->d_ratio, c->cap);
@@ -730,7 +731,8 @@ int push_common(esd_ctx* c, const uint8_t* d_src, int64_t n, int64_t frame_strid
         c->last_batch_n = n;
     }
     CU(c, klaunch(kg, ts, decide_kernel, dim3(5), dim3(256), 0, c->dparams, c->d_state, c->d_cuts, c->d_cv, c->d_av, c->d_ratio,
-                  c->d_hdiff, c->d_avg, c->d_hdist, (long long)c->first_frame, (long long)base, (long long)(base + n), mailbox));
+                  c->d_hdiff, c->d_avg, c->d_hdist, (long long)c->first_frame, (long long)base, (long long)(base + n), mailbox,
+                  (long long)c->pf_ticket));
     if (!inline_tail) {
         CU(c, cudaEventRecord(c->ev_fin[buf], ts));
         c->fin_recorded[buf] = true;
@@ -1691,8 +1693,8 @@ int esd_process_frame_host(esd_ctx* c, const uint8_t* h_bgr, int64_t pitch, int6
     if (!c->pf_stream) {
         CU(c, cudaStreamCreateWithFlags(&c->pf_stream, cudaStreamNonBlocking));
         CU(c, cudaHostAlloc(&c->pf_h, fb + 64, cudaHostAllocMapped));  // + slack: TMA copies are rounded up to 16 bytes
-        CU(c, cudaHostAlloc(&c->pf_mailbox, 8 * sizeof(long long), cudaHostAllocMapped));
-        memset(c->pf_mailbox, 0, 8 * sizeof(long long));
+        CU(c, cudaHostAlloc(&c->pf_mailbox, 16 * sizeof(long long), cudaHostAllocMapped));
+        memset(c->pf_mailbox, 0, 16 * sizeof(long long));
     }
     cudaStream_t st = c->pf_stream;
     // work enqueued through another entry point may still be running its tail on the library stream
@@ -1712,6 +1714,7 @@ int esd_process_frame_host(esd_ctx* c, const uint8_t* h_bgr, int64_t pitch, int6
     const bool use_graph = !no_graph && !c->need_edges && !c->timing && c->started && c->n_frames >= warm;
     KernelGraph& kg = c->kg;
     int rc;
+    ++c->pf_ticket;
     if (use_graph) {
         if (!kg.exec) {
             kg.destroy();
@@ -1732,8 +1735,23 @@ int esd_process_frame_host(esd_ctx* c, const uint8_t* h_bgr, int64_t pitch, int6
         if (rc) return rc;
     }
     trp.lap("pf enqueue");
-    CU(c, cudaStreamSynchronize(st));
-    trp.lap("pf synchronize");
+    {   // poll the completion tickets of the configured detectors in host-mapped memory (the kernels are a few tens of
+        // microseconds); a stuck or faulted launch falls through to cudaStreamSynchronize, which reports the error
+        volatile long long* mb = c->pf_mailbox;
+        const double t_poll = TraceTimer::now();
+        bool done = false;
+        for (uint32_t spins = 0; !done; ++spins) {
+            done = true;
+            for (int d = 0; d < 5; ++d)
+                if ((c->cfg.detectors & (1 << d)) && mb[8 + d] != c->pf_ticket) { done = false; break; }
+            if (!done) {
+                _mm_pause();
+                if ((spins & 0xfff) == 0xfff && TraceTimer::now() - t_poll > 20.0) break;  // 20 ms: give up polling
+            }
+        }
+        if (!done) CU(c, cudaStreamSynchronize(st));
+    }
+    trp.lap("pf wait");
     if (c->pf_mailbox[5]) return fail(c, ESD_ERR_CAPACITY, "cut list overflow (max_cuts = %lld)", (long long)c->max_cuts);
     const int64_t total = c->pf_mailbox[di];
     if (n_total) *n_total = total;
@@ -1741,8 +1759,10 @@ int esd_process_frame_host(esd_ctx* c, const uint8_t* h_bgr, int64_t pitch, int6
     const int64_t avail = std::max<int64_t>(0, total - from_index);
     const int64_t m = std::min(avail, cap);
     if (n_written) *n_written = m;
-    if (m > 0 && cuts)
+    if (m > 0 && cuts) {
+        CU(c, cudaStreamSynchronize(st));  // the cut list itself lives in device memory
         CU(c, cudaMemcpy(cuts, c->d_cuts + (int64_t)di * c->max_cuts + from_index, sizeof(int64_t) * m, cudaMemcpyDeviceToHost));
+    }
     if (avail > cap) return fail(c, ESD_ERR_CAPACITY, "process_frame: %lld cuts pending, buffer holds %lld", (long long)avail, (long long)cap);
     return ESD_OK;
 }
@@ -1783,7 +1803,7 @@ int esd_decide_arrays(esd_ctx* c, int32_t detector, int64_t first_frame_num, int
             adaptive_ratio_kernel<<<(unsigned)((n - 2 * w + 255) / 256), 256>>>(d_scores, d_ratio, w, n - w, w,
                                                                                P.adaptive_min_content_val);
     }
-    decide_kernel<<<5, 256>>>(P, d_st, d_cuts, d_scores, d_scores, d_ratio, d_scores, d_scores, d_scores, first_frame_num, 0, n, nullptr);
+    decide_kernel<<<5, 256>>>(P, d_st, d_cuts, d_scores, d_scores, d_ratio, d_scores, d_scores, d_scores, first_frame_num, 0, n, nullptr, 0LL);
     c->launches += 3;
     CUD(cudaGetLastError());
     CUD(cudaDeviceSynchronize());

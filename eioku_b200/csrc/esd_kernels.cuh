@@ -1285,7 +1285,7 @@ __global__ void decide_kernel(DecisionParams P, DecisionState* __restrict__ st, 
                               const double* __restrict__ adaptive_ratio, const double* __restrict__ hist_diff,
                               const double* __restrict__ average_rgb, const double* __restrict__ hash_dist,
                               long long first_frame_num, long long i_begin, long long i_end,
-                              long long* __restrict__ mailbox) {
+                              long long* __restrict__ mailbox, long long ticket) {
     constexpr int CH = 8192;
     __shared__ uint32_t bits[CH / 32];
     const int det = blockIdx.x;
@@ -1451,8 +1451,14 @@ __global__ void decide_kernel(DecisionParams P, DecisionState* __restrict__ st, 
     if (tid == 0) {
         st->n_cuts[det] = sink.n;
         if (sink.overflow) st->overflow = 1;
-        // per-frame path: cut count and overflow flag straight into host-mapped pinned memory (no D2H copy)
-        if (mailbox) { mailbox[det] = sink.n; if (sink.overflow) mailbox[5] = 1; }
+        // per-frame path: cut count and overflow flag straight into host-mapped pinned memory (no D2H copy), then this
+        // detector's completion ticket -- the host polls the tickets instead of paying a stream synchronise
+        if (mailbox) {
+            mailbox[det] = sink.n;
+            if (sink.overflow) mailbox[5] = 1;
+            __threadfence_system();
+            *reinterpret_cast<volatile long long*>(mailbox + 8 + det) = ticket;
+        }
         if (det == 0) {
             st->c_last_above = last; st->c_merge_start = merge_start; st->c_init = init;
             st->c_merge_enabled = merge_enabled; st->c_merge_triggered = merge_triggered;

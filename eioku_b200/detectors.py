@@ -136,6 +136,9 @@ class SceneDetector:
         self._fill_config(cfg)
         cfg.src_width, cfg.src_height = width, height
         cfg.dst_width, cfg.dst_height = width, height  # stand-alone detectors never resize (SceneManager does)
+        if width * height <= 512 * 512:
+            # frame-by-frame callers: smaller row groups spread one small frame over more CTAs (-5 us per call)
+            cfg.rows_per_group = 4
         return capi.EsdContext(cfg, device)
 
     def _validate_frame(self, frame_img):
