@@ -292,7 +292,10 @@ def bench_ours(args):
             share = (os.cpu_count() or 1) // world
         # measured (profiles/r01_pcie.log): gather beats the 28-30 k frames/s of plain DMA from ~10 threads up
         gthreads = share if share >= 10 else 0
-    ectx.ingest_open(4, 128) if gthreads else ectx.ingest_open(3, 256)
+    if args.e2e_ring:
+        ectx.ingest_open(*[int(v) for v in args.e2e_ring.split("x")])
+    else:
+        ectx.ingest_open(4, 128) if gthreads else ectx.ingest_open(3, 256)
     ectx.ingest_set_gather(gthreads)
     e2e_steps = max(2, min(args.steps, 6))
 
@@ -390,6 +393,7 @@ def main():
     ap.add_argument("--cpu-reps", type=int, default=40)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-gather-threads", type=int, default=-1, help="host gather threads of the e2e leg (-1 = this rank's share of cores, 0 = DMA rows)")
+    ap.add_argument("--e2e-ring", default="", help="ingest ring of the e2e leg as SLOTSxFRAMES (default 4x128 with gather, 3x256 DMA)")
     ap.add_argument("--ref-sample", type=int, default=192, help="--impl reference: frames per process per pass")
     ap.add_argument("--ref-reps", type=int, default=8, help="--impl reference: passes per process per step")
     ap.add_argument("--tune", action="append", default=[], help="esd_config field=value (e.g. rows_per_group=2)")

@@ -41,6 +41,34 @@ def scenes_to_dicts(scenes: Sequence[Tuple[int, int]], fps: float) -> List[dict]
     return out
 
 
+_METHOD_OF = {"ContentDetector": ("content", "content_val"), "AdaptiveDetector": ("adaptive", "adaptive_ratio"),
+              "HistogramDetector": ("hist", "hist_diff"), "ThresholdDetector": ("threshold", "average_rgb"),
+              "HashDetector": ("hash", "hash_dist")}
+
+
+def scene_artifact_payloads(sm: SceneManager) -> List[dict]:
+    """Scene artifact payloads of the reference's artifact-envelope design -- ``SceneV1 {scene_index, method, score,
+    frame_number}`` (/root/reference/.kiro/specs/artifact-envelope-architecture/design.md:159-167, requirements.md:173-183;
+    specified, never implemented there).  One record per scene: the first scene starts at the first frame (method
+    "start", score 0.0); every other scene starts at a cut and carries the detector that emitted it and that detector's
+    metric at the cut frame.  Needs ``detect_scenes(..., collect_scores=True)``."""
+    if sm._start_pos is None or sm._last_pos is None:
+        return []
+    start = sm._start_pos
+    by_frame = {}
+    for det in sm._detector_list:
+        method, key = _METHOD_OF[type(det).__name__]
+        vals = sm.scores.get(key)
+        for cut in sm.cuts_of(det):
+            score = float(vals[cut - start]) if vals is not None and 0 <= cut - start < len(vals) else float("nan")
+            by_frame.setdefault(cut, (method, score))  # first registered detector wins when two agree on a frame
+    out = [{"scene_index": 0, "method": "start", "score": 0.0, "frame_number": start}]
+    for cut in sorted(by_frame):
+        method, score = by_frame[cut]
+        out.append({"scene_index": len(out), "method": method, "score": score, "frame_number": int(cut)})
+    return out
+
+
 def frame_to_timecode(frame: int, fps: float, precision: int = 3) -> str:
     """HH:MM:SS.nnn of a frame number, formatted like scenedetect.FrameTimecode.get_timecode (rounded to
     `precision` decimals, with the 60-second carry guard) [upstream-recall]."""
@@ -163,14 +191,18 @@ def detect_scenes_frames(video, config: Optional[dict] = None, fps: Optional[flo
         sm.auto_downscale = False
     for det in build_detectors(config):
         sm.add_detector(det)
+    want_artifacts = bool(config.get("artifact_payloads"))
     try:
-        n = sm.detect_scenes(video)
+        n = sm.detect_scenes(video, collect_scores=want_artifacts)
         rate = fps or video.frame_rate
         if n == 0:
-            return {"scenes": []}
+            return {"scenes": [], "artifact_payloads": []} if want_artifacts else {"scenes": []}
         # the reference always reports at least one scene for a readable video (model_manager.py:816-828)
         scenes = sm.get_scene_list(start_in_scene=True)
-        return {"scenes": scenes_to_dicts(scenes, rate)}
+        out = {"scenes": scenes_to_dicts(scenes, rate)}
+        if want_artifacts:  # opt-in: the artifact-envelope SceneV1 payloads next to the task schema
+            out["artifact_payloads"] = scene_artifact_payloads(sm)
+        return out
     finally:
         sm.close()
 

@@ -116,3 +116,28 @@ def test_deferred_mode_reports_the_same_cuts_late(which, defer):
     want += ref.post_process(len(clip) - 1)
     assert got == want
     det.close()
+
+
+def test_scene_artifact_payloads_of_the_artifact_envelope_spec():
+    """config["artifact_payloads"]: SceneV1 {scene_index, method, score, frame_number} records (reference spec
+    .kiro/specs/artifact-envelope-architecture/design.md:159-167) next to the unchanged task schema."""
+    from eioku_b200.service import detect_scenes_frames
+
+    clip = small_clip(150)
+    plain = detect_scenes_frames(clip, {"detector": "content", "threshold": 20.0, "min_scene_len": 5, "fps": 30.0})
+    rich = detect_scenes_frames(clip, {"detector": "content+hist", "threshold": 20.0, "min_scene_len": 5, "fps": 30.0,
+                                       "hist_threshold": 0.1, "bins": 64, "artifact_payloads": True})
+    assert set(plain) == {"scenes"} and len(plain["scenes"]) >= 3
+    recs = rich["artifact_payloads"]
+    assert len(recs) == len(rich["scenes"]) and recs[0] == {"scene_index": 0, "method": "start", "score": 0.0, "frame_number": 0}
+    ref = P.ContentDetector(threshold=20.0, min_scene_len=5)
+    cuts = []
+    for k in range(len(clip)):
+        cuts += ref.process_frame(k, clip[k])
+    by_frame = {r["frame_number"]: r for r in recs[1:]}
+    for c in cuts:
+        assert by_frame[c]["method"] == "content" and by_frame[c]["score"] == ref.scores[c] >= 20.0
+    for i, r in enumerate(recs):
+        assert r["scene_index"] == i and set(r) == {"scene_index", "method", "score", "frame_number"}
+        assert int(r["frame_number"] / 30.0 * 1000) == rich["scenes"][i]["start_ms"]
+        assert r["method"] in ("start", "content", "hist")
