@@ -51,6 +51,8 @@ def check_bits(got, want, margins, what=""):
     (320, 180, 3, 2),    # odd bit count (9): the median is the middle element
     (300, 200, 32, 2),   # the largest supported hash: 1024 bits from a 64 x 64 DCT
     (200, 120, 5, 4),
+    (1920, 1080, 16, 2),  # stand-alone detector on full-resolution frames: 60-byte integer column sums, 3 bands of rows
+    (640, 360, 16, 2), (1000, 2000, 16, 2),
 ])
 def test_hash_stages_vs_cv2(w, h, size, lowpass):
     rng = np.random.default_rng(w * 131 + h * 7 + size)
