@@ -170,6 +170,7 @@ struct esd_ctx {
     int alg_row_bytes = 0;  // 32-byte sectors of a row that contain a horizontal tap, in bytes
     int64_t alg_frame_bytes = 0;  // sum over the touched rows (NV12: Y rows and UV rows have different sector sets)
     bool nv12 = false;
+    bool extras = false;    // the fused kernel also emits sum(B+G+R) / the V plane / the gray plane (kernel template EXTRAS)
     int n_touched_y = 0;    // NV12: the first n_touched_y entries of `touched` are Y rows, the rest UV rows (as H + row)
     bool resize = false;
     int pxt = 1;
@@ -321,36 +322,40 @@ int64_t gcd64(int64_t a, int64_t b) { while (b) { int64_t t = a % b; a = b; b = 
 // Python round(): half to even on the double quotient
 long py_round(double x) { return lrint(x); }
 
-// the kernel instance for a (content, hist, aligned, nv12) combination; NV12 exists only for resizing contexts
-template <bool RESIZE, int PXT>
-void (*fused_fn(bool content, bool hist, bool aligned, bool nv12))(const FusedParams) {
-#define ESD_PICK(C, H)                                                                                           \
-    do {                                                                                                         \
-        if constexpr (RESIZE && PXT <= 4) {                                                                      \
-            if (nv12) return aligned ? fused_score_kernel<RESIZE, PXT, C, H, true, true> : fused_score_kernel<RESIZE, PXT, C, H, false, true>; \
-        }                                                                                                        \
-        return aligned ? fused_score_kernel<RESIZE, PXT, C, H, true> : fused_score_kernel<RESIZE, PXT, C, H, false>; \
-    } while (0)
-    if (content && hist) ESD_PICK(true, true);
-    if (content) ESD_PICK(true, false);
-    ESD_PICK(false, true);
-#undef ESD_PICK
+// the kernel instance for a (content, hist, aligned, nv12, extras) combination; NV12 exists only for resizing contexts
+template <bool RESIZE, int PXT, bool C, bool H>
+void (*fused_fn_ch(bool aligned, bool nv12, bool extras))(const FusedParams) {
+    if constexpr (RESIZE && PXT <= 4) {
+        if (nv12) {
+            if (extras) return aligned ? fused_score_kernel<RESIZE, PXT, C, H, true, true, true> : fused_score_kernel<RESIZE, PXT, C, H, false, true, true>;
+            return aligned ? fused_score_kernel<RESIZE, PXT, C, H, true, true, false> : fused_score_kernel<RESIZE, PXT, C, H, false, true, false>;
+        }
+    }
+    if (extras) return aligned ? fused_score_kernel<RESIZE, PXT, C, H, true, false, true> : fused_score_kernel<RESIZE, PXT, C, H, false, false, true>;
+    return aligned ? fused_score_kernel<RESIZE, PXT, C, H, true, false, false> : fused_score_kernel<RESIZE, PXT, C, H, false, false, false>;
 }
 
 template <bool RESIZE, int PXT>
-cudaError_t launch_fused_rp(bool content, bool hist, bool aligned, bool nv12, const FusedParams& p, int grid, size_t smem,
+void (*fused_fn(bool content, bool hist, bool aligned, bool nv12, bool extras))(const FusedParams) {
+    if (content && hist) return fused_fn_ch<RESIZE, PXT, true, true>(aligned, nv12, extras);
+    if (content) return fused_fn_ch<RESIZE, PXT, true, false>(aligned, nv12, extras);
+    return fused_fn_ch<RESIZE, PXT, false, true>(aligned, nv12, extras);
+}
+
+template <bool RESIZE, int PXT>
+cudaError_t launch_fused_rp(bool content, bool hist, bool aligned, bool nv12, bool extras, const FusedParams& p, int grid, size_t smem,
                             cudaStream_t st, KernelGraph& kg) {
-    return klaunch(kg, st, fused_fn<RESIZE, PXT>(content, hist, aligned, nv12), dim3(grid), dim3(kThreads), smem, p);
+    return klaunch(kg, st, fused_fn<RESIZE, PXT>(content, hist, aligned, nv12, extras), dim3(grid), dim3(kThreads), smem, p);
 }
 
 template <bool RESIZE, int PXT>
-cudaError_t occupancy_rp(bool content, bool hist, bool nv12, size_t smem, int* out) {
+cudaError_t occupancy_rp(bool content, bool hist, bool nv12, bool extras, size_t smem, int* out) {
     for (int al = 0; al < 2; ++al) {
-        cudaError_t e = cudaFuncSetAttribute(fused_fn<RESIZE, PXT>(content, hist, al != 0, nv12),
+        cudaError_t e = cudaFuncSetAttribute(fused_fn<RESIZE, PXT>(content, hist, al != 0, nv12, extras),
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, fused_fn<RESIZE, PXT>(content, hist, true, nv12), kThreads, smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, fused_fn<RESIZE, PXT>(content, hist, true, nv12, extras), kThreads, smem);
 }
 
 #define ESD_DISPATCH(FN, resize, pxt, ...)                                           \
@@ -668,7 +673,7 @@ int push_common(esd_ctx* c, const uint8_t* d_src, int64_t n, int64_t frame_strid
     }
     const bool aligned = ((reinterpret_cast<uintptr_t>(d_src) | (c->nv12 ? reinterpret_cast<uintptr_t>(p.src_uv) : 0) |
                            (uintptr_t)frame_stride | (uintptr_t)row_stride) & 15u) == 0;
-    CU(c, ESD_DISPATCH(launch_fused_rp, c->resize, c->pxt, c->need_content, c->need_hist, aligned, c->nv12, p, plan.grid, c->smem_bytes, st, kg));
+    CU(c, ESD_DISPATCH(launch_fused_rp, c->resize, c->pxt, c->need_content, c->need_hist, aligned, c->nv12, c->extras, p, plan.grid, c->smem_bytes, st, kg));
     c->launches++;
     tr.lap("launch fused");
     if (c->timing) {
@@ -900,6 +905,7 @@ int esd_create(esd_ctx** out, const esd_config* cfg, int device) {
     c->need_hist = (cfg->detectors & ESD_DET_HIST) != 0;
     c->need_edges = ((cfg->detectors & ESD_DET_CONTENT) && cfg->content_weights[3] > 0.0) ||
                     ((cfg->detectors & ESD_DET_ADAPTIVE) && cfg->adaptive_weights[3] > 0.0);
+    c->extras = c->need_edges || c->need_hash || (cfg->detectors & ESD_DET_THRESHOLD) != 0;
     if (c->need_edges) {
         // _estimated_kernel_size: 4 + round(sqrt(w * h) / 192), made odd
         int ks = cfg->edge_kernel_size;
@@ -1171,7 +1177,7 @@ int esd_create(esd_ctx** out, const esd_config* cfg, int device) {
         return bail(ESD_ERR_UNSUPPORTED);
     }
     int occ = 0;
-    CUB(ESD_DISPATCH(occupancy_rp, c->resize, c->pxt, c->need_content, c->need_hist, c->nv12, c->smem_bytes, &occ));
+    CUB(ESD_DISPATCH(occupancy_rp, c->resize, c->pxt, c->need_content, c->need_hist, c->nv12, c->extras, c->smem_bytes, &occ));
     if (occ < 1) {
         fail(c, ESD_ERR_UNSUPPORTED, "fused kernel does not fit on an SM (smem %zu)", c->smem_bytes);
         return bail(ESD_ERR_UNSUPPORTED);

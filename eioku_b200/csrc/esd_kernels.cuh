@@ -193,7 +193,9 @@ __device__ __forceinline__ void nv12_pixel(int y, const Chroma& c, int& b, int& 
 
 // One destination row of one frame for one consumer thread (PXT columns).  SPECIAL = the stage carries a rare flag
 // (halo frame, first frame of the video / of the batch, last frame of the batch); the common path has none.
-template <bool RESIZE, int PXT, bool CONTENT, bool HIST, bool SPECIAL, bool NV12>
+// EXTRAS = this launch needs one of the per-pixel side outputs (sum of B+G+R for ThresholdDetector, V plane for the edge
+// detector, gray plane for the hash detector); the common launches compile all three out (9-12 instructions per pixel).
+template <bool RESIZE, int PXT, bool CONTENT, bool HIST, bool SPECIAL, bool NV12, bool EXTRAS>
 __device__ __forceinline__ void score_row(const FusedParams& p, const uint8_t* __restrict__ row0, const uint8_t* __restrict__ row1,
                                           const uint8_t* __restrict__ uv0, const uint8_t* __restrict__ uv1, uint32_t misuv,
                                           uint32_t mis0, uint32_t mis1, uint32_t b0s, uint32_t b1s, int flags, int rloc,
@@ -259,7 +261,7 @@ __device__ __forceinline__ void score_row(const FusedParams& p, const uint8_t* _
                 r = (px >> 16) & 255u;
             }
             if (CONTENT) {
-                if (p.want_bgr && !(SPECIAL && (flags & F_HALO))) acc_bgr += (uint32_t)(b + g + r);
+                if (EXTRAS && p.want_bgr && !(SPECIAL && (flags & F_HALO))) acc_bgr += (uint32_t)(b + g + r);
                 const uint32_t cur = bgr_to_hsv_packed(b, g, r, s_sdiv, s_hdiv);
                 uint32_t* slot = s_prev + (rloc * PXT + k) * kConsumers + tid;
                 uint32_t pv;
@@ -271,7 +273,7 @@ __device__ __forceinline__ void score_row(const FusedParams& p, const uint8_t* _
                 } else {
                     pv = *slot;
                 }
-                if (p.vplane && !(SPECIAL && (flags & F_HALO)))
+                if (EXTRAS && p.vplane && !(SPECIAL && (flags & F_HALO)))
                     p.vplane[((size_t)frame * p.dst_h + row) * p.dst_w + d] = (uint8_t)(cur >> 16);
                 const uint32_t diff = __vabsdiffu4(cur, pv);
                 acc_hv += diff & 0x00ff00ffu;
@@ -282,7 +284,7 @@ __device__ __forceinline__ void score_row(const FusedParams& p, const uint8_t* _
                 const int y = (4899 * r + 9617 * g + 1868 * b + 8192) >> 14;
                 atomicAdd(&s_hist_cur[(y * p.bins) >> 8], 1u);
             }
-            if (p.gplane && !(SPECIAL && (flags & F_HALO)))
+            if (EXTRAS && p.gplane && !(SPECIAL && (flags & F_HALO)))
                 p.gplane[((size_t)frame * p.dst_h + row) * p.dst_w + d] = bgr_to_gray(b, g, r);
         }
     }
@@ -290,7 +292,7 @@ __device__ __forceinline__ void score_row(const FusedParams& p, const uint8_t* _
 
 // Full-resolution rows (no resize) with 16-byte aligned rows: a thread takes four consecutive pixels = three aligned
 // words, so there are no funnel shifts, the previous HSV moves as one 16-byte vector and guards are per quad.
-template <int QPT, bool CONTENT, bool HIST, bool SPECIAL>
+template <int QPT, bool CONTENT, bool HIST, bool SPECIAL, bool EXTRAS>
 __device__ __forceinline__ void score_row_quads(const FusedParams& p, const uint8_t* __restrict__ row0, int flags, int rloc,
                                                 int row, int frame, int tid, const int* __restrict__ s_sdiv,
                                                 const int* __restrict__ s_hdiv, uint32_t* __restrict__ s_prev,
@@ -310,12 +312,12 @@ __device__ __forceinline__ void score_row_quads(const FusedParams& p, const uint
             for (int e = 0; e < 4; ++e) {
                 const int b = px[e] & 255u, g = (px[e] >> 8) & 255u, r = (px[e] >> 16) & 255u;
                 cur[e] = CONTENT ? bgr_to_hsv_packed(b, g, r, s_sdiv, s_hdiv) : 0u;
-                if (CONTENT && p.want_bgr && e < nvalid && !(SPECIAL && (flags & F_HALO))) acc_bgr += (uint32_t)(b + g + r);
+                if (EXTRAS && CONTENT && p.want_bgr && e < nvalid && !(SPECIAL && (flags & F_HALO))) acc_bgr += (uint32_t)(b + g + r);
                 if (HIST && e < nvalid && !(SPECIAL && (flags & F_HALO))) {
                     const int y = (4899 * r + 9617 * g + 1868 * b + 8192) >> 14;
                     atomicAdd(&s_hist_cur[(y * p.bins) >> 8], 1u);
                 }
-                if (p.gplane && e < nvalid && !(SPECIAL && (flags & F_HALO)))
+                if (EXTRAS && p.gplane && e < nvalid && !(SPECIAL && (flags & F_HALO)))
                     p.gplane[((size_t)frame * p.dst_h + row) * p.dst_w + 4 * q + e] = bgr_to_gray(b, g, r);
             }
             if (CONTENT) {
@@ -332,13 +334,13 @@ __device__ __forceinline__ void score_row_quads(const FusedParams& p, const uint
                     }
                     if (flags & F_SAVE)
                         for (int e = 0; e < nvalid; ++e) p.prev_out[(size_t)row * p.dst_w + 4 * q + e] = cur[e];
-                    if (p.vplane && !(flags & F_HALO))
+                    if (EXTRAS && p.vplane && !(flags & F_HALO))
                         for (int e = 0; e < nvalid; ++e)
                             p.vplane[((size_t)frame * p.dst_h + row) * p.dst_w + 4 * q + e] = (uint8_t)(cur[e] >> 16);
                 } else {
                     const uint4 t = *slot;
                     pv[0] = t.x; pv[1] = t.y; pv[2] = t.z; pv[3] = t.w;
-                    if (p.vplane)
+                    if (EXTRAS && p.vplane)
                         for (int e = 0; e < nvalid; ++e)
                             p.vplane[((size_t)frame * p.dst_h + row) * p.dst_w + 4 * q + e] = (uint8_t)(cur[e] >> 16);
                 }
@@ -356,7 +358,7 @@ __device__ __forceinline__ void score_row_quads(const FusedParams& p, const uint
 
 // ALIGNED: every source row starts on a 16-byte boundary (base, pitch and frame stride multiples of 16), so the
 // per-row misalignment is zero and each thread's smem word offset / funnel shift are loop invariants.
-template <bool RESIZE, int PXT, bool CONTENT, bool HIST, bool ALIGNED, bool NV12 = false>
+template <bool RESIZE, int PXT, bool CONTENT, bool HIST, bool ALIGNED, bool NV12 = false, bool EXTRAS = true>
 __global__ void __launch_bounds__(kThreads) fused_score_kernel(const FusedParams p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     // ---- carve shared memory (host twin: fused_smem_bytes in esd.cu)
@@ -529,7 +531,7 @@ __global__ void __launch_bounds__(kThreads) fused_score_kernel(const FusedParams
         if (flags & (F_HALO | F_NOPREV | F_CTXPREV | F_SAVE)) {
             for (int q = 0; q < nrows; ++q) {
                 if (kQuads) {
-                    score_row_quads<(PXT >= 4 ? PXT / 4 : 1), CONTENT, HIST, true>(p, stage + q * row_slot, flags, rloc0 + q, row_first + q,
+                    score_row_quads<(PXT >= 4 ? PXT / 4 : 1), CONTENT, HIST, true, EXTRAS>(p, stage + q * row_slot, flags, rloc0 + q, row_first + q,
                                                                                    m.x, tid, s_sdiv, s_hdiv, s_prev, hist_cur, acc_hv,
                                                                                    acc_s, acc_bgr);
                     continue;
@@ -538,7 +540,7 @@ __global__ void __launch_bounds__(kThreads) fused_score_kernel(const FusedParams
                 const uint32_t mis0 = ALIGNED ? 0u : (mr.z & 0xffu), mis1 = ALIGNED ? 0u : ((mr.z >> 8) & 0xffu);
                 const uint8_t* uvp0 = stage + q * row_slot + 2 * p.rowbuf;
                 const uint8_t* uvp1 = (mr.w & 0x10000u) ? uvp0 : uvp0 + p.rowbuf;
-                score_row<RESIZE, PXT, CONTENT, HIST, true, NV12>(p, stage + q * row_slot, stage + q * row_slot + p.rowbuf, uvp0, uvp1,
+                score_row<RESIZE, PXT, CONTENT, HIST, true, NV12, EXTRAS>(p, stage + q * row_slot, stage + q * row_slot + p.rowbuf, uvp0, uvp1,
                                                                   ALIGNED ? (mr.w & 0x10000u) : mr.w, mis0, mis1, mr.x, mr.y, flags, rloc0 + q,
                                                                   row_first + q, m.x, tid, xoff, xa01, s_sdiv, s_hdiv, s_prev,
                                                                   hist_cur, acc_hv, acc_s, acc_bgr);
@@ -546,7 +548,7 @@ __global__ void __launch_bounds__(kThreads) fused_score_kernel(const FusedParams
         } else {
             for (int q = 0; q < nrows; ++q) {
                 if (kQuads) {
-                    score_row_quads<(PXT >= 4 ? PXT / 4 : 1), CONTENT, HIST, false>(p, stage + q * row_slot, flags, rloc0 + q, row_first + q,
+                    score_row_quads<(PXT >= 4 ? PXT / 4 : 1), CONTENT, HIST, false, EXTRAS>(p, stage + q * row_slot, flags, rloc0 + q, row_first + q,
                                                                                     m.x, tid, s_sdiv, s_hdiv, s_prev, hist_cur, acc_hv,
                                                                                     acc_s, acc_bgr);
                     continue;
@@ -555,7 +557,7 @@ __global__ void __launch_bounds__(kThreads) fused_score_kernel(const FusedParams
                 const uint32_t mis0 = ALIGNED ? 0u : (mr.z & 0xffu), mis1 = ALIGNED ? 0u : ((mr.z >> 8) & 0xffu);
                 const uint8_t* uvp0 = stage + q * row_slot + 2 * p.rowbuf;
                 const uint8_t* uvp1 = (mr.w & 0x10000u) ? uvp0 : uvp0 + p.rowbuf;
-                score_row<RESIZE, PXT, CONTENT, HIST, false, NV12>(p, stage + q * row_slot, stage + q * row_slot + p.rowbuf, uvp0, uvp1,
+                score_row<RESIZE, PXT, CONTENT, HIST, false, NV12, EXTRAS>(p, stage + q * row_slot, stage + q * row_slot + p.rowbuf, uvp0, uvp1,
                                                                    ALIGNED ? (mr.w & 0x10000u) : mr.w, mis0, mis1, mr.x, mr.y, flags, rloc0 + q,
                                                                    row_first + q, m.x, tid, xoff, xa01, s_sdiv, s_hdiv, s_prev,
                                                                    hist_cur, acc_hv, acc_s, acc_bgr);
@@ -573,7 +575,7 @@ __global__ void __launch_bounds__(kThreads) fused_score_kernel(const FusedParams
                     const uint32_t sh = __reduce_add_sync(0xffffffffu, acc_hv & 0xffffu);
                     const uint32_t sv = __reduce_add_sync(0xffffffffu, acc_hv >> 16);
                     const uint32_t ss = __reduce_add_sync(0xffffffffu, acc_s);
-                    const uint32_t sb = p.want_bgr ? __reduce_add_sync(0xffffffffu, acc_bgr) : 0u;
+                    const uint32_t sb = (EXTRAS && p.want_bgr) ? __reduce_add_sync(0xffffffffu, acc_bgr) : 0u;
                     if (lane == 0)
                         p.part[((size_t)m.x * p.n_groups + group) * kConsumerWarps + warp] = make_uint4(sh, ss, sv, sb);
                 }
