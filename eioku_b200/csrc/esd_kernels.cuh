@@ -155,7 +155,10 @@ __device__ __forceinline__ uint32_t bgr_to_hsv_packed(int b, int g, int r, const
     int m = min(min(b, g), r);
     int diff = v - m;
     int s = (diff * sdiv[v] + (1 << 11)) >> 12;
-    int h = (v == r) ? (g - b) : ((v == g) ? (b - r + 2 * diff) : (r - g + 4 * diff));
+    // branch-free select (a divergent branch here cost more issue slots than the two spare subtractions)
+    const int hr = g - b, hg = b - r + 2 * diff, hb = r - g + 4 * diff;
+    int h = (v == g) ? hg : hb;
+    h = (v == r) ? hr : h;
     h = (h * hdiv[diff] + (1 << 11)) >> 12;
     h += (h < 0) ? 180 : 0;
     return (uint32_t)h | ((uint32_t)s << 8) | ((uint32_t)v << 16);
@@ -469,7 +472,7 @@ __global__ void __launch_bounds__(kThreads) fused_score_kernel(const FusedParams
                         }
                     }
                     const int flags = fflags | ((r + nr >= r_end) ? F_FRAME_END : 0);
-                    meta[s] = make_int4(f, (r - r_begin) | (r << 8), flags, nr);
+                    meta[s] = make_int4(f, (r - r_begin) | (r << 8), flags, nr | (un.rg << 8));  // w: rows in the stage | row group << 8
                     const uint32_t bar = full_base + 8u * s;
                     const uint32_t dst = stage_base + (uint32_t)s * stage_bytes;
                     mbar_arrive_expect_tx(bar, tx);
@@ -523,7 +526,7 @@ __global__ void __launch_bounds__(kThreads) fused_score_kernel(const FusedParams
         const int4 m = meta[s];
         const int flags = m.z;
         if (flags & F_END) break;
-        const int nrows = m.w;
+        const int nrows = m.w & 0xff;
         const int rloc0 = m.y & 0xff;
         const int row_first = m.y >> 8;
         const uint8_t* stage = s_stage + (size_t)s * stage_bytes;
@@ -569,7 +572,7 @@ __global__ void __launch_bounds__(kThreads) fused_score_kernel(const FusedParams
 
         if (flags & F_FRAME_END) {
             const bool scored = !(flags & F_HALO);
-            const int group = row_first / p.rows_per_group;
+            const int group = m.w >> 8;
             if (CONTENT) {
                 if (scored) {
                     const uint32_t sh = __reduce_add_sync(0xffffffffu, acc_hv & 0xffffu);
