@@ -157,7 +157,10 @@ ESD_API int esd_get_touched_rows(const esd_ctx* ctx, int32_t* rows, int32_t cap)
  * Asynchronous on `stream`. */
 ESD_API int esd_push_frames(esd_ctx* ctx, const uint8_t* d_bgr, int64_t n, int64_t frame_stride_bytes,
                     int64_t pitch_bytes, int64_t first_frame_num, void* stream);
-/* NV12 contexts: Y plane and interleaved UV plane given separately (as a decoder surface has them: the UV plane usually
+/* Replaces: the BGR conversion a decoder hand-off performs before scoring -- `cv2.VideoCapture.read()` delivers BGR made by
+ * swscale from the decoder's YUV 4:2:0 output (the other tasks' decode loop, model_manager.py:237-263); here the decoder's
+ * surface is consumed as it is and converted in the kernel with cv2.cvtColor(COLOR_YUV2BGR_NV12)'s arithmetic.
+ * NV12 contexts: Y plane and interleaved UV plane given separately (as a decoder surface has them: the UV plane usually
  * starts at an aligned height); both use `pitch_bytes` and `frame_stride_bytes`.  esd_push_frames on an NV12 context is
  * the contiguous case d_uv = d_y + src_height * pitch_bytes.  This is the device half of SURVEY.md 8f N1 (decode ->
  * device): the scoring chain consumes decoder surfaces directly, 0.97 MB instead of 1.66 MB per 1080p frame. */
@@ -213,7 +216,10 @@ ESD_API int esd_read_scores(esd_ctx* ctx, int64_t from_frame, int64_t n, uint64_
  * only when a delta_edges weight is > 0.  Synchronises. */
 ESD_API int esd_read_edge_counts(esd_ctx* ctx, int64_t from_frame, int64_t n, uint32_t* counts);
 
-/* HashDetector's per-frame results: `bits` [n][ceil(size*size/32)] (bit i of the row-major size x size hash in word
+/* Replaces: nothing in the shipped reference (its ffmpeg scene filter has one fixed metric, model_manager.py:731-745);
+ * PySceneDetect's HashDetector.process_frame / StatsManager metric `hash_dist [size=N lowpass=M]` in the specified design
+ * (README.md:56 names PySceneDetect as the scene detector).
+ * HashDetector's per-frame results: `bits` [n][ceil(size*size/32)] (bit i of the row-major size x size hash in word
  * i / 32, bit i % 32; padding bits zero) and `hash_dist` = Hamming distance to the previous frame / size^2 (NaN for the
  * first frame).  Either pointer may be NULL.  The integer stages (BGR2GRAY, INTER_AREA) are bit-exact with OpenCV; the
  * DCT is evaluated in float64, so a bit whose coefficient lies within float32 rounding noise of the median may differ
