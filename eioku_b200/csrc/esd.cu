@@ -1696,9 +1696,10 @@ int esd_process_frame_host(esd_ctx* c, const uint8_t* h_bgr, int64_t pitch, int6
     CU(c, cudaSetDevice(c->device));
     const int H = c->cfg.src_height;
     const size_t fb = (size_t)H * c->row_bytes;
-    if (!c->pf_stream) {
-        CU(c, cudaStreamCreateWithFlags(&c->pf_stream, cudaStreamNonBlocking));
-        CU(c, cudaHostAlloc(&c->pf_h, fb + 64, cudaHostAllocMapped));  // + slack: TMA copies are rounded up to 16 bytes
+    // first call: each resource on its own, so a failed allocation is retried instead of leaving a half-built path
+    if (!c->pf_stream) CU(c, cudaStreamCreateWithFlags(&c->pf_stream, cudaStreamNonBlocking));
+    if (!c->pf_h) CU(c, cudaHostAlloc(&c->pf_h, fb + 64, cudaHostAllocMapped));  // + slack: TMA copies are rounded up to 16 bytes
+    if (!c->pf_mailbox) {
         CU(c, cudaHostAlloc(&c->pf_mailbox, 16 * sizeof(long long), cudaHostAllocMapped));
         memset(c->pf_mailbox, 0, 16 * sizeof(long long));
     }
