@@ -321,3 +321,65 @@ def test_sharded_detect_gloo_world2():
         assert p.exitcode == 0
     assert out["n"] == 160 and out["sum0"] == [0, 0, 0]
     assert out["adaptive"] == want and len(want) >= 2
+
+
+# ------------------------------------------------------------------------------------------- later round-1 additions
+def test_hash_detector_fills_config_and_metric_key():
+    from eioku_b200.detectors import HashDetector
+
+    cfg = capi.default_config()
+    cfg.detectors = 0
+    d = HashDetector(threshold=0.3, size=8, lowpass=4, min_scene_len=9)
+    d._fill_config(cfg)
+    assert cfg.detectors == capi.ESD_DET_HASH
+    assert (cfg.hash_threshold, cfg.hash_size, cfg.hash_lowpass, cfg.hash_min_scene_len) == (0.3, 8, 4, 9)
+    assert d.get_metrics() == ["hash_dist [size=8 lowpass=4]"] and d.event_buffer_length == 0
+    assert d.defer(32).event_buffer_length == 31
+    a = AdaptiveDetector(window_width=3).defer(8)
+    assert a.event_buffer_length == 3 + 7
+
+
+def test_nv12_video_geometry_and_test_content():
+    from eioku_b200 import synth
+    from eioku_b200.scene_manager import TensorVideo
+
+    rng = np.random.default_rng(0)
+    bgr = rng.integers(0, 256, (3, 8, 12, 3), dtype=np.uint8)
+    nv12 = synth.bgr_to_test_nv12(bgr)
+    assert nv12.shape == (3, 12, 12)
+    assert np.array_equal(nv12[:, :8], bgr[..., 1])
+    assert np.array_equal(nv12[:, 8:, 0::2], bgr[:, 0::2, 0::2, 0]) and np.array_equal(nv12[:, 8:, 1::2], bgr[:, 0::2, 0::2, 2])
+    v = TensorVideo(nv12, 25.0, pixel_format="nv12")
+    assert v.frame_size == (12, 8) and v.read_batch(2).shape == (2, 12, 12)
+    with pytest.raises(ValueError):
+        TensorVideo(bgr, pixel_format="nv12")
+    with pytest.raises(ValueError):
+        TensorVideo(nv12, pixel_format="i420")
+    # the closed-form NV12 -> BGR conversion agrees with cv2 on this content too
+    cv2 = pytest.importorskip("cv2")
+    from oracle import closed_form as cf
+
+    assert np.array_equal(cf.nv12_to_bgr_u8(nv12[0]), cv2.cvtColor(nv12[0], cv2.COLOR_YUV2BGR_NV12))
+
+
+def test_scene_artifact_payloads_from_a_finished_manager():
+    """SceneV1 {scene_index, method, score, frame_number} (reference spec, artifact-envelope design.md:159-167)."""
+    from eioku_b200.detectors import HashDetector
+    from eioku_b200.scene_manager import SceneManager
+    from eioku_b200.service import scene_artifact_payloads
+
+    sm = SceneManager.__new__(SceneManager)   # no device needed: fill in what detect_scenes leaves behind
+    c, h = ContentDetector(), HashDetector()
+    sm._detector_list = [c, h]
+    sm._start_pos, sm._last_pos = 100, 199
+    sm._cuts_by_detector = {"ContentDetector": [130, 160], "HashDetector": [130, 181]}
+    sm.scores = {"content_val": np.arange(100, dtype=np.float64), "hash_dist": np.full(100, 0.5)}
+    recs = scene_artifact_payloads(sm)
+    assert recs == [
+        {"scene_index": 0, "method": "start", "score": 0.0, "frame_number": 100},
+        {"scene_index": 1, "method": "content", "score": 30.0, "frame_number": 130},
+        {"scene_index": 2, "method": "content", "score": 60.0, "frame_number": 160},
+        {"scene_index": 3, "method": "hash", "score": 0.5, "frame_number": 181},
+    ]
+    sm._start_pos = None
+    assert scene_artifact_payloads(sm) == []
