@@ -894,7 +894,7 @@ int esd_create(esd_ctx** out, const esd_config* cfg, int device) {
         fail(c, ESD_ERR_INVALID, "esd_create: unknown src_format %d", cfg->src_format);
         return bail(ESD_ERR_INVALID);
     }
-    if (c->nv12 && (!c->resize || (W & 1) || (H & 1) || H > 32766)) {
+    if (c->nv12 && (!c->resize || (W & 1) || (H & 1) || H > 32766 || W > 8190)) {
         fail(c, ESD_ERR_UNSUPPORTED, "NV12 input needs even dimensions and a downscaling context (frames %dx%d -> %dx%d)", W, H, dw, dh);
         return bail(ESD_ERR_UNSUPPORTED);
     }
@@ -1088,12 +1088,16 @@ int esd_create(esd_ctx** out, const esd_config* cfg, int device) {
     {
         std::vector<uint2> xt(dw);
         for (int x = 0; x < dw; ++x) {
-            if (c->resize) { xt[x].x = (uint32_t)((c->nv12 ? 1 : 3) * xo0[x]); xt[x].y = (uint32_t)xa0[x] | ((uint32_t)xa1[x] << 16); }
+            if (c->resize && c->nv12) {  // luma byte offset | chroma pair byte offset << 13 | tap 1 in the next pair << 26
+                const uint32_t x0 = (uint32_t)xo0[x];
+                xt[x].x = x0 | ((x0 & ~1u) << 13) | ((x0 & 1u) << 26);
+                xt[x].y = (uint32_t)xa0[x] | ((uint32_t)xa1[x] << 16);
+            } else if (c->resize) { xt[x].x = (uint32_t)(3 * xo0[x]); xt[x].y = (uint32_t)xa0[x] | ((uint32_t)xa1[x] << 16); }
             else { xt[x].x = (uint32_t)(3 * x); xt[x].y = 2048u; }
         }
         {  // sector-granular touched bytes per row (SURVEY.md section 8d accounting)
             std::vector<char> sec((c->row_bytes + 31) / 32, 0);
-            for (int x = 0; x < dw; ++x) {
+            for (int x = 0; x < dw && !c->nv12; ++x) {  // (NV12's x table is packed differently: handled below)
                 const int b0 = (int)xt[x].x, b1 = std::min(c->row_bytes, b0 + (c->resize ? 6 : 3)) - 1;
                 for (int q = b0 / 32; q <= b1 / 32; ++q) sec[q] = 1;
             }
@@ -1121,13 +1125,15 @@ int esd_create(esd_ctx** out, const esd_config* cfg, int device) {
         }
         CUB(cudaMalloc(&c->d_xtab, sizeof(uint2) * dw));
         CUB(cudaMemcpy(c->d_xtab, xt.data(), sizeof(uint2) * dw, cudaMemcpyHostToDevice));
-        if (c->resize && !c->nv12) {  // tap-compact layout: column d of a gathered row holds [tap0 BGR, tap1 BGR] at byte 6 d
-            c->tap_row_bytes = (6 * dw + 15) & ~15;
+        if (c->resize) {
+            // tap-compact layout.  BGR24: column d of a gathered row holds [tap0 BGR, tap1 BGR] at byte 6 d.  NV12: a gathered
+            // Y row holds [Y(x0), Y(x0+1)] at byte 2 d, a gathered UV row [U V of tap 0, U V of tap 1] at byte 4 d (one pitch).
+            c->tap_row_bytes = ((c->nv12 ? 4 : 6) * dw + 15) & ~15;
             c->tap_src_off.resize(dw);
             std::vector<uint2> xt2(dw);
             for (int x = 0; x < dw; ++x) {
-                c->tap_src_off[x] = 3 * xo0[x];
-                xt2[x].x = (uint32_t)(6 * x);
+                c->tap_src_off[x] = (c->nv12 ? 1 : 3) * xo0[x];
+                xt2[x].x = c->nv12 ? ((uint32_t)(2 * x) | ((uint32_t)(4 * x) << 13) | (1u << 26)) : (uint32_t)(6 * x);
                 xt2[x].y = xt[x].y;
             }
             CUB(cudaMalloc(&c->d_xtab_taps, sizeof(uint2) * dw));
@@ -1421,6 +1427,8 @@ int esd_ingest_push_host(esd_ctx* c, const uint8_t* h_bgr, int64_t n, int64_t fr
             // ~3*scale bytes) into the pinned slot: 3.75x fewer PCIe bytes again at 1080p (442 KB per frame)
             { int rcp = ensure_pinned(c, s, (size_t)c->frames_per_slot * tfb); if (rcp) return rcp; }
             const int dw = c->dst_w, trb = c->tap_row_bytes, rb = c->row_bytes;
+            const bool nv12 = c->nv12;
+            const int n_touched_y = c->n_touched_y;
             const int* off = c->tap_src_off.data();
             const int32_t* touched = c->touched.data();
             uint8_t* dst_base = s.h_pinned;
@@ -1446,7 +1454,34 @@ int esd_ingest_push_host(esd_ctx* c, const uint8_t* h_bgr, int64_t n, int64_t fr
                         for (int b = 0; b < rb; b += 2048) __builtin_prefetch(nx + b, 0, 1);
                     }
                     int d = 0;
-                    if (pf_dist > 0) {
+                    if (nv12) {
+                        // NV12: two luma bytes per column from a Y row, the two chroma pairs of the taps from a UV row
+                        const uint8_t* nx = sr;
+                        if (it + 1 < hi) {
+                            const int64_t f1 = (it + 1) / nt, i1 = (it + 1) - f1 * nt;
+                            nx = src + f1 * frame_stride + (int64_t)touched[i1] * pitch;
+                        }
+                        const bool luma = i < n_touched_y;
+                        for (; d < dw; ++d) {
+                            const int x0 = off[d];
+                            if (pf_dist > 0 && (d & 7) == 0) {
+                                const int o = x0 + pf_dist;
+                                __builtin_prefetch(o < rb ? sr + o : nx + (o - rb), 0, 3);
+                            }
+                            if (luma) {
+                                dr[2 * d] = sr[x0];
+                                dr[2 * d + 1] = sr[std::min(x0 + 1, rb - 1)];
+                            } else {
+                                const int c0 = x0 & ~1, c1 = std::min(x0 + 1, rb - 1) & ~1;
+                                uint16_t a, b;
+                                memcpy(&a, sr + c0, 2);
+                                memcpy(&b, sr + c1, 2);
+                                memcpy(dr + 4 * d, &a, 2);
+                                memcpy(dr + 4 * d + 2, &b, 2);
+                            }
+                        }
+                        if (luma && nt_stores) memset(dr + 2 * dw, 0, (size_t)(trb - 2 * dw));
+                    } else if (pf_dist > 0) {
                         // rolling software prefetch `pf_dist` bytes ahead, running over into the next touched row
                         const uint8_t* nx = sr;
                         if (it + 1 < hi) {
@@ -1529,7 +1564,7 @@ int esd_ingest_push_host(esd_ctx* c, const uint8_t* h_bgr, int64_t n, int64_t fr
 int esd_ingest_set_gather(esd_ctx* c, int32_t n_threads) {
     if (!c) return ESD_ERR_INVALID;
     if (n_threads < 0 || n_threads > 256) return fail(c, ESD_ERR_INVALID, "ingest: gather threads must be in 0..256");
-    if (n_threads > 0 && (!c->resize || c->nv12)) return fail(c, ESD_ERR_UNSUPPORTED, "ingest: tap gather needs a resizing BGR24 context");
+    if (n_threads > 0 && !c->resize) return fail(c, ESD_ERR_UNSUPPORTED, "ingest: tap gather needs a resizing context");
     CU(c, cudaSetDevice(c->device));
     int rc = sync_all(c);
     if (rc) return rc;

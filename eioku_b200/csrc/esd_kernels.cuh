@@ -212,14 +212,16 @@ __device__ __forceinline__ void score_row(const FusedParams& p, const uint8_t* _
         if (d < p.dst_w) {
             int b, g, r;
             if (RESIZE && NV12) {
-                // xoff = source column x0 of tap 0 (tap 1 is x0 + 1); chroma pair index x >> 1
+                // xoff packs, per destination column: byte offset of the two luma taps in a Y row (bits 0-12), byte offset
+                // of the chroma pair of tap 0 in a UV row (bits 13-25) and whether tap 1 uses the next pair (bit 26).
+                // Full rows: x0 | (x0 & ~1) << 13 | (x0 & 1) << 26; gathered tap rows: 2 d | 4 d << 13 | 1 << 26.
                 uint32_t nx;
-                const uint32_t x0 = xoff[k];
+                const uint32_t x0 = xoff[k] & 0x1fffu;
                 const uint32_t ya = lds_u32_unaligned(row0, x0 + mis0, nx);   // [Y(x0), Y(x0+1), ..] of source row 0
                 const uint32_t yb = lds_u32_unaligned(row1, x0 + mis1, nx);   // same for source row 1
-                const uint32_t co = (x0 & ~1u);
+                const uint32_t co = (xoff[k] >> 13) & 0x1fffu;
                 const uint32_t ca = lds_u32_unaligned(uv0, co + (misuv & 0xffu), nx);         // [U V U' V'] for row 0
-                const uint32_t sh = (x0 & 1u) * 16u;  // odd x0: tap 1 belongs to the next chroma pair
+                const uint32_t sh = (xoff[k] >> 26) * 16u;  // tap 1 belongs to the next chroma pair
                 const Chroma c00 = nv12_chroma(ca & 255u, (ca >> 8) & 255u);
                 const Chroma c01 = nv12_chroma((ca >> sh) & 255u, (ca >> (sh + 8u)) & 255u);
                 Chroma c10 = c00, c11 = c01;

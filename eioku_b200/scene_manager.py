@@ -216,7 +216,7 @@ class SceneManager:
             if isinstance(batch, np.ndarray):
                 if not host_ring_open:
                     ctx.ingest_open(3, min(self._batch_frames, 64))
-                    if self._ingest_threads > 0 and ctx.dst_size != (width, height) and not nv12:
+                    if self._ingest_threads > 0 and ctx.dst_size != (width, height):
                         ctx.ingest_set_gather(self._ingest_threads)
                     host_ring_open = True
                 if nv12:

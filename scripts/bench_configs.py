@@ -366,6 +366,21 @@ def config_nv12(dev, local, n=2048, steps=20):
     out["host_ring_frames_per_s"] = 4 * m / dt
     out["host_ring_GBps"] = 4 * m * int(ctx.geometry.compact_frame_bytes) / dt / 1e9
     ctx.close()
+    for threads in (8, 16):
+        if threads > (os.cpu_count() or 1):
+            continue
+        ctx = capi.EsdContext(cfg, local)
+        ctx.ingest_open(4, 128)
+        ctx.ingest_set_gather(threads)
+        for i in range(2):
+            ctx.ingest_push_nv12_numpy(hn, i * m)
+        ctx.synchronize()
+        t0 = time.perf_counter()
+        for i in range(2, 6):
+            ctx.ingest_push_nv12_numpy(hn, i * m)
+        ctx.synchronize()
+        out[f"host_gather{threads}_frames_per_s"] = 4 * m / (time.perf_counter() - t0)
+        ctx.close()
     return out
 
 

@@ -104,11 +104,22 @@ def test_nv12_layouts_pitch_separate_planes_and_ingest():
             got = ctx.read_scores(0, n)
             h2d, _ = ctx.ingest_stats()
             assert h2d == n * ctx.geometry.compact_frame_bytes < n * w * h * 3 // 2
-            with pytest.raises(capi.EsdError):
-                ctx.ingest_set_gather(4)     # the tap gather is a BGR24 feature
             for k in want:
                 assert np.array_equal(np.nan_to_num(got[k], nan=-1), np.nan_to_num(want[k], nan=-1)), k
             ctx.ingest_close()
+        # host tap gather: threads copy the two luma bytes / two chroma pairs per destination column of the touched rows
+        for threads in (1, 5):
+            with nv12_ctx(w, h) as ctx:
+                ctx.ingest_open(3, 5)
+                ctx.ingest_set_gather(threads)
+                ctx.ingest_push_nv12_numpy(host.numpy()[:7], 0)
+                ctx.ingest_push_nv12_numpy(host.numpy()[7:], 7)
+                got = ctx.read_scores(0, n)
+                h2d, _ = ctx.ingest_stats()
+                assert h2d == n * len(ctx.touched_rows()) * 1024 < n * ctx.geometry.compact_frame_bytes   # 4 * 256 bytes per row
+                for k in want:
+                    assert np.array_equal(np.nan_to_num(got[k], nan=-1), np.nan_to_num(want[k], nan=-1)), (k, threads)
+                ctx.ingest_close()
 
 
 def test_nv12_clip_through_scene_manager_all_detectors():
@@ -137,6 +148,8 @@ def test_nv12_clip_through_scene_manager_all_detectors():
         for d in dets.values():
             sm.add_detector(d)
         frames = nv12 if source == "device" else nv12_np
+        if source == "host":
+            sm._ingest_threads = 3   # host frames through the NV12 tap gather
         assert sm.detect_scenes(TensorVideo(frames, 30.0, pixel_format="nv12"), collect_scores=True) == n
         for name in refs:
             assert sm.cuts_of(dets[name]) == want[name], (source, name)
