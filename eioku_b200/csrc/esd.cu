@@ -11,7 +11,6 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <dlfcn.h>
-#include <emmintrin.h>
 #include <string.h>
 #include <stdlib.h>
 #include <time.h>
@@ -28,6 +27,7 @@
 #include <vector>
 
 #include "esd_kernels.cuh"
+#include "ingest_gather.h"
 #include "synth_core.h"
 
 using namespace esd;
@@ -1426,93 +1426,23 @@ int esd_ingest_push_host(esd_ctx* c, const uint8_t* h_bgr, int64_t n, int64_t fr
             // host threads gather, per touched row, the two BGR taps of every destination column (6 of every
             // ~3*scale bytes) into the pinned slot: 3.75x fewer PCIe bytes again at 1080p (442 KB per frame)
             { int rcp = ensure_pinned(c, s, (size_t)c->frames_per_slot * tfb); if (rcp) return rcp; }
-            const int dw = c->dst_w, trb = c->tap_row_bytes, rb = c->row_bytes;
-            const bool nv12 = c->nv12;
-            const int n_touched_y = c->n_touched_y;
-            const int* off = c->tap_src_off.data();
-            const int32_t* touched = c->touched.data();
-            uint8_t* dst_base = s.h_pinned;
             static const int pf_env = getenv("ESD_GATHER_PF") ? atoi(getenv("ESD_GATHER_PF")) : -1;
-            // measured best of 0 / 512 ... 8192 at 1080p (profiles/r01_gather_prefetch.log); never further than one row
-            const int pf_dist = std::min(pf_env >= 0 ? pf_env : 4096, c->row_bytes);
-
-            constexpr int kMaxTapRow = 6 * 1024 + 16;  // dst_w <= 1024 in resizing contexts
             static const bool nt_off = getenv("ESD_GATHER_NT") && atoi(getenv("ESD_GATHER_NT")) == 0;  // A/B switch
-            const bool nt_stores = !nt_off && trb <= kMaxTapRow;  // +11 % with 16 threads (profiles/r01_gather_prefetch.log)
+            GatherSpec gs{};
+            gs.dst_w = c->dst_w;
+            gs.tap_row_bytes = c->tap_row_bytes;
+            gs.row_bytes = c->row_bytes;
+            gs.off = c->tap_src_off.data();
+            gs.touched = c->touched.data();
+            gs.n_touched = nt;
+            gs.n_touched_y = c->n_touched_y;
+            gs.nv12 = c->nv12;
+            // measured best of 0 / 512 ... 8192 at 1080p (profiles/r01_gather_prefetch.log); never further than one row
+            gs.prefetch_bytes = std::min(pf_env >= 0 ? pf_env : 4096, c->row_bytes);
+            gs.nt_stores = !nt_off;  // +11 % with 16 threads (profiles/r01_gather_prefetch.log)
+            uint8_t* dst_base = s.h_pinned;
             std::function<void(int64_t, int64_t)> job = [=](int64_t lo, int64_t hi) {
-                for (int64_t it = lo; it < hi; ++it) {
-                    const int64_t f = it / nt, i = it - f * nt;
-                    const uint8_t* sr = src + f * frame_stride + (int64_t)touched[i] * pitch;
-                    uint8_t* const out_row = dst_base + it * trb;
-                    alignas(64) uint8_t tmp_row[kMaxTapRow];
-                    // the ring slot is written once and read by the DMA engine: assemble the row in L1 and stream it out
-                    // with non-temporal stores (no read-for-ownership of the 442 KB per frame)
-                    uint8_t* dr = nt_stores ? tmp_row : out_row;
-                    if (pf_dist == 0 && it + 1 < hi) {  // touch the next row's pages early: hardware prefetchers stop at 4 KB boundaries
-                        const int64_t f1 = (it + 1) / nt, i1 = (it + 1) - f1 * nt;
-                        const uint8_t* nx = src + f1 * frame_stride + (int64_t)touched[i1] * pitch;
-                        for (int b = 0; b < rb; b += 2048) __builtin_prefetch(nx + b, 0, 1);
-                    }
-                    int d = 0;
-                    if (nv12) {
-                        // NV12: two luma bytes per column from a Y row, the two chroma pairs of the taps from a UV row
-                        const uint8_t* nx = sr;
-                        if (it + 1 < hi) {
-                            const int64_t f1 = (it + 1) / nt, i1 = (it + 1) - f1 * nt;
-                            nx = src + f1 * frame_stride + (int64_t)touched[i1] * pitch;
-                        }
-                        const bool luma = i < n_touched_y;
-                        for (; d < dw; ++d) {
-                            const int x0 = off[d];
-                            if (pf_dist > 0 && (d & 7) == 0) {
-                                const int o = x0 + pf_dist;
-                                __builtin_prefetch(o < rb ? sr + o : nx + (o - rb), 0, 3);
-                            }
-                            if (luma) {
-                                dr[2 * d] = sr[x0];
-                                dr[2 * d + 1] = sr[std::min(x0 + 1, rb - 1)];
-                            } else {
-                                const int c0 = x0 & ~1, c1 = std::min(x0 + 1, rb - 1) & ~1;
-                                uint16_t a, b;
-                                memcpy(&a, sr + c0, 2);
-                                memcpy(&b, sr + c1, 2);
-                                memcpy(dr + 4 * d, &a, 2);
-                                memcpy(dr + 4 * d + 2, &b, 2);
-                            }
-                        }
-                        if (luma && nt_stores) memset(dr + 2 * dw, 0, (size_t)(trb - 2 * dw));
-                    } else if (pf_dist > 0) {
-                        // rolling software prefetch `pf_dist` bytes ahead, running over into the next touched row
-                        const uint8_t* nx = sr;
-                        if (it + 1 < hi) {
-                            const int64_t f1 = (it + 1) / nt, i1 = (it + 1) - f1 * nt;
-                            nx = src + f1 * frame_stride + (int64_t)touched[i1] * pitch;
-                        }
-                        for (; d < dw - 1 && off[d] + 8 <= rb; ++d) {
-                            if ((d & 3) == 0) {
-                                const int o = off[d] + pf_dist;
-                                __builtin_prefetch(o < rb ? sr + o : nx + (o - rb), 0, 3);
-                            }
-                            uint64_t v;
-                            memcpy(&v, sr + off[d], 8);
-                            memcpy(dr + 6 * d, &v, 8);
-                        }
-                    }
-                    for (; d < dw - 1 && off[d] + 8 <= rb; ++d) {  // 8-byte moves; the 2 spare bytes are overwritten by d + 1
-                        uint64_t v;
-                        memcpy(&v, sr + off[d], 8);
-                        memcpy(dr + 6 * d, &v, 8);
-                    }
-                    for (; d < dw; ++d) {
-                        const int nbytes = std::min(6, rb - off[d]);  // a clamped last column only has tap 0 (tap 1 weighs 0)
-                        memcpy(dr + 6 * d, sr + off[d], (size_t)nbytes);
-                        if (nbytes < 6) memset(dr + 6 * d + nbytes, 0, (size_t)(6 - nbytes));
-                    }
-                    if (nt_stores)
-                        for (int b = 0; b < trb; b += 16)
-                            _mm_stream_si128(reinterpret_cast<__m128i*>(out_row + b), _mm_load_si128(reinterpret_cast<const __m128i*>(tmp_row + b)));
-                }
-                if (nt_stores) _mm_sfence();
+                gather_tap_rows(gs, src, frame_stride, pitch, dst_base, lo, hi);
             };
             TraceTimer tr;
             c->pool->parallel_for(m * nt, 16, job);

@@ -1,0 +1,111 @@
+// ingest_gather.h -- host-side tap gather of the ingest path (no CUDA in here: unit-tested on the CPU by
+// tests/test_host_gather.py through tests/gather_shim.cpp).
+//
+// For every touched source row the fused kernel only reads, per destination column, the two horizontal taps:
+//   BGR24: 6 bytes [tap0 B G R, tap1 B G R] at byte 3 * x0         -> written at byte 6 * d of the gathered row
+//   NV12 Y row: 2 bytes [Y(x0), Y(x0 + 1)]                          -> written at byte 2 * d
+//   NV12 UV row: the chroma pairs of the two taps [U V, U' V']      -> written at byte 4 * d
+// (x0 = source column of tap 0; a clamped last column repeats the last pixel -- its tap 1 has weight 0).
+// The rows of a frame are laid out in the order of the touched-row list with one pitch (`tap_row_bytes`).
+#pragma once
+#include <emmintrin.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <algorithm>
+
+namespace esd {
+
+struct GatherSpec {
+    int dst_w;              // destination columns
+    int tap_row_bytes;      // pitch of a gathered row (multiple of 16)
+    int row_bytes;          // bytes of a source row (src_w * 3, or src_w for NV12)
+    const int* off;         // [dst_w] byte offset of tap 0 in a BGR24 row (3 * x0), or x0 for NV12
+    const int32_t* touched; // [n_touched] source rows, ascending (NV12: Y rows, then UV rows as src_height + r)
+    int64_t n_touched;
+    int n_touched_y;        // NV12: how many of them are Y rows
+    bool nv12;
+    int prefetch_bytes;     // rolling software prefetch distance (0 = touch the next row's pages only)
+    bool nt_stores;         // assemble each row in L1 and stream it out with non-temporal stores
+};
+
+constexpr int kMaxTapRow = 6 * 1024 + 16;  // dst_w <= 1024 in resizing contexts
+
+// Gathers items [lo, hi) of the (frame-major, touched-row-minor) item sequence of `src` (frames `frame_stride` apart, rows
+// `pitch` apart) into dst_base + item * tap_row_bytes.  dst_base must be 16-byte aligned when nt_stores is set.
+inline void gather_tap_rows(const GatherSpec& g, const uint8_t* src, int64_t frame_stride, int64_t pitch, uint8_t* dst_base,
+                            int64_t lo, int64_t hi) {
+    const int dw = g.dst_w, trb = g.tap_row_bytes, rb = g.row_bytes, pf = g.prefetch_bytes;
+    const int* off = g.off;
+    const bool nt = g.nt_stores && trb <= kMaxTapRow;
+    alignas(64) uint8_t tmp_row[kMaxTapRow];
+    for (int64_t it = lo; it < hi; ++it) {
+        const int64_t f = it / g.n_touched, i = it - f * g.n_touched;
+        const uint8_t* sr = src + f * frame_stride + (int64_t)g.touched[i] * pitch;
+        uint8_t* const out_row = dst_base + it * trb;
+        // the ring slot is written once and read by the DMA engine: no read-for-ownership of the gathered bytes
+        uint8_t* dr = nt ? tmp_row : out_row;
+        const uint8_t* nx = sr;  // where the prefetch runs on to after this row
+        if (it + 1 < hi) {
+            const int64_t f1 = (it + 1) / g.n_touched, i1 = (it + 1) - f1 * g.n_touched;
+            nx = src + f1 * frame_stride + (int64_t)g.touched[i1] * pitch;
+            if (pf == 0)  // hardware prefetchers stop at 4 KB boundaries: touch the next row's pages early
+                for (int b = 0; b < rb; b += 2048) __builtin_prefetch(nx + b, 0, 1);
+        }
+        int d = 0;
+        if (g.nv12 && i < g.n_touched_y) {
+            // luma: one unaligned 16-bit move per column
+            for (; d < dw && off[d] + 2 <= rb; ++d) {
+                if (pf > 0 && (d & 7) == 0) {
+                    const int o = off[d] + pf;
+                    __builtin_prefetch(o < rb ? sr + o : nx + (o - rb), 0, 3);
+                }
+                uint16_t v;
+                memcpy(&v, sr + off[d], 2);
+                memcpy(dr + 2 * d, &v, 2);
+            }
+            for (; d < dw; ++d) dr[2 * d] = dr[2 * d + 1] = sr[rb - 1];  // clamped last column
+            if (nt) memset(dr + 2 * dw, 0, (size_t)(trb - 2 * dw));
+        } else if (g.nv12) {
+            // chroma: an odd x0 takes two consecutive pairs (one 32-bit move), an even x0 the same pair twice
+            for (; d < dw; ++d) {
+                const int x0 = off[d];
+                if (pf > 0 && (d & 7) == 0) {
+                    const int o = x0 + pf;
+                    __builtin_prefetch(o < rb ? sr + o : nx + (o - rb), 0, 3);
+                }
+                const int c0 = x0 & ~1;
+                uint32_t v;
+                if ((x0 & 1) && c0 + 4 <= rb) {
+                    memcpy(&v, sr + c0, 4);
+                } else {
+                    uint16_t a;
+                    memcpy(&a, sr + c0, 2);
+                    v = (uint32_t)a | ((uint32_t)a << 16);
+                }
+                memcpy(dr + 4 * d, &v, 4);
+            }
+        } else {
+            for (; d < dw - 1 && off[d] + 8 <= rb; ++d) {  // 8-byte moves; the 2 spare bytes are overwritten by d + 1
+                if (pf > 0 && (d & 3) == 0) {
+                    const int o = off[d] + pf;
+                    __builtin_prefetch(o < rb ? sr + o : nx + (o - rb), 0, 3);
+                }
+                uint64_t v;
+                memcpy(&v, sr + off[d], 8);
+                memcpy(dr + 6 * d, &v, 8);
+            }
+            for (; d < dw; ++d) {
+                const int nbytes = std::min(6, rb - off[d]);  // a clamped last column only has tap 0 (tap 1 weighs 0)
+                memcpy(dr + 6 * d, sr + off[d], (size_t)nbytes);
+                if (nbytes < 6) memset(dr + 6 * d + nbytes, 0, (size_t)(6 - nbytes));
+            }
+        }
+        if (nt)
+            for (int b = 0; b < trb; b += 16)
+                _mm_stream_si128(reinterpret_cast<__m128i*>(out_row + b), _mm_load_si128(reinterpret_cast<const __m128i*>(tmp_row + b)));
+    }
+    if (nt) _mm_sfence();
+}
+
+}  // namespace esd
