@@ -27,6 +27,7 @@
 #include <vector>
 
 #include "esd_kernels.cuh"
+#include "host_tables.h"
 #include "ingest_gather.h"
 #include "synth_core.h"
 
@@ -294,31 +295,6 @@ int sync_all(esd_ctx* c) {
     return ESD_OK;
 }
 
-// OpenCV resize.cpp INTER_LINEAR coefficient setup: float32 fraction from a double
-// scale, cvRound (half-even) to 11-bit fixed point.
-void axis_tables(int src, int dst, std::vector<int>& o0, std::vector<int>& o1, std::vector<int>& c0,
-                 std::vector<int>& c1) {
-    o0.resize(dst); o1.resize(dst); c0.resize(dst); c1.resize(dst);
-    const double inv_scale = (double)dst / (double)src;
-    const double scale = 1.0 / inv_scale;
-    for (int d = 0; d < dst; ++d) {
-        volatile double pos = (d + 0.5) * scale;  // volatile: no FMA contraction / excess precision
-        pos = pos - 0.5;
-        float f = (float)pos;
-        int s = (int)floorf(f);
-        f -= (float)s;
-        if (s < 0) { s = 0; f = 0.f; }
-        if (s >= src - 1) { s = src - 1; f = 0.f; }
-        o0[d] = s;
-        o1[d] = std::min(s + 1, src - 1);
-        volatile float w0 = (1.f - f) * 2048.f, w1 = f * 2048.f;
-        c0[d] = (int)lrintf(w0);
-        c1[d] = (int)lrintf(w1);
-    }
-}
-
-int64_t gcd64(int64_t a, int64_t b) { while (b) { int64_t t = a % b; a = b; b = t; } return a; }
-
 // Python round(): half to even on the double quotient
 long py_round(double x) { return lrint(x); }
 
@@ -386,45 +362,10 @@ void free_plans(esd_ctx* c) {
 // Work decomposition.  A unit is (row group, frame range); units that do not start at frame 0
 // re-read one halo frame to rebuild the previous HSV, so fewer/longer units are cheaper.
 int build_plan(esd_ctx* c, int64_t n, UnitPlan* out) {
-    const int G = c->n_groups;
-    const int64_t total = (int64_t)G * n;  // (group, frame) items
-    int grid = (int)std::min<int64_t>((int64_t)c->num_sms * c->ctas_per_sm, total);
     std::vector<Unit> units;
-    std::vector<int> begin(grid + 1, 0);
-    int mode = c->cfg.split_mode ? c->cfg.split_mode : ESD_SPLIT_STRIPS;
-    if (mode == ESD_SPLIT_STRIPS) {
-        // contiguous strips of the (group-major, frame-minor) item sequence, one per CTA
-        for (int g = 0; g < grid; ++g) {
-            int64_t lo = total * g / grid, hi = total * (g + 1) / grid;
-            begin[g] = (int)units.size();
-            while (lo < hi) {
-                const int rg = (int)(lo / n);
-                const int64_t f0 = lo % n;
-                const int64_t f1 = std::min<int64_t>(n, f0 + (hi - lo));
-                units.push_back(Unit{rg, (int)f0, (int)f1, 0});
-                lo += f1 - f0;
-            }
-        }
-        begin[grid] = (int)units.size();
-    } else {
-        // frame chunks shared by all row groups; consecutive CTAs work on the same frames
-        int64_t n_chunks = std::max<int64_t>(1, ((int64_t)grid * 4 + G - 1) / G);
-        n_chunks = std::min<int64_t>(n_chunks, std::max<int64_t>(1, n / 16));
-        // make the unit count a multiple of the grid when possible
-        const int64_t per = grid / gcd64(grid, G);
-        if (n_chunks >= per) n_chunks = n_chunks / per * per;
-        std::vector<Unit> all;
-        for (int64_t ch = 0; ch < n_chunks; ++ch)
-            for (int rg = 0; rg < G; ++rg)
-                all.push_back(Unit{rg, (int)(n * ch / n_chunks), (int)(n * (ch + 1) / n_chunks), 0});
-        grid = (int)std::min<int64_t>(grid, (int64_t)all.size());
-        begin.assign(grid + 1, 0);
-        for (int g = 0; g < grid; ++g) {
-            begin[g] = (int)units.size();
-            for (size_t u = g; u < all.size(); u += grid) units.push_back(all[u]);
-        }
-        begin[grid] = (int)units.size();
-    }
+    std::vector<int> begin;
+    const int grid = build_unit_plan(c->n_groups, n, (int64_t)c->num_sms * c->ctas_per_sm,
+                                     c->cfg.split_mode ? c->cfg.split_mode : ESD_SPLIT_STRIPS, units, begin);
     out->grid = grid;
     out->n_units = (int)units.size();
     CU(c, cudaMalloc(&out->d_units, sizeof(Unit) * std::max<size_t>(1, units.size())));
@@ -947,27 +888,10 @@ int esd_create(esd_ctx** out, const esd_config* cfg, int device) {
         hp.isx = (int)sx; hp.isy = (int)sy;
         hp.fast = (fabs(sx - hp.isx) < 2.220446049250313e-16 && fabs(sy - hp.isy) < 2.220446049250313e-16) ? 1 : 0;
         hp.fast_scale = (float)(1.0 / (hp.isx * hp.isy));
-        // OpenCV resize.cpp computeResizeAreaTab, one axis (cn = 1)
-        auto area_tab = [](int ssize, int dsize, std::vector<int>& begin, std::vector<int>& src, std::vector<float>& wt) {
-            const double scale = (double)ssize / dsize;
-            begin.assign(1, 0);
-            for (int d = 0; d < dsize; ++d) {
-                volatile double fsx1 = d * scale;
-                volatile double fsx2 = fsx1 + scale;
-                const double cell = std::min(scale, ssize - fsx1);
-                int sx1 = (int)ceil(fsx1), sx2 = (int)floor(fsx2);
-                sx2 = std::min(sx2, ssize - 1);
-                sx1 = std::min(sx1, sx2);
-                if (sx1 - fsx1 > 1e-3) { src.push_back(sx1 - 1); wt.push_back((float)((sx1 - fsx1) / cell)); }
-                for (int x = sx1; x < sx2; ++x) { src.push_back(x); wt.push_back((float)(1.0 / cell)); }
-                if (fsx2 - sx2 > 1e-3) { src.push_back(sx2); wt.push_back((float)(std::min(std::min(fsx2 - sx2, 1.), cell) / cell)); }
-                begin.push_back((int)src.size());
-            }
-        };
         std::vector<int> xb, xs, yb, ys;
         std::vector<float> xw, yw;
-        area_tab(dw, hp.S, xb, xs, xw);
-        area_tab(dh, hp.S, yb, ys, yw);
+        area_axis_table(dw, hp.S, xb, xs, xw);
+        area_axis_table(dh, hp.S, yb, ys, yw);
         for (int d = 0; d < hp.S; ++d)  // hash_kernel walks the taps of a destination column as consecutive pixels
             for (int k = xb[d] + 1; k < xb[d + 1]; ++k)
                 if (xs[k] != xs[k - 1] + 1) {

@@ -12,6 +12,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "host_tables.h"  // struct Unit
+
 namespace esd {
 
 #ifndef ESD_CONSUMER_WARPS
@@ -25,9 +27,6 @@ constexpr int kMaxRowsPerStage = 4;  // destination rows staged per pipeline slo
 
 enum : int { F_HALO = 1, F_NOPREV = 2, F_CTXPREV = 4, F_SAVE = 8, F_FRAME_END = 16, F_END = 32 };
 
-struct Unit {  // frames [f0, f1) (batch-relative) of destination-row group rg
-    int rg, f0, f1, pad;
-};
 
 struct YRow {  // per destination row
     int row0, row1;    // source rows (full layout); NV12: rows of the Y plane
