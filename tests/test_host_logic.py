@@ -280,9 +280,11 @@ def _gloo_worker(rank, world, port, q):
     def score_shard(s):
         frames = co.synth_frames(seed, w, h, sch.descs[s.load_start:s.load_end])
         det = PP.AdaptiveDetector(window_width=ww, min_scene_len=5, backend="closed_form")
+        hd = PP.HashDetector(threshold=0.3, min_scene_len=5, backend="closed_form")
         for k, f in enumerate(frames):
             det.process_frame(s.load_start + k, f)
-        return {"adaptive_val": np.array(det.scores), "sums3": np.stack(det.sums)}
+            hd.process_frame(s.load_start + k, f)
+        return {"adaptive_val": np.array(det.scores), "sums3": np.stack(det.sums), "hash_dist": np.array(hd.dists)}
 
     def decide(m):
         # single global pass over the concatenated scores with the oracle's state machine
@@ -293,14 +295,22 @@ def _gloo_worker(rank, world, port, q):
         cuts = []
         for k, v in enumerate(m["adaptive_val"]):
             cuts += det.process_frame(k, v)
-        return {"adaptive": cuts, "n": len(m["adaptive_val"]), "sum0": m["sums3"][0].tolist()}
+        hcuts, last = [], 0   # HashDetector's rule on the merged distances (first frame: NaN, never a cut)
+        for k, v in enumerate(m["hash_dist"]):
+            if v >= 0.3 and k - last >= 5:
+                hcuts.append(k)
+                last = k
+        return {"adaptive": cuts, "hash": hcuts, "hash_dist0": float(m["hash_dist"][0]), "n": len(m["adaptive_val"]),
+                "sum0": m["sums3"][0].tolist()}
 
     out = sh.sharded_detect(score_shard, decide, n, window_width=ww)
     if rank == 0:
         frames = co.synth_frames(seed, w, h, sch.descs)
         ref = PP.AdaptiveDetector(window_width=ww, min_scene_len=5, backend="closed_form")
         want, _ = PP.detect(frames, [ref], backend="closed_form", auto_downscale=False)
-        q.put((out, want))
+        href = PP.HashDetector(threshold=0.3, min_scene_len=5, backend="closed_form")
+        hwant, _ = PP.detect(frames, [href], backend="closed_form", auto_downscale=False)
+        q.put((out, want, hwant))
     dist.destroy_process_group()
 
 
@@ -315,12 +325,13 @@ def test_sharded_detect_gloo_world2():
     procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    out, want = q.get(timeout=180)
+    out, want, hwant = q.get(timeout=300)
     for p in procs:
         p.join(60)
         assert p.exitcode == 0
     assert out["n"] == 160 and out["sum0"] == [0, 0, 0]
     assert out["adaptive"] == want and len(want) >= 2
+    assert out["hash"] == hwant and len(hwant) >= 1 and np.isnan(out["hash_dist0"])
 
 
 # ------------------------------------------------------------------------------------------- later round-1 additions
