@@ -45,7 +45,7 @@ typedef enum esd_status {
     ESD_ERR_CUDA = -2,        /* a CUDA runtime call failed (see esd_last_error) */
     ESD_ERR_NOMEM = -3,
     ESD_ERR_STATE = -4,       /* call out of order (e.g. non-sequential frame numbers) */
-    ESD_ERR_UNSUPPORTED = -5, /* e.g. delta_edges weight != 0, dst width > 4096 */
+    ESD_ERR_UNSUPPORTED = -5, /* e.g. destination width > 1024 when resizing, odd-size hash DCT, NV12 without a downscale */
     ESD_ERR_CAPACITY = -6     /* caller buffer or cut list too small */
 } esd_status;
 
