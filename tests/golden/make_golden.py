@@ -11,6 +11,7 @@ What is frozen (SURVEY.md section 8c "golden vectors to create"):
                 BASELINE configs, computed by oracle/psd_cv2.py (PySceneDetect logic on real cv2)
                 on frames from the CPU twin of the clip generator.
   filter_vectors.json   FlashFilter / min_scene_len state-machine unit vectors.
+  nv12_*.npz    the NV12 input path: cv2.cvtColor(COLOR_YUV2BGR_NV12) + resize + detector logic on NV12 test content.
   hash_*.npz    HashDetector on the same clips, from real cv2 (cvtColor GRAY, resize INTER_AREA,
                 dct): per-frame hash bits, the bits whose DCT coefficient lies within 4e-6 of the median
                 ("unstable": cv2.dct's float32 rounding is build-dependent), hash_dist, cut list, and a sha256
@@ -144,6 +145,34 @@ def hash_clip(name, seed, w, h, n, chunk=64, size=16, lowpass=2):
           f"in {time.time() - t0:.1f}s", flush=True)
 
 
+def nv12_clip(name, seed, w, h, n):
+    """NV12 input: the synthetic clip re-expressed as NV12 test content (synth.bgr_to_test_nv12), converted
+    by real cv2 (COLOR_YUV2BGR_NV12), downscaled and scored by PySceneDetect's logic -- what the fused NV12 kernel must equal."""
+    t0 = time.time()
+    sch = synth.build_schedule(seed, n, min_len=20, max_len=70)
+    from oracle import closed_form as cf
+    dw, dh = cf.downscaled_size(w, h, cf.compute_downscale_factor(w))
+    dets = {"content": P.ContentDetector(threshold=27.0, min_scene_len=15), "adaptive": P.AdaptiveDetector(),
+            "hist": P.HistogramDetector()}
+    cuts = {k: [] for k in dets}
+    k = 0
+    sha = hashlib.sha256()
+    for a in range(0, n, 60):
+        nv12 = synth.bgr_to_test_nv12(co.synth_frames(seed, w, h, sch.descs[a:a + 60]))
+        sha.update(nv12.tobytes())
+        for f in nv12:
+            small = cv2.resize(cv2.cvtColor(f, cv2.COLOR_YUV2BGR_NV12), (dw, dh), interpolation=cv2.INTER_LINEAR)
+            for nm, d in dets.items():
+                cuts[nm] += d.process_frame(k, small)
+            k += 1
+    np.savez_compressed(os.path.join(HERE, f"nv12_{name}.npz"), seed=seed, width=w, height=h, n_frames=n, dst=np.array([dw, dh]),
+                        sums3=np.stack(dets["content"].sums).astype(np.uint64), content_val=np.array(dets["content"].scores),
+                        hist_diff=np.array(dets["hist"].diffs), cuts_content=np.array(cuts["content"], np.int64),
+                        cuts_adaptive=np.array(cuts["adaptive"], np.int64), cuts_hist=np.array(cuts["hist"], np.int64),
+                        input_sha256=np.frombuffer(sha.digest(), np.uint8), versions=json.dumps(VERSIONS))
+    print(f"nv12_{name}: {n} frames in {time.time() - t0:.1f}s; cuts {[len(v) for v in cuts.values()]}", flush=True)
+
+
 def filter_vectors():
     rng = np.random.default_rng(7)
     vecs = []
@@ -183,6 +212,8 @@ if __name__ == "__main__":
         hash_clip("c1_720p", 1001, 1280, 720, 1800)
         hash_clip("c2_1080p_head", 1002, 1920, 1080, 600)
         hash_clip("c4_4k_head_s8l4", 1004, 3840, 2160, 120, size=8, lowpass=4)
+    if not only or "nv12" in only:
+        nv12_clip("c2_1080p_head", 1002, 1920, 1080, 240)
     if full:
         clip("c2_1080p_full", 1002, 1920, 1080, 18000)
         clip("c4_4k_full", 1004, 3840, 2160, 3600)

@@ -184,3 +184,29 @@ def test_nv12_errors():
         t = torch.zeros((1, 540, 640), dtype=torch.uint8, device=DEV)
         with pytest.raises(capi.EsdError):
             ctx.push_nv12_device(t.data_ptr(), t.data_ptr() + 360 * 640, 1, 540 * 640, 640, 0)
+
+
+def test_nv12_clip_vs_committed_cv2_golden():
+    """The same kind of clip against the committed golden (tests/golden/make_golden.py nv12: real cv2 conversion + PySceneDetect's
+    logic, generated in the build container): integer sums, float64 scores, hist_diff and the three cut lists."""
+    import hashlib
+
+    g = load_golden("nv12_c2_1080p_head.npz")
+    w, h, n, seed = int(g["width"]), int(g["height"]), int(g["n_frames"]), int(g["seed"])
+    sch = synth.build_schedule(seed, n, min_len=20, max_len=70)
+    bgr = torch.empty((n, h, w, 3), dtype=torch.uint8, device=DEV)
+    capi.synth_fill(bgr, seed, sch.descs)
+    nv12 = synth.bgr_to_test_nv12(bgr)
+    assert hashlib.sha256(nv12.cpu().numpy().tobytes()).digest() == bytes(g["input_sha256"])
+    dets = [ContentDetector(threshold=27.0, min_scene_len=15), AdaptiveDetector(), HistogramDetector()]
+    sm = SceneManager(batch_frames=100)
+    for d in dets:
+        sm.add_detector(d)
+    assert sm.detect_scenes(TensorVideo(nv12, 30.0, pixel_format="nv12"), collect_scores=True) == n
+    assert np.array_equal(sm.scores["sums3"], g["sums3"])
+    assert np.array_equal(sm.scores["content_val"].view(np.uint64), g["content_val"].view(np.uint64))
+    assert np.array_equal(sm.scores["hist_diff"][1:].view(np.uint64), g["hist_diff"][1:].view(np.uint64))
+    assert sm.cuts_of(dets[0]) == g["cuts_content"].tolist() and len(g["cuts_content"]) >= 3
+    assert sm.cuts_of(dets[1]) == g["cuts_adaptive"].tolist()
+    assert sm.cuts_of(dets[2]) == g["cuts_hist"].tolist()
+    sm.close()

@@ -261,3 +261,16 @@ def test_nv12_to_bgr_restatement_exhaustive_vs_cv2():
             y[dy::2, dx::2] = (grp * 4 + dy * 2 + dx).astype(np.uint8)
     nv12 = np.vstack([y, uv])
     assert np.array_equal(cv2.cvtColor(nv12, cv2.COLOR_YUV2BGR_NV12), cf.nv12_to_bgr_u8(nv12))
+
+
+def test_nv12_closed_form_pipeline_vs_cv2_golden():
+    """Oracle restatement of the NV12 path (closed-form NV12 -> BGR, C resize / HSV sums) against the cv2-derived golden."""
+    g = load_golden("nv12_c2_1080p_head.npz")
+    w, h, seed = int(g["width"]), int(g["height"]), int(g["seed"])
+    n = 40
+    sch = synth.build_schedule(seed, int(g["n_frames"]), min_len=20, max_len=70)
+    nv12 = synth.bgr_to_test_nv12(co.synth_frames(seed, w, h, sch.descs[:n]))
+    bgr = np.stack([cf.nv12_to_bgr_u8(f) for f in nv12])
+    dw, dh = [int(v) for v in g["dst"]]
+    sums, _, _ = co.score_frames(bgr, dw, dh)
+    assert np.array_equal(sums.astype(np.uint64), g["sums3"][:n])
