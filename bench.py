@@ -166,8 +166,8 @@ def bench_reference(args):
     times = []
     total = 0
     res = None
-    # a CPU step is ~2 s of wall clock; keep the whole arm within a few minutes whatever K/W the caller passes
-    args.steps = min(args.steps, 20)
+    # a CPU step is ~3 s of wall clock (16 cores); keep the whole arm within a few minutes whatever K/W the caller passes
+    args.steps = min(args.steps, 12)
     args.warmup = min(args.warmup, 2)
     for i in range(args.warmup + args.steps):
         res = cpu_baseline.run(frames, "content", cores=cores, reps=reps)
@@ -395,7 +395,7 @@ def main():
     ap.add_argument("--e2e-gather-threads", type=int, default=-1, help="host gather threads of the e2e leg (-1 = this rank's share of cores, 0 = DMA rows)")
     ap.add_argument("--e2e-ring", default="", help="ingest ring of the e2e leg as SLOTSxFRAMES (default 4x128 with gather, 3x256 DMA)")
     ap.add_argument("--ref-sample", type=int, default=192, help="--impl reference: frames per process per pass")
-    ap.add_argument("--ref-reps", type=int, default=8, help="--impl reference: passes per process per step")
+    ap.add_argument("--ref-reps", type=int, default=40, help="--impl reference: passes per process per step (same as the cpu_baseline leg)")
     ap.add_argument("--tune", action="append", default=[], help="esd_config field=value (e.g. rows_per_group=2)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)  # timing rule: at least 3 warm-up steps
