@@ -125,7 +125,7 @@ def cpu_model() -> str:
 
 def host_sample_frames(n: int, start: int = 0) -> np.ndarray:
     """n frames of the config-2 clip on the host (GPU generator if there is one, else the CPU twin)."""
-    from eioku_b200 import synth
+    import synthclip as synth
 
     sch = synth.build_schedule(SEED, start + n)
     descs = sch.descs[start:start + n]
@@ -136,7 +136,7 @@ def host_sample_frames(n: int, start: int = 0) -> np.ndarray:
             from eioku_b200 import capi
 
             out = torch.empty((n, H, W, 3), dtype=torch.uint8, device="cuda:0")
-            capi.synth_fill(out, SEED, descs)
+            synth.fill(out, SEED, descs)
             return out.cpu().numpy()
     except Exception:
         pass
@@ -194,7 +194,8 @@ def bench_reference(args):
 def bench_ours(args):
     import torch
 
-    from eioku_b200 import capi, synth
+    from eioku_b200 import capi
+    import synthclip as synth
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; eioku_b200 has no CPU fallback (use --impl reference for the CPU arm)")
@@ -216,7 +217,7 @@ def bench_ours(args):
     first = rank * NB
     sch = synth.build_schedule(SEED, first + NB)
     clip = torch.empty((NB, H, W, 3), dtype=torch.uint8, device=dev)
-    capi.synth_fill(clip, SEED, sch.descs[first:first + NB])
+    synth.fill(clip, SEED, sch.descs[first:first + NB])
     torch.cuda.synchronize()
 
     cfg = capi.default_config()

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libesd.so")
 SOURCES = ["esd.cu"]
-DEPS = ["esd.cu", "esd_kernels.cuh", "ingest_gather.h", "host_tables.h", "synth_core.h", os.path.join("..", "..", "include", "esd.h")]
+DEPS = ["esd.cu", "esd_kernels.cuh", "ingest_gather.h", "host_tables.h", os.path.join("..", "..", "include", "esd.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

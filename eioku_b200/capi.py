@@ -12,22 +12,26 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("ESD_LIB") or os.path.join(_HERE, "libesd.so")  # ESD_LIB: tuning experiments only
 
 ESD_DET_CONTENT, ESD_DET_ADAPTIVE, ESD_DET_HIST, ESD_DET_THRESHOLD, ESD_DET_HASH = 1, 2, 4, 8, 16
-ESD_ABI_VERSION = 2
+ESD_ABI_VERSION = 3
 ESD_THRESH_FLOOR, ESD_THRESH_CEILING = 0, 1
 ESD_FILTER_MERGE, ESD_FILTER_SUPPRESS = 0, 1
 ESD_DOWNSCALE_FLOAT, ESD_DOWNSCALE_INT = 0, 1
 ESD_SPLIT_AUTO, ESD_SPLIT_STRIPS, ESD_SPLIT_CHUNKS = 0, 1, 2
 ESD_FMT_BGR24, ESD_FMT_NV12 = 0, 1
+ESD_SCORE_CONTENT_VAL, ESD_SCORE_ADAPTIVE_VAL, ESD_SCORE_HIST_DIFF, ESD_SCORE_AVERAGE_RGB, ESD_SCORE_HASH_DIST, ESD_SCORE_ADAPTIVE_RATIO = range(6)
+# the score array each detector's decision pass consumes (esd_decide_arrays / esd_decide_device)
+DECISION_SCORE_KIND = {ESD_DET_CONTENT: ESD_SCORE_CONTENT_VAL, ESD_DET_ADAPTIVE: ESD_SCORE_ADAPTIVE_VAL, ESD_DET_HIST: ESD_SCORE_HIST_DIFF,
+                       ESD_DET_THRESHOLD: ESD_SCORE_AVERAGE_RGB, ESD_DET_HASH: ESD_SCORE_HASH_DIST}
 
 # every symbol include/esd.h declares (tests check that the library exports all of them)
 EXPORTED_SYMBOLS = (
     "esd_abi_version", "esd_strerror", "esd_last_error", "esd_device_count", "esd_config_default",
     "esd_create", "esd_destroy", "esd_reset", "esd_get_geometry", "esd_get_touched_rows",
     "esd_push_frames", "esd_push_nv12", "esd_push_rows", "esd_ingest_open", "esd_ingest_push_host", "esd_ingest_close", "esd_ingest_set_gather",
-    "esd_ingest_stats", "esd_synchronize", "esd_join", "esd_frames_pushed", "esd_read_scores", "esd_read_edge_counts", "esd_read_average_rgb",
+    "esd_ingest_stats", "esd_ingest_wait_copied", "esd_decide_device", "esd_copy_scores_device", "esd_synchronize", "esd_join", "esd_frames_pushed", "esd_read_scores", "esd_read_edge_counts", "esd_read_average_rgb",
     "esd_read_hash", "esd_debug_read_hash_input", "esd_process_frame_host",
     "esd_post_process", "esd_get_cuts",
-    "esd_decide_arrays", "esd_debug_read_prev", "esd_set_timing", "esd_kernel_time", "esd_kernel_launches", "esd_synth_fill",
+    "esd_decide_arrays", "esd_debug_read_prev", "esd_set_timing", "esd_kernel_time", "esd_kernel_launches",
 )
 
 
@@ -120,12 +124,14 @@ def load_library(path: Optional[str] = None):
     L.esd_debug_read_hash_input.argtypes = [vp, i64, vp, i64]
     L.esd_post_process.argtypes = [vp, i32, i64, vp, i64, C.POINTER(i64)]
     L.esd_decide_arrays.argtypes = [vp, i32, i64, i64, vp, vp, vp, i64, C.POINTER(i64)]
+    L.esd_decide_device.argtypes = [vp, i32, i64, i64, vp, vp, vp, i64, C.POINTER(i64), vp]
+    L.esd_copy_scores_device.argtypes = [vp, i32, i64, i64, vp, i32, vp]
+    L.esd_ingest_wait_copied.argtypes = [vp]
     L.esd_debug_read_prev.argtypes = [vp, vp, i64]
     L.esd_set_timing.argtypes = [vp, i32]
     L.esd_kernel_time.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i64)]
     L.esd_kernel_launches.restype = i64
     L.esd_kernel_launches.argtypes = [vp]
-    L.esd_synth_fill.argtypes = [vp, i32, i32, i64, i64, C.c_uint32, vp, i64, C.c_int, vp]
     if L.esd_abi_version() != ESD_ABI_VERSION:
         raise ImportError("libesd.so ABI version mismatch")
     if path == LIB_PATH:
@@ -410,6 +416,25 @@ class EsdContext:
                                               _np_ptr(cuts), cap, C.byref(nc)), "esd_decide_arrays")
         return cuts[: nc.value].tolist(), ratio
 
+    def decide_device(self, detector: int, first_frame_num: int, d_scores_ptr: int, n: int, stream: int = 0, d_ratio_ptr: int = 0):
+        """Decision pass over float64 scores already resident on this ctx's device -> list of cut frame numbers."""
+        cap = max(16, min(int(n), int(self.cfg.max_cuts) if self.cfg.max_cuts > 0 else 65536))
+        cuts = np.empty(cap, np.int64)
+        nc = C.c_int64()
+        self._check(self._L.esd_decide_device(self._h, detector, first_frame_num, n, C.c_void_p(d_scores_ptr),
+                                              C.c_void_p(d_ratio_ptr) if d_ratio_ptr else None, _np_ptr(cuts), cap, C.byref(nc),
+                                              C.c_void_p(stream)), "esd_decide_device")
+        return cuts[: nc.value].tolist()
+
+    def copy_scores_device(self, kind: int, from_frame: int, n: int, dst_ptr: int, dst_device: int = -1, stream: int = 0):
+        """Async device-to-device (peer) copy of one per-frame score array into `dst_ptr` on `dst_device`."""
+        self._check(self._L.esd_copy_scores_device(self._h, kind, from_frame, n, C.c_void_p(dst_ptr), int(dst_device),
+                                                   C.c_void_p(stream)), "esd_copy_scores_device")
+
+    def ingest_wait_copied(self):
+        """Wait until the H2D copies of every ingest push so far have read the caller's (pinned) frames."""
+        self._check(self._L.esd_ingest_wait_copied(self._h), "esd_ingest_wait_copied")
+
     def debug_last_hsv(self) -> np.ndarray:
         """uint8 [dst_h, dst_w, 3] HSV of the last pushed frame at detector resolution (test hook)."""
         w, h = self.dst_size
@@ -434,20 +459,3 @@ class EsdContext:
     @property
     def kernel_launches(self) -> int:
         return int(self._L.esd_kernel_launches(self._h))
-
-
-def synth_fill(out_tensor, seed: int, descs: np.ndarray):
-    """Fill a CUDA uint8 tensor [N,H,W,3] with the synthetic clip frames described by `descs` (int32 [N,8])."""
-    import torch
-
-    L = load_library()
-    descs = np.ascontiguousarray(descs, np.int32)
-    n, h, w, _ = out_tensor.shape
-    assert out_tensor.is_cuda and out_tensor.dtype == torch.uint8 and out_tensor.is_contiguous()
-    assert descs.shape == (n, 8)
-    stream = torch.cuda.current_stream(out_tensor.device).cuda_stream
-    rc = L.esd_synth_fill(C.c_void_p(out_tensor.data_ptr()), w, h, out_tensor.stride(1), out_tensor.stride(0),
-                          seed & 0xFFFFFFFF, _np_ptr(descs), n, out_tensor.device.index, C.c_void_p(stream))
-    if rc != 0:
-        raise EsdError(rc, "esd_synth_fill", (L.esd_last_error(None) or b"").decode())
-    return out_tensor

@@ -29,7 +29,6 @@
 #include "esd_kernels.cuh"
 #include "host_tables.h"
 #include "ingest_gather.h"
-#include "synth_core.h"
 
 using namespace esd;
 
@@ -254,6 +253,18 @@ struct esd_ctx {
     KernelGraph kg;                    // DIRECT except inside esd_process_frame_host
     int64_t pf_ticket = 0;             // sequence number decide_kernel posts into the mailbox when a detector's pass is done
 
+    // stand-alone decision pass (esd_decide_arrays / esd_decide_device): persistent, grow-only scratch -- no allocation,
+    // no legacy-stream launch and no device-wide synchronisation per call
+    cudaStream_t dec_stream = nullptr;
+    double* dec_d_scores = nullptr;      // [dec_cap] staged host scores
+    double* dec_d_ratio = nullptr;       // [dec_cap] adaptive ratios of the pass
+    int64_t dec_cap = 0;
+    DecisionState* dec_d_state = nullptr;
+    uint8_t* dec_h = nullptr;            // pinned, host-mapped: [16 x i64 mailbox][max_cuts x i64 cuts][dec_h_scores x f64 staging]
+    int64_t dec_h_scores = 0;
+    int64_t dec_ticket = 0;
+    bool poisoned = false;               // a push failed after its fused kernel was enqueued: state is undefined until esd_reset
+
     // ingest
     std::vector<IngestSlot> ring;
     int frames_per_slot = 0;
@@ -464,6 +475,7 @@ int ensure_scratch(esd_ctx* c, int64_t n) {
 }
 
 int reset_video_state(esd_ctx* c) {
+    c->poisoned = false;
     c->first_frame = 0;
     c->n_frames = 0;
     c->started = false;
@@ -544,11 +556,16 @@ int push_common(esd_ctx* c, const uint8_t* d_src, int64_t n, int64_t frame_strid
     TraceTimer tr;
     if (!d_src || n <= 0) return fail(c, ESD_ERR_INVALID, "push: null frames or n <= 0");
     if (n > 0x7fffff00LL / std::max(1, c->n_groups)) return fail(c, ESD_ERR_INVALID, "push: batch too large (%lld frames)", (long long)n);
+    if (c->poisoned) return fail(c, ESD_ERR_STATE, "push: an earlier push failed half-way; call esd_reset");
     CU(c, cudaSetDevice(c->device));
-    if (!c->started) {
-        c->first_frame = first_frame_num;
-        c->started = true;
-    } else if (first_frame_num != c->first_frame + c->n_frames) {
+    // Per-video state (started / first_frame, scratch and previous-frame parities, n_frames) is committed only once the fused
+    // kernel is enqueued: a push that fails earlier leaves the ctx untouched and may be retried; one that fails later
+    // (tail launches, graph node updates) poisons the ctx until esd_reset instead of silently diffing against a half-made batch.
+    struct PoisonGuard {
+        esd_ctx* c; bool armed = false, ok = false;
+        ~PoisonGuard() { if (armed && !ok) c->poisoned = true; }
+    } guard{c};
+    if (c->started && first_frame_num != c->first_frame + c->n_frames) {
         return fail(c, ESD_ERR_STATE, "push: frame numbers must be sequential (expected %lld, got %lld)",
                     (long long)(c->first_frame + c->n_frames), (long long)first_frame_num);
     }
@@ -596,7 +613,6 @@ int push_common(esd_ctx* c, const uint8_t* d_src, int64_t n, int64_t frame_strid
     p.prev_in = c->d_prev[c->prev_parity];
     p.prev_out = c->d_prev[c->prev_parity ^ 1];
     const int buf = c->part_buf;
-    c->part_buf ^= 1;
     p.part = c->d_part[buf];
     p.hist_part = c->d_hist_part[buf];
     p.vplane = c->need_edges ? c->d_vplane[buf] : nullptr;
@@ -615,13 +631,19 @@ int push_common(esd_ctx* c, const uint8_t* d_src, int64_t n, int64_t frame_strid
     const bool aligned = ((reinterpret_cast<uintptr_t>(d_src) | (c->nv12 ? reinterpret_cast<uintptr_t>(p.src_uv) : 0) |
                            (uintptr_t)frame_stride | (uintptr_t)row_stride) & 15u) == 0;
     CU(c, ESD_DISPATCH(launch_fused_rp, c->resize, c->pxt, c->need_content, c->need_hist, aligned, c->nv12, c->extras, p, plan.grid, c->smem_bytes, st, kg));
+    guard.armed = true;
+    if (!c->started) {
+        c->first_frame = first_frame_num;
+        c->started = true;
+    }
+    c->part_buf ^= 1;
+    c->prev_parity ^= 1;
     c->launches++;
     tr.lap("launch fused");
     if (c->timing) {
         CU(c, cudaEventRecord(e1, st));
         c->timing_events.emplace_back(e0, e1);
     }
-    c->prev_parity ^= 1;
     // tail (finalize + decision) on the library's own stream, ordered after this fused kernel
     cudaStream_t ts = inline_tail ? st : c->aux_stream;
     if (!inline_tail) {
@@ -685,23 +707,9 @@ int push_common(esd_ctx* c, const uint8_t* d_src, int64_t n, int64_t frame_strid
     }
     c->launches++;
     c->n_frames += n;
+    guard.ok = true;
     tr.lap("launch tail");
     return ESD_OK;
-}
-
-__global__ void synth_fill_kernel(uint8_t* out, int W, int H, long long pitch, long long frame_stride, uint32_t seed,
-                                  const syn_frame_desc* __restrict__ descs, long long n) {
-    const long long px = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long per = (long long)W * H;
-    if (px >= per * n) return;
-    const long long f = px / per;
-    const int rem = (int)(px - f * per);
-    const int y = rem / W, x = rem - y * W;
-    const syn_frame_desc d = descs[f];
-    uint8_t* o = out + f * frame_stride + (long long)y * pitch + 3LL * x;
-    o[0] = (uint8_t)syn_pixel(seed, &d, x, y, 0, W, H);
-    o[1] = (uint8_t)syn_pixel(seed, &d, x, y, 1, W, H);
-    o[2] = (uint8_t)syn_pixel(seed, &d, x, y, 2, W, H);
 }
 
 }  // namespace
@@ -1141,6 +1149,7 @@ int esd_create(esd_ctx** out, const esd_config* cfg, int device) {
     P.thresh_method = cfg->thresh_method;
     P.hash_threshold = cfg->hash_threshold;
     P.hash_min_scene_len = cfg->hash_min_scene_len;
+    P.cuts_stride = c->max_cuts;
 
     CUB(cudaMalloc(&c->d_state, sizeof(DecisionState)));
     CUB(cudaMalloc(&c->d_cuts, sizeof(long long) * 5 * c->max_cuts));
@@ -1177,6 +1186,9 @@ void esd_destroy(esd_ctx* c) {
     for (int b = 0; b < 2; ++b) { cudaFree(c->d_part[b]); cudaFree(c->d_hist_part[b]); cudaFree(c->d_vplane[b]); if (c->ev_fin[b]) cudaEventDestroy(c->ev_fin[b]); }
     cudaFree(c->d_edge_bits); cudaFree(c->d_edge_prev);
     c->kg.destroy();
+    cudaFree(c->dec_d_scores); cudaFree(c->dec_d_ratio); cudaFree(c->dec_d_state);
+    if (c->dec_h) cudaFreeHost(c->dec_h);
+    if (c->dec_stream) cudaStreamDestroy(c->dec_stream);
     if (c->pf_h) cudaFreeHost(c->pf_h);
     if (c->pf_mailbox) cudaFreeHost(c->pf_mailbox);
     if (c->pf_stream) cudaStreamDestroy(c->pf_stream);
@@ -1427,6 +1439,14 @@ int esd_ingest_set_gather(esd_ctx* c, int32_t n_threads) {
     return ESD_OK;
 }
 
+int esd_ingest_wait_copied(esd_ctx* c) {
+    if (!c) return ESD_ERR_INVALID;
+    if (c->ring.empty()) return fail(c, ESD_ERR_STATE, "ingest ring not open");
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaStreamSynchronize(c->copy_stream));  // the H2D copies only: scoring keeps running on the compute stream
+    return ESD_OK;
+}
+
 int esd_ingest_stats(const esd_ctx* c, int64_t* bytes, int64_t* copies) {
     if (!c) return ESD_ERR_INVALID;
     if (bytes) *bytes = c->h2d_bytes;
@@ -1663,6 +1683,73 @@ int esd_process_frame_host(esd_ctx* c, const uint8_t* h_bgr, int64_t pitch, int6
     return ESD_OK;
 }
 
+// Scratch of the stand-alone decision pass: device score/ratio arrays and the state block grow only; results (cut
+// counts, completion ticket, the cuts themselves) are written by decide_kernel straight into host-mapped pinned memory.
+static int ensure_decide_scratch(esd_ctx* c, int64_t n_dev, int64_t n_host_stage) {
+    if (!c->dec_stream) CU(c, cudaStreamCreateWithFlags(&c->dec_stream, cudaStreamNonBlocking));
+    if (!c->dec_d_state) CU(c, cudaMalloc(&c->dec_d_state, sizeof(DecisionState)));
+    if (n_dev > c->dec_cap) {
+        const int64_t ncap = std::max<int64_t>(n_dev, std::max<int64_t>(32768, 2 * c->dec_cap));
+        CU(c, cudaStreamSynchronize(c->dec_stream));
+        cudaFree(c->dec_d_scores); cudaFree(c->dec_d_ratio);
+        c->dec_d_scores = c->dec_d_ratio = nullptr;
+        c->dec_cap = 0;
+        CU(c, cudaMalloc(&c->dec_d_scores, sizeof(double) * ncap));
+        CU(c, cudaMalloc(&c->dec_d_ratio, sizeof(double) * ncap));
+        c->dec_cap = ncap;
+    }
+    if (!c->dec_h || n_host_stage > c->dec_h_scores) {
+        const int64_t ns = std::max<int64_t>(n_host_stage, std::max<int64_t>(32768, 2 * c->dec_h_scores));
+        if (c->dec_h) { CU(c, cudaStreamSynchronize(c->dec_stream)); cudaFreeHost(c->dec_h); c->dec_h = nullptr; c->dec_h_scores = 0; }
+        CU(c, cudaHostAlloc(&c->dec_h, 16 * sizeof(long long) + sizeof(long long) * c->max_cuts + sizeof(double) * ns, cudaHostAllocMapped));
+        memset(c->dec_h, 0, 16 * sizeof(long long));
+        c->dec_h_scores = ns;
+    }
+    return ESD_OK;
+}
+
+// Enqueue the pass over device-resident scores on `st`, wait for this pass only (ticket poll, stream sync as fallback) and
+// hand the cuts back.  d_ratio: device array [n] that receives the adaptive ratios (ESD_DET_ADAPTIVE; library scratch if null).
+static int decide_on_device(esd_ctx* c, int32_t detector, int di, int64_t first_frame_num, int64_t n, const double* d_scores,
+                            double* d_ratio, cudaStream_t st, int64_t* cuts, int64_t cap, int64_t* n_cuts, bool sync_stream) {
+    long long* mailbox = reinterpret_cast<long long*>(c->dec_h);
+    long long* h_cuts = mailbox + 16;
+    mailbox[di] = 0; mailbox[5] = 0;
+    const long long ticket = ++c->dec_ticket;
+    DecisionParams P = c->dparams;
+    P.detectors = detector;
+    P.cuts_stride = 0;  // one list: only `detector` runs
+    CU(c, cudaMemsetAsync(c->dec_d_state, 0, sizeof(DecisionState), st));
+    if (detector == ESD_DET_ADAPTIVE) {
+        if (!d_ratio) d_ratio = c->dec_d_ratio;
+        adaptive_ratio_full_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_scores, d_ratio, (long long)n, P.adaptive_w,
+                                                                                P.adaptive_min_content_val);
+        CU(c, cudaGetLastError());
+        c->launches++;
+    }
+    decide_kernel<<<5, 256, 0, st>>>(P, c->dec_d_state, h_cuts, d_scores, d_scores, d_ratio ? d_ratio : d_scores, d_scores, d_scores, d_scores,
+                                     first_frame_num, 0, n, mailbox, ticket);
+    CU(c, cudaGetLastError());
+    c->launches++;
+    if (sync_stream) {
+        CU(c, cudaStreamSynchronize(st));
+    } else {
+        volatile long long* mb = mailbox;
+        const double t_poll = TraceTimer::now();
+        bool done = false;
+        for (uint32_t spins = 0; !(done = (mb[8 + di] == ticket)); ++spins) {
+            _mm_pause();
+            if ((spins & 0xfff) == 0xfff && TraceTimer::now() - t_poll > 50.0) break;  // 50 ms: let the runtime report what happened
+        }
+        if (!done) CU(c, cudaStreamSynchronize(st));
+    }
+    const int64_t total = mailbox[di];
+    if (n_cuts) *n_cuts = total;
+    if (mailbox[5] || total > cap) return fail(c, ESD_ERR_CAPACITY, "decide: %lld cuts, buffer holds %lld (max_cuts %lld)", (long long)total, (long long)cap, (long long)c->max_cuts);
+    if (total > 0 && cuts) memcpy(cuts, h_cuts, sizeof(int64_t) * total);
+    return ESD_OK;
+}
+
 int esd_decide_arrays(esd_ctx* c, int32_t detector, int64_t first_frame_num, int64_t n, const double* scores,
                       double* adaptive_ratio_out, int64_t* cuts, int64_t cap, int64_t* n_cuts) {
     if (!c || !scores || n < 0) return ESD_ERR_INVALID;
@@ -1671,48 +1758,71 @@ int esd_decide_arrays(esd_ctx* c, int32_t detector, int64_t first_frame_num, int
     CU(c, cudaSetDevice(c->device));
     if (n_cuts) *n_cuts = 0;
     if (n == 0) return ESD_OK;
-    double *d_scores = nullptr, *d_ratio = nullptr;
-    DecisionState* d_st = nullptr;
-    long long* d_cuts = nullptr;
-    int rc = ESD_OK;
-    auto cleanup = [&]() { cudaFree(d_scores); cudaFree(d_ratio); cudaFree(d_st); cudaFree(d_cuts); };
-#define CUD(call)                                                                                  \
-    do {                                                                                           \
-        cudaError_t e_ = (call);                                                                   \
-        if (e_ != cudaSuccess) {                                                                   \
-            cleanup();                                                                             \
-            return fail(c, ESD_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_));          \
-        }                                                                                          \
-    } while (0)
-    CUD(cudaMalloc(&d_scores, sizeof(double) * n));
-    CUD(cudaMalloc(&d_ratio, sizeof(double) * n));
-    CUD(cudaMalloc(&d_st, sizeof(DecisionState)));
-    CUD(cudaMalloc(&d_cuts, sizeof(long long) * 5 * c->max_cuts));
-    CUD(cudaMemcpy(d_scores, scores, sizeof(double) * n, cudaMemcpyHostToDevice));
-    CUD(cudaMemset(d_st, 0, sizeof(DecisionState)));
-    fill_nan_kernel<<<(unsigned)((n + 255) / 256), 256>>>(d_ratio, n);
-    DecisionParams P = c->dparams;
-    P.detectors = detector;
-    if (detector == ESD_DET_ADAPTIVE) {
-        const int w = P.adaptive_w;
-        if (n - w > w)
-            adaptive_ratio_kernel<<<(unsigned)((n - 2 * w + 255) / 256), 256>>>(d_scores, d_ratio, w, n - w, w,
-                                                                               P.adaptive_min_content_val);
+    int rc = ensure_decide_scratch(c, n, n);
+    if (rc) return rc;
+    double* stage = reinterpret_cast<double*>(c->dec_h + 16 * sizeof(long long) + sizeof(long long) * c->max_cuts);
+    memcpy(stage, scores, sizeof(double) * n);
+    CU(c, cudaMemcpyAsync(c->dec_d_scores, stage, sizeof(double) * n, cudaMemcpyHostToDevice, c->dec_stream));
+    if (!(adaptive_ratio_out && detector == ESD_DET_ADAPTIVE)) {
+        rc = decide_on_device(c, detector, di, first_frame_num, n, c->dec_d_scores, nullptr, c->dec_stream, cuts, cap, n_cuts, false);
+        if (adaptive_ratio_out) for (int64_t i = 0; i < n; ++i) adaptive_ratio_out[i] = NAN;  // no ratios for the other detectors
+        return rc;
     }
-    decide_kernel<<<5, 256>>>(P, d_st, d_cuts, d_scores, d_scores, d_ratio, d_scores, d_scores, d_scores, first_frame_num, 0, n, nullptr, 0LL);
-    c->launches += 3;
-    CUD(cudaGetLastError());
-    CUD(cudaDeviceSynchronize());
-    DecisionState st;
-    CUD(cudaMemcpy(&st, d_st, sizeof st, cudaMemcpyDeviceToHost));
-    const int64_t total = st.n_cuts[di];
-    if (n_cuts) *n_cuts = total;
-    if (st.overflow || total > cap) rc = fail(c, ESD_ERR_CAPACITY, "decide_arrays: %lld cuts, buffer holds %lld", (long long)total, (long long)cap);
-    else if (total > 0 && cuts) CUD(cudaMemcpy(cuts, d_cuts + (int64_t)di * c->max_cuts, sizeof(int64_t) * total, cudaMemcpyDeviceToHost));
-    if (adaptive_ratio_out) CUD(cudaMemcpy(adaptive_ratio_out, d_ratio, sizeof(double) * n, cudaMemcpyDeviceToHost));
-#undef CUD
-    cleanup();
+    // adaptive with the ratios wanted on the host: the pass, then the D2H copy of the ratios behind it
+    rc = decide_on_device(c, detector, di, first_frame_num, n, c->dec_d_scores, c->dec_d_ratio, c->dec_stream, cuts, cap, n_cuts, false);
+    if (rc && rc != ESD_ERR_CAPACITY) return rc;
+    CU(c, cudaMemcpyAsync(stage, c->dec_d_ratio, sizeof(double) * n, cudaMemcpyDeviceToHost, c->dec_stream));
+    CU(c, cudaStreamSynchronize(c->dec_stream));
+    memcpy(adaptive_ratio_out, stage, sizeof(double) * n);
     return rc;
+}
+
+int esd_decide_device(esd_ctx* c, int32_t detector, int64_t first_frame_num, int64_t n, const double* d_scores,
+                      double* d_adaptive_ratio_out, int64_t* cuts, int64_t cap, int64_t* n_cuts, void* stream) {
+    if (!c || !d_scores || n < 0) return ESD_ERR_INVALID;
+    const int di = det_index(detector);
+    if (di < 0 || !(c->cfg.detectors & detector)) return fail(c, ESD_ERR_INVALID, "decide_device: detector %d not configured", detector);
+    CU(c, cudaSetDevice(c->device));
+    if (n_cuts) *n_cuts = 0;
+    if (n == 0) return ESD_OK;
+    int rc = validate_device_span(c, reinterpret_cast<const uint8_t*>(d_scores), sizeof(double) * (size_t)n, "decide_device (scores)");
+    if (rc) return rc;
+    if (d_adaptive_ratio_out) {
+        rc = validate_device_span(c, reinterpret_cast<const uint8_t*>(d_adaptive_ratio_out), sizeof(double) * (size_t)n, "decide_device (ratios)");
+        if (rc) return rc;
+    }
+    rc = ensure_decide_scratch(c, detector == ESD_DET_ADAPTIVE && !d_adaptive_ratio_out ? n : 0, 0);
+    if (rc) return rc;
+    return decide_on_device(c, detector, di, first_frame_num, n, d_scores, d_adaptive_ratio_out, (cudaStream_t)stream, cuts, cap, n_cuts, false);
+}
+
+int esd_copy_scores_device(esd_ctx* c, int32_t kind, int64_t from_frame, int64_t n, double* d_dst, int32_t dst_device, void* stream) {
+    if (!c || !d_dst || n < 0) return ESD_ERR_INVALID;
+    if (n == 0) return ESD_OK;
+    const int64_t i0 = from_frame - c->first_frame;
+    if (!c->started || i0 < 0 || i0 + n > c->n_frames)
+        return fail(c, ESD_ERR_INVALID, "copy_scores_device: range [%lld, %lld) outside pushed frames", (long long)from_frame, (long long)(from_frame + n));
+    const double* src = nullptr;
+    switch (kind) {
+        case ESD_SCORE_CONTENT_VAL: src = c->need_content ? c->d_cv : nullptr; break;
+        case ESD_SCORE_ADAPTIVE_VAL: src = c->need_content ? c->d_av : nullptr; break;
+        case ESD_SCORE_ADAPTIVE_RATIO: src = (c->cfg.detectors & ESD_DET_ADAPTIVE) ? c->d_ratio : nullptr; break;
+        case ESD_SCORE_HIST_DIFF: src = c->need_hist ? c->d_hdiff : nullptr; break;
+        case ESD_SCORE_AVERAGE_RGB: src = (c->cfg.detectors & ESD_DET_THRESHOLD) ? c->d_avg : nullptr; break;
+        case ESD_SCORE_HASH_DIST: src = c->need_hash ? c->d_hdist : nullptr; break;
+        default: return fail(c, ESD_ERR_INVALID, "copy_scores_device: unknown score kind %d", kind);
+    }
+    if (!src) return fail(c, ESD_ERR_STATE, "copy_scores_device: score kind %d is not produced by the configured detectors", kind);
+    CU(c, cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    // order the copy behind every finalize tail enqueued so far (they run on the library's stream)
+    CU(c, cudaEventRecord(c->ev_join, c->aux_stream));
+    CU(c, cudaStreamWaitEvent(st, c->ev_join, 0));
+    if (dst_device == c->device || dst_device < 0)
+        CU(c, cudaMemcpyAsync(d_dst, src + i0, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+    else
+        CU(c, cudaMemcpyPeerAsync(d_dst, dst_device, src + i0, c->device, sizeof(double) * n, st));
+    return ESD_OK;
 }
 
 int esd_debug_read_prev(esd_ctx* c, uint32_t* out, int64_t cap) {
@@ -1751,26 +1861,5 @@ int esd_kernel_time(esd_ctx* c, double* fused_ms, int64_t* fused_launches) {
 }
 
 int64_t esd_kernel_launches(const esd_ctx* c) { return c ? c->launches : 0; }
-
-int esd_synth_fill(uint8_t* d_out, int32_t width, int32_t height, int64_t pitch, int64_t frame_stride, uint32_t seed,
-                   const int32_t* descs, int64_t n, int device, void* stream) {
-    if (!d_out || !descs || n <= 0 || width < 1 || height < 1) return ESD_ERR_INVALID;
-    if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, ESD_ERR_CUDA, "synth_fill: cudaSetDevice(%d) failed", device);
-    syn_frame_desc* d_desc = nullptr;
-    cudaError_t e = cudaMalloc(&d_desc, sizeof(syn_frame_desc) * n);
-    if (e != cudaSuccess) return fail(nullptr, ESD_ERR_CUDA, "synth_fill: %s", cudaGetErrorString(e));
-    cudaStream_t st = (cudaStream_t)stream;
-    e = cudaMemcpyAsync(d_desc, descs, sizeof(syn_frame_desc) * n, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) {
-        const long long total = (long long)width * height * n;
-        synth_fill_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_out, width, height, pitch, frame_stride, seed,
-                                                                           d_desc, n);
-        e = cudaGetLastError();
-    }
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    cudaFree(d_desc);
-    if (e != cudaSuccess) return fail(nullptr, ESD_ERR_CUDA, "synth_fill: %s", cudaGetErrorString(e));
-    return ESD_OK;
-}
 
 }  // extern "C"

@@ -773,6 +773,35 @@ __global__ void adaptive_ratio_kernel(const double* __restrict__ val, double* __
     ratio[t] = r;
 }
 
+// Stand-alone flavour for a whole score array (global decision pass of frame-range sharding): thread per frame index,
+// NaN where the window is incomplete, so no separate fill pass is needed.
+__global__ void adaptive_ratio_full_kernel(const double* __restrict__ val, double* __restrict__ ratio, long long n, int w,
+                                           double min_content_val) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    if (t < w || t >= n - w) {
+        ratio[t] = __longlong_as_double(0x7ff8000000000000LL);
+        return;
+    }
+    double sum = 0.0;
+    bool first = true;
+    for (int k = -w; k <= w; ++k) {
+        if (k == 0) continue;
+        const double s = val[t + k];
+        sum = first ? s : __dadd_rn(sum, s);
+        first = false;
+    }
+    const double avg = __ddiv_rn(sum, __dmul_rn(2.0, (double)w));
+    const double target = val[t];
+    double r = 0.0;
+    if (!(fabs(avg) < 0.00001)) {
+        const double q = __ddiv_rn(target, avg);
+        r = (255.0 < q) ? 255.0 : q;
+    } else if (target >= min_content_val) {
+        r = 255.0;
+    }
+    ratio[t] = r;
+}
 
 // ----------------------------------------------------------------------------------- edges
 // ContentDetector._detect_edges on the device: numpy.median(lum) -> Canny(low, high) -> dilate(k x k ones).
@@ -1269,6 +1298,7 @@ struct DecisionParams {
     int thresh_min_scene_len, thresh_method;  // method 0 FLOOR, 1 CEILING
     double hash_threshold;
     int hash_min_scene_len, pad;
+    long long cuts_stride;  // cut list of detector d starts at cuts + d * cuts_stride (max_cuts; 0 = one shared list, stand-alone pass)
 };
 
 struct CutSink {
@@ -1299,7 +1329,7 @@ __global__ void decide_kernel(DecisionParams P, DecisionState* __restrict__ st, 
     const int tid = threadIdx.x;
 
     // thread 0's register copy of this detector's state
-    CutSink sink{cuts + (size_t)det * P.max_cuts, 0, P.max_cuts, 0};
+    CutSink sink{cuts + (size_t)det * P.cuts_stride, 0, P.max_cuts, 0};
     long long last = 0, merge_start = 0;
     int init = 0, merge_enabled = 0, merge_triggered = 0;
     if (tid == 0) {

@@ -33,11 +33,13 @@ class FlashFilter:
 
 
 class StatsManager:
-    """Minimal stand-in for scenedetect.stats_manager.StatsManager: per-frame metric store."""
+    """Stand-in for scenedetect.stats_manager.StatsManager: per-frame metric store + the stats-file CSV writer
+    (``Frame Number,Timecode,<metric keys sorted>``, 1-based frame numbers, one row per frame holding metrics)."""
 
-    def __init__(self):
+    def __init__(self, fps: float = 30.0):
         self._frame_metrics: Dict[int, Dict[str, float]] = {}
         self._metric_keys: List[str] = []
+        self.fps = float(fps)  # for the Timecode column; SceneManager.detect_scenes sets it from the video
 
     def register_metrics(self, keys):
         for k in keys:
@@ -59,17 +61,23 @@ class StatsManager:
     def metric_keys(self):
         return list(self._metric_keys)
 
-    def save_to_csv(self, csv_file):
+    def save_to_csv(self, csv_file, fps: Optional[float] = None):
+        """scenedetect.StatsManager.save_to_csv [upstream-recall]: header ``Frame Number,Timecode`` + the sorted metric
+        keys; per frame the 1-based frame number, its HH:MM:SS.nnn timecode and ``str(metric)`` per key."""
         import csv
 
+        from .service import frame_to_timecode
+
+        rate = float(fps or self.fps)
         own = isinstance(csv_file, (str, bytes))
         f = open(csv_file, "w", newline="") if own else csv_file
         try:
             wr = csv.writer(f, lineterminator="\n")
-            wr.writerow(["Frame Number"] + self._metric_keys)
+            keys = sorted(self._metric_keys)
+            wr.writerow(["Frame Number", "Timecode"] + keys)
             for fn in sorted(self._frame_metrics):
                 row = self._frame_metrics[fn]
-                wr.writerow([fn + 1] + [("" if row.get(k) is None else repr(float(row[k]))) for k in self._metric_keys])
+                wr.writerow([fn + 1, frame_to_timecode(fn, rate)] + [str(row.get(k)) for k in keys])
         finally:
             if own:
                 f.close()
@@ -193,7 +201,12 @@ class SceneDetector:
 
     def _publish_metrics(self, first_frame_num: int, n: int):
         sc = self._ctx.read_scores(first_frame_num, n)
+        # the first frame of the video has no predecessor: PySceneDetect's _calculate_frame_score returns before it
+        # stores any content metric for it
+        first_video_frame = first_frame_num + n - self._ctx.frames_pushed
         for k in range(n):
+            if first_frame_num + k == first_video_frame and isinstance(self, ContentDetector):
+                continue
             m = self._metrics_for(sc, k)
             if m:
                 self.stats_manager.set_metrics(first_frame_num + k, m)
@@ -472,7 +485,7 @@ class ThresholdDetector(SceneDetector):
 
     def post_process(self, frame_num: int) -> List[int]:
         cuts = self._flush_staged()
-        ctx = self._ctx or self._manager_ctx
+        ctx = self._manager_ctx or self._ctx  # while a SceneManager drives this detector its context is the live one
         if ctx is None:
             return cuts
         return cuts + ctx.post_process(capi.ESD_DET_THRESHOLD, frame_num)

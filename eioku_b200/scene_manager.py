@@ -200,6 +200,8 @@ class SceneManager:
             self._frame_rate = float(fps)
         else:
             self._frame_rate = float(getattr(video, "frame_rate", 30.0))
+        if self.stats_manager is not None:
+            self.stats_manager.fps = self._frame_rate
         width, height = video.frame_size
         self.close()
         nv12 = getattr(video, "pixel_format", "bgr24") == "nv12"
@@ -224,7 +226,7 @@ class SceneManager:
                 else:
                     ctx.ingest_push_numpy(batch, pos)
                 if not getattr(video, "frames_stable", False):
-                    ctx.synchronize()  # the producer may recycle `batch` as soon as we return to read_batch
+                    ctx.ingest_wait_copied()  # the producer may recycle `batch` as soon as we return to read_batch (H2D done; scoring continues)
             elif nv12:
                 ctx.push_nv12_tensor(batch, pos)
             else:

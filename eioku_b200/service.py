@@ -306,6 +306,46 @@ def scene_detection_response(video_path: str, config: dict, scenes: Sequence[dic
             "scenes": [{"scene_index": s["scene_index"], "start_ms": s["start_ms"], "end_ms": s["end_ms"]} for s in scenes]}
 
 
+def scene_artifact_envelopes(result: dict, video_id: str, run_id: Optional[str] = None, created_at=None,
+                             task_type: str = "scene_detection") -> List[dict]:
+    """The ArtifactEnvelope fields the reference's task handler builds per scene from a scene-task result
+    (/root/reference/ml-service/src/workers/task_handler.py:145-153 provenance defaults, :257-331 per-item loop;
+    dataclass at ml-service/src/domain/artifacts.py:7-73), as a pure function: one dict per scene, keyed like the
+    dataclass, so ``ArtifactEnvelope(**d)`` validates.  `result` is what ``detect_scenes`` returns, optionally with the
+    provenance keys of ``scene_detection_response`` merged in; like the handler, a missing producer falls back to
+    "ml-service"/"1.0.0", missing hashes to "", and items without start_ms/end_ms or with start > end are dropped."""
+    import json
+    import uuid
+    from datetime import datetime, timezone
+
+    run_id = run_id or result.get("run_id") or str(uuid.uuid4())
+    created_at = created_at or datetime.now(timezone.utc).replace(tzinfo=None)
+    out = []
+    for idx, scene in enumerate(result.get("scenes", [])):
+        if "start_ms" not in scene or "end_ms" not in scene:
+            continue  # task_handler.py:277-293: no time information -> dropped
+        a, b = int(scene["start_ms"]), int(scene["end_ms"])
+        if a < 0 or b < 0 or a > b:
+            continue  # task_handler.py:295-308
+        out.append({
+            "artifact_id": f"{video_id}_{task_type}_{run_id}_{idx}",
+            "asset_id": video_id,
+            "artifact_type": "scene",  # task_to_artifact_type, task_handler.py:160-168
+            "schema_version": 1,
+            "span_start_ms": a,
+            "span_end_ms": b,
+            "payload_json": json.dumps(scene),
+            "producer": result.get("producer", "ml-service"),
+            "producer_version": result.get("producer_version", "1.0.0"),
+            "model_profile": result.get("model_profile", "balanced"),
+            "config_hash": result.get("config_hash", ""),
+            "input_hash": result.get("input_hash", ""),
+            "run_id": run_id,
+            "created_at": created_at,
+        })
+    return out
+
+
 class ModelManager:
     """The scene-detection slice of the reference's ModelManager (model_manager.py:715)."""
 

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define ESD_ABI_VERSION 2
+#define ESD_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define ESD_API __attribute__((visibility("default")))
@@ -44,7 +44,7 @@ typedef enum esd_status {
     ESD_ERR_INVALID = -1,     /* bad argument / config */
     ESD_ERR_CUDA = -2,        /* a CUDA runtime call failed (see esd_last_error) */
     ESD_ERR_NOMEM = -3,
-    ESD_ERR_STATE = -4,       /* call out of order (e.g. non-sequential frame numbers) */
+    ESD_ERR_STATE = -4,       /* call out of order (e.g. non-sequential frame numbers; a push after a half-failed push) */
     ESD_ERR_UNSUPPORTED = -5, /* e.g. destination width > 1024 when resizing, odd-size hash DCT, NV12 without a downscale */
     ESD_ERR_CAPACITY = -6     /* caller buffer or cut list too small */
 } esd_status;
@@ -192,6 +192,11 @@ ESD_API int esd_ingest_close(esd_ctx* ctx);
  * every destination column reads (6 * dst_width bytes per row) into the pinned ring, so e.g. 442 KB instead of
  * 1.66 MB per 1080p frame cross PCIe; the host does no arithmetic.  0 (default) = DMA of whole touched rows, no CPU work. */
 ESD_API int esd_ingest_set_gather(esd_ctx* ctx, int32_t n_threads);
+/* Lifetime rule of esd_ingest_push_host: with PINNED caller memory (and no gather threads) the H2D copies read the caller's
+ * frames directly and are still in flight when the call returns -- the frames must stay valid and unmodified until
+ * esd_ingest_wait_copied (H2D copies done; scoring may still be running) or esd_synchronize returns.  Pageable frames and
+ * the gather path are consumed before the call returns. */
+ESD_API int esd_ingest_wait_copied(esd_ctx* ctx);
 /* bytes moved host->device by the ingest path since esd_reset */
 ESD_API int esd_ingest_stats(const esd_ctx* ctx, int64_t* h2d_bytes, int64_t* h2d_copies);
 
@@ -247,12 +252,28 @@ ESD_API int esd_get_cuts(esd_ctx* ctx, int32_t detector, int64_t from_index, int
 
 /* Stand-alone decision pass over score arrays already on the host (merge step of frame-range
  * sharding: shards return scores, one global pass decides).  Uses the ctx's detector parameters but
- * none of its frame state.  For ESD_DET_ADAPTIVE `scores` = adaptive_val (ratios are recomputed);
+ * none of its frame state.  Runs on a library-owned stream with persistent pinned / device scratch (no allocation, no
+ * device-wide synchronisation: other contexts of the device keep running).  For ESD_DET_ADAPTIVE `scores` = adaptive_val (ratios are recomputed);
  * ESD_DET_CONTENT: content_val; ESD_DET_HIST: hist_diff (NaN = no previous frame); ESD_DET_THRESHOLD: average_rgb;
  * ESD_DET_HASH: hash_dist (NaN = no previous frame). */
 ESD_API int esd_decide_arrays(esd_ctx* ctx, int32_t detector, int64_t first_frame_num, int64_t n,
                       const double* scores, double* adaptive_ratio_out, int64_t* cuts, int64_t cap,
                       int64_t* n_cuts);
+
+/* Same decision pass over scores ALREADY ON THE DEVICE of this ctx (e.g. score slabs peer-copied or all-gathered from the
+ * shards of a long video, so the merge never visits the host).  Enqueued on `stream` (the caller's); waits for this pass
+ * only (no device-wide synchronisation) and returns the cuts.  d_adaptive_ratio_out: optional device array [n] that
+ * receives the recomputed adaptive ratios (ESD_DET_ADAPTIVE). */
+ESD_API int esd_decide_device(esd_ctx* ctx, int32_t detector, int64_t first_frame_num, int64_t n, const double* d_scores,
+                              double* d_adaptive_ratio_out, int64_t* cuts, int64_t cap, int64_t* n_cuts, void* stream);
+
+/* One per-frame float64 score array of frames [from_frame, from_frame + n), copied device-to-device into `d_dst` on device
+ * `dst_device` (peer copy over NVLink when it differs from the ctx's device; < 0 = the ctx's own device).  Asynchronous on
+ * `stream` (a stream of the ctx's device), ordered behind every scoring tail enqueued so far. */
+enum { ESD_SCORE_CONTENT_VAL = 0, ESD_SCORE_ADAPTIVE_VAL = 1, ESD_SCORE_HIST_DIFF = 2, ESD_SCORE_AVERAGE_RGB = 3,
+       ESD_SCORE_HASH_DIST = 4, ESD_SCORE_ADAPTIVE_RATIO = 5 };
+ESD_API int esd_copy_scores_device(esd_ctx* ctx, int32_t kind, int64_t from_frame, int64_t n, double* d_dst, int32_t dst_device,
+                                   void* stream);
 
 /* Instrumentation: CUDA-event timing of the fused scoring kernel on the launching stream. */
 ESD_API int esd_set_timing(esd_ctx* ctx, int32_t enable);
@@ -264,12 +285,6 @@ ESD_API int64_t esd_kernel_launches(const esd_ctx* ctx);
 /* Test hook: packed H | S<<8 | V<<16 of the last pushed frame at detector resolution
  * ([dst_height][dst_width] uint32), i.e. the on-device twin of cvtColor(resize(frame)).  Synchronises. */
 ESD_API int esd_debug_read_prev(esd_ctx* ctx, uint32_t* out, int64_t cap_elems);
-
-/* Synthetic clip filler (benchmark/test input, csrc/synth_core.h): writes n frames of WxHx3 BGR
- * described by host descriptors `descs` (int32[n][8]) into device memory. */
-ESD_API int esd_synth_fill(uint8_t* d_out, int32_t width, int32_t height, int64_t pitch_bytes,
-                   int64_t frame_stride_bytes, uint32_t seed, const int32_t* descs, int64_t n,
-                   int device, void* stream);
 
 #ifdef __cplusplus
 }

@@ -17,7 +17,7 @@ _lib = None
 
 def build(force: bool = False) -> str:
     src = os.path.join(_HERE, "esd_oracle.c")
-    hdr = os.path.join(_HERE, "..", "eioku_b200", "csrc", "synth_core.h")
+    hdr = os.path.join(_HERE, "..", "synthclip", "synth_core.h")
     stale = (not os.path.exists(_SO)) or any(
         os.path.exists(p) and os.path.getmtime(p) > os.path.getmtime(_SO) for p in (src, hdr))
     if force or stale:

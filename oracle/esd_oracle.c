@@ -22,7 +22,7 @@
 #include <stdlib.h>
 #include <string.h>
 
-#include "../eioku_b200/csrc/synth_core.h"
+#include "../synthclip/synth_core.h"
 
 #define ORC_API __attribute__((visibility("default")))
 

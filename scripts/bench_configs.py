@@ -19,7 +19,8 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-from eioku_b200 import capi, sharding, synth  # noqa: E402
+from eioku_b200 import capi, sharding  # noqa: E402
+import synthclip as synth
 from eioku_b200.detectors import AdaptiveDetector, ContentDetector, HistogramDetector  # noqa: E402
 from eioku_b200.scene_manager import SceneManager  # noqa: E402
 
@@ -43,7 +44,7 @@ def dist_env():
 def fill(seed, w, h, descs, dev, chunk=256):
     out = torch.empty((len(descs), h, w, 3), dtype=torch.uint8, device=dev)
     for a in range(0, len(descs), chunk):
-        capi.synth_fill(out[a:a + chunk], seed, descs[a:a + chunk])
+        synth.fill(out[a:a + chunk], seed, descs[a:a + chunk])
     return out
 
 

@@ -3,10 +3,11 @@ rolling software-prefetch distance of the gather loop (0 = the next-row page tou
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
-from eioku_b200 import capi, synth
+from eioku_b200 import capi
+import synthclip as synth
 W, H, n = 1920, 1080, 512
 sch = synth.build_schedule(1002, n)
-clip = torch.empty((n, H, W, 3), dtype=torch.uint8, device="cuda:0"); capi.synth_fill(clip, 1002, sch.descs)
+clip = torch.empty((n, H, W, 3), dtype=torch.uint8, device="cuda:0"); synth.fill(clip, 1002, sch.descs)
 host_pinned = clip.cpu().pin_memory().numpy()
 cfg = capi.default_config(); cfg.src_width, cfg.src_height = W, H
 ref = capi.EsdContext(cfg, 0); ref.push_tensor(clip, 0); want = ref.read_scores(0, n, ["sums3"])["sums3"]; ref.close()

@@ -1,10 +1,11 @@
 import os, sys, itertools
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from eioku_b200 import capi, synth
+from eioku_b200 import capi
+import synthclip as synth
 W,H,n=1920,1080,128
 sch=synth.build_schedule(1002,n)
-clip=torch.empty((n,H,W,3),dtype=torch.uint8,device="cuda:0"); capi.synth_fill(clip,1002,sch.descs)
+clip=torch.empty((n,H,W,3),dtype=torch.uint8,device="cuda:0"); synth.fill(clip,1002,sch.descs)
 stream=torch.cuda.current_stream().cuda_stream
 for R,RS,S,occ in [(0,0,0,0),(2,1,4,0),(2,2,3,0),(4,1,4,0),(1,1,4,0),(4,2,2,0)]:
     cfg=capi.default_config(); cfg.src_width,cfg.src_height,cfg.dst_width,cfg.dst_height=W,H,W,H

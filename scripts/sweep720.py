@@ -2,12 +2,13 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from eioku_b200 import capi, synth
+from eioku_b200 import capi
+import synthclip as synth
 W, H, n, seed = int(os.environ.get("W", 1280)), int(os.environ.get("H", 720)), 1800, 1001
 sch = synth.build_schedule(seed, n)
 clip = torch.empty((n, H, W, 3), dtype=torch.uint8, device="cuda:0")
 for a in range(0, n, 300):
-    capi.synth_fill(clip[a:a + 300], seed, sch.descs[a:a + 300])
+    synth.fill(clip[a:a + 300], seed, sch.descs[a:a + 300])
 stream = torch.cuda.current_stream().cuda_stream
 for (st, rs, rg) in [(0, 0, 0), (2, 4, 16), (3, 4, 16), (4, 4, 16), (3, 2, 16), (4, 2, 16), (6, 2, 16), (3, 4, 8), (4, 3, 16), (3, 3, 16)]:
     cfg = capi.default_config()

@@ -1,8 +1,8 @@
 """Seeded synthetic clip *schedule* (SURVEY.md section 8d): which scene(s), blend, pan
 and noise stream every frame is made of.  The schedule is pure Python/integer, so it
 is identical everywhere; pixels are produced from it either on the GPU
-(``eioku_b200.capi.synth_fill`` -> ``esd_synth_fill``) or by the CPU twin that the
-test-suite's oracle builds from the same ``csrc/synth_core.h``.
+(``synthclip.fill`` -> ``libesd_synth.so``) or by the CPU twin that the
+test-suite's oracle builds from the same ``synthclip/synth_core.h``.
 
 Clip structure: scene lengths uniform in [45, 240] frames; every 5th transition is a
 24-frame dissolve, every 11th a 30-frame fade through black, the rest hard cuts;

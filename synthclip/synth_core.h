@@ -1,4 +1,4 @@
-/* Synthetic clip pixel generator -- shared by the CUDA filler (esd_synth.cu) and
+/* Synthetic clip pixel generator -- shared by the CUDA filler (synthclip/synth_fill.cu) and
  * the CPU twin (oracle/esd_oracle.c) so that both produce identical bytes.
  *
  * This is benchmark/test *input* infrastructure, not part
@@ -25,7 +25,7 @@
 #define SYN_SCENE_BLACK (-1)
 #define SYN_SCENE_WHITE (-2)
 
-/* one descriptor per frame, built on the host by eioku_b200/synth.py */
+/* one descriptor per frame, built on the host by synthclip/schedule.py */
 typedef struct syn_frame_desc {
     int32_t scene_a; /* scene id >= 0, or SYN_SCENE_BLACK / SYN_SCENE_WHITE */
     int32_t scene_b;

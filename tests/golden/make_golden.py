@@ -32,7 +32,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(HERE, "..", ".."))
 
-from eioku_b200 import synth  # noqa: E402
+import synthclip as synth  # noqa: E402
 from oracle import c_oracle as co  # noqa: E402
 from oracle import psd_cv2 as P  # noqa: E402
 

@@ -6,7 +6,8 @@ import pytest
 pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
 
-from eioku_b200 import capi, synth  # noqa: E402
+from eioku_b200 import capi  # noqa: E402
+import synthclip as synth
 from eioku_b200.detectors import AdaptiveDetector, ContentDetector, HistogramDetector, StatsManager  # noqa: E402
 from eioku_b200.scene_manager import SceneManager, TensorVideo  # noqa: E402
 from oracle import c_oracle as co  # noqa: E402

@@ -18,7 +18,8 @@ pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
 cv2 = pytest.importorskip("cv2")
 
-from eioku_b200 import capi, synth  # noqa: E402
+from eioku_b200 import capi  # noqa: E402
+import synthclip as synth
 from eioku_b200.detectors import ContentDetector, HashDetector, StatsManager  # noqa: E402
 from eioku_b200.scene_manager import BatchVideo, SceneManager  # noqa: E402
 from eioku_b200.service import detect_scenes_frames  # noqa: E402
@@ -111,7 +112,7 @@ def test_hash_clip_golden(name):
                 for k in range(a - batch, a):
                     thumbs.update(sm._ctx.debug_hash_input(k).tobytes())
             out = torch.empty((len(sch.descs[a:a + batch]), h, w, 3), dtype=torch.uint8, device=DEV)
-            capi.synth_fill(out, seed, sch.descs[a:a + batch])
+            synth.fill(out, seed, sch.descs[a:a + batch])
             ctx_box["on"] = True
             yield out
 
@@ -150,7 +151,7 @@ def test_hash_thumbnails_sha_vs_golden():
     with capi.EsdContext(cfg, 0) as ctx:
         for a in range(0, n, 100):
             out = torch.empty((100, h, w, 3), dtype=torch.uint8, device=DEV)
-            capi.synth_fill(out, seed, sch.descs[a:a + 100])
+            synth.fill(out, seed, sch.descs[a:a + 100])
             ctx.push_tensor(out, a)
             for k in range(a, a + 100):
                 sha.update(ctx.debug_hash_input(k).tobytes())

@@ -11,7 +11,8 @@ pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
 cv2 = pytest.importorskip("cv2")
 
-from eioku_b200 import capi, synth  # noqa: E402
+from eioku_b200 import capi  # noqa: E402
+import synthclip as synth
 from eioku_b200.detectors import AdaptiveDetector, ContentDetector, HashDetector, HistogramDetector, ThresholdDetector  # noqa: E402
 from eioku_b200.scene_manager import BatchVideo, SceneManager, TensorVideo  # noqa: E402
 from oracle import c_oracle as co  # noqa: E402
@@ -128,7 +129,7 @@ def test_nv12_clip_through_scene_manager_all_detectors():
     w, h, n, seed = 1920, 1080, 240, 1002
     sch = synth.build_schedule(seed, n, min_len=20, max_len=70)
     bgr_syn = torch.empty((n, h, w, 3), dtype=torch.uint8, device=DEV)
-    capi.synth_fill(bgr_syn, seed, sch.descs)
+    synth.fill(bgr_syn, seed, sch.descs)
     nv12 = synth.bgr_to_test_nv12(bgr_syn)
     nv12_np = nv12.cpu().numpy()
     assert np.array_equal(nv12_np, synth.bgr_to_test_nv12(bgr_syn.cpu().numpy()))
@@ -195,7 +196,7 @@ def test_nv12_clip_vs_committed_cv2_golden():
     w, h, n, seed = int(g["width"]), int(g["height"]), int(g["n_frames"]), int(g["seed"])
     sch = synth.build_schedule(seed, n, min_len=20, max_len=70)
     bgr = torch.empty((n, h, w, 3), dtype=torch.uint8, device=DEV)
-    capi.synth_fill(bgr, seed, sch.descs)
+    synth.fill(bgr, seed, sch.descs)
     nv12 = synth.bgr_to_test_nv12(bgr)
     assert hashlib.sha256(nv12.cpu().numpy().tobytes()).digest() == bytes(g["input_sha256"])
     dets = [ContentDetector(threshold=27.0, min_scene_len=15), AdaptiveDetector(), HistogramDetector()]

@@ -13,7 +13,8 @@ pytestmark = pytest.mark.gpu
 
 torch = pytest.importorskip("torch")
 
-from eioku_b200 import capi, synth  # noqa: E402
+from eioku_b200 import capi  # noqa: E402
+import synthclip as synth
 from eioku_b200.detectors import (AdaptiveDetector, ContentDetector, FlashFilter, HistogramDetector,  # noqa: E402
                                   ThresholdDetector)
 from eioku_b200.scene_manager import SceneManager, TensorVideo  # noqa: E402
@@ -39,7 +40,7 @@ def make_ctx(w, h, dst=None, detectors=ALL, **kw):
 
 def gpu_clip(seed, w, h, descs):
     out = torch.empty((len(descs), h, w, 3), dtype=torch.uint8, device=DEV)
-    capi.synth_fill(out, seed, descs)
+    synth.fill(out, seed, descs)
     return out
 
 
@@ -604,8 +605,8 @@ def test_model_manager_on_a_real_video_file(tmp_path):
     ref_cuts, _ = P.detect(decoded, [ref_det], backend="closed_form")
     assert scenes == P.get_scenes_from_cuts(ref_cuts, 0, n)
     rows = open(stats_csv).read().strip().split("\n")
-    assert rows[0].startswith("Frame Number,content_val") and len(rows) == n  # header + frames 2..n (frame 1 has no score)
-    assert float(rows[1].split(",")[1]) == ref_det.scores[1]
+    assert rows[0].startswith("Frame Number,Timecode,content_val") and len(rows) == n  # header + frames 2..n (frame 1 has no score)
+    assert rows[1].split(",")[:2] == ["2", "00:00:00.040"] and float(rows[1].split(",")[2]) == ref_det.scores[1]
     np.save(str(tmp_path / "clip.npy"), np.stack(decoded))
     assert asyncio.run(ModelManager().detect_scenes(str(tmp_path / "clip.npy"), {"fps": 25.0})) == \
         P.detect_scenes_dicts(decoded, [P.ContentDetector(backend="closed_form")], 25.0, backend="closed_form")

@@ -230,7 +230,12 @@ def test_stats_manager_csv():
     buf = io.StringIO()
     sm.save_to_csv(buf)
     lines = buf.getvalue().strip().split("\n")
-    assert lines[0] == "Frame Number,content_val,delta_hue" and lines[2] == "2,1.5,2.0"
+    # scenedetect's stats-file layout: Frame Number (1-based), Timecode, then the metric keys sorted; str() per value
+    assert lines[0] == "Frame Number,Timecode,content_val,delta_hue"
+    assert lines[1] == "1,00:00:00.000,0.0,None" and lines[2] == "2,00:00:00.033,1.5,2.0"
+    buf = io.StringIO()
+    sm.save_to_csv(buf, fps=25.0)
+    assert buf.getvalue().strip().split("\n")[2] == "2,00:00:00.040,1.5,2.0"
 
 
 # ------------------------------------------------------------------------------------------- sharding
@@ -268,7 +273,7 @@ def _gloo_worker(rank, world, port, q):
 
     sys.path.insert(0, ROOT)
     from eioku_b200 import sharding as sh
-    from eioku_b200 import synth
+    import synthclip as synth
     from oracle import c_oracle as co
     from oracle import psd_cv2 as PP
 
@@ -351,7 +356,7 @@ def test_hash_detector_fills_config_and_metric_key():
 
 
 def test_nv12_video_geometry_and_test_content():
-    from eioku_b200 import synth
+    import synthclip as synth
     from eioku_b200.scene_manager import TensorVideo
 
     rng = np.random.default_rng(0)

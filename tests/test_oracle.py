@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from conftest import GOLDEN, load_golden
-from eioku_b200 import synth
+import synthclip as synth
 from oracle import c_oracle as co
 from oracle import closed_form as cf
 from oracle import psd_cv2 as P
@@ -226,7 +226,7 @@ def test_hash_closed_form_vs_cv2_golden():
     thumbnails hash matches the restated integer stages."""
     import hashlib
 
-    from eioku_b200 import synth
+    import synthclip as synth
     from oracle import c_oracle as co
     g = load_golden("hash_c2_1080p_head.npz")
     w, h, seed = int(g["width"]), int(g["height"]), int(g["seed"])
