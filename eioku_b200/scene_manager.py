@@ -115,6 +115,7 @@ class SceneManager:
         self._last_pos: Optional[int] = None
         self._frame_rate = 30.0
         self._ctx: Optional[capi.EsdContext] = None
+        self._ctx_key = None
         self.scores: dict = {}
 
     # ---- PySceneDetect-compatible knobs
@@ -189,9 +190,11 @@ class SceneManager:
         return capi.EsdContext(cfg, self._device if device is None else device)
 
     # ---- detection
-    def detect_scenes(self, video=None, frames=None, fps: Optional[float] = None, collect_scores: bool = False) -> int:
+    def detect_scenes(self, video=None, frames=None, fps: Optional[float] = None, collect_scores: bool = False,
+                      reuse_context: bool = False) -> int:
         """Process every frame of `video` (TensorVideo / BatchVideo) or of `frames` ([N,H,W,3]).
-        Returns the number of frames processed."""
+        Returns the number of frames processed.  reuse_context: keep the device context of the previous call when the
+        geometry and detectors are unchanged (library batches: a reset instead of a rebuild per video)."""
         if video is None:
             if frames is None:
                 raise ValueError("detect_scenes needs video= or frames=")
@@ -203,9 +206,16 @@ class SceneManager:
         if self.stats_manager is not None:
             self.stats_manager.fps = self._frame_rate
         width, height = video.frame_size
-        self.close()
         nv12 = getattr(video, "pixel_format", "bgr24") == "nv12"
-        self._ctx = ctx = self.make_context(width, height, pixel_format="nv12" if nv12 else "bgr24")
+        key = (width, height, nv12, tuple(id(d) for d in self._detector_list), self._auto_downscale, self._downscale)
+        if reuse_context and self._ctx is not None and self._ctx_key == key:
+            ctx = self._ctx
+            ctx.reset()
+            self._cuts_by_detector = {}
+        else:
+            self.close()
+            self._ctx = ctx = self.make_context(width, height, pixel_format="nv12" if nv12 else "bgr24")
+            self._ctx_key = key
         start = int(getattr(video, "start_frame", 0))
         self._start_pos = start
         pos = start

@@ -177,9 +177,17 @@ def build_detectors(config: dict) -> list:
 
 
 def detect_scenes_frames(video, config: Optional[dict] = None, fps: Optional[float] = None, device: int = 0,
-                         batch_frames: int = 512) -> dict:
-    """Synchronous core: `video` is a TensorVideo/BatchVideo or an [N,H,W,3] uint8 array/tensor."""
+                         batch_frames: int = 512, devices: Optional[Sequence[int]] = None) -> dict:
+    """Synchronous core: `video` is a TensorVideo/BatchVideo or an [N,H,W,3] uint8 array/tensor.
+
+    devices: more than one GPU id fans ONE video out over the box by frame ranges with the window_width + 1 halo and a
+    single global decision pass (eioku_b200.multi.detect_sharded); `video` must then be a host array (or a TensorVideo
+    over one) so every device can pull its own range, or a list of per-device CUDA tensors (multi.plan_shards)."""
     config = config or {}
+    if devices is not None and len(devices) > 1:
+        return _detect_scenes_sharded(video, config, fps, list(devices), batch_frames)
+    if devices:
+        device = int(devices[0])
     if not hasattr(video, "read_batch"):
         video = TensorVideo(video, fps or float(config.get("fps", 30.0)))
     sm = SceneManager(device=device, batch_frames=batch_frames,
@@ -205,6 +213,30 @@ def detect_scenes_frames(video, config: Optional[dict] = None, fps: Optional[flo
         return out
     finally:
         sm.close()
+
+
+def _detect_scenes_sharded(video, config: dict, fps: Optional[float], devices: List[int], batch_frames: int) -> dict:
+    from . import multi
+
+    pixel_format, start = "bgr24", 0
+    if isinstance(video, TensorVideo):
+        fps = fps or video.frame_rate
+        pixel_format, start = video.pixel_format, video.start_frame
+        video = video.frames
+    if hasattr(video, "read_batch"):
+        raise ValueError("frame-range sharding needs random access to the frames: pass an array, a TensorVideo over a host "
+                         "array, or one CUDA tensor per device")
+    if not isinstance(video, (list, tuple)) and not isinstance(video, np.ndarray):
+        raise ValueError("frame-range sharding over several devices takes host frames (numpy) or per-device CUDA tensors")
+    rate = fps or float(config.get("fps", 30.0))
+    if "downscale" in config or config.get("auto_downscale") is False:
+        raise ValueError("devices=[...] supports the default auto-downscale only")
+    res = multi.detect_sharded(video, build_detectors(config), devices, fps=rate, batch_frames=max(batch_frames, 256),
+                               downscale_mode=str(config.get("downscale_mode", "float")),
+                               ingest_threads=int(config.get("ingest_threads", 0)), pixel_format=pixel_format, start_frame=start)
+    if res.n_frames == 0:
+        return {"scenes": []}
+    return {"scenes": scenes_to_dicts(res.scene_list(start_in_scene=True), rate)}
 
 
 def detect(video, detector, stats_file_path: Optional[str] = None, start_in_scene: bool = False, fps: Optional[float] = None,
@@ -349,15 +381,22 @@ def scene_artifact_envelopes(result: dict, video_id: str, run_id: Optional[str] 
 class ModelManager:
     """The scene-detection slice of the reference's ModelManager (model_manager.py:715)."""
 
-    def __init__(self, decoder: Optional[Callable[[str, dict], object]] = None, device: int = 0):
+    def __init__(self, decoder: Optional[Callable[[str, dict], object]] = None, device: int = 0,
+                 devices: Optional[Sequence[int]] = None):
+        """devices: GPUs one job may fan out over (frame-range sharding; the reference's worker runs one job at a time,
+        ml-service/src/main_worker.py:124, so a job is the unit that has to use the whole box)."""
         self._decoder = decoder or _default_decoder
         self._device = device
+        self._devices = list(devices) if devices else None
 
     async def detect_scenes(self, video_path: str, config: dict) -> dict:
         try:
             logger.info("Scene detection: %s", video_path)
             video = self._decoder(video_path, config or {})
-            result = detect_scenes_frames(video, config, device=self._device)
+            if self._devices and len(self._devices) > 1 and isinstance(getattr(video, "frames", None), np.ndarray):
+                result = detect_scenes_frames(video, config, devices=self._devices)
+            else:
+                result = detect_scenes_frames(video, config, device=self._devices[0] if self._devices else self._device)
             logger.info("Scene detection complete: %d scenes", len(result["scenes"]))
             return result
         except Exception as e:

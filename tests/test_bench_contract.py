@@ -33,6 +33,32 @@ def test_reference_arm_line():
     assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
+def test_reference_arm_honours_steps_and_warmup_and_never_loads_the_product():
+    """the reference arm must not clamp --steps/--warmup, must not load libesd.so (its frames come
+    from the CPU twin of the clip generator) and prints the same `config` object as the GPU arm."""
+    code = (
+        "import sys, runpy, io, json, contextlib\n"
+        "sys.argv = ['bench.py', '--impl', 'reference', '--steps', '4', '--warmup', '3', '--ref-sample', '6', '--ref-reps', '1']\n"
+        "buf = io.StringIO()\n"
+        "with contextlib.redirect_stdout(buf):\n"
+        "    try:\n"
+        "        runpy.run_path(%r, run_name='__main__')\n"
+        "    except SystemExit as e:\n"
+        "        assert not e.code, e.code\n"
+        "assert not any(m == 'eioku_b200' or m.startswith('eioku_b200.') for m in sys.modules), 'reference arm imported the product'\n"
+        "maps = open('/proc/self/maps').read()\n"
+        "assert 'libesd.so' not in maps and 'libesd_synth.so' not in maps, 'reference arm mapped a product library'\n"
+        "print(buf.getvalue())\n") % os.path.join(ROOT, "bench.py")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    d = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith("{")][0])
+    assert d["steps"] == 4 and d["warmup"] == 3
+    sys.path.insert(0, ROOT)
+    import bench
+
+    assert d["config"] == bench.bench_config(1, 2048)
+
+
 def test_reference_arm_other_ranks_exit_quietly():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
                          capture_output=True, text=True, timeout=120, env={**os.environ, "RANK": "1", "WORLD_SIZE": "2"})

@@ -28,3 +28,18 @@ def test_bench_line_contract():
     assert e["value"] > 0 and e["h2d_bytes_per_step"] in (128 * 1658880, 128 * 288 * 1536) and e["d2h_bytes_per_step"] > 0
     assert e["value"] < d["value"]
     assert d["value"] > 5e5
+    # sustained timing: >= 10 segments of exactly K steps, value from the median segment
+    t = d["timing"]
+    assert t["segments"] >= 10 and t["steps_per_segment"] == 5 and t["segment_ms_min"] <= t["segment_ms_median"] <= t["segment_ms_max"]
+    assert abs(d["ms_per_step"] - t["segment_ms_median"] / 5) < 1e-9
+    # parity gate against the committed cv2 golden of the clip that was timed
+    assert d["parity"]["checked"] is True and d["parity"]["bit_exact"] is True and d["parity"]["frames"] >= 512
+    assert set(e["modes"]) == {"gather", "dma_rows", "pageable_gather", "pageable_rows"} and e["mode"] in e["modes"]
+    assert e["value"] == max(m["value"] for m in e["modes"].values())
+    # both arms print the same config object and honour steps / warm-up
+    ref = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "5", "--warmup", "3",
+                          "--frames-per-step", "512", "--ref-sample", "6", "--ref-reps", "1"], capture_output=True, text=True, timeout=600)
+    assert ref.returncode == 0, ref.stderr[-2000:]
+    r = json.loads([ln for ln in ref.stdout.splitlines() if ln.startswith("{")][-1])
+    assert r["config"] == d["config"] and r["steps"] == d["steps"] and r["warmup"] == d["warmup"]
+    assert r["metric"] == d["metric"] and r["unit"] == d["unit"] and r["higher_is_better"] == d["higher_is_better"]
