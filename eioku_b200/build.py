@@ -36,7 +36,27 @@ def is_stale() -> bool:
     return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
 
 
+DECODE_LIB = os.path.join(HERE, "libesd_decode.so")
+DECODE_DEPS = ["esd_decode.cu", os.path.join("..", "..", "include", "esd_decode.h")]
+
+
+def build_decode(force: bool = False, verbose: bool = False) -> str:
+    """libesd_decode.so: Motion-JPEG (AVI) -> device BGR frames through nvJPEG (include/esd_decode.h)."""
+    stale = not os.path.exists(DECODE_LIB) or any(os.path.getmtime(os.path.join(CSRC, d)) > os.path.getmtime(DECODE_LIB) for d in DECODE_DEPS)
+    if not force and not stale:
+        return DECODE_LIB
+    cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
+           "-Xcompiler", "-fPIC,-fvisibility=hidden", "-o", DECODE_LIB, os.path.join(CSRC, "esd_decode.cu"), "-lnvjpeg"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed building libesd_decode.so")
+    return DECODE_LIB
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
+    build_decode(force, verbose)
     if not force and not is_stale():
         return LIB
     cmd = [_nvcc()] + NVCC_FLAGS + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]

@@ -65,6 +65,7 @@ class EsdGeometry(C.Structure):
         ("dst_width", C.c_int32), ("dst_height", C.c_int32),
         ("n_touched_rows", C.c_int32), ("row_bytes", C.c_int32),
         ("alg_bytes_per_frame", C.c_int64), ("compact_frame_bytes", C.c_int64),
+        ("lane_stride", C.c_int32), ("lane_stride_taps", C.c_int32),
     ]
 
 

@@ -176,6 +176,7 @@ struct esd_ctx {
     int pxt = 1;
     int rows_per_group = 0, n_groups = 0, stages = 0, rowbuf = 0, stage_bytes = 0, rows_per_stage = 1;
     int ctas_per_sm = 0;
+    int lane_stride = 1, lane_stride_taps = 1;  // consumer lane -> column stride (host_tables.h: choose_lane_stride), full rows / gathered taps
     size_t smem_bytes = 0;
     bool need_content = false, need_hist = false, need_edges = false, need_hash = false;
     int edge_ksize = 0, edge_words = 0;
@@ -604,6 +605,7 @@ int push_common(esd_ctx* c, const uint8_t* d_src, int64_t n, int64_t frame_strid
     p.has_prev = base > 0 ? 1 : 0;
     p.bins = c->cfg.hist_bins;
     p.want_bgr = (c->cfg.detectors & ESD_DET_THRESHOLD) ? 1 : 0;
+    p.lane_stride = layout == LAYOUT_TAPS ? c->lane_stride_taps : c->lane_stride;
     p.yrows = c->d_yrows;
     p.xtab = layout == LAYOUT_TAPS ? c->d_xtab_taps : c->d_xtab;
     p.sdiv = c->d_sdiv;
@@ -698,7 +700,7 @@ int push_common(esd_ctx* c, const uint8_t* d_src, int64_t n, int64_t frame_strid
         c->last_batch_base = base;
         c->last_batch_n = n;
     }
-    CU(c, klaunch(kg, ts, decide_kernel, dim3(5), dim3(256), 0, c->dparams, c->d_state, c->d_cuts, c->d_cv, c->d_av, c->d_ratio,
+    CU(c, klaunch(kg, ts, decide_kernel, dim3(5), dim3(kDecideThreads), 0, c->dparams, c->d_state, c->d_cuts, c->d_cv, c->d_av, c->d_ratio,
                   c->d_hdiff, c->d_avg, c->d_hdist, (long long)c->first_frame, (long long)base, (long long)(base + n), mailbox,
                   (long long)c->pf_ticket));
     if (!inline_tail) {
@@ -1070,6 +1072,14 @@ int esd_create(esd_ctx** out, const esd_config* cfg, int device) {
             }
             CUB(cudaMalloc(&c->d_xtab_taps, sizeof(uint2) * dw));
             CUB(cudaMemcpy(c->d_xtab_taps, xt2.data(), sizeof(uint2) * dw, cudaMemcpyHostToDevice));
+            // bank-aware lane -> column mapping (BGR24: three words per row and tap pair; NV12: two luma words -- its chroma
+            // words follow the same lattice at half the density)
+            std::vector<uint32_t> off(dw), off2(dw);
+            for (int x = 0; x < dw; ++x) { off[x] = xt[x].x & (c->nv12 ? 0x1fffu : 0xffffffffu); off2[x] = xt2[x].x & (c->nv12 ? 0x1fffu : 0xffffffffu); }
+            const int forced = cfg->reserved1;  // tuning / A-B switch: 1, 2, 4, 8 force a stride; 0 = choose
+            const bool ok = forced == 1 || forced == 2 || forced == 4 || forced == 8;
+            c->lane_stride = ok ? forced : choose_lane_stride(off, dw, c->nv12 ? 2 : 3);
+            c->lane_stride_taps = ok ? forced : choose_lane_stride(off2, dw, c->nv12 ? 2 : 3);
         }
     }
     {  // OpenCV RGB2HSV_b tables (A.3)
@@ -1217,6 +1227,8 @@ int esd_get_geometry(const esd_ctx* c, esd_geometry* g) {
     g->row_bytes = c->row_bytes;
     g->alg_bytes_per_frame = c->alg_frame_bytes;
     g->compact_frame_bytes = (int64_t)c->touched.size() * c->row_bytes;
+    g->lane_stride = c->lane_stride;
+    g->lane_stride_taps = c->lane_stride_taps;
     return ESD_OK;
 }
 
@@ -1719,16 +1731,15 @@ static int decide_on_device(esd_ctx* c, int32_t detector, int di, int64_t first_
     DecisionParams P = c->dparams;
     P.detectors = detector;
     P.cuts_stride = 0;  // one list: only `detector` runs
-    CU(c, cudaMemsetAsync(c->dec_d_state, 0, sizeof(DecisionState), st));
-    if (detector == ESD_DET_ADAPTIVE) {
-        if (!d_ratio) d_ratio = c->dec_d_ratio;
+    P.fresh_state = 1;  // starts from the zero state inside the kernel: no memset launch, `dec_d_state` is never touched
+    if (detector == ESD_DET_ADAPTIVE && d_ratio) {  // the caller wants the ratios: a pass of their own; otherwise computed inline
         adaptive_ratio_full_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_scores, d_ratio, (long long)n, P.adaptive_w,
                                                                                 P.adaptive_min_content_val);
         CU(c, cudaGetLastError());
         c->launches++;
     }
-    decide_kernel<<<5, 256, 0, st>>>(P, c->dec_d_state, h_cuts, d_scores, d_scores, d_ratio ? d_ratio : d_scores, d_scores, d_scores, d_scores,
-                                     first_frame_num, 0, n, mailbox, ticket);
+    decide_kernel<<<5, kDecideThreads, 0, st>>>(P, c->dec_d_state, h_cuts, d_scores, d_scores, d_ratio, d_scores, d_scores, d_scores,
+                                                first_frame_num, 0, n, mailbox, ticket);
     CU(c, cudaGetLastError());
     c->launches++;
     if (sync_stream) {
@@ -1791,7 +1802,7 @@ int esd_decide_device(esd_ctx* c, int32_t detector, int64_t first_frame_num, int
         rc = validate_device_span(c, reinterpret_cast<const uint8_t*>(d_adaptive_ratio_out), sizeof(double) * (size_t)n, "decide_device (ratios)");
         if (rc) return rc;
     }
-    rc = ensure_decide_scratch(c, detector == ESD_DET_ADAPTIVE && !d_adaptive_ratio_out ? n : 0, 0);
+    rc = ensure_decide_scratch(c, 0, 0);
     if (rc) return rc;
     return decide_on_device(c, detector, di, first_frame_num, n, d_scores, d_adaptive_ratio_out, (cudaStream_t)stream, cuts, cap, n_cuts, false);
 }

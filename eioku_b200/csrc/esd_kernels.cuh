@@ -52,6 +52,7 @@ struct FusedParams {
     int has_prev;
     int bins;
     int want_bgr;  // also accumulate sum(B+G+R) per frame (ThresholdDetector's average_rgb)
+    int lane_stride;  // 1, 2, 4 or 8: destination columns between neighbouring lanes of a consumer warp (bank-conflict-free taps)
     const YRow* yrows;
     const uint2* xtab;  // per destination column: {byte offset of tap 0, a0 | a1 << 16}
     const int* sdiv;
@@ -201,13 +202,13 @@ template <bool RESIZE, int PXT, bool CONTENT, bool HIST, bool SPECIAL, bool NV12
 __device__ __forceinline__ void score_row(const FusedParams& p, const uint8_t* __restrict__ row0, const uint8_t* __restrict__ row1,
                                           const uint8_t* __restrict__ uv0, const uint8_t* __restrict__ uv1, uint32_t misuv,
                                           uint32_t mis0, uint32_t mis1, uint32_t b0s, uint32_t b1s, int flags, int rloc,
-                                          int row, int frame, int tid, const uint32_t (&xoff)[PXT], const uint32_t (&xa01)[PXT],
+                                          int row, int frame, int tid, int col, const uint32_t (&xoff)[PXT], const uint32_t (&xa01)[PXT],
                                           const int* __restrict__ s_sdiv, const int* __restrict__ s_hdiv,
                                           uint32_t* __restrict__ s_prev, uint32_t* __restrict__ s_hist_cur,
                                           uint32_t& acc_hv, uint32_t& acc_s, uint32_t& acc_bgr) {
 #pragma unroll
     for (int k = 0; k < PXT; ++k) {
-        const int d = k * kConsumers + tid;
+        const int d = k * kConsumers + col;  // this thread's destination column (per-thread state stays indexed by tid)
         if (d < p.dst_w) {
             int b, g, r;
             if (RESIZE && NV12) {
@@ -502,10 +503,16 @@ __global__ void __launch_bounds__(kThreads) fused_score_kernel(const FusedParams
     // ==================================================================== consumer warps
     const int lane = tid & 31;
     const int warp = tid >> 5;
+    // Lane -> destination column.  Neighbouring columns' taps lie 3 * scale bytes apart in the staged row (22.5 B at 1080p),
+    // so 32 consecutive columns hit some shared-memory banks twice (48 % of the shared-load wavefronts were replays,
+    // profiles/r01_fused_full.md).  With lanes `lane_stride` columns apart (host-chosen so that the tap words of a warp fall
+    // into distinct banks: 8 columns = 180 B = 45 words at 1080p) the loads are conflict-free; the warps interleave.
+    const int ks = p.lane_stride;
+    const int col = ks * lane + (warp & (ks - 1)) + 32 * ks * (warp / ks);
     uint32_t xoff[PXT], xa01[PXT];
 #pragma unroll
     for (int k = 0; k < PXT; ++k) {
-        const int d = k * kConsumers + tid;
+        const int d = k * kConsumers + col;
         if (RESIZE) {
             const uint2 xe = (d < p.dst_w) ? p.xtab[d] : make_uint2(0u, 0u);
             xoff[k] = xe.x;
@@ -546,7 +553,7 @@ __global__ void __launch_bounds__(kThreads) fused_score_kernel(const FusedParams
                 const uint8_t* uvp1 = (mr.w & 0x10000u) ? uvp0 : uvp0 + p.rowbuf;
                 score_row<RESIZE, PXT, CONTENT, HIST, true, NV12, EXTRAS>(p, stage + q * row_slot, stage + q * row_slot + p.rowbuf, uvp0, uvp1,
                                                                   ALIGNED ? (mr.w & 0x10000u) : mr.w, mis0, mis1, mr.x, mr.y, flags, rloc0 + q,
-                                                                  row_first + q, m.x, tid, xoff, xa01, s_sdiv, s_hdiv, s_prev,
+                                                                  row_first + q, m.x, tid, col, xoff, xa01, s_sdiv, s_hdiv, s_prev,
                                                                   hist_cur, acc_hv, acc_s, acc_bgr);
             }
         } else {
@@ -563,7 +570,7 @@ __global__ void __launch_bounds__(kThreads) fused_score_kernel(const FusedParams
                 const uint8_t* uvp1 = (mr.w & 0x10000u) ? uvp0 : uvp0 + p.rowbuf;
                 score_row<RESIZE, PXT, CONTENT, HIST, false, NV12, EXTRAS>(p, stage + q * row_slot, stage + q * row_slot + p.rowbuf, uvp0, uvp1,
                                                                    ALIGNED ? (mr.w & 0x10000u) : mr.w, mis0, mis1, mr.x, mr.y, flags, rloc0 + q,
-                                                                   row_first + q, m.x, tid, xoff, xa01, s_sdiv, s_hdiv, s_prev,
+                                                                   row_first + q, m.x, tid, col, xoff, xa01, s_sdiv, s_hdiv, s_prev,
                                                                    hist_cur, acc_hv, acc_s, acc_bgr);
             }
         }
@@ -747,12 +754,8 @@ __global__ void hist_diff_kernel(const uint32_t* __restrict__ counts, int bins, 
     }
 }
 
-// AdaptiveDetector rolling-window ratio (A.6): one thread per target frame index t in [t_begin, t_end);
-// val/ratio are indexed from the first frame of the video (or of the array).
-__global__ void adaptive_ratio_kernel(const double* __restrict__ val, double* __restrict__ ratio, long long t_begin,
-                                      long long t_end, int w, double min_content_val) {
-    const long long t = t_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= t_end) return;
+// AdaptiveDetector rolling-window ratio (A.6) of target frame t: val[t - w .. t + w] must exist.
+__device__ __forceinline__ double adaptive_ratio_at(const double* __restrict__ val, long long t, int w, double min_content_val) {
     double sum = 0.0;
     bool first = true;
     for (int k = -w; k <= w; ++k) {
@@ -770,7 +773,15 @@ __global__ void adaptive_ratio_kernel(const double* __restrict__ val, double* __
     } else if (target >= min_content_val) {
         r = 255.0;
     }
-    ratio[t] = r;
+    return r;
+}
+
+// one thread per target frame index t in [t_begin, t_end); val/ratio are indexed from the first frame of the video
+__global__ void adaptive_ratio_kernel(const double* __restrict__ val, double* __restrict__ ratio, long long t_begin,
+                                      long long t_end, int w, double min_content_val) {
+    const long long t = t_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= t_end) return;
+    ratio[t] = adaptive_ratio_at(val, t, w, min_content_val);
 }
 
 // Stand-alone flavour for a whole score array (global decision pass of frame-range sharding): thread per frame index,
@@ -779,28 +790,7 @@ __global__ void adaptive_ratio_full_kernel(const double* __restrict__ val, doubl
                                            double min_content_val) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
-    if (t < w || t >= n - w) {
-        ratio[t] = __longlong_as_double(0x7ff8000000000000LL);
-        return;
-    }
-    double sum = 0.0;
-    bool first = true;
-    for (int k = -w; k <= w; ++k) {
-        if (k == 0) continue;
-        const double s = val[t + k];
-        sum = first ? s : __dadd_rn(sum, s);
-        first = false;
-    }
-    const double avg = __ddiv_rn(sum, __dmul_rn(2.0, (double)w));
-    const double target = val[t];
-    double r = 0.0;
-    if (!(fabs(avg) < 0.00001)) {
-        const double q = __ddiv_rn(target, avg);
-        r = (255.0 < q) ? 255.0 : q;
-    } else if (target >= min_content_val) {
-        r = 255.0;
-    }
-    ratio[t] = r;
+    ratio[t] = (t < w || t >= n - w) ? __longlong_as_double(0x7ff8000000000000LL) : adaptive_ratio_at(val, t, w, min_content_val);
 }
 
 // ----------------------------------------------------------------------------------- edges
@@ -1299,6 +1289,7 @@ struct DecisionParams {
     double hash_threshold;
     int hash_min_scene_len, pad;
     long long cuts_stride;  // cut list of detector d starts at cuts + d * cuts_stride (max_cuts; 0 = one shared list, stand-alone pass)
+    int fresh_state, pad5;  // stand-alone pass: start from the zero state and do not touch `st` (no memset launch needed)
 };
 
 struct CutSink {
@@ -1312,11 +1303,13 @@ struct CutSink {
     }
 };
 
-// grid = 5 blocks (content, adaptive, hist, threshold, hash); frames [i_begin, i_end) are indices from first_frame_num.
+constexpr int kDecideThreads = 1024;
+
+// grid = 5 blocks (content, adaptive, hist, threshold, hash) of kDecideThreads; frames [i_begin, i_end) are indices from first_frame_num.
 // The threshold tests run in parallel into a shared bitmask; one thread then walks the sequential
 // FlashFilter / min_scene_len state machine (A.5-A.7) with its state in registers, visiting only
 // frames that can change it (set bits, or every frame while a MERGE burst is open).
-__global__ void decide_kernel(DecisionParams P, DecisionState* __restrict__ st, long long* __restrict__ cuts,
+__global__ void __launch_bounds__(kDecideThreads) decide_kernel(DecisionParams P, DecisionState* __restrict__ st, long long* __restrict__ cuts,
                               const double* __restrict__ content_val, const double* __restrict__ adaptive_val,
                               const double* __restrict__ adaptive_ratio, const double* __restrict__ hist_diff,
                               const double* __restrict__ average_rgb, const double* __restrict__ hash_dist,
@@ -1332,7 +1325,9 @@ __global__ void decide_kernel(DecisionParams P, DecisionState* __restrict__ st, 
     CutSink sink{cuts + (size_t)det * P.cuts_stride, 0, P.max_cuts, 0};
     long long last = 0, merge_start = 0;
     int init = 0, merge_enabled = 0, merge_triggered = 0;
-    if (tid == 0) {
+    if (tid == 0 && P.fresh_state) {
+        if (!(det == 0 && !(P.content_min_scene_len > 0)) && det != 2) { init = 1; last = first_frame_num + i_begin; }
+    } else if (tid == 0) {
         sink.n = st->n_cuts[det];
         if (det == 0) {
             last = st->c_last_above; merge_start = st->c_merge_start; init = st->c_init;
@@ -1355,25 +1350,46 @@ __global__ void decide_kernel(DecisionParams P, DecisionState* __restrict__ st, 
                 : det == 2 ? P.hist_min_scene_len : det == 3 ? P.thresh_min_scene_len : P.hash_min_scene_len;
     // ThresholdDetector state (thread 0): merge_start doubles as last_fade.frame
     int t_processed = 0, t_fade_out = 0;
-    if (tid == 0 && det == 3) { t_processed = st->t_processed; t_fade_out = st->t_fade_out; merge_start = st->t_fade_frame; }
+    if (tid == 0 && det == 3 && !P.fresh_state) { t_processed = st->t_processed; t_fade_out = st->t_fade_out; merge_start = st->t_fade_frame; }
 
     for (long long c0 = i_begin; c0 < i_end; c0 += CH) {
         const long long c1 = (c0 + CH < i_end) ? c0 + CH : i_end;
-        for (int j = tid; j < CH; j += blockDim.x) {
-            const long long i = c0 + j;
-            bool bit = false;
-            if (i < c1) {
-                if (det == 0) bit = content_val[i] >= P.content_threshold;
-                else if (det == 1) {
-                    const long long t = i - P.adaptive_w;
-                    if (i >= 2LL * P.adaptive_w)
-                        bit = adaptive_ratio[t] >= P.adaptive_threshold && adaptive_val[t] >= P.adaptive_min_content_val;
-                } else if (det == 2) bit = hist_diff[i] <= P.hist_threshold;  // NaN (no previous frame) compares false
-                else if (det == 4) bit = hash_dist[i] >= P.hash_threshold;    // NaN (no previous frame) compares false
-                else bit = average_rgb[i] < P.thresh_threshold;                // "below the fade threshold"
+        // threshold tests of the chunk, eight frames per thread per pass with the loads issued before the first use
+        // (a 256-thread block walking 8192 frames one load at a time was latency-bound: ~30 us per chunk)
+        for (int j0 = 0; j0 < CH; j0 += 8 * (int)blockDim.x) {
+            bool bit[8];
+            if (det == 1) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const long long i = c0 + j0 + u * (int)blockDim.x + tid;
+                    bit[u] = false;
+                    if (i < c1 && i >= 2LL * P.adaptive_w) {
+                        const long long t = i - P.adaptive_w;
+                        const double r = adaptive_ratio ? adaptive_ratio[t] : adaptive_ratio_at(adaptive_val, t, P.adaptive_w, P.adaptive_min_content_val);
+                        bit[u] = r >= P.adaptive_threshold && adaptive_val[t] >= P.adaptive_min_content_val;
+                    }
+                }
+            } else {
+                const double* __restrict__ src = det == 0 ? content_val : det == 2 ? hist_diff : det == 4 ? hash_dist : average_rgb;
+                double v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const long long i = c0 + j0 + u * (int)blockDim.x + tid;
+                    v[u] = i < c1 ? src[i] : __longlong_as_double(0x7ff8000000000000LL);  // NaN: every test below is false
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    bit[u] = det == 0 ? v[u] >= P.content_threshold
+                           : det == 2 ? v[u] <= P.hist_threshold   // NaN (no previous frame) compares false
+                           : det == 4 ? v[u] >= P.hash_threshold   // NaN (no previous frame) compares false
+                                      : v[u] < P.thresh_threshold; // "below the fade threshold"
             }
-            const uint32_t word = __ballot_sync(0xffffffffu, bit);
-            if ((tid & 31) == 0) bits[j >> 5] = word;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int j = j0 + u * (int)blockDim.x + tid;
+                const uint32_t word = __ballot_sync(0xffffffffu, bit[u]);
+                if ((tid & 31) == 0 && j < CH) bits[j >> 5] = word;
+            }
         }
         __syncthreads();
         if (tid == 0) {
@@ -1485,8 +1501,10 @@ __global__ void decide_kernel(DecisionParams P, DecisionState* __restrict__ st, 
         __syncthreads();
     }
     if (tid == 0) {
-        st->n_cuts[det] = sink.n;
-        if (sink.overflow) st->overflow = 1;
+        if (!P.fresh_state) {
+            st->n_cuts[det] = sink.n;
+            if (sink.overflow) st->overflow = 1;
+        }
         // per-frame path: cut count and overflow flag straight into host-mapped pinned memory (no D2H copy), then this
         // detector's completion ticket -- the host polls the tickets instead of paying a stream synchronise
         if (mailbox) {
@@ -1495,6 +1513,7 @@ __global__ void decide_kernel(DecisionParams P, DecisionState* __restrict__ st, 
             __threadfence_system();
             *reinterpret_cast<volatile long long*>(mailbox + 8 + det) = ticket;
         }
+        if (P.fresh_state) return;
         if (det == 0) {
             st->c_last_above = last; st->c_merge_start = merge_start; st->c_init = init;
             st->c_merge_enabled = merge_enabled; st->c_merge_triggered = merge_triggered;

@@ -58,6 +58,40 @@ inline void area_axis_table(int ssize, int dsize, std::vector<int>& begin, std::
     }
 }
 
+// Shared-memory wavefronts one staged-row read costs the eight consumer warps when lanes are `ks` destination columns apart
+// (column of (warp, lane) = ks * lane + warp % ks + 32 * ks * (warp / ks)): every thread reads `n_words` consecutive 32-bit
+// words starting at the word that holds byte `byte_off[column]`; a warp-wide load takes as many passes as the busiest of
+// the 32 banks has DISTINCT words.  Columns >= dst_w (threads without a pixel) do not load.
+inline int64_t tap_load_wavefronts(const std::vector<uint32_t>& byte_off, int dst_w, int n_words, int ks, int warps = 8) {
+    int64_t total = 0;
+    for (int w = 0; w < warps; ++w)
+        for (int j = 0; j < n_words; ++j) {
+            std::vector<uint32_t> seen[32];
+            int worst = 0;
+            for (int l = 0; l < 32; ++l) {
+                const int col = ks * l + (w & (ks - 1)) + 32 * ks * (w / ks);
+                if (col >= dst_w) continue;
+                const uint32_t word = (byte_off[col] >> 2) + (uint32_t)j;
+                auto& v = seen[word & 31u];
+                if (std::find(v.begin(), v.end(), word) == v.end()) v.push_back(word);
+                worst = std::max(worst, (int)v.size());
+            }
+            total += worst;
+        }
+    return total;
+}
+
+// The lane stride (1, 2, 4, 8) with the fewest wavefronts; ties go to the smaller stride (better-coalesced side outputs).
+inline int choose_lane_stride(const std::vector<uint32_t>& byte_off, int dst_w, int n_words) {
+    int best = 1;
+    int64_t best_cost = tap_load_wavefronts(byte_off, dst_w, n_words, 1);
+    for (int ks = 2; ks <= 8; ks *= 2) {
+        const int64_t c = tap_load_wavefronts(byte_off, dst_w, n_words, ks);
+        if (c < best_cost) { best_cost = c; best = ks; }
+    }
+    return best;
+}
+
 inline int64_t gcd64(int64_t a, int64_t b) { while (b) { int64_t t = a % b; a = b; b = t; } return a; }
 
 // Work decomposition of one fused launch over n_groups row groups x n frames.  A unit is (row group, frame range); units

@@ -163,12 +163,15 @@ def decide_merged(ctx: capi.EsdContext, flags: Sequence[int], merged, n_frames: 
 def detect_sharded(frames, detectors: Sequence[SceneDetector], devices: Sequence[int], fps: float = 30.0,
                    batch_frames: int = 1024, downscale_mode: str = "float", tuning: Optional[dict] = None,
                    collect_scores: bool = False, ingest_threads: int = 0, pixel_format: str = "bgr24",
-                   start_frame: int = 0) -> ShardedResult:
+                   start_frame: int = 0, n_frames: Optional[int] = None, frame_size: Optional[Tuple[int, int]] = None) -> ShardedResult:
     """Frame-range sharding of ONE video over `devices` (one process, one esd_ctx + stream per device).
 
     `frames`: a host array [N,H,W,3] uint8 (numpy, pinned or pageable -- each device's ingest ring pulls its own range),
     or a list with one entry per device holding that device's load range [load_start, load_end) as a CUDA tensor on that
-    device (frames born on the devices, e.g. by per-GPU decoders); use ``plan_shards`` to get the ranges.
+    device (frames born on the devices; use ``plan_shards`` to get the ranges), or a callable ``(shard, device) -> source``
+    returning a video source (``read_batch``) for the shard's load range on that device -- e.g. one GPU decoder per device
+    (``decode.MjpegVideo(path, device, first_frame=shard.load_start, end_frame=shard.load_end)``); the callable flavour
+    needs `n_frames` and `frame_size` (width, height).
     """
     import torch
 
@@ -178,7 +181,12 @@ def detect_sharded(frames, detectors: Sequence[SceneDetector], devices: Sequence
     _check_shardable(detectors)
     w = halo_width(detectors)
     pre_sharded = isinstance(frames, (list, tuple))
-    if pre_sharded:
+    per_device_source = callable(frames)
+    if per_device_source:
+        if n_frames is None or frame_size is None:
+            raise ValueError("a per-device source factory needs n_frames= and frame_size=")
+        n_total = int(n_frames)
+    elif pre_sharded:
         if len(frames) != len(devices):
             raise ValueError("pre-sharded frames: one tensor per device")
         n_total = None
@@ -191,7 +199,9 @@ def detect_sharded(frames, detectors: Sequence[SceneDetector], devices: Sequence
     if n_total == 0:
         return ShardedResult(0, start_frame, {type(d).__name__: [] for d in detectors}, shards=shards)
     sample = frames[0] if pre_sharded else frames
-    if pixel_format == "nv12":
+    if per_device_source:
+        width, height = int(frame_size[0]), int(frame_size[1])
+    elif pixel_format == "nv12":
         width, height = int(sample.shape[2]), int(sample.shape[1]) * 2 // 3
     else:
         width, height = int(sample.shape[2]), int(sample.shape[1])
@@ -211,7 +221,26 @@ def detect_sharded(frames, detectors: Sequence[SceneDetector], devices: Sequence
             sc = ShardScorer(detectors, width, height, devices[g], sh, batch_frames, downscale_mode, tuning, pixel_format,
                              ingest_threads)
             scorers[g] = sc
-            if pre_sharded:
+            if per_device_source:
+                import torch as _torch
+
+                with _torch.cuda.device(devices[g]), _torch.cuda.stream(sc.stream):
+                    src = frames(sh, devices[g])
+                    try:
+                        while True:
+                            b = src.read_batch(batch_frames)
+                            if b is None or b.shape[0] == 0:
+                                break
+                            if isinstance(b, np.ndarray):
+                                sc.push_host(b)
+                            else:
+                                sc.push_device(b)
+                        # the source's buffers must outlive the scoring that reads them
+                        sc.stream.synchronize()
+                    finally:
+                        if hasattr(src, "close"):
+                            src.close()
+            elif pre_sharded:
                 t = frames[g]
                 if int(t.shape[0]) != sh.load_end - sh.load_start:
                     raise ValueError(f"device {devices[g]}: tensor holds {int(t.shape[0])} frames, its load range has {sh.load_end - sh.load_start}")

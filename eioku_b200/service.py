@@ -239,6 +239,22 @@ def _detect_scenes_sharded(video, config: dict, fps: Optional[float], devices: L
     return {"scenes": scenes_to_dicts(res.scene_list(start_in_scene=True), rate)}
 
 
+def _detect_scenes_mjpeg_sharded(video_path: str, probe, config: dict, devices: List[int]) -> dict:
+    """One Motion-JPEG file over several GPUs: MJPEG is intra-only, so every device decodes its own frame range (+ halo)."""
+    from . import decode, multi
+
+    n, size, rate = probe.n_frames, probe.frame_size, probe.frame_rate
+    probe.close()
+    batch = int(config.get("decode_batch", 64))
+    res = multi.detect_sharded(
+        lambda sh, dev: decode.MjpegVideo(video_path, device=dev, batch_frames=batch, first_frame=sh.load_start, end_frame=sh.load_end),
+        build_detectors(config), devices, fps=rate, batch_frames=batch, downscale_mode=str(config.get("downscale_mode", "float")),
+        n_frames=n, frame_size=size)
+    if res.n_frames == 0:
+        return {"scenes": []}
+    return {"scenes": scenes_to_dicts(res.scene_list(start_in_scene=True), rate)}
+
+
 def detect(video, detector, stats_file_path: Optional[str] = None, start_in_scene: bool = False, fps: Optional[float] = None,
            device: int = 0) -> List[Tuple[int, int]]:
     """Counterpart of ``scenedetect.detect(video_path, detector, ...)``: run one detector over a video and return the
@@ -263,11 +279,17 @@ def detect(video, detector, stats_file_path: Optional[str] = None, start_in_scen
 
 
 def _default_decoder(video_path: str, config: dict):
-    """Frames for a path.  Decode is out of scope (north_star); this handles .npy frame dumps and,
-    when OpenCV is importable, container files via cv2.VideoCapture in host batches."""
+    """Frames for a path: .npy frame dumps; Motion-JPEG AVI files decoded ON THE GPU (eioku_b200.decode, SURVEY.md 8f N1 --
+    the decoded frames never visit host memory); any other container through cv2.VideoCapture in host batches, the
+    reference's own decode loop (model_manager.py:237-263), feeding the ingest ring."""
     if video_path.endswith(".npy"):
         arr = np.load(video_path, mmap_mode="r")
         return TensorVideo(arr, float(config.get("fps", 30.0)))
+    if config.get("gpu_decode", True):
+        from . import decode
+
+        if decode.is_mjpeg_avi(video_path):
+            return decode.MjpegVideo(video_path, device=int(config.get("device", 0)), batch_frames=int(config.get("decode_batch", 64)))
     try:
         import cv2  # noqa: WPS433 (decode helper only; never used for scoring)
     except Exception as e:  # pragma: no cover
@@ -392,8 +414,11 @@ class ModelManager:
     async def detect_scenes(self, video_path: str, config: dict) -> dict:
         try:
             logger.info("Scene detection: %s", video_path)
-            video = self._decoder(video_path, config or {})
-            if self._devices and len(self._devices) > 1 and isinstance(getattr(video, "frames", None), np.ndarray):
+            dev0 = self._devices[0] if self._devices else self._device
+            video = self._decoder(video_path, {**(config or {}), "device": dev0})
+            if self._devices and len(self._devices) > 1 and type(video).__name__ == "MjpegVideo":
+                result = _detect_scenes_mjpeg_sharded(video_path, video, config or {}, self._devices)
+            elif self._devices and len(self._devices) > 1 and isinstance(getattr(video, "frames", None), np.ndarray):
                 result = detect_scenes_frames(video, config, devices=self._devices)
             else:
                 result = detect_scenes_frames(video, config, device=self._devices[0] if self._devices else self._device)

@@ -108,7 +108,7 @@ typedef struct esd_config {
     int32_t split_mode;        /* ESD_SPLIT_* */
     int32_t ctas_per_sm;
     int32_t rows_per_stage;    /* destination rows staged per pipeline slot (1..4) */
-    int32_t reserved1;
+    int32_t reserved1;         /* tuning: consumer lane stride in destination columns (1, 2, 4, 8); 0 = bank-conflict-free choice */
     int64_t max_cuts;          /* per-detector cut capacity (default 65536) */
     int64_t initial_capacity;  /* frames of per-frame score storage to pre-allocate (grows by doubling) */
 
@@ -127,6 +127,8 @@ typedef struct esd_geometry {
     int32_t row_bytes;           /* bytes per source row: src_width * 3 (BGR24) or src_width (NV12) */
     int64_t alg_bytes_per_frame; /* algorithmic HBM bytes per frame: 32-byte sectors of the touched rows that hold a tap */
     int64_t compact_frame_bytes; /* n_touched_rows * row_bytes: one frame in the compact layout = bytes the kernel fetches */
+    int32_t lane_stride;         /* destination columns between neighbouring consumer lanes (bank-conflict-free tap loads) */
+    int32_t lane_stride_taps;    /* the same for the gathered-taps ingest layout */
 } esd_geometry;
 
 ESD_API int esd_abi_version(void);

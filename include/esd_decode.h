@@ -1,0 +1,82 @@
+/* esd_decode.h -- C ABI of libesd_decode.so: compressed video -> device-resident BGR frames, for libesd.so to score.
+ *
+ * SURVEY.md section 8f row N1 (decode -> device).  Replaces the decode loop every frame-based task of the reference runs
+ * on the CPU -- `cap = cv2.VideoCapture(video_path)` ... `ret, frame = cap.read()`
+ * (/root/reference/ml-service/src/services/model_manager.py:237-263) -- and, for the scene task as shipped, the
+ * `ffmpeg -i <path>` child process that decodes every frame on the host (model_manager.py:736-755).  Here the host only
+ * walks the container and hands the COMPRESSED pictures to the GPU: decoded frames are born in HBM and never visit host
+ * memory, which is what bounds the host-frame ingest path (esd_ingest_*: PCIe + host DRAM).
+ *
+ * What this image offers: NVDEC is closed to the container (libnvcuvid loads, but cuvidGetDecoderCaps answers
+ * CUDA_ERROR_NO_DEVICE for every codec because NVIDIA_DRIVER_CAPABILITIES is "compute,utility" -- profiles/r02_nvdec_caps.log),
+ * so the decoder is nvJPEG (CUDA toolkit, header + library present) on Motion-JPEG in an AVI (RIFF) container: the hardware
+ * JPEG engine when the library grants it, else the GPU-Huffman hybrid, else the default backend.  MJPEG is intra-only, so any
+ * frame range can be decoded independently -- the frame-range sharding of eioku_b200.multi applies unchanged.
+ *
+ * Output: dense uint8 BGR24 frames [n][height][width * 3] in a library-owned device buffer (double-buffered), exactly the
+ * layout esd_push_frames takes.  nvJPEG's colour conversion is JFIF full-range YCbCr -> BGR like libjpeg's; decoders differ
+ * in IDCT / chroma upsampling rounding, so parity is defined on the DECODED surface: download it, run the oracle on it,
+ * demand bit-exact sums / scores / cuts (tests/test_gpu_decode.py).
+ *
+ * Conventions as in esd.h: plain C, POD only, 0 or a negative status, never throws; not thread-safe per handle; several
+ * handles (one per thread / GPU) are independent.
+ */
+#ifndef ESD_DECODE_H
+#define ESD_DECODE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define ESD_DEC_API __attribute__((visibility("default")))
+#else
+#define ESD_DEC_API
+#endif
+
+#define ESD_DECODE_ABI_VERSION 1
+
+typedef struct esd_mjpeg esd_mjpeg;
+
+enum { ESD_DEC_OK = 0, ESD_DEC_ERR_INVALID = -1, ESD_DEC_ERR_CUDA = -2, ESD_DEC_ERR_IO = -3, ESD_DEC_ERR_FORMAT = -4,
+       ESD_DEC_ERR_NVJPEG = -5, ESD_DEC_ERR_UNSUPPORTED = -6 };
+/* nvJPEG back end: AUTO tries HARDWARE, then GPU_HYBRID, then DEFAULT */
+enum { ESD_JPEG_AUTO = 0, ESD_JPEG_DEFAULT = 1, ESD_JPEG_GPU_HYBRID = 2, ESD_JPEG_HARDWARE = 3 };
+
+typedef struct esd_mjpeg_info {
+    int32_t width, height;
+    int32_t fps_num, fps_den;   /* AVI stream header dwRate / dwScale */
+    int64_t n_frames;           /* pictures in the container */
+    int64_t compressed_bytes;   /* sum of their sizes */
+    int32_t backend;            /* ESD_JPEG_* actually in use */
+    int32_t hw_engines;         /* hardware JPEG engines the library reports (0 unless backend == HARDWARE) */
+    int32_t batch_frames;
+    int32_t reserved;
+} esd_mjpeg_info;
+
+ESD_DEC_API int esd_decode_abi_version(void);
+/* detail of the last failure on this handle (or of the last esd_mjpeg_open failure when h == NULL) */
+ESD_DEC_API const char* esd_mjpeg_last_error(const esd_mjpeg* h);
+
+/* Replaces: cv2.VideoCapture(video_path) + the CAP_PROP_* queries (model_manager.py:237-246).
+ * Opens an AVI file whose video stream is Motion-JPEG (fourcc MJPG / mjpg / AVI1 ...), indexes its pictures and creates the
+ * nvJPEG decoder on `device`.  batch_frames: pictures decoded per esd_mjpeg_read (device buffer = 2 * batch * W * H * 3 bytes). */
+ESD_DEC_API int esd_mjpeg_open(esd_mjpeg** out, const char* avi_path, int device, int32_t batch_frames, int32_t backend);
+ESD_DEC_API int esd_mjpeg_get_info(const esd_mjpeg* h, esd_mjpeg_info* out);
+/* next picture to decode (0-based); MJPEG is intra-only, so any position is a valid entry point */
+ESD_DEC_API int esd_mjpeg_seek(esd_mjpeg* h, int64_t frame);
+/* Replaces: `ret, frame = cap.read()` x batch_frames (model_manager.py:248-263).
+ * Decodes up to min(batch_frames, max_frames) pictures starting at the current position into the library's device buffer as dense
+ * BGR24 [n][height][width * 3]; *d_bgr / *n_frames describe them (n_frames == 0 at the end of the stream).  The decode is
+ * enqueued on `stream` (cudaStream_t of the handle's device): work the caller enqueues on `stream` afterwards (e.g.
+ * esd_push_frames) is ordered behind it, and the buffer stays valid until the second next esd_mjpeg_read -- by then the
+ * consumer's work on `stream` is known to have been enqueued, and the library orders its writes behind it. */
+ESD_DEC_API int esd_mjpeg_read(esd_mjpeg* h, int64_t max_frames, void* stream, uint8_t** d_bgr, int64_t* n_frames);
+ESD_DEC_API void esd_mjpeg_close(esd_mjpeg* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ESD_DECODE_H */

@@ -34,4 +34,10 @@ int shim_unit_plan(int n_groups, long long n, long long max_ctas, int mode, int*
     memcpy(begin, b.data(), sizeof(int) * b.size());
     return grid;
 }
+// wavefronts of one staged-row read for lane stride ks; *best receives choose_lane_stride's pick
+long long shim_tap_wavefronts(const unsigned* byte_off, int dst_w, int n_words, int ks, int* best) {
+    std::vector<uint32_t> off(byte_off, byte_off + dst_w);
+    if (best) *best = esd::choose_lane_stride(off, dst_w, n_words);
+    return esd::tap_load_wavefronts(off, dst_w, n_words, ks);
+}
 }

@@ -13,7 +13,8 @@ pytestmark = pytest.mark.gpu
 
 def test_bench_line_contract():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "5", "--warmup", "3", "--no-cpu",
-                          "--frames-per-step", "512", "--e2e-frames", "128"], capture_output=True, text=True, timeout=600)
+                          "--frames-per-step", "512", "--e2e-frames", "128", "--compressed-frames", "48", "--compressed-passes", "1", "--decode-sessions", "2"],
+                         capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stderr[-2000:]
     d = json.loads([ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1])
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
@@ -36,6 +37,9 @@ def test_bench_line_contract():
     assert d["parity"]["checked"] is True and d["parity"]["bit_exact"] is True and d["parity"]["frames"] >= 512
     assert set(e["modes"]) == {"gather", "dma_rows", "pageable_gather", "pageable_rows"} and e["mode"] in e["modes"]
     assert e["value"] == max(m["value"] for m in e["modes"].values())
+    c = d["e2e_compressed"]
+    assert c["value"] > 0 and c["bit_exact_on_decoded_surface"] is True and c["sessions_per_gpu"] == 2 and c["file_frames"] == 48
+    assert 0 < c["h2d_bytes_per_frame"] < 1920 * 1080 * 3 / 4
     # both arms print the same config object and honour steps / warm-up
     ref = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "5", "--warmup", "3",
                           "--frames-per-step", "512", "--ref-sample", "6", "--ref-reps", "1"], capture_output=True, text=True, timeout=600)

@@ -1,0 +1,173 @@
+"""GPU: compressed video -> device frames -> scores.  Parity is defined on the DECODED surface: what the
+GPU decoder produced is downloaded, the oracle (PySceneDetect logic on the closed forms / cv2) runs on exactly those frames,
+and sums / scores / cuts must be bit-exact.  That the decoder decodes the right pictures is checked separately against
+cv2.VideoCapture's decode of the same file (PSNR: two JPEG decoders differ in IDCT and chroma-upsampling rounding)."""
+import asyncio
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+cv2 = pytest.importorskip("cv2")
+
+import synthclip as synth  # noqa: E402
+from eioku_b200 import decode, service  # noqa: E402
+from eioku_b200.detectors import AdaptiveDetector, ContentDetector, HistogramDetector  # noqa: E402
+from eioku_b200.scene_manager import SceneManager  # noqa: E402
+from oracle import c_oracle as co  # noqa: E402
+from oracle import psd_cv2 as P  # noqa: E402
+
+
+def _write_avi(path, frames, fourcc="MJPG", fps=25.0):
+    h, w = frames.shape[1:3]
+    wr = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*fourcc), fps, (w, h))
+    assert wr.isOpened()
+    for f in frames:
+        wr.write(f)
+    wr.release()
+
+
+@pytest.fixture(scope="module")
+def mjpeg_clip(tmp_path_factory):
+    d = tmp_path_factory.mktemp("mjpeg")
+    n, w, h, seed = 150, 640, 360, 77
+    sch = synth.build_schedule(seed, n, min_len=20, max_len=50)
+    frames = co.synth_frames(seed, w, h, sch.descs)
+    path = str(d / "clip.avi")
+    _write_avi(path, frames)
+    return path, frames
+
+
+def _decode_all(path, **kw):
+    with decode.MjpegVideo(path, **kw) as v:
+        out = []
+        while True:
+            b = v.read_batch(0)
+            if b is None:
+                break
+            out.append(b.cpu().numpy())  # copies: the tensor aliases the decoder's ring
+        return np.concatenate(out), v.frame_rate, v.backend, v.n_frames
+
+
+def test_decoder_decodes_the_right_pictures(mjpeg_clip):
+    path, src = mjpeg_clip
+    got, fps, backend, n = _decode_all(path, batch_frames=32)
+    assert got.shape == src.shape and n == src.shape[0] and fps == 25.0 and backend in ("hardware", "gpu_hybrid", "default")
+    cap = cv2.VideoCapture(path)
+    ref = []
+    while True:
+        ok, f = cap.read()
+        if not ok:
+            break
+        ref.append(f)
+    ref = np.stack(ref)
+    assert ref.shape == got.shape
+    mse = np.mean((got.astype(np.float64) - ref.astype(np.float64)) ** 2, axis=(1, 2, 3))
+    psnr = 10 * np.log10(255.0 ** 2 / np.maximum(mse, 1e-9))
+    assert psnr.min() > 30.0, psnr.min()  # same pictures (garbage would sit below 15 dB); decoder rounding / chroma upsampling apart
+    print(f"nvJPEG backend {backend}: PSNR vs cv2/ffmpeg decode min {psnr.min():.1f} dB")
+
+
+class _Tee:
+    """Video source wrapper that keeps a device-side copy of every batch the SceneManager scores: the decoded surface."""
+
+    def __init__(self, src):
+        self.src, self.kept = src, []
+        self.frame_size, self.frame_rate, self.start_frame, self.pixel_format = src.frame_size, src.frame_rate, src.start_frame, src.pixel_format
+
+    def read_batch(self, n):
+        b = self.src.read_batch(n)
+        if b is not None:
+            self.kept.append(b.clone())  # same stream as the decode and the scoring
+        return b
+
+    def frames(self):
+        return torch.cat(self.kept).cpu().numpy()
+
+
+def test_parity_on_the_decoded_surface(mjpeg_clip):
+    """The frames the scoring kernels read are downloaded (a device-side copy made between decode and scoring) and the
+    oracle runs on exactly those: integer sums, float64 scores, histograms' differences and cut lists bit-exact."""
+    path, _ = mjpeg_clip
+    sm = SceneManager(batch_frames=64)
+    dets = [ContentDetector(min_scene_len=10), AdaptiveDetector(window_width=2, min_scene_len=10), HistogramDetector(min_scene_len=10)]
+    for d in dets:
+        sm.add_detector(d)
+    with decode.MjpegVideo(path, batch_frames=48) as v:
+        tee = _Tee(v)
+        n = sm.detect_scenes(tee, collect_scores=True)
+        decoded = tee.frames()
+    assert n == v.n_frames == decoded.shape[0]
+    want_sums, _, _ = co.score_frames(decoded, 256, 144)
+    assert np.array_equal(sm.scores["sums3"].astype(np.int64), want_sums)
+    oc = P.ContentDetector(min_scene_len=10, backend="closed_form")
+    oa = P.AdaptiveDetector(window_width=2, min_scene_len=10, backend="closed_form")
+    oh = P.HistogramDetector(min_scene_len=10, backend="closed_form")
+    for o, d in ((oc, dets[0]), (oa, dets[1]), (oh, dets[2])):
+        cuts, _ = P.detect(decoded, [o], backend="closed_form")
+        assert sm.cuts_of(d) == cuts, type(d).__name__
+    assert np.array_equal(np.array(oc.scores).view(np.uint64), sm.scores["content_val"].view(np.uint64))
+    assert np.array_equal(np.array(oh.diffs)[1:].view(np.uint64), sm.scores["hist_diff"][1:].view(np.uint64))
+    assert len(sm.cuts_of(dets[0])) >= 2
+    sm.close()
+    # how repeatable is the decoder itself?  (reported, not asserted: nvJPEG does not promise bit-identical output across
+    # batch compositions; parity above never depends on it)
+    again, *_ = _decode_all(path, batch_frames=48)
+    other, *_ = _decode_all(path, batch_frames=64)
+    print(f"nvJPEG repeatability: same batching differs in {int((again != decoded).sum())} bytes, "
+          f"other batching in {int((other != decoded).sum())} of {decoded.size} bytes (max |delta| {int(np.abs(other.astype(int) - decoded.astype(int)).max())})")
+
+
+def test_ranges_are_independent(mjpeg_clip):
+    path, _ = mjpeg_clip
+    full, *_ = _decode_all(path, batch_frames=64)
+    part, *_ = _decode_all(path, batch_frames=7, first_frame=50, end_frame=93)
+    close = lambda a, b: a.shape == b.shape and int(np.abs(a.astype(int) - b.astype(int)).max()) <= 2  # noqa: E731 (decoder rounding)
+    assert close(part, full[50:93])
+    with decode.MjpegVideo(path, batch_frames=16) as v:
+        v.seek(140)
+        b = v.read_batch(64)
+        assert b.shape[0] == 10 and close(b.cpu().numpy(), full[140:150])
+        assert v.read_batch(64) is None
+        with pytest.raises(decode.DecodeError):
+            v.seek(10 ** 6)
+
+
+def test_task_surface_decodes_on_the_gpu_and_shards_by_frame_range(mjpeg_clip):
+    path, _ = mjpeg_clip
+    decoded, *_ = _decode_all(path)
+    cfg = {"detector": "content+adaptive", "min_scene_len": 10, "window_width": 2}
+    # a separate decode may differ from the scored one by decoder rounding (+-1 in a few bytes), far from any threshold here
+    want = P.detect_scenes_dicts(decoded, [P.ContentDetector(min_scene_len=10, backend="closed_form"),
+                                           P.AdaptiveDetector(window_width=2, min_scene_len=10, backend="closed_form")], 25.0, backend="closed_form")
+    got = asyncio.run(service.ModelManager().detect_scenes(path, cfg))
+    assert got == want and len(got["scenes"]) >= 3
+    k = torch.cuda.device_count()
+    many = asyncio.run(service.ModelManager(devices=[g % k for g in range(3)]).detect_scenes(path, cfg))
+    assert many == want
+    # gpu_decode=False keeps the reference's host decode loop (cv2.VideoCapture) -- other pixels, same schema
+    host = asyncio.run(service.ModelManager().detect_scenes(path, {**cfg, "gpu_decode": False}))
+    assert [s["scene_index"] for s in host["scenes"]] == list(range(len(host["scenes"])))
+
+
+def test_unsupported_and_broken_files(tmp_path, mjpeg_clip):
+    _, frames = mjpeg_clip
+    other = str(tmp_path / "mpeg4.avi")
+    _write_avi(other, frames[:20], fourcc="mp4v")
+    assert not decode.is_mjpeg_avi(other)
+    with pytest.raises(decode.DecodeError) as e:
+        decode.MjpegVideo(other)
+    assert e.value.status == -6 and "not Motion-JPEG" in str(e.value)
+    got = asyncio.run(service.ModelManager().detect_scenes(other, {}))  # falls back to the host decoder
+    assert len(got["scenes"]) >= 1
+    junk = str(tmp_path / "junk.avi")
+    open(junk, "wb").write(b"RIFF" + b"\x00" * 64)
+    with pytest.raises(decode.DecodeError):
+        decode.MjpegVideo(junk)
+    with pytest.raises(decode.DecodeError):
+        decode.MjpegVideo(str(tmp_path / "missing.avi"))
+    with pytest.raises(decode.DecodeError):
+        decode.MjpegVideo(mjpeg_clip[0], batch_frames=0)

@@ -399,3 +399,60 @@ def test_scene_artifact_payloads_from_a_finished_manager():
     ]
     sm._start_pos = None
     assert scene_artifact_payloads(sm) == []
+
+
+# ------------------------------------------------------------------------------------------- round 2: decode library boundary
+def test_decode_library_exports_every_declared_symbol(lib_built):
+    from eioku_b200 import decode
+
+    hdr = open(os.path.join(ROOT, "include", "esd_decode.h")).read()
+    declared = sorted(set(re.findall(r"ESD_DEC_API\s+[\w\s\*]+?\b(esd_\w+)\s*\(", hdr)))
+    assert sorted(decode.EXPORTED_SYMBOLS) == declared and len(declared) == 7
+    L = decode.load_library()
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.esd_decode_abi_version() == decode.ESD_DECODE_ABI_VERSION == int(re.search(r"#define ESD_DECODE_ABI_VERSION (\d+)", hdr).group(1))
+    out = subprocess.run(["nm", "-D", "--defined-only", decode.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (\w+)", out))
+    assert set(declared) <= exported and not [s for s in exported if not s.startswith("esd_")]
+    src = "#include <stddef.h>\n#include <stdio.h>\n#include \"esd_decode.h\"\nint main(void){printf(\"%zu %zu %zu\\n\", sizeof(esd_mjpeg_info), offsetof(esd_mjpeg_info, n_frames), offsetof(esd_mjpeg_info, backend));return 0;}\n"
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "l.c"), "w").write(src)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "l.c"), "-o", os.path.join(d, "l")])
+        got = list(map(int, subprocess.check_output([os.path.join(d, "l")]).split()))
+    assert got == [ctypes.sizeof(decode.MjpegInfo), decode.MjpegInfo.n_frames.offset, decode.MjpegInfo.backend.offset]
+
+
+def test_mjpeg_sniffing_and_no_cpu_fallback(tmp_path):
+    cv2 = pytest.importorskip("cv2")
+    from eioku_b200 import decode
+
+    frames = np.random.default_rng(0).integers(0, 255, (4, 48, 64, 3), dtype=np.uint8)
+    for fourcc, want in (("MJPG", True), ("mp4v", False)):
+        p = str(tmp_path / f"{fourcc}.avi")
+        w = cv2.VideoWriter(p, cv2.VideoWriter_fourcc(*fourcc), 30.0, (64, 48))
+        for f in frames:
+            w.write(f)
+        w.release()
+        assert decode.is_mjpeg_avi(p) is want
+    assert not decode.is_mjpeg_avi(str(tmp_path / "nope.avi"))
+    if not _has_gpu():
+        with pytest.raises(decode.DecodeError) as e:
+            decode.MjpegVideo(str(tmp_path / "MJPG.avi"))
+        assert "no CPU fallback" in str(e.value)
+
+
+def test_all_gather_scores_single_rank_and_schema_packing():
+    import torch
+
+    local = torch.arange(12, dtype=torch.float64).reshape(2, 6)
+    assert torch.equal(sharding.all_gather_scores(local, [4]), local[:, :4])
+    schema = [("adaptive_val", 1, np.float64), ("sums3", 3, np.uint64)]
+    part = {"adaptive_val": np.array([0.5, np.nan, 2.0]), "sums3": np.array([[1, 2, 3], [4, 5, 6], [7, 8, 9400320]], np.uint64)}
+    m = sharding._pack(part, schema, 3, 5)
+    assert tuple(m.shape) == (4, 5)
+    back = sharding._unpack(m[:, :3], schema)
+    assert back["sums3"].dtype == np.uint64 and np.array_equal(back["sums3"], part["sums3"])
+    assert np.array_equal(np.nan_to_num(back["adaptive_val"], nan=-1), np.nan_to_num(part["adaptive_val"], nan=-1))
+    with pytest.raises(ValueError):
+        sharding._pack({"x": np.array([1 << 60], np.uint64)}, [("x", 1, np.uint64)], 1, 1)
