@@ -14,6 +14,8 @@
 #include <string.h>
 #include <stdlib.h>
 #include <time.h>
+#include <sched.h>
+#include <memory>
 
 #include <algorithm>
 #include <atomic>
@@ -52,70 +54,105 @@ struct IngestSlot {
     bool in_flight = false;
 };
 
-// Minimal fork-join pool for the host-side tap gather of the ingest path.
-class GatherPool {
+// Host-side tap gather workers: ONE pool per process, shared by every context (node-level budget).  A context per GPU
+// each with its own pool oversubscribed the host (8 ranks x 16 threads on 32 cores); here the pool
+// has at most `budget()` threads -- the CPUs this process may run on, divided by the ranks sharing the node
+// (LOCAL_WORLD_SIZE under torchrun) -- and concurrent parallel_for calls of several contexts (one feeding thread per
+// GPU, eioku_b200.multi) share them: jobs queue up, workers drain the front job block by block, the submitting thread helps.
+class SharedGatherPool {
    public:
-    explicit GatherPool(int n) {
-        for (int i = 0; i < n; ++i) workers_.emplace_back([this, i] { run(i); });
+    static SharedGatherPool& instance() {
+        static SharedGatherPool* p = new SharedGatherPool();  // leaked on purpose: worker threads may outlive static destructors
+        return *p;
     }
-    ~GatherPool() {
+    static int budget() {
+        int cpus = (int)std::thread::hardware_concurrency();
+        cpu_set_t set;
+        if (sched_getaffinity(0, sizeof set, &set) == 0) cpus = CPU_COUNT(&set);
+        int ranks = 1;
+        if (const char* e = getenv("LOCAL_WORLD_SIZE")) ranks = std::max(1, atoi(e));
+        if (const char* e = getenv("ESD_NODE_RANKS")) ranks = std::max(1, atoi(e));
+        return std::max(1, cpus / ranks);
+    }
+    // at least `n` workers (capped at the budget); returns the pool size
+    int ensure(int n) {
+        std::lock_guard<std::mutex> lk(m_);
+        const int want = std::min(std::max(n, 1), budget());
+        while ((int)workers_.size() < want) workers_.emplace_back([this] { run(); });
+        return (int)workers_.size();
+    }
+    int size() {
+        std::lock_guard<std::mutex> lk(m_);
+        return (int)workers_.size();
+    }
+    // fn(lo, hi) over [0, n_items) in blocks; returns when every block has run.  `max_workers` bounds how many pool threads
+    // may work on THIS job at once (a context that asked for fewer threads than the pool has keeps to its share).
+    void parallel_for(int64_t n_items, int64_t block, int max_workers, const std::function<void(int64_t, int64_t)>& fn) {
+        auto job = std::make_shared<Job>();
+        job->fn = &fn;
+        job->n = n_items;
+        job->block = std::max<int64_t>(1, block);
+        job->remaining.store(n_items);
+        job->max_workers = std::max(1, max_workers);
         {
             std::lock_guard<std::mutex> lk(m_);
-            stop_ = true;
-            ++gen_;
+            queue_.push_back(job);
         }
         cv_.notify_all();
-        for (auto& t : workers_) t.join();
-    }
-    // fn(item) for item in [0, n_items), items handed out dynamically in blocks
-    void parallel_for(int64_t n_items, int64_t block, const std::function<void(int64_t, int64_t)>& fn) {
+        work_on(*job, true);  // the submitter helps instead of sleeping
+        std::unique_lock<std::mutex> lk(job->m);
+        job->done.wait(lk, [&] { return job->remaining.load() <= 0; });
         {
-            std::lock_guard<std::mutex> lk(m_);
-            fn_ = &fn;
-            n_items_ = n_items;
-            block_ = block;
-            next_.store(0);
-            pending_ = (int)workers_.size();
-            ++gen_;
+            std::lock_guard<std::mutex> lk2(m_);
+            queue_.erase(std::remove(queue_.begin(), queue_.end(), job), queue_.end());
         }
-        cv_.notify_all();
-        std::unique_lock<std::mutex> lk(m_);
-        done_cv_.wait(lk, [this] { return pending_ == 0; });
-        fn_ = nullptr;
     }
 
    private:
-    void run(int) {
-        uint64_t seen = 0;
+    struct Job {
+        const std::function<void(int64_t, int64_t)>* fn = nullptr;
+        int64_t n = 0, block = 1;
+        std::atomic<int64_t> next{0}, remaining{0};
+        std::atomic<int> active{0};
+        int max_workers = 1;
+        std::mutex m;
+        std::condition_variable done;
+    };
+    void work_on(Job& j, bool submitter) {
+        if (!submitter && j.active.fetch_add(1) >= j.max_workers - 1) {  // the submitter counts as one worker of its job
+            j.active.fetch_sub(1);
+            return;
+        }
         for (;;) {
-            const std::function<void(int64_t, int64_t)>* fn;
-            {
-                std::unique_lock<std::mutex> lk(m_);
-                cv_.wait(lk, [&] { return gen_ != seen; });
-                seen = gen_;
-                if (stop_) return;
-                fn = fn_;
-            }
-            for (;;) {
-                const int64_t lo = next_.fetch_add(block_);
-                if (lo >= n_items_) break;
-                (*fn)(lo, std::min(n_items_, lo + block_));
-            }
-            {
-                std::lock_guard<std::mutex> lk(m_);
-                if (--pending_ == 0) done_cv_.notify_all();
+            const int64_t lo = j.next.fetch_add(j.block);
+            if (lo >= j.n) break;
+            const int64_t hi = std::min(j.n, lo + j.block);
+            (*j.fn)(lo, hi);
+            if (j.remaining.fetch_sub(hi - lo) - (hi - lo) <= 0) {
+                std::lock_guard<std::mutex> lk(j.m);
+                j.done.notify_all();
             }
         }
+        if (!submitter) j.active.fetch_sub(1);
     }
-    std::vector<std::thread> workers_;
+    void run() {
+        for (;;) {
+            std::shared_ptr<Job> job;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] {
+                    for (auto& q : queue_)
+                        if (q->next.load() < q->n && q->active.load() < q->max_workers - 1) { job = q; return true; }
+                    return false;
+                });
+            }
+            work_on(*job, false);
+        }
+    }
     std::mutex m_;
-    std::condition_variable cv_, done_cv_;
-    const std::function<void(int64_t, int64_t)>* fn_ = nullptr;
-    std::atomic<int64_t> next_{0};
-    int64_t n_items_ = 0, block_ = 1;
-    int pending_ = 0;
-    uint64_t gen_ = 0;
-    bool stop_ = false;
+    std::condition_variable cv_;
+    std::vector<std::thread> workers_;
+    std::vector<std::shared_ptr<Job>> queue_;
 };
 
 // Kernel launcher of push_common.  DIRECT launches on the stream; the per-frame plugin path (esd_process_frame_host) is
@@ -273,7 +310,7 @@ struct esd_ctx {
     cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
     int64_t h2d_bytes = 0, h2d_copies = 0;
     // tap gather: host threads copy only the 6 bytes (two BGR taps) each destination column reads from a touched row
-    GatherPool* pool = nullptr;
+    int gather_threads = 0;              // > 0: gather enabled, at most this many threads of the process-wide pool per push
     int tap_row_bytes = 0;               // 6 * dst_w rounded up to 16
     uint2* d_xtab_taps = nullptr;        // x table for the tap-compact layout {6 d, a0 | a1 << 16}
     std::vector<int> tap_src_off;        // byte offset of tap 0 in a source row, per destination column
@@ -1187,8 +1224,6 @@ void esd_destroy(esd_ctx* c) {
     esd_ingest_close(c);
     free_plans(c);
     for (auto& ev : c->timing_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
-    delete c->pool;
-    c->pool = nullptr;
     cudaFree(c->d_xtab_taps);
     cudaFree(c->d_yrows); cudaFree(c->d_xtab); cudaFree(c->d_sdiv); cudaFree(c->d_hdiv);
     cudaFree(c->d_prev[0]); cudaFree(c->d_prev[1]); cudaFree(c->d_state); cudaFree(c->d_cuts);
@@ -1357,7 +1392,7 @@ int esd_ingest_push_host(esd_ctx* c, const uint8_t* h_bgr, int64_t n, int64_t fr
         i = j;
     }
     // the tap gather only pays when it shrinks the rows (downscale factor > 2)
-    const bool gather = c->pool != nullptr && c->resize && c->tap_row_bytes < c->row_bytes;
+    const bool gather = c->gather_threads > 0 && c->resize && c->tap_row_bytes < c->row_bytes;
     const int64_t tfb = nt * c->tap_row_bytes;  // tap-compact frame bytes
     for (int64_t done = 0; done < n;) {
         const int64_t m = std::min<int64_t>(c->frames_per_slot, n - done);
@@ -1393,7 +1428,7 @@ int esd_ingest_push_host(esd_ctx* c, const uint8_t* h_bgr, int64_t n, int64_t fr
                 gather_tap_rows(gs, src, frame_stride, pitch, dst_base, lo, hi);
             };
             TraceTimer tr;
-            c->pool->parallel_for(m * nt, 16, job);
+            SharedGatherPool::instance().parallel_for(m * nt, 16, c->gather_threads, job);
             tr.lap("host tap gather");
             CU(c, cudaMemcpyAsync(s.d_rows, s.h_pinned, (size_t)(m * tfb), cudaMemcpyHostToDevice, c->copy_stream));
             tr.lap("memcpyAsync call");
@@ -1446,8 +1481,8 @@ int esd_ingest_set_gather(esd_ctx* c, int32_t n_threads) {
     CU(c, cudaSetDevice(c->device));
     int rc = sync_all(c);
     if (rc) return rc;
-    delete c->pool;
-    c->pool = n_threads > 0 ? new GatherPool(n_threads) : nullptr;
+    // n_threads workers of the process-wide pool at most (the pool itself never exceeds the node budget)
+    c->gather_threads = n_threads > 0 ? std::min(n_threads, SharedGatherPool::instance().ensure(n_threads)) : 0;
     return ESD_OK;
 }
 

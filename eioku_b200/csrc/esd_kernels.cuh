@@ -209,7 +209,11 @@ __device__ __forceinline__ void score_row(const FusedParams& p, const uint8_t* _
 #pragma unroll
     for (int k = 0; k < PXT; ++k) {
         const int d = k * kConsumers + col;  // this thread's destination column (per-thread state stays indexed by tid)
-        if (d < p.dst_w) {
+        // No branch around the pixel: threads without a column (d >= dst_w) compute on the row's first bytes (their x offset
+        // is 0) and only their side effects are predicated off, so the body is straight-line code and two rows can be
+        // interleaved by the scheduler (the consumer warps are latency-bound: ~4 warps per scheduler).
+        const bool valid = d < p.dst_w;
+        {
             int b, g, r;
             if (RESIZE && NV12) {
                 // xoff packs, per destination column: byte offset of the two luma taps in a Y row (bits 0-12), byte offset
@@ -266,30 +270,30 @@ __device__ __forceinline__ void score_row(const FusedParams& p, const uint8_t* _
                 r = (px >> 16) & 255u;
             }
             if (CONTENT) {
-                if (EXTRAS && p.want_bgr && !(SPECIAL && (flags & F_HALO))) acc_bgr += (uint32_t)(b + g + r);
+                if (EXTRAS && p.want_bgr && valid && !(SPECIAL && (flags & F_HALO))) acc_bgr += (uint32_t)(b + g + r);
                 const uint32_t cur = bgr_to_hsv_packed(b, g, r, s_sdiv, s_hdiv);
                 uint32_t* slot = s_prev + (rloc * PXT + k) * kConsumers + tid;
                 uint32_t pv;
                 if (SPECIAL) {
                     pv = cur;
                     if (!(flags & (F_HALO | F_NOPREV)))
-                        pv = (flags & F_CTXPREV) ? __ldg(p.prev_in + (size_t)row * p.dst_w + d) : *slot;
-                    if (flags & F_SAVE) p.prev_out[(size_t)row * p.dst_w + d] = cur;
+                        pv = (flags & F_CTXPREV) ? (valid ? __ldg(p.prev_in + (size_t)row * p.dst_w + d) : cur) : *slot;
+                    if ((flags & F_SAVE) && valid) p.prev_out[(size_t)row * p.dst_w + d] = cur;
                 } else {
                     pv = *slot;
                 }
-                if (EXTRAS && p.vplane && !(SPECIAL && (flags & F_HALO)))
+                if (EXTRAS && p.vplane && valid && !(SPECIAL && (flags & F_HALO)))
                     p.vplane[((size_t)frame * p.dst_h + row) * p.dst_w + d] = (uint8_t)(cur >> 16);
-                const uint32_t diff = __vabsdiffu4(cur, pv);
+                const uint32_t diff = valid ? __vabsdiffu4(cur, pv) : 0u;
                 acc_hv += diff & 0x00ff00ffu;
                 acc_s += (diff >> 8) & 0xffu;
                 *slot = cur;
             }
-            if (HIST && !(SPECIAL && (flags & F_HALO))) {
+            if (HIST && valid && !(SPECIAL && (flags & F_HALO))) {
                 const int y = (4899 * r + 9617 * g + 1868 * b + 8192) >> 14;
                 atomicAdd(&s_hist_cur[(y * p.bins) >> 8], 1u);
             }
-            if (EXTRAS && p.gplane && !(SPECIAL && (flags & F_HALO)))
+            if (EXTRAS && p.gplane && valid && !(SPECIAL && (flags & F_HALO)))
                 p.gplane[((size_t)frame * p.dst_h + row) * p.dst_w + d] = bgr_to_gray(b, g, r);
         }
     }
@@ -518,7 +522,7 @@ __global__ void __launch_bounds__(kThreads) fused_score_kernel(const FusedParams
             xoff[k] = xe.x;
             xa01[k] = xe.y;
         } else {
-            xoff[k] = (uint32_t)(3 * d);
+            xoff[k] = (d < p.dst_w) ? (uint32_t)(3 * d) : 0u;
             xa01[k] = 0;
         }
     }
@@ -557,12 +561,13 @@ __global__ void __launch_bounds__(kThreads) fused_score_kernel(const FusedParams
                                                                   hist_cur, acc_hv, acc_s, acc_bgr);
             }
         } else {
-            for (int q = 0; q < nrows; ++q) {
+            // common path (no rare flag): rows in pairs, so that the two independent dependency chains overlap
+            auto fast_row = [&](int q) {
                 if (kQuads) {
                     score_row_quads<(PXT >= 4 ? PXT / 4 : 1), CONTENT, HIST, false, EXTRAS>(p, stage + q * row_slot, flags, rloc0 + q, row_first + q,
                                                                                     m.x, tid, s_sdiv, s_hdiv, s_prev, hist_cur, acc_hv,
                                                                                     acc_s, acc_bgr);
-                    continue;
+                    return;
                 }
                 const uint4 mr = meta_r[s * kMaxRowsPerStage + q];
                 const uint32_t mis0 = ALIGNED ? 0u : (mr.z & 0xffu), mis1 = ALIGNED ? 0u : ((mr.z >> 8) & 0xffu);
@@ -572,7 +577,15 @@ __global__ void __launch_bounds__(kThreads) fused_score_kernel(const FusedParams
                                                                    ALIGNED ? (mr.w & 0x10000u) : mr.w, mis0, mis1, mr.x, mr.y, flags, rloc0 + q,
                                                                    row_first + q, m.x, tid, col, xoff, xa01, s_sdiv, s_hdiv, s_prev,
                                                                    hist_cur, acc_hv, acc_s, acc_bgr);
+            };
+            int q = 0;
+            if (!kQuads && !NV12 && PXT == 1) {
+                for (; q + 1 < nrows; q += 2) {
+                    fast_row(q);
+                    fast_row(q + 1);
+                }
             }
+            for (; q < nrows; ++q) fast_row(q);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty_base + 8u * s);  // stage may be refilled

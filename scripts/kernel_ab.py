@@ -92,11 +92,13 @@ def main():
     ap.add_argument("--cases", default="1080p,720p,4k,nv12")
     ap.add_argument("--strides", default="1,0")
     ap.add_argument("--seconds", type=float, default=1.5)
+    ap.add_argument("--tune", action="append", default=[], help="extra esd_config field=value applied to every case")
     args = ap.parse_args()
+    extra = {kv.split("=")[0]: int(kv.split("=")[1]) for kv in args.tune}
     C, H = capi.ESD_DET_CONTENT, capi.ESD_DET_HIST
     for case in args.cases.split(","):
         for ks in [int(x) for x in args.strides.split(",")]:
-            tune = {"reserved1": ks}
+            tune = {"reserved1": ks, **extra}
             if case == "1080p":
                 run_case(case, 1920, 1080, 2048, C, capi.ESD_FMT_BGR24, tune, args.seconds)
             elif case == "720p":

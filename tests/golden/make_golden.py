@@ -60,7 +60,12 @@ def cube():
     img = np.stack([x & 255, (x >> 8) & 255, (x >> 16) & 255], -1).astype(np.uint8).reshape(4096, 4096, 3)
     hsv = cv2.cvtColor(img, cv2.COLOR_BGR2HSV)
     y = cv2.cvtColor(img, cv2.COLOR_BGR2YUV)[..., 0]
+    gray = cv2.cvtColor(img, cv2.COLOR_BGR2GRAY)
+    # per-row 256-bin histograms of Y (uint32 [4096][256]): what a GPU context with frames = rows of the cube can be asked for
+    rowhist = np.stack([np.bincount(r, minlength=256) for r in y]).astype(np.uint32)
     out = {"hsv_sha256": hashlib.sha256(hsv.tobytes()).hexdigest(), "y_sha256": hashlib.sha256(np.ascontiguousarray(y).tobytes()).hexdigest(),
+           "gray_sha256": hashlib.sha256(np.ascontiguousarray(gray).tobytes()).hexdigest(),
+           "y_rowhist_sha256": hashlib.sha256(rowhist.tobytes()).hexdigest(),
            "layout": "index = b | g<<8 | r<<16, reshaped 4096x4096x3", "versions": VERSIONS}
     json.dump(out, open(os.path.join(HERE, "cube.json"), "w"), indent=1)
 
