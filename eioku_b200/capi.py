@@ -29,7 +29,7 @@ EXPORTED_SYMBOLS = (
     "esd_create", "esd_destroy", "esd_reset", "esd_get_geometry", "esd_get_touched_rows",
     "esd_push_frames", "esd_push_nv12", "esd_push_rows", "esd_ingest_open", "esd_ingest_push_host", "esd_ingest_close", "esd_ingest_set_gather",
     "esd_ingest_stats", "esd_ingest_wait_copied", "esd_decide_device", "esd_copy_scores_device", "esd_synchronize", "esd_join", "esd_frames_pushed", "esd_read_scores", "esd_read_edge_counts", "esd_read_average_rgb",
-    "esd_read_hash", "esd_debug_read_hash_input", "esd_process_frame_host",
+    "esd_read_hash", "esd_read_hash_margin", "esd_debug_read_hash_input", "esd_process_frame_host",
     "esd_post_process", "esd_get_cuts",
     "esd_decide_arrays", "esd_debug_read_prev", "esd_set_timing", "esd_kernel_time", "esd_kernel_launches",
 )
@@ -121,6 +121,7 @@ def load_library(path: Optional[str] = None):
     L.esd_read_average_rgb.argtypes = [vp, i64, i64, vp]
     L.esd_read_edge_counts.argtypes = [vp, i64, i64, vp]
     L.esd_read_hash.argtypes = [vp, i64, i64, vp, vp]
+    L.esd_read_hash_margin.argtypes = [vp, i64, i64, vp]
     L.esd_process_frame_host.argtypes = [vp, vp, i64, i64, i32, i64, vp, i64, C.POINTER(i64), C.POINTER(i64)]
     L.esd_debug_read_hash_input.argtypes = [vp, i64, vp, i64]
     L.esd_post_process.argtypes = [vp, i32, i64, vp, i64, C.POINTER(i64)]
@@ -361,6 +362,12 @@ class EsdContext:
         self._check(self._L.esd_read_hash(self._h, from_frame, n, _np_ptr(raw), _np_ptr(dist)), "esd_read_hash")
         bits = np.unpackbits(raw.view(np.uint8).reshape(n, words * 4), axis=1, bitorder="little")[:, :size * size]
         return bits.reshape(n, size, size).astype(bool), dist
+
+    def read_hash_margin(self, from_frame: int, n: int) -> np.ndarray:
+        """float32 [n]: per frame the smallest |DCT coefficient - median| (a hash bit is only defined above cv2.dct's noise, ~4e-6)."""
+        out = np.empty(n, np.float32)
+        self._check(self._L.esd_read_hash_margin(self._h, from_frame, n, _np_ptr(out)), "esd_read_hash_margin")
+        return out
 
     def debug_hash_input(self, frame: int) -> np.ndarray:
         """uint8 [S, S] INTER_AREA thumbnail the hash of `frame` was computed from (most recent push only; test hook)."""

@@ -256,6 +256,7 @@ struct esd_ctx {
     uint32_t* d_counts = nullptr;  // [cap][bins]
     uint32_t* d_hash = nullptr;    // [cap][hash_words] perceptual hash bits
     double* d_hdist = nullptr;     // HashDetector hash_dist (normalised Hamming distance to the previous frame)
+    float* d_hmargin = nullptr;    // HashDetector: smallest |DCT coefficient - median| per frame (stability of its weakest bit)
     uint8_t* d_slab = nullptr;     // backing allocation of the six arrays above
 
     // per-batch scratch
@@ -432,7 +433,7 @@ int ensure_capacity(esd_ctx* c, int64_t frames_needed) {
     { int rc0 = sync_all(c); if (rc0) return rc0; }
     const int64_t bins = c->need_hist ? c->cfg.hist_bins : 0;
     const int64_t hwords = c->need_hash ? c->hash_words : 0;
-    const size_t bytes = (size_t)ncap * (3 * sizeof(unsigned long long) + 6 * sizeof(double) + (bins + 1 + hwords) * sizeof(uint32_t));
+    const size_t bytes = (size_t)ncap * (3 * sizeof(unsigned long long) + 6 * sizeof(double) + (bins + 2 + hwords) * sizeof(uint32_t));
     uint8_t* slab = nullptr;
     CU(c, cudaMalloc(&slab, bytes));
     uint8_t* q = slab;
@@ -453,6 +454,7 @@ int ensure_capacity(esd_ctx* c, int64_t frames_needed) {
     auto* n_edge = carve(&c->d_edge_counts, 1);
     auto* n_counts = carve(&c->d_counts, bins);
     auto* n_hash = carve(&c->d_hash, hwords);
+    auto* n_hmargin = carve(&c->d_hmargin, 1);
     if (used > 0) {
         CU(c, cudaMemcpy(n_sums, c->d_sums3, sizeof(unsigned long long) * 3 * used, cudaMemcpyDeviceToDevice));
         CU(c, cudaMemcpy(n_cv, c->d_cv, sizeof(double) * used, cudaMemcpyDeviceToDevice));
@@ -464,6 +466,7 @@ int ensure_capacity(esd_ctx* c, int64_t frames_needed) {
         if (bins) CU(c, cudaMemcpy(n_counts, c->d_counts, sizeof(uint32_t) * bins * used, cudaMemcpyDeviceToDevice));
         CU(c, cudaMemcpy(n_hdist, c->d_hdist, sizeof(double) * used, cudaMemcpyDeviceToDevice));
         if (hwords) CU(c, cudaMemcpy(n_hash, c->d_hash, sizeof(uint32_t) * hwords * used, cudaMemcpyDeviceToDevice));
+        CU(c, cudaMemcpy(n_hmargin, c->d_hmargin, sizeof(float) * used, cudaMemcpyDeviceToDevice));
     }
     cudaFree(c->d_slab);
     c->d_slab = slab;
@@ -471,6 +474,7 @@ int ensure_capacity(esd_ctx* c, int64_t frames_needed) {
     c->d_counts = bins ? n_counts : nullptr;
     c->d_hdist = n_hdist;
     c->d_hash = hwords ? n_hash : nullptr;
+    c->d_hmargin = n_hmargin;
     // ratios not yet computed read back as NaN
     fill_nan_kernel<<<(unsigned)((ncap - used + 255) / 256), 256>>>(c->d_ratio + used, ncap - used);
     CU(c, cudaGetLastError());
@@ -727,7 +731,8 @@ int push_common(esd_ctx* c, const uint8_t* d_src, int64_t n, int64_t frame_strid
         c->launches += 2;
     }
     if (c->need_hash) {
-        const HashParams& hp = c->hparams;
+        HashParams hp = c->hparams;
+        hp.margin_out = c->d_hmargin + base;
         const size_t hsmem = c->hash_smem;
         CU(c, klaunch(kg, ts, c->hash_fn, dim3((unsigned)n), dim3(kHashThreads), hsmem, c->d_gplane[buf], (int)n, hp, c->d_hash_small,
                       c->d_hash + base * c->hash_words));
@@ -1147,6 +1152,18 @@ int esd_create(esd_ctx** out, const esd_config* cfg, int device) {
     // rows per group: 16 measured best at 1080p->256x144 (profiles/r01_sweep.md); the previous-frame HSV of
     // a group lives in shared memory (R * pxt KB), keep it <= 32 KB unless the caller insists
     int R = cfg->rows_per_group > 0 ? cfg->rows_per_group : wide_noresize ? std::max(1, std::min(4, 32 / c->pxt)) : std::max(1, std::min(16, 32 / c->pxt));
+    if (cfg->rows_per_group <= 0 && !wide_noresize && R == 16 && c->need_content) {
+        // Narrow source rows (720p BGR24, 1080p NV12) leave room for a third CTA per SM if the previous-frame HSV of a group
+        // takes 8 KB instead of 16: the consumer warps are latency-bound there (issue slots 60 % busy with ~4 warps per
+        // scheduler, profiles/r02_fused_ncu.md), so 27 resident warps beat 18 -- 720p 0.84 -> 0.90 of the HBM peak
+        // (profiles/r02_kernel_ab_paired_rows_shapes.log).  1080p / 4K BGR24 rows fit two CTAs either way and keep 16.
+        const int S0 = cfg->pipeline_stages > 0 ? std::min(cfg->pipeline_stages, kMaxStages) : (c->rows_per_stage >= 4 ? 2 : c->rows_per_stage > 1 ? 3 : 4);
+        auto ctas_for = [&](int r) {
+            const size_t smem = fused_smem_bytes(c, r, S0) + 1024;  // + the per-CTA reservation
+            return (int)std::min<size_t>(prop.sharedMemPerMultiprocessor / smem, (size_t)(prop.maxThreadsPerMultiProcessor / kThreads));
+        };
+        if (ctas_for(8) > ctas_for(16)) R = 8;
+    }
     R = std::min(R, dh);
     R = std::min(R, 255);
     while (R > 1 && ((int64_t)R * c->pxt > 256 || (int64_t)R * dw > 65535)) --R;
@@ -1569,6 +1586,19 @@ int esd_read_hash(esd_ctx* c, int64_t from_frame, int64_t n, uint32_t* bits, dou
     if (rc) return rc;
     if (bits) CU(c, cudaMemcpy(bits, c->d_hash + i0 * c->hash_words, sizeof(uint32_t) * n * c->hash_words, cudaMemcpyDeviceToHost));
     if (hash_dist) CU(c, cudaMemcpy(hash_dist, c->d_hdist + i0, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    return ESD_OK;
+}
+
+int esd_read_hash_margin(esd_ctx* c, int64_t from_frame, int64_t n, float* min_margin) {
+    if (!c || !min_margin) return ESD_ERR_INVALID;
+    if (n == 0) return ESD_OK;
+    const int64_t i0 = from_frame - c->first_frame;
+    if (!c->started || n < 0 || i0 < 0 || i0 + n > c->n_frames)
+        return fail(c, ESD_ERR_INVALID, "read_hash_margin: range outside pushed frames");
+    if (!c->need_hash) return fail(c, ESD_ERR_STATE, "read_hash_margin: no hash detector configured");
+    int rc = esd_synchronize(c);
+    if (rc) return rc;
+    CU(c, cudaMemcpy(min_margin, c->d_hmargin + i0, sizeof(float) * n, cudaMemcpyDeviceToHost));
     return ESD_OK;
 }
 

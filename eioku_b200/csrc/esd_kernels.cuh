@@ -1022,6 +1022,7 @@ struct HashParams {
     const double* C;   // [hs][S] orthonormal DCT-II rows
     int words;         // ceil(hs * hs / 32)
     int band_rows;     // source rows of horizontal sums the shared-memory band buffer holds
+    float* margin_out; // [n] smallest |coefficient - median| of each frame of this launch (how far its weakest bit is from flipping)
 };
 constexpr int kHashThreads = 256;
 
@@ -1098,7 +1099,7 @@ __global__ void __launch_bounds__(kHashThreads, 8) hash_kernel(const uint8_t* __
     __shared__ uint32_t s_hist[256];
     __shared__ uint32_t s_sel[2];
     __shared__ int s_max;
-    __shared__ uint32_t s_cnt, s_min;
+    __shared__ uint32_t s_cnt, s_min, s_margin;
     const int tid = threadIdx.x;
     const int n_itab = 3 * S + 2 + P.n_yent;
     for (int i = tid; i < n_itab; i += kHashThreads) s_xb[i] = P.itab[i];
@@ -1109,7 +1110,7 @@ __global__ void __launch_bounds__(kHashThreads, 8) hash_kernel(const uint8_t* __
     for (int f = blockIdx.x; f < n_frames; f += gridDim.x) {
         const uint8_t* g = gplane + (size_t)f * P.w * P.h;
         __syncthreads();  // tables staged / previous frame done with every buffer
-        if (tid == 0) { s_max = 0; s_cnt = 0; s_min = 0xffffffffu; }
+        if (tid == 0) { s_max = 0; s_cnt = 0; s_min = 0xffffffffu; s_margin = 0x7f800000u; }
         // ---- INTER_AREA, separable exactly like OpenCV: per source row the horizontal sums (phase 1), then the
         //      vertical combination per destination pixel (phase 2), in bands of destination rows whose source rows fit
         //      the shared-memory buffer.
@@ -1241,6 +1242,14 @@ __global__ void __launch_bounds__(kHashThreads, 8) hash_kernel(const uint8_t* __
             const float hi = (s_cnt > (uint32_t)k_hi) ? med : key_float(s_min);
             med = __fmul_rn(__fadd_rn(med, hi), 0.5f);
         }
+        {   // the frame's weakest bit: min |coefficient - median| (non-negative floats order like their bit patterns)
+            uint32_t mg = 0x7f800000u;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (q * kHashThreads + tid < N) mg = min(mg, __float_as_uint(fabsf(__fsub_rn(mine[q], med))));
+            mg = __reduce_min_sync(0xffffffffu, mg);
+            if ((tid & 31) == 0) atomicMin(&s_margin, mg);
+        }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int idx = q * kHashThreads + tid;
@@ -1250,6 +1259,8 @@ __global__ void __launch_bounds__(kHashThreads, 8) hash_kernel(const uint8_t* __
                 if ((tid & 31) == 0 && (idx >> 5) < P.words) bits_out[(size_t)f * P.words + (idx >> 5)] = word;
             }
         }
+        __syncthreads();  // every warp's atomicMin into s_margin has landed
+        if (tid == 0 && P.margin_out) P.margin_out[f] = __uint_as_float(s_margin);
     }
 }
 

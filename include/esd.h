@@ -232,6 +232,13 @@ ESD_API int esd_read_edge_counts(esd_ctx* ctx, int64_t from_frame, int64_t n, ui
  * DCT is evaluated in float64, so a bit whose coefficient lies within float32 rounding noise of the median may differ
  * from a given cv2 build (cv2.dct itself differs between its IPP and plain paths).  Synchronises. */
 ESD_API int esd_read_hash(esd_ctx* ctx, int64_t from_frame, int64_t n, uint32_t* bits, double* hash_dist);
+/* How far each frame's hash is from flipping a bit: min over the size^2 bits of |DCT coefficient - median| (float32).  cv2.dct's
+ * float32 output differs between OpenCV builds (IPP / plain) by 1-2 ulp of the coefficients (~1e-6 for this normalisation), so
+ * a frame whose margin is below ~4e-6 has bits that a given cv2 build may set differently; every frame above it hashes
+ * identically to cv2 (tests/test_gpu_hash.py).  This is the documented tolerance of the one detector that is not bit-exact by
+ * construction (BASELINE north_star states none for it): bits with margin > 4e-6 are exact, the others are reported here.
+ * Synchronises. */
+ESD_API int esd_read_hash_margin(esd_ctx* ctx, int64_t from_frame, int64_t n, float* min_margin);
 /* Test hook: the (size*lowpass)^2 uint8 INTER_AREA thumbnail the hash of frame `frame` was computed from; only frames of
  * the most recent push are available.  Synchronises. */
 ESD_API int esd_debug_read_hash_input(esd_ctx* ctx, int64_t frame, uint8_t* out, int64_t cap);

@@ -79,6 +79,15 @@ def test_hash_stages_vs_cv2(w, h, size, lowpass):
         want_cuts += ref.process_frame(k, frames[k])
     bits, dist = det._ctx.read_hash(0, n)
     nun = check_bits(bits, np.array(ref.hashes), np.array(ref.margins), f"{w}x{h} size {size}")
+    # esd_read_hash_margin: the device reports how far each frame's weakest bit is from flipping; it agrees with cv2's own
+    # coefficients up to the DCT noise, and every frame it calls stable (margin > 2 * MARGIN) hashes exactly like cv2
+    margin = det._ctx.read_hash_margin(0, n)
+    ref_min = np.array(ref.margins, np.float64).reshape(n, -1).min(1)
+    assert margin.dtype == np.float32 and np.all(np.abs(margin - ref_min) <= MARGIN), (margin, ref_min)
+    for k in range(n):
+        if margin[k] > 2 * MARGIN:
+            assert np.array_equal(bits[k], np.array(ref.hashes[k])), k
+    assert margin[3] == 0.0  # the black frame: every coefficient equals the median
     assert np.isnan(dist[0])
     for k in range(1, n):
         assert abs(dist[k] - ref.dists[k]) * size * size <= nun[k] + nun[k - 1] + 1e-9
