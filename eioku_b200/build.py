@@ -37,7 +37,7 @@ def is_stale() -> bool:
 
 
 DECODE_LIB = os.path.join(HERE, "libesd_decode.so")
-DECODE_DEPS = ["esd_decode.cu", os.path.join("..", "..", "include", "esd_decode.h")]
+DECODE_DEPS = ["esd_decode.cu", "jpeg_core.h", "jpeg_parse.h", os.path.join("..", "..", "include", "esd_decode.h")]
 
 
 def build_decode(force: bool = False, verbose: bool = False) -> str:

@@ -16,8 +16,11 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <map>
 #include <string>
 #include <vector>
+
+#include "jpeg_parse.h"
 
 namespace {
 thread_local std::string g_open_error;
@@ -56,6 +59,21 @@ struct esd_mjpeg {
     std::vector<const unsigned char*> ptrs;
     std::vector<size_t> lens;
     std::vector<nvjpegImage_t> imgs;
+    // native decoder (ESD_JPEG_NATIVE): this library's own kernels over csrc/jpeg_core.h
+    esdjpeg::FrameGeometry geo{};
+    int tq[3] = {0, 0, 0}, td[3] = {0, 0, 0}, ta[3] = {0, 0, 0};
+    int blocks_per_frame = 0;
+    size_t plane_bytes = 0;                      // Y + Cb + Cr sample planes of one frame (MCU-padded)
+    std::map<std::string, int> huff_sets;        // DHT bytes -> index into d_huff
+    esdjpeg::ScanTables* d_huff = nullptr;       // [kMaxHuffSets]
+    uint8_t* d_comp = nullptr;                   // compressed pictures of the batch
+    size_t d_comp_bytes = 0;
+    struct NativeDesc { uint32_t off, len; int32_t huff_set, pad; };
+    NativeDesc* d_desc = nullptr;                // [batch]
+    uint16_t* d_quant = nullptr;                 // [batch][3][64] natural order, per component
+    int16_t* d_coef = nullptr;                   // [batch][blocks_per_frame][64]
+    uint8_t* d_planes = nullptr;                 // [batch][plane_bytes]
+    std::vector<uint8_t> h_meta[2];              // pinned-free host staging of descriptors + quant tables (copied with the batch)
 };
 
 namespace {
@@ -132,6 +150,129 @@ nvjpegBackend_t nj_backend(int b) {
 
 }  // namespace
 
+
+// =========================================================================== native baseline-JPEG decoder (ESD_JPEG_NATIVE)
+// Three kernels per batch, all arithmetic in csrc/jpeg_core.h (checked bit-exact against cv2.imdecode on the CPU):
+//   jpeg_entropy_kernel  one thread per PICTURE walks its Huffman-coded scan (the only sequential part of JPEG; pictures
+//                        written by ffmpeg / OpenCV carry no restart markers, so the parallelism is across the pictures of the
+//                        batch and across decoder sessions) and scatters the non-zero coefficients into a zeroed buffer;
+//   jpeg_idct_kernel     one thread per 8x8 block: dequantise + libjpeg's ISLOW IDCT -> MCU-padded Y / Cb / Cr planes;
+//   jpeg_color_kernel    one thread per four pixels: fancy h2v2 chroma upsampling + JFIF YCbCr -> BGR24, written in the
+//                        dense layout esd_push_frames reads.
+namespace {
+constexpr int kMaxHuffSets = 16;
+__constant__ uint8_t c_natural_order[64] = ESD_JPEG_NATURAL_ORDER;
+
+struct NativeLayout {
+    int n;                       // pictures in the batch
+    int mcus_x, mcus_y, restart_interval;
+    int width, height;
+    int blocks_per_frame;        // 6 * mcus_x * mcus_y
+    int td[3], ta[3];
+    unsigned long long plane_bytes;
+};
+
+__global__ void jpeg_entropy_kernel(NativeLayout L, const uint8_t* __restrict__ stage, const esd_mjpeg::NativeDesc* __restrict__ desc,
+                                    const esdjpeg::ScanTables* __restrict__ huff, int16_t* __restrict__ coef) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= L.n) return;
+    const esd_mjpeg::NativeDesc d = desc[f];
+    const esdjpeg::ScanTables& T = huff[d.huff_set];
+    esdjpeg::BitReader br;
+    br.init(stage + d.off, (int)d.len);
+    int pred[3] = {0, 0, 0};
+    int16_t* cf = coef + (size_t)f * L.blocks_per_frame * 64;
+    const int ybx = 2 * L.mcus_x;
+    int16_t* cb = cf + (size_t)4 * L.mcus_x * L.mcus_y * 64;
+    int16_t* cr = cb + (size_t)L.mcus_x * L.mcus_y * 64;
+    int mcu = 0;
+    for (int my = 0; my < L.mcus_y; ++my)
+        for (int mx = 0; mx < L.mcus_x; ++mx, ++mcu) {
+            if (L.restart_interval && mcu && mcu % L.restart_interval == 0) { br.restart(); pred[0] = pred[1] = pred[2] = 0; }
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+                esdjpeg::decode_block(br, T.dc[L.td[0]], T.ac[L.ta[0]], c_natural_order, pred[0],
+                                      cf + ((size_t)(2 * my + (b >> 1)) * ybx + 2 * mx + (b & 1)) * 64);
+            esdjpeg::decode_block(br, T.dc[L.td[1]], T.ac[L.ta[1]], c_natural_order, pred[1], cb + ((size_t)my * L.mcus_x + mx) * 64);
+            esdjpeg::decode_block(br, T.dc[L.td[2]], T.ac[L.ta[2]], c_natural_order, pred[2], cr + ((size_t)my * L.mcus_x + mx) * 64);
+        }
+}
+
+__global__ void __launch_bounds__(128) jpeg_idct_kernel(NativeLayout L, const int16_t* __restrict__ coef, const uint16_t* __restrict__ quant,
+                                                        uint8_t* __restrict__ planes) {
+    const int blk = blockIdx.x * blockDim.x + threadIdx.x;
+    const int f = blockIdx.y;
+    if (blk >= L.blocks_per_frame) return;
+    const int ny = 4 * L.mcus_x * L.mcus_y, nc = L.mcus_x * L.mcus_y;
+    const int comp = blk < ny ? 0 : (blk < ny + nc ? 1 : 2);
+    const int local = comp == 0 ? blk : (comp == 1 ? blk - ny : blk - ny - nc);
+    const int bw = comp == 0 ? 2 * L.mcus_x : L.mcus_x;  // blocks per row of this component
+    const int by = local / bw, bx = local - by * bw;
+    const int stride = bw * 8;
+    const size_t ysz = (size_t)(2 * L.mcus_x * 8) * (L.mcus_y * 16), csz = (size_t)(L.mcus_x * 8) * (L.mcus_y * 8);
+    uint8_t* plane = planes + (size_t)f * L.plane_bytes + (comp == 0 ? 0 : (comp == 1 ? ysz : ysz + csz));
+    uint8_t* out = plane + (size_t)(by * 8) * stride + bx * 8;
+    const uint4* src = reinterpret_cast<const uint4*>(coef + ((size_t)f * L.blocks_per_frame + blk) * 64);
+    union { uint4 v[8]; int16_t c[64]; } u;
+    uint32_t ac = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        u.v[i] = src[i];
+        ac |= u.v[i].y | u.v[i].z | u.v[i].w | (i ? u.v[i].x : (u.v[i].x & 0xffff0000u));
+    }
+    const uint16_t* q = quant + ((size_t)f * 3 + comp) * 64;
+    if (ac == 0) {
+        // DC only: both passes of the ISLOW IDCT reduce to (4 * dc * q0 + 16) >> 5 for every sample (same rounding)
+        const int32_t v = esdjpeg::descale(((int32_t)u.c[0] * (int32_t)q[0]) << 2, 5);
+        const uint32_t s = esdjpeg::range_limit(v);
+        const uint32_t w4 = s * 0x01010101u;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) *reinterpret_cast<uint2*>(out + (size_t)r * stride) = make_uint2(w4, w4);
+        return;
+    }
+    uint16_t ql[64];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const uint4 t = reinterpret_cast<const uint4*>(q)[i];
+        reinterpret_cast<uint4*>(ql)[i] = t;
+    }
+    union { uint2 v[8]; uint8_t b[64]; } o;
+    esdjpeg::idct_islow(u.c, ql, o.b, 8);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) *reinterpret_cast<uint2*>(out + (size_t)r * stride) = o.v[r];
+}
+
+__global__ void __launch_bounds__(256) jpeg_color_kernel(NativeLayout L, const uint8_t* __restrict__ planes, uint8_t* __restrict__ bgr) {
+    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int y = blockIdx.y, f = blockIdx.z;
+    if (x4 >= L.width) return;
+    const int yw = 2 * L.mcus_x * 8, cw = L.mcus_x * 8;
+    const size_t ysz = (size_t)yw * (L.mcus_y * 16), csz = (size_t)cw * (L.mcus_y * 8);
+    const uint8_t* Y = planes + (size_t)f * L.plane_bytes;
+    const uint8_t* Cb = Y + ysz;
+    const uint8_t* Cr = Cb + csz;
+    const int rcw = (L.width + 1) >> 1, rch = (L.height + 1) >> 1;
+    const uint32_t yy = *reinterpret_cast<const uint32_t*>(Y + (size_t)y * yw + x4);  // yw is a multiple of 16, x4 of 4
+    uint8_t px[12];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int x = min(x4 + k, L.width - 1);
+        esdjpeg::ycc_to_bgr((int)((yy >> (8 * k)) & 255u), esdjpeg::fancy_chroma(Cb, cw, rcw, rch, x, y),
+                            esdjpeg::fancy_chroma(Cr, cw, rcw, rch, x, y), px + 3 * k);
+    }
+    uint8_t* o = bgr + ((size_t)f * L.height + y) * (size_t)L.width * 3 + (size_t)x4 * 3;
+    if (x4 + 4 <= L.width && ((L.width * 3) & 3) == 0) {  // 12 bytes on a 4-byte boundary
+        uint32_t* ow = reinterpret_cast<uint32_t*>(o);
+        ow[0] = px[0] | (px[1] << 8) | (px[2] << 16) | ((uint32_t)px[3] << 24);
+        ow[1] = px[4] | (px[5] << 8) | (px[6] << 16) | ((uint32_t)px[7] << 24);
+        ow[2] = px[8] | (px[9] << 8) | (px[10] << 16) | ((uint32_t)px[11] << 24);
+    } else {
+        for (int k = 0; k < 4 && x4 + k < L.width; ++k) { o[3 * k] = px[3 * k]; o[3 * k + 1] = px[3 * k + 1]; o[3 * k + 2] = px[3 * k + 2]; }
+    }
+}
+
+}  // namespace
+
 extern "C" {
 
 int esd_decode_abi_version(void) { return ESD_DECODE_ABI_VERSION; }
@@ -146,6 +287,7 @@ void esd_mjpeg_close(esd_mjpeg* h) {
         cudaFree(h->d_out[b]);
         if (h->h_stage[b]) cudaFreeHost(h->h_stage[b]);
     }
+    cudaFree(h->d_huff); cudaFree(h->d_comp); cudaFree(h->d_coef); cudaFree(h->d_planes);
     if (h->state) nvjpegJpegStateDestroy(h->state);
     if (h->nj) nvjpegDestroy(h->nj);
     if (h->map) munmap(const_cast<uint8_t*>(h->map), h->map_bytes);
@@ -158,7 +300,7 @@ int esd_mjpeg_open(esd_mjpeg** out, const char* path, int device, int32_t batch_
     if (!out || !path) return fail(nullptr, ESD_DEC_ERR_INVALID, "esd_mjpeg_open: null argument");
     *out = nullptr;
     if (batch_frames < 1 || batch_frames > 4096) return fail(nullptr, ESD_DEC_ERR_INVALID, "esd_mjpeg_open: batch_frames must be in 1..4096");
-    if (backend < ESD_JPEG_AUTO || backend > ESD_JPEG_HARDWARE) return fail(nullptr, ESD_DEC_ERR_INVALID, "esd_mjpeg_open: unknown backend %d", backend);
+    if (backend < ESD_JPEG_AUTO || backend > ESD_JPEG_NATIVE) return fail(nullptr, ESD_DEC_ERR_INVALID, "esd_mjpeg_open: unknown backend %d", backend);
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
         cudaGetLastError();
@@ -192,11 +334,36 @@ int esd_mjpeg_open(esd_mjpeg** out, const char* path, int device, int32_t batch_
     if (h->pics.empty()) { fail(h, ESD_DEC_ERR_FORMAT, "%s: no pictures in the movi list", path); return bail(ESD_DEC_ERR_FORMAT); }
 
     if (cudaSetDevice(device) != cudaSuccess) { fail(h, ESD_DEC_ERR_CUDA, "cudaSetDevice(%d) failed", device); return bail(ESD_DEC_ERR_CUDA); }
-    // back end: what the caller asked for, or the best one the library grants
+    const size_t frame_bytes = (size_t)h->width * h->height * 3;
+    // back end: what the caller asked for, or the best one available.  NATIVE first: it needs nothing but the stream to qualify.
+    if (backend == ESD_JPEG_AUTO || backend == ESD_JPEG_NATIVE) {
+        esdjpeg::JpegHeader jh;
+        std::string why;
+        const Picture& p0 = h->pics[0];
+        const bool ok = p0.offset + p0.size <= h->map_bytes && esdjpeg::parse_jpeg(h->map + p0.offset, p0.size, &jh, &why) &&
+                        jh.width == h->width && jh.height == h->height;
+        if (ok) {
+            h->geo = esdjpeg::geometry_of(jh);
+            for (int c = 0; c < 3; ++c) { h->tq[c] = jh.tq[c]; h->td[c] = jh.td[c]; h->ta[c] = jh.ta[c]; }
+            h->blocks_per_frame = 6 * h->geo.mcus_x * h->geo.mcus_y;
+            h->plane_bytes = (size_t)(h->geo.mcus_x * 16) * (h->geo.mcus_y * 16) * 3 / 2;
+            cudaError_t e = cudaMalloc(&h->d_huff, sizeof(esdjpeg::ScanTables) * kMaxHuffSets);
+            if (e == cudaSuccess) e = cudaMalloc(&h->d_coef, (size_t)h->batch * h->blocks_per_frame * 64 * sizeof(int16_t));
+            if (e == cudaSuccess) e = cudaMalloc(&h->d_planes, (size_t)h->batch * h->plane_bytes);
+            if (e != cudaSuccess) {
+                fail(h, ESD_DEC_ERR_CUDA, "native decoder: device buffers for %d frames could not be allocated: %s", h->batch, cudaGetErrorString(e));
+                return bail(ESD_DEC_ERR_CUDA);
+            }
+            h->backend = ESD_JPEG_NATIVE;
+        } else if (backend == ESD_JPEG_NATIVE) {
+            fail(h, ESD_DEC_ERR_UNSUPPORTED, "native decoder: %s", why.empty() ? "picture size differs from the stream header" : why.c_str());
+            return bail(ESD_DEC_ERR_UNSUPPORTED);
+        }
+    }
     const int order_auto[3] = {ESD_JPEG_HARDWARE, ESD_JPEG_GPU_HYBRID, ESD_JPEG_DEFAULT};
     const int order_one[1] = {backend};
     const int* order = backend == ESD_JPEG_AUTO ? order_auto : order_one;
-    const int n_order = backend == ESD_JPEG_AUTO ? 3 : 1;
+    const int n_order = h->backend == ESD_JPEG_NATIVE ? 0 : (backend == ESD_JPEG_AUTO ? 3 : 1);
     nvjpegStatus_t js = NVJPEG_STATUS_NOT_INITIALIZED;
     for (int i = 0; i < n_order; ++i) {
         js = nvjpegCreateEx(nj_backend(order[i]), nullptr, nullptr, NVJPEG_FLAGS_DEFAULT, &h->nj);
@@ -210,12 +377,11 @@ int esd_mjpeg_open(esd_mjpeg** out, const char* path, int device, int32_t batch_
         h->nj = nullptr;
         cudaGetLastError();
     }
-    if (!h->nj) { fail(h, ESD_DEC_ERR_NVJPEG, "nvJPEG: no usable back end (last status %d)", (int)js); return bail(ESD_DEC_ERR_NVJPEG); }
+    if (!h->nj && h->backend != ESD_JPEG_NATIVE) { fail(h, ESD_DEC_ERR_NVJPEG, "nvJPEG: no usable back end (last status %d)", (int)js); return bail(ESD_DEC_ERR_NVJPEG); }
     if (h->backend == ESD_JPEG_HARDWARE) {
         unsigned cores = 0;
         if (nvjpegGetHardwareDecoderInfo(h->nj, &h->hw_engines, &cores) != NVJPEG_STATUS_SUCCESS) h->hw_engines = 0;
     }
-    const size_t frame_bytes = (size_t)h->width * h->height * 3;
     for (int b = 0; b < 2; ++b) {
         if (cudaMalloc(&h->d_out[b], frame_bytes * h->batch) != cudaSuccess || cudaEventCreateWithFlags(&h->done[b], cudaEventDisableTiming) != cudaSuccess) {
             fail(h, ESD_DEC_ERR_CUDA, "device buffer of %d frames (%zu bytes) could not be allocated: %s", h->batch, frame_bytes * h->batch,
@@ -265,8 +431,12 @@ int esd_mjpeg_read(esd_mjpeg* h, int64_t max_frames, void* stream, uint8_t** d_b
         if (e != cudaSuccess) return fail(h, ESD_DEC_ERR_CUDA, "decode of an earlier batch failed: %s", cudaGetErrorString(e));
         h->in_flight[b] = false;
     }
-    size_t total = 0;
+    const bool native = h->backend == ESD_JPEG_NATIVE;
+    // pinned staging of the batch: [descriptors n x 16][quantisation tables n x 3 x 64 x u16][pictures, 64-byte aligned]
+    const size_t meta = native ? (((size_t)n * sizeof(esd_mjpeg::NativeDesc) + (size_t)n * 3 * 64 * sizeof(uint16_t) + 63) & ~(size_t)63) : 0;
+    size_t total = meta;
     for (int64_t i = 0; i < n; ++i) total += ((size_t)h->pics[h->pos + i].size + 63) & ~(size_t)63;
+    total += 64;  // the entropy kernel's four-byte look-ahead may read past the last picture
     if (total > h->h_stage_bytes[b]) {
         if (h->h_stage[b]) cudaFreeHost(h->h_stage[b]);
         h->h_stage[b] = nullptr;
@@ -277,27 +447,84 @@ int esd_mjpeg_read(esd_mjpeg* h, int64_t max_frames, void* stream, uint8_t** d_b
         h->h_stage_bytes[b] = want;
     }
     const size_t frame_bytes = (size_t)h->width * h->height * 3;
-    size_t off = 0;
+    size_t off = meta;
+    esd_mjpeg::NativeDesc* hdesc = reinterpret_cast<esd_mjpeg::NativeDesc*>(h->h_stage[b]);
+    uint16_t* hquant = reinterpret_cast<uint16_t*>(h->h_stage[b] + (size_t)n * sizeof(esd_mjpeg::NativeDesc));
     for (int64_t i = 0; i < n; ++i) {
         const Picture& p = h->pics[h->pos + i];
         if (p.offset + p.size > h->map_bytes) return fail(h, ESD_DEC_ERR_FORMAT, "picture %lld lies outside the file", (long long)(h->pos + i));
         memcpy(h->h_stage[b] + off, h->map + p.offset, p.size);
-        h->ptrs[i] = h->h_stage[b] + off;
-        h->lens[i] = p.size;
+        if (native) {
+            // header walk on the host (a few markers); the Huffman tables are built only for a DHT not seen before in this file
+            esdjpeg::JpegHeader jh;
+            std::string why;
+            const uint8_t* pic = h->h_stage[b] + off;
+            if (!esdjpeg::parse_jpeg(pic, p.size, &jh, &why, false))
+                return fail(h, ESD_DEC_ERR_UNSUPPORTED, "picture %lld: %s", (long long)(h->pos + i), why.c_str());
+            bool same = jh.width == h->width && jh.height == h->height && jh.restart_interval == h->geo.restart_interval;
+            for (int c = 0; c < 3; ++c) same = same && jh.td[c] == h->td[c] && jh.ta[c] == h->ta[c];
+            if (!same) return fail(h, ESD_DEC_ERR_UNSUPPORTED, "picture %lld changes the stream's geometry / table selectors", (long long)(h->pos + i));
+            auto it = h->huff_sets.find(jh.dht_bytes);
+            if (it == h->huff_sets.end()) {
+                if ((int)h->huff_sets.size() >= kMaxHuffSets)
+                    return fail(h, ESD_DEC_ERR_UNSUPPORTED, "more than %d distinct Huffman table sets in one file", kMaxHuffSets);
+                esdjpeg::JpegHeader full;
+                if (!esdjpeg::parse_jpeg(pic, p.size, &full, &why, true)) return fail(h, ESD_DEC_ERR_UNSUPPORTED, "picture %lld: %s", (long long)(h->pos + i), why.c_str());
+                const int idx = (int)h->huff_sets.size();
+                // synchronous upload of a new table set (once per file for constant tables): nothing in flight reads this slot yet
+                if (cudaMemcpy(h->d_huff + idx, &full.huff, sizeof(esdjpeg::ScanTables), cudaMemcpyHostToDevice) != cudaSuccess)
+                    return fail(h, ESD_DEC_ERR_CUDA, "Huffman table upload failed");
+                it = h->huff_sets.emplace(jh.dht_bytes, idx).first;
+            }
+            hdesc[i].off = (uint32_t)(off + jh.scan_offset);
+            hdesc[i].len = (uint32_t)jh.scan_len;
+            hdesc[i].huff_set = it->second;
+            hdesc[i].pad = 0;
+            for (int c = 0; c < 3; ++c) memcpy(hquant + ((size_t)i * 3 + c) * 64, jh.quant[jh.tq[c]], 64 * sizeof(uint16_t));
+        } else {
+            h->ptrs[i] = h->h_stage[b] + off;
+            h->lens[i] = p.size;
+            memset(&h->imgs[i], 0, sizeof(nvjpegImage_t));
+            h->imgs[i].channel[0] = h->d_out[b] + (size_t)i * frame_bytes;
+            h->imgs[i].pitch[0] = (size_t)h->width * 3;
+        }
         off += ((size_t)p.size + 63) & ~(size_t)63;
-        memset(&h->imgs[i], 0, sizeof(nvjpegImage_t));
-        h->imgs[i].channel[0] = h->d_out[b] + (size_t)i * frame_bytes;
-        h->imgs[i].pitch[0] = (size_t)h->width * 3;
     }
-    if (h->initialized_batch != (int)n) {  // the batched API wants exactly the initialised number of pictures (tail of the stream)
-        nvjpegStatus_t js = nvjpegDecodeBatchedInitialize(h->nj, h->state, (int)n, 1, NVJPEG_OUTPUT_BGRI);
-        if (js != NVJPEG_STATUS_SUCCESS) return fail(h, ESD_DEC_ERR_NVJPEG, "nvjpegDecodeBatchedInitialize(%lld) failed: status %d", (long long)n, (int)js);
-        h->initialized_batch = (int)n;
+    if (native) {
+        if (total > h->d_comp_bytes) {  // device mirror of the staging block (grow-only; everything that used it ran on `st` before)
+            if (h->d_comp) { cudaStreamSynchronize(st); cudaFree(h->d_comp); h->d_comp = nullptr; h->d_comp_bytes = 0; }
+            const size_t want = total + total / 4 + 4096;
+            if (cudaMalloc(&h->d_comp, want) != cudaSuccess) return fail(h, ESD_DEC_ERR_CUDA, "device staging of %zu bytes could not be allocated", want);
+            h->d_comp_bytes = want;
+        }
+        NativeLayout L{};
+        L.n = (int)n;
+        L.mcus_x = h->geo.mcus_x; L.mcus_y = h->geo.mcus_y; L.restart_interval = h->geo.restart_interval;
+        L.width = h->width; L.height = h->height;
+        L.blocks_per_frame = h->blocks_per_frame;
+        for (int c = 0; c < 3; ++c) { L.td[c] = h->td[c]; L.ta[c] = h->ta[c]; }
+        L.plane_bytes = h->plane_bytes;
+        cudaError_t e = cudaMemcpyAsync(h->d_comp, h->h_stage[b], total, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(h->d_coef, 0, (size_t)n * h->blocks_per_frame * 64 * sizeof(int16_t), st);
+        if (e != cudaSuccess) return fail(h, ESD_DEC_ERR_CUDA, "native decode: staging copy failed: %s", cudaGetErrorString(e));
+        const esd_mjpeg::NativeDesc* ddesc = reinterpret_cast<const esd_mjpeg::NativeDesc*>(h->d_comp);
+        const uint16_t* dquant = reinterpret_cast<const uint16_t*>(h->d_comp + (size_t)n * sizeof(esd_mjpeg::NativeDesc));
+        jpeg_entropy_kernel<<<(unsigned)((n + 31) / 32), 32, 0, st>>>(L, h->d_comp, ddesc, h->d_huff, h->d_coef);
+        jpeg_idct_kernel<<<dim3((unsigned)((h->blocks_per_frame + 127) / 128), (unsigned)n), 128, 0, st>>>(L, h->d_coef, dquant, h->d_planes);
+        jpeg_color_kernel<<<dim3((unsigned)(((h->width + 3) / 4 + 255) / 256), (unsigned)h->height, (unsigned)n), 256, 0, st>>>(L, h->d_planes, h->d_out[b]);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return fail(h, ESD_DEC_ERR_CUDA, "native decode kernels: %s", cudaGetErrorString(e));
+    } else {
+        if (h->initialized_batch != (int)n) {  // the batched API wants exactly the initialised number of pictures (tail of the stream)
+            nvjpegStatus_t js = nvjpegDecodeBatchedInitialize(h->nj, h->state, (int)n, 1, NVJPEG_OUTPUT_BGRI);
+            if (js != NVJPEG_STATUS_SUCCESS) return fail(h, ESD_DEC_ERR_NVJPEG, "nvjpegDecodeBatchedInitialize(%lld) failed: status %d", (long long)n, (int)js);
+            h->initialized_batch = (int)n;
+        }
+        nvjpegStatus_t js = nvjpegDecodeBatched(h->nj, h->state, h->ptrs.data(), h->lens.data(), h->imgs.data(), st);
+        if (js != NVJPEG_STATUS_SUCCESS)
+            return fail(h, ESD_DEC_ERR_NVJPEG, "nvjpegDecodeBatched failed at frame %lld: status %d (%s)", (long long)h->pos, (int)js,
+                        js == NVJPEG_STATUS_JPEG_NOT_SUPPORTED ? "bitstream not supported by this back end" : js == NVJPEG_STATUS_BAD_JPEG ? "bad JPEG" : "see nvjpeg.h");
     }
-    nvjpegStatus_t js = nvjpegDecodeBatched(h->nj, h->state, h->ptrs.data(), h->lens.data(), h->imgs.data(), st);
-    if (js != NVJPEG_STATUS_SUCCESS)
-        return fail(h, ESD_DEC_ERR_NVJPEG, "nvjpegDecodeBatched failed at frame %lld: status %d (%s)", (long long)h->pos, (int)js,
-                    js == NVJPEG_STATUS_JPEG_NOT_SUPPORTED ? "bitstream not supported by this back end" : js == NVJPEG_STATUS_BAD_JPEG ? "bad JPEG" : "see nvjpeg.h");
     if (cudaEventRecord(h->done[b], st) != cudaSuccess) return fail(h, ESD_DEC_ERR_CUDA, "cudaEventRecord failed");
     h->in_flight[b] = true;
     h->reads++;

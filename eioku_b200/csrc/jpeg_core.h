@@ -1,0 +1,297 @@
+// jpeg_core.h -- baseline JPEG (ISO/IEC 10918-1, 8-bit, Huffman, 4:2:0) decoding arithmetic shared by the CUDA kernels of
+// libesd_decode.so (csrc/esd_decode.cu) and by a CPU test shim (tests/jpeg_shim.cpp), so that the exact same code is checked
+// on the CPU against cv2.imdecode before it runs on a GPU.
+//
+// The arithmetic restates libjpeg's defaults, which is what OpenCV's imdecode runs (libjpeg-turbo: dct_method JDCT_ISLOW,
+// do_fancy_upsampling TRUE; its SIMD paths are bit-exact with the C code):
+//   * jidctint.c  jpeg_idct_islow      -- Loeffler-Ligtenberg-Moschytz, CONST_BITS 13, PASS1_BITS 2
+//   * jdsample.c  h2v2_fancy_upsample  -- triangle filter, 3/4 - 1/4 vertically then horizontally, bias 8 / 7
+//   * jdcolor.c   ycc_rgb_convert      -- 16-bit fixed-point JFIF YCbCr -> RGB
+// so a decoded picture is bit-identical to cv2.imdecode's (tests/test_host_jpeg.py on the CPU, tests/test_gpu_decode.py on
+// the device).  Not a general JPEG decoder: progressive / arithmetic / 12-bit / other subsamplings are rejected by the host
+// parser and those files go to nvJPEG or to the host decoder.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define JPG_HD __host__ __device__ __forceinline__
+#define JPG_M __host__ __device__ __forceinline__   // member functions
+#else
+#define JPG_HD static inline
+#define JPG_M inline
+#endif
+
+namespace esdjpeg {
+
+constexpr int kLookBits = 9;  // Huffman look-ahead table width
+
+// zig-zag position -> natural (row-major) position inside an 8x8 block (device code keeps its own __constant__ copy and
+// passes it to decode_block)
+#define ESD_JPEG_NATURAL_ORDER                                                                                                   \
+    {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6,  7,  14, 21, 28, \
+     35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63}
+static const uint8_t kNaturalOrderHost[64] = ESD_JPEG_NATURAL_ORDER;
+
+// One Huffman table in decoding form (libjpeg's d_derived_tbl, reduced).
+struct HuffTable {
+    uint16_t look[1 << kLookBits];  // (code length << 8) | symbol for codes of <= kLookBits bits, 0 = longer code
+    int32_t maxcode[18];            // largest code of each length (-1 = none); [17] = sentinel
+    int32_t valoffset[17];          // huffval index of the first code of each length, minus that code
+    uint8_t huffval[256];
+};
+
+// Everything one scan needs (per file; per-frame quantisation tables are allowed to differ and travel separately).
+struct ScanTables {
+    HuffTable dc[2], ac[2];
+};
+
+struct FrameGeometry {
+    int width, height;          // picture
+    int mcus_x, mcus_y;         // 16x16 MCUs
+    int yblocks_x, cblocks_x;   // blocks per row: luma 2 * mcus_x, chroma mcus_x
+    int restart_interval;       // MCUs between RSTn markers, 0 = none
+};
+
+// Builds `t` from the DHT payload (16 counts + values).  Returns false for an invalid table.
+inline bool build_huff_table(const uint8_t* counts, const uint8_t* vals, int nvals, HuffTable* t) {
+    int total = 0;
+    for (int i = 0; i < 16; ++i) total += counts[i];
+    if (total > 256 || total != nvals) return false;
+    for (int i = 0; i < 256; ++i) t->huffval[i] = i < nvals ? vals[i] : 0;
+    for (int i = 0; i < (1 << kLookBits); ++i) t->look[i] = 0;
+    int code = 0, k = 0;
+    for (int len = 1; len <= 16; ++len) {
+        const int n = counts[len - 1];
+        t->valoffset[len] = k - code;
+        if (n) {
+            for (int j = 0; j < n; ++j) {
+                if (len <= kLookBits) {
+                    const int first = (code + j) << (kLookBits - len);
+                    for (int f = 0; f < (1 << (kLookBits - len)); ++f) t->look[first + f] = (uint16_t)((len << 8) | t->huffval[k + j]);
+                }
+            }
+            code += n;
+            k += n;
+            t->maxcode[len] = code - 1;
+            if (code > (1 << len)) return false;
+        } else {
+            t->maxcode[len] = -1;
+        }
+        code <<= 1;
+    }
+    t->maxcode[0] = -1;
+    t->valoffset[0] = 0;
+    t->maxcode[17] = 0x7fffffff;
+    return true;
+}
+
+// MSB-first bit reader over an entropy-coded segment with byte stuffing (FF00 -> FF).  A marker ends the data: zeros follow.
+struct BitReader {
+    const uint8_t* p;
+    const uint8_t* end;
+    uint64_t buf;  // valid bits are the top `bits`
+    int bits;
+    int marker;    // marker code seen (0 = none)
+
+    JPG_M void init(const uint8_t* data, int len) { p = data; end = data + len; buf = 0; bits = 0; marker = 0; }
+
+    JPG_M void fill() {
+        // fast path: four bytes without an FF
+        if (bits <= 32 && !marker && p + 4 <= end) {
+            const uint32_t w = ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | (uint32_t)p[3];
+            const uint32_t v = ~w;
+            if (!((v - 0x01010101u) & ~v & 0x80808080u)) {  // no byte of w is 0xFF
+                buf |= (uint64_t)w << (32 - bits);
+                bits += 32;
+                p += 4;
+                return;
+            }
+        }
+        while (bits <= 56) {
+            uint32_t b = 0;
+            if (!marker && p < end) {
+                b = *p++;
+                if (b == 0xFF) {
+                    while (p < end && *p == 0xFF) ++p;        // fill bytes before a marker
+                    const uint32_t b2 = p < end ? *p : 0xD9u;
+                    if (b2 == 0) ++p;                          // stuffed zero: the data byte 0xFF
+                    else { marker = (int)b2; --p; b = 0; }     // a marker ends the data (p stays on its 0xFF); zeros follow
+                }
+            }
+            buf |= (uint64_t)b << (56 - bits);
+            bits += 8;
+        }
+    }
+    JPG_M uint32_t peek16() {
+        if (bits < 16) fill();
+        return (uint32_t)(buf >> 48);
+    }
+    JPG_M void skip(int n) { buf <<= n; bits -= n; }
+    JPG_M int32_t receive_extend(int s) {  // s in 1..15 (16 for the degenerate DC case)
+        if (bits < s) fill();
+        const uint32_t v = (uint32_t)(buf >> (64 - s));
+        skip(s);
+        // HUFF_EXTEND: values below 2^(s-1) are negative
+        return (int32_t)v < (1 << (s - 1)) ? (int32_t)v - (1 << s) + 1 : (int32_t)v;
+    }
+    // after a restart interval: drop the partial byte, step over the RSTn marker
+    JPG_M void restart() {
+        buf = 0; bits = 0;
+        if (marker >= 0xD0 && marker <= 0xD7) { p += 2; marker = 0; }
+        else if (!marker) {  // marker not reached through the bit buffer yet: find it
+            while (p + 1 < end && !(p[0] == 0xFF && p[1] >= 0xD0 && p[1] <= 0xD7)) ++p;
+            if (p + 1 < end) p += 2;
+        }
+    }
+};
+
+JPG_HD int decode_symbol(BitReader& br, const HuffTable& t) {
+    const uint32_t pk = br.peek16();
+    const uint32_t e = t.look[pk >> (16 - kLookBits)];
+    if (e) {
+        br.skip((int)(e >> 8));
+        return (int)(e & 255u);
+    }
+    int len = kLookBits + 1;
+    int32_t code = (int32_t)(pk >> (16 - len));
+    while (len <= 16 && code > t.maxcode[len]) {
+        ++len;
+        code = (int32_t)(pk >> (16 - len));
+    }
+    if (len > 16) { br.skip(16); return 0; }  // corrupt data: resynchronise on garbage rather than loop
+    br.skip(len);
+    return t.huffval[(code + t.valoffset[len]) & 255];
+}
+
+// One 8x8 block: DC difference + AC run/size pairs -> coefficients in NATURAL order (the caller has zeroed `coef`).
+// Returns the zig-zag index of the last non-zero coefficient.
+JPG_HD int decode_block(BitReader& br, const HuffTable& dc, const HuffTable& ac, const uint8_t* natural, int& pred, int16_t* coef) {
+    int s = decode_symbol(br, dc);
+    if (s) pred += br.receive_extend(s > 16 ? 16 : s);
+    coef[0] = (int16_t)pred;
+    int last = 0;
+    for (int k = 1; k < 64;) {
+        const int rs = decode_symbol(br, ac);
+        const int r = rs >> 4;
+        s = rs & 15;
+        if (s == 0) {
+            if (r != 15) break;  // EOB
+            k += 16;
+            continue;
+        }
+        k += r;
+        if (k > 63) break;  // corrupt
+        coef[natural[k]] = (int16_t)br.receive_extend(s);
+        last = k;
+        ++k;
+    }
+    return last;
+}
+
+// ---- jidctint.c jpeg_idct_islow ------------------------------------------------------------------------------------
+JPG_HD int32_t descale(int32_t x, int n) { return (x + (1 << (n - 1))) >> n; }
+JPG_HD uint8_t range_limit(int32_t x) {  // sample + CENTERJSAMPLE clamped to 0..255
+    x += 128;
+    return (uint8_t)(x < 0 ? 0 : (x > 255 ? 255 : x));
+}
+
+// coef: 64 quantised coefficients (natural order); quant: 64 quantisation steps (natural order); out: 8 rows of 8 samples.
+JPG_HD void idct_islow(const int16_t* coef, const uint16_t* quant, uint8_t* out, int out_stride) {
+    constexpr int CONST_BITS = 13, PASS1_BITS = 2;
+    constexpr int32_t F_0_298 = 2446, F_0_390 = 3196, F_0_541 = 4433, F_0_765 = 6270, F_0_899 = 7373, F_1_175 = 9633, F_1_501 = 12299,
+                      F_1_847 = 15137, F_1_961 = 16069, F_2_053 = 16819, F_2_562 = 20995, F_3_072 = 25172;
+    int32_t ws[64];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {  // pass 1: columns
+        const int32_t i0 = coef[c] * (int32_t)quant[c], i1 = coef[8 + c] * (int32_t)quant[8 + c], i2 = coef[16 + c] * (int32_t)quant[16 + c],
+                      i3 = coef[24 + c] * (int32_t)quant[24 + c], i4 = coef[32 + c] * (int32_t)quant[32 + c],
+                      i5 = coef[40 + c] * (int32_t)quant[40 + c], i6 = coef[48 + c] * (int32_t)quant[48 + c],
+                      i7 = coef[56 + c] * (int32_t)quant[56 + c];
+        int32_t z2 = i2, z3 = i6;
+        int32_t z1 = (z2 + z3) * F_0_541;
+        int32_t tmp2 = z1 + z3 * (-F_1_847);
+        int32_t tmp3 = z1 + z2 * F_0_765;
+        z2 = i0; z3 = i4;
+        int32_t tmp0 = (z2 + z3) << CONST_BITS;
+        int32_t tmp1 = (z2 - z3) << CONST_BITS;
+        const int32_t tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
+        tmp0 = i7; tmp1 = i5; tmp2 = i3; tmp3 = i1;
+        z1 = tmp0 + tmp3; z2 = tmp1 + tmp2; z3 = tmp0 + tmp2;
+        int32_t z4 = tmp1 + tmp3;
+        const int32_t z5 = (z3 + z4) * F_1_175;
+        tmp0 *= F_0_298; tmp1 *= F_2_053; tmp2 *= F_3_072; tmp3 *= F_1_501;
+        z1 *= -F_0_899; z2 *= -F_2_562; z3 *= -F_1_961; z4 *= -F_0_390;
+        z3 += z5; z4 += z5;
+        tmp0 += z1 + z3; tmp1 += z2 + z4; tmp2 += z2 + z3; tmp3 += z1 + z4;
+        ws[c] = descale(tmp10 + tmp3, CONST_BITS - PASS1_BITS);
+        ws[56 + c] = descale(tmp10 - tmp3, CONST_BITS - PASS1_BITS);
+        ws[8 + c] = descale(tmp11 + tmp2, CONST_BITS - PASS1_BITS);
+        ws[48 + c] = descale(tmp11 - tmp2, CONST_BITS - PASS1_BITS);
+        ws[16 + c] = descale(tmp12 + tmp1, CONST_BITS - PASS1_BITS);
+        ws[40 + c] = descale(tmp12 - tmp1, CONST_BITS - PASS1_BITS);
+        ws[24 + c] = descale(tmp13 + tmp0, CONST_BITS - PASS1_BITS);
+        ws[32 + c] = descale(tmp13 - tmp0, CONST_BITS - PASS1_BITS);
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {  // pass 2: rows
+        const int32_t* w = ws + 8 * r;
+        int32_t z2 = w[2], z3 = w[6];
+        int32_t z1 = (z2 + z3) * F_0_541;
+        int32_t tmp2 = z1 + z3 * (-F_1_847);
+        int32_t tmp3 = z1 + z2 * F_0_765;
+        int32_t tmp0 = (w[0] + w[4]) << CONST_BITS;
+        int32_t tmp1 = (w[0] - w[4]) << CONST_BITS;
+        const int32_t tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
+        tmp0 = w[7]; tmp1 = w[5]; tmp2 = w[3]; tmp3 = w[1];
+        z1 = tmp0 + tmp3; z2 = tmp1 + tmp2; z3 = tmp0 + tmp2;
+        int32_t z4 = tmp1 + tmp3;
+        const int32_t z5 = (z3 + z4) * F_1_175;
+        tmp0 *= F_0_298; tmp1 *= F_2_053; tmp2 *= F_3_072; tmp3 *= F_1_501;
+        z1 *= -F_0_899; z2 *= -F_2_562; z3 *= -F_1_961; z4 *= -F_0_390;
+        z3 += z5; z4 += z5;
+        tmp0 += z1 + z3; tmp1 += z2 + z4; tmp2 += z2 + z3; tmp3 += z1 + z4;
+        constexpr int SH = CONST_BITS + PASS1_BITS + 3;
+        uint8_t* o = out + r * out_stride;
+        o[0] = range_limit(descale(tmp10 + tmp3, SH));
+        o[7] = range_limit(descale(tmp10 - tmp3, SH));
+        o[1] = range_limit(descale(tmp11 + tmp2, SH));
+        o[6] = range_limit(descale(tmp11 - tmp2, SH));
+        o[2] = range_limit(descale(tmp12 + tmp1, SH));
+        o[5] = range_limit(descale(tmp12 - tmp1, SH));
+        o[3] = range_limit(descale(tmp13 + tmp0, SH));
+        o[4] = range_limit(descale(tmp13 - tmp0, SH));
+    }
+}
+
+// ---- jdsample.c h2v2_fancy_upsample + jdcolor.c ycc_rgb_convert -----------------------------------------------------------
+// Chroma sample for output pixel (x, y) from the half-resolution plane `c` (cw x ch real samples, row stride cstride).
+JPG_HD int colsum(const uint8_t* c, int cstride, int ch, int cy, int nb, int i) {
+    (void)ch;
+    return 3 * (int)c[cy * cstride + i] + (int)c[nb * cstride + i];
+}
+JPG_HD int fancy_chroma(const uint8_t* c, int cstride, int cw, int ch, int x, int y) {
+    const int cy = y >> 1;
+    int nb = (y & 1) ? cy + 1 : cy - 1;  // the nearer neighbouring chroma row; the picture's first / last row is replicated
+    nb = nb < 0 ? 0 : (nb > ch - 1 ? ch - 1 : nb);
+    const int i = x >> 1;
+    const int cur = colsum(c, cstride, ch, cy, nb, i);
+    if (!(x & 1)) {
+        if (i == 0) return (cur * 4 + 8) >> 4;
+        return (cur * 3 + colsum(c, cstride, ch, cy, nb, i - 1) + 8) >> 4;
+    }
+    if (i == cw - 1) return (cur * 4 + 7) >> 4;
+    return (cur * 3 + colsum(c, cstride, ch, cy, nb, i + 1) + 7) >> 4;
+}
+JPG_HD uint8_t clamp255(int v) { return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v)); }
+// JFIF YCbCr -> B, G, R exactly like jdcolor.c's tables (SCALEBITS 16)
+JPG_HD void ycc_to_bgr(int y, int cb, int cr, uint8_t* bgr) {
+    cb -= 128; cr -= 128;
+    const int r = y + ((91881 * cr + 32768) >> 16);                   // FIX(1.40200)
+    const int b = y + ((116130 * cb + 32768) >> 16);                  // FIX(1.77200)
+    const int g = y + ((-22554 * cb + 32768 - 46802 * cr) >> 16);     // FIX(0.34414), FIX(0.71414); ONE_HALF sits in Cb_g_tab
+    bgr[0] = clamp255(b);
+    bgr[1] = clamp255(g);
+    bgr[2] = clamp255(r);
+}
+
+}  // namespace esdjpeg

@@ -3,7 +3,8 @@
 Stands where ``cv2.VideoCapture`` stands in the reference's decode loops
 (/root/reference/ml-service/src/services/model_manager.py:237-263) and where the ``ffmpeg -i`` child of the shipped scene task
 stands (:736-755): ``MjpegVideo(path)`` is a video source for :class:`eioku_b200.scene_manager.SceneManager` whose batches
-are CUDA tensors decoded by nvJPEG -- the decoded frames never exist in host memory.  Motion-JPEG in AVI only (NVDEC is
+are CUDA tensors decoded on the GPU -- by this library's own baseline-JPEG kernels (bit-identical to cv2.imdecode) or, for
+streams those do not cover, by nvJPEG -- so the decoded frames never exist in host memory.  Motion-JPEG in AVI only (NVDEC is
 closed to this container, include/esd_decode.h); anything else raises and the caller falls back to its host decoder.
 """
 from __future__ import annotations
@@ -15,8 +16,9 @@ from typing import Optional, Tuple
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libesd_decode.so")
 ESD_DECODE_ABI_VERSION = 1
-ESD_JPEG_AUTO, ESD_JPEG_DEFAULT, ESD_JPEG_GPU_HYBRID, ESD_JPEG_HARDWARE = 0, 1, 2, 3
-BACKEND_NAMES = {ESD_JPEG_DEFAULT: "default", ESD_JPEG_GPU_HYBRID: "gpu_hybrid", ESD_JPEG_HARDWARE: "hardware"}
+ESD_JPEG_AUTO, ESD_JPEG_DEFAULT, ESD_JPEG_GPU_HYBRID, ESD_JPEG_HARDWARE, ESD_JPEG_NATIVE = 0, 1, 2, 3, 4
+# native = this library's own kernels (bit-identical to cv2.imdecode); the others are nvJPEG back ends
+BACKEND_NAMES = {ESD_JPEG_DEFAULT: "default", ESD_JPEG_GPU_HYBRID: "gpu_hybrid", ESD_JPEG_HARDWARE: "hardware", ESD_JPEG_NATIVE: "native"}
 EXPORTED_SYMBOLS = ("esd_decode_abi_version", "esd_mjpeg_last_error", "esd_mjpeg_open", "esd_mjpeg_get_info", "esd_mjpeg_seek",
                     "esd_mjpeg_read", "esd_mjpeg_close")
 

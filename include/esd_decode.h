@@ -14,9 +14,10 @@
  * frame range can be decoded independently -- the frame-range sharding of eioku_b200.multi applies unchanged.
  *
  * Output: dense uint8 BGR24 frames [n][height][width * 3] in a library-owned device buffer (double-buffered), exactly the
- * layout esd_push_frames takes.  nvJPEG's colour conversion is JFIF full-range YCbCr -> BGR like libjpeg's; decoders differ
- * in IDCT / chroma upsampling rounding, so parity is defined on the DECODED surface: download it, run the oracle on it,
- * demand bit-exact sums / scores / cuts (tests/test_gpu_decode.py).
+ * layout esd_push_frames takes.  The NATIVE back end reproduces libjpeg's default arithmetic, so its pictures are bit-identical to
+ * cv2.imdecode's (tests/test_host_jpeg.py on the CPU, tests/test_gpu_decode.py on the device); nvJPEG's differ from libjpeg's in
+ * IDCT / chroma-upsampling rounding (PSNR ~55 dB).  Either way the scoring parity is defined on the DECODED surface: download
+ * it, run the oracle on it, demand bit-exact sums / scores / cuts.
  *
  * Conventions as in esd.h: plain C, POD only, 0 or a negative status, never throws; not thread-safe per handle; several
  * handles (one per thread / GPU) are independent.
@@ -42,8 +43,11 @@ typedef struct esd_mjpeg esd_mjpeg;
 
 enum { ESD_DEC_OK = 0, ESD_DEC_ERR_INVALID = -1, ESD_DEC_ERR_CUDA = -2, ESD_DEC_ERR_IO = -3, ESD_DEC_ERR_FORMAT = -4,
        ESD_DEC_ERR_NVJPEG = -5, ESD_DEC_ERR_UNSUPPORTED = -6 };
-/* nvJPEG back end: AUTO tries HARDWARE, then GPU_HYBRID, then DEFAULT */
-enum { ESD_JPEG_AUTO = 0, ESD_JPEG_DEFAULT = 1, ESD_JPEG_GPU_HYBRID = 2, ESD_JPEG_HARDWARE = 3 };
+/* Decoder back end.  NATIVE = this library's own sm_100a kernels (csrc/jpeg_core.h: Huffman decode, libjpeg's ISLOW IDCT, fancy
+ * h2v2 upsampling, JFIF colour conversion -- bit-identical to cv2.imdecode / libjpeg-turbo) for what ffmpeg and OpenCV write
+ * into MJPEG files: baseline or extended-sequential Huffman, 8-bit, 4:2:0, one interleaved scan.  The others are nvJPEG's.
+ * AUTO tries NATIVE, then HARDWARE, then GPU_HYBRID, then DEFAULT. */
+enum { ESD_JPEG_AUTO = 0, ESD_JPEG_DEFAULT = 1, ESD_JPEG_GPU_HYBRID = 2, ESD_JPEG_HARDWARE = 3, ESD_JPEG_NATIVE = 4 };
 
 typedef struct esd_mjpeg_info {
     int32_t width, height;

@@ -102,6 +102,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--frames", type=int, default=256)
     ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--backends", default="native,hardware,gpu_hybrid,default")
     ap.add_argument("--sessions", default="1,2,4,8")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -114,7 +115,9 @@ def main():
         with decode.MjpegVideo(path, batch_frames=args.batch) as v:
             out["auto_backend"] = v.backend
             out["hw_engines"] = int(v.info.hw_engines)
-        for name, be in (("hardware", decode.ESD_JPEG_HARDWARE), ("gpu_hybrid", decode.ESD_JPEG_GPU_HYBRID), ("default", decode.ESD_JPEG_DEFAULT)):
+        for name, be in (("native", decode.ESD_JPEG_NATIVE), ("hardware", decode.ESD_JPEG_HARDWARE), ("gpu_hybrid", decode.ESD_JPEG_GPU_HYBRID), ("default", decode.ESD_JPEG_DEFAULT)):
+            if name not in args.backends.split(","):
+                continue
             for s in [int(x) for x in args.sessions.split(",")]:
                 for score in (False, True):
                     r = run_sessions(path, s, be, score, args.batch)

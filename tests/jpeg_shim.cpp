@@ -1,0 +1,52 @@
+// Test shim (CPU): runs eioku_b200/csrc/jpeg_core.h + jpeg_parse.h -- the arithmetic of libesd_decode.so's own JPEG decoder --
+// on the host so that tests/test_host_jpeg.py can compare it with cv2.imdecode bit for bit.  Not part of the product.
+#include "../eioku_b200/csrc/jpeg_parse.h"
+
+#include <vector>
+
+using namespace esdjpeg;
+
+extern "C" {
+// returns 0 and fills width / height, or -1 (message in err, 256 bytes)
+int shim_jpeg_info(const uint8_t* data, long n, int* width, int* height, char* err) {
+    JpegHeader h;
+    std::string e;
+    if (!parse_jpeg(data, (size_t)n, &h, &e)) { strncpy(err, e.c_str(), 255); err[255] = 0; return -1; }
+    *width = h.width; *height = h.height;
+    return 0;
+}
+// decodes into out[height][width][3] BGR
+int shim_jpeg_decode(const uint8_t* data, long n, uint8_t* out, char* err) {
+    JpegHeader h;
+    std::string e;
+    if (!parse_jpeg(data, (size_t)n, &h, &e)) { strncpy(err, e.c_str(), 255); err[255] = 0; return -1; }
+    const FrameGeometry g = geometry_of(h);
+    const int yw = g.yblocks_x * 8, yh = g.mcus_y * 16, cw = g.cblocks_x * 8, ch = g.mcus_y * 8;
+    std::vector<uint8_t> Y((size_t)yw * yh), Cb((size_t)cw * ch), Cr((size_t)cw * ch);
+    BitReader br;
+    br.init(data + h.scan_offset, (int)h.scan_len);
+    int pred[3] = {0, 0, 0};
+    int16_t coef[64];
+    int mcu = 0;
+    for (int my = 0; my < g.mcus_y; ++my)
+        for (int mx = 0; mx < g.mcus_x; ++mx, ++mcu) {
+            if (g.restart_interval && mcu && mcu % g.restart_interval == 0) { br.restart(); pred[0] = pred[1] = pred[2] = 0; }
+            for (int b = 0; b < 4; ++b) {
+                memset(coef, 0, sizeof coef);
+                decode_block(br, h.huff.dc[h.td[0]], h.huff.ac[h.ta[0]], kNaturalOrderHost, pred[0], coef);
+                idct_islow(coef, h.quant[h.tq[0]], &Y[(size_t)(my * 16 + (b >> 1) * 8) * yw + mx * 16 + (b & 1) * 8], yw);
+            }
+            for (int c = 1; c < 3; ++c) {
+                memset(coef, 0, sizeof coef);
+                decode_block(br, h.huff.dc[h.td[c]], h.huff.ac[h.ta[c]], kNaturalOrderHost, pred[c], coef);
+                idct_islow(coef, h.quant[h.tq[c]], &(c == 1 ? Cb : Cr)[(size_t)(my * 8) * cw + mx * 8], cw);
+            }
+        }
+    const int rcw = (h.width + 1) / 2, rch = (h.height + 1) / 2;  // real (downsampled) chroma size
+    for (int y = 0; y < h.height; ++y)
+        for (int x = 0; x < h.width; ++x)
+            ycc_to_bgr(Y[(size_t)y * yw + x], fancy_chroma(Cb.data(), cw, rcw, rch, x, y), fancy_chroma(Cr.data(), cw, rcw, rch, x, y),
+                       out + ((size_t)y * h.width + x) * 3);
+    return 0;
+}
+}

@@ -52,9 +52,52 @@ def _decode_all(path, **kw):
         return np.concatenate(out), v.frame_rate, v.backend, v.n_frames
 
 
+def _avi_pictures(path):
+    """The JPEG pictures of an AVI written by cv2.VideoWriter (movi list of 00dc chunks)."""
+    import struct
+
+    b = open(path, "rb").read()
+    i = b.find(b"movi") + 4
+    out = []
+    while i + 8 <= len(b) and b[i:i + 4] in (b"00dc", b"00db"):
+        sz = struct.unpack("<I", b[i + 4:i + 8])[0]
+        out.append(b[i + 8:i + 8 + sz])
+        i += 8 + sz + (sz & 1)
+    return out
+
+
+def test_native_decoder_is_bit_identical_to_cv2_imdecode(mjpeg_clip, tmp_path):
+    """The library's own kernels (Huffman decode, libjpeg's ISLOW IDCT, fancy upsampling, JFIF colour conversion) against the
+    real reference decoder, picture by picture, every byte: the decoder itself is pinned, not only the scoring behind it."""
+    path, src = mjpeg_clip
+    got, fps, backend, n = _decode_all(path, batch_frames=40, backend=decode.ESD_JPEG_NATIVE)
+    assert backend == "native" and got.shape == src.shape and fps == 25.0
+    pics = _avi_pictures(path)
+    assert len(pics) == n
+    for k, jpg in enumerate(pics):
+        want = cv2.imdecode(np.frombuffer(jpg, np.uint8), cv2.IMREAD_COLOR)
+        assert np.array_equal(got[k], want), (k, int(np.abs(got[k].astype(int) - want.astype(int)).max()))
+    # AUTO picks the native decoder for such a file; odd sizes (not multiples of 16 / 2 / 4) and a low quality go through it too
+    with decode.MjpegVideo(path) as v:
+        assert v.backend == "native"
+    rng = np.random.default_rng(3)
+    for (w, h, q) in ((322, 182, 95), (53, 37, 60), (1280, 720, 30)):
+        frames = [cv2.resize(rng.integers(0, 256, (5, 7, 3), dtype=np.uint8), (w, h), interpolation=cv2.INTER_CUBIC) for _ in range(5)]
+        frames = [np.clip(f.astype(int) + rng.integers(-8, 9, f.shape), 0, 255).astype(np.uint8) for f in frames]
+        p2 = str(tmp_path / f"odd_{w}x{h}.avi")
+        wr = cv2.VideoWriter(p2, cv2.VideoWriter_fourcc(*"MJPG"), 30.0, (w, h))
+        wr.set(cv2.VIDEOWRITER_PROP_QUALITY, q)
+        for f in frames:
+            wr.write(f)
+        wr.release()
+        dec, *_ = _decode_all(p2, batch_frames=3, backend=decode.ESD_JPEG_NATIVE)
+        for k, jpg in enumerate(_avi_pictures(p2)):
+            assert np.array_equal(dec[k], cv2.imdecode(np.frombuffer(jpg, np.uint8), cv2.IMREAD_COLOR)), (w, h, k)
+
+
 def test_decoder_decodes_the_right_pictures(mjpeg_clip):
     path, src = mjpeg_clip
-    got, fps, backend, n = _decode_all(path, batch_frames=32)
+    got, fps, backend, n = _decode_all(path, batch_frames=32, backend=decode.ESD_JPEG_GPU_HYBRID)
     assert got.shape == src.shape and n == src.shape[0] and fps == 25.0 and backend in ("hardware", "gpu_hybrid", "default")
     cap = cv2.VideoCapture(path)
     ref = []
@@ -88,7 +131,8 @@ class _Tee:
         return torch.cat(self.kept).cpu().numpy()
 
 
-def test_parity_on_the_decoded_surface(mjpeg_clip):
+@pytest.mark.parametrize("backend", [decode.ESD_JPEG_NATIVE, decode.ESD_JPEG_GPU_HYBRID])
+def test_parity_on_the_decoded_surface(mjpeg_clip, backend):
     """The frames the scoring kernels read are downloaded (a device-side copy made between decode and scoring) and the
     oracle runs on exactly those: integer sums, float64 scores, histograms' differences and cut lists bit-exact."""
     path, _ = mjpeg_clip
@@ -96,7 +140,7 @@ def test_parity_on_the_decoded_surface(mjpeg_clip):
     dets = [ContentDetector(min_scene_len=10), AdaptiveDetector(window_width=2, min_scene_len=10), HistogramDetector(min_scene_len=10)]
     for d in dets:
         sm.add_detector(d)
-    with decode.MjpegVideo(path, batch_frames=48) as v:
+    with decode.MjpegVideo(path, batch_frames=48, backend=backend) as v:
         tee = _Tee(v)
         n = sm.detect_scenes(tee, collect_scores=True)
         decoded = tee.frames()
@@ -115,9 +159,11 @@ def test_parity_on_the_decoded_surface(mjpeg_clip):
     sm.close()
     # how repeatable is the decoder itself?  (reported, not asserted: nvJPEG does not promise bit-identical output across
     # batch compositions; parity above never depends on it)
-    again, *_ = _decode_all(path, batch_frames=48)
-    other, *_ = _decode_all(path, batch_frames=64)
-    print(f"nvJPEG repeatability: same batching differs in {int((again != decoded).sum())} bytes, "
+    again, *_ = _decode_all(path, batch_frames=48, backend=backend)
+    other, *_ = _decode_all(path, batch_frames=64, backend=backend)
+    if backend == decode.ESD_JPEG_NATIVE:  # the library's own decoder is deterministic whatever the batching
+        assert np.array_equal(again, decoded) and np.array_equal(other, decoded)
+    print(f"backend {backend} repeatability: same batching differs in {int((again != decoded).sum())} bytes, "
           f"other batching in {int((other != decoded).sum())} of {decoded.size} bytes (max |delta| {int(np.abs(other.astype(int) - decoded.astype(int)).max())})")
 
 

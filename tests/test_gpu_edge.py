@@ -242,3 +242,29 @@ def test_bad_frame_pointers_are_rejected_before_launch():
         ctx.push_device(pinned.data_ptr(), 2, pinned.stride(0), pinned.stride(1), 3)  # pinned host memory is reachable (zero-copy)
         assert ctx.read_scores(3, 2)["sums3"][1].tolist() == [0, 0, 0]
         del own
+
+
+@pytest.mark.parametrize("w,h,dst", [(322, 182, (129, 73)), (4, 3, None), (5, 2, None), (1280, 36, (256, 7))])
+def test_every_base_misalignment_and_odd_pitch(w, h, dst):
+    """Frames whose first byte sits at each of the 16 residues mod 16 (15 included), with a row pitch and a frame stride
+    that are not multiples of 16 and -- for the tiny geometries -- rows shorter than one 16-byte bulk-copy unit."""
+    n = 5
+    rng = np.random.default_rng(w * 7 + h)
+    fr = rng.integers(0, 256, (n, h, w, 3), dtype=np.uint8)
+    dw, dh = dst if dst else (w, h)
+    sums, hist, cv, hd = oracle_scores(fr, dw, dh)
+    pitch = w * 3 + (1 if (w * 3) % 2 == 0 else 2)          # odd
+    fs = h * pitch + 7
+    dev_fr = torch.from_numpy(fr).to(DEV).view(n, h, w * 3)
+    for off in range(16):
+        raw = torch.zeros(off + n * fs + 64, dtype=torch.uint8, device=DEV)
+        assert raw.data_ptr() % 256 == 0
+        frames = raw[off:off + n * fs].view(n, fs)
+        for r in range(h):
+            frames[:, r * pitch: r * pitch + w * 3] = dev_fr[:, r]
+        with make_ctx(w, h, (dw, dh)) as ctx:
+            ctx.push_device(raw.data_ptr() + off, n, fs, pitch, 0, torch.cuda.current_stream().cuda_stream)
+            sc = ctx.read_scores(0, n)
+        assert np.array_equal(sc["sums3"].astype(np.int64), sums), off
+        assert np.array_equal(sc["hist"], hist), off
+        assert same_f64(sc["content_val"], cv) and same_f64(sc["hist_diff"], hd), off

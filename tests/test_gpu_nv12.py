@@ -211,3 +211,40 @@ def test_nv12_clip_vs_committed_cv2_golden():
     assert sm.cuts_of(dets[1]) == g["cuts_adaptive"].tolist()
     assert sm.cuts_of(dets[2]) == g["cuts_hist"].tolist()
     sm.close()
+
+
+@pytest.mark.parametrize("oy,ouv", [(0, 15), (15, 0), (15, 15), (7, 9), (1, 2), (8, 4), (3, 12)])
+def test_nv12_every_plane_misalignment(oy, ouv):
+    """memory safety rests on parity over ragged layouts.  Y plane starting at byte residue `oy` and UV
+    plane at residue `ouv` (mod 16), an odd row pitch, a frame stride that is not a multiple of 16: the bulk copies are
+    rounded to 16-byte boundaries and the misalignments travel in the stage metadata -- results must equal the dense case."""
+    w, h, n = 322, 182, 6
+    rng = np.random.default_rng(oy * 16 + ouv)
+    nv12 = rng.integers(0, 256, (n, h * 3 // 2, w), dtype=np.uint8)
+    with nv12_ctx(w, h, (129, 73)) as ctx:
+        ctx.push_nv12_tensor(torch.from_numpy(nv12).to(DEV), 0)
+        want = ctx.read_scores(0, n)
+    pitch = w + 3                                   # odd pitch: every row has another residue
+    gap = (ouv - (oy + h * pitch)) % 16             # puts the UV plane's first byte at residue ouv
+    fs = oy + h * pitch + gap + (h // 2) * pitch + 5   # frame stride, not a multiple of 16 in general
+    raw = torch.zeros(n * fs + 64, dtype=torch.uint8, device=DEV)
+    base = raw.data_ptr()
+    assert base % 256 == 0
+    frames = raw[:n * fs].view(n, fs)
+    y = torch.from_numpy(nv12[:, :h]).to(DEV)
+    uv = torch.from_numpy(nv12[:, h:]).to(DEV)
+    for r in range(h):
+        frames[:, oy + r * pitch: oy + r * pitch + w] = y[:, r]
+    uv0 = oy + h * pitch + gap
+    for r in range(h // 2):
+        frames[:, uv0 + r * pitch: uv0 + r * pitch + w] = uv[:, r]
+    assert (base + oy) % 16 == oy and (base + uv0) % 16 == ouv
+    with nv12_ctx(w, h, (129, 73)) as ctx:
+        ctx.push_nv12_device(base + oy, base + uv0, n, fs, pitch, 0, torch.cuda.current_stream().cuda_stream)
+        got = ctx.read_scores(0, n)
+        hsv = ctx.debug_last_hsv()
+    for k in want:
+        assert np.array_equal(np.nan_to_num(got[k], nan=-1), np.nan_to_num(want[k], nan=-1)), k
+    bgr = to_bgr(nv12)
+    sums, hist, last_hsv = co.score_frames(bgr, 129, 73, bins=256)
+    assert np.array_equal(got["sums3"].astype(np.int64), sums) and np.array_equal(hsv, last_hsv)
