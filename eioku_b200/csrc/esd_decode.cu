@@ -64,11 +64,9 @@ struct esd_mjpeg {
     int tq[3] = {0, 0, 0}, td[3] = {0, 0, 0}, ta[3] = {0, 0, 0};
     int blocks_per_frame = 0;
     size_t plane_bytes = 0;                      // Y + Cb + Cr sample planes of one frame (MCU-padded)
-    std::map<std::string, int> huff_sets;        // DHT bytes -> index into d_huff
-    esdjpeg::ScanTables* d_huff = nullptr;       // [kMaxHuffSets]
     uint8_t* d_comp = nullptr;                   // compressed pictures of the batch
     size_t d_comp_bytes = 0;
-    struct NativeDesc { uint32_t off, len; int32_t huff_set, pad; };
+    struct NativeDesc { uint32_t off, len; uint32_t dht[4]; uint16_t nvals[4]; };  // dht / nvals: DC0, DC1, AC0, AC1 (offset of the 16 counts in the staging block; 0 = table absent)
     NativeDesc* d_desc = nullptr;                // [batch]
     uint16_t* d_quant = nullptr;                 // [batch][3][64] natural order, per component
     int16_t* d_coef = nullptr;                   // [batch][blocks_per_frame][64]
@@ -160,7 +158,6 @@ nvjpegBackend_t nj_backend(int b) {
 //   jpeg_color_kernel    one thread per four pixels: fancy h2v2 chroma upsampling + JFIF YCbCr -> BGR24, written in the
 //                        dense layout esd_push_frames reads.
 namespace {
-constexpr int kMaxHuffSets = 16;
 __constant__ uint8_t c_natural_order[64] = ESD_JPEG_NATURAL_ORDER;
 
 struct NativeLayout {
@@ -172,12 +169,27 @@ struct NativeLayout {
     unsigned long long plane_bytes;
 };
 
-__global__ void jpeg_entropy_kernel(NativeLayout L, const uint8_t* __restrict__ stage, const esd_mjpeg::NativeDesc* __restrict__ desc,
-                                    const esdjpeg::ScanTables* __restrict__ huff, int16_t* __restrict__ coef) {
-    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+// ffmpeg's encoder optimises the Huffman tables PER PICTURE, so every thread builds the decoding tables of its own picture from
+// the picture's DHT segments -- into its own 5.7 KB slice of shared memory (32 pictures = 178 KB per block, one block per SM):
+// every symbol costs a dependent table look-up, and from global memory that latency would dominate the kernel.
+constexpr int kEntropyThreads = 32;
+__global__ void __launch_bounds__(kEntropyThreads) jpeg_entropy_kernel(NativeLayout L, const uint8_t* __restrict__ stage,
+                                                                       const esd_mjpeg::NativeDesc* __restrict__ desc, int16_t* __restrict__ coef) {
+    extern __shared__ __align__(16) uint8_t ent_smem[];
+    __shared__ uint8_t s_nat[64];
+    esdjpeg::ScanTables* tabs = reinterpret_cast<esdjpeg::ScanTables*>(ent_smem);
+    for (int i = threadIdx.x; i < 64; i += kEntropyThreads) s_nat[i] = c_natural_order[i];
+    __syncthreads();
+    const int f = blockIdx.x * kEntropyThreads + threadIdx.x;
     if (f >= L.n) return;
     const esd_mjpeg::NativeDesc d = desc[f];
-    const esdjpeg::ScanTables& T = huff[d.huff_set];
+    esdjpeg::ScanTables& T = tabs[threadIdx.x];
+    bool ok = true;
+    for (int t = 0; t < 4; ++t) {
+        esdjpeg::HuffTable* tb = t < 2 ? &T.dc[t] : &T.ac[t - 2];
+        if (d.dht[t]) ok = esdjpeg::build_huff_table(stage + d.dht[t], stage + d.dht[t] + 16, (int)d.nvals[t], tb) && ok;
+    }
+    if (!ok) return;  // the host validated the tables; a picture that still fails decodes to zero coefficients (mid-grey)
     esdjpeg::BitReader br;
     br.init(stage + d.off, (int)d.len);
     int pred[3] = {0, 0, 0};
@@ -185,16 +197,21 @@ __global__ void jpeg_entropy_kernel(NativeLayout L, const uint8_t* __restrict__ 
     const int ybx = 2 * L.mcus_x;
     int16_t* cb = cf + (size_t)4 * L.mcus_x * L.mcus_y * 64;
     int16_t* cr = cb + (size_t)L.mcus_x * L.mcus_y * 64;
+    const esdjpeg::HuffTable& ydc = T.dc[L.td[0]];
+    const esdjpeg::HuffTable& yac = T.ac[L.ta[0]];
+    const esdjpeg::HuffTable& bdc = T.dc[L.td[1]];
+    const esdjpeg::HuffTable& bac = T.ac[L.ta[1]];
+    const esdjpeg::HuffTable& rdc = T.dc[L.td[2]];
+    const esdjpeg::HuffTable& rac = T.ac[L.ta[2]];
     int mcu = 0;
     for (int my = 0; my < L.mcus_y; ++my)
         for (int mx = 0; mx < L.mcus_x; ++mx, ++mcu) {
             if (L.restart_interval && mcu && mcu % L.restart_interval == 0) { br.restart(); pred[0] = pred[1] = pred[2] = 0; }
 #pragma unroll
             for (int b = 0; b < 4; ++b)
-                esdjpeg::decode_block(br, T.dc[L.td[0]], T.ac[L.ta[0]], c_natural_order, pred[0],
-                                      cf + ((size_t)(2 * my + (b >> 1)) * ybx + 2 * mx + (b & 1)) * 64);
-            esdjpeg::decode_block(br, T.dc[L.td[1]], T.ac[L.ta[1]], c_natural_order, pred[1], cb + ((size_t)my * L.mcus_x + mx) * 64);
-            esdjpeg::decode_block(br, T.dc[L.td[2]], T.ac[L.ta[2]], c_natural_order, pred[2], cr + ((size_t)my * L.mcus_x + mx) * 64);
+                esdjpeg::decode_block(br, ydc, yac, s_nat, pred[0], cf + ((size_t)(2 * my + (b >> 1)) * ybx + 2 * mx + (b & 1)) * 64);
+            esdjpeg::decode_block(br, bdc, bac, s_nat, pred[1], cb + ((size_t)my * L.mcus_x + mx) * 64);
+            esdjpeg::decode_block(br, rdc, rac, s_nat, pred[2], cr + ((size_t)my * L.mcus_x + mx) * 64);
         }
 }
 
@@ -287,7 +304,7 @@ void esd_mjpeg_close(esd_mjpeg* h) {
         cudaFree(h->d_out[b]);
         if (h->h_stage[b]) cudaFreeHost(h->h_stage[b]);
     }
-    cudaFree(h->d_huff); cudaFree(h->d_comp); cudaFree(h->d_coef); cudaFree(h->d_planes);
+    cudaFree(h->d_comp); cudaFree(h->d_coef); cudaFree(h->d_planes);
     if (h->state) nvjpegJpegStateDestroy(h->state);
     if (h->nj) nvjpegDestroy(h->nj);
     if (h->map) munmap(const_cast<uint8_t*>(h->map), h->map_bytes);
@@ -347,7 +364,7 @@ int esd_mjpeg_open(esd_mjpeg** out, const char* path, int device, int32_t batch_
             for (int c = 0; c < 3; ++c) { h->tq[c] = jh.tq[c]; h->td[c] = jh.td[c]; h->ta[c] = jh.ta[c]; }
             h->blocks_per_frame = 6 * h->geo.mcus_x * h->geo.mcus_y;
             h->plane_bytes = (size_t)(h->geo.mcus_x * 16) * (h->geo.mcus_y * 16) * 3 / 2;
-            cudaError_t e = cudaMalloc(&h->d_huff, sizeof(esdjpeg::ScanTables) * kMaxHuffSets);
+            cudaError_t e = cudaFuncSetAttribute(jpeg_entropy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kEntropyThreads * sizeof(esdjpeg::ScanTables)));
             if (e == cudaSuccess) e = cudaMalloc(&h->d_coef, (size_t)h->batch * h->blocks_per_frame * 64 * sizeof(int16_t));
             if (e == cudaSuccess) e = cudaMalloc(&h->d_planes, (size_t)h->batch * h->plane_bytes);
             if (e != cudaSuccess) {
@@ -464,22 +481,14 @@ int esd_mjpeg_read(esd_mjpeg* h, int64_t max_frames, void* stream, uint8_t** d_b
             bool same = jh.width == h->width && jh.height == h->height && jh.restart_interval == h->geo.restart_interval;
             for (int c = 0; c < 3; ++c) same = same && jh.td[c] == h->td[c] && jh.ta[c] == h->ta[c];
             if (!same) return fail(h, ESD_DEC_ERR_UNSUPPORTED, "picture %lld changes the stream's geometry / table selectors", (long long)(h->pos + i));
-            auto it = h->huff_sets.find(jh.dht_bytes);
-            if (it == h->huff_sets.end()) {
-                if ((int)h->huff_sets.size() >= kMaxHuffSets)
-                    return fail(h, ESD_DEC_ERR_UNSUPPORTED, "more than %d distinct Huffman table sets in one file", kMaxHuffSets);
-                esdjpeg::JpegHeader full;
-                if (!esdjpeg::parse_jpeg(pic, p.size, &full, &why, true)) return fail(h, ESD_DEC_ERR_UNSUPPORTED, "picture %lld: %s", (long long)(h->pos + i), why.c_str());
-                const int idx = (int)h->huff_sets.size();
-                // synchronous upload of a new table set (once per file for constant tables): nothing in flight reads this slot yet
-                if (cudaMemcpy(h->d_huff + idx, &full.huff, sizeof(esdjpeg::ScanTables), cudaMemcpyHostToDevice) != cudaSuccess)
-                    return fail(h, ESD_DEC_ERR_CUDA, "Huffman table upload failed");
-                it = h->huff_sets.emplace(jh.dht_bytes, idx).first;
-            }
             hdesc[i].off = (uint32_t)(off + jh.scan_offset);
             hdesc[i].len = (uint32_t)jh.scan_len;
-            hdesc[i].huff_set = it->second;
-            hdesc[i].pad = 0;
+            for (int t = 0; t < 4; ++t) {  // DC0, DC1, AC0, AC1: where the picture's own tables start (built on the device)
+                const int tc = t >> 1, id = t & 1;
+                const bool have = tc ? jh.have_ac[id] : jh.have_dc[id];
+                hdesc[i].dht[t] = have ? (uint32_t)(off + jh.dht_pos[tc][id]) : 0u;
+                hdesc[i].nvals[t] = (uint16_t)(have ? jh.dht_nvals[tc][id] : 0);
+            }
             for (int c = 0; c < 3; ++c) memcpy(hquant + ((size_t)i * 3 + c) * 64, jh.quant[jh.tq[c]], 64 * sizeof(uint16_t));
         } else {
             h->ptrs[i] = h->h_stage[b] + off;
@@ -509,7 +518,8 @@ int esd_mjpeg_read(esd_mjpeg* h, int64_t max_frames, void* stream, uint8_t** d_b
         if (e != cudaSuccess) return fail(h, ESD_DEC_ERR_CUDA, "native decode: staging copy failed: %s", cudaGetErrorString(e));
         const esd_mjpeg::NativeDesc* ddesc = reinterpret_cast<const esd_mjpeg::NativeDesc*>(h->d_comp);
         const uint16_t* dquant = reinterpret_cast<const uint16_t*>(h->d_comp + (size_t)n * sizeof(esd_mjpeg::NativeDesc));
-        jpeg_entropy_kernel<<<(unsigned)((n + 31) / 32), 32, 0, st>>>(L, h->d_comp, ddesc, h->d_huff, h->d_coef);
+        jpeg_entropy_kernel<<<(unsigned)((n + kEntropyThreads - 1) / kEntropyThreads), kEntropyThreads, kEntropyThreads * sizeof(esdjpeg::ScanTables), st>>>(
+            L, h->d_comp, ddesc, h->d_coef);
         jpeg_idct_kernel<<<dim3((unsigned)((h->blocks_per_frame + 127) / 128), (unsigned)n), 128, 0, st>>>(L, h->d_coef, dquant, h->d_planes);
         jpeg_color_kernel<<<dim3((unsigned)(((h->width + 3) / 4 + 255) / 256), (unsigned)h->height, (unsigned)n), 256, 0, st>>>(L, h->d_planes, h->d_out[b]);
         e = cudaGetLastError();

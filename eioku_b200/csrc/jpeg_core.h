@@ -53,7 +53,7 @@ struct FrameGeometry {
 };
 
 // Builds `t` from the DHT payload (16 counts + values).  Returns false for an invalid table.
-inline bool build_huff_table(const uint8_t* counts, const uint8_t* vals, int nvals, HuffTable* t) {
+JPG_HD bool build_huff_table(const uint8_t* counts, const uint8_t* vals, int nvals, HuffTable* t) {
     int total = 0;
     for (int i = 0; i < 16; ++i) total += counts[i];
     if (total > 256 || total != nvals) return false;

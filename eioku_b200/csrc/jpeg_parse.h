@@ -20,6 +20,8 @@ struct JpegHeader {
     int td[3] = {0, 0, 0}, ta[3] = {0, 0, 0};
     ScanTables huff;
     bool have_dc[2] = {false, false}, have_ac[2] = {false, false};
+    size_t dht_pos[2][2] = {{0, 0}, {0, 0}};  // [class: 0 DC, 1 AC][table id]: offset of the 16 code-length counts inside the picture
+    int dht_nvals[2][2] = {{0, 0}, {0, 0}};   // number of symbol values that follow the counts
     int restart_interval = 0;
     size_t scan_offset = 0, scan_len = 0;  // entropy-coded data inside the picture's bytes
     // raw DHT payload bytes concatenated: pictures of one file are compared by these to share device tables
@@ -66,6 +68,13 @@ inline bool parse_jpeg(const uint8_t* d, size_t n, JpegHeader* h, std::string* e
                 int total = 0;
                 for (int i = 0; i < 16; ++i) total += s[q + 1 + i];
                 if (tc > 1 || t > 1 || q + 17 + total > sl) return fail("bad DHT (baseline allows tables 0 and 1)");
+                {   // cheap validity check (Kraft inequality) for tables that are built elsewhere (on the device)
+                    int code = 0;
+                    for (int i = 0; i < 16; ++i) { code = (code + s[q + 1 + i]) << 1; if (code > (2 << (i + 1))) return fail("over-subscribed Huffman table"); }
+                    if (total > 256) return fail("bad DHT");
+                }
+                h->dht_pos[tc][t] = (size_t)(s - d) + q + 1;
+                h->dht_nvals[tc][t] = total;
                 HuffTable* tb = tc ? &h->huff.ac[t] : &h->huff.dc[t];
                 if (build_huff && !build_huff_table(s + q + 1, s + q + 17, total, tb)) return fail("invalid Huffman table");
                 (tc ? h->have_ac : h->have_dc)[t] = true;
