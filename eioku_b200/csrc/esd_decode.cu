@@ -63,6 +63,7 @@ struct esd_mjpeg {
     esdjpeg::FrameGeometry geo{};
     int tq[3] = {0, 0, 0}, td[3] = {0, 0, 0}, ta[3] = {0, 0, 0};
     int blocks_per_frame = 0;
+    bool flat = false;                           // no restart interval: the host removes the byte stuffing and the flat scan decoder runs
     size_t plane_bytes = 0;                      // Y + Cb + Cr sample planes of one frame (MCU-padded)
     uint8_t* d_comp = nullptr;                   // compressed pictures of the batch
     size_t d_comp_bytes = 0;
@@ -215,6 +216,31 @@ __global__ void __launch_bounds__(kEntropyThreads) jpeg_entropy_kernel(NativeLay
         }
 }
 
+// Fast path (no restart markers, byte stuffing removed by the host while it stages the picture): the flat, branch-uniform scan
+// decoder of jpeg_core.h -- a warp walks 32 pictures in lock-step, one Huffman symbol per iteration.
+__global__ void __launch_bounds__(kEntropyThreads) jpeg_entropy_flat_kernel(NativeLayout L, const uint8_t* __restrict__ stage,
+                                                                            const esd_mjpeg::NativeDesc* __restrict__ desc,
+                                                                            int16_t* __restrict__ coef) {
+    extern __shared__ __align__(16) uint8_t ent_smem[];
+    __shared__ uint8_t s_nat[64];
+    esdjpeg::ScanTables* tabs = reinterpret_cast<esdjpeg::ScanTables*>(ent_smem);
+    for (int i = threadIdx.x; i < 64; i += kEntropyThreads) s_nat[i] = c_natural_order[i];
+    __syncthreads();
+    const int f = blockIdx.x * kEntropyThreads + threadIdx.x;
+    if (f >= L.n) return;
+    const esd_mjpeg::NativeDesc d = desc[f];
+    esdjpeg::ScanTables& T = tabs[threadIdx.x];
+    bool ok = true;
+    for (int t = 0; t < 4; ++t) {
+        esdjpeg::HuffTable* tb = t < 2 ? &T.dc[t] : &T.ac[t - 2];
+        if (d.dht[t]) ok = esdjpeg::build_huff_table(stage + d.dht[t], stage + d.dht[t] + 16, (int)d.nvals[t], tb) && ok;
+    }
+    if (!ok) return;
+    const int td[3] = {L.td[0], L.td[1], L.td[2]}, ta[3] = {L.ta[0], L.ta[1], L.ta[2]};
+    esdjpeg::decode_scan_flat(reinterpret_cast<const uint32_t*>(stage + d.off), (int)d.len, T, td, ta, s_nat, L.mcus_x, L.mcus_y,
+                              coef + (size_t)f * L.blocks_per_frame * 64);
+}
+
 __global__ void __launch_bounds__(128) jpeg_idct_kernel(NativeLayout L, const int16_t* __restrict__ coef, const uint16_t* __restrict__ quant,
                                                         uint8_t* __restrict__ planes) {
     const int blk = blockIdx.x * blockDim.x + threadIdx.x;
@@ -364,7 +390,9 @@ int esd_mjpeg_open(esd_mjpeg** out, const char* path, int device, int32_t batch_
             for (int c = 0; c < 3; ++c) { h->tq[c] = jh.tq[c]; h->td[c] = jh.td[c]; h->ta[c] = jh.ta[c]; }
             h->blocks_per_frame = 6 * h->geo.mcus_x * h->geo.mcus_y;
             h->plane_bytes = (size_t)(h->geo.mcus_x * 16) * (h->geo.mcus_y * 16) * 3 / 2;
+            h->flat = jh.restart_interval == 0;
             cudaError_t e = cudaFuncSetAttribute(jpeg_entropy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kEntropyThreads * sizeof(esdjpeg::ScanTables)));
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(jpeg_entropy_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kEntropyThreads * sizeof(esdjpeg::ScanTables)));
             if (e == cudaSuccess) e = cudaMalloc(&h->d_coef, (size_t)h->batch * h->blocks_per_frame * 64 * sizeof(int16_t));
             if (e == cudaSuccess) e = cudaMalloc(&h->d_planes, (size_t)h->batch * h->plane_bytes);
             if (e != cudaSuccess) {
@@ -452,7 +480,7 @@ int esd_mjpeg_read(esd_mjpeg* h, int64_t max_frames, void* stream, uint8_t** d_b
     // pinned staging of the batch: [descriptors n x 16][quantisation tables n x 3 x 64 x u16][pictures, 64-byte aligned]
     const size_t meta = native ? (((size_t)n * sizeof(esd_mjpeg::NativeDesc) + (size_t)n * 3 * 64 * sizeof(uint16_t) + 63) & ~(size_t)63) : 0;
     size_t total = meta;
-    for (int64_t i = 0; i < n; ++i) total += ((size_t)h->pics[h->pos + i].size + 63) & ~(size_t)63;
+    for (int64_t i = 0; i < n; ++i) total += ((size_t)h->pics[h->pos + i].size + 16 + 63) & ~(size_t)63;
     total += 64;  // the entropy kernel's four-byte look-ahead may read past the last picture
     if (total > h->h_stage_bytes[b]) {
         if (h->h_stage[b]) cudaFreeHost(h->h_stage[b]);
@@ -470,14 +498,28 @@ int esd_mjpeg_read(esd_mjpeg* h, int64_t max_frames, void* stream, uint8_t** d_b
     for (int64_t i = 0; i < n; ++i) {
         const Picture& p = h->pics[h->pos + i];
         if (p.offset + p.size > h->map_bytes) return fail(h, ESD_DEC_ERR_FORMAT, "picture %lld lies outside the file", (long long)(h->pos + i));
-        memcpy(h->h_stage[b] + off, h->map + p.offset, p.size);
+        if (!native) memcpy(h->h_stage[b] + off, h->map + p.offset, p.size);
         if (native) {
-            // header walk on the host (a few markers); the Huffman tables are built only for a DHT not seen before in this file
+            // header walk on the host (a few markers); the Huffman tables are built on the device from the picture's own DHT
             esdjpeg::JpegHeader jh;
             std::string why;
-            const uint8_t* pic = h->h_stage[b] + off;
+            const uint8_t* pic = h->map + p.offset;
             if (!esdjpeg::parse_jpeg(pic, p.size, &jh, &why, false))
                 return fail(h, ESD_DEC_ERR_UNSUPPORTED, "picture %lld: %s", (long long)(h->pos + i), why.c_str());
+            if (h->flat) {
+                // staged: [headers up to the scan][scan with the byte stuffing removed, on a 4-byte boundary, zero padded]
+                memcpy(h->h_stage[b] + off, pic, jh.scan_offset);
+                const size_t so = (jh.scan_offset + 3) & ~(size_t)3;
+                bool clean = true;
+                const size_t nb = esdjpeg::unstuff_scan(pic + jh.scan_offset, jh.scan_len, h->h_stage[b] + off + so, &clean);
+                if (!clean) return fail(h, ESD_DEC_ERR_UNSUPPORTED, "picture %lld carries restart markers without a restart interval", (long long)(h->pos + i));
+                const size_t padded = (nb + 3 + 8) & ~(size_t)3;  // two zero words behind the data
+                memset(h->h_stage[b] + off + so + nb, 0, padded - nb);
+                jh.scan_offset = so;
+                jh.scan_len = padded / 4;  // words
+            } else {
+                memcpy(h->h_stage[b] + off, pic, p.size);
+            }
             bool same = jh.width == h->width && jh.height == h->height && jh.restart_interval == h->geo.restart_interval;
             for (int c = 0; c < 3; ++c) same = same && jh.td[c] == h->td[c] && jh.ta[c] == h->ta[c];
             if (!same) return fail(h, ESD_DEC_ERR_UNSUPPORTED, "picture %lld changes the stream's geometry / table selectors", (long long)(h->pos + i));
@@ -497,7 +539,7 @@ int esd_mjpeg_read(esd_mjpeg* h, int64_t max_frames, void* stream, uint8_t** d_b
             h->imgs[i].channel[0] = h->d_out[b] + (size_t)i * frame_bytes;
             h->imgs[i].pitch[0] = (size_t)h->width * 3;
         }
-        off += ((size_t)p.size + 63) & ~(size_t)63;
+        off += ((size_t)p.size + 16 + 63) & ~(size_t)63;
     }
     if (native) {
         if (total > h->d_comp_bytes) {  // device mirror of the staging block (grow-only; everything that used it ran on `st` before)
@@ -518,8 +560,10 @@ int esd_mjpeg_read(esd_mjpeg* h, int64_t max_frames, void* stream, uint8_t** d_b
         if (e != cudaSuccess) return fail(h, ESD_DEC_ERR_CUDA, "native decode: staging copy failed: %s", cudaGetErrorString(e));
         const esd_mjpeg::NativeDesc* ddesc = reinterpret_cast<const esd_mjpeg::NativeDesc*>(h->d_comp);
         const uint16_t* dquant = reinterpret_cast<const uint16_t*>(h->d_comp + (size_t)n * sizeof(esd_mjpeg::NativeDesc));
-        jpeg_entropy_kernel<<<(unsigned)((n + kEntropyThreads - 1) / kEntropyThreads), kEntropyThreads, kEntropyThreads * sizeof(esdjpeg::ScanTables), st>>>(
-            L, h->d_comp, ddesc, h->d_coef);
+        const unsigned egrid = (unsigned)((n + kEntropyThreads - 1) / kEntropyThreads);
+        const size_t esmem = kEntropyThreads * sizeof(esdjpeg::ScanTables);
+        if (h->flat) jpeg_entropy_flat_kernel<<<egrid, kEntropyThreads, esmem, st>>>(L, h->d_comp, ddesc, h->d_coef);
+        else jpeg_entropy_kernel<<<egrid, kEntropyThreads, esmem, st>>>(L, h->d_comp, ddesc, h->d_coef);
         jpeg_idct_kernel<<<dim3((unsigned)((h->blocks_per_frame + 127) / 128), (unsigned)n), 128, 0, st>>>(L, h->d_coef, dquant, h->d_planes);
         jpeg_color_kernel<<<dim3((unsigned)(((h->width + 3) / 4 + 255) / 256), (unsigned)h->height, (unsigned)n), 256, 0, st>>>(L, h->d_planes, h->d_out[b]);
         e = cudaGetLastError();

@@ -12,6 +12,7 @@
 // parser and those files go to nvJPEG or to the host decoder.
 #pragma once
 #include <stdint.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define JPG_HD __host__ __device__ __forceinline__
@@ -37,6 +38,7 @@ struct HuffTable {
     uint16_t look[1 << kLookBits];  // (code length << 8) | symbol for codes of <= kLookBits bits, 0 = longer code
     int32_t maxcode[18];            // largest code of each length (-1 = none); [17] = sentinel
     int32_t valoffset[17];          // huffval index of the first code of each length, minus that code
+    uint32_t limit[17];             // left-aligned 16-bit windows below limit[L] hold a code of at most L bits (canonical codes)
     uint8_t huffval[256];
 };
 
@@ -77,10 +79,12 @@ JPG_HD bool build_huff_table(const uint8_t* counts, const uint8_t* vals, int nva
         } else {
             t->maxcode[len] = -1;
         }
+        t->limit[len] = (uint32_t)code << (16 - len);
         code <<= 1;
     }
     t->maxcode[0] = -1;
     t->valoffset[0] = 0;
+    t->limit[0] = 0;
     t->maxcode[17] = 0x7fffffff;
     return true;
 }
@@ -186,6 +190,106 @@ JPG_HD int decode_block(BitReader& br, const HuffTable& dc, const HuffTable& ac,
         ++k;
     }
     return last;
+}
+
+
+// ---- scan decoding as ONE flat loop ---------------------------------------------------------------------------------------
+// The same decoding as decode_block over a whole interleaved 4:2:0 scan, written so that every symbol takes the same
+// instruction path: one iteration = one Huffman symbol (a DC size or an AC run/size) plus its extra bits, the position inside
+// the block / MCU / picture is data, not control flow.  On the GPU a warp decodes 32 PICTURES in lock-step this way (the
+// nested-loop form diverges at every branch and ran ~1 500 cycles per symbol; profiles/r02_decode_probe_native_v1.log).
+// Input: the scan with the byte stuffing already removed (FF 00 -> FF), starting on a 4-byte boundary, `nwords` 32-bit words
+// long including at least two words of zero padding, no restart markers.  `cf` receives the non-zero coefficients of the
+// picture (natural order inside a block; blocks: luma rows of 2 * mcus_x, then Cb, then Cr), the caller has zeroed it.
+JPG_HD void decode_scan_flat(const uint32_t* __restrict__ words, int nwords, const ScanTables& T, const int* td, const int* ta,
+                             const uint8_t* __restrict__ natural, int mcus_x, int mcus_y, int16_t* __restrict__ cf) {
+    uint64_t buf = 0;
+    int bits = 0, wi = 0;
+    int pred0 = 0, pred1 = 0, pred2 = 0;
+    const int ybx = 2 * mcus_x;
+    int16_t* const cbp = cf + (size_t)4 * mcus_x * mcus_y * 64;
+    int16_t* const crp = cbp + (size_t)mcus_x * mcus_y * 64;
+    const HuffTable* const dct[3] = {&T.dc[td[0]], &T.dc[td[1]], &T.dc[td[2]]};
+    const HuffTable* const act[3] = {&T.ac[ta[0]], &T.ac[ta[1]], &T.ac[ta[2]]};
+    int mx = 0, my = 0, b = 0, comp = 0, kpos = 0;
+    long remaining = (long)6 * mcus_x * mcus_y;
+    int16_t* blk = cf;  // block (my = 0, mx = 0, b = 0)
+    const HuffTable* cur_dc = dct[0];
+    const HuffTable* cur_ac = act[0];
+    while (remaining > 0) {
+        if (bits <= 32) {  // at most 16 + 15 bits are consumed per iteration
+            uint32_t w = wi < nwords ? words[wi] : 0u;
+            ++wi;
+            w = (w >> 24) | ((w >> 8) & 0xff00u) | ((w << 8) & 0xff0000u) | (w << 24);  // big-endian bit order
+            buf |= (uint64_t)w << (32 - bits);
+            bits += 32;
+        }
+        const uint32_t pk = (uint32_t)(buf >> 48);
+        const bool is_dc = kpos == 0;
+        const HuffTable* tab = is_dc ? cur_dc : cur_ac;
+        const uint32_t e = tab->look[pk >> (16 - kLookBits)];
+        int len = (int)(e >> 8), sym = (int)(e & 255u);
+        if (e == 0) {  // a code longer than the look-ahead: its length from the canonical limits, no loop
+            len = kLookBits + 1;
+#pragma unroll
+            for (int L = kLookBits + 1; L < 16; ++L) len += pk >= tab->limit[L] ? 1 : 0;
+            sym = tab->huffval[((int)(pk >> (16 - len)) + tab->valoffset[len]) & 255];
+        }
+        buf <<= len;
+        const int size = is_dc ? (sym > 15 ? 15 : sym) : (sym & 15);
+        const int run = is_dc ? 0 : (sym >> 4);
+        const uint32_t v = size ? (uint32_t)(buf >> (64 - size)) : 0u;
+        buf <<= size;
+        bits -= len + size;
+        const int val = size ? ((int)v < (1 << (size - 1)) ? (int)v - (1 << size) + 1 : (int)v) : 0;
+        if (is_dc) {
+            pred0 += comp == 0 ? val : 0;
+            pred1 += comp == 1 ? val : 0;
+            pred2 += comp == 2 ? val : 0;
+            blk[0] = (int16_t)(comp == 0 ? pred0 : (comp == 1 ? pred1 : pred2));
+            kpos = 1;
+        } else if (size == 0) {
+            kpos = run == 15 ? kpos + 16 : 64;  // ZRL or end of block
+        } else {
+            kpos += run;
+            if (kpos < 64) blk[natural[kpos]] = (int16_t)val;
+            ++kpos;
+        }
+        if (kpos >= 64) {  // next block of the MCU / next MCU
+            --remaining;
+            kpos = 0;
+            if (++b == 6) {
+                b = 0;
+                if (++mx == mcus_x) { mx = 0; ++my; }
+            }
+            comp = b < 4 ? 0 : b - 3;
+            blk = b < 4 ? cf + ((size_t)(2 * my + (b >> 1)) * ybx + 2 * mx + (b & 1)) * 64
+                        : (b == 4 ? cbp : crp) + ((size_t)my * mcus_x + mx) * 64;
+            cur_dc = dct[comp];
+            cur_ac = act[comp];
+        }
+    }
+}
+
+// Host helper: copies an entropy-coded segment up to its first marker with the byte stuffing removed.  Returns the number of
+// bytes written; *clean is set to false when a restart marker was met (the flat decoder does not handle restarts).
+inline size_t unstuff_scan(const uint8_t* src, size_t n, uint8_t* dst, bool* clean) {
+    size_t o = 0, i = 0;
+    *clean = true;
+    while (i < n) {
+        const uint8_t* ff = (const uint8_t*)memchr(src + i, 0xFF, n - i);
+        const size_t run = ff ? (size_t)(ff - (src + i)) : n - i;
+        memcpy(dst + o, src + i, run);
+        o += run;
+        i += run;
+        if (!ff) break;
+        if (i + 1 >= n) break;            // a lone FF at the end
+        if (src[i + 1] == 0) { dst[o++] = 0xFF; i += 2; continue; }
+        if (src[i + 1] == 0xFF) { ++i; continue; }  // fill byte
+        if (src[i + 1] >= 0xD0 && src[i + 1] <= 0xD7) *clean = false;
+        break;                            // a marker ends the segment
+    }
+    return o;
 }
 
 // ---- jidctint.c jpeg_idct_islow ------------------------------------------------------------------------------------

@@ -15,14 +15,32 @@ int shim_jpeg_info(const uint8_t* data, long n, int* width, int* height, char* e
     *width = h.width; *height = h.height;
     return 0;
 }
-// decodes into out[height][width][3] BGR
-int shim_jpeg_decode(const uint8_t* data, long n, uint8_t* out, char* err) {
+// decodes into out[height][width][3] BGR.  flat != 0: the flat scan decoder (what the GPU's fast path runs: unstuffed input, one
+// loop, coefficient buffer + separate IDCT pass); flat == 0: the nested decode_block form.
+int shim_jpeg_decode(const uint8_t* data, long n, uint8_t* out, char* err, int flat) {
     JpegHeader h;
     std::string e;
     if (!parse_jpeg(data, (size_t)n, &h, &e)) { strncpy(err, e.c_str(), 255); err[255] = 0; return -1; }
     const FrameGeometry g = geometry_of(h);
     const int yw = g.yblocks_x * 8, yh = g.mcus_y * 16, cw = g.cblocks_x * 8, ch = g.mcus_y * 8;
     std::vector<uint8_t> Y((size_t)yw * yh), Cb((size_t)cw * ch), Cr((size_t)cw * ch);
+    if (flat) {
+        std::vector<uint32_t> clean_words(h.scan_len / 4 + 4, 0u);
+        bool clean = true;
+        unstuff_scan(data + h.scan_offset, h.scan_len, reinterpret_cast<uint8_t*>(clean_words.data()), &clean);
+        if (!clean || g.restart_interval) { strncpy(err, "restart markers: not for the flat decoder", 255); return -2; }
+        const size_t nblocks = (size_t)6 * g.mcus_x * g.mcus_y;
+        std::vector<int16_t> coef(nblocks * 64, 0);
+        decode_scan_flat(clean_words.data(), (int)clean_words.size(), h.huff, h.td, h.ta, kNaturalOrderHost, g.mcus_x, g.mcus_y, coef.data());
+        const size_t ny = (size_t)4 * g.mcus_x * g.mcus_y, nc = (size_t)g.mcus_x * g.mcus_y;
+        for (size_t b = 0; b < nblocks; ++b) {
+            const int comp = b < ny ? 0 : (b < ny + nc ? 1 : 2);
+            const size_t local = comp == 0 ? b : (comp == 1 ? b - ny : b - ny - nc);
+            const int bw = comp == 0 ? g.yblocks_x : g.cblocks_x;
+            uint8_t* plane = comp == 0 ? Y.data() : (comp == 1 ? Cb.data() : Cr.data());
+            idct_islow(&coef[b * 64], h.quant[h.tq[comp]], plane + (size_t)(local / bw) * 8 * (bw * 8) + (local % bw) * 8, bw * 8);
+        }
+    } else {
     BitReader br;
     br.init(data + h.scan_offset, (int)h.scan_len);
     int pred[3] = {0, 0, 0};
@@ -42,6 +60,7 @@ int shim_jpeg_decode(const uint8_t* data, long n, uint8_t* out, char* err) {
                 idct_islow(coef, h.quant[h.tq[c]], &(c == 1 ? Cb : Cr)[(size_t)(my * 8) * cw + mx * 8], cw);
             }
         }
+    }
     const int rcw = (h.width + 1) / 2, rch = (h.height + 1) / 2;  // real (downsampled) chroma size
     for (int y = 0; y < h.height; ++y)
         for (int x = 0; x < h.width; ++x)

@@ -20,17 +20,20 @@ def shim(tmp_path_factory):
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", str(so), os.path.join(ROOT, "tests", "jpeg_shim.cpp")])
     L = C.CDLL(str(so))
     L.shim_jpeg_info.argtypes = [C.c_void_p, C.c_long, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_char_p]
-    L.shim_jpeg_decode.argtypes = [C.c_void_p, C.c_long, C.c_void_p, C.c_char_p]
+    L.shim_jpeg_decode.argtypes = [C.c_void_p, C.c_long, C.c_void_p, C.c_char_p, C.c_int]
     return L
 
 
-def decode(L, jpg: bytes):
+def decode(L, jpg: bytes, flat: int = 0):
     buf = np.frombuffer(jpg, np.uint8)
     w, h, err = C.c_int(), C.c_int(), C.create_string_buffer(256)
     if L.shim_jpeg_info(buf.ctypes.data, buf.size, C.byref(w), C.byref(h), err) != 0:
         raise ValueError(err.value.decode())
     out = np.empty((h.value, w.value, 3), np.uint8)
-    assert L.shim_jpeg_decode(buf.ctypes.data, buf.size, out.ctypes.data, err) == 0, err.value
+    rc = L.shim_jpeg_decode(buf.ctypes.data, buf.size, out.ctypes.data, err, flat)
+    if rc == -2:
+        return None  # restart markers: the flat decoder declines
+    assert rc == 0, err.value
     return out
 
 
@@ -60,6 +63,11 @@ def test_decoder_arithmetic_is_bit_exact_with_cv2_imdecode(shim, quality):
             got = decode(shim, jpg.tobytes())
             assert got.shape == want.shape, (name, quality)
             assert np.array_equal(got, want), (name, quality, extra, int(np.abs(got.astype(int) - want.astype(int)).max()))
+            flat = decode(shim, jpg.tobytes(), flat=1)   # the GPU fast path's form: unstuffed scan, one flat loop
+            if extra and extra[0] == cv2.IMWRITE_JPEG_RST_INTERVAL:
+                assert flat is None   # a restart interval is declared: those pictures take the general decoder
+            else:
+                assert flat is not None and np.array_equal(flat, want), (name, quality, extra, "flat")
 
 
 def test_mjpeg_avi_pictures_written_by_cv2_decode_bit_exactly(shim, tmp_path):
@@ -81,6 +89,7 @@ def test_mjpeg_avi_pictures_written_by_cv2_decode_bit_exactly(shim, tmp_path):
         jpg = b[i + 8:i + 8 + sz]
         want = cv2.imdecode(np.frombuffer(jpg, np.uint8), cv2.IMREAD_COLOR)
         assert np.array_equal(decode(shim, jpg), want), n
+        assert np.array_equal(decode(shim, jpg, flat=1), want), n
         i += 8 + sz + (sz & 1)
         n += 1
     assert n == 4
