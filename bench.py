@@ -444,9 +444,9 @@ def compressed_leg(local, rank, world, dist, dev, args, barrier, all_max):
                 with torch.cuda.device(local):
                     st = torch.cuda.Stream(device=local)
                     with torch.cuda.stream(st):
-                        smi = SceneManager(device=local, batch_frames=64)
+                        smi = SceneManager(device=local, batch_frames=args.decode_batch, tuning={"reserved2": 24})
                         smi.add_detector(ContentDetector())
-                        vi = decode.MjpegVideo(path, device=local, batch_frames=64)
+                        vi = decode.MjpegVideo(path, device=local, batch_frames=args.decode_batch)
                         smi.detect_scenes(vi, reuse_context=True)  # warm-up pass
                         gate.wait()
                         for _ in range(passes):
@@ -759,6 +759,7 @@ def main():
     ap.add_argument("--compressed-passes", type=int, default=3)
     ap.add_argument("--compressed-cpu-passes", type=int, default=2)
     ap.add_argument("--decode-sessions", type=int, default=0, help="GPU decoder sessions per rank (0 = min(8, cores / 2))")
+    ap.add_argument("--decode-batch", type=int, default=128, help="pictures per decode batch and session")
     ap.add_argument("--config3", default="auto", choices=["auto", "on", "off"], help="run BASELINE config 3 on the ranks (auto: when N > 1)")
     ap.add_argument("--config3-frames", type=int, default=18000)
     ap.add_argument("--ref-sample", type=int, default=192, help="--impl reference: frames per process per pass")

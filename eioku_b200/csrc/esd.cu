@@ -414,7 +414,11 @@ void free_plans(esd_ctx* c) {
 int build_plan(esd_ctx* c, int64_t n, UnitPlan* out) {
     std::vector<Unit> units;
     std::vector<int> begin;
-    const int grid = build_unit_plan(c->n_groups, n, (int64_t)c->num_sms * c->ctas_per_sm,
+    // reserved2 > 0 caps the grid: a context that shares the GPU with other kernels (e.g. a decoder whose blocks own whole SMs'
+    // shared memory) must not wait for every SM to become free for a batch that 16 CTAs finish in a few hundred microseconds
+    int64_t max_ctas = (int64_t)c->num_sms * c->ctas_per_sm;
+    if (c->cfg.reserved2 > 0) max_ctas = std::min<int64_t>(max_ctas, c->cfg.reserved2);
+    const int grid = build_unit_plan(c->n_groups, n, max_ctas,
                                      c->cfg.split_mode ? c->cfg.split_mode : ESD_SPLIT_STRIPS, units, begin);
     out->grid = grid;
     out->n_units = (int)units.size();

@@ -203,32 +203,50 @@ JPG_HD int decode_block(BitReader& br, const HuffTable& dc, const HuffTable& ac,
 // picture (natural order inside a block; blocks: luma rows of 2 * mcus_x, then Cb, then Cr), the caller has zeroed it.
 JPG_HD void decode_scan_flat(const uint32_t* __restrict__ words, int nwords, const ScanTables& T, const int* td, const int* ta,
                              const uint8_t* __restrict__ natural, int mcus_x, int mcus_y, int16_t* __restrict__ cf) {
-    // Everything below is selects and arithmetic on purpose: the only branches are the loop itself, the (rare) long-code
-    // path and predicated memory operations.  ncu on the first version (branches around the DC / EOB / block-advance cases):
-    // 192 warp instructions per symbol with 12.7 of 32 lanes active on average.
-    uint64_t buf = 0;
-    int bits = 0, wi = 0;
-    int pred0 = 0, pred1 = 0, pred2 = 0;
+    // A single warp per SM runs this (the per-picture Huffman tables fill the shared memory), so the loop is bound by the
+    // LATENCY of its dependency chain, not by issue slots.  Hence: (1) selects and arithmetic instead of branches (first
+    // version: 192 warp instructions per symbol with 12.7 of 32 lanes active); (2) the chain symbol -> position -> next table
+    // is kept short -- the state of the NEXT block (its tables, its coefficient offset) is computed from the current block's
+    // state only, in the shadow of the look-up, and merely selected when the block ends; (3) code and extra bits are taken from
+    // one 32-bit window, one 64-bit shift per symbol; (4) the next input word is loaded one refill ahead.
     const int ybx64 = 2 * mcus_x * 64;                   // one row of luma blocks, in coefficients
     const int cb0 = 4 * mcus_x * mcus_y * 64;            // first Cb coefficient
     const int cr0 = cb0 + mcus_x * mcus_y * 64;          // first Cr coefficient
     const HuffTable* const tab0 = &T.dc[0];              // dc[0], dc[1], ac[0], ac[1] are contiguous
     const int dsel0 = td[0], dsel1 = td[1], dsel2 = td[2];
     const int asel0 = 2 + ta[0], asel1 = 2 + ta[1], asel2 = 2 + ta[2];
+    uint64_t buf = 0;
+    int bits = 0, wi = 1;
+    uint32_t nextw = nwords > 0 ? words[0] : 0u;         // loaded one refill ahead
+    int pred0 = 0, pred1 = 0, pred2 = 0;
     int mx = 0, b = 0, comp = 0, kpos = 0;
     int ybase = 0, cbase = 0;                            // coefficient offsets of the current MCU's first luma / chroma block
     int blk = 0;                                         // coefficient offset of the current block
     int dsel = dsel0, asel = asel0;
     int remaining = 6 * mcus_x * mcus_y;
     while (remaining > 0) {
-        const bool need = bits <= 32;                    // at most 16 + 15 bits are consumed per iteration
-        uint32_t w = 0;
-        if (need && wi < nwords) w = words[wi];
-        wi += need ? 1 : 0;
+        // ---- state of the next block, from the current block's state only (independent of the symbols decoded below)
+        const bool n_mcu_end = b == 5;
+        const int nb = n_mcu_end ? 0 : b + 1;
+        const bool n_row_end = n_mcu_end && mx + 1 == mcus_x;
+        const int nmx = n_mcu_end ? (n_row_end ? 0 : mx + 1) : mx;
+        const int nybase = ybase + (n_mcu_end ? (n_row_end ? 128 + ybx64 : 128) : 0);  // two blocks right; at the row end skip the lower block row
+        const int ncbase = cbase + (n_mcu_end ? 64 : 0);
+        const int ncomp = nb < 4 ? 0 : nb - 3;
+        const int nblk = nb < 4 ? nybase + (nb & 1) * 64 + (nb >> 1) * ybx64 : (nb == 4 ? cb0 : cr0) + ncbase;
+        const int ndsel = ncomp == 0 ? dsel0 : (ncomp == 1 ? dsel1 : dsel2);
+        const int nasel = ncomp == 0 ? asel0 : (ncomp == 1 ? asel1 : asel2);
+        // ---- refill: at most 16 + 15 bits are consumed per symbol
+        const bool need = bits <= 32;
+        uint32_t w = nextw;
         w = (w >> 24) | ((w >> 8) & 0xff00u) | ((w << 8) & 0xff0000u) | (w << 24);  // big-endian bit order
         buf |= need ? ((uint64_t)w << (32 - bits)) : 0ull;
         bits += need ? 32 : 0;
-        const uint32_t pk = (uint32_t)(buf >> 48);
+        if (need) nextw = wi < nwords ? words[wi] : 0u;
+        wi += need ? 1 : 0;
+        // ---- one symbol
+        const uint32_t win = (uint32_t)(buf >> 32);
+        const uint32_t pk = win >> 16;
         const bool is_dc = kpos == 0;
         const HuffTable* tab = tab0 + (is_dc ? dsel : asel);
         const uint32_t e = tab->look[pk >> (16 - kLookBits)];
@@ -239,11 +257,10 @@ JPG_HD void decode_scan_flat(const uint32_t* __restrict__ words, int nwords, con
             for (int L = kLookBits + 1; L < 16; ++L) len += pk >= tab->limit[L] ? 1 : 0;
             sym = tab->huffval[((int)(pk >> (16 - len)) + tab->valoffset[len]) & 255];
         }
-        buf <<= len;
         const int size = is_dc ? (sym > 15 ? 15 : sym) : (sym & 15);
         const int run = is_dc ? 0 : (sym >> 4);
-        const int v = (int)((buf >> 1) >> (63 - size));  // the next `size` bits (0 for size == 0)
-        buf <<= size;
+        const int v = (int)(((win << len) >> 1) >> (31 - size));          // the `size` bits behind the code (0 for size == 0)
+        buf <<= len + size;
         bits -= len + size;
         const int val = v < ((1 << size) >> 1) ? v - (1 << size) + 1 : v;  // HUFF_EXTEND; size == 0 gives 0
         // DC: accumulate the prediction of this component
@@ -256,20 +273,18 @@ JPG_HD void decode_scan_flat(const uint32_t* __restrict__ words, int nwords, con
         const int where = is_dc ? 0 : (int)natural[kk & 63];
         if (coded) cf[blk + where] = (int16_t)(is_dc ? pred : val);
         kpos = is_dc ? 1 : (size != 0 ? kk + 1 : (run == 15 ? kpos + 16 : 64));
-        // end of block: step through the MCU (Y00 Y01 Y10 Y11 Cb Cr), the MCU row, the picture
+        // ---- end of block: adopt the precomputed state
         const bool end = kpos >= 64;
         remaining -= end ? 1 : 0;
         kpos = end ? 0 : kpos;
-        const bool mcu_end = end && b == 5;
-        b = end ? (b == 5 ? 0 : b + 1) : b;
-        const bool row_end = mcu_end && mx + 1 == mcus_x;
-        mx = mcu_end ? (row_end ? 0 : mx + 1) : mx;
-        ybase += mcu_end ? (row_end ? 128 + ybx64 : 128) : 0;             // two blocks right; at the row end skip the lower block row
-        cbase += mcu_end ? 64 : 0;
-        comp = b < 4 ? 0 : b - 3;
-        blk = b < 4 ? ybase + (b & 1) * 64 + (b >> 1) * ybx64 : (b == 4 ? cb0 : cr0) + cbase;
-        dsel = comp == 0 ? dsel0 : (comp == 1 ? dsel1 : dsel2);
-        asel = comp == 0 ? asel0 : (comp == 1 ? asel1 : asel2);
+        b = end ? nb : b;
+        mx = end ? nmx : mx;
+        ybase = end ? nybase : ybase;
+        cbase = end ? ncbase : cbase;
+        comp = end ? ncomp : comp;
+        blk = end ? nblk : blk;
+        dsel = end ? ndsel : dsel;
+        asel = end ? nasel : asel;
     }
 }
 

@@ -117,7 +117,7 @@ typedef struct esd_config {
     int32_t hash_size;         /* hash is size x size bits (default 16; size * size <= 1024) */
     int32_t hash_lowpass;      /* DCT runs on a (size * lowpass)^2 INTER_AREA thumbnail (default 2; size * lowpass <= 64, even) */
     int32_t hash_min_scene_len;
-    int32_t reserved2;
+    int32_t reserved2;         /* tuning: upper bound of the fused kernel's grid in CTAs (0 = every SM x occupancy) */
 } esd_config;
 
 /* derived geometry, for the caller's roofline accounting and ingest sizing */

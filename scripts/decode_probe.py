@@ -50,7 +50,7 @@ def run_sessions(path, sessions, backend, score, batch, passes=2):
             with torch.cuda.stream(st):
                 sm = None
                 if score:
-                    sm = SceneManager(batch_frames=batch)
+                    sm = SceneManager(batch_frames=batch, tuning={"reserved2": 24})
                     sm.add_detector(ContentDetector())
                 v = decode.MjpegVideo(path, batch_frames=batch, backend=backend)
                 # warm-up pass
