@@ -72,7 +72,6 @@ struct esd_mjpeg {
     uint16_t* d_quant = nullptr;                 // [batch][3][64] natural order, per component
     int16_t* d_coef = nullptr;                   // [batch][blocks_per_frame][64]
     uint8_t* d_planes = nullptr;                 // [batch][plane_bytes]
-    esdjpeg::BlockInfo* d_info = nullptr;        // [blocks_per_frame + 1] per-block constants of a scan, decoding order
     std::vector<uint8_t> h_meta[2];              // pinned-free host staging of descriptors + quant tables (copied with the batch)
 };
 
@@ -221,7 +220,7 @@ __global__ void __launch_bounds__(kEntropyThreads) jpeg_entropy_kernel(NativeLay
 // decoder of jpeg_core.h -- a warp walks 32 pictures in lock-step, one Huffman symbol per iteration.
 __global__ void __launch_bounds__(kEntropyThreads) jpeg_entropy_flat_kernel(NativeLayout L, const uint8_t* __restrict__ stage,
                                                                             const esd_mjpeg::NativeDesc* __restrict__ desc,
-                                                                            const esdjpeg::BlockInfo* __restrict__ info, int16_t* __restrict__ coef) {
+                                                                            int16_t* __restrict__ coef) {
     extern __shared__ __align__(16) uint8_t ent_smem[];
     __shared__ uint8_t s_nat[64];
     esdjpeg::ScanTables* tabs = reinterpret_cast<esdjpeg::ScanTables*>(ent_smem);
@@ -237,7 +236,8 @@ __global__ void __launch_bounds__(kEntropyThreads) jpeg_entropy_flat_kernel(Nati
         if (d.dht[t]) ok = esdjpeg::build_huff_table(stage + d.dht[t], stage + d.dht[t] + 16, (int)d.nvals[t], tb) && ok;
     }
     if (!ok) return;
-    esdjpeg::decode_scan_flat(reinterpret_cast<const uint32_t*>(stage + d.off), (int)d.len, T, info, L.blocks_per_frame, s_nat,
+    const int td[3] = {L.td[0], L.td[1], L.td[2]}, ta[3] = {L.ta[0], L.ta[1], L.ta[2]};
+    esdjpeg::decode_scan_flat(reinterpret_cast<const uint32_t*>(stage + d.off), (int)d.len, T, td, ta, s_nat, L.mcus_x, L.mcus_y,
                               coef + (size_t)f * L.blocks_per_frame * 64);
 }
 
@@ -330,7 +330,7 @@ void esd_mjpeg_close(esd_mjpeg* h) {
         cudaFree(h->d_out[b]);
         if (h->h_stage[b]) cudaFreeHost(h->h_stage[b]);
     }
-    cudaFree(h->d_info); cudaFree(h->d_comp); cudaFree(h->d_coef); cudaFree(h->d_planes);
+    cudaFree(h->d_comp); cudaFree(h->d_coef); cudaFree(h->d_planes);
     if (h->state) nvjpegJpegStateDestroy(h->state);
     if (h->nj) nvjpegDestroy(h->nj);
     if (h->map) munmap(const_cast<uint8_t*>(h->map), h->map_bytes);
@@ -395,12 +395,6 @@ int esd_mjpeg_open(esd_mjpeg** out, const char* path, int device, int32_t batch_
             if (e == cudaSuccess) e = cudaFuncSetAttribute(jpeg_entropy_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kEntropyThreads * sizeof(esdjpeg::ScanTables)));
             if (e == cudaSuccess) e = cudaMalloc(&h->d_coef, (size_t)h->batch * h->blocks_per_frame * 64 * sizeof(int16_t));
             if (e == cudaSuccess) e = cudaMalloc(&h->d_planes, (size_t)h->batch * h->plane_bytes);
-            if (e == cudaSuccess) e = cudaMalloc(&h->d_info, sizeof(esdjpeg::BlockInfo) * (h->blocks_per_frame + 1));
-            if (e == cudaSuccess) {
-                std::vector<esdjpeg::BlockInfo> info((size_t)h->blocks_per_frame + 1);
-                esdjpeg::build_block_info(h->geo.mcus_x, h->geo.mcus_y, h->td, h->ta, info.data());
-                e = cudaMemcpy(h->d_info, info.data(), sizeof(esdjpeg::BlockInfo) * info.size(), cudaMemcpyHostToDevice);
-            }
             if (e != cudaSuccess) {
                 fail(h, ESD_DEC_ERR_CUDA, "native decoder: device buffers for %d frames could not be allocated: %s", h->batch, cudaGetErrorString(e));
                 return bail(ESD_DEC_ERR_CUDA);
@@ -568,7 +562,7 @@ int esd_mjpeg_read(esd_mjpeg* h, int64_t max_frames, void* stream, uint8_t** d_b
         const uint16_t* dquant = reinterpret_cast<const uint16_t*>(h->d_comp + (size_t)n * sizeof(esd_mjpeg::NativeDesc));
         const unsigned egrid = (unsigned)((n + kEntropyThreads - 1) / kEntropyThreads);
         const size_t esmem = kEntropyThreads * sizeof(esdjpeg::ScanTables);
-        if (h->flat) jpeg_entropy_flat_kernel<<<egrid, kEntropyThreads, esmem, st>>>(L, h->d_comp, ddesc, h->d_info, h->d_coef);
+        if (h->flat) jpeg_entropy_flat_kernel<<<egrid, kEntropyThreads, esmem, st>>>(L, h->d_comp, ddesc, h->d_coef);
         else jpeg_entropy_kernel<<<egrid, kEntropyThreads, esmem, st>>>(L, h->d_comp, ddesc, h->d_coef);
         jpeg_idct_kernel<<<dim3((unsigned)((h->blocks_per_frame + 127) / 128), (unsigned)n), 128, 0, st>>>(L, h->d_coef, dquant, h->d_planes);
         jpeg_color_kernel<<<dim3((unsigned)(((h->width + 3) / 4 + 255) / 256), (unsigned)h->height, (unsigned)n), 256, 0, st>>>(L, h->d_planes, h->d_out[b]);

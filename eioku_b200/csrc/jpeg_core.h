@@ -201,49 +201,41 @@ JPG_HD int decode_block(BitReader& br, const HuffTable& dc, const HuffTable& ac,
 // Input: the scan with the byte stuffing already removed (FF 00 -> FF), starting on a 4-byte boundary, `nwords` 32-bit words
 // long including at least two words of zero padding, no restart markers.  `cf` receives the non-zero coefficients of the
 // picture (natural order inside a block; blocks: luma rows of 2 * mcus_x, then Cb, then Cr), the caller has zeroed it.
-// Per-block constants of a scan, in decoding order (6 entries per MCU): where the block's coefficients go and which tables it
-// uses.  The same for every picture of a stream, so it is built once (build_block_info) and read through the cache.
-struct BlockInfo {
-    int32_t coef_offset;   // first coefficient of the block inside the picture's coefficient buffer
-    uint8_t dsel, asel;    // table index for DC / AC symbols: dc[0], dc[1], ac[0], ac[1] -> 0..3
-    uint8_t comp, pad;
-};
-
-inline void build_block_info(int mcus_x, int mcus_y, const int* td, const int* ta, BlockInfo* out /* [6 * mcus_x * mcus_y + 1] */) {
-    const int ybx64 = 2 * mcus_x * 64;
-    const int cb0 = 4 * mcus_x * mcus_y * 64, cr0 = cb0 + mcus_x * mcus_y * 64;
-    int n = 0;
-    for (int my = 0; my < mcus_y; ++my)
-        for (int mx = 0; mx < mcus_x; ++mx)
-            for (int b = 0; b < 6; ++b, ++n) {
-                const int comp = b < 4 ? 0 : b - 3;
-                out[n].coef_offset = b < 4 ? ((2 * my + (b >> 1)) * 2 * mcus_x + 2 * mx + (b & 1)) * 64
-                                           : (b == 4 ? cb0 : cr0) + (my * mcus_x + mx) * 64;
-                (void)ybx64;
-                out[n].dsel = (uint8_t)td[comp];
-                out[n].asel = (uint8_t)(2 + ta[comp]);
-                out[n].comp = (uint8_t)comp;
-                out[n].pad = 0;
-            }
-    out[n] = out[n - 1];  // sentinel: read (and ignored) when the last block ends
-}
-
-JPG_HD void decode_scan_flat(const uint32_t* __restrict__ words, int nwords, const ScanTables& T, const BlockInfo* __restrict__ info,
-                             int n_blocks, const uint8_t* __restrict__ natural, int16_t* __restrict__ cf) {
+JPG_HD void decode_scan_flat(const uint32_t* __restrict__ words, int nwords, const ScanTables& T, const int* td, const int* ta,
+                             const uint8_t* __restrict__ natural, int mcus_x, int mcus_y, int16_t* __restrict__ cf) {
     // A single warp per SM runs this (the per-picture Huffman tables fill the shared memory), so the loop is bound by the
-    // LATENCY of its instruction stream (~4 cycles per instruction for a lone warp), not by issue slots.  Hence: (1) selects
-    // and arithmetic instead of branches (first version: 192 warp instructions per symbol with 12.7 of 32 lanes active);
-    // (2) nothing about the block structure is computed here: the next block's constants come from `info`, loaded one block
-    // ahead; (3) code and extra bits are taken from one 32-bit window, one 64-bit shift per symbol; (4) the next input word is
-    // loaded one refill ahead.
+    // LATENCY of its dependency chain, not by issue slots.  Hence: (1) selects and arithmetic instead of branches (first
+    // version: 192 warp instructions per symbol with 12.7 of 32 lanes active); (2) the chain symbol -> position -> next table
+    // is kept short -- the state of the NEXT block (its tables, its coefficient offset) is computed from the current block's
+    // state only, in the shadow of the look-up, and merely selected when the block ends; (3) code and extra bits are taken from
+    // one 32-bit window, one 64-bit shift per symbol; (4) the next input word is loaded one refill ahead.
+    const int ybx64 = 2 * mcus_x * 64;                   // one row of luma blocks, in coefficients
+    const int cb0 = 4 * mcus_x * mcus_y * 64;            // first Cb coefficient
+    const int cr0 = cb0 + mcus_x * mcus_y * 64;          // first Cr coefficient
     const HuffTable* const tab0 = &T.dc[0];              // dc[0], dc[1], ac[0], ac[1] are contiguous
+    const int dsel0 = td[0], dsel1 = td[1], dsel2 = td[2];
+    const int asel0 = 2 + ta[0], asel1 = 2 + ta[1], asel2 = 2 + ta[2];
     uint64_t buf = 0;
     int bits = 0, wi = 1;
     uint32_t nextw = nwords > 0 ? words[0] : 0u;         // loaded one refill ahead
     int pred0 = 0, pred1 = 0, pred2 = 0;
-    int kpos = 0, seq = 0;
-    BlockInfo cur = info[0], nxt = info[1];
-    while (seq < n_blocks) {
+    int mx = 0, b = 0, comp = 0, kpos = 0;
+    int ybase = 0, cbase = 0;                            // coefficient offsets of the current MCU's first luma / chroma block
+    int blk = 0;                                         // coefficient offset of the current block
+    int dsel = dsel0, asel = asel0;
+    int remaining = 6 * mcus_x * mcus_y;
+    while (remaining > 0) {
+        // ---- state of the next block, from the current block's state only (independent of the symbols decoded below)
+        const bool n_mcu_end = b == 5;
+        const int nb = n_mcu_end ? 0 : b + 1;
+        const bool n_row_end = n_mcu_end && mx + 1 == mcus_x;
+        const int nmx = n_mcu_end ? (n_row_end ? 0 : mx + 1) : mx;
+        const int nybase = ybase + (n_mcu_end ? (n_row_end ? 128 + ybx64 : 128) : 0);  // two blocks right; at the row end skip the lower block row
+        const int ncbase = cbase + (n_mcu_end ? 64 : 0);
+        const int ncomp = nb < 4 ? 0 : nb - 3;
+        const int nblk = nb < 4 ? nybase + (nb & 1) * 64 + (nb >> 1) * ybx64 : (nb == 4 ? cb0 : cr0) + ncbase;
+        const int ndsel = ncomp == 0 ? dsel0 : (ncomp == 1 ? dsel1 : dsel2);
+        const int nasel = ncomp == 0 ? asel0 : (ncomp == 1 ? asel1 : asel2);
         // ---- refill: at most 16 + 15 bits are consumed per symbol
         const bool need = bits <= 32;
         uint32_t w = nextw;
@@ -256,7 +248,7 @@ JPG_HD void decode_scan_flat(const uint32_t* __restrict__ words, int nwords, con
         const uint32_t win = (uint32_t)(buf >> 32);
         const uint32_t pk = win >> 16;
         const bool is_dc = kpos == 0;
-        const HuffTable* tab = tab0 + (is_dc ? cur.dsel : cur.asel);
+        const HuffTable* tab = tab0 + (is_dc ? dsel : asel);
         const uint32_t e = tab->look[pk >> (16 - kLookBits)];
         int len = (int)(e >> 8), sym = (int)(e & 255u);
         if (e == 0) {  // a code longer than the look-ahead: its length from the canonical limits, no loop
@@ -272,23 +264,27 @@ JPG_HD void decode_scan_flat(const uint32_t* __restrict__ words, int nwords, con
         bits -= len + size;
         const int val = v < ((1 << size) >> 1) ? v - (1 << size) + 1 : v;  // HUFF_EXTEND; size == 0 gives 0
         // DC: accumulate the prediction of this component
-        pred0 += (is_dc && cur.comp == 0) ? val : 0;
-        pred1 += (is_dc && cur.comp == 1) ? val : 0;
-        pred2 += (is_dc && cur.comp == 2) ? val : 0;
-        const int pred = cur.comp == 0 ? pred0 : (cur.comp == 1 ? pred1 : pred2);
+        pred0 += (is_dc && comp == 0) ? val : 0;
+        pred1 += (is_dc && comp == 1) ? val : 0;
+        pred2 += (is_dc && comp == 2) ? val : 0;
+        const int pred = comp == 0 ? pred0 : (comp == 1 ? pred1 : pred2);
         const int kk = kpos + run;                                       // zig-zag position of an AC coefficient
         const bool coded = is_dc || (size != 0 && kk < 64);
         const int where = is_dc ? 0 : (int)natural[kk & 63];
-        if (coded) cf[cur.coef_offset + where] = (int16_t)(is_dc ? pred : val);
+        if (coded) cf[blk + where] = (int16_t)(is_dc ? pred : val);
         kpos = is_dc ? 1 : (size != 0 ? kk + 1 : (run == 15 ? kpos + 16 : 64));
-        // ---- end of block: adopt the next block's constants, fetch the ones after it
+        // ---- end of block: adopt the precomputed state
         const bool end = kpos >= 64;
+        remaining -= end ? 1 : 0;
         kpos = end ? 0 : kpos;
-        seq += end ? 1 : 0;
-        if (end) {
-            cur = nxt;
-            nxt = info[seq + 1 <= n_blocks ? seq + 1 : n_blocks];
-        }
+        b = end ? nb : b;
+        mx = end ? nmx : mx;
+        ybase = end ? nybase : ybase;
+        cbase = end ? ncbase : cbase;
+        comp = end ? ncomp : comp;
+        blk = end ? nblk : blk;
+        dsel = end ? ndsel : dsel;
+        asel = end ? nasel : asel;
     }
 }
 

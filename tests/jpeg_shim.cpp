@@ -31,9 +31,7 @@ int shim_jpeg_decode(const uint8_t* data, long n, uint8_t* out, char* err, int f
         if (!clean || g.restart_interval) { strncpy(err, "restart markers: not for the flat decoder", 255); return -2; }
         const size_t nblocks = (size_t)6 * g.mcus_x * g.mcus_y;
         std::vector<int16_t> coef(nblocks * 64, 0);
-        std::vector<BlockInfo> info(nblocks + 1);
-        build_block_info(g.mcus_x, g.mcus_y, h.td, h.ta, info.data());
-        decode_scan_flat(clean_words.data(), (int)clean_words.size(), h.huff, info.data(), (int)nblocks, kNaturalOrderHost, coef.data());
+        decode_scan_flat(clean_words.data(), (int)clean_words.size(), h.huff, h.td, h.ta, kNaturalOrderHost, g.mcus_x, g.mcus_y, coef.data());
         const size_t ny = (size_t)4 * g.mcus_x * g.mcus_y, nc = (size_t)g.mcus_x * g.mcus_y;
         for (size_t b = 0; b < nblocks; ++b) {
             const int comp = b < ny ? 0 : (b < ny + nc ? 1 : 2);
