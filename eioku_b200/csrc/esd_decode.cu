@@ -194,10 +194,7 @@ __global__ void __launch_bounds__(kEntropyThreads) jpeg_entropy_kernel(NativeLay
     esdjpeg::BitReader br;
     br.init(stage + d.off, (int)d.len);
     int pred[3] = {0, 0, 0};
-    int16_t* cf = coef + (size_t)f * L.blocks_per_frame * 64;
-    const int ybx = 2 * L.mcus_x;
-    int16_t* cb = cf + (size_t)4 * L.mcus_x * L.mcus_y * 64;
-    int16_t* cr = cb + (size_t)L.mcus_x * L.mcus_y * 64;
+    int16_t* cf = coef + (size_t)f * L.blocks_per_frame * 64;  // decoding order: six blocks per MCU
     const esdjpeg::HuffTable& ydc = T.dc[L.td[0]];
     const esdjpeg::HuffTable& yac = T.ac[L.ta[0]];
     const esdjpeg::HuffTable& bdc = T.dc[L.td[1]];
@@ -208,11 +205,11 @@ __global__ void __launch_bounds__(kEntropyThreads) jpeg_entropy_kernel(NativeLay
     for (int my = 0; my < L.mcus_y; ++my)
         for (int mx = 0; mx < L.mcus_x; ++mx, ++mcu) {
             if (L.restart_interval && mcu && mcu % L.restart_interval == 0) { br.restart(); pred[0] = pred[1] = pred[2] = 0; }
+            int16_t* m = cf + (size_t)mcu * 6 * 64;
 #pragma unroll
-            for (int b = 0; b < 4; ++b)
-                esdjpeg::decode_block(br, ydc, yac, s_nat, pred[0], cf + ((size_t)(2 * my + (b >> 1)) * ybx + 2 * mx + (b & 1)) * 64);
-            esdjpeg::decode_block(br, bdc, bac, s_nat, pred[1], cb + ((size_t)my * L.mcus_x + mx) * 64);
-            esdjpeg::decode_block(br, rdc, rac, s_nat, pred[2], cr + ((size_t)my * L.mcus_x + mx) * 64);
+            for (int b = 0; b < 4; ++b) esdjpeg::decode_block(br, ydc, yac, s_nat, pred[0], m + b * 64);
+            esdjpeg::decode_block(br, bdc, bac, s_nat, pred[1], m + 4 * 64);
+            esdjpeg::decode_block(br, rdc, rac, s_nat, pred[2], m + 5 * 64);
         }
 }
 
@@ -237,7 +234,7 @@ __global__ void __launch_bounds__(kEntropyThreads) jpeg_entropy_flat_kernel(Nati
     }
     if (!ok) return;
     const int td[3] = {L.td[0], L.td[1], L.td[2]}, ta[3] = {L.ta[0], L.ta[1], L.ta[2]};
-    esdjpeg::decode_scan_flat(reinterpret_cast<const uint32_t*>(stage + d.off), (int)d.len, T, td, ta, s_nat, L.mcus_x, L.mcus_y,
+    esdjpeg::decode_scan_flat(reinterpret_cast<const uint32_t*>(stage + d.off), (int)d.len, T, td, ta, s_nat, L.mcus_x * L.mcus_y,
                               coef + (size_t)f * L.blocks_per_frame * 64);
 }
 
@@ -246,11 +243,9 @@ __global__ void __launch_bounds__(128) jpeg_idct_kernel(NativeLayout L, const in
     const int blk = blockIdx.x * blockDim.x + threadIdx.x;
     const int f = blockIdx.y;
     if (blk >= L.blocks_per_frame) return;
-    const int ny = 4 * L.mcus_x * L.mcus_y, nc = L.mcus_x * L.mcus_y;
-    const int comp = blk < ny ? 0 : (blk < ny + nc ? 1 : 2);
-    const int local = comp == 0 ? blk : (comp == 1 ? blk - ny : blk - ny - nc);
-    const int bw = comp == 0 ? 2 * L.mcus_x : L.mcus_x;  // blocks per row of this component
-    const int by = local / bw, bx = local - by * bw;
+    int comp, bx, by;
+    esdjpeg::block_position(blk, L.mcus_x, &comp, &bx, &by);  // coefficients are stored in decoding order
+    const int bw = comp == 0 ? 2 * L.mcus_x : L.mcus_x;       // blocks per row of this component
     const int stride = bw * 8;
     const size_t ysz = (size_t)(2 * L.mcus_x * 8) * (L.mcus_y * 16), csz = (size_t)(L.mcus_x * 8) * (L.mcus_y * 8);
     uint8_t* plane = planes + (size_t)f * L.plane_bytes + (comp == 0 ? 0 : (comp == 1 ? ysz : ysz + csz));

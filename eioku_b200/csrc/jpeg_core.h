@@ -202,16 +202,15 @@ JPG_HD int decode_block(BitReader& br, const HuffTable& dc, const HuffTable& ac,
 // long including at least two words of zero padding, no restart markers.  `cf` receives the non-zero coefficients of the
 // picture (natural order inside a block; blocks: luma rows of 2 * mcus_x, then Cb, then Cr), the caller has zeroed it.
 JPG_HD void decode_scan_flat(const uint32_t* __restrict__ words, int nwords, const ScanTables& T, const int* td, const int* ta,
-                             const uint8_t* __restrict__ natural, int mcus_x, int mcus_y, int16_t* __restrict__ cf) {
+                             const uint8_t* __restrict__ natural, int n_mcus, int16_t* __restrict__ cf) {
     // A single warp per SM runs this (the per-picture Huffman tables fill the shared memory), so the loop is bound by the
-    // LATENCY of its dependency chain, not by issue slots.  Hence: (1) selects and arithmetic instead of branches (first
-    // version: 192 warp instructions per symbol with 12.7 of 32 lanes active); (2) the chain symbol -> position -> next table
-    // is kept short -- the state of the NEXT block (its tables, its coefficient offset) is computed from the current block's
-    // state only, in the shadow of the look-up, and merely selected when the block ends; (3) code and extra bits are taken from
-    // one 32-bit window, one 64-bit shift per symbol; (4) the next input word is loaded one refill ahead.
-    const int ybx64 = 2 * mcus_x * 64;                   // one row of luma blocks, in coefficients
-    const int cb0 = 4 * mcus_x * mcus_y * 64;            // first Cb coefficient
-    const int cr0 = cb0 + mcus_x * mcus_y * 64;          // first Cr coefficient
+    // LATENCY of its instruction stream (~4 cycles per instruction for a lone warp), not by issue slots.  Hence: (1) selects
+    // and arithmetic instead of branches (first version: 192 warp instructions per symbol with 12.7 of 32 lanes active);
+    // (2) coefficients are stored in DECODING order (block s of the scan at cf + 64 s: Y00 Y01 Y10 Y11 Cb Cr per MCU), so the
+    // loop knows nothing about the picture's geometry -- the IDCT kernel, which is parallel, maps blocks to positions;
+    // (3) the table selectors of the next block are computed in the shadow of the look-up and merely selected when a block
+    // ends; (4) code and extra bits are taken from one 32-bit window, one 64-bit shift per symbol; (5) the next input word is
+    // loaded one refill ahead.
     const HuffTable* const tab0 = &T.dc[0];              // dc[0], dc[1], ac[0], ac[1] are contiguous
     const int dsel0 = td[0], dsel1 = td[1], dsel2 = td[2];
     const int asel0 = 2 + ta[0], asel1 = 2 + ta[1], asel2 = 2 + ta[2];
@@ -219,21 +218,14 @@ JPG_HD void decode_scan_flat(const uint32_t* __restrict__ words, int nwords, con
     int bits = 0, wi = 1;
     uint32_t nextw = nwords > 0 ? words[0] : 0u;         // loaded one refill ahead
     int pred0 = 0, pred1 = 0, pred2 = 0;
-    int mx = 0, b = 0, comp = 0, kpos = 0;
-    int ybase = 0, cbase = 0;                            // coefficient offsets of the current MCU's first luma / chroma block
+    int b = 0, comp = 0, kpos = 0;
     int blk = 0;                                         // coefficient offset of the current block
     int dsel = dsel0, asel = asel0;
-    int remaining = 6 * mcus_x * mcus_y;
+    int remaining = 6 * n_mcus;
     while (remaining > 0) {
-        // ---- state of the next block, from the current block's state only (independent of the symbols decoded below)
-        const bool n_mcu_end = b == 5;
-        const int nb = n_mcu_end ? 0 : b + 1;
-        const bool n_row_end = n_mcu_end && mx + 1 == mcus_x;
-        const int nmx = n_mcu_end ? (n_row_end ? 0 : mx + 1) : mx;
-        const int nybase = ybase + (n_mcu_end ? (n_row_end ? 128 + ybx64 : 128) : 0);  // two blocks right; at the row end skip the lower block row
-        const int ncbase = cbase + (n_mcu_end ? 64 : 0);
+        // ---- selectors of the next block (independent of the symbols decoded below)
+        const int nb = b == 5 ? 0 : b + 1;
         const int ncomp = nb < 4 ? 0 : nb - 3;
-        const int nblk = nb < 4 ? nybase + (nb & 1) * 64 + (nb >> 1) * ybx64 : (nb == 4 ? cb0 : cr0) + ncbase;
         const int ndsel = ncomp == 0 ? dsel0 : (ncomp == 1 ? dsel1 : dsel2);
         const int nasel = ncomp == 0 ? asel0 : (ncomp == 1 ? asel1 : asel2);
         // ---- refill: at most 16 + 15 bits are consumed per symbol
@@ -273,19 +265,25 @@ JPG_HD void decode_scan_flat(const uint32_t* __restrict__ words, int nwords, con
         const int where = is_dc ? 0 : (int)natural[kk & 63];
         if (coded) cf[blk + where] = (int16_t)(is_dc ? pred : val);
         kpos = is_dc ? 1 : (size != 0 ? kk + 1 : (run == 15 ? kpos + 16 : 64));
-        // ---- end of block: adopt the precomputed state
+        // ---- end of block
         const bool end = kpos >= 64;
         remaining -= end ? 1 : 0;
         kpos = end ? 0 : kpos;
+        blk += end ? 64 : 0;
         b = end ? nb : b;
-        mx = end ? nmx : mx;
-        ybase = end ? nybase : ybase;
-        cbase = end ? ncbase : cbase;
         comp = end ? ncomp : comp;
-        blk = end ? nblk : blk;
         dsel = end ? ndsel : dsel;
         asel = end ? nasel : asel;
     }
+}
+
+// Where block `s` of the scan (decoding order) lies: component and block coordinates inside that component's plane.
+JPG_HD void block_position(int s, int mcus_x, int* comp, int* bx, int* by) {
+    const int mcu = s / 6, b = s - 6 * mcu;
+    const int my = mcu / mcus_x, mx = mcu - my * mcus_x;
+    *comp = b < 4 ? 0 : b - 3;
+    *bx = b < 4 ? 2 * mx + (b & 1) : mx;
+    *by = b < 4 ? 2 * my + (b >> 1) : my;
 }
 
 // Host helper: copies an entropy-coded segment up to its first marker with the byte stuffing removed.  Returns the number of

@@ -31,14 +31,13 @@ int shim_jpeg_decode(const uint8_t* data, long n, uint8_t* out, char* err, int f
         if (!clean || g.restart_interval) { strncpy(err, "restart markers: not for the flat decoder", 255); return -2; }
         const size_t nblocks = (size_t)6 * g.mcus_x * g.mcus_y;
         std::vector<int16_t> coef(nblocks * 64, 0);
-        decode_scan_flat(clean_words.data(), (int)clean_words.size(), h.huff, h.td, h.ta, kNaturalOrderHost, g.mcus_x, g.mcus_y, coef.data());
-        const size_t ny = (size_t)4 * g.mcus_x * g.mcus_y, nc = (size_t)g.mcus_x * g.mcus_y;
-        for (size_t b = 0; b < nblocks; ++b) {
-            const int comp = b < ny ? 0 : (b < ny + nc ? 1 : 2);
-            const size_t local = comp == 0 ? b : (comp == 1 ? b - ny : b - ny - nc);
+        decode_scan_flat(clean_words.data(), (int)clean_words.size(), h.huff, h.td, h.ta, kNaturalOrderHost, g.mcus_x * g.mcus_y, coef.data());
+        for (size_t b = 0; b < nblocks; ++b) {  // coefficients are in decoding order: block_position maps them into the planes
+            int comp, bx, by;
+            block_position((int)b, g.mcus_x, &comp, &bx, &by);
             const int bw = comp == 0 ? g.yblocks_x : g.cblocks_x;
             uint8_t* plane = comp == 0 ? Y.data() : (comp == 1 ? Cb.data() : Cr.data());
-            idct_islow(&coef[b * 64], h.quant[h.tq[comp]], plane + (size_t)(local / bw) * 8 * (bw * 8) + (local % bw) * 8, bw * 8);
+            idct_islow(&coef[b * 64], h.quant[h.tq[comp]], plane + (size_t)by * 8 * (bw * 8) + bx * 8, bw * 8);
         }
     } else {
     BitReader br;
