@@ -186,6 +186,30 @@ def bench_reference(args):
                 total += res["frames_total"]
     dt = sum(times)
     value = total / dt
+    # the compressed-file leg of the same arm: cv2.VideoCapture decode (the reference's decode loop, model_manager.py:237-263)
+    # + PySceneDetect logic on cv2, one process per core, each decoding and scoring the whole file -- the counterpart of the GPU
+    # arm's `e2e_compressed`.  The file is the same Motion-JPEG AVI (frames from the CPU twin of the clip generator).
+    comp = None
+    if not args.no_compressed:
+        import cv2
+
+        n = args.compressed_frames
+        shm = "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
+        path = os.path.join(shm, f"esd_bench_mjpeg_ref_{os.getpid()}.avi")
+        wr = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"MJPG"), float(FPS), (W, H))
+        for a in range(0, n, 32):
+            for f in cpu_sample_frames(min(32, n - a), a):
+                wr.write(f)
+        wr.release()
+        try:
+            with cpu_baseline.Runner(video_path=path, cores=cores) as runner:
+                runner.step(1)
+                r = runner.step(args.compressed_cpu_passes)
+            comp = {"value": r["frames_per_s"], "unit": UNIT, "cores": r["cores"], "seconds": r["seconds"], "file_frames": n,
+                    "file_bytes": os.path.getsize(path),
+                    "what": "cv2.VideoCapture decode + PySceneDetect logic on cv2, one process per core, each decoding and scoring the whole file"}
+        finally:
+            os.remove(path)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 * dt / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
@@ -198,6 +222,8 @@ def bench_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if comp is not None:
+        line["e2e_compressed"] = comp
     print(json.dumps(line), flush=True)
     return 0
 

@@ -23,7 +23,9 @@ def _run(args, env=None):
 
 
 def test_reference_arm_line():
-    d = _run(["--impl", "reference", "--steps", "1", "--warmup", "1", "--ref-sample", "6", "--ref-reps", "1"])
+    d = _run(["--impl", "reference", "--steps", "1", "--warmup", "1", "--ref-sample", "6", "--ref-reps", "1", "--compressed-frames", "4",
+              "--compressed-cpu-passes", "1"])
+    assert d["e2e_compressed"]["value"] > 0 and d["e2e_compressed"]["file_frames"] == 4
     assert BASE_KEYS <= set(d) and d["impl"] == "reference"
     assert d["metric"] == "frames/sec (1080p ContentDetector)" and d["unit"] == "frames/s" and d["higher_is_better"] is True
     assert d["value"] > 0 and d["dtype"] == "u8" and d["data"] == "synthetic" and d["vs_baseline"] is None
@@ -38,7 +40,7 @@ def test_reference_arm_honours_steps_and_warmup_and_never_loads_the_product():
     from the CPU twin of the clip generator) and prints the same `config` object as the GPU arm."""
     code = (
         "import sys, runpy, io, json, contextlib\n"
-        "sys.argv = ['bench.py', '--impl', 'reference', '--steps', '4', '--warmup', '3', '--ref-sample', '6', '--ref-reps', '1']\n"
+        "sys.argv = ['bench.py', '--impl', 'reference', '--steps', '4', '--warmup', '3', '--ref-sample', '6', '--ref-reps', '1', '--no-compressed']\n"
         "buf = io.StringIO()\n"
         "with contextlib.redirect_stdout(buf):\n"
         "    try:\n"
