@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(128) jpeg_idct_kernel(NativeLayout L, const in
                                                         uint8_t* __restrict__ planes) {
     const int blk = blockIdx.x * blockDim.x + threadIdx.x;
     const int f = blockIdx.y;
-    if (blk >= L.blocks_per_frame) return;
+    if (blk >= L.blocks_per_frame - 1) return;  // the last block of a picture's buffer is the entropy stage's scratch
     int comp, bx, by;
     esdjpeg::block_position(blk, L.mcus_x, &comp, &bx, &by);  // coefficients are stored in decoding order
     const int bw = comp == 0 ? 2 * L.mcus_x : L.mcus_x;       // blocks per row of this component
@@ -383,7 +383,7 @@ int esd_mjpeg_open(esd_mjpeg** out, const char* path, int device, int32_t batch_
         if (ok) {
             h->geo = esdjpeg::geometry_of(jh);
             for (int c = 0; c < 3; ++c) { h->tq[c] = jh.tq[c]; h->td[c] = jh.td[c]; h->ta[c] = jh.ta[c]; }
-            h->blocks_per_frame = 6 * h->geo.mcus_x * h->geo.mcus_y;
+            h->blocks_per_frame = 6 * h->geo.mcus_x * h->geo.mcus_y + 1;  // + one spare block per picture (scratch of the flat decoder)
             h->plane_bytes = (size_t)(h->geo.mcus_x * 16) * (h->geo.mcus_y * 16) * 3 / 2;
             h->flat = jh.restart_interval == 0;
             cudaError_t e = cudaFuncSetAttribute(jpeg_entropy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kEntropyThreads * sizeof(esdjpeg::ScanTables)));

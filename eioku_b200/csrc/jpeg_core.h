@@ -200,7 +200,8 @@ JPG_HD int decode_block(BitReader& br, const HuffTable& dc, const HuffTable& ac,
 // nested-loop form diverges at every branch and ran ~1 500 cycles per symbol; profiles/r02_decode_probe_native_v1.log).
 // Input: the scan with the byte stuffing already removed (FF 00 -> FF), starting on a 4-byte boundary, `nwords` 32-bit words
 // long including at least two words of zero padding, no restart markers.  `cf` receives the non-zero coefficients of the
-// picture (natural order inside a block; blocks: luma rows of 2 * mcus_x, then Cb, then Cr), the caller has zeroed it.
+// picture (natural order inside a block; blocks in decoding order) and has room for ONE SPARE BLOCK behind the last (scratch);
+// the caller has zeroed it.
 JPG_HD void decode_scan_flat(const uint32_t* __restrict__ words, int nwords, const ScanTables& T, const int* td, const int* ta,
                              const uint8_t* __restrict__ natural, int n_mcus, int16_t* __restrict__ cf) {
     // A single warp per SM runs this (the per-picture Huffman tables fill the shared memory), so the loop is bound by the
@@ -222,6 +223,7 @@ JPG_HD void decode_scan_flat(const uint32_t* __restrict__ words, int nwords, con
     int blk = 0;                                         // coefficient offset of the current block
     int dsel = dsel0, asel = asel0;
     int remaining = 6 * n_mcus;
+    const int spare = 6 * n_mcus * 64;                   // one spare block behind the last: the sink of coefficient-less symbols
     while (remaining > 0) {
         // ---- selectors of the next block (independent of the symbols decoded below)
         const int nb = b == 5 ? 0 : b + 1;
@@ -230,12 +232,14 @@ JPG_HD void decode_scan_flat(const uint32_t* __restrict__ words, int nwords, con
         const int nasel = ncomp == 0 ? asel0 : (ncomp == 1 ? asel1 : asel2);
         // ---- refill: at most 16 + 15 bits are consumed per symbol
         const bool need = bits <= 32;
+        const uint32_t nm = need ? 0xffffffffu : 0u;     // masks instead of ?: below -- the compiler turned the selects into divergent branches
         uint32_t w = nextw;
         w = (w >> 24) | ((w >> 8) & 0xff00u) | ((w << 8) & 0xff0000u) | (w << 24);  // big-endian bit order
-        buf |= need ? ((uint64_t)w << (32 - bits)) : 0ull;
-        bits += need ? 32 : 0;
-        if (need) nextw = wi < nwords ? words[wi] : 0u;
-        wi += need ? 1 : 0;
+        buf |= ((uint64_t)(w & nm) << ((32 - bits) & 63));
+        bits += (int)(32u & nm);
+        const uint32_t fetched = words[wi < nwords ? wi : nwords - 1];  // unconditional (same word until consumed: it stays in L1)
+        nextw = (fetched & nm) | (nextw & ~nm);
+        wi += (int)(1u & nm);
         // ---- one symbol
         const uint32_t win = (uint32_t)(buf >> 32);
         const uint32_t pk = win >> 16;
@@ -249,31 +253,36 @@ JPG_HD void decode_scan_flat(const uint32_t* __restrict__ words, int nwords, con
             for (int L = kLookBits + 1; L < 16; ++L) len += pk >= tab->limit[L] ? 1 : 0;
             sym = tab->huffval[((int)(pk >> (16 - len)) + tab->valoffset[len]) & 255];
         }
-        const int size = is_dc ? (sym > 15 ? 15 : sym) : (sym & 15);
-        const int run = is_dc ? 0 : (sym >> 4);
+        const int dm = is_dc ? -1 : 0;                                     // all ones for the DC symbol of a block
+        const int size = ((sym > 15 ? 15 : sym) & dm) | ((sym & 15) & ~dm);
+        const int run = (sym >> 4) & ~dm;
         const int v = (int)(((win << len) >> 1) >> (31 - size));          // the `size` bits behind the code (0 for size == 0)
         buf <<= len + size;
         bits -= len + size;
-        const int val = v < ((1 << size) >> 1) ? v - (1 << size) + 1 : v;  // HUFF_EXTEND; size == 0 gives 0
+        const int neg = v < ((1 << size) >> 1) ? -1 : 0;                   // HUFF_EXTEND; size == 0 gives 0
+        const int val = v + ((1 - (1 << size)) & neg);
         // DC: accumulate the prediction of this component
-        pred0 += (is_dc && comp == 0) ? val : 0;
-        pred1 += (is_dc && comp == 1) ? val : 0;
-        pred2 += (is_dc && comp == 2) ? val : 0;
+        pred0 += val & dm & (comp == 0 ? -1 : 0);
+        pred1 += val & dm & (comp == 1 ? -1 : 0);
+        pred2 += val & dm & (comp == 2 ? -1 : 0);
         const int pred = comp == 0 ? pred0 : (comp == 1 ? pred1 : pred2);
         const int kk = kpos + run;                                       // zig-zag position of an AC coefficient
-        const bool coded = is_dc || (size != 0 && kk < 64);
-        const int where = is_dc ? 0 : (int)natural[kk & 63];
-        if (coded) cf[blk + where] = (int16_t)(is_dc ? pred : val);
-        kpos = is_dc ? 1 : (size != 0 ? kk + 1 : (run == 15 ? kpos + 16 : 64));
+        const int cm = (is_dc || (size != 0 && kk < 64)) ? -1 : 0;       // a coefficient is stored
+        const int where = (int)natural[kk & 63] & ~dm;
+        // unconditional store: symbols that carry no coefficient (EOB, ZRL) write to the spare block behind the picture's last
+        cf[((blk + where) & cm) | (spare & ~cm)] = (int16_t)((pred & dm) | (val & ~dm));
+        const int zm = size != 0 ? -1 : 0;
+        const int k_ac = ((kk + 1) & zm) | ((run == 15 ? kpos + 16 : 64) & ~zm);
+        kpos = (1 & dm) | (k_ac & ~dm);
         // ---- end of block
-        const bool end = kpos >= 64;
-        remaining -= end ? 1 : 0;
-        kpos = end ? 0 : kpos;
-        blk += end ? 64 : 0;
-        b = end ? nb : b;
-        comp = end ? ncomp : comp;
-        dsel = end ? ndsel : dsel;
-        asel = end ? nasel : asel;
+        const int em = kpos >= 64 ? -1 : 0;
+        remaining += em;
+        kpos &= ~em;
+        blk += 64 & em;
+        b = (nb & em) | (b & ~em);
+        comp = (ncomp & em) | (comp & ~em);
+        dsel = (ndsel & em) | (dsel & ~em);
+        asel = (nasel & em) | (asel & ~em);
     }
 }
 

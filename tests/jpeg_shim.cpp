@@ -30,7 +30,7 @@ int shim_jpeg_decode(const uint8_t* data, long n, uint8_t* out, char* err, int f
         unstuff_scan(data + h.scan_offset, h.scan_len, reinterpret_cast<uint8_t*>(clean_words.data()), &clean);
         if (!clean || g.restart_interval) { strncpy(err, "restart markers: not for the flat decoder", 255); return -2; }
         const size_t nblocks = (size_t)6 * g.mcus_x * g.mcus_y;
-        std::vector<int16_t> coef(nblocks * 64, 0);
+        std::vector<int16_t> coef((nblocks + 1) * 64, 0);  // + the spare block
         decode_scan_flat(clean_words.data(), (int)clean_words.size(), h.huff, h.td, h.ta, kNaturalOrderHost, g.mcus_x * g.mcus_y, coef.data());
         for (size_t b = 0; b < nblocks; ++b) {  // coefficients are in decoding order: block_position maps them into the planes
             int comp, bx, by;
