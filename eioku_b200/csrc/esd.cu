@@ -480,9 +480,9 @@ int ensure_capacity(esd_ctx* c, int64_t frames_needed) {
     c->d_hash = hwords ? n_hash : nullptr;
     c->d_hmargin = n_hmargin;
     // ratios not yet computed read back as NaN
-    fill_nan_kernel<<<(unsigned)((ncap - used + 255) / 256), 256>>>(c->d_ratio + used, ncap - used);
+    fill_nan_kernel<<<(unsigned)((ncap - used + 255) / 256), 256, 0, c->aux_stream>>>(c->d_ratio + used, ncap - used);
     CU(c, cudaGetLastError());
-    CU(c, cudaDeviceSynchronize());
+    CU(c, cudaStreamSynchronize(c->aux_stream));
     c->cap = ncap;
     return ESD_OK;
 }
@@ -530,12 +530,14 @@ int reset_video_state(esd_ctx* c) {
     c->h2d_copies = 0;
     c->last_batch_base = c->last_batch_n = 0;
     if (c->pf_mailbox) memset(c->pf_mailbox, 0, 8 * sizeof(long long));  // counts and overflow; the tickets keep increasing
-    CU(c, cudaMemset(c->d_state, 0, sizeof(DecisionState)));
+    // on the library's own stream, waiting for this context only: a reset must not stall the other contexts of the device
+    // (several decoder sessions per GPU reset their context once per video)
+    CU(c, cudaMemsetAsync(c->d_state, 0, sizeof(DecisionState), c->aux_stream));
     if (c->cap) {
-        fill_nan_kernel<<<(unsigned)((c->cap + 255) / 256), 256>>>(c->d_ratio, c->cap);
+        fill_nan_kernel<<<(unsigned)((c->cap + 255) / 256), 256, 0, c->aux_stream>>>(c->d_ratio, c->cap);
         CU(c, cudaGetLastError());
     }
-    CU(c, cudaDeviceSynchronize());
+    CU(c, cudaStreamSynchronize(c->aux_stream));
     return ESD_OK;
 }
 
@@ -1241,7 +1243,9 @@ int esd_create(esd_ctx** out, const esd_config* cfg, int device) {
 void esd_destroy(esd_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaDeviceSynchronize();
+    sync_all(c);  // this context's streams only: destroying one context must not stall the others on the device
+    if (c->pf_stream) cudaStreamSynchronize(c->pf_stream);
+    if (c->dec_stream) cudaStreamSynchronize(c->dec_stream);
     esd_ingest_close(c);
     free_plans(c);
     for (auto& ev : c->timing_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
@@ -1271,7 +1275,9 @@ void esd_destroy(esd_ctx* c) {
 int esd_reset(esd_ctx* c) {
     if (!c) return ESD_ERR_INVALID;
     CU(c, cudaSetDevice(c->device));
-    CU(c, cudaDeviceSynchronize());
+    { int rc = sync_all(c); if (rc) return rc; }
+    if (c->pf_stream) CU(c, cudaStreamSynchronize(c->pf_stream));
+    if (c->compute_stream) CU(c, cudaStreamSynchronize(c->compute_stream));
     return reset_video_state(c);
 }
 

@@ -213,8 +213,9 @@ JPG_HD void decode_scan_flat(const uint32_t* __restrict__ words, int nwords, con
     // ends; (4) code and extra bits are taken from one 32-bit window, one 64-bit shift per symbol; (5) the next input word is
     // loaded one refill ahead.
     const HuffTable* const tab0 = &T.dc[0];              // dc[0], dc[1], ac[0], ac[1] are contiguous
-    const int dsel0 = td[0], dsel1 = td[1], dsel2 = td[2];
-    const int asel0 = 2 + ta[0], asel1 = 2 + ta[1], asel2 = 2 + ta[2];
+    const uint32_t dpack = (uint32_t)td[0] | ((uint32_t)td[1] << 8) | ((uint32_t)td[2] << 16);                    // table selector of
+    const uint32_t apack = (uint32_t)(2 + ta[0]) | ((uint32_t)(2 + ta[1]) << 8) | ((uint32_t)(2 + ta[2]) << 16);  // component c in byte c
+    const int dsel0 = td[0], asel0 = 2 + ta[0];
     uint64_t buf = 0;
     int bits = 0, wi = 1;
     uint32_t nextw = nwords > 0 ? words[0] : 0u;         // loaded one refill ahead
@@ -228,8 +229,8 @@ JPG_HD void decode_scan_flat(const uint32_t* __restrict__ words, int nwords, con
         // ---- selectors of the next block (independent of the symbols decoded below)
         const int nb = b == 5 ? 0 : b + 1;
         const int ncomp = nb < 4 ? 0 : nb - 3;
-        const int ndsel = ncomp == 0 ? dsel0 : (ncomp == 1 ? dsel1 : dsel2);
-        const int nasel = ncomp == 0 ? asel0 : (ncomp == 1 ? asel1 : asel2);
+        const int ndsel = (int)((dpack >> (8 * ncomp)) & 255u);
+        const int nasel = (int)((apack >> (8 * ncomp)) & 255u);
         // ---- refill: at most 16 + 15 bits are consumed per symbol
         const bool need = bits <= 32;
         const uint32_t nm = need ? 0xffffffffu : 0u;     // masks instead of ?: below -- the compiler turned the selects into divergent branches
@@ -265,7 +266,7 @@ JPG_HD void decode_scan_flat(const uint32_t* __restrict__ words, int nwords, con
         pred0 += val & dm & (comp == 0 ? -1 : 0);
         pred1 += val & dm & (comp == 1 ? -1 : 0);
         pred2 += val & dm & (comp == 2 ? -1 : 0);
-        const int pred = comp == 0 ? pred0 : (comp == 1 ? pred1 : pred2);
+        const int pred = (pred0 & (comp == 0 ? -1 : 0)) | (pred1 & (comp == 1 ? -1 : 0)) | (pred2 & (comp == 2 ? -1 : 0));
         const int kk = kpos + run;                                       // zig-zag position of an AC coefficient
         const int cm = (is_dc || (size != 0 && kk < 64)) ? -1 : 0;       // a coefficient is stored
         const int where = (int)natural[kk & 63] & ~dm;
