@@ -12,12 +12,12 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("ESD_LIB") or os.path.join(_HERE, "libesd.so")  # ESD_LIB: tuning experiments only
 
 ESD_DET_CONTENT, ESD_DET_ADAPTIVE, ESD_DET_HIST, ESD_DET_THRESHOLD, ESD_DET_HASH = 1, 2, 4, 8, 16
-ESD_ABI_VERSION = 3
+ESD_ABI_VERSION = 4
 ESD_THRESH_FLOOR, ESD_THRESH_CEILING = 0, 1
 ESD_FILTER_MERGE, ESD_FILTER_SUPPRESS = 0, 1
 ESD_DOWNSCALE_FLOAT, ESD_DOWNSCALE_INT = 0, 1
 ESD_SPLIT_AUTO, ESD_SPLIT_STRIPS, ESD_SPLIT_CHUNKS = 0, 1, 2
-ESD_FMT_BGR24, ESD_FMT_NV12 = 0, 1
+ESD_FMT_BGR24, ESD_FMT_NV12, ESD_FMT_I420 = 0, 1, 2
 ESD_SCORE_CONTENT_VAL, ESD_SCORE_ADAPTIVE_VAL, ESD_SCORE_HIST_DIFF, ESD_SCORE_AVERAGE_RGB, ESD_SCORE_HASH_DIST, ESD_SCORE_ADAPTIVE_RATIO = range(6)
 # the score array each detector's decision pass consumes (esd_decide_arrays / esd_decide_device)
 DECISION_SCORE_KIND = {ESD_DET_CONTENT: ESD_SCORE_CONTENT_VAL, ESD_DET_ADAPTIVE: ESD_SCORE_ADAPTIVE_VAL, ESD_DET_HIST: ESD_SCORE_HIST_DIFF,
@@ -27,7 +27,7 @@ DECISION_SCORE_KIND = {ESD_DET_CONTENT: ESD_SCORE_CONTENT_VAL, ESD_DET_ADAPTIVE:
 EXPORTED_SYMBOLS = (
     "esd_abi_version", "esd_strerror", "esd_last_error", "esd_device_count", "esd_config_default",
     "esd_create", "esd_destroy", "esd_reset", "esd_get_geometry", "esd_get_touched_rows",
-    "esd_push_frames", "esd_push_nv12", "esd_push_rows", "esd_ingest_open", "esd_ingest_push_host", "esd_ingest_close", "esd_ingest_set_gather",
+    "esd_push_frames", "esd_push_nv12", "esd_push_i420", "esd_push_rows", "esd_ingest_open", "esd_ingest_push_host", "esd_ingest_close", "esd_ingest_set_gather",
     "esd_ingest_stats", "esd_ingest_wait_copied", "esd_decide_device", "esd_copy_scores_device", "esd_synchronize", "esd_join", "esd_frames_pushed", "esd_read_scores", "esd_read_edge_counts", "esd_read_average_rgb",
     "esd_read_hash", "esd_read_hash_margin", "esd_debug_read_hash_input", "esd_process_frame_host",
     "esd_post_process", "esd_get_cuts",
@@ -107,6 +107,7 @@ def load_library(path: Optional[str] = None):
     L.esd_push_frames.argtypes = [vp, vp, i64, i64, i64, i64, vp]
     L.esd_push_rows.argtypes = [vp, vp, i64, i64, vp]
     L.esd_push_nv12.argtypes = [vp, vp, vp, i64, i64, i64, i64, vp]
+    L.esd_push_i420.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64, i64, vp]
     L.esd_ingest_open.argtypes = [vp, i32, i32]
     L.esd_ingest_push_host.argtypes = [vp, vp, i64, i64, i64, i64]
     L.esd_ingest_close.argtypes = [vp]
@@ -241,22 +242,29 @@ class EsdContext:
         self._check(self._L.esd_push_nv12(self._h, C.c_void_p(y_ptr), C.c_void_p(uv_ptr), n, frame_stride, pitch, first_frame_num,
                                           C.c_void_p(stream)), "esd_push_nv12")
 
+    def push_i420_device(self, y_ptr: int, u_ptr: int, v_ptr: int, n: int, frame_stride: int, pitch_y: int, pitch_uv: int,
+                         first_frame_num: int, stream: int = 0):
+        """Planar YUV 4:2:0 frames on the device, the three planes of frame 0 given separately (an AVFrame's data[0..2])."""
+        self._check(self._L.esd_push_i420(self._h, C.c_void_p(y_ptr), C.c_void_p(u_ptr), C.c_void_p(v_ptr), n, frame_stride, pitch_y,
+                                          pitch_uv, first_frame_num, C.c_void_p(stream)), "esd_push_i420")
+
     def _check_nv12_shape(self, n_rows: int, w: int):
         W, H = self.cfg.src_width, self.cfg.src_height
-        if self.cfg.src_format != ESD_FMT_NV12:
-            raise ValueError("context was not created with src_format = ESD_FMT_NV12")
+        if self.cfg.src_format not in (ESD_FMT_NV12, ESD_FMT_I420):
+            raise ValueError("context was not created with src_format = ESD_FMT_NV12 / ESD_FMT_I420")
         if (w, n_rows) != (W, H * 3 // 2):
-            raise ValueError(f"NV12 frames must be [N, {H * 3 // 2}, {W}] (Y plane then interleaved UV), got [.., {n_rows}, {w}]")
+            raise ValueError(f"YUV 4:2:0 frames must be [N, {H * 3 // 2}, {W}] (Y plane, then the chroma plane(s)), got [.., {n_rows}, {w}]")
 
     def push_nv12_tensor(self, frames, first_frame_num: int, stream: Optional[int] = None):
-        """frames: torch.uint8 CUDA tensor [N, H*3/2, W] -- contiguous NV12 frames (rows dense, any row pitch)."""
+        """frames: torch.uint8 CUDA tensor [N, H*3/2, W] -- contiguous NV12 frames (rows dense, any row pitch), or, on an I420
+        context, contiguous I420 frames (the array cv2.cvtColor(COLOR_YUV2BGR_I420) takes: rows must be W bytes apart)."""
         import torch
 
         if frames.dim() == 2:
             frames = frames.unsqueeze(0)
         if frames.dtype != torch.uint8 or not frames.is_cuda:
             raise ValueError("push_nv12_tensor needs a CUDA uint8 tensor")
-        if frames.stride(2) != 1:
+        if frames.stride(2) != 1 or (self.cfg.src_format == ESD_FMT_I420 and frames.stride(1) != frames.shape[2]):
             frames = frames.contiguous()
         n, rows, w = frames.shape
         self._check_nv12_shape(rows, w)
@@ -269,7 +277,7 @@ class EsdContext:
         """Host NV12 frames [N, H*3/2, W] through the ingest ring (touched Y and UV rows only cross PCIe)."""
         if frames.ndim == 2:
             frames = frames[None]
-        if frames.dtype != np.uint8 or frames.strides[2] != 1:
+        if frames.dtype != np.uint8 or frames.strides[2] != 1 or (self.cfg.src_format == ESD_FMT_I420 and frames.strides[1] != frames.shape[2]):
             frames = np.ascontiguousarray(frames, np.uint8)
         n, rows, w = frames.shape
         self._check_nv12_shape(rows, w)

@@ -206,7 +206,11 @@ struct esd_ctx {
     int dst_w = 0, dst_h = 0, row_bytes = 0;
     int alg_row_bytes = 0;  // 32-byte sectors of a row that contain a horizontal tap, in bytes
     int64_t alg_frame_bytes = 0;  // sum over the touched rows (NV12: Y rows and UV rows have different sector sets)
-    bool nv12 = false;
+    bool nv12 = false;      // the fused kernel's YUV 4:2:0 variant (NV12 and I420 contexts)
+    bool i420 = false;      // planar chroma: the touched U / V rows are interleaved into NV12 rows first (i420_interleave_kernel)
+    int* d_uv_src_rows = nullptr;   // I420: chroma row of each touched UV row, in `touched` order
+    uint8_t* d_uvpack = nullptr;    // I420 device pushes: [n][touched UV rows][row_bytes] interleaved chroma (grow-only)
+    size_t uvpack_bytes = 0;
     bool extras = false;    // the fused kernel also emits sum(B+G+R) / the V plane / the gray plane (kernel template EXTRAS)
     int n_touched_y = 0;    // NV12: the first n_touched_y entries of `touched` are Y rows, the rest UV rows (as H + row)
     bool resize = false;
@@ -594,12 +598,14 @@ struct TraceTimer {
 };
 
 enum Layout { LAYOUT_FULL = 0, LAYOUT_ROWS = 1, LAYOUT_TAPS = 2 };
+// I420 device pushes: the touched chroma rows, interleaved, in a buffer of their own ([n][touched UV rows] rows of `row_stride`)
+struct UvPacked { int64_t frame_stride, row_stride; };
 
 // inline_tail: run the finalize/decision tail on `st` itself (per-frame path: nothing to overlap with, and the
 // cross-stream event round trip would cost more than the tail)
 int push_common(esd_ctx* c, const uint8_t* d_src, int64_t n, int64_t frame_stride, int64_t row_stride, int layout,
                 int64_t first_frame_num, cudaStream_t st, bool inline_tail = false, long long* mailbox = nullptr,
-                const uint8_t* d_uv = nullptr) {
+                const uint8_t* d_uv = nullptr, const UvPacked* uvp = nullptr) {
     const bool compact = layout != LAYOUT_FULL;
     TraceTimer tr;
     if (!d_src || n <= 0) return fail(c, ESD_ERR_INVALID, "push: null frames or n <= 0");
@@ -639,6 +645,9 @@ int push_common(esd_ctx* c, const uint8_t* d_src, int64_t n, int64_t frame_strid
     p.src_uv = d_uv ? d_uv : d_src + (int64_t)c->cfg.src_height * row_stride;  // NV12 default: UV plane right behind the Y plane
     p.frame_stride = frame_stride;
     p.row_stride = row_stride;
+    p.uv_frame_stride = uvp ? uvp->frame_stride : frame_stride;
+    p.uv_row_stride = uvp ? uvp->row_stride : row_stride;
+    p.uv_packed_base = uvp ? c->n_touched_y : -1;
     p.compact = compact ? 1 : 0;
     p.n_frames = (int)n;
     p.dst_w = c->dst_w;
@@ -678,7 +687,7 @@ int push_common(esd_ctx* c, const uint8_t* d_src, int64_t n, int64_t frame_strid
         CU(c, cudaEventRecord(e0, st));
     }
     const bool aligned = ((reinterpret_cast<uintptr_t>(d_src) | (c->nv12 ? reinterpret_cast<uintptr_t>(p.src_uv) : 0) |
-                           (uintptr_t)frame_stride | (uintptr_t)row_stride) & 15u) == 0;
+                           (uintptr_t)frame_stride | (uintptr_t)row_stride | (uintptr_t)p.uv_frame_stride | (uintptr_t)p.uv_row_stride) & 15u) == 0;
     CU(c, ESD_DISPATCH(launch_fused_rp, c->resize, c->pxt, c->need_content, c->need_hist, aligned, c->nv12, c->extras, p, plan.grid, c->smem_bytes, st, kg));
     guard.armed = true;
     if (!c->started) {
@@ -888,13 +897,14 @@ int esd_create(esd_ctx** out, const esd_config* cfg, int device) {
     }
     c->dst_w = dw; c->dst_h = dh;
     c->resize = !(dw == W && dh == H);
-    c->nv12 = cfg->src_format == ESD_FMT_NV12;
-    if (cfg->src_format != ESD_FMT_BGR24 && cfg->src_format != ESD_FMT_NV12) {
+    c->i420 = cfg->src_format == ESD_FMT_I420;
+    c->nv12 = cfg->src_format == ESD_FMT_NV12 || c->i420;
+    if (cfg->src_format != ESD_FMT_BGR24 && cfg->src_format != ESD_FMT_NV12 && cfg->src_format != ESD_FMT_I420) {
         fail(c, ESD_ERR_INVALID, "esd_create: unknown src_format %d", cfg->src_format);
         return bail(ESD_ERR_INVALID);
     }
     if (c->nv12 && (!c->resize || (W & 1) || (H & 1) || H > 32766 || W > 8190)) {
-        fail(c, ESD_ERR_UNSUPPORTED, "NV12 input needs even dimensions and a downscaling context (frames %dx%d -> %dx%d)", W, H, dw, dh);
+        fail(c, ESD_ERR_UNSUPPORTED, "NV12 / I420 input needs even dimensions and a downscaling context (frames %dx%d -> %dx%d)", W, H, dw, dh);
         return bail(ESD_ERR_UNSUPPORTED);
     }
     c->row_bytes = c->nv12 ? W : W * 3;
@@ -1063,6 +1073,12 @@ int esd_create(esd_ctx** out, const esd_config* cfg, int device) {
                 yr[y].uvrows = (uint32_t)(yo0[y] >> 1) | ((uint32_t)(yo1[y] >> 1) << 16);
                 yr[y].cuvrows = (uint32_t)uvidx[yo0[y] >> 1] | ((uint32_t)uvidx[yo1[y] >> 1] << 16);
             }
+        }
+        if (c->i420) {
+            std::vector<int> rows;
+            for (size_t i = (size_t)c->n_touched_y; i < c->touched.size(); ++i) rows.push_back(c->touched[i] - H);
+            CUB(cudaMalloc(&c->d_uv_src_rows, sizeof(int) * std::max<size_t>(1, rows.size())));
+            CUB(cudaMemcpy(c->d_uv_src_rows, rows.data(), sizeof(int) * rows.size(), cudaMemcpyHostToDevice));
         }
         CUB(cudaMalloc(&c->d_yrows, sizeof(YRow) * dh));
         CUB(cudaMemcpy(c->d_yrows, yr.data(), sizeof(YRow) * dh, cudaMemcpyHostToDevice));
@@ -1250,6 +1266,7 @@ void esd_destroy(esd_ctx* c) {
     free_plans(c);
     for (auto& ev : c->timing_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     cudaFree(c->d_xtab_taps);
+    cudaFree(c->d_uv_src_rows); cudaFree(c->d_uvpack);
     cudaFree(c->d_yrows); cudaFree(c->d_xtab); cudaFree(c->d_sdiv); cudaFree(c->d_hdiv);
     cudaFree(c->d_prev[0]); cudaFree(c->d_prev[1]); cudaFree(c->d_state); cudaFree(c->d_cuts);
     cudaFree(c->d_slab);
@@ -1304,6 +1321,12 @@ int esd_get_touched_rows(const esd_ctx* c, int32_t* rows, int32_t cap) {
 int esd_push_frames(esd_ctx* c, const uint8_t* d_bgr, int64_t n, int64_t frame_stride, int64_t pitch,
                     int64_t first_frame_num, void* stream) {
     if (!c) return ESD_ERR_INVALID;
+    if (c->i420) {  // contiguous I420 frames: Y plane (pitch), then the U and the V plane (pitch / 2 each, src_height / 2 rows)
+        if (pitch & 1) return fail(c, ESD_ERR_INVALID, "push: I420 frames need an even pitch (chroma rows are pitch / 2 apart)");
+        const uint8_t* d_u = d_bgr ? d_bgr + (int64_t)c->cfg.src_height * pitch : nullptr;
+        return esd_push_i420(c, d_bgr, d_u, d_u ? d_u + (int64_t)(c->cfg.src_height / 2) * (pitch / 2) : nullptr, n, frame_stride, pitch,
+                             pitch / 2, first_frame_num, stream);
+    }
     if (c->nv12)  // contiguous NV12 frames: the UV plane starts at row src_height of the same pitch
         return esd_push_nv12(c, d_bgr, d_bgr ? d_bgr + (int64_t)c->cfg.src_height * pitch : nullptr, n, frame_stride, pitch,
                              first_frame_num, stream);
@@ -1321,7 +1344,7 @@ int esd_push_frames(esd_ctx* c, const uint8_t* d_bgr, int64_t n, int64_t frame_s
 int esd_push_nv12(esd_ctx* c, const uint8_t* d_y, const uint8_t* d_uv, int64_t n, int64_t frame_stride, int64_t pitch,
                   int64_t first_frame_num, void* stream) {
     if (!c) return ESD_ERR_INVALID;
-    if (!c->nv12) return fail(c, ESD_ERR_STATE, "push_nv12: the context was created for BGR24 frames (src_format)");
+    if (!c->nv12 || c->i420) return fail(c, ESD_ERR_STATE, "push_nv12: the context was not created for NV12 frames (src_format)");
     if (!d_y || !d_uv) return fail(c, ESD_ERR_INVALID, "push_nv12: null plane");
     if (pitch < c->row_bytes) return fail(c, ESD_ERR_INVALID, "push_nv12: pitch %lld < row bytes %d", (long long)pitch, c->row_bytes);
     const int H = c->cfg.src_height;
@@ -1333,6 +1356,58 @@ int esd_push_nv12(esd_ctx* c, const uint8_t* d_y, const uint8_t* d_uv, int64_t n
         if (rc) return rc;
     }
     return push_common(c, d_y, n, frame_stride, pitch, LAYOUT_FULL, first_frame_num, (cudaStream_t)stream, false, nullptr, d_uv);
+}
+
+// launches i420_interleave_kernel for n frames: chroma rows from (u, v) -> interleaved rows at dst
+static int interleave_chroma(esd_ctx* c, const uint8_t* u, const uint8_t* v, int64_t src_fs, int64_t src_pitch, const int* src_rows,
+                             uint8_t* dst, int64_t dst_fs, int64_t dst_pitch, int64_t n, cudaStream_t st) {
+    const int n_uv = (int)c->touched.size() - c->n_touched_y;
+    const int half_w = c->cfg.src_width / 2;
+    for (int64_t f0 = 0; f0 < n; f0 += 65535) {  // gridDim.y limit
+        const int64_t m = std::min<int64_t>(65535, n - f0);
+        CU(c, klaunch(c->kg, st, i420_interleave_kernel, dim3((unsigned)n_uv, (unsigned)m), dim3(kInterleaveThreads), (size_t)(2 * half_w),
+                      u + f0 * src_fs, v + f0 * src_fs, (long long)src_fs, (long long)src_pitch, src_rows, dst + f0 * dst_fs,
+                      (long long)dst_fs, (long long)dst_pitch, half_w));
+        c->launches++;
+    }
+    return ESD_OK;
+}
+
+int esd_push_i420(esd_ctx* c, const uint8_t* d_y, const uint8_t* d_u, const uint8_t* d_v, int64_t n, int64_t frame_stride,
+                  int64_t pitch_y, int64_t pitch_uv, int64_t first_frame_num, void* stream) {
+    if (!c) return ESD_ERR_INVALID;
+    if (!c->i420) return fail(c, ESD_ERR_STATE, "push_i420: the context was not created for I420 frames (src_format)");
+    if (!d_y || !d_u || !d_v) return fail(c, ESD_ERR_INVALID, "push_i420: null plane");
+    if (n <= 0) return fail(c, ESD_ERR_INVALID, "push: null frames or n <= 0");
+    if (pitch_y < c->row_bytes || pitch_uv < c->row_bytes / 2)
+        return fail(c, ESD_ERR_INVALID, "push_i420: pitch %lld / %lld < row bytes %d / %d", (long long)pitch_y, (long long)pitch_uv,
+                    c->row_bytes, c->row_bytes / 2);
+    const int H = c->cfg.src_height;
+    const size_t fspan = (size_t)(n - 1) * (size_t)frame_stride;
+    int rc = validate_device_span(c, d_y, fspan + (size_t)(H - 1) * (size_t)pitch_y + (size_t)c->row_bytes, "push_i420 (Y plane)");
+    if (rc) return rc;
+    const size_t cspan = fspan + (size_t)(H / 2 - 1) * (size_t)pitch_uv + (size_t)(c->row_bytes / 2);
+    if ((rc = validate_device_span(c, d_u, cspan, "push_i420 (U plane)"))) return rc;
+    if ((rc = validate_device_span(c, d_v, cspan, "push_i420 (V plane)"))) return rc;
+    if (c->poisoned) return fail(c, ESD_ERR_STATE, "push: an earlier push failed half-way; call esd_reset");
+    CU(c, cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n_uv = (int64_t)c->touched.size() - c->n_touched_y;
+    const int64_t uv_pitch = (c->row_bytes + 15) & ~15;
+    const size_t need = (size_t)n * (size_t)n_uv * (size_t)uv_pitch;
+    if (need > c->uvpack_bytes) {
+        if ((rc = sync_all(c))) return rc;  // an earlier push may still read the old buffer
+        cudaFree(c->d_uvpack);
+        c->d_uvpack = nullptr;
+        c->uvpack_bytes = 0;
+        CU(c, cudaMalloc(&c->d_uvpack, need));
+        c->uvpack_bytes = need;
+    }
+    // the repack writes the buffer the previous push's fused kernel reads: order this stream behind it first
+    if ((rc = order_after_last(c, st))) return rc;
+    if ((rc = interleave_chroma(c, d_u, d_v, frame_stride, pitch_uv, c->d_uv_src_rows, c->d_uvpack, n_uv * uv_pitch, uv_pitch, n, st))) return rc;
+    const UvPacked uvp{n_uv * uv_pitch, uv_pitch};
+    return push_common(c, d_y, n, frame_stride, pitch_y, LAYOUT_FULL, first_frame_num, st, false, nullptr, c->d_uvpack, &uvp);
 }
 
 int esd_push_rows(esd_ctx* c, const uint8_t* d_rows, int64_t n, int64_t first_frame_num, void* stream) {
@@ -1402,6 +1477,7 @@ int esd_ingest_push_host(esd_ctx* c, const uint8_t* h_bgr, int64_t n, int64_t fr
     if (c->ring.empty()) return fail(c, ESD_ERR_STATE, "ingest ring not open");
     if (!h_bgr || n <= 0) return fail(c, ESD_ERR_INVALID, "ingest: null frames or n <= 0");
     if (pitch < c->row_bytes) return fail(c, ESD_ERR_INVALID, "ingest: pitch < row bytes");
+    if (c->i420 && (pitch & 1)) return fail(c, ESD_ERR_INVALID, "ingest: I420 frames need an even pitch (chroma rows are pitch / 2 apart)");
     CU(c, cudaSetDevice(c->device));
     cudaPointerAttributes attr;
     bool pinned = false;
@@ -1412,9 +1488,14 @@ int esd_ingest_push_host(esd_ctx* c, const uint8_t* h_bgr, int64_t n, int64_t fr
     // runs of consecutive touched rows: (first compact index, first source row, length)
     struct Run { int crow, row, len; };
     std::vector<Run> runs;
-    for (int i = 0; i < (int)nt;) {
+    // I420: only the Y rows go by runs; a touched chroma row is two half rows (U, V) from two planes, copied side by side into its
+    // compact row and interleaved on the device (i420_interleave_kernel, in place) before the fused kernel reads it
+    const int nt_runs = c->i420 ? c->n_touched_y : (int)nt;
+    const int H = c->cfg.src_height, half_row = c->row_bytes / 2;
+    const int64_t u_off = (int64_t)H * pitch, v_off = u_off + (int64_t)(H / 2) * (pitch / 2);
+    for (int i = 0; i < nt_runs;) {
         int j = i + 1;
-        while (j < (int)nt && c->touched[j] == c->touched[j - 1] + 1 && pitch == c->row_bytes) ++j;
+        while (j < nt_runs && c->touched[j] == c->touched[j - 1] + 1 && pitch == c->row_bytes) ++j;
         runs.push_back(Run{i, c->touched[i], j - i});
         i = j;
     }
@@ -1447,6 +1528,8 @@ int esd_ingest_push_host(esd_ctx* c, const uint8_t* h_bgr, int64_t n, int64_t fr
             gs.n_touched = nt;
             gs.n_touched_y = c->n_touched_y;
             gs.nv12 = c->nv12;
+            gs.i420 = c->i420;
+            gs.src_height = H;
             // measured best of 0 / 512 ... 8192 at 1080p (profiles/r01_gather_prefetch.log); never further than one row
             gs.prefetch_bytes = std::min(pf_env >= 0 ? pf_env : 4096, c->row_bytes);
             gs.nt_stores = !nt_off;  // +11 % with 16 threads (profiles/r01_gather_prefetch.log)
@@ -1479,6 +1562,15 @@ int esd_ingest_push_host(esd_ctx* c, const uint8_t* h_bgr, int64_t n, int64_t fr
                                         (size_t)r.len * c->row_bytes, (size_t)m, cudaMemcpyHostToDevice, c->copy_stream));
                 c->h2d_copies++;
             }
+            for (int i = nt_runs; i < (int)nt; ++i) {
+                const int64_t r = c->touched[i] - H;
+                uint8_t* drow = s.d_rows + (int64_t)i * c->row_bytes;
+                CU(c, cudaMemcpy2DAsync(drow, (size_t)cfb, src + u_off + r * (pitch / 2), (size_t)frame_stride, (size_t)half_row, (size_t)m,
+                                        cudaMemcpyHostToDevice, c->copy_stream));
+                CU(c, cudaMemcpy2DAsync(drow + half_row, (size_t)cfb, src + v_off + r * (pitch / 2), (size_t)frame_stride, (size_t)half_row,
+                                        (size_t)m, cudaMemcpyHostToDevice, c->copy_stream));
+                c->h2d_copies += 2;
+            }
         } else {
             // pageable source: the CPU gathers the touched rows into the pinned slot
             { int rcp = ensure_pinned(c, s, (size_t)c->frames_per_slot * cfb); if (rcp) return rcp; }
@@ -1486,12 +1578,25 @@ int esd_ingest_push_host(esd_ctx* c, const uint8_t* h_bgr, int64_t n, int64_t fr
                 for (const Run& r : runs)
                     memcpy(s.h_pinned + f * cfb + (int64_t)r.crow * c->row_bytes, src + f * frame_stride + (int64_t)r.row * pitch,
                            (size_t)r.len * c->row_bytes);
+            for (int64_t f = 0; f < m; ++f)
+                for (int i = nt_runs; i < (int)nt; ++i) {
+                    const int64_t r = c->touched[i] - H;
+                    uint8_t* drow = s.h_pinned + f * cfb + (int64_t)i * c->row_bytes;
+                    memcpy(drow, src + f * frame_stride + u_off + r * (pitch / 2), (size_t)half_row);
+                    memcpy(drow + half_row, src + f * frame_stride + v_off + r * (pitch / 2), (size_t)half_row);
+                }
             CU(c, cudaMemcpyAsync(s.d_rows, s.h_pinned, (size_t)(m * cfb), cudaMemcpyHostToDevice, c->copy_stream));
             c->h2d_copies++;
         }
         c->h2d_bytes += m * cfb;
         CU(c, cudaEventRecord(s.copied, c->copy_stream));
         CU(c, cudaStreamWaitEvent(c->compute_stream, s.copied, 0));
+        if (c->i420) {
+            int rci = order_after_last(c, c->compute_stream);
+            uint8_t* uv0 = s.d_rows + (int64_t)c->n_touched_y * c->row_bytes;
+            if (!rci) rci = interleave_chroma(c, uv0, uv0 + half_row, cfb, c->row_bytes, nullptr, uv0, cfb, c->row_bytes, m, c->compute_stream);
+            if (rci) return rci;
+        }
         int rc = esd_push_rows(c, s.d_rows, m, first_frame_num + done, c->compute_stream);
         if (rc) return rc;
         CU(c, cudaEventRecord(s.consumed, c->compute_stream));

@@ -55,6 +55,12 @@ struct esd_mjpeg {
     size_t h_stage_bytes[2] = {0, 0};
     cudaEvent_t done[2] = {nullptr, nullptr};
     bool in_flight[2] = {false, false};
+    // ESD_DEC_TIMING=1: CUDA events around the stages of every batch, summarised on stderr when the handle closes
+    bool timing = getenv("ESD_DEC_TIMING") != nullptr;
+    cudaEvent_t tev[2][4] = {};
+    bool tev_armed[2] = {false, false};
+    double t_sum[4] = {0, 0, 0, 0};   // ms: staging copy + clear, entropy, idct + colour, host staging
+    int64_t t_batches = 0, t_pictures = 0;
     int64_t reads = 0;
     std::vector<const unsigned char*> ptrs;
     std::vector<size_t> lens;
@@ -317,14 +323,31 @@ int esd_decode_abi_version(void) { return ESD_DECODE_ABI_VERSION; }
 
 const char* esd_mjpeg_last_error(const esd_mjpeg* h) { return h ? h->err.c_str() : g_open_error.c_str(); }
 
+static void collect_timing(esd_mjpeg* h, int b) {
+    if (!h->timing || !h->tev_armed[b]) return;
+    h->tev_armed[b] = false;
+    for (int k = 0; k < 3; ++k) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, h->tev[b][k], h->tev[b][k + 1]) == cudaSuccess) h->t_sum[k] += ms;
+    }
+    h->t_batches++;
+    cudaGetLastError();
+}
+
 void esd_mjpeg_close(esd_mjpeg* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     for (int b = 0; b < 2; ++b) {
         if (h->done[b]) { cudaEventSynchronize(h->done[b]); cudaEventDestroy(h->done[b]); }
+        collect_timing(h, b);
+        for (int k = 0; k < 4; ++k) if (h->tev[b][k]) cudaEventDestroy(h->tev[b][k]);
         cudaFree(h->d_out[b]);
         if (h->h_stage[b]) cudaFreeHost(h->h_stage[b]);
     }
+    if (h->timing && h->t_batches)
+        fprintf(stderr, "[esd_decode timing] %lld batches, %lld pictures: host staging %.2f ms, copy+clear %.2f ms, entropy %.2f ms, idct+colour %.2f ms per batch\n",
+                (long long)h->t_batches, (long long)h->t_pictures, h->t_sum[3] / h->t_batches, h->t_sum[0] / h->t_batches, h->t_sum[1] / h->t_batches,
+                h->t_sum[2] / h->t_batches);
     cudaFree(h->d_comp); cudaFree(h->d_coef); cudaFree(h->d_planes);
     if (h->state) nvjpegJpegStateDestroy(h->state);
     if (h->nj) nvjpegDestroy(h->nj);
@@ -470,7 +493,10 @@ int esd_mjpeg_read(esd_mjpeg* h, int64_t max_frames, void* stream, uint8_t** d_b
         cudaError_t e = cudaEventSynchronize(h->done[b]);
         if (e != cudaSuccess) return fail(h, ESD_DEC_ERR_CUDA, "decode of an earlier batch failed: %s", cudaGetErrorString(e));
         h->in_flight[b] = false;
+        collect_timing(h, b);
     }
+    timespec ts0;
+    clock_gettime(CLOCK_MONOTONIC, &ts0);
     const bool native = h->backend == ESD_JPEG_NATIVE;
     // pinned staging of the batch: [descriptors n x 16][quantisation tables n x 3 x 64 x u16][pictures, 64-byte aligned]
     const size_t meta = native ? (((size_t)n * sizeof(esd_mjpeg::NativeDesc) + (size_t)n * 3 * 64 * sizeof(uint16_t) + 63) & ~(size_t)63) : 0;
@@ -550,6 +576,14 @@ int esd_mjpeg_read(esd_mjpeg* h, int64_t max_frames, void* stream, uint8_t** d_b
         L.blocks_per_frame = h->blocks_per_frame;
         for (int c = 0; c < 3; ++c) { L.td[c] = h->td[c]; L.ta[c] = h->ta[c]; }
         L.plane_bytes = h->plane_bytes;
+        if (h->timing) {
+            timespec ts1;
+            clock_gettime(CLOCK_MONOTONIC, &ts1);
+            h->t_sum[3] += (ts1.tv_sec - ts0.tv_sec) * 1e3 + (ts1.tv_nsec - ts0.tv_nsec) * 1e-6;
+            h->t_pictures += n;
+            for (int k = 0; k < 4; ++k) if (!h->tev[b][k]) cudaEventCreate(&h->tev[b][k]);
+            cudaEventRecord(h->tev[b][0], st);
+        }
         cudaError_t e = cudaMemcpyAsync(h->d_comp, h->h_stage[b], total, cudaMemcpyHostToDevice, st);
         if (e == cudaSuccess) e = cudaMemsetAsync(h->d_coef, 0, (size_t)n * h->blocks_per_frame * 64 * sizeof(int16_t), st);
         if (e != cudaSuccess) return fail(h, ESD_DEC_ERR_CUDA, "native decode: staging copy failed: %s", cudaGetErrorString(e));
@@ -557,10 +591,13 @@ int esd_mjpeg_read(esd_mjpeg* h, int64_t max_frames, void* stream, uint8_t** d_b
         const uint16_t* dquant = reinterpret_cast<const uint16_t*>(h->d_comp + (size_t)n * sizeof(esd_mjpeg::NativeDesc));
         const unsigned egrid = (unsigned)((n + kEntropyThreads - 1) / kEntropyThreads);
         const size_t esmem = kEntropyThreads * sizeof(esdjpeg::ScanTables);
+        if (h->timing) cudaEventRecord(h->tev[b][1], st);
         if (h->flat) jpeg_entropy_flat_kernel<<<egrid, kEntropyThreads, esmem, st>>>(L, h->d_comp, ddesc, h->d_coef);
         else jpeg_entropy_kernel<<<egrid, kEntropyThreads, esmem, st>>>(L, h->d_comp, ddesc, h->d_coef);
+        if (h->timing) cudaEventRecord(h->tev[b][2], st);
         jpeg_idct_kernel<<<dim3((unsigned)((h->blocks_per_frame + 127) / 128), (unsigned)n), 128, 0, st>>>(L, h->d_coef, dquant, h->d_planes);
         jpeg_color_kernel<<<dim3((unsigned)(((h->width + 3) / 4 + 255) / 256), (unsigned)h->height, (unsigned)n), 256, 0, st>>>(L, h->d_planes, h->d_out[b]);
+        if (h->timing) { cudaEventRecord(h->tev[b][3], st); h->tev_armed[b] = true; }
         e = cudaGetLastError();
         if (e != cudaSuccess) return fail(h, ESD_DEC_ERR_CUDA, "native decode kernels: %s", cudaGetErrorString(e));
     } else {

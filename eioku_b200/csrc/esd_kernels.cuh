@@ -38,10 +38,12 @@ struct YRow {  // per destination row
 
 struct FusedParams {
     const uint8_t* src;
-    const uint8_t* src_uv;   // NV12: interleaved UV plane of frame 0 (same row and frame strides as the Y plane)
+    const uint8_t* src_uv;   // NV12: interleaved UV plane of frame 0 (full layout; the compact layout keeps UV rows behind the Y rows)
     long long frame_stride;  // bytes between frames
     long long row_stride;    // bytes between rows (pitch, or row_bytes in the compact layout)
+    long long uv_frame_stride, uv_row_stride;  // NV12, full layout: the same two for the UV plane (a decoder surface: equal to Y's)
     int compact;
+    int uv_packed_base;  // >= 0: src_uv holds only the touched UV rows (I420 repack, i420_interleave_kernel): row index = cuvrows - this
     int n_frames;
     int dst_w, dst_h;
     int row_bytes;  // bytes of one source row: src_w * 3 (BGR24) or src_w (NV12: Y rows and UV rows alike)
@@ -460,10 +462,12 @@ __global__ void __launch_bounds__(kThreads) fused_score_kernel(const FusedParams
                             uint32_t misuv = 0;
                             if (NV12) {
                                 // UV rows: from the UV plane (full layout) or from the compact frame (absolute indices)
-                                const uint8_t* uvbase = p.compact ? frame : p.src_uv + (long long)f * p.frame_stride;
-                                const uint32_t rows = p.compact ? yr.cuvrows : yr.uvrows;
-                                const uint8_t* u0 = uvbase + (long long)(rows & 0xffffu) * p.row_stride;
-                                const uint8_t* u1 = uvbase + (long long)(rows >> 16) * p.row_stride;
+                                const uint8_t* uvbase = p.compact ? frame : p.src_uv + (long long)f * p.uv_frame_stride;
+                                const long long uvrs = p.compact ? p.row_stride : p.uv_row_stride;
+                                uint32_t rows = p.compact ? yr.cuvrows : yr.uvrows;
+                                if (!p.compact && p.uv_packed_base >= 0) rows = yr.cuvrows - (uint32_t)p.uv_packed_base * 0x10001u;
+                                const uint8_t* u0 = uvbase + (long long)(rows & 0xffffu) * uvrs;
+                                const uint8_t* u1 = uvbase + (long long)(rows >> 16) * uvrs;
                                 const uint32_t m0 = ALIGNED ? 0u : (uint32_t)(reinterpret_cast<uintptr_t>(u0) & 15u);
                                 const uint32_t m1 = ALIGNED ? 0u : (uint32_t)(reinterpret_cast<uintptr_t>(u1) & 15u);
                                 nbu0[q] = (m0 + (uint32_t)p.row_bytes + 15u) & ~15u;
@@ -640,6 +644,44 @@ __device__ __forceinline__ double content_val_of(const unsigned long long s[3], 
     acc = __dadd_rn(acc, __dmul_rn(dv, W.w[2]));
     acc = __dadd_rn(acc, __dmul_rn(de, W.w[3]));
     return __ddiv_rn(acc, W.div);
+}
+
+// Planar I420 (what software decoders emit: Y plane, U plane, V plane, chroma planes half-size) -> the interleaved UV rows the
+// NV12 variant of the fused kernel stages.  One block per (touched chroma row j, frame): the U and V halves of the row go
+// through shared memory, so the kernel also works IN PLACE on a ring-slot row that holds [U row][V row] (what the ingest's DMA
+// leaves there: a copy engine cannot interleave).  Only the chroma rows the taps touch are converted.
+constexpr int kInterleaveThreads = 128;
+__global__ void __launch_bounds__(kInterleaveThreads) i420_interleave_kernel(
+    const uint8_t* __restrict__ u_plane, const uint8_t* __restrict__ v_plane, long long src_frame_stride, long long src_pitch,
+    const int* __restrict__ src_rows /* [gridDim.x] chroma row per j, or nullptr: row j */, uint8_t* __restrict__ dst,
+    long long dst_frame_stride, long long dst_pitch, int half_w) {
+    extern __shared__ uint8_t s_uv[];  // [2][half_w]
+    const int j = blockIdx.x, f = blockIdx.y;
+    const long long r = src_rows ? src_rows[j] : j;
+    const uint8_t* u = u_plane + f * src_frame_stride + r * src_pitch;
+    const uint8_t* v = v_plane + f * src_frame_stride + r * src_pitch;
+    for (int x = threadIdx.x; x < half_w; x += kInterleaveThreads) {
+        s_uv[x] = u[x];
+        s_uv[half_w + x] = v[x];
+    }
+    __syncthreads();
+    uint8_t* out = dst + f * dst_frame_stride + (long long)j * dst_pitch;
+    if ((reinterpret_cast<uintptr_t>(out) & 3u) == 0) {
+        for (int x = 2 * threadIdx.x; x < half_w; x += 2 * kInterleaveThreads) {  // two chroma pairs per 32-bit store
+            if (x + 1 < half_w) {
+                *reinterpret_cast<uint32_t*>(out + 2 * x) = (uint32_t)s_uv[x] | ((uint32_t)s_uv[half_w + x] << 8) |
+                                                            ((uint32_t)s_uv[x + 1] << 16) | ((uint32_t)s_uv[half_w + x + 1] << 24);
+            } else {
+                out[2 * x] = s_uv[x];
+                out[2 * x + 1] = s_uv[half_w + x];
+            }
+        }
+    } else {
+        for (int x = threadIdx.x; x < half_w; x += kInterleaveThreads) {
+            out[2 * x] = s_uv[x];
+            out[2 * x + 1] = s_uv[half_w + x];
+        }
+    }
 }
 
 // one warp per frame: reduce the per-(group,warp) partials, emit sums and both content_val flavours

@@ -5,6 +5,9 @@
 //   BGR24: 6 bytes [tap0 B G R, tap1 B G R] at byte 3 * x0         -> written at byte 6 * d of the gathered row
 //   NV12 Y row: 2 bytes [Y(x0), Y(x0 + 1)]                          -> written at byte 2 * d
 //   NV12 UV row: the chroma pairs of the two taps [U V, U' V']      -> written at byte 4 * d
+//   I420 (planar chroma, contiguous frame: Y rows of `pitch`, then src_height / 2 U rows and as many V rows of pitch / 2):
+//        Y rows as NV12's; a chroma row reads U[c], V[c] from the two planes and writes the same interleaved pairs at 4 * d,
+//        so the device sees exactly the NV12 tap layout
 // (x0 = source column of tap 0; a clamped last column repeats the last pixel -- its tap 1 has weight 0).
 // The rows of a frame are laid out in the order of the touched-row list with one pitch (`tap_row_bytes`).
 #pragma once
@@ -25,6 +28,8 @@ struct GatherSpec {
     int64_t n_touched;
     int n_touched_y;        // NV12: how many of them are Y rows
     bool nv12;
+    bool i420;              // planar chroma (nv12 is set too: the gathered layout is NV12's)
+    int src_height;         // I420: rows of the Y plane
     int prefetch_bytes;     // rolling software prefetch distance (0 = touch the next row's pages only)
     bool nt_stores;         // assemble each row in L1 and stream it out with non-temporal stores
 };
@@ -42,6 +47,9 @@ inline void gather_tap_rows(const GatherSpec& g, const uint8_t* src, int64_t fra
     for (int64_t it = lo; it < hi; ++it) {
         const int64_t f = it / g.n_touched, i = it - f * g.n_touched;
         const uint8_t* sr = src + f * frame_stride + (int64_t)g.touched[i] * pitch;
+        const bool planar_chroma = g.i420 && i >= g.n_touched_y;
+        if (planar_chroma)  // U row of chroma row r; the V row lies src_height / 2 chroma rows further
+            sr = src + f * frame_stride + (int64_t)g.src_height * pitch + (int64_t)(g.touched[i] - g.src_height) * (pitch / 2);
         uint8_t* const out_row = dst_base + it * trb;
         // the ring slot is written once and read by the DMA engine: no read-for-ownership of the gathered bytes
         uint8_t* dr = nt ? tmp_row : out_row;
@@ -66,6 +74,19 @@ inline void gather_tap_rows(const GatherSpec& g, const uint8_t* src, int64_t fra
             }
             for (; d < dw; ++d) dr[2 * d] = dr[2 * d + 1] = sr[rb - 1];  // clamped last column
             if (nt) memset(dr + 2 * dw, 0, (size_t)(trb - 2 * dw));
+        } else if (planar_chroma) {
+            const uint8_t* sv = sr + (int64_t)(g.src_height / 2) * (pitch / 2);
+            const int cw = rb / 2;
+            for (; d < dw; ++d) {
+                const int x0 = off[d];
+                if (pf > 0 && (d & 15) == 0) {
+                    const int o = (x0 + pf) >> 1;
+                    if (o < cw) { __builtin_prefetch(sr + o, 0, 3); __builtin_prefetch(sv + o, 0, 3); }
+                }
+                const int c0 = x0 >> 1, c1 = ((x0 & 1) && c0 + 1 < cw) ? c0 + 1 : c0;
+                const uint32_t v = (uint32_t)sr[c0] | ((uint32_t)sv[c0] << 8) | ((uint32_t)sr[c1] << 16) | ((uint32_t)sv[c1] << 24);
+                memcpy(dr + 4 * d, &v, 4);
+            }
         } else if (g.nv12) {
             // chroma: an odd x0 takes two consecutive pairs (one 32-bit move), an even x0 the same pair twice
             for (; d < dw; ++d) {

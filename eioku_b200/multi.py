@@ -95,7 +95,7 @@ class ShardScorer:
         self._batch = int(batch_frames)
         self._ingest_threads = int(ingest_threads)
         self._ring_open = False
-        self._nv12 = pixel_format == "nv12"
+        self._nv12 = pixel_format in ("nv12", "i420")
         with torch.cuda.device(self.device):
             self.stream = torch.cuda.Stream(device=self.device)
             self.done = torch.cuda.Event()
@@ -201,7 +201,7 @@ def detect_sharded(frames, detectors: Sequence[SceneDetector], devices: Sequence
     sample = frames[0] if pre_sharded else frames
     if per_device_source:
         width, height = int(frame_size[0]), int(frame_size[1])
-    elif pixel_format == "nv12":
+    elif pixel_format in ("nv12", "i420"):
         width, height = int(sample.shape[2]), int(sample.shape[1]) * 2 // 3
     else:
         width, height = int(sample.shape[2]), int(sample.shape[1])

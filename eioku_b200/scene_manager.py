@@ -42,17 +42,21 @@ def get_scenes_from_cuts(cut_list: Sequence[int], start_pos: int, end_pos: int) 
     return scene_list
 
 
+# YUV 4:2:0 source formats: frames are [N, H*3/2, W] arrays (Y plane, then the chroma plane(s))
+YUV420_FORMATS = {"nv12": capi.ESD_FMT_NV12, "i420": capi.ESD_FMT_I420}
+
+
 class TensorVideo:
     """A decoded clip held as one array: numpy uint8 [N,H,W,3] (host) or a CUDA torch tensor.
     Stands where PySceneDetect's VideoStream stands; decode itself is out of scope."""
 
     def __init__(self, frames, fps: float = 30.0, start_frame: int = 0, pixel_format: str = "bgr24"):
         self.pixel_format = pixel_format
-        if pixel_format == "nv12":
+        if pixel_format in YUV420_FORMATS:
             if frames.ndim != 3 or frames.shape[1] % 3:
-                raise ValueError("NV12 frames must be [N, H*3/2, W] uint8 (Y plane, then the interleaved UV plane)")
+                raise ValueError("NV12 / I420 frames must be [N, H*3/2, W] uint8 (Y plane, then the interleaved UV plane or the U and V planes)")
         elif pixel_format != "bgr24":
-            raise ValueError("pixel_format must be 'bgr24' or 'nv12'")
+            raise ValueError("pixel_format must be 'bgr24', 'nv12' or 'i420'")
         elif frames.ndim != 4 or frames.shape[3] != 3:
             raise ValueError("frames must be [N,H,W,3] uint8 BGR")
         self.frames = frames
@@ -64,7 +68,7 @@ class TensorVideo:
 
     @property
     def frame_size(self) -> Tuple[int, int]:
-        if self.pixel_format == "nv12":
+        if self.pixel_format in YUV420_FORMATS:
             return int(self.frames.shape[2]), int(self.frames.shape[1]) * 2 // 3
         return int(self.frames.shape[2]), int(self.frames.shape[1])
 
@@ -184,7 +188,7 @@ class SceneManager:
             det._fill_config(cfg)
         cfg.src_width, cfg.src_height = width, height
         cfg.dst_width, cfg.dst_height = self._target_size(width, height)
-        cfg.src_format = capi.ESD_FMT_NV12 if pixel_format == "nv12" else capi.ESD_FMT_BGR24
+        cfg.src_format = YUV420_FORMATS.get(pixel_format, capi.ESD_FMT_BGR24)
         for k, v in self._tuning.items():
             setattr(cfg, k, v)
         return capi.EsdContext(cfg, self._device if device is None else device)
@@ -206,15 +210,16 @@ class SceneManager:
         if self.stats_manager is not None:
             self.stats_manager.fps = self._frame_rate
         width, height = video.frame_size
-        nv12 = getattr(video, "pixel_format", "bgr24") == "nv12"
-        key = (width, height, nv12, tuple(id(d) for d in self._detector_list), self._auto_downscale, self._downscale)
+        pixel_format = getattr(video, "pixel_format", "bgr24")
+        nv12 = pixel_format in YUV420_FORMATS   # [N, H*3/2, W] batches: NV12, or planar I420
+        key = (width, height, pixel_format, tuple(id(d) for d in self._detector_list), self._auto_downscale, self._downscale)
         if reuse_context and self._ctx is not None and self._ctx_key == key:
             ctx = self._ctx
             ctx.reset()
             self._cuts_by_detector = {}
         else:
             self.close()
-            self._ctx = ctx = self.make_context(width, height, pixel_format="nv12" if nv12 else "bgr24")
+            self._ctx = ctx = self.make_context(width, height, pixel_format=pixel_format)
             self._ctx_key = key
         start = int(getattr(video, "start_frame", 0))
         self._start_pos = start

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define ESD_ABI_VERSION 3
+#define ESD_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define ESD_API __attribute__((visibility("default")))
@@ -61,8 +61,10 @@ enum { ESD_DOWNSCALE_FLOAT = 0, ESD_DOWNSCALE_INT = 1 };
 enum { ESD_SPLIT_AUTO = 0, ESD_SPLIT_STRIPS = 1, ESD_SPLIT_CHUNKS = 2 };
 /* pixel format of the frames handed to the library.  NV12 (what NVDEC and most hardware decoders emit: a Y plane followed
  * by an interleaved half-resolution UV plane) is converted exactly like cv2.cvtColor(COLOR_YUV2BGR_NV12) inside the fused
- * kernel, only for the source pixels the downscale taps read; it needs a downscaling context and even dimensions. */
-enum { ESD_FMT_BGR24 = 0, ESD_FMT_NV12 = 1 };
+ * kernel, only for the source pixels the downscale taps read; it needs a downscaling context and even dimensions.
+ * I420 (planar YUV 4:2:0 -- what software decoders emit: ffmpeg / PyAV `yuv420p`: Y plane, U plane, V plane) is the same
+ * arithmetic, cv2.cvtColor(COLOR_YUV2BGR_I420): the chroma rows the taps touch are interleaved on the device first. */
+enum { ESD_FMT_BGR24 = 0, ESD_FMT_NV12 = 1, ESD_FMT_I420 = 2 };
 
 typedef struct esd_config {
     uint32_t struct_size;      /* = sizeof(esd_config) */
@@ -168,8 +170,16 @@ ESD_API int esd_push_frames(esd_ctx* ctx, const uint8_t* d_bgr, int64_t n, int64
  * device): the scoring chain consumes decoder surfaces directly, 0.97 MB instead of 1.66 MB per 1080p frame. */
 ESD_API int esd_push_nv12(esd_ctx* ctx, const uint8_t* d_y, const uint8_t* d_uv, int64_t n, int64_t frame_stride_bytes,
                           int64_t pitch_bytes, int64_t first_frame_num, void* stream);
+/* I420 contexts: the three planes of frame 0 given separately (an AVFrame's data[0..2]); frame k's planes lie
+ * k * frame_stride_bytes further; Y rows are pitch_y_bytes apart, U and V rows pitch_uv_bytes.  esd_push_frames (device) and
+ * esd_ingest_push_host (host) on an I420 context take the contiguous case: Y plane, then src_height / 2 U rows and as many V rows
+ * of pitch / 2 -- the (H * 3 / 2, W) array cv2.cvtColor(COLOR_YUV2BGR_I420) takes. */
+ESD_API int esd_push_i420(esd_ctx* ctx, const uint8_t* d_y, const uint8_t* d_u, const uint8_t* d_v, int64_t n,
+                          int64_t frame_stride_bytes, int64_t pitch_y_bytes, int64_t pitch_uv_bytes, int64_t first_frame_num,
+                          void* stream);
 /* Same, for frames stored in the compact layout [n][n_touched_rows][row_bytes] (touched rows only,
- * ascending source-row order; NV12: the touched Y rows, then the touched UV rows) that the ingest ring produces. */
+ * ascending source-row order; NV12 and I420: the touched Y rows, then the touched chroma rows as interleaved UV rows) that the
+ * ingest ring produces. */
 ESD_API int esd_push_rows(esd_ctx* ctx, const uint8_t* d_rows, int64_t n, int64_t first_frame_num, void* stream);
 
 /* Replaces: one call of PySceneDetect's `SceneDetector.process_frame(frame_num, frame_img)` with a host (numpy) frame --

@@ -10,3 +10,4 @@ c=d["e2e_compressed"]; print({k:v for k,v in c.items() if k not in ("note","cpu_
 print("cpu_baseline", d["cpu_baseline"]["value"], d["clocks"])
 PY
 bash scripts/gpu_profile.sh r02
+timeout 120 ./probes/sector_probe > gpurun_out/r02_sector_probe.log 2>&1; echo "sector rc=$?"; cat gpurun_out/r02_sector_probe.log

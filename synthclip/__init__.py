@@ -12,7 +12,7 @@ import os
 
 import numpy as np
 
-from .schedule import (DESC_FIELDS, SCENE_BLACK, SCENE_WHITE, ClipSchedule, bgr_to_test_nv12,  # noqa: F401
+from .schedule import (DESC_FIELDS, SCENE_BLACK, SCENE_WHITE, ClipSchedule, bgr_to_test_nv12, nv12_to_i420,  # noqa: F401
                        build_schedule)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))

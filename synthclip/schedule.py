@@ -122,3 +122,16 @@ def bgr_to_test_nv12(frames):
     out[:, h:, 0::2] = frames[:, 0::2, 0::2, 0]
     out[:, h:, 1::2] = frames[:, 0::2, 0::2, 2]
     return out
+
+
+def nv12_to_i420(nv12):
+    """The same samples as planar I420: [N, H * 3 // 2, W] uint8 with the Y plane, then the U plane and the V plane (each
+    H/2 rows of W/2 bytes, stored densely) -- the array cv2.cvtColor(COLOR_YUV2BGR_I420) takes.  numpy or torch."""
+    n, rows, w = nv12.shape
+    h = rows * 2 // 3
+    out = nv12.copy() if isinstance(nv12, np.ndarray) else nv12.clone()
+    q = (h // 2) * (w // 2)
+    flat = out.reshape(n, rows * w)
+    flat[:, h * w:h * w + q] = nv12[:, h:, 0::2].reshape(n, q)
+    flat[:, h * w + q:] = nv12[:, h:, 1::2].reshape(n, q)
+    return out

@@ -18,7 +18,7 @@ def shim(tmp_path_factory):
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", str(so), os.path.join(ROOT, "tests", "gather_shim.cpp")])
     L = C.CDLL(str(so))
     vp, i32, i64 = C.c_void_p, C.c_int, C.c_int64
-    L.shim_gather.argtypes = [i32, i32, i32, vp, vp, i64, i32, i32, i32, i32, vp, i64, i64, vp, i64, i64]
+    L.shim_gather.argtypes = [i32, i32, i32, vp, vp, i64, i32, i32, i32, i32, vp, i64, i64, vp, i64, i64, i32]
     L.shim_gather.restype = None
     return L
 
@@ -50,7 +50,7 @@ def test_bgr_tap_gather_layout(shim, w, h, dw, dh, nt, pf):
     items = n * nt_rows
     for lo, hi in ((0, 7), (7, items - 3), (items - 3, items)):   # ragged ranges, as the worker pool hands them out
         shim.shim_gather(dw, trb, w * 3, off.ctypes.data, rows.ctypes.data, nt_rows, nt_rows, 0, min(pf, w * 3), nt,
-                         frames.ctypes.data, frames.strides[0], pitch, dst.ctypes.data, lo, hi)
+                         frames.ctypes.data, frames.strides[0], pitch, dst.ctypes.data, lo, hi, 0)
     got = dst.reshape(n, nt_rows, trb)
     px = frames[:, :, :w * 3].reshape(n, h, w, 3)
     x1 = np.minimum(xo + 1, w - 1)
@@ -76,7 +76,7 @@ def test_nv12_tap_gather_layout(shim, w, h, dw, dh, nt, pf):
     items = n * nt_rows
     for lo, hi in ((0, 5), (5, items)):
         shim.shim_gather(dw, trb, w, xo.ctypes.data, touched.ctypes.data, nt_rows, len(yrows), 1, min(pf, w), nt,
-                         frames.ctypes.data, frames.strides[0], pitch, dst.ctypes.data, lo, hi)
+                         frames.ctypes.data, frames.strides[0], pitch, dst.ctypes.data, lo, hi, 0)
     got = dst.reshape(n, nt_rows, trb)
     x1 = np.minimum(xo + 1, w - 1)
     ysrc = frames[:, yrows, :w]
@@ -89,3 +89,31 @@ def test_nv12_tap_gather_layout(shim, w, h, dw, dh, nt, pf):
         assert np.array_equal(got[:, ny:, 4 * d + 2:4 * d + 4], uvsrc[:, :, c1:c1 + 2]), d
     if nt:
         assert not got[:, :ny, 2 * dw:].any()   # luma rows are zero-padded to the common pitch
+
+
+@pytest.mark.parametrize("w,h,dw,dh", [(1920, 1080, 256, 144), (642, 362, 256, 144), (300, 200, 256, 171), (34, 18, 17, 9)])
+@pytest.mark.parametrize("nt,pf", [(0, 0), (1, 4096)])
+def test_i420_tap_gather_equals_nv12_gather_of_the_interleaved_frame(shim, w, h, dw, dh, nt, pf):
+    """Planar I420 host frames gather into exactly the NV12 tap layout: same bytes as gathering the interleaved (NV12) form."""
+    import synthclip as synth
+
+    rng = np.random.default_rng(w + dh)
+    n = 2
+    nv12 = rng.integers(0, 256, (n, h * 3 // 2, w), dtype=np.uint8)
+    i420 = synth.nv12_to_i420(nv12)
+    xo, yrows = geometry(w, h, dw, dh)
+    uvrows = np.unique(yrows >> 1)
+    touched = np.concatenate([yrows, h + uvrows]).astype(np.int32)
+    trb = (4 * dw + 15) & ~15
+    nt_rows = len(touched)
+    items = n * nt_rows
+    out = []
+    for fmt, frames in ((1, nv12), (2, i420)):
+        dst = aligned(items * trb)
+        for lo, hi in ((0, 3), (3, items)):
+            shim.shim_gather(dw, trb, w, xo.ctypes.data, touched.ctypes.data, nt_rows, len(yrows), fmt, min(pf, w), nt,
+                             frames.ctypes.data, frames.strides[0], w, dst.ctypes.data, lo, hi, h)
+        out.append(dst.reshape(n, nt_rows, trb)[:, :, :4 * dw].copy())
+    ny = len(yrows)
+    assert np.array_equal(out[0][:, :ny, :2 * dw], out[1][:, :ny, :2 * dw])
+    assert np.array_equal(out[0][:, ny:], out[1][:, ny:])

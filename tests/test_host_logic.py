@@ -370,12 +370,19 @@ def test_nv12_video_geometry_and_test_content():
     with pytest.raises(ValueError):
         TensorVideo(bgr, pixel_format="nv12")
     with pytest.raises(ValueError):
-        TensorVideo(nv12, pixel_format="i420")
+        TensorVideo(nv12, pixel_format="yuyv")
+    # planar I420 carries the same samples: the (H*3/2, W) array cv2.cvtColor(COLOR_YUV2BGR_I420) takes
+    i420 = synth.nv12_to_i420(nv12)
+    assert i420.shape == nv12.shape and np.array_equal(i420[:, :8], nv12[:, :8])
+    assert np.array_equal(i420[:, 8:10].reshape(3, 4, 6), nv12[:, 8:, 0::2]) and np.array_equal(i420[:, 10:].reshape(3, 4, 6), nv12[:, 8:, 1::2])
+    assert TensorVideo(i420, pixel_format="i420").frame_size == (12, 8)
     # the closed-form NV12 -> BGR conversion agrees with cv2 on this content too
     cv2 = pytest.importorskip("cv2")
     from oracle import closed_form as cf
 
     assert np.array_equal(cf.nv12_to_bgr_u8(nv12[0]), cv2.cvtColor(nv12[0], cv2.COLOR_YUV2BGR_NV12))
+    # and cv2 converts the planar form to the very same picture: one arithmetic, two chroma layouts
+    assert np.array_equal(cv2.cvtColor(i420[0], cv2.COLOR_YUV2BGR_I420), cv2.cvtColor(nv12[0], cv2.COLOR_YUV2BGR_NV12))
 
 
 def test_scene_artifact_payloads_from_a_finished_manager():
