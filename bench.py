@@ -31,6 +31,10 @@ if ROOT not in sys.path:
 
 import numpy as np  # noqa: E402
 
+# the product sets the same default on import (eioku_b200/__init__.py explains it); here as well so that it holds whichever
+# module touches CUDA first
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 W, H, FPS = 1920, 1080, 30
 DST = (256, 144)  # PySceneDetect >= 0.6.2 auto-downscale of a 1920-wide frame (factor 7.5)
 TOUCHED_ROW_BYTES = 288 * W * 3  # source bytes of one frame the 2x2 taps read
@@ -784,7 +788,7 @@ def main():
     ap.add_argument("--e2e-gather-threads", type=int, default=-1, help="host gather threads per rank (-1 = this rank's share of the host cores)")
     ap.add_argument("--e2e-ring", default="", help="ingest ring of the e2e leg as SLOTSxFRAMES (default 4x128 with gather, 3x256 DMA)")
     ap.add_argument("--no-compressed", action="store_true", help="skip the compressed-file end-to-end leg")
-    ap.add_argument("--compressed-frames", type=int, default=256)
+    ap.add_argument("--compressed-frames", type=int, default=768, help="length of the Motion-JPEG file (three decode batches per pass: the decoder's double buffering needs more than one)")
     ap.add_argument("--compressed-passes", type=int, default=6)
     ap.add_argument("--compressed-cpu-passes", type=int, default=2)
     ap.add_argument("--decode-sessions", type=int, default=0, help="GPU decoder sessions per rank (0 = 8)")

@@ -17,6 +17,7 @@
 
 #include <algorithm>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -61,6 +62,8 @@ struct esd_mjpeg {
     bool tev_armed[2] = {false, false};
     double t_sum[4] = {0, 0, 0, 0};   // ms: staging copy + clear, entropy, idct + colour, host staging
     int64_t t_batches = 0, t_pictures = 0;
+    int timeline = getenv("ESD_DEC_TIMING") ? atoi(getenv("ESD_DEC_TIMING")) : 0;   // 2: per-batch timeline against a process-wide origin
+    double host_t[2][3] = {};         // ms since the origin: read entered, staging begins (slot free), staging ends
     int64_t reads = 0;
     std::vector<const unsigned char*> ptrs;
     std::vector<size_t> lens;
@@ -323,9 +326,30 @@ int esd_decode_abi_version(void) { return ESD_DECODE_ABI_VERSION; }
 
 const char* esd_mjpeg_last_error(const esd_mjpeg* h) { return h ? h->err.c_str() : g_open_error.c_str(); }
 
+// process-wide origin of the ESD_DEC_TIMING=2 timelines: a device event and the host clock taken together after a synchronise
+static cudaEvent_t g_origin_ev = nullptr;
+static double g_origin_ms = 0.0;
+static double host_ms() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+static void ensure_origin() {
+    static std::once_flag once;
+    std::call_once(once, [] {
+        cudaEventCreate(&g_origin_ev);
+        cudaDeviceSynchronize();
+        cudaEventRecord(g_origin_ev, 0);
+        cudaEventSynchronize(g_origin_ev);
+        g_origin_ms = host_ms();
+    });
+}
+
 static void collect_timing(esd_mjpeg* h, int b) {
     if (!h->timing || !h->tev_armed[b]) return;
     h->tev_armed[b] = false;
+    if (h->timeline >= 2) {
+        float t[4] = {0, 0, 0, 0};
+        for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&t[k], g_origin_ev, h->tev[b][k]);
+        fprintf(stderr, "[esd_decode timeline %p] host: enter %.1f stage %.1f..%.1f | device: copy %.1f entropy %.1f..%.1f done %.1f\n", (void*)h,
+                h->host_t[b][0], h->host_t[b][1], h->host_t[b][2], t[0], t[1], t[2], t[3]);
+    }
     for (int k = 0; k < 3; ++k) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, h->tev[b][k], h->tev[b][k + 1]) == cudaSuccess) h->t_sum[k] += ms;
@@ -488,6 +512,8 @@ int esd_mjpeg_read(esd_mjpeg* h, int64_t max_frames, void* stream, uint8_t** d_b
     if (cudaSetDevice(h->device) != cudaSuccess) return fail(h, ESD_DEC_ERR_CUDA, "cudaSetDevice(%d) failed", h->device);
     cudaStream_t st = (cudaStream_t)stream;
     const int b = (int)(h->reads & 1);
+    if (h->timeline >= 2) ensure_origin();
+    const double t_enter = h->timeline >= 2 ? host_ms() - g_origin_ms : 0.0;
     // the pinned staging of this slot was last read by the decode two reads ago
     if (h->in_flight[b]) {
         cudaError_t e = cudaEventSynchronize(h->done[b]);
@@ -581,6 +607,11 @@ int esd_mjpeg_read(esd_mjpeg* h, int64_t max_frames, void* stream, uint8_t** d_b
             clock_gettime(CLOCK_MONOTONIC, &ts1);
             h->t_sum[3] += (ts1.tv_sec - ts0.tv_sec) * 1e3 + (ts1.tv_nsec - ts0.tv_nsec) * 1e-6;
             h->t_pictures += n;
+            if (h->timeline >= 2) {
+                h->host_t[b][0] = t_enter;
+                h->host_t[b][1] = ts0.tv_sec * 1e3 + ts0.tv_nsec * 1e-6 - g_origin_ms;
+                h->host_t[b][2] = host_ms() - g_origin_ms;
+            }
             for (int k = 0; k < 4; ++k) if (!h->tev[b][k]) cudaEventCreate(&h->tev[b][k]);
             cudaEventRecord(h->tev[b][0], st);
         }
