@@ -444,7 +444,12 @@ def compressed_leg(local, rank, world, dist, dev, args, barrier, all_max):
     size = os.path.getsize(path)
     # a decoder session is one host thread that spends its time inside libesd_decode / libesd (GIL released): ~30 us of host work
     # per picture, so the session count is chosen for pictures in flight on the GPU, not by the core count
-    sessions = args.decode_sessions if args.decode_sessions > 0 else 8
+    # (a node's cores are shared by its ranks: at least 2, at most 8 sessions per rank)
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 8
+    sessions = args.decode_sessions if args.decode_sessions > 0 else max(2, min(8, cores // max(1, world)))
     out = None
     try:
         # parity on the decoded surface: the frames one session scored, downloaded, through the oracle's integer chain

@@ -470,7 +470,7 @@ int esd_mjpeg_open(esd_mjpeg** out, const char* path, int device, int32_t batch_
         if (nvjpegGetHardwareDecoderInfo(h->nj, &h->hw_engines, &cores) != NVJPEG_STATUS_SUCCESS) h->hw_engines = 0;
     }
     for (int b = 0; b < 2; ++b) {
-        if (cudaMalloc(&h->d_out[b], frame_bytes * h->batch) != cudaSuccess || cudaEventCreateWithFlags(&h->done[b], cudaEventDisableTiming) != cudaSuccess) {
+        if (cudaMalloc(&h->d_out[b], frame_bytes * h->batch) != cudaSuccess || cudaEventCreateWithFlags(&h->done[b], cudaEventDisableTiming | cudaEventBlockingSync) != cudaSuccess) {
             fail(h, ESD_DEC_ERR_CUDA, "device buffer of %d frames (%zu bytes) could not be allocated: %s", h->batch, frame_bytes * h->batch,
                  cudaGetErrorString(cudaGetLastError()));
             return bail(ESD_DEC_ERR_CUDA);
@@ -514,7 +514,8 @@ int esd_mjpeg_read(esd_mjpeg* h, int64_t max_frames, void* stream, uint8_t** d_b
     const int b = (int)(h->reads & 1);
     if (h->timeline >= 2) ensure_origin();
     const double t_enter = h->timeline >= 2 ? host_ms() - g_origin_ms : 0.0;
-    // the pinned staging of this slot was last read by the decode two reads ago
+    // the pinned staging of this slot was last read by the decode two reads ago (the event blocks instead of spinning: a job runs
+    // a session per ~256 pictures in flight, and spinning waiters would take the cores the staging threads need)
     if (h->in_flight[b]) {
         cudaError_t e = cudaEventSynchronize(h->done[b]);
         if (e != cudaSuccess) return fail(h, ESD_DEC_ERR_CUDA, "decode of an earlier batch failed: %s", cudaGetErrorString(e));
