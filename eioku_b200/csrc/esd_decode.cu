@@ -74,13 +74,22 @@ struct esd_mjpeg {
     int blocks_per_frame = 0;
     bool flat = false;                           // no restart interval: the host removes the byte stuffing and the flat scan decoder runs
     size_t plane_bytes = 0;                      // Y + Cb + Cr sample planes of one frame (MCU-padded)
-    uint8_t* d_comp = nullptr;                   // compressed pictures of the batch
-    size_t d_comp_bytes = 0;
+    // Two decode lanes: batch k runs on lane k & 1 (a stream of the library's own, with its own staging mirror, coefficient and
+    // plane scratch), so the entropy stage of batch k + 1 overlaps batch k's instead of queueing behind it on the caller's stream
+    // -- a session keeps 2 x batch pictures in flight, which is what the decoder's throughput is made of.  The caller's stream
+    // waits for the lane's `done` event; the lane waits for `consumed`, recorded on the caller's stream at the next read (when the
+    // work that reads this slot's previous contents has been enqueued).  ESD_DEC_LANES=1 restores the single-stream order.
+    int lanes = getenv("ESD_DEC_LANES") && atoi(getenv("ESD_DEC_LANES")) == 1 ? 1 : 2;
+    cudaStream_t lane[2] = {nullptr, nullptr};
+    cudaEvent_t consumed[2] = {nullptr, nullptr};
+    bool have_consumed[2] = {false, false};
+    uint8_t* d_comp[2] = {nullptr, nullptr};     // compressed pictures of the batch
+    size_t d_comp_bytes[2] = {0, 0};
     struct NativeDesc { uint32_t off, len; uint32_t dht[4]; uint16_t nvals[4]; };  // dht / nvals: DC0, DC1, AC0, AC1 (offset of the 16 counts in the staging block; 0 = table absent)
     NativeDesc* d_desc = nullptr;                // [batch]
     uint16_t* d_quant = nullptr;                 // [batch][3][64] natural order, per component
-    int16_t* d_coef = nullptr;                   // [batch][blocks_per_frame][64]
-    uint8_t* d_planes = nullptr;                 // [batch][plane_bytes]
+    int16_t* d_coef[2] = {nullptr, nullptr};     // [batch][blocks_per_frame][64], per lane
+    uint8_t* d_planes[2] = {nullptr, nullptr};   // [batch][plane_bytes], per lane
     std::vector<uint8_t> h_meta[2];              // pinned-free host staging of descriptors + quant tables (copied with the batch)
 };
 
@@ -372,7 +381,11 @@ void esd_mjpeg_close(esd_mjpeg* h) {
         fprintf(stderr, "[esd_decode timing] %lld batches, %lld pictures: host staging %.2f ms, copy+clear %.2f ms, entropy %.2f ms, idct+colour %.2f ms per batch\n",
                 (long long)h->t_batches, (long long)h->t_pictures, h->t_sum[3] / h->t_batches, h->t_sum[0] / h->t_batches, h->t_sum[1] / h->t_batches,
                 h->t_sum[2] / h->t_batches);
-    cudaFree(h->d_comp); cudaFree(h->d_coef); cudaFree(h->d_planes);
+    for (int b = 0; b < 2; ++b) {
+        if (h->lane[b]) { cudaStreamSynchronize(h->lane[b]); cudaStreamDestroy(h->lane[b]); }
+        if (h->consumed[b]) cudaEventDestroy(h->consumed[b]);
+        cudaFree(h->d_comp[b]); cudaFree(h->d_coef[b]); cudaFree(h->d_planes[b]);
+    }
     if (h->state) nvjpegJpegStateDestroy(h->state);
     if (h->nj) nvjpegDestroy(h->nj);
     if (h->map) munmap(const_cast<uint8_t*>(h->map), h->map_bytes);
@@ -435,8 +448,12 @@ int esd_mjpeg_open(esd_mjpeg** out, const char* path, int device, int32_t batch_
             h->flat = jh.restart_interval == 0;
             cudaError_t e = cudaFuncSetAttribute(jpeg_entropy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kEntropyThreads * sizeof(esdjpeg::ScanTables)));
             if (e == cudaSuccess) e = cudaFuncSetAttribute(jpeg_entropy_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kEntropyThreads * sizeof(esdjpeg::ScanTables)));
-            if (e == cudaSuccess) e = cudaMalloc(&h->d_coef, (size_t)h->batch * h->blocks_per_frame * 64 * sizeof(int16_t));
-            if (e == cudaSuccess) e = cudaMalloc(&h->d_planes, (size_t)h->batch * h->plane_bytes);
+            for (int b = 0; b < h->lanes && e == cudaSuccess; ++b) {
+                e = cudaMalloc(&h->d_coef[b], (size_t)h->batch * h->blocks_per_frame * 64 * sizeof(int16_t));
+                if (e == cudaSuccess) e = cudaMalloc(&h->d_planes[b], (size_t)h->batch * h->plane_bytes);
+                if (e == cudaSuccess && h->lanes > 1) e = cudaStreamCreateWithFlags(&h->lane[b], cudaStreamNonBlocking);
+                if (e == cudaSuccess && h->lanes > 1) e = cudaEventCreateWithFlags(&h->consumed[b], cudaEventDisableTiming);
+            }
             if (e != cudaSuccess) {
                 fail(h, ESD_DEC_ERR_CUDA, "native decoder: device buffers for %d frames could not be allocated: %s", h->batch, cudaGetErrorString(e));
                 return bail(ESD_DEC_ERR_CUDA);
@@ -512,6 +529,14 @@ int esd_mjpeg_read(esd_mjpeg* h, int64_t max_frames, void* stream, uint8_t** d_b
     if (cudaSetDevice(h->device) != cudaSuccess) return fail(h, ESD_DEC_ERR_CUDA, "cudaSetDevice(%d) failed", h->device);
     cudaStream_t st = (cudaStream_t)stream;
     const int b = (int)(h->reads & 1);
+    const bool laned = h->backend == ESD_JPEG_NATIVE && h->lanes > 1;
+    const int ln = laned ? b : 0;                 // scratch set of this batch
+    cudaStream_t ds = laned ? h->lane[b] : st;    // where the decode runs
+    if (laned && h->reads >= 1) {
+        // everything the caller enqueued since the previous read -- the work that consumes that batch -- lies before this point
+        if (cudaEventRecord(h->consumed[b ^ 1], st) != cudaSuccess) return fail(h, ESD_DEC_ERR_CUDA, "cudaEventRecord failed");
+        h->have_consumed[b ^ 1] = true;
+    }
     if (h->timeline >= 2) ensure_origin();
     const double t_enter = h->timeline >= 2 ? host_ms() - g_origin_ms : 0.0;
     // the pinned staging of this slot was last read by the decode two reads ago (the event blocks instead of spinning: a job runs
@@ -590,12 +615,16 @@ int esd_mjpeg_read(esd_mjpeg* h, int64_t max_frames, void* stream, uint8_t** d_b
         off += ((size_t)p.size + 16 + 63) & ~(size_t)63;
     }
     if (native) {
-        if (total > h->d_comp_bytes) {  // device mirror of the staging block (grow-only; everything that used it ran on `st` before)
-            if (h->d_comp) { cudaStreamSynchronize(st); cudaFree(h->d_comp); h->d_comp = nullptr; h->d_comp_bytes = 0; }
+        if (total > h->d_comp_bytes[ln]) {  // device mirror of the staging block (grow-only; everything that used it ran on `ds` before)
+            if (h->d_comp[ln]) { cudaStreamSynchronize(ds); cudaFree(h->d_comp[ln]); h->d_comp[ln] = nullptr; h->d_comp_bytes[ln] = 0; }
             const size_t want = total + total / 4 + 4096;
-            if (cudaMalloc(&h->d_comp, want) != cudaSuccess) return fail(h, ESD_DEC_ERR_CUDA, "device staging of %zu bytes could not be allocated", want);
-            h->d_comp_bytes = want;
+            if (cudaMalloc(&h->d_comp[ln], want) != cudaSuccess) return fail(h, ESD_DEC_ERR_CUDA, "device staging of %zu bytes could not be allocated", want);
+            h->d_comp_bytes[ln] = want;
         }
+        // this slot's output was last read by the consumer of the batch two reads ago: the lane waits for that work, not for the
+        // caller's whole stream (which also holds the wait for the other lane's batch)
+        if (laned && h->have_consumed[b] && cudaStreamWaitEvent(ds, h->consumed[b], 0) != cudaSuccess)
+            return fail(h, ESD_DEC_ERR_CUDA, "cudaStreamWaitEvent failed");
         NativeLayout L{};
         L.n = (int)n;
         L.mcus_x = h->geo.mcus_x; L.mcus_y = h->geo.mcus_y; L.restart_interval = h->geo.restart_interval;
@@ -614,22 +643,22 @@ int esd_mjpeg_read(esd_mjpeg* h, int64_t max_frames, void* stream, uint8_t** d_b
                 h->host_t[b][2] = host_ms() - g_origin_ms;
             }
             for (int k = 0; k < 4; ++k) if (!h->tev[b][k]) cudaEventCreate(&h->tev[b][k]);
-            cudaEventRecord(h->tev[b][0], st);
+            cudaEventRecord(h->tev[b][0], ds);
         }
-        cudaError_t e = cudaMemcpyAsync(h->d_comp, h->h_stage[b], total, cudaMemcpyHostToDevice, st);
-        if (e == cudaSuccess) e = cudaMemsetAsync(h->d_coef, 0, (size_t)n * h->blocks_per_frame * 64 * sizeof(int16_t), st);
+        cudaError_t e = cudaMemcpyAsync(h->d_comp[ln], h->h_stage[b], total, cudaMemcpyHostToDevice, ds);
+        if (e == cudaSuccess) e = cudaMemsetAsync(h->d_coef[ln], 0, (size_t)n * h->blocks_per_frame * 64 * sizeof(int16_t), ds);
         if (e != cudaSuccess) return fail(h, ESD_DEC_ERR_CUDA, "native decode: staging copy failed: %s", cudaGetErrorString(e));
-        const esd_mjpeg::NativeDesc* ddesc = reinterpret_cast<const esd_mjpeg::NativeDesc*>(h->d_comp);
-        const uint16_t* dquant = reinterpret_cast<const uint16_t*>(h->d_comp + (size_t)n * sizeof(esd_mjpeg::NativeDesc));
+        const esd_mjpeg::NativeDesc* ddesc = reinterpret_cast<const esd_mjpeg::NativeDesc*>(h->d_comp[ln]);
+        const uint16_t* dquant = reinterpret_cast<const uint16_t*>(h->d_comp[ln] + (size_t)n * sizeof(esd_mjpeg::NativeDesc));
         const unsigned egrid = (unsigned)((n + kEntropyThreads - 1) / kEntropyThreads);
         const size_t esmem = kEntropyThreads * sizeof(esdjpeg::ScanTables);
-        if (h->timing) cudaEventRecord(h->tev[b][1], st);
-        if (h->flat) jpeg_entropy_flat_kernel<<<egrid, kEntropyThreads, esmem, st>>>(L, h->d_comp, ddesc, h->d_coef);
-        else jpeg_entropy_kernel<<<egrid, kEntropyThreads, esmem, st>>>(L, h->d_comp, ddesc, h->d_coef);
-        if (h->timing) cudaEventRecord(h->tev[b][2], st);
-        jpeg_idct_kernel<<<dim3((unsigned)((h->blocks_per_frame + 127) / 128), (unsigned)n), 128, 0, st>>>(L, h->d_coef, dquant, h->d_planes);
-        jpeg_color_kernel<<<dim3((unsigned)(((h->width + 3) / 4 + 255) / 256), (unsigned)h->height, (unsigned)n), 256, 0, st>>>(L, h->d_planes, h->d_out[b]);
-        if (h->timing) { cudaEventRecord(h->tev[b][3], st); h->tev_armed[b] = true; }
+        if (h->timing) cudaEventRecord(h->tev[b][1], ds);
+        if (h->flat) jpeg_entropy_flat_kernel<<<egrid, kEntropyThreads, esmem, ds>>>(L, h->d_comp[ln], ddesc, h->d_coef[ln]);
+        else jpeg_entropy_kernel<<<egrid, kEntropyThreads, esmem, ds>>>(L, h->d_comp[ln], ddesc, h->d_coef[ln]);
+        if (h->timing) cudaEventRecord(h->tev[b][2], ds);
+        jpeg_idct_kernel<<<dim3((unsigned)((h->blocks_per_frame + 127) / 128), (unsigned)n), 128, 0, ds>>>(L, h->d_coef[ln], dquant, h->d_planes[ln]);
+        jpeg_color_kernel<<<dim3((unsigned)(((h->width + 3) / 4 + 255) / 256), (unsigned)h->height, (unsigned)n), 256, 0, ds>>>(L, h->d_planes[ln], h->d_out[b]);
+        if (h->timing) { cudaEventRecord(h->tev[b][3], ds); h->tev_armed[b] = true; }
         e = cudaGetLastError();
         if (e != cudaSuccess) return fail(h, ESD_DEC_ERR_CUDA, "native decode kernels: %s", cudaGetErrorString(e));
     } else {
@@ -643,7 +672,8 @@ int esd_mjpeg_read(esd_mjpeg* h, int64_t max_frames, void* stream, uint8_t** d_b
             return fail(h, ESD_DEC_ERR_NVJPEG, "nvjpegDecodeBatched failed at frame %lld: status %d (%s)", (long long)h->pos, (int)js,
                         js == NVJPEG_STATUS_JPEG_NOT_SUPPORTED ? "bitstream not supported by this back end" : js == NVJPEG_STATUS_BAD_JPEG ? "bad JPEG" : "see nvjpeg.h");
     }
-    if (cudaEventRecord(h->done[b], st) != cudaSuccess) return fail(h, ESD_DEC_ERR_CUDA, "cudaEventRecord failed");
+    if (cudaEventRecord(h->done[b], ds) != cudaSuccess) return fail(h, ESD_DEC_ERR_CUDA, "cudaEventRecord failed");
+    if (laned && cudaStreamWaitEvent(st, h->done[b], 0) != cudaSuccess) return fail(h, ESD_DEC_ERR_CUDA, "cudaStreamWaitEvent failed");
     h->in_flight[b] = true;
     h->reads++;
     h->pos += n;

@@ -1381,8 +1381,14 @@ __global__ void __launch_bounds__(kDecideThreads) decide_kernel(DecisionParams P
                               const double* __restrict__ average_rgb, const double* __restrict__ hash_dist,
                               long long first_frame_num, long long i_begin, long long i_end,
                               long long* __restrict__ mailbox, long long ticket) {
-    constexpr int CH = 8192;
+    constexpr int CH = 16384;
     __shared__ uint32_t bits[CH / 32];
+    // frames of the chunk whose test is true, ascending: the sequential walk steps through this list instead of scanning the
+    // bitmask a word at a time (one thread's dependent smem load + branches cost ~300 cycles per empty word: 100 of the 116 us
+    // an 18 000-frame pass took, profiles/r02_decide_ncu.md)
+    __shared__ uint16_t s_idx[CH];
+    __shared__ int s_warp_sum[kDecideThreads / 32];
+    __shared__ int s_count;
     const int det = blockIdx.x;
     if (!(P.detectors & (1 << det)) || i_end <= i_begin) return;
     const int tid = threadIdx.x;
@@ -1458,6 +1464,37 @@ __global__ void __launch_bounds__(kDecideThreads) decide_kernel(DecisionParams P
             }
         }
         __syncthreads();
+        if (det != 3) {
+            // compaction: thread t owns word t (CH / 32 = 512 words <= kDecideThreads): block-wide exclusive scan of the popcounts
+            static_assert(CH / 32 <= kDecideThreads, "one word per thread");
+            const int nj_all = (int)(c1 - c0);
+            uint32_t word = 0;
+            if (tid < CH / 32) {
+                word = bits[tid];
+                const int first = tid * 32;
+                if (first >= nj_all) word = 0;
+                else if (first + 32 > nj_all) word &= (1u << (nj_all - first)) - 1u;   // frames beyond the chunk's end carry no test
+            }
+            const int cnt = __popc(word);
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if ((tid & 31) >= o) incl += v;
+            }
+            if ((tid & 31) == 31) s_warp_sum[tid >> 5] = incl;
+            __syncthreads();
+            int base = 0;
+            for (int w = 0; w < (tid >> 5); ++w) base += s_warp_sum[w];
+            int o = base + incl - cnt;
+            while (word) {
+                const int bpos = __ffs(word) - 1;
+                s_idx[o++] = (uint16_t)(tid * 32 + bpos);
+                word &= word - 1;
+            }
+            if (tid == kDecideThreads - 1) s_count = base + incl;
+            __syncthreads();
+        }
         if (tid == 0) {
             const int nj = (int)(c1 - c0);
             int j = 0;
@@ -1502,17 +1539,13 @@ __global__ void __launch_bounds__(kDecideThreads) decide_kernel(DecisionParams P
                 }
                 j = nj;
             }
+            const int m = det != 3 ? s_count : 0;   // above-threshold frames of this chunk
+            int pnext = 0;                            // next entry of s_idx; invariant: s_idx[pnext] >= j
             while (j < nj) {
                 if (det == 0 && merge_triggered) {
                     // Open MERGE burst: nothing changes between above-threshold frames, and the burst closes at
                     // the first below-threshold frame fstar = last + L once (last - merge_start) >= L.
-                    int ja = j;
-                    while (ja < nj) {
-                        const uint32_t word = bits[ja >> 5] >> (ja & 31);
-                        if (word) { ja += __ffs(word) - 1; break; }
-                        ja = (ja | 31) + 1;
-                    }
-                    if (ja > nj) ja = nj;
+                    const int ja = pnext < m ? (int)s_idx[pnext] : nj;
                     const long long fn_a = first_frame_num + c0 + ja;  // next above frame (or end of chunk)
                     if ((last - merge_start) >= L) {
                         const long long fn_j = first_frame_num + c0 + j;
@@ -1527,15 +1560,15 @@ __global__ void __launch_bounds__(kDecideThreads) decide_kernel(DecisionParams P
                     if (ja >= nj) break;
                     last = fn_a;  // above frame inside the burst only advances last_above
                     j = ja + 1;
+                    ++pnext;
                     continue;
                 }
                 const bool every_frame = (det == 2 && last == 0);
                 if (!every_frame) {  // jump to the next frame whose test is true
-                    uint32_t word = bits[j >> 5] >> (j & 31);
-                    if (word == 0) { j = (j | 31) + 1; continue; }
-                    j += __ffs(word) - 1;
-                    if (j >= nj) break;
+                    if (pnext >= m) break;
+                    j = (int)s_idx[pnext];
                 }
+                if (pnext < m && (int)s_idx[pnext] == j) ++pnext;
                 const bool above = (bits[j >> 5] >> (j & 31)) & 1u;
                 const long long fn = first_frame_num + c0 + j;
                 ++j;

@@ -32,6 +32,7 @@ struct GatherSpec {
     int src_height;         // I420: rows of the Y plane
     int prefetch_bytes;     // rolling software prefetch distance (0 = touch the next row's pages only)
     bool nt_stores;         // assemble each row in L1 and stream it out with non-temporal stores
+    int prefetch_hint;      // experiment knob of the BGR24 loop: 0 = into L1 (prefetcht0), 1 = L2 (prefetcht1), 2 = L3 (prefetcht2), 3 = non-temporal
 };
 
 constexpr int kMaxTapRow = 6 * 1024 + 16;  // dst_w <= 1024 in resizing contexts
@@ -110,7 +111,13 @@ inline void gather_tap_rows(const GatherSpec& g, const uint8_t* src, int64_t fra
             for (; d < dw - 1 && off[d] + 8 <= rb; ++d) {  // 8-byte moves; the 2 spare bytes are overwritten by d + 1
                 if (pf > 0 && (d & 3) == 0) {
                     const int o = off[d] + pf;
-                    __builtin_prefetch(o < rb ? sr + o : nx + (o - rb), 0, 3);
+                    const uint8_t* pa = o < rb ? sr + o : nx + (o - rb);
+                    switch (g.prefetch_hint) {
+                        case 1: __builtin_prefetch(pa, 0, 2); break;
+                        case 2: __builtin_prefetch(pa, 0, 1); break;
+                        case 3: __builtin_prefetch(pa, 0, 0); break;
+                        default: __builtin_prefetch(pa, 0, 3); break;
+                    }
                 }
                 uint64_t v;
                 memcpy(&v, sr + off[d], 8);

@@ -73,10 +73,12 @@ ESD_DEC_API int esd_mjpeg_get_info(const esd_mjpeg* h, esd_mjpeg_info* out);
 ESD_DEC_API int esd_mjpeg_seek(esd_mjpeg* h, int64_t frame);
 /* Replaces: `ret, frame = cap.read()` x batch_frames (model_manager.py:248-263).
  * Decodes up to min(batch_frames, max_frames) pictures starting at the current position into the library's device buffer as dense
- * BGR24 [n][height][width * 3]; *d_bgr / *n_frames describe them (n_frames == 0 at the end of the stream).  The decode is
- * enqueued on `stream` (cudaStream_t of the handle's device): work the caller enqueues on `stream` afterwards (e.g.
- * esd_push_frames) is ordered behind it, and the buffer stays valid until the second next esd_mjpeg_read -- by then the
- * consumer's work on `stream` is known to have been enqueued, and the library orders its writes behind it. */
+ * BGR24 [n][height][width * 3]; *d_bgr / *n_frames describe them (n_frames == 0 at the end of the stream).  The call returns
+ * once the decode is ENQUEUED, and `stream` (cudaStream_t of the handle's device) is made to wait for it: work the caller
+ * enqueues on `stream` afterwards (e.g. esd_push_frames) is ordered behind the decode.  (The own decoder runs consecutive batches
+ * on two streams of the library's so that their entropy stages overlap; nvJPEG decodes on `stream` itself.)  The buffer stays
+ * valid until the second next esd_mjpeg_read: the work that consumes a batch must be enqueued on `stream` before the next read
+ * call, which is where the library takes note of it and orders its later writes to that buffer behind it. */
 ESD_DEC_API int esd_mjpeg_read(esd_mjpeg* h, int64_t max_frames, void* stream, uint8_t** d_bgr, int64_t* n_frames);
 ESD_DEC_API void esd_mjpeg_close(esd_mjpeg* h);
 
