@@ -1533,6 +1533,11 @@ int esd_ingest_push_host(esd_ctx* c, const uint8_t* h_bgr, int64_t n, int64_t fr
             // measured best of 0 / 512 ... 8192 at 1080p (profiles/r01_gather_prefetch.log); never further than one row
             gs.prefetch_bytes = std::min(pf_env >= 0 ? pf_env : 4096, c->row_bytes);
             gs.nt_stores = !nt_off;  // +11 % with 16 threads (profiles/r01_gather_prefetch.log)
+            static const int streams_env = getenv("ESD_GATHER_STREAMS") ? atoi(getenv("ESD_GATHER_STREAMS")) : kGatherStreams;  // A/B switch: 1
+            static const int pf8_env = getenv("ESD_GATHER_PF8") ? atoi(getenv("ESD_GATHER_PF8")) : 384;
+            gs.streams = streams_env;
+            gs.prefetch_bytes_multi = pf8_env;
+            gs.prefetch_hint = 0;
             uint8_t* dst_base = s.h_pinned;
             std::function<void(int64_t, int64_t)> job = [=](int64_t lo, int64_t hi) {
                 gather_tap_rows(gs, src, frame_stride, pitch, dst_base, lo, hi);

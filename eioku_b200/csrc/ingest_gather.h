@@ -32,10 +32,60 @@ struct GatherSpec {
     int src_height;         // I420: rows of the Y plane
     int prefetch_bytes;     // rolling software prefetch distance (0 = touch the next row's pages only)
     bool nt_stores;         // assemble each row in L1 and stream it out with non-temporal stores
+    int streams;            // BGR24: rows gathered in lock-step per thread (1 = one after another; 8 = the default of the ingest path)
+    int prefetch_bytes_multi;  // prefetch distance of the multi-stream loop (each stream runs 1/streams as fast: shorter than prefetch_bytes)
     int prefetch_hint;      // experiment knob of the BGR24 loop: 0 = into L1 (prefetcht0), 1 = L2 (prefetcht1), 2 = L3 (prefetcht2), 3 = non-temporal
 };
 
 constexpr int kMaxTapRow = 6 * 1024 + 16;  // dst_w <= 1024 in resizing contexts
+constexpr int kGatherStreams = 8;          // rows in lock-step in the multi-stream BGR24 loop
+constexpr int kGatherStreamGap = 2;        // consecutive items per stream: one block = 16 items
+
+// BGR24, multi-stream: one core sustains ~6.5 GB/s walking ONE row at a time (a dozen cache misses in flight, the hardware
+// prefetchers restarting at every row); gathering eight rows in lock-step keeps eight independent miss streams in flight and
+// measured +27 % per core (scripts/gather_probe.py, profiles/r02_gather_streams.log).  Items [lo, lo + 16) of the item sequence:
+// stream s takes items lo + 2 s and lo + 2 s + 1.  Rows are assembled in L1 and streamed out (non-temporal), as in the loop below.
+inline void gather_tap_rows_bgr_block(const GatherSpec& g, const uint8_t* src, int64_t frame_stride, int64_t pitch, uint8_t* dst_base,
+                                      int64_t lo) {
+    const int dw = g.dst_w, trb = g.tap_row_bytes, rb = g.row_bytes, pf = g.prefetch_bytes_multi;
+    const int* off = g.off;
+    // the assembled rows lie tstride apart, NOT a multiple of 4 KB plus a few bytes: with a stride of kMaxTapRow (6 160 B) the eight
+    // stores of a column alias in their low 12 address bits and the loop ran 2.3x slower than one row at a time
+    alignas(64) uint8_t tmp_all[kGatherStreams * (kMaxTapRow + 192)];
+    const int tstride = ((trb + 63) & ~63) + 192;
+    uint8_t* tmp[kGatherStreams];
+    for (int s = 0; s < kGatherStreams; ++s) tmp[s] = tmp_all + s * tstride;
+    int dfast = 0;  // columns whose 8-byte move stays inside the row
+    while (dfast < dw - 1 && off[dfast] + 8 <= rb) ++dfast;
+    for (int j = 0; j < kGatherStreamGap; ++j) {
+        const uint8_t* sr[kGatherStreams];
+        for (int s = 0; s < kGatherStreams; ++s) {
+            const int64_t it = lo + s * kGatherStreamGap + j;
+            const int64_t f = it / g.n_touched, i = it - f * g.n_touched;
+            sr[s] = src + f * frame_stride + (int64_t)g.touched[i] * pitch;
+        }
+        for (int d = 0; d < dfast; ++d) {
+            if (pf > 0 && (d & 3) == 0)
+                for (int s = 0; s < kGatherStreams; ++s) __builtin_prefetch(sr[s] + off[d] + pf, 0, 2);  // runs on into the next row: harmless
+            for (int s = 0; s < kGatherStreams; ++s) {
+                uint64_t v;
+                memcpy(&v, sr[s] + off[d], 8);
+                memcpy(tmp[s] + 6 * d, &v, 8);  // the 2 spare bytes are overwritten by column d + 1
+            }
+        }
+        for (int s = 0; s < kGatherStreams; ++s) {
+            for (int d = dfast; d < dw; ++d) {
+                const int nbytes = std::min(6, rb - off[d]);  // a clamped last column only has tap 0 (tap 1 weighs 0)
+                memcpy(tmp[s] + 6 * d, sr[s] + off[d], (size_t)nbytes);
+                if (nbytes < 6) memset(tmp[s] + 6 * d + nbytes, 0, (size_t)(6 - nbytes));
+            }
+            if (trb > 6 * dw) memset(tmp[s] + 6 * dw, 0, (size_t)(trb - 6 * dw));
+            uint8_t* out_row = dst_base + (lo + s * kGatherStreamGap + j) * trb;
+            for (int b = 0; b < trb; b += 16)
+                _mm_stream_si128(reinterpret_cast<__m128i*>(out_row + b), _mm_load_si128(reinterpret_cast<const __m128i*>(tmp[s] + b)));
+        }
+    }
+}
 
 // Gathers items [lo, hi) of the (frame-major, touched-row-minor) item sequence of `src` (frames `frame_stride` apart, rows
 // `pitch` apart) into dst_base + item * tap_row_bytes.  dst_base must be 16-byte aligned when nt_stores is set.
@@ -44,6 +94,11 @@ inline void gather_tap_rows(const GatherSpec& g, const uint8_t* src, int64_t fra
     const int dw = g.dst_w, trb = g.tap_row_bytes, rb = g.row_bytes, pf = g.prefetch_bytes;
     const int* off = g.off;
     const bool nt = g.nt_stores && trb <= kMaxTapRow;
+    if (!g.nv12 && nt && g.streams == kGatherStreams) {
+        constexpr int64_t kBlock = kGatherStreams * kGatherStreamGap;
+        for (; lo + kBlock <= hi; lo += kBlock) gather_tap_rows_bgr_block(g, src, frame_stride, pitch, dst_base, lo);
+        if (lo >= hi) { _mm_sfence(); return; }
+    }
     alignas(64) uint8_t tmp_row[kMaxTapRow];
     for (int64_t it = lo; it < hi; ++it) {
         const int64_t f = it / g.n_touched, i = it - f * g.n_touched;

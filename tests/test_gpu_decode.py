@@ -95,6 +95,36 @@ def test_native_decoder_is_bit_identical_to_cv2_imdecode(mjpeg_clip, tmp_path):
             assert np.array_equal(dec[k], cv2.imdecode(np.frombuffer(jpg, np.uint8), cv2.IMREAD_COLOR)), (w, h, k)
 
 
+@pytest.mark.parametrize("lanes", ["2", "1"])
+def test_decode_lanes_respect_a_slow_asynchronous_consumer(mjpeg_clip, monkeypatch, lanes):
+    """Consecutive batches decode on two streams of the library's own (ESD_DEC_LANES=1: on the caller's).  The ring slot of batch k
+    is rewritten by batch k + 2: that write must wait for whatever the caller enqueued to consume batch k -- here an asynchronous
+    copy queued behind a deliberately slow kernel, no host synchronisation anywhere in the loop -- and the caller's stream must
+    see finished pictures.  30 small batches; every byte against cv2.imdecode."""
+    monkeypatch.setenv("ESD_DEC_LANES", lanes)
+    path, src = mjpeg_clip
+    n = src.shape[0]
+    keep = torch.empty((n,) + src.shape[1:], dtype=torch.uint8, device="cuda:0")
+    ballast = torch.randn((2048, 2048), device="cuda:0")
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        with decode.MjpegVideo(path, batch_frames=5, backend=decode.ESD_JPEG_NATIVE) as v:
+            pos = 0
+            while True:
+                b = v.read_batch(0)
+                if b is None:
+                    break
+                for _ in range(3):
+                    ballast = (ballast @ ballast).clamp_(-1, 1)     # the consumer is late: ~1 ms of work ahead of the copy
+                keep[pos:pos + b.shape[0]].copy_(b, non_blocking=True)
+                pos += int(b.shape[0])
+            st.synchronize()
+    assert pos == n
+    got = keep.cpu().numpy()
+    for k, jpg in enumerate(_avi_pictures(path)):
+        assert np.array_equal(got[k], cv2.imdecode(np.frombuffer(jpg, np.uint8), cv2.IMREAD_COLOR)), k
+
+
 def test_decoder_decodes_the_right_pictures(mjpeg_clip):
     path, src = mjpeg_clip
     got, fps, backend, n = _decode_all(path, batch_frames=32, backend=decode.ESD_JPEG_GPU_HYBRID)

@@ -18,7 +18,7 @@ def shim(tmp_path_factory):
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", str(so), os.path.join(ROOT, "tests", "gather_shim.cpp")])
     L = C.CDLL(str(so))
     vp, i32, i64 = C.c_void_p, C.c_int, C.c_int64
-    L.shim_gather.argtypes = [i32, i32, i32, vp, vp, i64, i32, i32, i32, i32, vp, i64, i64, vp, i64, i64, i32]
+    L.shim_gather.argtypes = [i32, i32, i32, vp, vp, i64, i32, i32, i32, i32, vp, i64, i64, vp, i64, i64, i32, i32]
     L.shim_gather.restype = None
     return L
 
@@ -36,8 +36,9 @@ def aligned(n, fill=0xEE):
 
 
 @pytest.mark.parametrize("w,h,dw,dh", [(1920, 1080, 256, 144), (642, 362, 256, 144), (300, 200, 256, 171), (34, 18, 17, 9)])
-@pytest.mark.parametrize("nt,pf", [(0, 0), (1, 4096), (1, 0), (0, 512)])
-def test_bgr_tap_gather_layout(shim, w, h, dw, dh, nt, pf):
+@pytest.mark.parametrize("nt,pf,streams", [(0, 0, 1), (1, 4096, 1), (1, 0, 1), (0, 512, 1), (1, 4096, 8), (1, 0, 8)])
+def test_bgr_tap_gather_layout(shim, w, h, dw, dh, nt, pf, streams):
+    """streams = 8: the ingest path's default, eight rows gathered in lock-step (blocks of 16 items; ragged remainders fall back)."""
     rng = np.random.default_rng(w + dw)
     n = 3
     pitch = w * 3 + 5
@@ -50,7 +51,7 @@ def test_bgr_tap_gather_layout(shim, w, h, dw, dh, nt, pf):
     items = n * nt_rows
     for lo, hi in ((0, 7), (7, items - 3), (items - 3, items)):   # ragged ranges, as the worker pool hands them out
         shim.shim_gather(dw, trb, w * 3, off.ctypes.data, rows.ctypes.data, nt_rows, nt_rows, 0, min(pf, w * 3), nt,
-                         frames.ctypes.data, frames.strides[0], pitch, dst.ctypes.data, lo, hi, 0)
+                         frames.ctypes.data, frames.strides[0], pitch, dst.ctypes.data, lo, hi, 0, streams)
     got = dst.reshape(n, nt_rows, trb)
     px = frames[:, :, :w * 3].reshape(n, h, w, 3)
     x1 = np.minimum(xo + 1, w - 1)
@@ -76,7 +77,7 @@ def test_nv12_tap_gather_layout(shim, w, h, dw, dh, nt, pf):
     items = n * nt_rows
     for lo, hi in ((0, 5), (5, items)):
         shim.shim_gather(dw, trb, w, xo.ctypes.data, touched.ctypes.data, nt_rows, len(yrows), 1, min(pf, w), nt,
-                         frames.ctypes.data, frames.strides[0], pitch, dst.ctypes.data, lo, hi, 0)
+                         frames.ctypes.data, frames.strides[0], pitch, dst.ctypes.data, lo, hi, 0, 1)
     got = dst.reshape(n, nt_rows, trb)
     x1 = np.minimum(xo + 1, w - 1)
     ysrc = frames[:, yrows, :w]
@@ -112,7 +113,7 @@ def test_i420_tap_gather_equals_nv12_gather_of_the_interleaved_frame(shim, w, h,
         dst = aligned(items * trb)
         for lo, hi in ((0, 3), (3, items)):
             shim.shim_gather(dw, trb, w, xo.ctypes.data, touched.ctypes.data, nt_rows, len(yrows), fmt, min(pf, w), nt,
-                             frames.ctypes.data, frames.strides[0], w, dst.ctypes.data, lo, hi, h)
+                             frames.ctypes.data, frames.strides[0], w, dst.ctypes.data, lo, hi, h, 1)
         out.append(dst.reshape(n, nt_rows, trb)[:, :, :4 * dw].copy())
     ny = len(yrows)
     assert np.array_equal(out[0][:, :ny, :2 * dw], out[1][:, :ny, :2 * dw])
