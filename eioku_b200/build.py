@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libesd.so")
 SOURCES = ["esd.cu"]
-DEPS = ["esd.cu", "esd_kernels.cuh", "ingest_gather.h", "host_tables.h", os.path.join("..", "..", "include", "esd.h")]
+DEPS = ["esd.cu", "esd_kernels.cuh", "ingest_gather.h", "host_tables.h", "guard_alloc.h", os.path.join("..", "..", "include", "esd.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -37,7 +37,7 @@ def is_stale() -> bool:
 
 
 DECODE_LIB = os.path.join(HERE, "libesd_decode.so")
-DECODE_DEPS = ["esd_decode.cu", "jpeg_core.h", "jpeg_parse.h", os.path.join("..", "..", "include", "esd_decode.h")]
+DECODE_DEPS = ["esd_decode.cu", "jpeg_core.h", "jpeg_parse.h", "guard_alloc.h", os.path.join("..", "..", "include", "esd_decode.h")]
 
 
 def build_decode(force: bool = False, verbose: bool = False) -> str:

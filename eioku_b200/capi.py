@@ -31,7 +31,7 @@ EXPORTED_SYMBOLS = (
     "esd_ingest_stats", "esd_ingest_wait_copied", "esd_decide_device", "esd_copy_scores_device", "esd_synchronize", "esd_join", "esd_frames_pushed", "esd_read_scores", "esd_read_edge_counts", "esd_read_average_rgb",
     "esd_read_hash", "esd_read_hash_margin", "esd_debug_read_hash_input", "esd_process_frame_host",
     "esd_post_process", "esd_get_cuts",
-    "esd_decide_arrays", "esd_debug_read_prev", "esd_set_timing", "esd_kernel_time", "esd_kernel_launches",
+    "esd_decide_arrays", "esd_debug_read_prev", "esd_debug_guard_selftest", "esd_set_timing", "esd_kernel_time", "esd_kernel_launches",
 )
 
 
@@ -131,6 +131,7 @@ def load_library(path: Optional[str] = None):
     L.esd_copy_scores_device.argtypes = [vp, i32, i64, i64, vp, i32, vp]
     L.esd_ingest_wait_copied.argtypes = [vp]
     L.esd_debug_read_prev.argtypes = [vp, vp, i64]
+    L.esd_debug_guard_selftest.argtypes = [C.c_int32]
     L.esd_set_timing.argtypes = [vp, i32]
     L.esd_kernel_time.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(i64)]
     L.esd_kernel_launches.restype = i64

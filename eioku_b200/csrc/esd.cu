@@ -30,6 +30,7 @@
 
 #include "esd_kernels.cuh"
 #include "host_tables.h"
+#include "guard_alloc.h"
 #include "ingest_gather.h"
 
 using namespace esd;
@@ -407,8 +408,8 @@ size_t fused_smem_bytes(const esd_ctx* c, int R, int stages) {
 
 void free_plans(esd_ctx* c) {
     for (auto& kv : c->plans) {
-        cudaFree(kv.second.d_units);
-        cudaFree(kv.second.d_begin);
+        esdguard::gfree(kv.second.d_units);
+        esdguard::gfree(kv.second.d_begin);
     }
     c->plans.clear();
 }
@@ -426,8 +427,8 @@ int build_plan(esd_ctx* c, int64_t n, UnitPlan* out) {
                                      c->cfg.split_mode ? c->cfg.split_mode : ESD_SPLIT_STRIPS, units, begin);
     out->grid = grid;
     out->n_units = (int)units.size();
-    CU(c, cudaMalloc(&out->d_units, sizeof(Unit) * std::max<size_t>(1, units.size())));
-    CU(c, cudaMalloc(&out->d_begin, sizeof(int) * begin.size()));
+    CU(c, esdguard::gmalloc(&out->d_units, sizeof(Unit) * std::max<size_t>(1, units.size())));
+    CU(c, esdguard::gmalloc(&out->d_begin, sizeof(int) * begin.size()));
     CU(c, cudaMemcpy(out->d_units, units.data(), sizeof(Unit) * units.size(), cudaMemcpyHostToDevice));
     CU(c, cudaMemcpy(out->d_begin, begin.data(), sizeof(int) * begin.size(), cudaMemcpyHostToDevice));
     return ESD_OK;
@@ -443,7 +444,7 @@ int ensure_capacity(esd_ctx* c, int64_t frames_needed) {
     const int64_t hwords = c->need_hash ? c->hash_words : 0;
     const size_t bytes = (size_t)ncap * (3 * sizeof(unsigned long long) + 6 * sizeof(double) + (bins + 2 + hwords) * sizeof(uint32_t));
     uint8_t* slab = nullptr;
-    CU(c, cudaMalloc(&slab, bytes));
+    CU(c, esdguard::gmalloc(&slab, bytes));
     uint8_t* q = slab;
     auto carve = [&](auto** dst, int64_t per_frame) {
         using T = typename std::remove_pointer<typename std::remove_pointer<decltype(dst)>::type>::type;
@@ -476,7 +477,7 @@ int ensure_capacity(esd_ctx* c, int64_t frames_needed) {
         if (hwords) CU(c, cudaMemcpy(n_hash, c->d_hash, sizeof(uint32_t) * hwords * used, cudaMemcpyDeviceToDevice));
         CU(c, cudaMemcpy(n_hmargin, c->d_hmargin, sizeof(float) * used, cudaMemcpyDeviceToDevice));
     }
-    cudaFree(c->d_slab);
+    esdguard::gfree(c->d_slab);
     c->d_slab = slab;
     c->d_sums3 = n_sums; c->d_cv = n_cv; c->d_av = n_av; c->d_ratio = n_ratio; c->d_hdiff = n_hdiff; c->d_avg = n_avg; c->d_edge_counts = n_edge;
     c->d_counts = bins ? n_counts : nullptr;
@@ -496,29 +497,29 @@ int ensure_scratch(esd_ctx* c, int64_t n) {
     { int rc0 = sync_all(c); if (rc0) return rc0; }
     c->part_cap_frames = 0;
     for (int b = 0; b < 2; ++b) {
-        cudaFree(c->d_part[b]);
-        cudaFree(c->d_hist_part[b]);
-        cudaFree(c->d_vplane[b]);
-        cudaFree(c->d_gplane[b]);
+        esdguard::gfree(c->d_part[b]);
+        esdguard::gfree(c->d_hist_part[b]);
+        esdguard::gfree(c->d_vplane[b]);
+        esdguard::gfree(c->d_gplane[b]);
         c->d_gplane[b] = nullptr;
         c->d_part[b] = nullptr;
         c->d_hist_part[b] = nullptr;
         c->d_vplane[b] = nullptr;
         c->fin_recorded[b] = false;
-        if (c->need_edges) CU(c, cudaMalloc(&c->d_vplane[b], (size_t)n * c->dst_w * c->dst_h));
-        if (c->need_hash) CU(c, cudaMalloc(&c->d_gplane[b], (size_t)n * c->dst_w * c->dst_h + 16));  // + slack: word loads
-        if (c->need_content) CU(c, cudaMalloc(&c->d_part[b], sizeof(uint4) * n * c->n_groups * kConsumerWarps));
-        if (c->need_hist) CU(c, cudaMalloc(&c->d_hist_part[b], sizeof(uint16_t) * n * c->n_groups * c->cfg.hist_bins));
+        if (c->need_edges) CU(c, esdguard::gmalloc(&c->d_vplane[b], (size_t)n * c->dst_w * c->dst_h));
+        if (c->need_hash) CU(c, esdguard::gmalloc(&c->d_gplane[b], (size_t)n * c->dst_w * c->dst_h + 16));  // + slack: word loads
+        if (c->need_content) CU(c, esdguard::gmalloc(&c->d_part[b], sizeof(uint4) * n * c->n_groups * kConsumerWarps));
+        if (c->need_hist) CU(c, esdguard::gmalloc(&c->d_hist_part[b], sizeof(uint16_t) * n * c->n_groups * c->cfg.hist_bins));
     }
     if (c->need_edges) {
-        cudaFree(c->d_edge_bits);
+        esdguard::gfree(c->d_edge_bits);
         c->d_edge_bits = nullptr;
-        CU(c, cudaMalloc(&c->d_edge_bits, sizeof(uint32_t) * n * c->edge_words));
+        CU(c, esdguard::gmalloc(&c->d_edge_bits, sizeof(uint32_t) * n * c->edge_words));
     }
     if (c->need_hash) {
-        cudaFree(c->d_hash_small);
+        esdguard::gfree(c->d_hash_small);
         c->d_hash_small = nullptr;
-        CU(c, cudaMalloc(&c->d_hash_small, (size_t)n * c->hparams.S * c->hparams.S));
+        CU(c, esdguard::gmalloc(&c->d_hash_small, (size_t)n * c->hparams.S * c->hparams.S));
     }
     c->part_cap_frames = n;
     return ESD_OK;
@@ -939,7 +940,7 @@ int esd_create(esd_ctx** out, const esd_config* cfg, int device) {
             return bail(ESD_ERR_UNSUPPORTED);
         }
         CUB(cudaFuncSetAttribute(edges_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esmem));
-        CUB(cudaMalloc(&c->d_edge_prev, sizeof(uint32_t) * c->edge_words));
+        CUB(esdguard::gmalloc(&c->d_edge_prev, sizeof(uint32_t) * c->edge_words));
     }
     if (c->need_hash) {
         HashParams& hp = c->hparams;
@@ -1005,9 +1006,9 @@ int esd_create(esd_ctx** out, const esd_config* cfg, int device) {
         itab.insert(itab.end(), bands.begin(), bands.end());
         std::vector<float> wtab(xw);
         wtab.insert(wtab.end(), yw.begin(), yw.end());
-        CUB(cudaMalloc(&c->d_hash_itab, sizeof(int) * itab.size()));
+        CUB(esdguard::gmalloc(&c->d_hash_itab, sizeof(int) * itab.size()));
         CUB(cudaMemcpy(c->d_hash_itab, itab.data(), sizeof(int) * itab.size(), cudaMemcpyHostToDevice));
-        CUB(cudaMalloc(&c->d_hash_wtab, sizeof(float) * wtab.size()));
+        CUB(esdguard::gmalloc(&c->d_hash_wtab, sizeof(float) * wtab.size()));
         CUB(cudaMemcpy(c->d_hash_wtab, wtab.data(), sizeof(float) * wtab.size(), cudaMemcpyHostToDevice));
         hp.itab = c->d_hash_itab;
         hp.wtab = c->d_hash_wtab;
@@ -1017,7 +1018,7 @@ int esd_create(esd_ctx** out, const esd_config* cfg, int device) {
         for (int u = 0; u < hp.hs; ++u)
             for (int i = 0; i < hp.S; ++i)
                 Cm[(size_t)u * hp.S + i] = u == 0 ? sqrt(1.0 / hp.S) : sqrt(2.0 / hp.S) * cos(pi * (2 * i + 1) * u / (2.0 * hp.S));
-        CUB(cudaMalloc(&c->d_hash_C, sizeof(double) * Cm.size()));
+        CUB(esdguard::gmalloc(&c->d_hash_C, sizeof(double) * Cm.size()));
         CUB(cudaMemcpy(c->d_hash_C, Cm.data(), sizeof(double) * Cm.size(), cudaMemcpyHostToDevice));
         hp.C = c->d_hash_C;
         {   // shared-memory carve-up of hash_kernel
@@ -1077,10 +1078,10 @@ int esd_create(esd_ctx** out, const esd_config* cfg, int device) {
         if (c->i420) {
             std::vector<int> rows;
             for (size_t i = (size_t)c->n_touched_y; i < c->touched.size(); ++i) rows.push_back(c->touched[i] - H);
-            CUB(cudaMalloc(&c->d_uv_src_rows, sizeof(int) * std::max<size_t>(1, rows.size())));
+            CUB(esdguard::gmalloc(&c->d_uv_src_rows, sizeof(int) * std::max<size_t>(1, rows.size())));
             CUB(cudaMemcpy(c->d_uv_src_rows, rows.data(), sizeof(int) * rows.size(), cudaMemcpyHostToDevice));
         }
-        CUB(cudaMalloc(&c->d_yrows, sizeof(YRow) * dh));
+        CUB(esdguard::gmalloc(&c->d_yrows, sizeof(YRow) * dh));
         CUB(cudaMemcpy(c->d_yrows, yr.data(), sizeof(YRow) * dh, cudaMemcpyHostToDevice));
     }
     {
@@ -1121,7 +1122,7 @@ int esd_create(esd_ctx** out, const esd_config* cfg, int device) {
                 c->alg_frame_bytes = (int64_t)c->touched.size() * c->alg_row_bytes;
             }
         }
-        CUB(cudaMalloc(&c->d_xtab, sizeof(uint2) * dw));
+        CUB(esdguard::gmalloc(&c->d_xtab, sizeof(uint2) * dw));
         CUB(cudaMemcpy(c->d_xtab, xt.data(), sizeof(uint2) * dw, cudaMemcpyHostToDevice));
         if (c->resize) {
             // tap-compact layout.  BGR24: column d of a gathered row holds [tap0 BGR, tap1 BGR] at byte 6 d.  NV12: a gathered
@@ -1134,7 +1135,7 @@ int esd_create(esd_ctx** out, const esd_config* cfg, int device) {
                 xt2[x].x = c->nv12 ? ((uint32_t)(2 * x) | ((uint32_t)(4 * x) << 13) | (1u << 26)) : (uint32_t)(6 * x);
                 xt2[x].y = xt[x].y;
             }
-            CUB(cudaMalloc(&c->d_xtab_taps, sizeof(uint2) * dw));
+            CUB(esdguard::gmalloc(&c->d_xtab_taps, sizeof(uint2) * dw));
             CUB(cudaMemcpy(c->d_xtab_taps, xt2.data(), sizeof(uint2) * dw, cudaMemcpyHostToDevice));
             // bank-aware lane -> column mapping (BGR24: three words per row and tap pair; NV12: two luma words -- its chroma
             // words follow the same lattice at half the density)
@@ -1153,8 +1154,8 @@ int esd_create(esd_ctx** out, const esd_config* cfg, int device) {
             sdiv[i] = (int)lrint((255 << 12) / (1. * i));
             hdiv[i] = (int)lrint((180 << 12) / (6. * i));
         }
-        CUB(cudaMalloc(&c->d_sdiv, sizeof sdiv));
-        CUB(cudaMalloc(&c->d_hdiv, sizeof hdiv));
+        CUB(esdguard::gmalloc(&c->d_sdiv, sizeof sdiv));
+        CUB(esdguard::gmalloc(&c->d_hdiv, sizeof hdiv));
         CUB(cudaMemcpy(c->d_sdiv, sdiv, sizeof sdiv, cudaMemcpyHostToDevice));
         CUB(cudaMemcpy(c->d_hdiv, hdiv, sizeof hdiv, cudaMemcpyHostToDevice));
     }
@@ -1237,11 +1238,11 @@ int esd_create(esd_ctx** out, const esd_config* cfg, int device) {
     P.hash_min_scene_len = cfg->hash_min_scene_len;
     P.cuts_stride = c->max_cuts;
 
-    CUB(cudaMalloc(&c->d_state, sizeof(DecisionState)));
-    CUB(cudaMalloc(&c->d_cuts, sizeof(long long) * 5 * c->max_cuts));
+    CUB(esdguard::gmalloc(&c->d_state, sizeof(DecisionState)));
+    CUB(esdguard::gmalloc(&c->d_cuts, sizeof(long long) * 5 * c->max_cuts));
     if (c->need_content) {
-        CUB(cudaMalloc(&c->d_prev[0], sizeof(uint32_t) * dw * dh));
-        CUB(cudaMalloc(&c->d_prev[1], sizeof(uint32_t) * dw * dh));
+        CUB(esdguard::gmalloc(&c->d_prev[0], sizeof(uint32_t) * dw * dh));
+        CUB(esdguard::gmalloc(&c->d_prev[1], sizeof(uint32_t) * dw * dh));
     }
     CUB(cudaEventCreateWithFlags(&c->order_event, cudaEventDisableTiming));
     CUB(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
@@ -1265,22 +1266,22 @@ void esd_destroy(esd_ctx* c) {
     esd_ingest_close(c);
     free_plans(c);
     for (auto& ev : c->timing_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
-    cudaFree(c->d_xtab_taps);
-    cudaFree(c->d_uv_src_rows); cudaFree(c->d_uvpack);
-    cudaFree(c->d_yrows); cudaFree(c->d_xtab); cudaFree(c->d_sdiv); cudaFree(c->d_hdiv);
-    cudaFree(c->d_prev[0]); cudaFree(c->d_prev[1]); cudaFree(c->d_state); cudaFree(c->d_cuts);
-    cudaFree(c->d_slab);
-    for (int b = 0; b < 2; ++b) { cudaFree(c->d_part[b]); cudaFree(c->d_hist_part[b]); cudaFree(c->d_vplane[b]); if (c->ev_fin[b]) cudaEventDestroy(c->ev_fin[b]); }
-    cudaFree(c->d_edge_bits); cudaFree(c->d_edge_prev);
+    esdguard::gfree(c->d_xtab_taps);
+    esdguard::gfree(c->d_uv_src_rows); esdguard::gfree(c->d_uvpack);
+    esdguard::gfree(c->d_yrows); esdguard::gfree(c->d_xtab); esdguard::gfree(c->d_sdiv); esdguard::gfree(c->d_hdiv);
+    esdguard::gfree(c->d_prev[0]); esdguard::gfree(c->d_prev[1]); esdguard::gfree(c->d_state); esdguard::gfree(c->d_cuts);
+    esdguard::gfree(c->d_slab);
+    for (int b = 0; b < 2; ++b) { esdguard::gfree(c->d_part[b]); esdguard::gfree(c->d_hist_part[b]); esdguard::gfree(c->d_vplane[b]); if (c->ev_fin[b]) cudaEventDestroy(c->ev_fin[b]); }
+    esdguard::gfree(c->d_edge_bits); esdguard::gfree(c->d_edge_prev);
     c->kg.destroy();
-    cudaFree(c->dec_d_scores); cudaFree(c->dec_d_ratio); cudaFree(c->dec_d_state);
+    esdguard::gfree(c->dec_d_scores); esdguard::gfree(c->dec_d_ratio); esdguard::gfree(c->dec_d_state);
     if (c->dec_h) cudaFreeHost(c->dec_h);
     if (c->dec_stream) cudaStreamDestroy(c->dec_stream);
     if (c->pf_h) cudaFreeHost(c->pf_h);
     if (c->pf_mailbox) cudaFreeHost(c->pf_mailbox);
     if (c->pf_stream) cudaStreamDestroy(c->pf_stream);
-    cudaFree(c->d_gplane[0]); cudaFree(c->d_gplane[1]); cudaFree(c->d_hash_small);
-    cudaFree(c->d_hash_itab); cudaFree(c->d_hash_wtab); cudaFree(c->d_hash_C);
+    esdguard::gfree(c->d_gplane[0]); esdguard::gfree(c->d_gplane[1]); esdguard::gfree(c->d_hash_small);
+    esdguard::gfree(c->d_hash_itab); esdguard::gfree(c->d_hash_wtab); esdguard::gfree(c->d_hash_C);
     if (c->order_event) cudaEventDestroy(c->order_event);
     if (c->ev_fused) cudaEventDestroy(c->ev_fused);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
@@ -1397,10 +1398,10 @@ int esd_push_i420(esd_ctx* c, const uint8_t* d_y, const uint8_t* d_u, const uint
     const size_t need = (size_t)n * (size_t)n_uv * (size_t)uv_pitch;
     if (need > c->uvpack_bytes) {
         if ((rc = sync_all(c))) return rc;  // an earlier push may still read the old buffer
-        cudaFree(c->d_uvpack);
+        esdguard::gfree(c->d_uvpack);
         c->d_uvpack = nullptr;
         c->uvpack_bytes = 0;
-        CU(c, cudaMalloc(&c->d_uvpack, need));
+        CU(c, esdguard::gmalloc(&c->d_uvpack, need));
         c->uvpack_bytes = need;
     }
     // the repack writes the buffer the previous push's fused kernel reads: order this stream behind it first
@@ -1444,7 +1445,7 @@ int esd_ingest_open(esd_ctx* c, int32_t n_slots, int32_t frames_per_slot) {
     c->next_slot = 0;
     for (auto& s : c->ring) {
         // the pinned staging buffer is only needed for pageable sources: allocated on first use
-        CU(c, cudaMalloc(&s.d_rows, slot_bytes));
+        CU(c, esdguard::gmalloc(&s.d_rows, slot_bytes));
         CU(c, cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
         CU(c, cudaEventCreateWithFlags(&s.consumed, cudaEventDisableTiming));
     }
@@ -1459,7 +1460,7 @@ int esd_ingest_close(esd_ctx* c) {
     if (c->compute_stream) cudaStreamSynchronize(c->compute_stream);
     for (auto& s : c->ring) {
         if (s.h_pinned) cudaFreeHost(s.h_pinned);
-        cudaFree(s.d_rows);
+        esdguard::gfree(s.d_rows);
         if (s.copied) cudaEventDestroy(s.copied);
         if (s.consumed) cudaEventDestroy(s.consumed);
     }
@@ -1884,15 +1885,15 @@ int esd_process_frame_host(esd_ctx* c, const uint8_t* h_bgr, int64_t pitch, int6
 // counts, completion ticket, the cuts themselves) are written by decide_kernel straight into host-mapped pinned memory.
 static int ensure_decide_scratch(esd_ctx* c, int64_t n_dev, int64_t n_host_stage) {
     if (!c->dec_stream) CU(c, cudaStreamCreateWithFlags(&c->dec_stream, cudaStreamNonBlocking));
-    if (!c->dec_d_state) CU(c, cudaMalloc(&c->dec_d_state, sizeof(DecisionState)));
+    if (!c->dec_d_state) CU(c, esdguard::gmalloc(&c->dec_d_state, sizeof(DecisionState)));
     if (n_dev > c->dec_cap) {
         const int64_t ncap = std::max<int64_t>(n_dev, std::max<int64_t>(32768, 2 * c->dec_cap));
         CU(c, cudaStreamSynchronize(c->dec_stream));
-        cudaFree(c->dec_d_scores); cudaFree(c->dec_d_ratio);
+        esdguard::gfree(c->dec_d_scores); esdguard::gfree(c->dec_d_ratio);
         c->dec_d_scores = c->dec_d_ratio = nullptr;
         c->dec_cap = 0;
-        CU(c, cudaMalloc(&c->dec_d_scores, sizeof(double) * ncap));
-        CU(c, cudaMalloc(&c->dec_d_ratio, sizeof(double) * ncap));
+        CU(c, esdguard::gmalloc(&c->dec_d_scores, sizeof(double) * ncap));
+        CU(c, esdguard::gmalloc(&c->dec_d_ratio, sizeof(double) * ncap));
         c->dec_cap = ncap;
     }
     if (!c->dec_h || n_host_stage > c->dec_h_scores) {
@@ -2030,6 +2031,17 @@ int esd_debug_read_prev(esd_ctx* c, uint32_t* out, int64_t cap) {
     if (rc) return rc;
     CU(c, cudaMemcpy(out, c->d_prev[c->prev_parity], sizeof(uint32_t) * n, cudaMemcpyDeviceToHost));
     return ESD_OK;
+}
+
+int esd_debug_guard_selftest(int32_t damage) {
+    // with ESD_GUARD=1: allocates a guarded buffer, optionally writes one byte past its end, frees it (the free verifies the
+    // red zones: a damaged one aborts the process).  Returns 1 when the guards are active, 0 when the wrappers are plain.
+    if (!esdguard::enabled()) return 0;
+    uint8_t* p = nullptr;
+    if (esdguard::gmalloc(&p, 1000) != cudaSuccess) return ESD_ERR_CUDA;
+    if (damage) cudaMemset(p + 1000, 0, 1);
+    esdguard::gfree(p);
+    return 1;
 }
 
 int esd_set_timing(esd_ctx* c, int32_t enable) {

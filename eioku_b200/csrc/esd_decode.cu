@@ -21,6 +21,7 @@
 #include <string>
 #include <vector>
 
+#include "guard_alloc.h"
 #include "jpeg_parse.h"
 
 namespace {
@@ -374,7 +375,7 @@ void esd_mjpeg_close(esd_mjpeg* h) {
         if (h->done[b]) { cudaEventSynchronize(h->done[b]); cudaEventDestroy(h->done[b]); }
         collect_timing(h, b);
         for (int k = 0; k < 4; ++k) if (h->tev[b][k]) cudaEventDestroy(h->tev[b][k]);
-        cudaFree(h->d_out[b]);
+        esdguard::gfree(h->d_out[b]);
         if (h->h_stage[b]) cudaFreeHost(h->h_stage[b]);
     }
     if (h->timing && h->t_batches)
@@ -384,7 +385,7 @@ void esd_mjpeg_close(esd_mjpeg* h) {
     for (int b = 0; b < 2; ++b) {
         if (h->lane[b]) { cudaStreamSynchronize(h->lane[b]); cudaStreamDestroy(h->lane[b]); }
         if (h->consumed[b]) cudaEventDestroy(h->consumed[b]);
-        cudaFree(h->d_comp[b]); cudaFree(h->d_coef[b]); cudaFree(h->d_planes[b]);
+        esdguard::gfree(h->d_comp[b]); esdguard::gfree(h->d_coef[b]); esdguard::gfree(h->d_planes[b]);
     }
     if (h->state) nvjpegJpegStateDestroy(h->state);
     if (h->nj) nvjpegDestroy(h->nj);
@@ -449,8 +450,8 @@ int esd_mjpeg_open(esd_mjpeg** out, const char* path, int device, int32_t batch_
             cudaError_t e = cudaFuncSetAttribute(jpeg_entropy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kEntropyThreads * sizeof(esdjpeg::ScanTables)));
             if (e == cudaSuccess) e = cudaFuncSetAttribute(jpeg_entropy_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kEntropyThreads * sizeof(esdjpeg::ScanTables)));
             for (int b = 0; b < h->lanes && e == cudaSuccess; ++b) {
-                e = cudaMalloc(&h->d_coef[b], (size_t)h->batch * h->blocks_per_frame * 64 * sizeof(int16_t));
-                if (e == cudaSuccess) e = cudaMalloc(&h->d_planes[b], (size_t)h->batch * h->plane_bytes);
+                e = esdguard::gmalloc(&h->d_coef[b], (size_t)h->batch * h->blocks_per_frame * 64 * sizeof(int16_t));
+                if (e == cudaSuccess) e = esdguard::gmalloc(&h->d_planes[b], (size_t)h->batch * h->plane_bytes);
                 if (e == cudaSuccess && h->lanes > 1) e = cudaStreamCreateWithFlags(&h->lane[b], cudaStreamNonBlocking);
                 if (e == cudaSuccess && h->lanes > 1) e = cudaEventCreateWithFlags(&h->consumed[b], cudaEventDisableTiming);
             }
@@ -487,7 +488,7 @@ int esd_mjpeg_open(esd_mjpeg** out, const char* path, int device, int32_t batch_
         if (nvjpegGetHardwareDecoderInfo(h->nj, &h->hw_engines, &cores) != NVJPEG_STATUS_SUCCESS) h->hw_engines = 0;
     }
     for (int b = 0; b < 2; ++b) {
-        if (cudaMalloc(&h->d_out[b], frame_bytes * h->batch) != cudaSuccess || cudaEventCreateWithFlags(&h->done[b], cudaEventDisableTiming | cudaEventBlockingSync) != cudaSuccess) {
+        if (esdguard::gmalloc(&h->d_out[b], frame_bytes * h->batch) != cudaSuccess || cudaEventCreateWithFlags(&h->done[b], cudaEventDisableTiming | cudaEventBlockingSync) != cudaSuccess) {
             fail(h, ESD_DEC_ERR_CUDA, "device buffer of %d frames (%zu bytes) could not be allocated: %s", h->batch, frame_bytes * h->batch,
                  cudaGetErrorString(cudaGetLastError()));
             return bail(ESD_DEC_ERR_CUDA);
@@ -616,9 +617,9 @@ int esd_mjpeg_read(esd_mjpeg* h, int64_t max_frames, void* stream, uint8_t** d_b
     }
     if (native) {
         if (total > h->d_comp_bytes[ln]) {  // device mirror of the staging block (grow-only; everything that used it ran on `ds` before)
-            if (h->d_comp[ln]) { cudaStreamSynchronize(ds); cudaFree(h->d_comp[ln]); h->d_comp[ln] = nullptr; h->d_comp_bytes[ln] = 0; }
+            if (h->d_comp[ln]) { cudaStreamSynchronize(ds); esdguard::gfree(h->d_comp[ln]); h->d_comp[ln] = nullptr; h->d_comp_bytes[ln] = 0; }
             const size_t want = total + total / 4 + 4096;
-            if (cudaMalloc(&h->d_comp[ln], want) != cudaSuccess) return fail(h, ESD_DEC_ERR_CUDA, "device staging of %zu bytes could not be allocated", want);
+            if (esdguard::gmalloc(&h->d_comp[ln], want) != cudaSuccess) return fail(h, ESD_DEC_ERR_CUDA, "device staging of %zu bytes could not be allocated", want);
             h->d_comp_bytes[ln] = want;
         }
         // this slot's output was last read by the consumer of the batch two reads ago: the lane waits for that work, not for the

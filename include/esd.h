@@ -304,6 +304,10 @@ ESD_API int64_t esd_kernel_launches(const esd_ctx* ctx);
 /* Test hook: packed H | S<<8 | V<<16 of the last pushed frame at detector resolution
  * ([dst_height][dst_width] uint32), i.e. the on-device twin of cvtColor(resize(frame)).  Synchronises. */
 ESD_API int esd_debug_read_prev(esd_ctx* ctx, uint32_t* out, int64_t cap_elems);
+/* Test hook for the red-zone allocator (csrc/guard_alloc.h; ESD_GUARD=1 puts 256-byte guard zones around every device buffer of
+ * the library and verifies them at free time -- this pool's stand-in for compute-sanitizer).  Returns 1 when the guards are
+ * active (0: plain allocations); damage != 0 writes one byte past a guarded buffer first, which must abort the process. */
+ESD_API int esd_debug_guard_selftest(int32_t damage);
 
 #ifdef __cplusplus
 }

@@ -1,5 +1,7 @@
 """GPU edge cases: empty / single-frame / tiny / ragged inputs, maximum widths, context reuse, overflow and
 metric export -- all against the oracle, through the C ABI."""
+import os
+
 import numpy as np
 import pytest
 
@@ -268,3 +270,22 @@ def test_every_base_misalignment_and_odd_pitch(w, h, dst):
         assert np.array_equal(sc["sums3"].astype(np.int64), sums), off
         assert np.array_equal(sc["hist"], hist), off
         assert same_f64(sc["content_val"], cv) and same_f64(sc["hist_diff"], hd), off
+
+
+def test_red_zone_allocator_catches_an_out_of_bounds_write():
+    """compute-sanitizer is closed on this pool; the library's own stand-in (csrc/guard_alloc.h, ESD_GUARD=1) surrounds every
+    device buffer with guard zones verified at free time.  In a child process: guards active; an undamaged buffer passes; a write
+    one byte past the end aborts.  (Run the whole GPU suite under ESD_GUARD=1 to check every kernel: profiles/r02_guard_suite.log.)"""
+    import subprocess
+    import sys
+
+    code = ("import os, sys; sys.path.insert(0, %r); from eioku_b200 import capi; L = capi.load_library(); "
+            "import torch; torch.zeros(1, device='cuda'); r = L.esd_debug_guard_selftest(int(sys.argv[1])); print('selftest', r)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, ESD_GUARD="1")
+    ok = subprocess.run([sys.executable, "-c", code % root, "0"], env=env, capture_output=True, text=True, timeout=120)
+    assert ok.returncode == 0 and "selftest 1" in ok.stdout, ok.stderr[-500:]
+    bad = subprocess.run([sys.executable, "-c", code % root, "1"], env=env, capture_output=True, text=True, timeout=120)
+    assert bad.returncode != 0 and "RED ZONE DAMAGED" in bad.stderr, (bad.returncode, bad.stderr[-500:])
+    off = subprocess.run([sys.executable, "-c", code % root, "1"], env=dict(os.environ, ESD_GUARD="0"), capture_output=True, text=True, timeout=120)
+    assert off.returncode == 0 and "selftest 0" in off.stdout
