@@ -173,3 +173,137 @@ def is_mjpeg_avi(path: str) -> bool:
         return False
     i = head.find(b"strh")
     return i >= 0 and head[i + 8:i + 12] == b"vids" and head[i + 12:i + 16].upper() in (b"MJPG", b"AVI1", b"JPEG", b"IJPG")
+
+
+class SeekError(RuntimeError):
+    """A capture did not land on the frame it was asked to seek to (or a range came up short)."""
+
+
+class CaptureRangeVideo:
+    """Frames [first_frame, end_frame) of a file through a cv2.VideoCapture of its own: the reference's host decode loop
+    (`cap = cv2.VideoCapture(path)` ... `cap.read()`, model_manager.py:237-263) for every codec OpenCV's FFmpeg build reads,
+    restricted to a frame range so that SEVERAL of them can decode one file at once (service: `decode_workers`; one capture per
+    frame-range shard, all shards scored on one GPU and merged by the usual global decision pass).  Frames are decoded straight
+    into one of two reused batch buffers by a thread of the source's own, so decoding the next batch overlaps whatever the caller
+    does with this one (cv2 and libesd both release the GIL); a batch stays valid until the next read_batch.  Host batches go
+    through the ingest ring, whose host-side copy of pageable memory is complete when the push returns.
+
+    A seek that does not land exactly breaks parity silently, so it is checked twice: the capture must report the requested
+    position, and the frames listed in `watch` (the first frames of the other ranges) are fingerprinted as they pass, so that the
+    caller can compare every range's first frame with the same frame as decoded by the range that owns it."""
+
+    pixel_format = "bgr24"
+    frames_stable = False
+
+    def __init__(self, path: str, first_frame: int = 0, end_frame: Optional[int] = None, batch_frames: int = 64, watch=(),
+                 threads: int = 0, prefetch: bool = True):
+        import queue
+        import threading
+
+        import cv2
+        import numpy as np
+
+        self._cv2, self._np = cv2, np
+        if threads > 0 and hasattr(cv2, "CAP_PROP_N_THREADS"):
+            # several captures at once: FFmpeg's own frame threads would otherwise take every core for each of them
+            self._cap = cv2.VideoCapture(path, cv2.CAP_FFMPEG, [cv2.CAP_PROP_N_THREADS, int(threads)])
+            if not self._cap.isOpened():
+                self._cap = cv2.VideoCapture(path)
+        else:
+            self._cap = cv2.VideoCapture(path)
+        if not self._cap.isOpened():
+            raise RuntimeError(f"Failed to open video: {path}")
+        self.n_frames = int(self._cap.get(cv2.CAP_PROP_FRAME_COUNT))
+        self.frame_size = (int(self._cap.get(cv2.CAP_PROP_FRAME_WIDTH)), int(self._cap.get(cv2.CAP_PROP_FRAME_HEIGHT)))
+        self.frame_rate = float(self._cap.get(cv2.CAP_PROP_FPS) or 30.0)
+        self.start_frame = int(first_frame)
+        self._end = self.n_frames if end_frame is None else min(int(end_frame), self.n_frames)
+        self._pos = self.start_frame
+        if self.start_frame:
+            self._cap.set(cv2.CAP_PROP_POS_FRAMES, self.start_frame)
+            got = int(self._cap.get(cv2.CAP_PROP_POS_FRAMES))
+            if got != self.start_frame:
+                self._cap.release()
+                raise SeekError(f"{path}: seek to frame {self.start_frame} landed on {got}")
+        self._batch = max(1, int(batch_frames))
+        self._watch = {int(f) for f in watch} | {self.start_frame}
+        self.digests = {}   # frame index -> fingerprint, for the watched frames this range decoded
+        shape = (self._batch, self.frame_size[1], self.frame_size[0], 3)
+        self._held = None
+        self._thread = None
+        if prefetch:
+            self._free, self._ready = queue.Queue(), queue.Queue()
+            for _ in range(2):
+                self._free.put(np.empty(shape, np.uint8))
+            self._thread = threading.Thread(target=self._pump, name="esd-capture", daemon=True)
+            self._thread.start()
+        else:
+            self._buf = np.empty(shape, np.uint8)
+
+    @staticmethod
+    def _fingerprint(frame) -> int:
+        import zlib
+
+        return zlib.crc32(frame[::4].tobytes())   # every fourth row: 1.5 MB of a 1080p frame
+
+    def _decode_into(self, buf) -> int:
+        k = min(self._batch, self._end - self._pos)
+        got = 0
+        for i in range(max(0, k)):
+            ok, frame = self._cap.read(buf[i])
+            if not ok:
+                break
+            if frame is not buf[i] and not self._np.shares_memory(frame, buf[i]):
+                buf[i][...] = frame
+            if self._pos + i in self._watch:
+                self.digests[self._pos + i] = self._fingerprint(buf[i])
+            got += 1
+        self._pos += got
+        return got
+
+    def _pump(self):
+        try:
+            while True:
+                buf = self._free.get()
+                if buf is None:
+                    return
+                got = self._decode_into(buf)
+                self._ready.put((buf, got))
+                if got == 0:
+                    return
+        except BaseException as e:  # noqa: BLE001 - handed to the reading thread
+            self._ready.put((e, -1))
+
+    def read_batch(self, n: int = 0):
+        if self._thread is None:
+            got = self._decode_into(self._buf)
+            return self._buf[:got] if got else None
+        if self._held is not None:        # the caller is done with the previous batch
+            self._free.put(self._held)
+            self._held = None
+        if self._ready is None:
+            return None
+        buf, got = self._ready.get()
+        if got < 0:
+            self._ready = None
+            raise buf
+        if got == 0:
+            self._ready = None
+            return None
+        self._held = buf
+        return buf[:got]
+
+    def close(self):
+        if self._thread is not None:
+            self._free.put(None)
+            self._thread.join(timeout=30)
+            self._thread = None
+        if self._cap is not None:
+            self._cap.release()
+            self._cap = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()

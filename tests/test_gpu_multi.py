@@ -208,3 +208,46 @@ def test_ingest_wait_copied_releases_pinned_frames_early():
         ctx.ingest_close()
     want, _, _ = co.score_frames(frames, 256, 144)
     assert np.array_equal(got.astype(np.int64), want)
+
+
+def test_one_file_decoded_by_several_host_captures_at_once(tmp_path, monkeypatch):
+    """`decode_workers`: frame ranges (+ halo) of one inter-coded file decoded by several cv2.VideoCapture instances concurrently,
+    all scored on one GPU, one global decision pass -- the scene list of the sequential decode, for every detector that shards;
+    and when two captures disagree about a frame (an inexact seek) the job falls back to the sequential decode."""
+    import asyncio
+
+    cv2 = pytest.importorskip("cv2")
+    from eioku_b200 import decode, service
+    from eioku_b200.service import ModelManager
+
+    w, h, n, seed = 640, 360, 260, 41
+    sch = synth.build_schedule(seed, n, min_len=25, max_len=60, noise_amp=0)
+    frames = co.synth_frames(seed, w, h, sch.descs)
+    path = str(tmp_path / "clip.mp4")
+    vw = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"mp4v"), 25.0, (w, h))
+    if not vw.isOpened():
+        pytest.skip("no mp4v encoder in this OpenCV build")
+    for f in frames:
+        vw.write(f)
+    vw.release()
+    for cfg in ({}, {"detector": "adaptive", "min_scene_len": 10}, {"detector": "hist"}, {"detector": "content+adaptive+hist"}):
+        want = asyncio.run(ModelManager().detect_scenes(path, {**cfg, "decode_workers": 1}))
+        assert len(want["scenes"]) >= (1 if cfg.get("detector") == "hist" else 3)
+        for workers in (2, 5):
+            got = asyncio.run(ModelManager().detect_scenes(path, {**cfg, "decode_workers": workers}))
+            assert got == want, (cfg, workers)
+    # the sharded path really ran ...
+    calls = []
+    real = service._detect_scenes_capture_sharded
+    monkeypatch.setattr(service, "_detect_scenes_capture_sharded", lambda *a, **k: calls.append(a[3]) or real(*a, **k))
+    assert asyncio.run(ModelManager().detect_scenes(path, {"decode_workers": 3})) == asyncio.run(ModelManager().detect_scenes(path, {"decode_workers": 1}))
+    assert calls == [3]
+    # ... and a capture that cannot be trusted is not: fingerprints that never agree -> sequential decode, same answer
+    import itertools
+
+    counter = itertools.count()
+    monkeypatch.setattr(decode.CaptureRangeVideo, "_fingerprint", staticmethod(lambda frame: next(counter)))
+    assert real(path, {}, 0, 3) is None
+    assert asyncio.run(ModelManager().detect_scenes(path, {"decode_workers": 3})) == asyncio.run(ModelManager().detect_scenes(path, {"decode_workers": 1}))
+    # short clips stay sequential by default
+    assert service.default_decode_workers(500) == 1 and service.default_decode_workers(100000) >= 1
