@@ -444,12 +444,13 @@ def compressed_leg(local, rank, world, dist, dev, args, barrier, all_max):
     size = os.path.getsize(path)
     # a decoder session is one host thread that spends its time inside libesd_decode / libesd (GIL released): ~30 us of host work
     # per picture, so the session count is chosen for pictures in flight on the GPU, not by the core count
-    # (a node's cores are shared by its ranks: at least 2, at most 8 sessions per rank)
+    # (a node's cores are shared by its ranks: at least 2, at most 4 sessions per rank)
     try:
         cores = len(os.sched_getaffinity(0))
     except AttributeError:
         cores = os.cpu_count() or 8
-    sessions = args.decode_sessions if args.decode_sessions > 0 else max(2, min(8, cores // max(1, world)))
+    # (with a block of threads per picture the GPU side saturates at 3-4 sessions: profiles/r02_decode_parallel.md)
+    sessions = args.decode_sessions if args.decode_sessions > 0 else max(2, min(4, cores // max(1, world)))
     out = None
     try:
         # parity on the decoded surface: the frames one session scored, downloaded, through the oracle's integer chain
@@ -796,8 +797,8 @@ def main():
     ap.add_argument("--compressed-frames", type=int, default=1024, help="length of the Motion-JPEG file (four decode batches per pass: the decoder keeps two batches in flight per session)")
     ap.add_argument("--compressed-passes", type=int, default=6)
     ap.add_argument("--compressed-cpu-passes", type=int, default=2)
-    ap.add_argument("--decode-sessions", type=int, default=0, help="GPU decoder sessions per rank (0 = 8)")
-    ap.add_argument("--decode-batch", type=int, default=256, help="pictures per decode batch and session")
+    ap.add_argument("--decode-sessions", type=int, default=0, help="GPU decoder sessions per rank (0 = up to 4, fewer when the ranks share few cores)")
+    ap.add_argument("--decode-batch", type=int, default=64, help="pictures per decode batch and session")
     ap.add_argument("--config3", default="auto", choices=["auto", "on", "off"], help="run BASELINE config 3 on the ranks (auto: when N > 1)")
     ap.add_argument("--config3-frames", type=int, default=18000)
     ap.add_argument("--ref-sample", type=int, default=192, help="--impl reference: frames per process per pass")

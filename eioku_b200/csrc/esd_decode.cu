@@ -73,6 +73,9 @@ struct esd_mjpeg {
     esdjpeg::FrameGeometry geo{};
     int tq[3] = {0, 0, 0}, td[3] = {0, 0, 0}, ta[3] = {0, 0, 0};
     int blocks_per_frame = 0;
+    // ESD_DEC_ENTROPY=flat keeps the thread-per-picture loop for pictures without restart markers (A/B switch); the default decodes
+    // each picture with a block of threads
+    bool parallel_entropy = !(getenv("ESD_DEC_ENTROPY") && strcmp(getenv("ESD_DEC_ENTROPY"), "flat") == 0);
     bool flat = false;                           // no restart interval: the host removes the byte stuffing and the flat scan decoder runs
     size_t plane_bytes = 0;                      // Y + Cb + Cr sample planes of one frame (MCU-padded)
     // Two decode lanes: batch k runs on lane k & 1 (a stream of the library's own, with its own staging mirror, coefficient and
@@ -255,6 +258,80 @@ __global__ void __launch_bounds__(kEntropyThreads) jpeg_entropy_flat_kernel(Nati
     const int td[3] = {L.td[0], L.td[1], L.td[2]}, ta[3] = {L.ta[0], L.ta[1], L.ta[2]};
     esdjpeg::decode_scan_flat(reinterpret_cast<const uint32_t*>(stage + d.off), (int)d.len, T, td, ta, s_nat, L.mcus_x * L.mcus_y,
                               coef + (size_t)f * L.blocks_per_frame * 64);
+}
+
+// Many threads per picture (jpeg_core.h: decode_span -- speculative sub-sequences that self-synchronise): one block per picture,
+// a thread per sub-sequence of the scan.  Rounds until no thread's start state changes (2-8 for camera / encoder content, at worst
+// one per sub-sequence, which is the sequential decoding at the old cost), block-wide prefix sums of the block counts and DC sums,
+// one writing pass.  A 1080p picture: ~1 000 threads x ~100 symbols per round instead of one thread x 275 000 symbols.
+constexpr int kParThreads = 1024;
+__global__ void __launch_bounds__(kParThreads) jpeg_entropy_parallel_kernel(NativeLayout L, const uint8_t* __restrict__ stage,
+                                                                            const esd_mjpeg::NativeDesc* __restrict__ desc,
+                                                                            int16_t* __restrict__ coef) {
+    __shared__ esdjpeg::ScanTables T;
+    __shared__ uint8_t s_nat[64];
+    __shared__ esdjpeg::SpanState s_end[kParThreads];
+    __shared__ int s_warp[4][kParThreads / 32];
+    __shared__ int s_bad;
+    const int tid = threadIdx.x, f = blockIdx.x;
+    const esd_mjpeg::NativeDesc d = desc[f];
+    if (tid == 0) s_bad = 0;
+    if (tid < 64) s_nat[tid] = c_natural_order[tid];
+    __syncthreads();
+    if (tid < 4) {   // DC0, DC1, AC0, AC1: the picture's own tables, one thread each
+        esdjpeg::HuffTable* tb = tid < 2 ? &T.dc[tid] : &T.ac[tid - 2];
+        if (d.dht[tid] && !esdjpeg::build_huff_table(stage + d.dht[tid], stage + d.dht[tid] + 16, (int)d.nvals[tid], tb)) s_bad = 1;
+    }
+    __syncthreads();
+    if (s_bad) return;
+    const int td[3] = {L.td[0], L.td[1], L.td[2]}, ta[3] = {L.ta[0], L.ta[1], L.ta[2]};
+    const uint32_t* words = reinterpret_cast<const uint32_t*>(stage + d.off);
+    const int nwords = (int)d.len;
+    const int total_blocks = 6 * L.mcus_x * L.mcus_y;
+    const uint32_t S = esdjpeg::span_bits_for(nwords, total_blocks, kParThreads), nbits = (uint32_t)nwords * 32u;
+    const int nt = (int)((nbits + S - 1) / S);
+    const bool active = tid < nt;
+    const unsigned long long e64 = (unsigned long long)(tid + 1) * S;
+    const uint32_t limit = (uint32_t)(e64 < nbits ? e64 : nbits);
+    esdjpeg::SpanState in{(uint32_t)tid * S, 0, 0};
+    esdjpeg::SpanResult res;
+    res.end = in; res.n_blocks = 0; res.dc[0] = res.dc[1] = res.dc[2] = 0;
+    if (active) res = esdjpeg::decode_span<false>(words, nwords, T, td, ta, s_nat, in, limit, nullptr, 0, nullptr, total_blocks);
+    for (;;) {
+        s_end[tid] = res.end;
+        __syncthreads();
+        bool changed = false;
+        if (active && tid > 0) {
+            const esdjpeg::SpanState nin = s_end[tid - 1];
+            if (!esdjpeg::same_state(nin, in)) { in = nin; changed = true; }
+        }
+        if (!__syncthreads_or(changed ? 1 : 0)) break;   // also: every read of s_end is done before the next round's writes
+        if (changed) res = esdjpeg::decode_span<false>(words, nwords, T, td, ta, s_nat, in, limit, nullptr, 0, nullptr, total_blocks);
+    }
+    // exclusive prefix sums over the threads: blocks completed and DC sums per component before this sub-sequence
+    int v[4] = {active ? res.n_blocks : 0, active ? res.dc[0] : 0, active ? res.dc[1] : 0, active ? res.dc[2] : 0};
+    int incl[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        int x = v[q];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, x, o);
+            if ((tid & 31) >= o) x += y;
+        }
+        incl[q] = x;
+        if ((tid & 31) == 31) s_warp[q][tid >> 5] = x;
+    }
+    __syncthreads();
+    int base[4] = {0, 0, 0, 0};
+    for (int w = 0; w < (tid >> 5); ++w) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) base[q] += s_warp[q][w];
+    }
+    if (!active) return;
+    const int blk0 = base[0] + incl[0] - v[0];
+    const int pred[3] = {base[1] + incl[1] - v[1], base[2] + incl[2] - v[2], base[3] + incl[3] - v[3]};
+    esdjpeg::decode_span<true>(words, nwords, T, td, ta, s_nat, in, limit, coef + (size_t)f * L.blocks_per_frame * 64, blk0, pred, total_blocks);
 }
 
 __global__ void __launch_bounds__(128) jpeg_idct_kernel(NativeLayout L, const int16_t* __restrict__ coef, const uint16_t* __restrict__ quant,
@@ -654,7 +731,8 @@ int esd_mjpeg_read(esd_mjpeg* h, int64_t max_frames, void* stream, uint8_t** d_b
         const unsigned egrid = (unsigned)((n + kEntropyThreads - 1) / kEntropyThreads);
         const size_t esmem = kEntropyThreads * sizeof(esdjpeg::ScanTables);
         if (h->timing) cudaEventRecord(h->tev[b][1], ds);
-        if (h->flat) jpeg_entropy_flat_kernel<<<egrid, kEntropyThreads, esmem, ds>>>(L, h->d_comp[ln], ddesc, h->d_coef[ln]);
+        if (h->flat && h->parallel_entropy) jpeg_entropy_parallel_kernel<<<(unsigned)n, kParThreads, 0, ds>>>(L, h->d_comp[ln], ddesc, h->d_coef[ln]);
+        else if (h->flat) jpeg_entropy_flat_kernel<<<egrid, kEntropyThreads, esmem, ds>>>(L, h->d_comp[ln], ddesc, h->d_coef[ln]);
         else jpeg_entropy_kernel<<<egrid, kEntropyThreads, esmem, ds>>>(L, h->d_comp[ln], ddesc, h->d_coef[ln]);
         if (h->timing) cudaEventRecord(h->tev[b][2], ds);
         jpeg_idct_kernel<<<dim3((unsigned)((h->blocks_per_frame + 127) / 128), (unsigned)n), 128, 0, ds>>>(L, h->d_coef[ln], dquant, h->d_planes[ln]);

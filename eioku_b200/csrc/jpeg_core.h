@@ -287,6 +287,173 @@ JPG_HD void decode_scan_flat(const uint32_t* __restrict__ words, int nwords, con
     }
 }
 
+// ---- one picture decoded by MANY threads: speculative sub-sequences that self-synchronise -----------------------------------
+// A scan without restart markers is one dependent chain -- yet Huffman streams resynchronise: a decoder started at an arbitrary bit
+// with a guessed state (block-in-MCU b, zig-zag position k) produces garbage for a while and then, with overwhelming probability,
+// falls into step with the true decoding and stays there (Klein & Wiseman; used for JPEG by Weissenberger & Schmidt, "Accelerating
+// JPEG decompression on GPUs", 2021).  The scan is cut into sub-sequences of S bits, thread t owns the symbols that START in
+// [t S, (t+1) S).  Round 0: every thread decodes its sub-sequence from the guess (p = t S, b = 0, k = 0) -- thread 0's start is the
+// true one.  Round r: thread t restarts from the END state thread t-1 reached in round r-1, if that differs from what it started
+// from before.  A fixed point is the sequential decoding (correct states spread at least one sub-sequence per round, in practice
+// they are there after 2-4 rounds).  Then block counts and DC sums are prefix-summed over the threads and a last pass writes the
+// coefficients -- DC absolute -- exactly where decode_scan_flat puts them.
+struct SpanState {
+    uint32_t p;   // bit position (in the unstuffed scan) where the next symbol starts
+    uint16_t b;   // block inside the MCU, 0..5 (0-3 luma, 4 Cb, 5 Cr)
+    uint16_t k;   // zig-zag position of the next coefficient; 0 = the next symbol is the DC size of a block
+};
+struct SpanResult {
+    SpanState end;     // state after the last symbol that starts before the limit
+    int n_blocks;      // blocks COMPLETED by those symbols
+    int dc[3];         // sum of the DC differences decoded, per component
+};
+JPG_HD bool same_state(const SpanState& a, const SpanState& b) { return a.p == b.p && a.b == b.b && a.k == b.k; }
+
+// Decodes the symbols that start in [start.p, limit_bit).  WRITE: coefficients go to cf (decoding order, natural order inside a
+// block) with `blk0` the index of the block in progress at the start, `pred` the DC predictors there, blocks >= total_blocks (the
+// zero padding behind the last real block decodes as garbage) sent to the spare block at cf + 64 * total_blocks.
+template <bool WRITE>
+JPG_HD SpanResult decode_span(const uint32_t* __restrict__ words, int nwords, const ScanTables& T, const int* td, const int* ta,
+                             const uint8_t* __restrict__ natural, SpanState start, uint32_t limit_bit, int16_t* __restrict__ cf,
+                             int blk0, const int* pred_in, int total_blocks) {
+    const HuffTable* const tab0 = &T.dc[0];
+    const uint32_t dpack = (uint32_t)td[0] | ((uint32_t)td[1] << 8) | ((uint32_t)td[2] << 16);
+    const uint32_t apack = (uint32_t)(2 + ta[0]) | ((uint32_t)(2 + ta[1]) << 8) | ((uint32_t)(2 + ta[2]) << 16);
+    uint32_t p = start.p;
+    int b = (int)start.b, kpos = (int)start.k;
+    int comp = b < 4 ? 0 : b - 3;
+    int dsel = (int)((dpack >> (8 * comp)) & 255u), asel = (int)((apack >> (8 * comp)) & 255u);
+    SpanResult R;
+    R.n_blocks = 0;
+    R.dc[0] = R.dc[1] = R.dc[2] = 0;
+    int pred0 = WRITE ? pred_in[0] : 0, pred1 = WRITE ? pred_in[1] : 0, pred2 = WRITE ? pred_in[2] : 0;
+    int blk = blk0;
+    const int last = nwords - 1;
+    auto be = [](uint32_t w) { return (w >> 24) | ((w >> 8) & 0xff00u) | ((w << 8) & 0xff0000u) | (w << 24); };
+    // bit buffer positioned at p: the top `bits` bits of buf are the stream from p on
+    int wi = (int)(p >> 5);
+    const int r0 = (int)(p & 31u);
+    uint64_t buf = (((uint64_t)be(words[wi < last ? wi : last]) << 32) | (uint64_t)be(words[wi + 1 < last ? wi + 1 : last])) << r0;
+    int bits = 64 - r0;
+    wi += 2;
+    uint32_t nextw = words[wi < last ? wi : last];
+    while (p < limit_bit) {
+        const int nb = b == 5 ? 0 : b + 1;
+        const int ncomp = nb < 4 ? 0 : nb - 3;
+        const int ndsel = (int)((dpack >> (8 * ncomp)) & 255u);
+        const int nasel = (int)((apack >> (8 * ncomp)) & 255u);
+        const uint32_t nm = bits <= 32 ? 0xffffffffu : 0u;
+        buf |= ((uint64_t)(be(nextw) & nm) << ((32 - bits) & 63));
+        bits += (int)(32u & nm);
+        wi += (int)(1u & nm);
+        const uint32_t fetched = words[wi < last ? wi : last];
+        nextw = (fetched & nm) | (nextw & ~nm);
+        const uint32_t win = (uint32_t)(buf >> 32);
+        const uint32_t pk = win >> 16;
+        const bool is_dc = kpos == 0;
+        const HuffTable* tab = tab0 + (is_dc ? dsel : asel);
+        const uint32_t e = tab->look[pk >> (16 - kLookBits)];
+        int len = (int)(e >> 8), sym = (int)(e & 255u);
+        if (e == 0) {
+            len = kLookBits + 1;
+#pragma unroll
+            for (int L = kLookBits + 1; L < 16; ++L) len += pk >= tab->limit[L] ? 1 : 0;
+            sym = tab->huffval[((int)(pk >> (16 - len)) + tab->valoffset[len]) & 255];
+        }
+        const int dm = is_dc ? -1 : 0;
+        const int size = ((sym > 15 ? 15 : sym) & dm) | ((sym & 15) & ~dm);
+        const int run = (sym >> 4) & ~dm;
+        const int v = (int)(((win << len) >> 1) >> (31 - size));
+        buf <<= len + size;
+        bits -= len + size;
+        p += (uint32_t)(len + size);
+        const int neg = v < ((1 << size) >> 1) ? -1 : 0;
+        const int val = v + ((1 - (1 << size)) & neg);
+        const int c0 = comp == 0 ? -1 : 0, c1 = comp == 1 ? -1 : 0, c2 = comp == 2 ? -1 : 0;
+        R.dc[0] += val & dm & c0;
+        R.dc[1] += val & dm & c1;
+        R.dc[2] += val & dm & c2;
+        const int kk = kpos + run;
+        if (WRITE) {
+            pred0 += val & dm & c0;
+            pred1 += val & dm & c1;
+            pred2 += val & dm & c2;
+            const int pred = (pred0 & c0) | (pred1 & c1) | (pred2 & c2);
+            const int cm = ((is_dc || (size != 0 && kk < 64)) && blk < total_blocks) ? -1 : 0;
+            const int where = (int)natural[kk & 63] & ~dm;
+            cf[((blk * 64 + where) & cm) | ((total_blocks * 64) & ~cm)] = (int16_t)((pred & dm) | (val & ~dm));
+        }
+        const int zm = size != 0 ? -1 : 0;
+        const int k_ac = ((kk + 1) & zm) | ((run == 15 ? kpos + 16 : 64) & ~zm);
+        kpos = (1 & dm) | (k_ac & ~dm);
+        const int em = kpos >= 64 ? -1 : 0;
+        R.n_blocks -= em;
+        kpos &= ~em;
+        blk -= em;
+        b = (nb & em) | (b & ~em);
+        comp = (ncomp & em) | (comp & ~em);
+        dsel = (ndsel & em) | (dsel & ~em);
+        asel = (nasel & em) | (asel & ~em);
+    }
+    R.end.p = p;
+    R.end.b = (uint16_t)b;
+    R.end.k = (uint16_t)kpos;
+    return R;
+}
+
+// Sub-sequence length for a scan of `nwords` words and `total_blocks` blocks decoded by at most `max_threads` threads: a multiple
+// of 32 bits, >= 512, and long enough to hold ~32 blocks -- states fall into step at block boundaries, and with only a few
+// boundaries per sub-sequence (large blocks: noisy content at high quality) the fixed point took 100+ rounds instead of 3-8.
+JPG_HD uint32_t span_bits_for(int nwords, int total_blocks, int max_threads) {
+    const uint32_t nbits = (uint32_t)nwords * 32u;
+    uint32_t s = (nbits + (uint32_t)max_threads - 1u) / (uint32_t)max_threads;
+    const uint32_t per_block = nbits / (uint32_t)(total_blocks > 0 ? total_blocks : 1);
+    if (s < 32u * per_block) s = 32u * per_block;
+    s = (s + 31u) & ~31u;
+    return s < 512u ? 512u : s;
+}
+
+#if !defined(__CUDACC__)
+// Host statement of the parallel scheme (the kernel in esd_decode.cu runs the same decode_span with a thread per sub-sequence):
+// returns the number of rounds the fixed point took.  Output as decode_scan_flat's.
+inline int decode_scan_parallel_host(const uint32_t* words, int nwords, const ScanTables& T, const int* td, const int* ta,
+                                     const uint8_t* natural, int n_mcus, int16_t* cf, int max_threads) {
+    const uint32_t S = span_bits_for(nwords, 6 * n_mcus, max_threads), nbits = (uint32_t)nwords * 32u;
+    const int nt = (int)((nbits + S - 1) / S);
+    const int total_blocks = 6 * n_mcus;
+    SpanState* in = new SpanState[nt];
+    SpanResult* res = new SpanResult[nt];
+    auto limit = [&](int t) { const uint64_t e = (uint64_t)(t + 1) * S; return (uint32_t)(e < nbits ? e : nbits); };
+    for (int t = 0; t < nt; ++t) {
+        in[t] = SpanState{(uint32_t)t * S, 0, 0};
+        res[t] = decode_span<false>(words, nwords, T, td, ta, natural, in[t], limit(t), nullptr, 0, nullptr, total_blocks);
+    }
+    int rounds = 1;
+    for (;; ++rounds) {
+        bool any = false;
+        SpanState* nin = new SpanState[nt];
+        for (int t = 0; t < nt; ++t) nin[t] = t == 0 ? in[0] : res[t - 1].end;   // Jacobi: everybody reads the previous round
+        for (int t = 1; t < nt; ++t)
+            if (!same_state(nin[t], in[t])) {
+                in[t] = nin[t];
+                res[t] = decode_span<false>(words, nwords, T, td, ta, natural, in[t], limit(t), nullptr, 0, nullptr, total_blocks);
+                any = true;
+            }
+        delete[] nin;
+        if (!any) break;
+    }
+    int blk = 0, pred[3] = {0, 0, 0};
+    for (int t = 0; t < nt; ++t) {
+        decode_span<true>(words, nwords, T, td, ta, natural, in[t], limit(t), cf, blk, pred, total_blocks);
+        blk += res[t].n_blocks;
+        for (int c = 0; c < 3; ++c) pred[c] += res[t].dc[c];
+    }
+    delete[] in;
+    delete[] res;
+    return rounds;
+}
+#endif
+
 // Where block `s` of the scan (decoding order) lies: component and block coordinates inside that component's plane.
 JPG_HD void block_position(int s, int mcus_x, int* comp, int* bx, int* by) {
     const int mcu = s / 6, b = s - 6 * mcu;

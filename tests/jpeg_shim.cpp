@@ -6,7 +6,9 @@
 
 using namespace esdjpeg;
 
+static int g_last_rounds = 0;
 extern "C" {
+int shim_last_rounds() { return g_last_rounds; }
 // returns 0 and fills width / height, or -1 (message in err, 256 bytes)
 int shim_jpeg_info(const uint8_t* data, long n, int* width, int* height, char* err) {
     JpegHeader h;
@@ -31,6 +33,13 @@ int shim_jpeg_decode(const uint8_t* data, long n, uint8_t* out, char* err, int f
         if (!clean || g.restart_interval) { strncpy(err, "restart markers: not for the flat decoder", 255); return -2; }
         const size_t nblocks = (size_t)6 * g.mcus_x * g.mcus_y;
         std::vector<int16_t> coef((nblocks + 1) * 64, 0);  // + the spare block
+        if (flat >= 2) {   // the many-threads-per-picture scheme (host statement), flat = the thread budget; coefficients must equal the flat loop's
+            g_last_rounds = decode_scan_parallel_host(clean_words.data(), (int)clean_words.size(), h.huff, h.td, h.ta, kNaturalOrderHost,
+                                                      g.mcus_x * g.mcus_y, coef.data(), flat);
+            std::vector<int16_t> ref((nblocks + 1) * 64, 0);
+            decode_scan_flat(clean_words.data(), (int)clean_words.size(), h.huff, h.td, h.ta, kNaturalOrderHost, g.mcus_x * g.mcus_y, ref.data());
+            if (memcmp(ref.data(), coef.data(), nblocks * 64 * sizeof(int16_t)) != 0) { strncpy(err, "parallel decode differs from the flat loop", 255); return -3; }
+        } else
         decode_scan_flat(clean_words.data(), (int)clean_words.size(), h.huff, h.td, h.ta, kNaturalOrderHost, g.mcus_x * g.mcus_y, coef.data());
         for (size_t b = 0; b < nblocks; ++b) {  // coefficients are in decoding order: block_position maps them into the planes
             int comp, bx, by;

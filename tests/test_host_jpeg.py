@@ -70,6 +70,29 @@ def test_decoder_arithmetic_is_bit_exact_with_cv2_imdecode(shim, quality):
                 assert flat is not None and np.array_equal(flat, want), (name, quality, extra, "flat")
 
 
+@pytest.mark.parametrize("quality", [100, 90, 60, 20])
+def test_many_threads_per_picture_reach_the_sequential_decoding(shim, quality):
+    """The self-synchronising scheme (jpeg_core.h: decode_span / decode_scan_parallel_host, what the GPU runs with a thread per
+    sub-sequence): speculative starts, rounds until no start state changes, prefix sums, one writing pass.  The shim compares the
+    coefficients with the flat loop's and the picture with cv2.imdecode; thread budgets from 2 to 1024 change the sub-sequence
+    length (>= 512 bits), never the result."""
+    shim.shim_last_rounds.restype = C.c_int
+    rng = np.random.default_rng(quality)
+    big = cv2.resize(rng.integers(0, 256, (27, 48, 3), dtype=np.uint8), (1920, 1080), interpolation=cv2.INTER_CUBIC)
+    big = np.clip(big.astype(int) + rng.integers(-6, 7, big.shape), 0, 255).astype(np.uint8)
+    worst = 0
+    for name, img in list(_images()) + [("1080p", big)]:
+        for extra in ([], [cv2.IMWRITE_JPEG_OPTIMIZE, 1]):
+            ok, jpg = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_QUALITY, quality, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420] + extra)
+            want = cv2.imdecode(jpg, cv2.IMREAD_COLOR)
+            for budget in ((2, 7, 64, 1024) if name != "1080p" else (1024, 300)):
+                got = decode(shim, jpg.tobytes(), flat=budget)
+                assert got is not None and np.array_equal(got, want), (name, quality, extra, budget)
+                worst = max(worst, shim.shim_last_rounds())
+    # correct states spread at least one sub-sequence per round; in practice a handful of rounds, far below the thread count
+    assert 1 <= worst <= 24, worst
+
+
 def test_mjpeg_avi_pictures_written_by_cv2_decode_bit_exactly(shim, tmp_path):
     """The pictures ffmpeg's mjpeg encoder puts into an AVI (what cv2.VideoWriter('MJPG') produces and bench.py feeds)."""
     import struct
