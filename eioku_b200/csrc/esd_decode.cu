@@ -18,6 +18,7 @@
 #include <algorithm>
 #include <map>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -76,6 +77,7 @@ struct esd_mjpeg {
     // ESD_DEC_ENTROPY=flat keeps the thread-per-picture loop for pictures without restart markers (A/B switch); the default decodes
     // each picture with a block of threads
     bool parallel_entropy = !(getenv("ESD_DEC_ENTROPY") && strcmp(getenv("ESD_DEC_ENTROPY"), "flat") == 0);
+    int stage_threads = getenv("ESD_DEC_STAGE_THREADS") ? std::max(1, atoi(getenv("ESD_DEC_STAGE_THREADS"))) : 4;   // host threads staging a batch
     bool flat = false;                           // no restart interval: the host removes the byte stuffing and the flat scan decoder runs
     size_t plane_bytes = 0;                      // Y + Cb + Cr sample planes of one frame (MCU-padded)
     // Two decode lanes: batch k runs on lane k & 1 (a stream of the library's own, with its own staging mirror, coefficient and
@@ -178,7 +180,7 @@ nvjpegBackend_t nj_backend(int b) {
 //                        written by ffmpeg / OpenCV carry no restart markers, so the parallelism is across the pictures of the
 //                        batch and across decoder sessions) and scatters the non-zero coefficients into a zeroed buffer;
 //   jpeg_idct_kernel     one thread per 8x8 block: dequantise + libjpeg's ISLOW IDCT -> MCU-padded Y / Cb / Cr planes;
-//   jpeg_color_kernel    one thread per four pixels: fancy h2v2 chroma upsampling + JFIF YCbCr -> BGR24, written in the
+//   jpeg_color_kernel    one thread per four pixels of two rows: fancy h2v2 chroma upsampling + JFIF YCbCr -> BGR24, written in the
 //                        dense layout esd_push_frames reads.
 namespace {
 __constant__ uint8_t c_natural_order[64] = ESD_JPEG_NATURAL_ORDER;
@@ -376,32 +378,64 @@ __global__ void __launch_bounds__(128) jpeg_idct_kernel(NativeLayout L, const in
     for (int r = 0; r < 8; ++r) *reinterpret_cast<uint2*>(out + (size_t)r * stride) = o.v[r];
 }
 
+// Four pixels of TWO picture rows (2r, 2r + 1) per thread: the rows share their chroma row cy = r, so the column sums of the
+// fancy h2v2 upsampling (3 * C[cy][j] + C[neighbour row][j], jdsample.c) are formed once per chroma column -- four columns
+// (j = i-1 .. i+2) serve the eight pixels; the first version recomputed two of them for every pixel and channel (1.66 ms of the
+// 3.6 ms a 256-picture batch spent behind the entropy stage).  Arithmetic and results are fancy_chroma's / ycc_to_bgr's.
 __global__ void __launch_bounds__(256) jpeg_color_kernel(NativeLayout L, const uint8_t* __restrict__ planes, uint8_t* __restrict__ bgr) {
     const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const int y = blockIdx.y, f = blockIdx.z;
-    if (x4 >= L.width) return;
-    const int yw = 2 * L.mcus_x * 8, cw = L.mcus_x * 8;
+    const int r = blockIdx.y, f = blockIdx.z;
+    const int y0 = 2 * r;
+    if (x4 >= L.width || y0 >= L.height) return;
+    const int yw = 2 * L.mcus_x * 8, cw = L.mcus_x * 8;   // padded strides
     const size_t ysz = (size_t)yw * (L.mcus_y * 16), csz = (size_t)cw * (L.mcus_y * 8);
     const uint8_t* Y = planes + (size_t)f * L.plane_bytes;
-    const uint8_t* Cb = Y + ysz;
-    const uint8_t* Cr = Cb + csz;
-    const int rcw = (L.width + 1) >> 1, rch = (L.height + 1) >> 1;
-    const uint32_t yy = *reinterpret_cast<const uint32_t*>(Y + (size_t)y * yw + x4);  // yw is a multiple of 16, x4 of 4
-    uint8_t px[12];
+    const int rcw = (L.width + 1) >> 1, rch = (L.height + 1) >> 1;   // real chroma size
+    const int cy = r;
+    const int nb0 = cy > 0 ? cy - 1 : 0;                 // neighbour chroma row of the even picture row / of the odd one
+    const int nb1 = cy + 1 < rch ? cy + 1 : rch - 1;
+    const int i = x4 >> 1;                               // even: (i, i + 1) is one aligned 16-bit load
+    const int jm = i > 0 ? i - 1 : 0, j2 = i + 2 < cw ? i + 2 : cw - 1;
+    int up[2][2][4];                                     // [channel][picture row parity][pixel]: upsampled chroma
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int x = min(x4 + k, L.width - 1);
-        esdjpeg::ycc_to_bgr((int)((yy >> (8 * k)) & 255u), esdjpeg::fancy_chroma(Cb, cw, rcw, rch, x, y),
-                            esdjpeg::fancy_chroma(Cr, cw, rcw, rch, x, y), px + 3 * k);
+    for (int c = 0; c < 2; ++c) {
+        const uint8_t* C = Y + ysz + (size_t)c * csz;
+        const uint8_t* rc = C + (size_t)cy * cw;
+        const uint8_t* ra = C + (size_t)nb0 * cw;
+        const uint8_t* rb = C + (size_t)nb1 * cw;
+        const uint32_t mc = *reinterpret_cast<const uint16_t*>(rc + i), ma = *reinterpret_cast<const uint16_t*>(ra + i),
+                       mb = *reinterpret_cast<const uint16_t*>(rb + i);
+        const int c3[4] = {3 * (int)rc[jm], 3 * (int)(mc & 255u), 3 * (int)(mc >> 8), 3 * (int)rc[j2]};
+        const int na[4] = {(int)ra[jm], (int)(ma & 255u), (int)(ma >> 8), (int)ra[j2]};
+        const int nb[4] = {(int)rb[jm], (int)(mb & 255u), (int)(mb >> 8), (int)rb[j2]};
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int* nn = q ? nb : na;
+            const int s0 = c3[0] + nn[0], s1 = c3[1] + nn[1], s2 = c3[2] + nn[2], s3 = c3[3] + nn[3];   // columns i-1, i, i+1, i+2
+            up[c][q][0] = i == 0 ? (s1 * 4 + 8) >> 4 : (s1 * 3 + s0 + 8) >> 4;
+            up[c][q][1] = i == rcw - 1 ? (s1 * 4 + 7) >> 4 : (s1 * 3 + s2 + 7) >> 4;
+            up[c][q][2] = (s2 * 3 + s1 + 8) >> 4;
+            up[c][q][3] = i + 1 == rcw - 1 ? (s2 * 4 + 7) >> 4 : (s2 * 3 + s3 + 7) >> 4;
+        }
     }
-    uint8_t* o = bgr + ((size_t)f * L.height + y) * (size_t)L.width * 3 + (size_t)x4 * 3;
-    if (x4 + 4 <= L.width && ((L.width * 3) & 3) == 0) {  // 12 bytes on a 4-byte boundary
-        uint32_t* ow = reinterpret_cast<uint32_t*>(o);
-        ow[0] = px[0] | (px[1] << 8) | (px[2] << 16) | ((uint32_t)px[3] << 24);
-        ow[1] = px[4] | (px[5] << 8) | (px[6] << 16) | ((uint32_t)px[7] << 24);
-        ow[2] = px[8] | (px[9] << 8) | (px[10] << 16) | ((uint32_t)px[11] << 24);
-    } else {
-        for (int k = 0; k < 4 && x4 + k < L.width; ++k) { o[3 * k] = px[3 * k]; o[3 * k + 1] = px[3 * k + 1]; o[3 * k + 2] = px[3 * k + 2]; }
+    const bool words = x4 + 4 <= L.width && ((L.width * 3) & 3) == 0;   // 12 bytes on a 4-byte boundary
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int y = y0 + q;
+        if (y >= L.height) break;
+        const uint32_t yy = *reinterpret_cast<const uint32_t*>(Y + (size_t)y * yw + x4);  // yw is a multiple of 16, x4 of 4
+        uint8_t px[12];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) esdjpeg::ycc_to_bgr((int)((yy >> (8 * k)) & 255u), up[0][q][k], up[1][q][k], px + 3 * k);
+        uint8_t* o = bgr + ((size_t)f * L.height + y) * (size_t)L.width * 3 + (size_t)x4 * 3;
+        if (words) {
+            uint32_t* ow = reinterpret_cast<uint32_t*>(o);
+            ow[0] = px[0] | (px[1] << 8) | (px[2] << 16) | ((uint32_t)px[3] << 24);
+            ow[1] = px[4] | (px[5] << 8) | (px[6] << 16) | ((uint32_t)px[7] << 24);
+            ow[2] = px[8] | (px[9] << 8) | (px[10] << 16) | ((uint32_t)px[11] << 24);
+        } else {
+            for (int k = 0; k < 4 && x4 + k < L.width; ++k) { o[3 * k] = px[3 * k]; o[3 * k + 1] = px[3 * k + 1]; o[3 * k + 2] = px[3 * k + 2]; }
+        }
     }
 }
 
@@ -646,51 +680,83 @@ int esd_mjpeg_read(esd_mjpeg* h, int64_t max_frames, void* stream, uint8_t** d_b
     size_t off = meta;
     esd_mjpeg::NativeDesc* hdesc = reinterpret_cast<esd_mjpeg::NativeDesc*>(h->h_stage[b]);
     uint16_t* hquant = reinterpret_cast<uint16_t*>(h->h_stage[b] + (size_t)n * sizeof(esd_mjpeg::NativeDesc));
+    // where each picture is staged (64-byte aligned): known from the sizes, so the pictures can be staged in parallel
+    std::vector<size_t> offs((size_t)n);
     for (int64_t i = 0; i < n; ++i) {
+        offs[(size_t)i] = off;
+        off += ((size_t)h->pics[h->pos + i].size + 16 + 63) & ~(size_t)63;
+    }
+    // stage_one: 0 or an error code, message in *msg.  Touches only picture i's slots of the staging block.
+    auto stage_one = [&](int64_t i, std::string* msg) -> int {
         const Picture& p = h->pics[h->pos + i];
-        if (p.offset + p.size > h->map_bytes) return fail(h, ESD_DEC_ERR_FORMAT, "picture %lld lies outside the file", (long long)(h->pos + i));
-        if (!native) memcpy(h->h_stage[b] + off, h->map + p.offset, p.size);
-        if (native) {
-            // header walk on the host (a few markers); the Huffman tables are built on the device from the picture's own DHT
-            esdjpeg::JpegHeader jh;
-            std::string why;
-            const uint8_t* pic = h->map + p.offset;
-            if (!esdjpeg::parse_jpeg(pic, p.size, &jh, &why, false))
-                return fail(h, ESD_DEC_ERR_UNSUPPORTED, "picture %lld: %s", (long long)(h->pos + i), why.c_str());
-            if (h->flat) {
-                // staged: [headers up to the scan][scan with the byte stuffing removed, on a 4-byte boundary, zero padded]
-                memcpy(h->h_stage[b] + off, pic, jh.scan_offset);
-                const size_t so = (jh.scan_offset + 3) & ~(size_t)3;
-                bool clean = true;
-                const size_t nb = esdjpeg::unstuff_scan(pic + jh.scan_offset, jh.scan_len, h->h_stage[b] + off + so, &clean);
-                if (!clean) return fail(h, ESD_DEC_ERR_UNSUPPORTED, "picture %lld carries restart markers without a restart interval", (long long)(h->pos + i));
-                const size_t padded = (nb + 3 + 8) & ~(size_t)3;  // two zero words behind the data
-                memset(h->h_stage[b] + off + so + nb, 0, padded - nb);
-                jh.scan_offset = so;
-                jh.scan_len = padded / 4;  // words
-            } else {
-                memcpy(h->h_stage[b] + off, pic, p.size);
-            }
-            bool same = jh.width == h->width && jh.height == h->height && jh.restart_interval == h->geo.restart_interval;
-            for (int c = 0; c < 3; ++c) same = same && jh.td[c] == h->td[c] && jh.ta[c] == h->ta[c];
-            if (!same) return fail(h, ESD_DEC_ERR_UNSUPPORTED, "picture %lld changes the stream's geometry / table selectors", (long long)(h->pos + i));
-            hdesc[i].off = (uint32_t)(off + jh.scan_offset);
-            hdesc[i].len = (uint32_t)jh.scan_len;
-            for (int t = 0; t < 4; ++t) {  // DC0, DC1, AC0, AC1: where the picture's own tables start (built on the device)
-                const int tc = t >> 1, id = t & 1;
-                const bool have = tc ? jh.have_ac[id] : jh.have_dc[id];
-                hdesc[i].dht[t] = have ? (uint32_t)(off + jh.dht_pos[tc][id]) : 0u;
-                hdesc[i].nvals[t] = (uint16_t)(have ? jh.dht_nvals[tc][id] : 0);
-            }
-            for (int c = 0; c < 3; ++c) memcpy(hquant + ((size_t)i * 3 + c) * 64, jh.quant[jh.tq[c]], 64 * sizeof(uint16_t));
-        } else {
+        const size_t off = offs[(size_t)i];
+        char buf[160];
+        if (p.offset + p.size > h->map_bytes) { snprintf(buf, sizeof buf, "picture %lld lies outside the file", (long long)(h->pos + i)); *msg = buf; return ESD_DEC_ERR_FORMAT; }
+        if (!native) {
+            memcpy(h->h_stage[b] + off, h->map + p.offset, p.size);
             h->ptrs[i] = h->h_stage[b] + off;
             h->lens[i] = p.size;
             memset(&h->imgs[i], 0, sizeof(nvjpegImage_t));
             h->imgs[i].channel[0] = h->d_out[b] + (size_t)i * frame_bytes;
             h->imgs[i].pitch[0] = (size_t)h->width * 3;
+            return 0;
         }
-        off += ((size_t)p.size + 16 + 63) & ~(size_t)63;
+        // header walk on the host (a few markers); the Huffman tables are built on the device from the picture's own DHT
+        esdjpeg::JpegHeader jh;
+        std::string why;
+        const uint8_t* pic = h->map + p.offset;
+        if (!esdjpeg::parse_jpeg(pic, p.size, &jh, &why, false)) { snprintf(buf, sizeof buf, "picture %lld: %s", (long long)(h->pos + i), why.c_str()); *msg = buf; return ESD_DEC_ERR_UNSUPPORTED; }
+        if (h->flat) {
+            // staged: [headers up to the scan][scan with the byte stuffing removed, on a 4-byte boundary, zero padded]
+            memcpy(h->h_stage[b] + off, pic, jh.scan_offset);
+            const size_t so = (jh.scan_offset + 3) & ~(size_t)3;
+            bool clean = true;
+            const size_t nb = esdjpeg::unstuff_scan(pic + jh.scan_offset, jh.scan_len, h->h_stage[b] + off + so, &clean);
+            if (!clean) { snprintf(buf, sizeof buf, "picture %lld carries restart markers without a restart interval", (long long)(h->pos + i)); *msg = buf; return ESD_DEC_ERR_UNSUPPORTED; }
+            const size_t padded = (nb + 3 + 8) & ~(size_t)3;  // two zero words behind the data
+            memset(h->h_stage[b] + off + so + nb, 0, padded - nb);
+            jh.scan_offset = so;
+            jh.scan_len = padded / 4;  // words
+        } else {
+            memcpy(h->h_stage[b] + off, pic, p.size);
+        }
+        bool same = jh.width == h->width && jh.height == h->height && jh.restart_interval == h->geo.restart_interval;
+        for (int c = 0; c < 3; ++c) same = same && jh.td[c] == h->td[c] && jh.ta[c] == h->ta[c];
+        if (!same) { snprintf(buf, sizeof buf, "picture %lld changes the stream's geometry / table selectors", (long long)(h->pos + i)); *msg = buf; return ESD_DEC_ERR_UNSUPPORTED; }
+        hdesc[i].off = (uint32_t)(off + jh.scan_offset);
+        hdesc[i].len = (uint32_t)jh.scan_len;
+        for (int t = 0; t < 4; ++t) {  // DC0, DC1, AC0, AC1: where the picture's own tables start (built on the device)
+            const int tc = t >> 1, id = t & 1;
+            const bool have = tc ? jh.have_ac[id] : jh.have_dc[id];
+            hdesc[i].dht[t] = have ? (uint32_t)(off + jh.dht_pos[tc][id]) : 0u;
+            hdesc[i].nvals[t] = (uint16_t)(have ? jh.dht_nvals[tc][id] : 0);
+        }
+        for (int c = 0; c < 3; ++c) memcpy(hquant + ((size_t)i * 3 + c) * 64, jh.quant[jh.tq[c]], 64 * sizeof(uint16_t));
+        return 0;
+    };
+    {
+        // The GPU decodes a 1080p picture in ~15 us; one host thread stages one in ~21 us (header walk + copy with the byte
+        // stuffing removed).  Helper threads take every k-th picture so that ONE session keeps the device busy.
+        // (one helper per 64 pictures: spawning threads for a 64-picture batch cost more than it saved -- staging 1.2 -> 5.9 ms)
+        const int helpers = std::max(1, std::min<int>(h->stage_threads, (int)(n / 64)));
+        std::vector<int> rcs((size_t)std::max(1, helpers), 0);
+        std::vector<std::string> msgs((size_t)std::max(1, helpers));
+        auto run = [&](int k, int stride) {
+            for (int64_t i = k; i < n; i += stride) {
+                const int rc = stage_one(i, &msgs[(size_t)k]);
+                if (rc) { rcs[(size_t)k] = rc; return; }
+            }
+        };
+        if (helpers <= 1) {
+            run(0, 1);
+        } else {
+            std::vector<std::thread> th;
+            for (int k = 1; k < helpers; ++k) th.emplace_back(run, k, helpers);
+            run(0, helpers);
+            for (auto& t : th) t.join();
+        }
+        for (size_t k = 0; k < rcs.size(); ++k)
+            if (rcs[k]) return fail(h, rcs[k], "%s", msgs[k].c_str());
     }
     if (native) {
         if (total > h->d_comp_bytes[ln]) {  // device mirror of the staging block (grow-only; everything that used it ran on `ds` before)
@@ -736,7 +802,7 @@ int esd_mjpeg_read(esd_mjpeg* h, int64_t max_frames, void* stream, uint8_t** d_b
         else jpeg_entropy_kernel<<<egrid, kEntropyThreads, esmem, ds>>>(L, h->d_comp[ln], ddesc, h->d_coef[ln]);
         if (h->timing) cudaEventRecord(h->tev[b][2], ds);
         jpeg_idct_kernel<<<dim3((unsigned)((h->blocks_per_frame + 127) / 128), (unsigned)n), 128, 0, ds>>>(L, h->d_coef[ln], dquant, h->d_planes[ln]);
-        jpeg_color_kernel<<<dim3((unsigned)(((h->width + 3) / 4 + 255) / 256), (unsigned)h->height, (unsigned)n), 256, 0, ds>>>(L, h->d_planes[ln], h->d_out[b]);
+        jpeg_color_kernel<<<dim3((unsigned)(((h->width + 3) / 4 + 255) / 256), (unsigned)((h->height + 1) / 2), (unsigned)n), 256, 0, ds>>>(L, h->d_planes[ln], h->d_out[b]);
         if (h->timing) { cudaEventRecord(h->tev[b][3], ds); h->tev_armed[b] = true; }
         e = cudaGetLastError();
         if (e != cudaSuccess) return fail(h, ESD_DEC_ERR_CUDA, "native decode kernels: %s", cudaGetErrorString(e));
