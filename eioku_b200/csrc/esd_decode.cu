@@ -95,6 +95,7 @@ struct esd_mjpeg {
     NativeDesc* d_desc = nullptr;                // [batch]
     uint16_t* d_quant = nullptr;                 // [batch][3][64] natural order, per component
     int16_t* d_coef[2] = {nullptr, nullptr};     // [batch][blocks_per_frame][64], per lane
+    bool coef_dirty[2] = {true, true};           // needs a full clear before the next batch (first use, or a batch that failed half-way)
     uint8_t* d_planes[2] = {nullptr, nullptr};   // [batch][plane_bytes], per lane
     std::vector<uint8_t> h_meta[2];              // pinned-free host staging of descriptors + quant tables (copied with the batch)
 };
@@ -336,7 +337,11 @@ __global__ void __launch_bounds__(kParThreads) jpeg_entropy_parallel_kernel(Nati
     esdjpeg::decode_span<true>(words, nwords, T, td, ta, s_nat, in, limit, coef + (size_t)f * L.blocks_per_frame * 64, blk0, pred, total_blocks);
 }
 
-__global__ void __launch_bounds__(128) jpeg_idct_kernel(NativeLayout L, const int16_t* __restrict__ coef, const uint16_t* __restrict__ quant,
+// The kernel also RESTORES THE ZEROS: the entropy stage writes only non-zero coefficients into a buffer that must be clear, and
+// clearing 6.3 MB per 1080p picture ahead of every batch was a fifth of the batch's time.  Each thread zeroes the 16-byte pieces of
+// its block that held anything (typically 1-3 of 8), so the buffer is clean again when the kernel ends and only ~a third of it is
+// ever written back.
+__global__ void __launch_bounds__(128) jpeg_idct_kernel(NativeLayout L, int16_t* __restrict__ coef, const uint16_t* __restrict__ quant,
                                                         uint8_t* __restrict__ planes) {
     const int blk = blockIdx.x * blockDim.x + threadIdx.x;
     const int f = blockIdx.y;
@@ -348,7 +353,7 @@ __global__ void __launch_bounds__(128) jpeg_idct_kernel(NativeLayout L, const in
     const size_t ysz = (size_t)(2 * L.mcus_x * 8) * (L.mcus_y * 16), csz = (size_t)(L.mcus_x * 8) * (L.mcus_y * 8);
     uint8_t* plane = planes + (size_t)f * L.plane_bytes + (comp == 0 ? 0 : (comp == 1 ? ysz : ysz + csz));
     uint8_t* out = plane + (size_t)(by * 8) * stride + bx * 8;
-    const uint4* src = reinterpret_cast<const uint4*>(coef + ((size_t)f * L.blocks_per_frame + blk) * 64);
+    uint4* src = reinterpret_cast<uint4*>(coef + ((size_t)f * L.blocks_per_frame + blk) * 64);
     union { uint4 v[8]; int16_t c[64]; } u;
     uint32_t ac = 0;
 #pragma unroll
@@ -356,6 +361,9 @@ __global__ void __launch_bounds__(128) jpeg_idct_kernel(NativeLayout L, const in
         u.v[i] = src[i];
         ac |= u.v[i].y | u.v[i].z | u.v[i].w | (i ? u.v[i].x : (u.v[i].x & 0xffff0000u));
     }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        if (u.v[i].x | u.v[i].y | u.v[i].z | u.v[i].w) src[i] = make_uint4(0u, 0u, 0u, 0u);
     const uint16_t* q = quant + ((size_t)f * 3 + comp) * 64;
     if (ac == 0) {
         // DC only: both passes of the ISLOW IDCT reduce to (4 * dc * q0 + 16) >> 5 for every sample (same rounding)
@@ -790,7 +798,9 @@ int esd_mjpeg_read(esd_mjpeg* h, int64_t max_frames, void* stream, uint8_t** d_b
             cudaEventRecord(h->tev[b][0], ds);
         }
         cudaError_t e = cudaMemcpyAsync(h->d_comp[ln], h->h_stage[b], total, cudaMemcpyHostToDevice, ds);
-        if (e == cudaSuccess) e = cudaMemsetAsync(h->d_coef[ln], 0, (size_t)n * h->blocks_per_frame * 64 * sizeof(int16_t), ds);
+        // the coefficient scratch is cleared once; after that the IDCT kernel leaves it clean (a batch that failed half-way clears again)
+        if (e == cudaSuccess && h->coef_dirty[ln]) e = cudaMemsetAsync(h->d_coef[ln], 0, (size_t)h->batch * h->blocks_per_frame * 64 * sizeof(int16_t), ds);
+        h->coef_dirty[ln] = true;
         if (e != cudaSuccess) return fail(h, ESD_DEC_ERR_CUDA, "native decode: staging copy failed: %s", cudaGetErrorString(e));
         const esd_mjpeg::NativeDesc* ddesc = reinterpret_cast<const esd_mjpeg::NativeDesc*>(h->d_comp[ln]);
         const uint16_t* dquant = reinterpret_cast<const uint16_t*>(h->d_comp[ln] + (size_t)n * sizeof(esd_mjpeg::NativeDesc));
@@ -806,6 +816,7 @@ int esd_mjpeg_read(esd_mjpeg* h, int64_t max_frames, void* stream, uint8_t** d_b
         if (h->timing) { cudaEventRecord(h->tev[b][3], ds); h->tev_armed[b] = true; }
         e = cudaGetLastError();
         if (e != cudaSuccess) return fail(h, ESD_DEC_ERR_CUDA, "native decode kernels: %s", cudaGetErrorString(e));
+        h->coef_dirty[ln] = false;   // entropy + IDCT are enqueued: the IDCT restores the zeros
     } else {
         if (h->initialized_batch != (int)n) {  // the batched API wants exactly the initialised number of pictures (tail of the stream)
             nvjpegStatus_t js = nvjpegDecodeBatchedInitialize(h->nj, h->state, (int)n, 1, NVJPEG_OUTPUT_BGRI);
