@@ -795,7 +795,7 @@ def main():
     ap.add_argument("--e2e-ring", default="", help="ingest ring of the e2e leg as SLOTSxFRAMES (default 4x128 with gather, 3x256 DMA)")
     ap.add_argument("--no-compressed", action="store_true", help="skip the compressed-file end-to-end leg")
     ap.add_argument("--compressed-frames", type=int, default=1024, help="length of the Motion-JPEG file (four decode batches per pass: the decoder keeps two batches in flight per session)")
-    ap.add_argument("--compressed-passes", type=int, default=6)
+    ap.add_argument("--compressed-passes", type=int, default=20, help="passes over the file per session inside the timed region (~1 s at 80 k frames/s)")
     ap.add_argument("--compressed-cpu-passes", type=int, default=2)
     ap.add_argument("--decode-sessions", type=int, default=0, help="GPU decoder sessions per rank (0 = up to 4, fewer when the ranks share few cores)")
     ap.add_argument("--decode-batch", type=int, default=64, help="pictures per decode batch and session")
