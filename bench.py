@@ -195,25 +195,32 @@ def bench_reference(args):
     # arm's `e2e_compressed`.  The file is the same Motion-JPEG AVI (frames from the CPU twin of the clip generator).
     comp = None
     if not args.no_compressed:
-        import cv2
+        path = None
+        try:  # this leg must never cost the arm its headline line
+            import cv2
 
-        n = args.compressed_frames
-        shm = "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
-        path = os.path.join(shm, f"esd_bench_mjpeg_ref_{os.getpid()}.avi")
-        wr = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"MJPG"), float(FPS), (W, H))
-        for a in range(0, n, 32):
-            for f in cpu_sample_frames(min(32, n - a), a):
-                wr.write(f)
-        wr.release()
-        try:
+            n = args.compressed_frames
+            shm = "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
+            path = os.path.join(shm, f"esd_bench_mjpeg_ref_{os.getpid()}.avi")
+            wr = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"MJPG"), float(FPS), (W, H))
+            if not wr.isOpened():
+                raise RuntimeError("this OpenCV build cannot write Motion-JPEG")
+            for a in range(0, n, 32):
+                for f in cpu_sample_frames(min(32, n - a), a):
+                    wr.write(f)
+            wr.release()
             with cpu_baseline.Runner(video_path=path, cores=cores) as runner:
                 runner.step(1)
                 r = runner.step(args.compressed_cpu_passes)
             comp = {"value": r["frames_per_s"], "unit": UNIT, "cores": r["cores"], "seconds": r["seconds"], "file_frames": n,
                     "file_bytes": os.path.getsize(path),
                     "what": "cv2.VideoCapture decode + PySceneDetect logic on cv2, one process per core, each decoding and scoring the whole file"}
+        except Exception as e:  # noqa: BLE001
+            sys.stderr.write(f"bench.py: compressed leg of the reference arm skipped ({type(e).__name__}: {e})\n")
+            comp = {"error": f"{type(e).__name__}: {e}"[:300], "unit": UNIT}
         finally:
-            os.remove(path)
+            if path and os.path.exists(path):
+                os.remove(path)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 * dt / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
@@ -416,6 +423,43 @@ def config3_leg(capi, synth, local, rank, world, dist, dev, args):
 
 
 def compressed_leg(local, rank, world, dist, dev, args, barrier, all_max):
+    """The compressed-file leg must never cost the run its headline: any failure in it (no MJPG writer in this OpenCV build, no
+    room in /dev/shm, a decoder error ...) is reported as `{"error": ...}` in `e2e_compressed` instead of killing the process --
+    on every rank alike, because the leg contains collectives: at two points the ranks agree (all-reduce of a failure flag) whether
+    all of them are still in, and leave together if not.  Only a parity mismatch stays fatal (SystemExit)."""
+
+    class _LegFailed(Exception):
+        pass
+
+    state = {"mine": None}
+
+    def agree(where, err=None):
+        if err is not None and state["mine"] is None:
+            state["mine"] = f"{where}: {err}"
+        if all_max(1.0 if state["mine"] is not None else 0.0) > 0.0:
+            raise _LegFailed(state["mine"] or f"{where}: another rank failed")
+
+    try:
+        try:
+            return _compressed_leg_body(local, rank, world, dist, dev, args, barrier, all_max, agree)
+        except _LegFailed:
+            raise
+        except SystemExit:
+            raise
+        except Exception as e:  # noqa: BLE001 - a failure before the first agreement point: tell the others, then leave
+            if state["mine"] is None:
+                state["mine"] = f"{type(e).__name__}: {e}"
+            try:
+                all_max(1.0)
+            except Exception:  # noqa: BLE001
+                pass
+            raise _LegFailed(state["mine"]) from e
+    except _LegFailed as e:
+        sys.stderr.write(f"bench.py: compressed leg skipped ({e})\n")
+        return {"error": str(e)[:300], "unit": UNIT}
+
+
+def _compressed_leg_body(local, rank, world, dist, dev, args, barrier, all_max, agree):
     """End to end from a COMPRESSED file: a 1080p Motion-JPEG AVI of the clip's head in /dev/shm -> nvJPEG on
     the GPU (libesd_decode) -> scoring -> cuts; `sessions` decoder sessions per GPU, each decoding and scoring the whole file
     (the shape of the CPU arm: one process per core, each decoding and scoring the whole file with cv2.VideoCapture + the
@@ -435,6 +479,8 @@ def compressed_leg(local, rank, world, dist, dev, args, barrier, all_max):
     path = os.path.join(shm, f"esd_bench_mjpeg_{os.getpid()}.avi")
     sch = synth.build_schedule(SEED, n)
     wr = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"MJPG"), float(FPS), (W, H))
+    if not wr.isOpened():
+        raise RuntimeError("this OpenCV build cannot write Motion-JPEG")
     for a in range(0, n, 64):
         t = torch.empty((min(64, n - a), H, W, 3), dtype=torch.uint8, device=dev)
         synth.fill(t, SEED, sch.descs[a:a + 64])
@@ -471,6 +517,7 @@ def compressed_leg(local, rank, world, dist, dev, args, barrier, all_max):
         if not bit_exact:
             raise SystemExit("bench.py: PARITY GATE FAILED on the decoded surface")
 
+        agree("set-up")          # every rank has its file, its parity check and the session count: none goes on alone
         frames_done = [0] * sessions
         errs = []
         gate = threading.Barrier(sessions + 1)
@@ -512,8 +559,7 @@ def compressed_leg(local, rank, world, dist, dev, args, barrier, all_max):
             dt = float("nan")
         for t in th:
             t.join()
-        if errs:
-            raise RuntimeError("compressed leg: " + errs[0])
+        agree("timed region", errs[0] if errs else None)
         dt = all_max(dt)
         value = world * sum(frames_done) / dt
         out = {"value": value, "unit": UNIT, "n_gpus": world,

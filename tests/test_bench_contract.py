@@ -74,3 +74,49 @@ def test_gpu_arm_refuses_to_run_on_cpu():
         pytest.skip("GPU present")
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True, timeout=300)
     assert out.returncode != 0 and "no CPU fallback" in (out.stderr + out.stdout)
+
+
+def test_a_failing_compressed_leg_does_not_cost_the_run_its_line(monkeypatch):
+    """bench.compressed_leg: any failure inside the leg comes back as {"error": ...} (so the headline line is still printed), the
+    ranks leave together (the failure flag goes through all_max), and only a parity mismatch -- SystemExit -- stays fatal."""
+    import bench
+
+    calls = []
+
+    def all_max(x):
+        calls.append(x)
+        return x
+
+    def boom(*a, **k):
+        raise RuntimeError("no Motion-JPEG writer here")
+
+    monkeypatch.setattr(bench, "_compressed_leg_body", boom)
+    out = bench.compressed_leg(0, 0, 1, None, "cuda:0", None, lambda: None, all_max)
+    assert "no Motion-JPEG writer here" in out["error"] and calls == [1.0]
+
+    def late(local, rank, world, dist, dev, args, barrier, all_max_, agree):
+        agree("set-up")
+        agree("timed region", "decoder said no")
+        raise AssertionError("not reached")
+
+    calls.clear()
+    monkeypatch.setattr(bench, "_compressed_leg_body", late)
+    out = bench.compressed_leg(0, 0, 1, None, "cuda:0", None, lambda: None, all_max)
+    assert out["error"].startswith("timed region: decoder said no") and calls == [0.0, 1.0]
+
+    def other_rank_failed(local, rank, world, dist, dev, args, barrier, all_max_, agree):
+        agree("set-up")
+        return {"value": 1.0}
+
+    monkeypatch.setattr(bench, "_compressed_leg_body", other_rank_failed)
+    assert "another rank failed" in bench.compressed_leg(0, 0, 2, None, "cuda:0", None, lambda: None, lambda x: 1.0)["error"]
+    assert bench.compressed_leg(0, 0, 1, None, "cuda:0", None, lambda: None, all_max) == {"value": 1.0}
+
+    def gate(*a, **k):
+        raise SystemExit("bench.py: PARITY GATE FAILED on the decoded surface")
+
+    monkeypatch.setattr(bench, "_compressed_leg_body", gate)
+    import pytest as _pytest
+
+    with _pytest.raises(SystemExit):
+        bench.compressed_leg(0, 0, 1, None, "cuda:0", None, lambda: None, all_max)
