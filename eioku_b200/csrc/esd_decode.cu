@@ -95,6 +95,8 @@ struct esd_mjpeg {
     NativeDesc* d_desc = nullptr;                // [batch]
     uint16_t* d_quant = nullptr;                 // [batch][3][64] natural order, per component
     int16_t* d_coef[2] = {nullptr, nullptr};     // [batch][blocks_per_frame][64], per lane
+    uint32_t* d_bstart[2] = {nullptr, nullptr};  // [batch][blocks_per_frame + 1]: sparse hand-off, where each block's entries begin
+    bool sparse_handoff = !(getenv("ESD_DEC_SPARSE") && atoi(getenv("ESD_DEC_SPARSE")) == 0);   // A/B switch
     bool coef_dirty[2] = {true, true};           // needs a full clear before the next batch (first use, or a batch that failed half-way)
     uint8_t* d_planes[2] = {nullptr, nullptr};   // [batch][plane_bytes], per lane
     std::vector<uint8_t> h_meta[2];              // pinned-free host staging of descriptors + quant tables (copied with the batch)
@@ -268,13 +270,14 @@ __global__ void __launch_bounds__(kEntropyThreads) jpeg_entropy_flat_kernel(Nati
 // one per sub-sequence, which is the sequential decoding at the old cost), block-wide prefix sums of the block counts and DC sums,
 // one writing pass.  A 1080p picture: ~1 000 threads x ~100 symbols per round instead of one thread x 275 000 symbols.
 constexpr int kParThreads = 1024;
+template <bool SPARSE>
 __global__ void __launch_bounds__(kParThreads) jpeg_entropy_parallel_kernel(NativeLayout L, const uint8_t* __restrict__ stage,
                                                                             const esd_mjpeg::NativeDesc* __restrict__ desc,
-                                                                            int16_t* __restrict__ coef) {
+                                                                            int16_t* __restrict__ coef, uint32_t* __restrict__ bstart) {
     __shared__ esdjpeg::ScanTables T;
     __shared__ uint8_t s_nat[64];
     __shared__ esdjpeg::SpanState s_end[kParThreads];
-    __shared__ int s_warp[4][kParThreads / 32];
+    __shared__ int s_warp[5][kParThreads / 32];
     __shared__ int s_bad;
     const int tid = threadIdx.x, f = blockIdx.x;
     const esd_mjpeg::NativeDesc d = desc[f];
@@ -299,7 +302,7 @@ __global__ void __launch_bounds__(kParThreads) jpeg_entropy_parallel_kernel(Nati
     esdjpeg::SpanState in{(uint32_t)tid * S, 0, 0};
     esdjpeg::SpanResult res;
     res.end = in; res.n_blocks = 0; res.dc[0] = res.dc[1] = res.dc[2] = 0;
-    if (active) res = esdjpeg::decode_span<false>(words, nwords, T, td, ta, s_nat, in, limit, nullptr, 0, nullptr, total_blocks);
+    if (active) res = esdjpeg::decode_span<esdjpeg::SPAN_COUNT>(words, nwords, T, td, ta, s_nat, in, limit, nullptr, 0, nullptr, total_blocks);
     for (;;) {
         s_end[tid] = res.end;
         __syncthreads();
@@ -309,13 +312,13 @@ __global__ void __launch_bounds__(kParThreads) jpeg_entropy_parallel_kernel(Nati
             if (!esdjpeg::same_state(nin, in)) { in = nin; changed = true; }
         }
         if (!__syncthreads_or(changed ? 1 : 0)) break;   // also: every read of s_end is done before the next round's writes
-        if (changed) res = esdjpeg::decode_span<false>(words, nwords, T, td, ta, s_nat, in, limit, nullptr, 0, nullptr, total_blocks);
+        if (changed) res = esdjpeg::decode_span<esdjpeg::SPAN_COUNT>(words, nwords, T, td, ta, s_nat, in, limit, nullptr, 0, nullptr, total_blocks);
     }
     // exclusive prefix sums over the threads: blocks completed and DC sums per component before this sub-sequence
-    int v[4] = {active ? res.n_blocks : 0, active ? res.dc[0] : 0, active ? res.dc[1] : 0, active ? res.dc[2] : 0};
-    int incl[4];
+    int v[5] = {active ? res.n_blocks : 0, active ? res.dc[0] : 0, active ? res.dc[1] : 0, active ? res.dc[2] : 0, active ? res.n_coefs : 0};
+    int incl[5];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < 5; ++q) {
         int x = v[q];
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -326,15 +329,78 @@ __global__ void __launch_bounds__(kParThreads) jpeg_entropy_parallel_kernel(Nati
         if ((tid & 31) == 31) s_warp[q][tid >> 5] = x;
     }
     __syncthreads();
-    int base[4] = {0, 0, 0, 0};
+    int base[5] = {0, 0, 0, 0, 0};
     for (int w = 0; w < (tid >> 5); ++w) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) base[q] += s_warp[q][w];
+        for (int q = 0; q < 5; ++q) base[q] += s_warp[q][w];
     }
     if (!active) return;
     const int blk0 = base[0] + incl[0] - v[0];
     const int pred[3] = {base[1] + incl[1] - v[1], base[2] + incl[2] - v[2], base[3] + incl[3] - v[3]};
-    esdjpeg::decode_span<true>(words, nwords, T, td, ta, s_nat, in, limit, coef + (size_t)f * L.blocks_per_frame * 64, blk0, pred, total_blocks);
+    int16_t* mine = coef + (size_t)f * L.blocks_per_frame * 64;
+    if (SPARSE)   // entry list in the picture's slice of the coefficient scratch (32 entries per block + the spare block as the sink)
+        esdjpeg::decode_span<esdjpeg::SPAN_SPARSE>(words, nwords, T, td, ta, s_nat, in, limit, mine, blk0, pred, total_blocks,
+                                                   bstart + (size_t)f * (L.blocks_per_frame + 1), base[4] + incl[4] - v[4], total_blocks * 32);
+    else
+        esdjpeg::decode_span<esdjpeg::SPAN_DENSE>(words, nwords, T, td, ta, s_nat, in, limit, mine, blk0, pred, total_blocks);
+}
+
+// IDCT from the sparse hand-off: a thread expands its block's entries into a column of a shared-memory tile ([64 positions][128
+// threads] int16: a warp's accesses to one position fall into 16 distinct words, conflict-free whatever the positions), then
+// runs the same ISLOW arithmetic.  Blocks with at most their DC entry take the short cut.
+__global__ void __launch_bounds__(128) jpeg_idct_sparse_kernel(NativeLayout L, const int16_t* __restrict__ coef, const uint32_t* __restrict__ bstart,
+                                                               const uint16_t* __restrict__ quant, uint8_t* __restrict__ planes) {
+    __shared__ int16_t tile[64][128];
+    const int blk = blockIdx.x * blockDim.x + threadIdx.x;
+    const int f = blockIdx.y;
+    const int total_blocks = L.blocks_per_frame - 1;
+    const bool live = blk < total_blocks;
+    int comp = 0, bx = 0, by = 0;
+    if (live) esdjpeg::block_position(blk, L.mcus_x, &comp, &bx, &by);
+    const int bw = comp == 0 ? 2 * L.mcus_x : L.mcus_x;
+    const int stride = bw * 8;
+    const size_t ysz = (size_t)(2 * L.mcus_x * 8) * (L.mcus_y * 16), csz = (size_t)(L.mcus_x * 8) * (L.mcus_y * 8);
+    uint8_t* plane = planes + (size_t)f * L.plane_bytes + (comp == 0 ? 0 : (comp == 1 ? ysz : ysz + csz));
+    uint8_t* out = plane + (size_t)(by * 8) * stride + bx * 8;
+    const uint32_t* list = reinterpret_cast<const uint32_t*>(coef + (size_t)f * L.blocks_per_frame * 64);
+    const uint32_t* bs = bstart + (size_t)f * (L.blocks_per_frame + 1);
+    const uint32_t cap = (uint32_t)total_blocks * 32u;
+    uint32_t st = 0, en = 0;
+    if (live) {
+        st = bs[blk]; en = bs[blk + 1];
+        if (en > cap) en = cap;
+        if (st > en) st = en;
+        if (en - st > 64u) en = st + 64u;
+    }
+    const uint16_t* q = quant + ((size_t)f * 3 + comp) * 64;
+    if (live && en - st <= 1u) {
+        // DC only (or an empty block): both passes of the ISLOW IDCT reduce to (4 * dc * q0 + 16) >> 5 for every sample
+        const int dc = en > st ? (int)(int16_t)(list[st] & 0xffffu) : 0;
+        const int32_t v = esdjpeg::descale((dc * (int32_t)q[0]) << 2, 5);
+        const uint32_t w4 = (uint32_t)esdjpeg::range_limit(v) * 0x01010101u;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) *reinterpret_cast<uint2*>(out + (size_t)r * stride) = make_uint2(w4, w4);
+    }
+    const bool full = live && en - st > 1u;
+    if (!__syncthreads_or(full ? 1 : 0)) return;   // nobody in this CTA needs the tile
+    if (full) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) tile[i][threadIdx.x] = 0;
+        for (uint32_t e = st; e < en; ++e) {
+            const uint32_t w = list[e];
+            tile[(w >> 16) & 63u][threadIdx.x] = (int16_t)(w & 0xffffu);
+        }
+        int16_t c[64];
+#pragma unroll
+        for (int i = 0; i < 64; ++i) c[i] = tile[i][threadIdx.x];
+        uint16_t ql[64];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) reinterpret_cast<uint4*>(ql)[i] = reinterpret_cast<const uint4*>(q)[i];
+        union { uint2 v[8]; uint8_t b[64]; } o;
+        esdjpeg::idct_islow(c, ql, o.b, 8);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) *reinterpret_cast<uint2*>(out + (size_t)r * stride) = o.v[r];
+    }
 }
 
 // The kernel also RESTORES THE ZEROS: the entropy stage writes only non-zero coefficients into a buffer that must be clear, and
@@ -504,7 +570,7 @@ void esd_mjpeg_close(esd_mjpeg* h) {
     for (int b = 0; b < 2; ++b) {
         if (h->lane[b]) { cudaStreamSynchronize(h->lane[b]); cudaStreamDestroy(h->lane[b]); }
         if (h->consumed[b]) cudaEventDestroy(h->consumed[b]);
-        esdguard::gfree(h->d_comp[b]); esdguard::gfree(h->d_coef[b]); esdguard::gfree(h->d_planes[b]);
+        esdguard::gfree(h->d_comp[b]); esdguard::gfree(h->d_coef[b]); esdguard::gfree(h->d_planes[b]); esdguard::gfree(h->d_bstart[b]);
     }
     if (h->state) nvjpegJpegStateDestroy(h->state);
     if (h->nj) nvjpegDestroy(h->nj);
@@ -571,6 +637,8 @@ int esd_mjpeg_open(esd_mjpeg** out, const char* path, int device, int32_t batch_
             for (int b = 0; b < h->lanes && e == cudaSuccess; ++b) {
                 e = esdguard::gmalloc(&h->d_coef[b], (size_t)h->batch * h->blocks_per_frame * 64 * sizeof(int16_t));
                 if (e == cudaSuccess) e = esdguard::gmalloc(&h->d_planes[b], (size_t)h->batch * h->plane_bytes);
+                if (e == cudaSuccess) e = esdguard::gmalloc(&h->d_bstart[b], (size_t)h->batch * (h->blocks_per_frame + 1) * sizeof(uint32_t));
+                if (e == cudaSuccess) e = cudaMemset(h->d_bstart[b], 0, (size_t)h->batch * (h->blocks_per_frame + 1) * sizeof(uint32_t));
                 if (e == cudaSuccess && h->lanes > 1) e = cudaStreamCreateWithFlags(&h->lane[b], cudaStreamNonBlocking);
                 if (e == cudaSuccess && h->lanes > 1) e = cudaEventCreateWithFlags(&h->consumed[b], cudaEventDisableTiming);
             }
@@ -798,8 +866,14 @@ int esd_mjpeg_read(esd_mjpeg* h, int64_t max_frames, void* stream, uint8_t** d_b
             cudaEventRecord(h->tev[b][0], ds);
         }
         cudaError_t e = cudaMemcpyAsync(h->d_comp[ln], h->h_stage[b], total, cudaMemcpyHostToDevice, ds);
-        // the coefficient scratch is cleared once; after that the IDCT kernel leaves it clean (a batch that failed half-way clears again)
-        if (e == cudaSuccess && h->coef_dirty[ln]) e = cudaMemsetAsync(h->d_coef[ln], 0, (size_t)h->batch * h->blocks_per_frame * 64 * sizeof(int16_t), ds);
+        // Sparse hand-off (entry list + block offsets in place of the cleared dense array) whenever every scan of the batch fits the
+        // list: a symbol that carries a coefficient is at least one bit long, so a scan of at most 32 x blocks bits cannot overflow
+        // 32 entries per block.  Larger pictures (> 196 KB of scan at 1080p) keep the dense hand-off.
+        bool sparse = h->flat && h->parallel_entropy && h->sparse_handoff && h->d_bstart[ln] != nullptr;
+        for (int64_t i = 0; i < n && sparse; ++i) sparse = (uint64_t)hdesc[i].len * 32u <= (uint64_t)(h->blocks_per_frame - 1) * 32u;
+        // dense: the coefficient scratch is cleared once; after that the IDCT kernel leaves it clean (a batch that failed half-way, or
+        // a sparse batch, which keeps its list there, clears again)
+        if (e == cudaSuccess && !sparse && h->coef_dirty[ln]) e = cudaMemsetAsync(h->d_coef[ln], 0, (size_t)h->batch * h->blocks_per_frame * 64 * sizeof(int16_t), ds);
         h->coef_dirty[ln] = true;
         if (e != cudaSuccess) return fail(h, ESD_DEC_ERR_CUDA, "native decode: staging copy failed: %s", cudaGetErrorString(e));
         const esd_mjpeg::NativeDesc* ddesc = reinterpret_cast<const esd_mjpeg::NativeDesc*>(h->d_comp[ln]);
@@ -807,16 +881,18 @@ int esd_mjpeg_read(esd_mjpeg* h, int64_t max_frames, void* stream, uint8_t** d_b
         const unsigned egrid = (unsigned)((n + kEntropyThreads - 1) / kEntropyThreads);
         const size_t esmem = kEntropyThreads * sizeof(esdjpeg::ScanTables);
         if (h->timing) cudaEventRecord(h->tev[b][1], ds);
-        if (h->flat && h->parallel_entropy) jpeg_entropy_parallel_kernel<<<(unsigned)n, kParThreads, 0, ds>>>(L, h->d_comp[ln], ddesc, h->d_coef[ln]);
+        if (sparse) jpeg_entropy_parallel_kernel<true><<<(unsigned)n, kParThreads, 0, ds>>>(L, h->d_comp[ln], ddesc, h->d_coef[ln], h->d_bstart[ln]);
+        else if (h->flat && h->parallel_entropy) jpeg_entropy_parallel_kernel<false><<<(unsigned)n, kParThreads, 0, ds>>>(L, h->d_comp[ln], ddesc, h->d_coef[ln], nullptr);
         else if (h->flat) jpeg_entropy_flat_kernel<<<egrid, kEntropyThreads, esmem, ds>>>(L, h->d_comp[ln], ddesc, h->d_coef[ln]);
         else jpeg_entropy_kernel<<<egrid, kEntropyThreads, esmem, ds>>>(L, h->d_comp[ln], ddesc, h->d_coef[ln]);
         if (h->timing) cudaEventRecord(h->tev[b][2], ds);
-        jpeg_idct_kernel<<<dim3((unsigned)((h->blocks_per_frame + 127) / 128), (unsigned)n), 128, 0, ds>>>(L, h->d_coef[ln], dquant, h->d_planes[ln]);
+        if (sparse) jpeg_idct_sparse_kernel<<<dim3((unsigned)((h->blocks_per_frame + 127) / 128), (unsigned)n), 128, 0, ds>>>(L, h->d_coef[ln], h->d_bstart[ln], dquant, h->d_planes[ln]);
+        else jpeg_idct_kernel<<<dim3((unsigned)((h->blocks_per_frame + 127) / 128), (unsigned)n), 128, 0, ds>>>(L, h->d_coef[ln], dquant, h->d_planes[ln]);
         jpeg_color_kernel<<<dim3((unsigned)(((h->width + 3) / 4 + 255) / 256), (unsigned)((h->height + 1) / 2), (unsigned)n), 256, 0, ds>>>(L, h->d_planes[ln], h->d_out[b]);
         if (h->timing) { cudaEventRecord(h->tev[b][3], ds); h->tev_armed[b] = true; }
         e = cudaGetLastError();
         if (e != cudaSuccess) return fail(h, ESD_DEC_ERR_CUDA, "native decode kernels: %s", cudaGetErrorString(e));
-        h->coef_dirty[ln] = false;   // entropy + IDCT are enqueued: the IDCT restores the zeros
+        h->coef_dirty[ln] = sparse;   // dense: entropy + IDCT are enqueued and the IDCT restores the zeros; sparse: the list stays
     } else {
         if (h->initialized_batch != (int)n) {  // the batched API wants exactly the initialised number of pictures (tail of the stream)
             nvjpegStatus_t js = nvjpegDecodeBatchedInitialize(h->nj, h->state, (int)n, 1, NVJPEG_OUTPUT_BGRI);

@@ -33,6 +33,21 @@ int shim_jpeg_decode(const uint8_t* data, long n, uint8_t* out, char* err, int f
         if (!clean || g.restart_interval) { strncpy(err, "restart markers: not for the flat decoder", 255); return -2; }
         const size_t nblocks = (size_t)6 * g.mcus_x * g.mcus_y;
         std::vector<int16_t> coef((nblocks + 1) * 64, 0);  // + the spare block
+        // the library's rule: a list of 32 entries per block holds any picture whose scan has at most that many BITS (a symbol that
+        // carries a coefficient is at least one bit long); larger scans keep the dense hand-off
+        if (flat < 0 && clean_words.size() * 32 > nblocks * 32) flat = -flat;
+        if (flat < 0) {    // the same scheme with the SPARSE hand-off (entry list + block offsets), expanded block by block: thread budget = -flat
+            const int cap = (int)nblocks * 32;
+            std::vector<uint32_t> list((size_t)cap + 1, 0xdeadbeefu), bstart(nblocks + 2, 0xffffffffu);
+            g_last_rounds = decode_scan_parallel_host(clean_words.data(), (int)clean_words.size(), h.huff, h.td, h.ta, kNaturalOrderHost,
+                                                      g.mcus_x * g.mcus_y, reinterpret_cast<int16_t*>(list.data()), -flat, bstart.data(), cap);
+            std::vector<int16_t> ref((nblocks + 1) * 64, 0);
+            decode_scan_flat(clean_words.data(), (int)clean_words.size(), h.huff, h.td, h.ta, kNaturalOrderHost, g.mcus_x * g.mcus_y, ref.data());
+            for (size_t b = 0; b < nblocks; ++b) {
+                expand_block(list.data(), bstart.data(), (int)b, cap, &coef[b * 64]);
+                if (memcmp(&ref[b * 64], &coef[b * 64], 128) != 0) { snprintf(err, 255, "sparse hand-off differs from the flat loop at block %zu", b); return -4; }
+            }
+        } else
         if (flat >= 2) {   // the many-threads-per-picture scheme (host statement), flat = the thread budget; coefficients must equal the flat loop's
             g_last_rounds = decode_scan_parallel_host(clean_words.data(), (int)clean_words.size(), h.huff, h.td, h.ta, kNaturalOrderHost,
                                                       g.mcus_x * g.mcus_y, coef.data(), flat);

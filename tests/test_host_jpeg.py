@@ -89,6 +89,9 @@ def test_many_threads_per_picture_reach_the_sequential_decoding(shim, quality):
                 got = decode(shim, jpg.tobytes(), flat=budget)
                 assert got is not None and np.array_equal(got, want), (name, quality, extra, budget)
                 worst = max(worst, shim.shim_last_rounds())
+                # and with the sparse hand-off to the IDCT (entry list + block offsets instead of the cleared dense array)
+                got = decode(shim, jpg.tobytes(), flat=-budget)
+                assert got is not None and np.array_equal(got, want), (name, quality, extra, budget, "sparse")
     # correct states spread at least one sub-sequence per round; in practice a handful of rounds, far below the thread count
     assert 1 <= worst <= 24, worst
 
