@@ -196,7 +196,9 @@ class CaptureRangeVideo:
     frames_stable = False
 
     def __init__(self, path: str, first_frame: int = 0, end_frame: Optional[int] = None, batch_frames: int = 64, watch=(),
-                 threads: int = 0, prefetch: bool = True):
+                 threads: int = 0, prefetch: bool = True, until_eof: bool = False):
+        """until_eof: ignore the container's frame count and read until the decoder stops (whole-file sources: some containers
+        under-report CAP_PROP_FRAME_COUNT)."""
         import queue
         import threading
 
@@ -217,7 +219,7 @@ class CaptureRangeVideo:
         self.frame_size = (int(self._cap.get(cv2.CAP_PROP_FRAME_WIDTH)), int(self._cap.get(cv2.CAP_PROP_FRAME_HEIGHT)))
         self.frame_rate = float(self._cap.get(cv2.CAP_PROP_FPS) or 30.0)
         self.start_frame = int(first_frame)
-        self._end = self.n_frames if end_frame is None else min(int(end_frame), self.n_frames)
+        self._end = (1 << 62) if until_eof else (self.n_frames if end_frame is None else min(int(end_frame), self.n_frames))
         self._pos = self.start_frame
         if self.start_frame:
             self._cap.set(cv2.CAP_PROP_POS_FRAMES, self.start_frame)

@@ -385,11 +385,9 @@ def _default_decoder(video_path: str, config: dict):
 
     # frames are decoded straight into reused batch buffers by a thread of the source's own (no per-batch np.stack, decode
     # overlapped with the push): 295 -> ~680 frames/s on a 1080p MPEG-4 file, the rate of cv2's decode itself
-    src = decode.CaptureRangeVideo(video_path, 0, None, batch_frames=int(config.get("decode_batch", 64)))
+    src = decode.CaptureRangeVideo(video_path, 0, None, batch_frames=int(config.get("decode_batch", 64)), until_eof=True)
     if "fps" in config and not src.frame_rate:
         src.frame_rate = float(config["fps"])
-    # some containers under-report CAP_PROP_FRAME_COUNT: a whole-file source reads until the decoder says stop
-    src._end = 1 << 62
     return src
 
 
