@@ -9,9 +9,11 @@
  *
  * What this image offers: NVDEC is closed to the container (libnvcuvid loads, but cuvidGetDecoderCaps answers
  * CUDA_ERROR_NO_DEVICE for every codec because NVIDIA_DRIVER_CAPABILITIES is "compute,utility" -- profiles/r02_nvdec_caps.log),
- * so the decoder is nvJPEG (CUDA toolkit, header + library present) on Motion-JPEG in an AVI (RIFF) container: the hardware
- * JPEG engine when the library grants it, else the GPU-Huffman hybrid, else the default backend.  MJPEG is intra-only, so any
- * frame range can be decoded independently -- the frame-range sharding of eioku_b200.multi applies unchanged.
+ * so the codec is Motion-JPEG in an AVI (RIFF) container, decoded with CUDA kernels alone: the library's own baseline-JPEG decoder
+ * (NATIVE: a block of threads per picture for the entropy stage, libjpeg's exact IDCT / upsampling / colour arithmetic) for what
+ * ffmpeg and OpenCV write, nvJPEG (CUDA toolkit) for the other JPEG flavours -- its hardware engine when a box grants it, else the
+ * GPU-Huffman hybrid, else the default back end.  MJPEG is intra-only, so any frame range can be decoded independently -- the
+ * frame-range sharding of eioku_b200.multi applies unchanged.
  *
  * Output: dense uint8 BGR24 frames [n][height][width * 3] in a library-owned device buffer (double-buffered), exactly the
  * layout esd_push_frames takes.  The NATIVE back end reproduces libjpeg's default arithmetic, so its pictures are bit-identical to
