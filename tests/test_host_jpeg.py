@@ -136,3 +136,25 @@ def test_unsupported_streams_are_rejected_not_misdecoded(shim):
         decode(shim, jpg.tobytes())
     with pytest.raises(ValueError):
         decode(shim, b"\xff\xd8\xff\xd9")
+
+
+def test_damaged_scans_never_leave_their_buffers(tmp_path):
+    """tests/jpeg_fuzz.cpp under AddressSanitizer + UBSan: the decoding code the device runs (flat loop, decode_span in its three
+    modes, expand_block), fed with bit-flipped / overwritten / truncated / random scans behind a real picture's tables, in buffers
+    of exactly the library's sizes.  Out-of-bounds reads are what neither the parity tests nor the red-zone allocator can see."""
+    exe = str(tmp_path / "jpeg_fuzz")
+    build = subprocess.run(["g++", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=all", "-o", exe,
+                            os.path.join(ROOT, "tests", "jpeg_fuzz.cpp")], capture_output=True, text=True)
+    if build.returncode != 0 and "sanitize" in build.stderr:
+        pytest.skip("this toolchain has no AddressSanitizer runtime")
+    assert build.returncode == 0, build.stderr[-2000:]
+    rng = np.random.default_rng(3)
+    smooth = cv2.resize(rng.integers(0, 256, (9, 16, 3), dtype=np.uint8), (320, 184), interpolation=cv2.INTER_CUBIC)
+    pics = {"smooth_q80_opt": (np.clip(smooth.astype(int) + rng.integers(-10, 11, smooth.shape), 0, 255).astype(np.uint8), 80, [cv2.IMWRITE_JPEG_OPTIMIZE, 1]),
+            "noise_q100": (rng.integers(0, 256, (72, 96, 3), dtype=np.uint8), 100, []),
+            "flat_q30": (np.full((40, 40, 3), (255, 0, 255), np.uint8), 30, [])}
+    for k, (name, (img, q, extra)) in enumerate(pics.items()):
+        p = str(tmp_path / f"{name}.jpg")
+        assert cv2.imwrite(p, img, [cv2.IMWRITE_JPEG_QUALITY, q, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420] + extra)
+        run = subprocess.run([exe, p, str(11 + k), "400"], capture_output=True, text=True, timeout=600)
+        assert run.returncode == 0 and "fuzz ok: 400 damaged scans" in run.stdout, (name, run.stdout[-300:], run.stderr[-3000:])
