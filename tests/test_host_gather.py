@@ -118,3 +118,20 @@ def test_i420_tap_gather_equals_nv12_gather_of_the_interleaved_frame(shim, w, h,
     ny = len(yrows)
     assert np.array_equal(out[0][:, :ny, :2 * dw], out[1][:, :ny, :2 * dw])
     assert np.array_equal(out[0][:, ny:], out[1][:, ny:])
+
+
+def test_gather_loops_stay_inside_exact_size_buffers_under_asan(tmp_path):
+    """tests/gather_asan.cpp: every gather variant (BGR24 one row / eight rows in lock-step, NV12, I420; plain and non-temporal
+    stores) over dense frames and ring slots of exactly the advertised sizes, under AddressSanitizer + UBSan -- a read past the
+    last row of a caller's frame would be a host crash in production and is invisible to the layout tests above."""
+    import subprocess
+
+    exe = str(tmp_path / "gather_asan")
+    src = os.path.join(os.path.dirname(os.path.abspath(__file__)), "gather_asan.cpp")
+    build = subprocess.run(["g++", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=all", "-o", exe, src],
+                           capture_output=True, text=True)
+    if build.returncode != 0 and "sanitize" in build.stderr:
+        pytest.skip("this toolchain has no AddressSanitizer runtime")
+    assert build.returncode == 0, build.stderr[-2000:]
+    run = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert run.returncode == 0 and "gather asan ok: 60 runs" in run.stdout, (run.stdout[-300:], run.stderr[-3000:])
