@@ -196,9 +196,11 @@ class CaptureRangeVideo:
     frames_stable = False
 
     def __init__(self, path: str, first_frame: int = 0, end_frame: Optional[int] = None, batch_frames: int = 64, watch=(),
-                 threads: int = 0, prefetch: bool = True, until_eof: bool = False):
+                 threads: int = 0, prefetch: bool = True, until_eof: bool = False, frame_count: Optional[int] = None):
         """until_eof: ignore the container's frame count and read until the decoder stops (whole-file sources: some containers
-        under-report CAP_PROP_FRAME_COUNT)."""
+        under-report CAP_PROP_FRAME_COUNT).  frame_count: the frame count the caller works with instead of the capture's own claim
+        (all ranges of one job must agree on it).  A range that ends at that count tries to grab one more frame when it gets
+        there and reports it in `trailing_frames` -- a container that under-reports its length must not lose its tail silently."""
         import queue
         import threading
 
@@ -215,7 +217,9 @@ class CaptureRangeVideo:
             self._cap = cv2.VideoCapture(path)
         if not self._cap.isOpened():
             raise RuntimeError(f"Failed to open video: {path}")
-        self.n_frames = int(self._cap.get(cv2.CAP_PROP_FRAME_COUNT))
+        self.n_frames = int(self._cap.get(cv2.CAP_PROP_FRAME_COUNT)) if frame_count is None else int(frame_count)
+        self.trailing_frames = None   # set once the claimed end of the file is reached: did the decoder have more?
+        self._until_eof = bool(until_eof)
         self.frame_size = (int(self._cap.get(cv2.CAP_PROP_FRAME_WIDTH)), int(self._cap.get(cv2.CAP_PROP_FRAME_HEIGHT)))
         self.frame_rate = float(self._cap.get(cv2.CAP_PROP_FPS) or 30.0)
         self.start_frame = int(first_frame)
@@ -250,6 +254,8 @@ class CaptureRangeVideo:
 
     def _decode_into(self, buf) -> int:
         k = min(self._batch, self._end - self._pos)
+        if k <= 0 and not self._until_eof and self._end >= self.n_frames and self.trailing_frames is None:
+            self.trailing_frames = bool(self._cap.grab())
         got = 0
         for i in range(max(0, k)):
             ok, frame = self._cap.read(buf[i])

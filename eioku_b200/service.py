@@ -294,7 +294,7 @@ def _detect_scenes_capture_sharded(video_path: str, config: dict, device: int, w
     sources = {}
 
     def make(sh, dev):
-        src = decode.CaptureRangeVideo(video_path, sh.load_start, sh.load_end, batch, watch=starts, threads=threads)
+        src = decode.CaptureRangeVideo(video_path, sh.load_start, sh.load_end, batch, watch=starts, threads=threads, frame_count=n)
         sources[sh.rank] = src
         return src
 
@@ -315,6 +315,11 @@ def _detect_scenes_capture_sharded(video_path: str, config: dict, device: int, w
             logger.warning("segment-parallel decode of %s: frame %d differs between two captures (inexact seek); decoding sequentially",
                            video_path, sh.load_start)
             return None
+    # ... and the file must end where the container said it does: a capture that still had frames behind the claimed count means
+    # the sequential decode (which reads until the decoder stops) would see a longer video
+    if any(src.trailing_frames for src in sources.values()):
+        logger.warning("segment-parallel decode of %s: the container under-reports its length; decoding sequentially", video_path)
+        return None
     if res.n_frames == 0:
         return {"scenes": []}
     return {"scenes": scenes_to_dicts(res.scene_list(start_in_scene=True), rate)}

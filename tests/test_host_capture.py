@@ -102,3 +102,18 @@ def test_which_files_get_several_captures(clip, tmp_path, monkeypatch):
     assert service.default_decode_workers(100000) == 1
     monkeypatch.setattr("os.sched_getaffinity", lambda pid: set(range(64)), raising=False)
     assert service.default_decode_workers(100000) == 8
+
+
+def test_a_container_that_under_reports_its_length_is_noticed(clip):
+    """The range that ends at the (claimed) end of the file tries one more frame: `trailing_frames` is what sends the service
+    back to the sequential decode instead of silently dropping the tail."""
+    path, seq = clip
+    n = seq.shape[0]
+    with decode.CaptureRangeVideo(path, n - 20, None, batch_frames=8) as v:
+        assert _read_all(v).shape[0] == 20 and v.trailing_frames is False
+    with decode.CaptureRangeVideo(path, n - 30, None, batch_frames=8, frame_count=n - 6) as v:   # "the container says n - 6"
+        assert _read_all(v).shape[0] == 24 and v.trailing_frames is True
+    with decode.CaptureRangeVideo(path, 0, 40, batch_frames=8) as v:   # a range in the middle never probes the end
+        assert _read_all(v).shape[0] == 40 and v.trailing_frames is None
+    with decode.CaptureRangeVideo(path, 0, None, batch_frames=16, until_eof=True, frame_count=10) as v:   # whole-file sources ignore the claim
+        assert _read_all(v).shape[0] == n and v.trailing_frames is None
